@@ -1,0 +1,212 @@
+/*
+ * svgr_b200.h -- C ABI of the svgrasterize B200 core (libsvgr_b200.so).
+ *
+ * The reference (aslpavel/svgrasterize.py) has no FFI: its rasterizer is Python + numpy
+ * called from Scene.render (svgrasterize.py:649-752) and main() (:3854-3881).  This
+ * header is the boundary a maintainer binds with ctypes to replace that hot path:
+ *
+ *   reference call                                           replaced by
+ *   -------------------------------------------------------  -----------------------------
+ *   Path.mask / bezier3_flatten_batch (:922, :2091)          svgr_render(.., SVGR_STOP_FLATTEN) + svgr_read_edges / svgr_read_boxes
+ *   line_signed_coverage + cumsum + fill rule (:2213, :983)  svgr_render(.., SVGR_STOP_COVERAGE) + svgr_read_mask / svgr_read_bins
+ *   Path.stroke (:1105)                                      svgr_render(.., SVGR_STOP_STROKE) + svgr_read_outline
+ *   Path.fill, Layer.compose/convert/opacity, canvas_* ,
+ *   Filter.__call__, Layer.convolve/morphology/color_matrix,
+ *   Scene.render (:995, :178, :277-416, :1801, :95-127, :649) svgr_render + svgr_node_info / svgr_read_node
+ *   canvas_merge_at + write_png quantisation (:3870-3881,:263) svgr_render canvas nodes -> RGBA8
+ *   ConvexHull.bbox (:2002)                                  svgr_cloud_bounds
+ *   arc_to_bezier3 (:2355)  [host, libm]                     svgr_arc_to_cubics
+ *
+ * Conventions: every function returns 0 on success, a negative SVGR_E_* code on
+ * failure (svgr_last_error gives the text).  Nothing throws.  No torch types: plain
+ * pointers, sizes and a cudaStream_t passed as void*.  All `program` arrays are HOST
+ * pointers; svgr_render copies them to the device itself (the copies are part of an
+ * end-to-end timing).  A context is bound to one device and is not thread-safe.
+ */
+#ifndef SVGR_B200_H
+#define SVGR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVGR_VERSION 100
+
+enum {
+    SVGR_OK = 0,
+    SVGR_E_INVALID = -1,  /* bad argument / malformed program: Python raises ValueError */
+    SVGR_E_CUDA = -2,     /* CUDA runtime error: Python raises RuntimeError */
+    SVGR_E_NOMEM = -3,
+    SVGR_E_UNSUPPORTED = -4,
+    SVGR_E_STROKE = -5, /* degenerate control polygon: the reference raises TypeError here (:2157) */
+};
+
+/* where svgr_render stops (taps for the stage-level parity tests and the eager API) */
+enum {
+    SVGR_STOP_NONE = 0,     /* full pipeline */
+    SVGR_STOP_STROKE = 1,   /* stroke outlines only */
+    SVGR_STOP_FLATTEN = 2,  /* + flatten, bounds */
+    SVGR_STOP_COVERAGE = 3, /* + binning, coverage masks */
+    SVGR_STOP_PLAN = 4,     /* flatten, bounds and the host plan only (node boxes; no pixels) */
+};
+
+/* scene-program node tags (the host encoder lowers the reference's Scene tree to these) */
+enum {
+    SVGR_N_EMPTY = 0,     /* renders nothing (reference returns None) */
+    SVGR_N_LEAF = 1,      /* a = path, b = paint (-1: mask only), c = paint linear_rgb flag, d = pattern `pat` node or -1 */
+    SVGR_N_GROUP = 2,     /* children over-composed (Layer.compose OVER); flags bit0 = linear_rgb */
+    SVGR_N_OPACITY = 3,   /* child 0 x f[0]; flags bit0 = linear_rgb */
+    SVGR_N_IN = 4,        /* compose([child0 (stencil), child1 (image)], IN); flags bit0 = linear_rgb */
+    SVGR_N_LUMA = 5,      /* luminance x alpha of child 0 as one channel; flags bit0 = linear_rgb */
+    SVGR_N_COMPOSE = 6,   /* Layer.compose(children, mode a, arithmetic k = f[0..3]); flags bit0 = linear_rgb */
+    SVGR_N_SRC_ALPHA = 7, /* (0,0,0,alpha) of child 0, premultiplied linear */
+    SVGR_N_CONVERT = 8,   /* Layer.convert(pre_alpha = a, linear_rgb = b) of child 0 */
+    SVGR_N_BLUR = 9,      /* Layer.convolve with kernel a of the kernel table */
+    SVGR_N_MORPH = 10,    /* Layer.morphology: window a x b, c = 1 max / 0 min */
+    SVGR_N_CMATRIX = 11,  /* Layer.color_matrix with matrix a */
+    SVGR_N_OFFSET = 12,   /* feOffset: f[0..1] = (dx, dy), a = index into the offset-transform table */
+    SVGR_N_MERGE_AT = 13, /* canvas_merge_at of child 0 onto zeros of bbox (a, b, c, d) */
+    SVGR_N_CANVAS = 14,   /* final canvas: a = rows, b = cols, flags bit0 = linear_rgb, f[0] = byte offset in the output */
+    SVGR_N_EXTERNAL = 15, /* a = index into the external layer table (host images handed in by the eager API) */
+};
+
+typedef struct svgr_node {
+    int32_t tag;
+    int32_t a, b, c, d;
+    int32_t child_off, child_cnt;
+    int32_t flags;
+    double f[4];
+} svgr_node;
+
+/* Gaussian kernel of one feGaussianBlur under one transform (blur_kernel, :1903-1944) */
+typedef struct svgr_kernel {
+    int32_t rows, cols;  /* kernel extent along image rows / columns */
+    int32_t separable;   /* 1: weights = row vector (rows) then column vector (cols); 0: rows x cols matrix */
+    int32_t weight_off;  /* offset into the weight table */
+} svgr_kernel;
+
+/* layer handed in from the host (eager Layer API) */
+typedef struct svgr_external {
+    const float *image; /* rows x cols x channels, float32, C-contiguous */
+    int32_t r0, c0, rows, cols;
+    int32_t channels; /* 1 or 4 */
+    int32_t pre_alpha, linear_rgb;
+    int32_t pad;
+} svgr_external;
+
+/* The records below are declared in svgr_types.h (same layout on host and device). */
+struct PathRec;
+struct StrokeRec;
+struct PaintRec;
+struct StopRec;
+
+typedef struct svgr_program {
+    /* fill geometry: arcs already expanded to cubics (svgr_arc_to_cubics) */
+    int64_t n_seg;
+    const uint8_t *seg_tag;   /* n_seg */
+    const double *seg_data;   /* n_seg x 8 */
+    const uint32_t *seg_path; /* n_seg */
+    /* one record per Path.mask call */
+    int32_t n_path;
+    const struct PathRec *paths;
+    /* stroke jobs: user-space source segments, outlines are produced on the device */
+    int32_t n_stroke;
+    const struct StrokeRec *strokes;
+    int32_t n_stroke_sub;
+    const int32_t *stroke_sub_off; /* n_stroke_sub + 1, into the stroke segments */
+    const int32_t *stroke_sub_job; /* n_stroke_sub */
+    int64_t n_stroke_seg;
+    const uint8_t *stroke_tag;
+    const double *stroke_data;
+    const int32_t *stroke_seg_job; /* n_stroke_seg */
+    /* paint */
+    int32_t n_paint;
+    const struct PaintRec *paints;
+    int32_t n_stop;
+    const struct StopRec *stops;
+    int32_t n_focal; /* number of two-circle gradient flags */
+    /* scene program, children before parents */
+    int32_t n_node;
+    const svgr_node *nodes;
+    int32_t n_child;
+    const int32_t *children;
+    /* filter tables */
+    int32_t n_kernel;
+    const svgr_kernel *kernels;
+    int32_t n_weight;
+    const float *weights;
+    int32_t n_matrix;
+    const float *matrices;   /* n_matrix x 20 (4x5 row-major) */
+    int32_t n_offset_tr;
+    const double *offset_tr; /* n_offset_tr x 12: forward 2x3 then inverse 2x3 */
+    /* external layers */
+    int32_t n_external;
+    const svgr_external *externals;
+    /* output */
+    int64_t canvas_bytes; /* total RGBA8 bytes written by the canvas nodes */
+} svgr_program;
+
+typedef struct svgr_stats {
+    int64_t n_edges;
+    int64_t n_outline_segs;
+    int64_t n_bands, n_cov_tiles, n_binned;
+    int64_t cov_floats, layer_floats; /* arena sizes */
+    int64_t n_ops, n_levels, n_launches;
+    int64_t mask_pixels, layer_pixels;
+    float ms_total, ms_h2d, ms_stroke, ms_flatten, ms_plan, ms_bin, ms_coverage, ms_compose, ms_canvas, ms_d2h;
+    int32_t retries;
+    int32_t pad;
+} svgr_stats;
+
+typedef struct svgr_ctx svgr_ctx;
+
+int svgr_version(void);
+/* sizeof of the ABI records, for binding self-checks: 0 PathRec, 1 StrokeRec, 2 PaintRec, 3 StopRec,
+ * 4 svgr_node, 5 svgr_kernel, 6 svgr_external, 7 svgr_program, 8 svgr_stats */
+int svgr_sizeof(int what);
+int svgr_create(int device, svgr_ctx **out);
+void svgr_destroy(svgr_ctx *ctx);
+const char *svgr_last_error(svgr_ctx *ctx);
+
+/* Render a program.  `out` receives canvas_bytes of RGBA8 (may be NULL when the program has no
+ * canvas nodes or the caller only wants taps); out_on_device != 0 means `out` is a device pointer.
+ * `stream` is a cudaStream_t (NULL = the context's own stream).  With timing != 0 the stage times
+ * in `stats` are measured with CUDA events (adds synchronisation). */
+int svgr_render(svgr_ctx *ctx, const svgr_program *prog, void *stream, int stop_after, uint8_t *out,
+                int out_on_device, int timing, svgr_stats *stats);
+
+/* Re-run the device part of the last svgr_render with the program already resident in HBM
+ * (no host->device copy of the program); used for kernel-only throughput measurements. */
+int svgr_render_resident(svgr_ctx *ctx, void *stream, uint8_t *out_device, int timing, svgr_stats *stats);
+
+/* ---- taps on the state left by the last svgr_render ------------------------------------- */
+int svgr_read_edges(svgr_ctx *ctx, double *edges, uint32_t *edge_path, int64_t cap, int64_t *n_edges);
+int svgr_read_boxes(svgr_ctx *ctx, int32_t *boxes /* n_path x 4 */, double *minmax /* n_path x 4 or NULL */);
+int svgr_read_mask(svgr_ctx *ctx, int32_t path, float *out /* rows x cols */);
+int svgr_read_bins(svgr_ctx *ctx, int32_t path, int32_t *band_off /* nbands + 1 */, uint32_t *bin_edges, int64_t cap,
+                   int64_t *n_binned);
+int svgr_read_outline(svgr_ctx *ctx, uint8_t *tag, double *data, uint32_t *path, int32_t *sub, int64_t cap,
+                      int64_t *n_segs);
+/* info[0] = kind (0 empty, 1 RGBA, 2 one channel), info[1..4] = r0, c0, rows, cols, info[5] = pre_alpha,
+ * info[6] = linear_rgb */
+int svgr_node_info(svgr_ctx *ctx, int32_t node, int32_t *info);
+int svgr_read_node(svgr_ctx *ctx, int32_t node, float *out /* rows x cols x channels */);
+
+/* ConvexHull.bbox(transform) for sets of paths of the last flattened program: query q covers the
+ * paths listed in q_paths[q_off[q] .. q_off[q+1]) and maps end points by q_inv[q] (2x3 inverse
+ * transform); out[q] = min x, min y, max x, max y in user space. */
+int svgr_cloud_bounds(svgr_ctx *ctx, int32_t n_query, const int32_t *q_off, const int32_t *q_paths,
+                      const double *q_inv, double *out);
+
+/* arc_to_bezier3 (svgrasterize.py:2355-2394) on the host with libm, bit-identical to the reference.
+ * Returns the number of cubics written (8 doubles each), or a negative code. */
+int64_t svgr_arc_to_cubics(double cx, double cy, double rx, double ry, double phi, double eta, double eta_delta,
+                           double *out, int64_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,1384 @@
+// engine.cu -- host side of libsvgr_b200.so: context, device buffers, the render
+// pipeline and the planner that turns a scene program + device-computed path
+// boxes into per-level op tables (the work Scene.render does node by node in the
+// reference, svgrasterize.py:649-752, done once per batch here).
+//
+// Pipeline of one svgr_render call (one stream, one host synchronisation):
+//   H2D program -> stroke (count/scan/emit/assemble) -> flatten + bounds
+//   -> D2H path boxes  [sync]  -> plan (host) -> H2D plan tables
+//   -> bin count / scan / fill -> coverage -> focal flags -> compose levels
+//   -> canvas quantise -> (D2H RGBA8)
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/svgr_b200.h"
+#include "svgr_kernels.h"
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(_e);                         \
+            return SVGR_E_CUDA;                                                                    \
+        }                                                                                          \
+    } while (0)
+
+#define FAIL(code, msg)    \
+    do {                   \
+        ctx->err = (msg);  \
+        return (code);     \
+    } while (0)
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes, bool keep = false)
+    {
+        if (bytes <= cap)
+            return cudaSuccess;
+        size_t ncap = bytes + bytes / 4 + 256;
+        void *np_ = nullptr;
+        cudaError_t e = cudaMalloc(&np_, ncap);
+        if (e != cudaSuccess)
+            return e;
+        if (keep && p && cap)
+            cudaMemcpy(np_, p, cap, cudaMemcpyDeviceToDevice);
+        if (p)
+            cudaFree(p);
+        p = np_, cap = ncap;
+        return cudaSuccess;
+    }
+    void release()
+    {
+        if (p)
+            cudaFree(p);
+        p = nullptr, cap = 0;
+    }
+    template <class T>
+    T *as() const
+    {
+        return (T *)p;
+    }
+};
+
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap)
+            return cudaSuccess;
+        size_t ncap = bytes + bytes / 4 + 256;
+        if (p)
+            cudaFreeHost(p);
+        p = nullptr, cap = 0;
+        cudaError_t e = cudaMallocHost(&p, ncap);
+        if (e == cudaSuccess)
+            cap = ncap;
+        return e;
+    }
+    void release()
+    {
+        if (p)
+            cudaFreeHost(p);
+        p = nullptr, cap = 0;
+    }
+};
+
+enum { VAL_EMPTY = 0 };  // otherwise SRC_L4 / SRC_L1 / SRC_COV / SRC_COVPAINT
+
+struct Val {
+    int kind = VAL_EMPTY;
+    int r0 = 0, c0 = 0, rows = 0, cols = 0;
+    int stride = 0;
+    int paint = -1;
+    float mul = 1.0f;
+    int pre = 1, lin = 1;
+    long long off = 0;
+    long long off2 = 0;
+    int stride2 = 0;
+    int level = 0;
+    bool one_channel() const { return kind == SRC_L1 || kind == SRC_COV; }
+};
+
+struct PlannedOp {
+    OpRec op;
+    int level;
+    int cls;  // 0 compose, 1 stencil, 2 conv2d, 3 canvas
+};
+
+struct Launch {
+    int cls;
+    int op_begin, op_count, n_tiles;
+    size_t smem;
+};
+
+struct StatusBlock {  // device -> host after flatten
+    unsigned long long n_edges;
+    int stroke_err;
+    int stroke_curves;   // total offset curves (pool use)
+    int outline_total;   // outline segments incl. padding
+    int outline_count;   // segments visible to flatten
+    int binned_total;
+    int pad;
+};
+
+}  // namespace
+
+struct svgr_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr;
+    std::string err;
+
+    // ---- resident program (device) + host copies of what the planner needs
+    bool have_program = false;
+    long long n_seg = 0;
+    int n_path = 0, n_stroke = 0, n_stroke_sub = 0, n_paint = 0, n_stop = 0, n_focal = 0, n_node = 0;
+    long long n_stroke_seg = 0;
+    long long canvas_bytes = 0;
+    DevBuf d_seg_tag, d_seg_data, d_seg_path, d_paths, d_strokes, d_ssub_off, d_ssub_job, d_stag, d_sdata, d_sseg_job;
+    DevBuf d_paints, d_stops, d_matrices, d_weights;
+    std::vector<PathRec> h_paths;
+    std::vector<PaintRec> h_paints;
+    std::vector<svgr_node> h_nodes;
+    std::vector<int32_t> h_children;
+    std::vector<svgr_kernel> h_kernels;
+    std::vector<double> h_offset_tr;
+    std::vector<svgr_external> h_ext;
+    std::vector<std::vector<float>> h_ext_data;
+    int n_weight = 0, n_matrix = 0;
+
+    // ---- stroke state
+    DevBuf d_scounts, d_soffs, d_scan_tmp, d_pool, d_sbound, d_sout_off, d_sout_total;
+    DevBuf d_otag, d_odata, d_opath, d_osub, d_ocount;
+    long long pool_cap = 0, outline_cap = 0;
+
+    // ---- flatten state
+    DevBuf d_edges, d_edge_path, d_minmax, d_boxes, d_minmax_f64, d_status;
+    long long edge_cap = 0;
+    long long n_edges = 0;
+    std::vector<PathBox> h_boxes;
+    PinBuf pin_boxes, pin_status, pin_plan, pin_out;
+
+    // ---- plan state
+    std::vector<MaskRec> h_masks;
+    std::vector<Val> vals;
+    std::vector<PlannedOp> ops;
+    std::vector<SrcRec> srcs;
+    std::vector<FocalJob> focal_jobs;
+    std::vector<Launch> launches;
+    int n_focal_blocks = 0;
+    long long n_bands = 0, n_cov_tiles = 0, cov_floats = 0, layer_floats = 0;
+    long long mask_pixels = 0, layer_pixels = 0;
+    int n_levels = 0;
+    DevBuf d_masks, d_band_cnt, d_band_off, d_band_cur, d_bin_edges, d_cov, d_layers, d_ops, d_srcs, d_focal_jobs,
+        d_focal_flags, d_canvas, d_q;
+    long long bin_cap = 0;
+    long long n_binned = 0;
+    bool planned = false, covered = false, composed = false;
+
+    cudaEvent_t ev[12] = {nullptr};
+};
+
+// ---------------------------------------------------------------------------------------------
+// planner
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline long long align4(long long v) { return (v + 3) & ~3ll; }
+
+struct Planner {
+    svgr_ctx *ctx;
+    std::string err;
+    long long layer_top = 0;
+
+    explicit Planner(svgr_ctx *c) : ctx(c) {}
+
+    Val alloc(int kind, int r0, int c0, int rows, int cols, int pre, int lin, int level)
+    {
+        Val v;
+        v.kind = kind, v.r0 = r0, v.c0 = c0, v.rows = rows, v.cols = cols, v.pre = pre, v.lin = lin, v.level = level;
+        layer_top = align4(layer_top);
+        v.off = layer_top;
+        if (kind == SRC_L4) {
+            v.stride = cols;
+            layer_top += 4ll * rows * cols;
+        } else {
+            v.stride = (int)align4(cols);
+            layer_top += (long long)rows * v.stride;
+        }
+        ctx->layer_pixels += (long long)rows * cols;
+        return v;
+    }
+
+    SrcRec src_of(const Val &v, int want_pre, int want_lin)
+    {
+        SrcRec s;
+        memset(&s, 0, sizeof s);
+        s.kind = v.kind;
+        s.r0 = v.r0, s.c0 = v.c0, s.rows = v.rows, s.cols = v.cols;
+        s.stride = v.stride;
+        s.paint = v.paint;
+        s.conv = v.one_channel() ? 0 : SVGR_CONV(v.pre, v.lin, want_pre, want_lin);
+        s.mul = v.mul;
+        s.off = v.off;
+        s.off2 = v.off2, s.stride2 = v.stride2;
+        return s;
+    }
+
+    // emits an op producing `out` from srcs
+    void emit(int cls, int kind, const Val &out, const std::vector<SrcRec> &ss, int mode, int post, float mul, int level,
+              const float *k = nullptr, int aux = 0, int k0 = 0, int k1 = 0, int stencil = 0)
+    {
+        PlannedOp p;
+        memset(&p, 0, sizeof p);
+        p.level = level, p.cls = cls;
+        OpRec &o = p.op;
+        o.kind = kind, o.mode = mode;
+        o.r0 = out.r0, o.c0 = out.c0, o.rows = out.rows, o.cols = out.cols;
+        o.stride = out.stride;
+        o.out_ch = out.kind == SRC_L4 ? 4 : 1;
+        o.out_off = out.off;
+        o.src_off = (int)ctx->srcs.size(), o.src_cnt = (int)ss.size();
+        o.post = post, o.aux = aux, o.k0 = k0, o.k1 = k1, o.stencil = stencil;
+        o.mul = mul;
+        if (k)
+            for (int i = 0; i < 4; i++)
+                o.k[i] = k[i];
+        for (auto &s : ss)
+            ctx->srcs.push_back(s);
+        ctx->ops.push_back(p);
+    }
+
+    // single-source pass: convert / multiply / post-process into a fresh layer
+    Val unary(const Val &v, int out_kind, int want_pre, int want_lin, int out_pre, int out_lin, int post, float mul,
+              int aux = 0)
+    {
+        Val out = alloc(out_kind, v.r0, v.c0, v.rows, v.cols, out_pre, out_lin, v.level + 1);
+        emit(0, OP_COMPOSE, out, {src_of(v, want_pre, want_lin)}, MODE_OVER, post, mul, out.level, nullptr, aux);
+        return out;
+    }
+
+    Val materialize(const Val &v)
+    {
+        if (v.kind == VAL_EMPTY || ((v.kind == SRC_L4 || v.kind == SRC_L1) && v.mul == 1.0f))
+            return v;
+        if (v.one_channel())
+            return unary(v, SRC_L1, v.pre, v.lin, v.pre, v.lin, POST_NONE, 1.0f);
+        return unary(v, SRC_L4, v.pre, v.lin, v.pre, v.lin, POST_NONE, 1.0f);
+    }
+
+    // Layer.compose (svgrasterize.py:178-207)
+    Val compose(std::vector<Val> layers, int mode, const float *k, int lin)
+    {
+        if (layers.empty())
+            return Val();
+        if (layers.size() == 1)
+            return layers[0];
+        int pre = mode != MODE_ARITH;
+        int level = 0;
+        for (auto &l : layers)
+            level = std::max(level, l.level);
+        level += 1;
+        int r0, c0, r1, c1;
+        if (mode == MODE_IN) {
+            r0 = c0 = INT32_MIN, r1 = c1 = INT32_MAX;
+            for (auto &l : layers) {
+                r0 = std::max(r0, l.r0), c0 = std::max(c0, l.c0);
+                r1 = std::min(r1, l.r0 + l.rows), c1 = std::min(c1, l.c0 + l.cols);
+            }
+            if (r1 - r0 <= 0 || c1 - c0 <= 0)
+                return Val();
+        } else {
+            r0 = c0 = INT32_MAX, r1 = c1 = INT32_MIN;
+            for (auto &l : layers) {
+                r0 = std::min(r0, l.r0), c0 = std::min(c0, l.c0);
+                r1 = std::max(r1, l.r0 + l.rows), c1 = std::max(c1, l.c0 + l.cols);
+            }
+        }
+        Val out = alloc(SRC_L4, r0, c0, r1 - r0, c1 - c0, pre, lin, level);
+        std::vector<SrcRec> ss;
+        ss.reserve(layers.size());
+        for (auto &l : layers)
+            ss.push_back(src_of(l, pre, lin));
+        emit(0, OP_COMPOSE, out, ss, mode, POST_NONE, 1.0f, level, k);
+        return out;
+    }
+
+    static int py_int(double v) { return (int)v; }  // Python int(): truncation toward zero
+
+    bool node(int i, Val &out)
+    {
+        const svgr_node &n = ctx->h_nodes[i];
+        const int32_t *ch = ctx->h_children.data() + n.child_off;
+        const int lin = n.flags & 1;
+        auto child = [&](int k) -> const Val & { return ctx->vals[ch[k]]; };
+        for (int k = 0; k < n.child_cnt; k++)
+            if (ch[k] < 0 || ch[k] >= i) {
+                err = "scene program: children must precede their parent";
+                return false;
+            }
+        out = Val();
+        switch (n.tag) {
+        case SVGR_N_EMPTY:
+            break;
+        case SVGR_N_LEAF: {
+            if (n.a < 0 || n.a >= ctx->n_path) {
+                err = "leaf: bad path index";
+                return false;
+            }
+            const MaskRec &m = ctx->h_masks[n.a];
+            if (m.rows <= 0 || m.cols <= 0)
+                break;
+            out.kind = n.b < 0 ? SRC_COV : SRC_COVPAINT;
+            out.r0 = m.r0, out.c0 = m.c0, out.rows = m.rows, out.cols = m.cols, out.stride = m.stride;
+            out.off = m.off;
+            out.paint = n.b;
+            out.pre = 1, out.lin = n.b < 0 ? 1 : (n.c != 0);
+            out.level = 0;
+            if (n.b >= 0) {
+                if (n.b >= ctx->n_paint) {
+                    err = "leaf: bad paint index";
+                    return false;
+                }
+                const PaintRec &p = ctx->h_paints[n.b];
+                if (p.kind == PAINT_PATTERN) {
+                    if (n.d < 0 || n.d >= i) {
+                        err = "pattern leaf: bad pattern node";
+                        return false;
+                    }
+                    const Val &pat = ctx->vals[n.d];
+                    if (pat.kind != SRC_L4) {  // tile rendered to nothing: Path.fill returns None (:1064-1065)
+                        out = Val();
+                        break;
+                    }
+                    out.off2 = pat.off, out.stride2 = pat.stride;
+                    out.pre = pat.pre, out.lin = pat.lin;
+                    out.level = pat.level;
+                } else if (p.kind == PAINT_RADIAL_FOCAL) {
+                    FocalJob j;
+                    j.paint = n.b, j.r0 = m.r0, j.c0 = m.c0, j.rows = m.rows, j.cols = m.cols;
+                    j.block_base = ctx->n_focal_blocks;
+                    ctx->n_focal_blocks += (int)(((long long)m.rows * m.cols + 1023) / 1024);
+                    ctx->focal_jobs.push_back(j);
+                }
+            }
+            break;
+        }
+        case SVGR_N_GROUP: {
+            std::vector<Val> ls;
+            for (int k = 0; k < n.child_cnt; k++)
+                if (child(k).kind != VAL_EMPTY)
+                    ls.push_back(child(k));
+            out = compose(ls, MODE_OVER, nullptr, lin);
+            break;
+        }
+        case SVGR_N_OPACITY: {
+            const Val &v = child(0);
+            if (v.kind == VAL_EMPTY)
+                break;
+            float value = (float)n.f[0];
+            if (v.one_channel() || (v.pre == 1 && v.lin == lin)) {
+                out = v;  // Layer.opacity: convert is a relabel here, the multiply folds into the source
+                out.mul = v.mul * value;
+                out.pre = 1, out.lin = lin;
+            } else {
+                out = unary(v, SRC_L4, 1, lin, 1, lin, POST_NONE, value);
+            }
+            break;
+        }
+        case SVGR_N_IN: {
+            if (n.child_cnt != 2) {
+                err = "IN node needs two children";
+                return false;
+            }
+            if (child(0).kind == VAL_EMPTY || child(1).kind == VAL_EMPTY)
+                break;
+            out = compose({child(0), child(1)}, MODE_IN, nullptr, lin);
+            break;
+        }
+        case SVGR_N_LUMA: {
+            const Val &v = child(0);
+            if (v.kind == VAL_EMPTY)
+                break;
+            if (v.one_channel()) {
+                err = "luminance mask of a one-channel layer (the reference raises here)";
+                return false;
+            }
+            out = unary(v, SRC_L1, 0, lin, 0, lin, POST_LUMA, 1.0f);
+            break;
+        }
+        case SVGR_N_COMPOSE: {
+            std::vector<Val> ls;
+            for (int k = 0; k < n.child_cnt; k++) {
+                if (child(k).kind == VAL_EMPTY)
+                    return true;  // a None input: the reference would fail later; propagate "nothing"
+                ls.push_back(child(k));
+            }
+            float kk[4] = {(float)n.f[0], (float)n.f[1], (float)n.f[2], (float)n.f[3]};
+            if (n.a < 0 || n.a > MODE_ARITH) {
+                err = "invalid compose mode";
+                return false;
+            }
+            out = compose(ls, n.a, kk, lin);
+            break;
+        }
+        case SVGR_N_SRC_ALPHA: {
+            const Val &v = child(0);
+            if (v.kind == VAL_EMPTY)
+                break;
+            // alpha is the last channel whatever the flags; no conversion (svgrasterize.py:1803-1808)
+            out = unary(v, SRC_L4, v.pre, v.lin, 1, 1, POST_ALPHA, 1.0f);
+            break;
+        }
+        case SVGR_N_CONVERT: {
+            const Val &v = child(0);
+            if (v.kind == VAL_EMPTY)
+                break;
+            int pre = n.a < 0 ? v.pre : (n.a != 0), l = n.b < 0 ? v.lin : (n.b != 0);
+            if (v.one_channel() || (v.pre == pre && v.lin == l)) {
+                out = v;
+                out.pre = pre, out.lin = l;
+            } else {
+                out = unary(v, SRC_L4, pre, l, pre, l, POST_NONE, 1.0f);
+            }
+            break;
+        }
+        case SVGR_N_BLUR: {
+            const Val &v = child(0);
+            if (v.kind == VAL_EMPTY)
+                break;
+            if (n.a < 0 || n.a >= (int)ctx->h_kernels.size()) {
+                err = "blur: bad kernel index";
+                return false;
+            }
+            const svgr_kernel &kn = ctx->h_kernels[n.a];
+            // Layer.convolve (svgrasterize.py:106-115): full convolution on straight-alpha linear RGBA
+            int orows = v.rows + kn.rows - 1, ocols = v.cols + kn.cols - 1;
+            int r0 = py_int((double)v.r0 - kn.rows / 2.0), c0 = py_int((double)v.c0 - kn.cols / 2.0);
+            if (kn.separable) {
+                Val tmp = alloc(SRC_L4, v.r0, c0, v.rows, ocols, 0, 1, v.level + 1);
+                emit(1, OP_STENCIL_H, tmp, {src_of(v, 0, 1)}, 0, 0, 1.0f, tmp.level, nullptr, kn.weight_off + kn.rows,
+                     kn.cols, 0, STENCIL_CONV);
+                out = alloc(SRC_L4, r0, c0, orows, ocols, 0, 1, tmp.level + 1);
+                emit(1, OP_STENCIL_V, out, {src_of(tmp, 0, 1)}, 0, 0, 1.0f, out.level, nullptr, kn.weight_off, kn.rows, 0,
+                     STENCIL_CONV);
+            } else {
+                out = alloc(SRC_L4, r0, c0, orows, ocols, 0, 1, v.level + 1);
+                emit(2, OP_CONV2D, out, {src_of(v, 0, 1)}, 0, 0, 1.0f, out.level, nullptr, kn.weight_off, kn.rows, kn.cols);
+            }
+            break;
+        }
+        case SVGR_N_MORPH: {
+            const Val &v = child(0);
+            if (v.kind == VAL_EMPTY)
+                break;
+            int k0 = n.a, k1 = n.b;
+            int st = n.c ? STENCIL_MAX : STENCIL_MIN;
+            int orows = v.rows - k0 + 1, ocols = v.cols - k1 + 1;
+            if (k0 < 1 || k1 < 1) {
+                err = "morphology: window must be >= 1";
+                return false;
+            }
+            if (orows <= 0 || ocols <= 0)
+                break;
+            // Layer.morphology (svgrasterize.py:120-127): premultiplied linear, top-left anchored, offset unchanged
+            Val tmp = alloc(SRC_L4, v.r0, v.c0, v.rows, ocols, 1, 1, v.level + 1);
+            emit(1, OP_STENCIL_H, tmp, {src_of(v, 1, 1)}, 0, 0, 1.0f, tmp.level, nullptr, 0, k1, 0, st);
+            out = alloc(SRC_L4, v.r0, v.c0, orows, ocols, 1, 1, tmp.level + 1);
+            emit(1, OP_STENCIL_V, out, {src_of(tmp, 1, 1)}, 0, 0, 1.0f, out.level, nullptr, 0, k0, 0, st);
+            break;
+        }
+        case SVGR_N_CMATRIX: {
+            const Val &v = child(0);
+            if (v.kind == VAL_EMPTY)
+                break;
+            if (n.a < 0 || n.a >= ctx->n_matrix) {
+                err = "color matrix: bad index";
+                return false;
+            }
+            out = unary(v, SRC_L4, 0, 1, 0, 1, POST_MATRIX, 1.0f, n.a);
+            break;
+        }
+        case SVGR_N_OFFSET: {
+            const Val &v = child(0);
+            if (v.kind == VAL_EMPTY)
+                break;
+            if (n.a < 0 || (size_t)(n.a + 1) * 12 > ctx->h_offset_tr.size()) {
+                err = "offset: bad transform index";
+                return false;
+            }
+            // filter_offset (svgrasterize.py:1844-1850): 1-D points go through numpy's vector @ matrix
+            // path, whose rounding is fma(x, m0, y*m1) + m2
+            const double *f = ctx->h_offset_tr.data() + 12 * n.a, *inv = f + 6;
+            double x = v.r0, y = v.c0;
+            double ux = fma(x, inv[0], y * inv[1]) + inv[2], uy = fma(x, inv[3], y * inv[4]) + inv[5];
+            ux = ux + n.f[0], uy = uy + n.f[1];
+            double tx = fma(ux, f[0], uy * f[1]) + f[2], ty = fma(ux, f[3], uy * f[4]) + f[5];
+            out = v;
+            out.r0 = v.r0 + (py_int(tx) - v.r0);
+            out.c0 = v.c0 + (py_int(ty) - v.c0);
+            if (v.kind == SRC_COVPAINT || v.kind == SRC_COV) {  // keep mask-relative sources anchored: materialise first
+                Val mat = materialize(v);
+                out = mat;
+                out.r0 = mat.r0 + (py_int(tx) - v.r0);
+                out.c0 = mat.c0 + (py_int(ty) - v.c0);
+            }
+            break;
+        }
+        case SVGR_N_MERGE_AT: {
+            const Val &v = child(0);
+            if (v.kind == VAL_EMPTY)
+                break;
+            if (n.c <= 0 || n.d <= 0)
+                break;
+            // canvas_merge_at onto zeros (svgrasterize.py:304-327): no conversion, result clipped to [0, 1]
+            Val o2 = alloc(SRC_L4, n.a, n.b, n.c, n.d, v.pre, v.lin, v.level + 1);
+            emit(0, OP_COMPOSE, o2, {src_of(v, v.pre, v.lin)}, MODE_OVER, POST_CLIP01, 1.0f, o2.level);
+            out = o2;
+            break;
+        }
+        case SVGR_N_CANVAS: {
+            Val v = n.child_cnt > 0 ? child(0) : Val();
+            if (v.one_channel()) {
+                err = "Only RGBA layers are supported";
+                return false;
+            }
+            PlannedOp p;
+            memset(&p, 0, sizeof p);
+            p.level = 1 << 30, p.cls = 3;
+            OpRec &o = p.op;
+            o.kind = OP_CANVAS, o.mode = lin;
+            o.r0 = 0, o.c0 = 0, o.rows = n.a, o.cols = n.b, o.stride = n.b, o.out_ch = 4;
+            o.out_off = (long long)n.f[0];
+            o.src_off = (int)ctx->srcs.size();
+            o.src_cnt = v.kind == VAL_EMPTY ? 0 : 1;
+            o.mul = 1.0f;
+            if (v.kind != VAL_EMPTY)
+                ctx->srcs.push_back(src_of(v, 1, lin));
+            if (o.rows < 0 || o.cols < 0 || o.out_off < 0 || o.out_off + 4ll * o.rows * o.cols > ctx->canvas_bytes) {
+                err = "canvas node outside the output buffer";
+                return false;
+            }
+            ctx->ops.push_back(p);
+            out = v;
+            break;
+        }
+        case SVGR_N_EXTERNAL: {
+            if (n.a < 0 || n.a >= (int)ctx->h_ext.size()) {
+                err = "external: bad index";
+                return false;
+            }
+            const svgr_external &e = ctx->h_ext[n.a];
+            if (e.rows <= 0 || e.cols <= 0)
+                break;
+            out = alloc(e.channels == 1 ? SRC_L1 : SRC_L4, e.r0, e.c0, e.rows, e.cols, e.pre_alpha != 0,
+                        e.linear_rgb != 0, 0);
+            break;
+        }
+        default:
+            err = "unknown node tag";
+            return false;
+        }
+        if ((n.flags & 2) && out.kind != VAL_EMPTY)
+            out = materialize(out);
+        return true;
+    }
+
+    bool run()
+    {
+        svgr_ctx *c = ctx;
+        c->ops.clear(), c->srcs.clear(), c->focal_jobs.clear(), c->launches.clear();
+        c->n_focal_blocks = 0;
+        c->layer_pixels = 0, c->mask_pixels = 0;
+        // ---- masks, bands, tiles
+        c->h_masks.assign(c->n_path, MaskRec());
+        long long cov_top = 0, band = 0, tile = 0;
+        for (int i = 0; i < c->n_path; i++) {
+            MaskRec &m = c->h_masks[i];
+            memset(&m, 0, sizeof m);
+            const PathBox &b = c->h_boxes[i];
+            m.band_base = (int)band, m.tile_base = (int)tile;
+            m.fill_rule = c->h_paths[i].fill_rule;
+            if (b.rows <= 0 || b.cols <= 0)
+                continue;
+            m.r0 = b.r0, m.c0 = b.c0, m.rows = b.rows, m.cols = b.cols;
+            m.stride = (int)align4(b.cols);
+            m.off = cov_top;
+            cov_top += (long long)m.rows * m.stride;
+            m.ntile_c = ceil_div(m.cols, SVGR_TILE_COLS);
+            int nb = ceil_div(m.rows, SVGR_BAND_ROWS);
+            band += nb;
+            tile += (long long)nb * m.ntile_c;
+            c->mask_pixels += (long long)m.rows * m.cols;
+            if (band > 0x7fffff00ll || tile > 0x7fffff00ll) {
+                err = "too many coverage tiles in one batch";
+                return false;
+            }
+        }
+        c->n_bands = band, c->n_cov_tiles = tile, c->cov_floats = cov_top;
+        // ---- nodes
+        c->vals.assign(c->n_node, Val());
+        for (int i = 0; i < c->n_node; i++)
+            if (!node(i, c->vals[i]))
+                return false;
+        c->layer_floats = align4(layer_top);
+        // ---- order ops by (level, class); stable so that srcs stay valid
+        std::stable_sort(c->ops.begin(), c->ops.end(), [](const PlannedOp &a, const PlannedOp &b) {
+            return a.level != b.level ? a.level < b.level : a.cls < b.cls;
+        });
+        int nl = 0, last_level = -1;
+        size_t i = 0;
+        while (i < c->ops.size()) {
+            size_t j = i;
+            Launch L;
+            L.cls = c->ops[i].cls, L.op_begin = (int)i, L.n_tiles = 0, L.smem = 0;
+            long long tiles = 0;
+            while (j < c->ops.size() && c->ops[j].level == c->ops[i].level && c->ops[j].cls == c->ops[i].cls) {
+                OpRec &o = c->ops[j].op;
+                int tr = SVGR_CMP_TR, tc = SVGR_CMP_TC;
+                size_t smem = 0;
+                if (o.kind == OP_STENCIL_H) {
+                    tr = SVGR_STH_TR, tc = SVGR_STH_TC;
+                    smem = (size_t)SVGR_STH_TR * (SVGR_STH_TC + o.k0 - 1) * 16;
+                } else if (o.kind == OP_STENCIL_V) {
+                    tr = SVGR_STV_TR, tc = SVGR_STV_TC;
+                    smem = (size_t)(SVGR_STV_TR + o.k0 - 1) * SVGR_STV_TC * 16;
+                } else if (o.kind == OP_CONV2D) {
+                    smem = (size_t)(SVGR_CMP_TR + o.k0 - 1) * (SVGR_CMP_TC + o.k1 - 1) * 16;
+                }
+                o.ntile_c = std::max(1, ceil_div(o.cols, tc));
+                o.tile_base = (int)tiles;
+                tiles += (long long)ceil_div(o.rows, tr) * ceil_div(o.cols, tc);
+                L.smem = std::max(L.smem, smem);
+                j++;
+            }
+            if (tiles > 0x7fffff00ll) {
+                err = "too many tiles in one launch";
+                return false;
+            }
+            if (L.smem > SVGR_MAX_DYN_SMEM) {
+                err = "stencil too long for shared-memory staging";
+                return false;
+            }
+            L.op_count = (int)(j - i), L.n_tiles = (int)tiles;
+            c->launches.push_back(L);
+            if (c->ops[i].level != last_level)
+                nl++, last_level = c->ops[i].level;
+            i = j;
+        }
+        c->n_levels = nl;
+        return true;
+    }
+};
+
+template <class T>
+cudaError_t upload(DevBuf &b, const T *src, size_t n, cudaStream_t s)
+{
+    cudaError_t e = b.ensure(std::max<size_t>(n, 1) * sizeof(T));
+    if (e != cudaSuccess || n == 0)
+        return e;
+    return cudaMemcpyAsync(b.p, src, n * sizeof(T), cudaMemcpyHostToDevice, s);
+}
+
+float ev_ms(cudaEvent_t a, cudaEvent_t b)
+{
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    return ms;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// pipeline
+// ---------------------------------------------------------------------------------------------
+static int load_program(svgr_ctx *ctx, const svgr_program *p, cudaStream_t s)
+{
+    if (!p)
+        FAIL(SVGR_E_INVALID, "null program");
+    if (p->n_seg < 0 || p->n_path < 0 || p->n_node < 0 || p->n_stroke_seg < 0)
+        FAIL(SVGR_E_INVALID, "negative count in program");
+    ctx->n_seg = p->n_seg, ctx->n_path = p->n_path, ctx->n_stroke = p->n_stroke, ctx->n_stroke_sub = p->n_stroke_sub;
+    ctx->n_stroke_seg = p->n_stroke_seg, ctx->n_paint = p->n_paint, ctx->n_stop = p->n_stop, ctx->n_focal = p->n_focal;
+    ctx->n_node = p->n_node, ctx->canvas_bytes = p->canvas_bytes;
+    ctx->n_weight = p->n_weight, ctx->n_matrix = p->n_matrix;
+    CK(upload(ctx->d_seg_tag, p->seg_tag, (size_t)p->n_seg, s));
+    CK(upload(ctx->d_seg_data, p->seg_data, (size_t)p->n_seg * 8, s));
+    CK(upload(ctx->d_seg_path, p->seg_path, (size_t)p->n_seg, s));
+    CK(upload(ctx->d_paths, p->paths, (size_t)p->n_path, s));
+    CK(upload(ctx->d_strokes, p->strokes, (size_t)p->n_stroke, s));
+    CK(upload(ctx->d_ssub_off, p->stroke_sub_off, p->n_stroke_sub > 0 ? (size_t)p->n_stroke_sub + 1 : 0, s));
+    CK(upload(ctx->d_ssub_job, p->stroke_sub_job, (size_t)p->n_stroke_sub, s));
+    CK(upload(ctx->d_stag, p->stroke_tag, (size_t)p->n_stroke_seg, s));
+    CK(upload(ctx->d_sdata, p->stroke_data, (size_t)p->n_stroke_seg * 8, s));
+    CK(upload(ctx->d_sseg_job, p->stroke_seg_job, (size_t)p->n_stroke_seg, s));
+    CK(upload(ctx->d_paints, p->paints, (size_t)p->n_paint, s));
+    CK(upload(ctx->d_stops, p->stops, (size_t)p->n_stop, s));
+    CK(upload(ctx->d_matrices, p->matrices, (size_t)p->n_matrix * 20, s));
+    CK(upload(ctx->d_weights, p->weights, (size_t)p->n_weight, s));
+    ctx->h_paths.assign(p->paths, p->paths + p->n_path);
+    ctx->h_paints.assign(p->paints, p->paints + p->n_paint);
+    ctx->h_nodes.assign(p->nodes, p->nodes + p->n_node);
+    ctx->h_children.assign(p->children, p->children + p->n_child);
+    ctx->h_kernels.assign(p->kernels, p->kernels + p->n_kernel);
+    ctx->h_offset_tr.assign(p->offset_tr, p->offset_tr + (size_t)p->n_offset_tr * 12);
+    ctx->h_ext.assign(p->externals, p->externals + p->n_external);
+    ctx->h_ext_data.clear();
+    for (int i = 0; i < p->n_external; i++) {
+        const svgr_external &e = p->externals[i];
+        if (e.channels != 1 && e.channels != 4)
+            FAIL(SVGR_E_INVALID, "external layer must have 1 or 4 channels");
+        size_t n = (size_t)std::max(e.rows, 0) * std::max(e.cols, 0) * e.channels;
+        ctx->h_ext_data.emplace_back(e.image, e.image + n);
+    }
+    for (int i = 0; i < p->n_node; i++) {
+        const svgr_node &n = p->nodes[i];
+        if (n.child_cnt < 0 || n.child_off < 0 || (long long)n.child_off + n.child_cnt > p->n_child)
+            FAIL(SVGR_E_INVALID, "node child range outside the children table");
+    }
+    for (long long i = 0; i < p->n_seg; i++)
+        if (p->seg_path[i] >= (uint32_t)p->n_path)
+            FAIL(SVGR_E_INVALID, "segment refers to a path outside the path table");
+    for (int i = 0; i < p->n_stroke; i++)
+        if (p->strokes[i].path < 0 || p->strokes[i].path >= p->n_path)
+            FAIL(SVGR_E_INVALID, "stroke refers to a path outside the path table");
+    for (int i = 0; i < p->n_paint; i++) {
+        const PaintRec &q = p->paints[i];
+        if (q.kind != PAINT_SOLID && q.kind != PAINT_PATTERN &&
+            (q.stop_cnt < 1 || q.stop_off < 0 || q.stop_off + q.stop_cnt > p->n_stop))
+            FAIL(SVGR_E_INVALID, "gradient without stops");
+        if (q.kind == PAINT_RADIAL_FOCAL && (q.flag < 0 || q.flag >= p->n_focal))
+            FAIL(SVGR_E_INVALID, "focal flag index out of range");
+    }
+    ctx->have_program = true;
+    ctx->planned = ctx->covered = ctx->composed = false;
+    return SVGR_OK;
+}
+
+static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *out, int out_on_device, int timing,
+                        svgr_stats *stats)
+{
+    if (!ctx->have_program)
+        FAIL(SVGR_E_INVALID, "no program loaded");
+    const int SM = ctx->sm_count;
+    int retries = 0;
+    float ms_stroke = 0, ms_flatten = 0, ms_plan = 0, ms_bin = 0, ms_cov = 0, ms_cmp = 0, ms_canvas = 0, ms_d2h = 0;
+    ctx->planned = ctx->covered = ctx->composed = false;
+    auto mark = [&](int i) {
+        if (timing)
+            cudaEventRecord(ctx->ev[i], s);
+    };
+
+    // ---- capacities (grow-only, kept between calls)
+    const long long S = ctx->n_stroke_seg;
+    if (ctx->edge_cap == 0)
+        ctx->edge_cap = 1024;
+    {
+        long long want = ctx->n_seg * 6 + S * 48 + 1024;
+        if (ctx->edge_cap < want)
+            ctx->edge_cap = want;
+    }
+    if (S > 0) {
+        ctx->pool_cap = std::max(ctx->pool_cap, S * 8 + 256);
+        ctx->outline_cap = std::max(ctx->outline_cap, S * 24 + 16ll * ctx->n_stroke_sub + 256);
+    }
+    CK(ctx->d_status.ensure(sizeof(StatusBlock)));
+    CK(ctx->pin_status.ensure(sizeof(StatusBlock)));
+    CK(ctx->d_minmax.ensure((size_t)std::max(ctx->n_path, 1) * 32));
+    CK(ctx->d_boxes.ensure((size_t)std::max(ctx->n_path, 1) * sizeof(PathBox)));
+    CK(ctx->d_minmax_f64.ensure((size_t)std::max(ctx->n_path, 1) * 32));
+    CK(ctx->pin_boxes.ensure((size_t)std::max(ctx->n_path, 1) * sizeof(PathBox)));
+    StatusBlock *d_st = ctx->d_status.as<StatusBlock>();
+    StatusBlock st;
+
+    for (;;) {
+        CK(ctx->d_edges.ensure((size_t)ctx->edge_cap * 32));
+        CK(ctx->d_edge_path.ensure((size_t)ctx->edge_cap * 4));
+        CK(cudaMemsetAsync(d_st, 0, sizeof(StatusBlock), s));
+        svgr_launch_minmax_init(ctx->d_minmax.as<unsigned long long>(), ctx->n_path, s);
+        mark(0);
+        // ---- stroke outlines
+        if (S > 0) {
+            if (S > 0x3fffffff)
+                FAIL(SVGR_E_INVALID, "too many stroke segments");
+            const int nS = (int)S, nSub = ctx->n_stroke_sub;
+            CK(ctx->d_scounts.ensure((size_t)(2 * nS + 1) * 4));
+            CK(ctx->d_soffs.ensure((size_t)(2 * nS + 1) * 4));
+            CK(ctx->d_scan_tmp.ensure((size_t)((2 * nS + nSub) / 2048 + 4) * 4));
+            CK(ctx->d_pool.ensure((size_t)ctx->pool_cap * svgr_stroke_curve_bytes()));
+            CK(ctx->d_sbound.ensure((size_t)(nSub + 1) * 4));
+            CK(ctx->d_sout_off.ensure((size_t)(nSub + 1) * 4));
+            CK(ctx->d_otag.ensure((size_t)ctx->outline_cap));
+            CK(ctx->d_odata.ensure((size_t)ctx->outline_cap * 64));
+            CK(ctx->d_opath.ensure((size_t)ctx->outline_cap * 4));
+            CK(ctx->d_osub.ensure((size_t)ctx->outline_cap * 4));
+            CK(cudaMemsetAsync(ctx->d_scounts.p, 0, (size_t)(2 * nS + 1) * 4, s));
+            svgr_launch_stroke_count(ctx->d_stag.as<uint8_t>(), ctx->d_sdata.as<double>(), ctx->d_sseg_job.as<int>(),
+                                     ctx->d_strokes.as<StrokeRec>(), nS, ctx->d_scounts.as<int>(), &d_st->stroke_err, s);
+            svgr_launch_exclusive_scan(ctx->d_scounts.as<int>(), ctx->d_soffs.as<int>(), 2 * nS + 1,
+                                       ctx->d_scan_tmp.as<int>(), &d_st->stroke_curves, s);
+            svgr_launch_stroke_emit(ctx->d_stag.as<uint8_t>(), ctx->d_sdata.as<double>(), ctx->d_sseg_job.as<int>(),
+                                    ctx->d_strokes.as<StrokeRec>(), nS, ctx->d_soffs.as<int>(), ctx->d_pool.p,
+                                    (int)std::min<long long>(ctx->pool_cap, 0x7fffffff), s);
+            svgr_launch_stroke_bound(ctx->d_ssub_off.as<int>(), nSub, nS, ctx->d_soffs.as<int>(), ctx->d_sbound.as<int>(), s);
+            svgr_launch_exclusive_scan(ctx->d_sbound.as<int>(), ctx->d_sout_off.as<int>(), nSub, ctx->d_scan_tmp.as<int>(),
+                                       &d_st->outline_total, s);
+            svgr_launch_stroke_assemble(ctx->d_stag.as<uint8_t>(), ctx->d_ssub_off.as<int>(), ctx->d_ssub_job.as<int>(),
+                                        ctx->d_strokes.as<StrokeRec>(), nSub, nS, ctx->d_soffs.as<int>(), ctx->d_pool.p,
+                                        ctx->d_sbound.as<int>(), ctx->d_sout_off.as<int>(), &d_st->outline_total, 0,
+                                        ctx->outline_cap, ctx->d_otag.as<uint8_t>(), ctx->d_odata.as<double>(),
+                                        ctx->d_opath.as<uint32_t>(), ctx->d_osub.as<int32_t>(), &d_st->outline_count,
+                                        &d_st->stroke_err, s);
+        }
+        mark(1);
+        // ---- flatten + bounds
+        if (stop_after != SVGR_STOP_STROKE) {
+            const double tol = 0.1;  // literal flatness of Path.mask (svgrasterize.py:955/:957)
+            const double thr = (tol * tol) * 16;
+            svgr_launch_flatten(ctx->d_seg_tag.as<uint8_t>(), ctx->d_seg_data.as<double>(), ctx->d_seg_path.as<uint32_t>(),
+                                ctx->n_seg, nullptr, ctx->d_paths.as<PathRec>(), thr, ctx->d_edges.as<double>(),
+                                ctx->d_edge_path.as<uint32_t>(), (unsigned long long)ctx->edge_cap, &d_st->n_edges,
+                                ctx->d_minmax.as<unsigned long long>(), SM, s);
+            if (S > 0)
+                svgr_launch_flatten(ctx->d_otag.as<uint8_t>(), ctx->d_odata.as<double>(), ctx->d_opath.as<uint32_t>(),
+                                    ctx->outline_cap, &d_st->outline_count, ctx->d_paths.as<PathRec>(), thr,
+                                    ctx->d_edges.as<double>(), ctx->d_edge_path.as<uint32_t>(),
+                                    (unsigned long long)ctx->edge_cap, &d_st->n_edges,
+                                    ctx->d_minmax.as<unsigned long long>(), SM, s);
+            svgr_launch_bounds(ctx->d_minmax.as<unsigned long long>(), ctx->d_paths.as<PathRec>(), ctx->n_path,
+                               ctx->d_boxes.as<PathBox>(), ctx->d_minmax_f64.as<double>(), s);
+            if (ctx->n_path > 0)
+                CK(cudaMemcpyAsync(ctx->pin_boxes.p, ctx->d_boxes.p, (size_t)ctx->n_path * sizeof(PathBox),
+                                   cudaMemcpyDeviceToHost, s));
+        }
+        CK(cudaMemcpyAsync(ctx->pin_status.p, d_st, sizeof(StatusBlock), cudaMemcpyDeviceToHost, s));
+        mark(2);
+        CK(cudaStreamSynchronize(s));
+        st = *(StatusBlock *)ctx->pin_status.p;
+        if (timing) {
+            ms_stroke += ev_ms(ctx->ev[0], ctx->ev[1]);
+            ms_flatten += ev_ms(ctx->ev[1], ctx->ev[2]);
+        }
+        bool again = false;
+        if ((long long)st.n_edges > ctx->edge_cap) {
+            ctx->edge_cap = (long long)st.n_edges + 1024;
+            again = true;
+        }
+        if (S > 0 && st.stroke_curves > ctx->pool_cap) {
+            ctx->pool_cap = (long long)st.stroke_curves + 256;
+            again = true;
+        }
+        if (S > 0 && st.outline_total > ctx->outline_cap) {
+            ctx->outline_cap = (long long)st.outline_total + 256;
+            again = true;
+        }
+        if (!again)
+            break;
+        if (++retries > 4)
+            FAIL(SVGR_E_NOMEM, "capacity retry limit reached");
+    }
+    if (st.stroke_err & 1)
+        FAIL(SVGR_E_STROKE, "cannot unpack non-iterable NoneType object");
+    if (st.stroke_err & 2)
+        FAIL(SVGR_E_INVALID, "stroke assembly overflow or unknown line cap");
+    ctx->n_edges = (long long)st.n_edges;
+    ctx->h_boxes.assign((PathBox *)ctx->pin_boxes.p, (PathBox *)ctx->pin_boxes.p + ctx->n_path);
+
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        stats->n_edges = ctx->n_edges;
+        stats->n_outline_segs = st.outline_count;
+        stats->retries = retries;
+        stats->ms_stroke = ms_stroke, stats->ms_flatten = ms_flatten;
+    }
+    if (stop_after == SVGR_STOP_STROKE || stop_after == SVGR_STOP_FLATTEN)
+        return SVGR_OK;
+    if (stop_after == SVGR_STOP_PLAN) {
+        Planner pl0(ctx);
+        if (!pl0.run())
+            FAIL(SVGR_E_INVALID, pl0.err);
+        ctx->planned = true;
+        return SVGR_OK;
+    }
+
+    // ---- plan
+    mark(3);
+    Planner pl(ctx);
+    if (!pl.run())
+        FAIL(SVGR_E_INVALID, pl.err);
+    ctx->planned = true;
+    {
+        // one pinned staging buffer for all plan tables
+        size_t b_masks = (size_t)ctx->n_path * sizeof(MaskRec);
+        size_t b_ops = ctx->ops.size() * sizeof(OpRec);
+        size_t b_srcs = ctx->srcs.size() * sizeof(SrcRec);
+        size_t b_focal = ctx->focal_jobs.size() * sizeof(FocalJob);
+        CK(ctx->pin_plan.ensure(b_masks + b_ops + b_srcs + b_focal + 64));
+        char *pp = (char *)ctx->pin_plan.p;
+        if (b_masks)
+            memcpy(pp, ctx->h_masks.data(), b_masks);
+        OpRec *po = (OpRec *)(pp + b_masks);
+        for (size_t i = 0; i < ctx->ops.size(); i++)
+            po[i] = ctx->ops[i].op;
+        if (b_srcs)
+            memcpy(pp + b_masks + b_ops, ctx->srcs.data(), b_srcs);
+        if (b_focal)
+            memcpy(pp + b_masks + b_ops + b_srcs, ctx->focal_jobs.data(), b_focal);
+        CK(ctx->d_masks.ensure(std::max<size_t>(b_masks, 16)));
+        CK(ctx->d_ops.ensure(std::max<size_t>(b_ops, 16)));
+        CK(ctx->d_srcs.ensure(std::max<size_t>(b_srcs, 16)));
+        CK(ctx->d_focal_jobs.ensure(std::max<size_t>(b_focal, 16)));
+        if (b_masks)
+            CK(cudaMemcpyAsync(ctx->d_masks.p, pp, b_masks, cudaMemcpyHostToDevice, s));
+        if (b_ops)
+            CK(cudaMemcpyAsync(ctx->d_ops.p, pp + b_masks, b_ops, cudaMemcpyHostToDevice, s));
+        if (b_srcs)
+            CK(cudaMemcpyAsync(ctx->d_srcs.p, pp + b_masks + b_ops, b_srcs, cudaMemcpyHostToDevice, s));
+        if (b_focal)
+            CK(cudaMemcpyAsync(ctx->d_focal_jobs.p, pp + b_masks + b_ops + b_srcs, b_focal, cudaMemcpyHostToDevice, s));
+    }
+    CK(ctx->d_cov.ensure((size_t)std::max<long long>(ctx->cov_floats, 4) * 4));
+    CK(ctx->d_layers.ensure((size_t)std::max<long long>(ctx->layer_floats, 4) * 4));
+    CK(ctx->d_focal_flags.ensure((size_t)std::max(ctx->n_focal, 1) * 4));
+    mark(4);
+
+    // ---- binning
+    const long long NB = ctx->n_bands;
+    if (NB > 0 && ctx->n_edges > 0) {
+        CK(ctx->d_band_cnt.ensure((size_t)(NB + 1) * 4));
+        CK(ctx->d_band_off.ensure((size_t)(NB + 1) * 4));
+        CK(ctx->d_band_cur.ensure((size_t)(NB + 1) * 4));
+        CK(ctx->d_scan_tmp.ensure((size_t)(NB / 2048 + 4) * 4));
+        CK(cudaMemsetAsync(ctx->d_band_cnt.p, 0, (size_t)(NB + 1) * 4, s));
+        CK(cudaMemsetAsync(ctx->d_band_cur.p, 0, (size_t)(NB + 1) * 4, s));
+        svgr_launch_bin_count(ctx->d_edges.as<double>(), ctx->d_edge_path.as<uint32_t>(), (unsigned long long)ctx->n_edges,
+                              ctx->d_masks.as<MaskRec>(), ctx->d_band_cnt.as<int>(), SM, s);
+        svgr_launch_exclusive_scan(ctx->d_band_cnt.as<int>(), ctx->d_band_off.as<int>(), NB + 1, ctx->d_scan_tmp.as<int>(),
+                                   &d_st->binned_total, s);
+        CK(cudaMemcpyAsync(ctx->pin_status.p, d_st, sizeof(StatusBlock), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        ctx->n_binned = ((StatusBlock *)ctx->pin_status.p)->binned_total;
+        CK(ctx->d_bin_edges.ensure((size_t)std::max<long long>(ctx->n_binned, 1) * 4));
+        svgr_launch_bin_fill(ctx->d_edges.as<double>(), ctx->d_edge_path.as<uint32_t>(), (unsigned long long)ctx->n_edges,
+                             ctx->d_masks.as<MaskRec>(), ctx->d_band_off.as<int>(), ctx->d_band_cur.as<int>(),
+                             ctx->d_bin_edges.as<uint32_t>(), SM, s);
+    } else if (NB > 0) {
+        CK(ctx->d_band_cnt.ensure((size_t)(NB + 1) * 4));
+        CK(ctx->d_band_off.ensure((size_t)(NB + 1) * 4));
+        CK(ctx->d_bin_edges.ensure(16));
+        CK(cudaMemsetAsync(ctx->d_band_cnt.p, 0, (size_t)(NB + 1) * 4, s));
+        CK(cudaMemsetAsync(ctx->d_band_off.p, 0, (size_t)(NB + 1) * 4, s));
+        ctx->n_binned = 0;
+    }
+    mark(5);
+    // ---- coverage
+    svgr_launch_coverage(ctx->d_edges.as<double>(), ctx->d_masks.as<MaskRec>(), ctx->n_path, (int)ctx->n_cov_tiles,
+                         ctx->d_band_off.as<int>(), ctx->d_band_cnt.as<int>(), ctx->d_bin_edges.as<uint32_t>(),
+                         ctx->d_cov.as<float>(), s);
+    ctx->covered = true;
+    mark(6);
+    int n_launches = 0;
+    if (stop_after != SVGR_STOP_COVERAGE) {
+        RenderTables T;
+        T.srcs = ctx->d_srcs.as<SrcRec>(), T.paints = ctx->d_paints.as<PaintRec>(), T.stops = ctx->d_stops.as<StopRec>();
+        T.focal_flags = ctx->d_focal_flags.as<int>(), T.cov = ctx->d_cov.as<float>(), T.layers = ctx->d_layers.as<float>();
+        T.matrices = ctx->d_matrices.as<float>(), T.weights = ctx->d_weights.as<float>();
+        if (ctx->n_focal > 0) {
+            CK(cudaMemsetAsync(ctx->d_focal_flags.p, 0, (size_t)ctx->n_focal * 4, s));
+            svgr_launch_focal_flags(T, ctx->d_focal_jobs.p, (int)ctx->focal_jobs.size(), ctx->n_focal_blocks,
+                                    ctx->d_focal_flags.as<int>(), s);
+        }
+        // external layers
+        for (int i = 0; i < ctx->n_node; i++) {
+            const svgr_node &n = ctx->h_nodes[i];
+            if (n.tag != SVGR_N_EXTERNAL || ctx->vals[i].kind == VAL_EMPTY)
+                continue;
+            const Val &v = ctx->vals[i];
+            const std::vector<float> &src = ctx->h_ext_data[n.a];
+            if (v.kind == SRC_L4)
+                CK(cudaMemcpyAsync(ctx->d_layers.as<float>() + v.off, src.data(), src.size() * 4, cudaMemcpyHostToDevice, s));
+            else
+                CK(cudaMemcpy2DAsync(ctx->d_layers.as<float>() + v.off, (size_t)v.stride * 4, src.data(), (size_t)v.cols * 4,
+                                     (size_t)v.cols * 4, v.rows, cudaMemcpyHostToDevice, s));
+        }
+        uint8_t *canvas = nullptr;
+        bool has_canvas = false;
+        for (auto &L : ctx->launches)
+            has_canvas |= (L.cls == 3);
+        if (has_canvas) {
+            if (out_on_device && out) {
+                canvas = out;
+            } else {
+                CK(ctx->d_canvas.ensure((size_t)std::max<long long>(ctx->canvas_bytes, 4)));
+                canvas = ctx->d_canvas.as<uint8_t>();
+            }
+        }
+        for (auto &L : ctx->launches) {
+            const OpRec *ops = ctx->d_ops.as<OpRec>() + L.op_begin;
+            if (L.cls == 3)
+                mark(7);
+            if (L.cls == 0)
+                svgr_launch_compose(T, ops, L.op_count, L.n_tiles, ctx->d_layers.as<float>(), s);
+            else if (L.cls == 1) {
+                if (svgr_launch_stencil(T, ops, L.op_count, L.n_tiles, L.smem, ctx->d_layers.as<float>(), s))
+                    FAIL(SVGR_E_UNSUPPORTED, "stencil needs more shared memory than available");
+            } else if (L.cls == 2) {
+                if (svgr_launch_conv2d(T, ops, L.op_count, L.n_tiles, L.smem, ctx->d_layers.as<float>(), s))
+                    FAIL(SVGR_E_UNSUPPORTED, "convolution needs more shared memory than available");
+            } else
+                svgr_launch_canvas(T, ops, L.op_count, L.n_tiles, canvas, s);
+            n_launches++;
+        }
+        if (!has_canvas)
+            mark(7);
+        mark(8);
+        if (has_canvas && out && !out_on_device)
+            CK(cudaMemcpyAsync(out, canvas, (size_t)ctx->canvas_bytes, cudaMemcpyDeviceToHost, s));
+        mark(9);
+        ctx->composed = true;
+    }
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    if (timing) {
+        ms_plan = ev_ms(ctx->ev[3], ctx->ev[4]);
+        ms_bin = ev_ms(ctx->ev[4], ctx->ev[5]);
+        ms_cov = ev_ms(ctx->ev[5], ctx->ev[6]);
+        if (stop_after != SVGR_STOP_COVERAGE) {
+            ms_cmp = ev_ms(ctx->ev[6], ctx->ev[7]);
+            ms_canvas = ev_ms(ctx->ev[7], ctx->ev[8]);
+            ms_d2h = ev_ms(ctx->ev[8], ctx->ev[9]);
+        }
+    }
+    if (stats) {
+        stats->n_bands = ctx->n_bands, stats->n_cov_tiles = ctx->n_cov_tiles, stats->n_binned = ctx->n_binned;
+        stats->cov_floats = ctx->cov_floats, stats->layer_floats = ctx->layer_floats;
+        stats->n_ops = (int64_t)ctx->ops.size(), stats->n_levels = ctx->n_levels;
+        stats->n_launches = n_launches;
+        stats->mask_pixels = ctx->mask_pixels, stats->layer_pixels = ctx->layer_pixels;
+        stats->ms_plan = ms_plan, stats->ms_bin = ms_bin, stats->ms_coverage = ms_cov, stats->ms_compose = ms_cmp;
+        stats->ms_canvas = ms_canvas, stats->ms_d2h = ms_d2h;
+        stats->ms_total = ms_stroke + ms_flatten + ms_plan + ms_bin + ms_cov + ms_cmp + ms_canvas + ms_d2h;
+    }
+    return SVGR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+#pragma GCC visibility push(default)
+
+int svgr_version(void) { return SVGR_VERSION; }
+
+int svgr_sizeof(int what)
+{
+    switch (what) {
+    case 0: return (int)sizeof(PathRec);
+    case 1: return (int)sizeof(StrokeRec);
+    case 2: return (int)sizeof(PaintRec);
+    case 3: return (int)sizeof(StopRec);
+    case 4: return (int)sizeof(svgr_node);
+    case 5: return (int)sizeof(svgr_kernel);
+    case 6: return (int)sizeof(svgr_external);
+    case 7: return (int)sizeof(svgr_program);
+    case 8: return (int)sizeof(svgr_stats);
+    default: return -1;
+    }
+}
+
+int svgr_create(int device, svgr_ctx **out)
+{
+    if (!out)
+        return SVGR_E_INVALID;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n)
+        return SVGR_E_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess)
+        return SVGR_E_CUDA;
+    svgr_ctx *ctx = new svgr_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess)
+        ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return SVGR_E_CUDA;
+    }
+    for (auto &e : ctx->ev)
+        cudaEventCreate(&e);
+    *out = ctx;
+    return SVGR_OK;
+}
+
+void svgr_destroy(svgr_ctx *ctx)
+{
+    if (!ctx)
+        return;
+    cudaSetDevice(ctx->device);
+    DevBuf *bufs[] = {&ctx->d_seg_tag, &ctx->d_seg_data, &ctx->d_seg_path, &ctx->d_paths, &ctx->d_strokes, &ctx->d_ssub_off,
+                      &ctx->d_ssub_job, &ctx->d_stag, &ctx->d_sdata, &ctx->d_sseg_job, &ctx->d_paints, &ctx->d_stops,
+                      &ctx->d_matrices, &ctx->d_weights, &ctx->d_scounts, &ctx->d_soffs, &ctx->d_scan_tmp, &ctx->d_pool,
+                      &ctx->d_sbound, &ctx->d_sout_off, &ctx->d_sout_total, &ctx->d_otag, &ctx->d_odata, &ctx->d_opath,
+                      &ctx->d_osub, &ctx->d_ocount, &ctx->d_edges, &ctx->d_edge_path, &ctx->d_minmax, &ctx->d_boxes,
+                      &ctx->d_minmax_f64, &ctx->d_status, &ctx->d_masks, &ctx->d_band_cnt, &ctx->d_band_off,
+                      &ctx->d_band_cur, &ctx->d_bin_edges, &ctx->d_cov, &ctx->d_layers, &ctx->d_ops, &ctx->d_srcs,
+                      &ctx->d_focal_jobs, &ctx->d_focal_flags, &ctx->d_canvas, &ctx->d_q};
+    for (DevBuf *b : bufs)
+        b->release();
+    ctx->pin_boxes.release(), ctx->pin_status.release(), ctx->pin_plan.release(), ctx->pin_out.release();
+    for (auto &e : ctx->ev)
+        if (e)
+            cudaEventDestroy(e);
+    if (ctx->own_stream)
+        cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+const char *svgr_last_error(svgr_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int svgr_render(svgr_ctx *ctx, const svgr_program *prog, void *stream, int stop_after, uint8_t *out, int out_on_device,
+                int timing, svgr_stats *stats)
+{
+    if (!ctx)
+        return SVGR_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->own_stream;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (timing) {
+        cudaEventCreate(&e0), cudaEventCreate(&e1);
+        cudaEventRecord(e0, s);
+    }
+    int rc = load_program(ctx, prog, s);
+    if (timing)
+        cudaEventRecord(e1, s);
+    if (rc == SVGR_OK)
+        rc = run_pipeline(ctx, s, stop_after, out, out_on_device, timing, stats);
+    if (timing) {
+        if (rc == SVGR_OK && stats) {
+            stats->ms_h2d = ev_ms(e0, e1);
+            stats->ms_total += stats->ms_h2d;
+        }
+        cudaEventDestroy(e0), cudaEventDestroy(e1);
+    }
+    return rc;
+}
+
+int svgr_render_resident(svgr_ctx *ctx, void *stream, uint8_t *out_device, int timing, svgr_stats *stats)
+{
+    if (!ctx)
+        return SVGR_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->own_stream;
+    return run_pipeline(ctx, s, SVGR_STOP_NONE, out_device, 1, timing, stats);
+}
+
+int svgr_read_edges(svgr_ctx *ctx, double *edges, uint32_t *edge_path, int64_t cap, int64_t *n_edges)
+{
+    if (!ctx || !n_edges)
+        return SVGR_E_INVALID;
+    *n_edges = ctx->n_edges;
+    int64_t n = std::min<int64_t>(cap, ctx->n_edges);
+    if (n > 0 && edges)
+        CK(cudaMemcpy(edges, ctx->d_edges.p, (size_t)n * 32, cudaMemcpyDeviceToHost));
+    if (n > 0 && edge_path)
+        CK(cudaMemcpy(edge_path, ctx->d_edge_path.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return SVGR_OK;
+}
+
+int svgr_read_boxes(svgr_ctx *ctx, int32_t *boxes, double *minmax)
+{
+    if (!ctx || !boxes)
+        return SVGR_E_INVALID;
+    if ((int)ctx->h_boxes.size() != ctx->n_path)
+        FAIL(SVGR_E_INVALID, "no flatten result to read");
+    if (ctx->n_path > 0)
+        memcpy(boxes, ctx->h_boxes.data(), (size_t)ctx->n_path * sizeof(PathBox));
+    if (minmax && ctx->n_path > 0)
+        CK(cudaMemcpy(minmax, ctx->d_minmax_f64.p, (size_t)ctx->n_path * 32, cudaMemcpyDeviceToHost));
+    return SVGR_OK;
+}
+
+int svgr_read_mask(svgr_ctx *ctx, int32_t path, float *out)
+{
+    if (!ctx || !out)
+        return SVGR_E_INVALID;
+    if (!ctx->covered || path < 0 || path >= ctx->n_path)
+        FAIL(SVGR_E_INVALID, "no coverage result for this path");
+    const MaskRec &m = ctx->h_masks[path];
+    if (m.rows <= 0 || m.cols <= 0)
+        return SVGR_OK;
+    CK(cudaMemcpy2D(out, (size_t)m.cols * 4, ctx->d_cov.as<float>() + m.off, (size_t)m.stride * 4, (size_t)m.cols * 4,
+                    m.rows, cudaMemcpyDeviceToHost));
+    return SVGR_OK;
+}
+
+int svgr_read_bins(svgr_ctx *ctx, int32_t path, int32_t *band_off, uint32_t *bin_edges, int64_t cap, int64_t *n_binned)
+{
+    if (!ctx || !band_off || !n_binned)
+        return SVGR_E_INVALID;
+    if (!ctx->covered || path < 0 || path >= ctx->n_path)
+        FAIL(SVGR_E_INVALID, "no binning result for this path");
+    const MaskRec &m = ctx->h_masks[path];
+    int nb = m.rows > 0 ? ceil_div(m.rows, SVGR_BAND_ROWS) : 0;
+    std::vector<int> off(nb + 1, 0);
+    if (nb > 0)
+        CK(cudaMemcpy(off.data(), ctx->d_band_off.as<int>() + m.band_base, (size_t)(nb + 1) * 4, cudaMemcpyDeviceToHost));
+    int base = off[0];
+    for (int i = 0; i <= nb; i++)
+        band_off[i] = off[i] - base;
+    *n_binned = off[nb] - base;
+    int64_t n = std::min<int64_t>(cap, *n_binned);
+    if (n > 0 && bin_edges)
+        CK(cudaMemcpy(bin_edges, ctx->d_bin_edges.as<uint32_t>() + base, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return SVGR_OK;
+}
+
+int svgr_read_outline(svgr_ctx *ctx, uint8_t *tag, double *data, uint32_t *path, int32_t *sub, int64_t cap,
+                      int64_t *n_segs)
+{
+    if (!ctx || !n_segs)
+        return SVGR_E_INVALID;
+    StatusBlock st = *(StatusBlock *)ctx->pin_status.p;
+    int64_t total = ctx->n_stroke_seg > 0 ? st.outline_count : 0;
+    *n_segs = total;
+    int64_t n = std::min<int64_t>(cap, total);
+    if (n > 0) {
+        if (tag)
+            CK(cudaMemcpy(tag, ctx->d_otag.p, (size_t)n, cudaMemcpyDeviceToHost));
+        if (data)
+            CK(cudaMemcpy(data, ctx->d_odata.p, (size_t)n * 64, cudaMemcpyDeviceToHost));
+        if (path)
+            CK(cudaMemcpy(path, ctx->d_opath.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+        if (sub)
+            CK(cudaMemcpy(sub, ctx->d_osub.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    }
+    return SVGR_OK;
+}
+
+int svgr_node_info(svgr_ctx *ctx, int32_t node, int32_t *info)
+{
+    if (!ctx || !info)
+        return SVGR_E_INVALID;
+    if (!ctx->planned || node < 0 || node >= ctx->n_node)
+        FAIL(SVGR_E_INVALID, "no plan / bad node index");
+    const Val &v = ctx->vals[node];
+    info[0] = v.kind == VAL_EMPTY ? 0 : (v.one_channel() ? 2 : 1);
+    info[1] = v.r0, info[2] = v.c0, info[3] = v.rows, info[4] = v.cols;
+    info[5] = v.pre, info[6] = v.lin;
+    info[7] = (v.kind == SRC_COVPAINT || v.mul != 1.0f) ? 1 : 0;  // 1: not materialised, svgr_read_node refuses
+    return SVGR_OK;
+}
+
+int svgr_read_node(svgr_ctx *ctx, int32_t node, float *out)
+{
+    if (!ctx || !out)
+        return SVGR_E_INVALID;
+    if (!ctx->composed || node < 0 || node >= ctx->n_node)
+        FAIL(SVGR_E_INVALID, "no render result / bad node index");
+    const Val &v = ctx->vals[node];
+    if (v.kind == VAL_EMPTY)
+        return SVGR_OK;
+    if (v.kind == SRC_COVPAINT || v.mul != 1.0f)
+        FAIL(SVGR_E_INVALID, "node is not materialised (set flags bit 1 on it)");
+    if (v.kind == SRC_L4) {
+        CK(cudaMemcpy(out, ctx->d_layers.as<float>() + v.off, (size_t)v.rows * v.cols * 16, cudaMemcpyDeviceToHost));
+    } else {
+        const float *base = (v.kind == SRC_COV ? ctx->d_cov.as<float>() : ctx->d_layers.as<float>()) + v.off;
+        CK(cudaMemcpy2D(out, (size_t)v.cols * 4, base, (size_t)v.stride * 4, (size_t)v.cols * 4, v.rows,
+                        cudaMemcpyDeviceToHost));
+    }
+    return SVGR_OK;
+}
+
+int svgr_cloud_bounds(svgr_ctx *ctx, int32_t n_query, const int32_t *q_off, const int32_t *q_paths, const double *q_inv,
+                      double *out)
+{
+    if (!ctx || n_query < 0 || (n_query > 0 && (!q_off || !q_paths || !q_inv || !out)))
+        return SVGR_E_INVALID;
+    if (n_query == 0)
+        return SVGR_OK;
+    if ((int)ctx->h_boxes.size() != ctx->n_path)
+        FAIL(SVGR_E_INVALID, "no flatten result");
+    CK(cudaSetDevice(ctx->device));
+    // invert the query -> paths lists into a CSR path -> queries
+    std::vector<int> pq_off(ctx->n_path + 1, 0);
+    for (int q = 0; q < n_query; q++)
+        for (int j = q_off[q]; j < q_off[q + 1]; j++) {
+            if (q_paths[j] < 0 || q_paths[j] >= ctx->n_path)
+                FAIL(SVGR_E_INVALID, "cloud query: bad path index");
+            pq_off[q_paths[j] + 1]++;
+        }
+    for (int i = 0; i < ctx->n_path; i++)
+        pq_off[i + 1] += pq_off[i];
+    std::vector<int> pq_idx(std::max(pq_off[ctx->n_path], 1)), cur(pq_off.begin(), pq_off.end() - 1);
+    for (int q = 0; q < n_query; q++)
+        for (int j = q_off[q]; j < q_off[q + 1]; j++)
+            pq_idx[cur[q_paths[j]]++] = q;
+    size_t b_off = pq_off.size() * 4, b_idx = pq_idx.size() * 4, b_inv = (size_t)n_query * 48, b_mm = (size_t)n_query * 32;
+    size_t a_idx = (b_off + 15) & ~15ull, a_inv = (a_idx + b_idx + 15) & ~15ull, a_mm = a_inv + b_inv, a_out = a_mm + b_mm;
+    CK(ctx->d_q.ensure(a_out + b_mm));
+    char *d = (char *)ctx->d_q.p;
+    cudaStream_t s = ctx->own_stream;
+    CK(cudaMemcpyAsync(d, pq_off.data(), b_off, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d + a_idx, pq_idx.data(), b_idx, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d + a_inv, q_inv, b_inv, cudaMemcpyHostToDevice, s));
+    svgr_launch_cloud_bounds(ctx->d_edges.as<double>(), ctx->d_edge_path.as<uint32_t>(),
+                             &ctx->d_status.as<StatusBlock>()->n_edges, (unsigned long long)ctx->edge_cap, (int *)d,
+                             (int *)(d + a_idx), (double *)(d + a_inv), (unsigned long long *)(d + a_mm),
+                             (double *)(d + a_out), n_query, ctx->sm_count, s);
+    CK(cudaMemcpyAsync(out, d + a_out, b_mm, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return SVGR_OK;
+}
+
+int64_t svgr_arc_to_cubics(double cx, double cy, double rx, double ry, double phi, double eta, double eta_delta,
+                           double *out, int64_t cap)
+{
+    // arc_to_bezier3 (svgrasterize.py:2355-2394): pieces of at most pi/4; np.linspace gives
+    // eta_i = i*step + eta with the last one forced to eta + delta; 2x2 . vec = fma(M0, u, M1*v)
+    const double c = cos(phi), sn = sin(phi);
+    const double M[2][2] = {{c, -sn}, {sn, c}};
+    const double max_angle = M_PI / 4;
+    double cnt_f = ceil(fabs(eta_delta) / max_angle);
+    if (!(cnt_f >= 0) || cnt_f > (double)cap)
+        return SVGR_E_INVALID;
+    int64_t count = (int64_t)cnt_f;
+    double stop = eta + eta_delta;
+    double step = count > 0 ? (stop - eta) / (double)count : 0.0;
+    for (int64_t i = 0; i < count; i++) {
+        double e1 = (double)i * step + eta;
+        double e2 = (i + 1 == count) ? stop : (double)(i + 1) * step + eta;
+        double t = tan((e2 - e1) / 2);
+        double sq = sqrt(4 + 3 * (t * t));
+        double alpha = sin(e2 - e1) * (sq - 1) / 3;
+        double u, v, p0[2], p3[2], d1[2], d2[2];
+        u = rx * cos(e1), v = ry * sin(e1);
+        p0[0] = fma(M[0][0], u, M[0][1] * v) + cx, p0[1] = fma(M[1][0], u, M[1][1] * v) + cy;
+        u = rx * cos(e2), v = ry * sin(e2);
+        p3[0] = fma(M[0][0], u, M[0][1] * v) + cx, p3[1] = fma(M[1][0], u, M[1][1] * v) + cy;
+        u = -rx * sin(e1), v = ry * cos(e1);
+        d1[0] = fma(M[0][0], u, M[0][1] * v), d1[1] = fma(M[1][0], u, M[1][1] * v);
+        u = -rx * sin(e2), v = ry * cos(e2);
+        d2[0] = fma(M[0][0], u, M[0][1] * v), d2[1] = fma(M[1][0], u, M[1][1] * v);
+        double *o = out + 8 * i;
+        o[0] = p0[0], o[1] = p0[1];
+        o[2] = p0[0] + alpha * d1[0], o[3] = p0[1] + alpha * d1[1];
+        o[4] = p3[0] - alpha * d2[0], o[5] = p3[1] - alpha * d2[1];
+        o[6] = p3[0], o[7] = p3[1];
+    }
+    return count;
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

@@ -1,0 +1,427 @@
+// k_coverage.cu -- edge binning + anti-aliased coverage (subsystem 2 of the hot path).
+//
+// Replaces, for every path of a batch at once:
+//   line_signed_coverage   svgrasterize.py:2213-2304 (pure-Python scalar loop, the #1 cost)
+//   np.cumsum + fill rule  svgrasterize.py:983-990
+//
+// Layout: every path owns a float32 mask (rows x stride, stride = cols rounded
+// up to 4 floats so that rows start 16-byte aligned) inside the coverage arena.
+// A mask is cut into bands of SVGR_BAND_ROWS rows; edges are binned to the bands
+// whose rows they cross (count -> scan -> fill), and one CTA renders one tile =
+// (band, chunk of SVGR_TILE_COLS columns):
+//   1. signed-area deltas of the band's edges are accumulated into a shared-memory
+//      trace tile (float32 shared atomics; the edge arithmetic itself is float64),
+//   2. each warp prefix-sums rows with register scans + warp shuffles,
+//   3. the fill rule and the 1e-6 snap are applied and the row leaves as 128-bit stores.
+// The trace never touches HBM: traffic is 36 B per binned edge in, 4 B per pixel out.
+//
+// Column chunks are independent because of the reference's own clamp rule
+// (SURVEY A7): coverage that falls left of column 0 is accumulated INTO column
+// 0; a chunk treats everything left of it the same way, which is exactly the
+// running winding number the prefix sum would have carried in.
+#include "svgr_kernels.h"
+
+#define COV_THREADS 128
+
+// ---------------------------------------------------------------------------------------------
+// generic exclusive scan of int32 (count -> offset), three phases
+// ---------------------------------------------------------------------------------------------
+#define SCAN_THREADS 256
+#define SCAN_ITEMS 8
+#define SCAN_BLOCK (SCAN_THREADS * SCAN_ITEMS)
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int *total, int *sh)
+{
+    // sh: 32 ints
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o)
+            incl += t;
+    }
+    if (lane == 31)
+        sh[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        int s = lane < (blockDim.x >> 5) ? sh[lane] : 0;
+        int si = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, si, o);
+            if (lane >= o)
+                si += t;
+        }
+        sh[lane] = si - s;
+        if (lane == 31)
+            sh[32] = si;
+    }
+    __syncthreads();
+    int res = incl - v + sh[w];
+    *total = sh[32];
+    __syncthreads();
+    return res;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_local_kernel(const int *__restrict__ in, int *__restrict__ out,
+                                                                  int *__restrict__ block_sums, long long n)
+{
+    __shared__ int sh[33];
+    long long base = (long long)blockIdx.x * SCAN_BLOCK + (long long)threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS];
+    int sum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        v[k] = (base + k < n) ? in[base + k] : 0;
+        sum += v[k];
+    }
+    int total;
+    int ex = block_exclusive_scan(sum, &total, sh);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        if (base + k < n)
+            out[base + k] = ex;
+        ex += v[k];
+    }
+    if (threadIdx.x == 0)
+        block_sums[blockIdx.x] = total;
+}
+
+// single block: scans up to any number of block sums sequentially in chunks
+__global__ void __launch_bounds__(SCAN_THREADS) scan_sums_kernel(int *__restrict__ sums, int nb, int *__restrict__ total_out)
+{
+    __shared__ int sh[33];
+    int carry = 0;
+    for (int base = 0; base < nb; base += SCAN_THREADS) {
+        int i = base + threadIdx.x;
+        int v = i < nb ? sums[i] : 0;
+        int total;
+        int ex = block_exclusive_scan(v, &total, sh);
+        if (i < nb)
+            sums[i] = ex + carry;
+        carry += total;
+    }
+    if (threadIdx.x == 0 && total_out)
+        *total_out = carry;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_add_kernel(int *__restrict__ out, const int *__restrict__ block_sums,
+                                                                long long n)
+{
+    long long base = (long long)blockIdx.x * SCAN_BLOCK + (long long)threadIdx.x * SCAN_ITEMS;
+    int add = block_sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++)
+        if (base + k < n)
+            out[base + k] += add;
+}
+
+// out[i] = sum(in[0..i)); out has n entries; *total_out = sum of all (may be null). tmp: ceil(n / SCAN_BLOCK) ints.
+void svgr_launch_exclusive_scan(const int *in, int *out, long long n, int *tmp, int *total_out, cudaStream_t s)
+{
+    if (n <= 0) {
+        if (total_out)
+            cudaMemsetAsync(total_out, 0, sizeof(int), s);
+        return;
+    }
+    int nb = (int)((n + SCAN_BLOCK - 1) / SCAN_BLOCK);
+    scan_local_kernel<<<nb, SCAN_THREADS, 0, s>>>(in, out, tmp, n);
+    scan_sums_kernel<<<1, SCAN_THREADS, 0, s>>>(tmp, nb, total_out);
+    if (nb > 1)
+        scan_add_kernel<<<nb, SCAN_THREADS, 0, s>>>(out, tmp, n);
+}
+
+// ---------------------------------------------------------------------------------------------
+// binning
+// ---------------------------------------------------------------------------------------------
+struct EdgeRows {
+    int y0, y1;  // mask-local row range [y0, y1) the edge writes to (empty if y0 >= y1)
+};
+
+// Rows of the mask that line_signed_coverage visits for this edge (svgrasterize.py:2232-2243),
+// plus a conservative cull of edges that lie entirely right of the mask (every write would hit
+// the `index >= w: continue` rule).
+__device__ __forceinline__ EdgeRows edge_rows(double er0, double ec0, double er1, double ec1, const MaskRec &m)
+{
+    EdgeRows out = {0, 0};
+    if (m.rows <= 0 || m.cols <= 0)
+        return out;
+    double r0 = er0 - (double)m.r0, r1 = er1 - (double)m.r0;
+    if (r0 == r1 || !(r0 == r0) || !(r1 == r1))
+        return out;
+    if (r0 > r1) {
+        double t = r0;
+        r0 = r1, r1 = t;
+    }
+    double c0 = ec0 - (double)m.c0, c1 = ec1 - (double)m.c0;
+    double cmin = c0 < c1 ? c0 : c1;
+    if (cmin >= (double)m.cols + 1.0)
+        return out;
+    double ys = r0 > 0.0 ? r0 : 0.0;
+    if (ys >= (double)m.rows)
+        return out;
+    double ye = ceil(r1);
+    out.y0 = (int)ys;
+    out.y1 = ye < (double)m.rows ? (int)ye : m.rows;
+    if (out.y1 < 0)
+        out.y1 = 0;
+    return out;
+}
+
+__global__ void bin_count_kernel(const double *__restrict__ edges, const uint32_t *__restrict__ edge_path,
+                                 unsigned long long n_edges, const MaskRec *__restrict__ masks,
+                                 int *__restrict__ band_count)
+{
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n_edges;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const double2 *e = reinterpret_cast<const double2 *>(edges + 4 * i);
+        double2 a = e[0], b = e[1];
+        const MaskRec &m = masks[edge_path[i]];
+        EdgeRows er = edge_rows(a.x, a.y, b.x, b.y, m);
+        if (er.y0 >= er.y1)
+            continue;
+        int b0 = er.y0 / SVGR_BAND_ROWS, b1 = (er.y1 - 1) / SVGR_BAND_ROWS;
+        for (int k = b0; k <= b1; k++)
+            atomicAdd(band_count + m.band_base + k, 1);
+    }
+}
+
+__global__ void bin_fill_kernel(const double *__restrict__ edges, const uint32_t *__restrict__ edge_path,
+                                unsigned long long n_edges, const MaskRec *__restrict__ masks,
+                                const int *__restrict__ band_off, int *__restrict__ band_cursor,
+                                uint32_t *__restrict__ bin_edges)
+{
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n_edges;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const double2 *e = reinterpret_cast<const double2 *>(edges + 4 * i);
+        double2 a = e[0], b = e[1];
+        const MaskRec &m = masks[edge_path[i]];
+        EdgeRows er = edge_rows(a.x, a.y, b.x, b.y, m);
+        if (er.y0 >= er.y1)
+            continue;
+        int b0 = er.y0 / SVGR_BAND_ROWS, b1 = (er.y1 - 1) / SVGR_BAND_ROWS;
+        for (int k = b0; k <= b1; k++) {
+            int band = m.band_base + k;
+            int pos = atomicAdd(band_cursor + band, 1);
+            bin_edges[band_off[band] + pos] = (uint32_t)i;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// coverage
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void put(float *row, int w, long long ix, double val)
+{
+    // index >= w dropped, index < 0 accumulated into column 0 (svgrasterize.py:2262 etc.)
+    if (ix >= w)
+        return;
+    atomicAdd(row + (ix > 0 ? (int)ix : 0), (float)val);
+}
+
+// One row crossing of one edge (svgrasterize.py:2244-2303), columns local to the tile.
+__device__ __forceinline__ void edge_row(float *row, int w, double x, double x_next, double d)
+{
+    double x0 = x, x1 = x_next;
+    if (!(x < x_next))
+        x0 = x_next, x1 = x;
+    double x0_floor = floor(x0), x1_ceil = ceil(x1);
+    if (x1_ceil <= 0.0) {  // whole span left of the tile: the deltas sum to d, all into column 0
+        atomicAdd(row, (float)d);
+        return;
+    }
+    if (x0_floor >= (double)w)
+        return;
+    long long x0i = (long long)x0_floor, x1i = (long long)x1_ceil;
+    if (x1i <= x0i + 1) {
+        double xmf = 0.5 * (x + x_next) - x0_floor;
+        put(row, w, x0i, d * (1.0 - xmf));
+        put(row, w, x0i + 1, d * xmf);
+        return;
+    }
+    double s = 1.0 / (x1 - x0);
+    double x0f = x0 - x0_floor;
+    double x1f = x1 - x1_ceil + 1.0;
+    double a0 = 0.5 * s * ((1.0 - x0f) * (1.0 - x0f));
+    double am = 0.5 * s * (x1f * x1f);
+    put(row, w, x0i, d * a0);
+    if (x1i == x0i + 2) {
+        put(row, w, x0i + 1, d * (1.0 - a0 - am));
+    } else {
+        double a1 = s * (1.5 - x0f);
+        put(row, w, x0i + 1, d * (a1 - a0));
+        double ds = d * s;
+        long long lo = x0i + 2, hi = x1i - 1;  // interior columns [lo, hi)
+        if (lo < 0) {
+            long long neg_end = hi < 0 ? hi : 0;
+            if (neg_end > lo)
+                atomicAdd(row, (float)((double)(neg_end - lo) * ds));
+            lo = neg_end > lo ? neg_end : lo;
+        }
+        if (hi > w)
+            hi = w;
+        float fds = (float)ds;
+        for (long long xi = lo; xi < hi; xi++)
+            atomicAdd(row + xi, fds);
+        double a2 = a1 + (double)(x1i - x0i - 3) * s;
+        put(row, w, x1i - 1, d * (1.0 - a2 - am));
+    }
+    put(row, w, x1i, d * am);
+}
+
+__device__ __forceinline__ float fill_rule_apply(float m, int rule)
+{
+    float v;
+    if (rule == 0) {
+        v = fminf(fabsf(m), 1.0f);
+    } else {
+        float r = fmodf(m + 1.0f, 2.0f);  // floored modulo of np.remainder
+        if (r < 0.0f)
+            r += 2.0f;
+        v = fabsf(r - 1.0f);
+    }
+    return v < 1e-6f ? 0.0f : v;
+}
+
+__global__ void __launch_bounds__(COV_THREADS)
+coverage_kernel(const double *__restrict__ edges, const MaskRec *__restrict__ masks, int n_masks,
+                const int *__restrict__ band_off, const int *__restrict__ band_cnt,
+                const uint32_t *__restrict__ bin_edges, float *__restrict__ cov)
+{
+    __shared__ __align__(16) float trace[SVGR_BAND_ROWS][SVGR_TILE_COLS];
+    __shared__ int s_mask;
+
+    // ---- tile -> (mask, band, column chunk): binary search in the tile_base prefix
+    const int tile = blockIdx.x;
+    if (threadIdx.x == 0) {
+        int lo = 0, hi = n_masks - 1;
+        while (lo < hi) {
+            int mid = (lo + hi + 1) >> 1;
+            if (masks[mid].tile_base <= tile)
+                lo = mid;
+            else
+                hi = mid - 1;
+        }
+        s_mask = lo;
+    }
+    __syncthreads();
+    const MaskRec m = masks[s_mask];
+    const int local = tile - m.tile_base;
+    const int band_local = local / m.ntile_c;
+    const int chunk = local - band_local * m.ntile_c;
+    const int yb = band_local * SVGR_BAND_ROWS;
+    const int nrows = min(SVGR_BAND_ROWS, m.rows - yb);
+    const int col0 = chunk * SVGR_TILE_COLS;
+    const int w = min(SVGR_TILE_COLS, m.cols - col0);     // columns that exist in the mask
+    const int wpad = min(SVGR_TILE_COLS, m.stride - col0);  // columns that exist in memory (multiple of 4)
+
+    // ---- 1. zero the trace tile
+    {
+        float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 *t4 = reinterpret_cast<float4 *>(&trace[0][0]);
+        for (int i = threadIdx.x; i < SVGR_BAND_ROWS * SVGR_TILE_COLS / 4; i += COV_THREADS)
+            t4[i] = z;
+    }
+    __syncthreads();
+
+    // ---- 2. accumulate the signed areas of this band's edges
+    const int band = m.band_base + band_local;
+    const int e_off = band_off[band], e_cnt = band_cnt[band];
+    for (int i = threadIdx.x; i < e_cnt; i += COV_THREADS) {
+        const double2 *e = reinterpret_cast<const double2 *>(edges + 4ull * bin_edges[e_off + i]);
+        double2 pa = e[0], pb = e[1];
+        double r0 = pa.x - (double)m.r0, c0 = pa.y - (double)m.c0;
+        double r1 = pb.x - (double)m.r0, c1 = pb.y - (double)m.c0;
+        double dir = 1.0;
+        if (!(r0 < r1)) {
+            double t;
+            dir = -1.0;
+            t = r0, r0 = r1, r1 = t;
+            t = c0, c0 = c1, c1 = t;
+        }
+        if (r0 == r1)
+            continue;
+        double dxdy = (c1 - c0) / (r1 - r0);
+        c0 -= (double)col0;
+        double ys = r0 > 0.0 ? r0 : 0.0;
+        int y_first = (int)ys;
+        double yend_f = ceil(r1);
+        int y_last = yend_f < (double)m.rows ? (int)yend_f : m.rows;
+        int ya = max(y_first, yb), yz = min(y_last, yb + nrows);
+        for (int y = ya; y < yz; y++) {
+            double ytop = (double)(y + 1) < r1 ? (double)(y + 1) : r1;
+            double ybot = (double)y > r0 ? (double)y : r0;
+            double dy = ytop - ybot;
+            double x = c0 + dxdy * (ybot - r0);
+            double x_next = x + dxdy * dy;
+            edge_row(trace[y - yb], w, x, x_next, dir * dy);
+        }
+    }
+    __syncthreads();
+
+    // ---- 3. prefix sum along columns, fill rule, 128-bit stores
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int y = warp; y < nrows; y += COV_THREADS / 32) {
+        float carry = 0.f;
+        float *dst = cov + m.off + (long long)(yb + y) * m.stride + col0;
+        for (int cb = 0; cb < wpad; cb += 128) {
+            int c = cb + 4 * lane;
+            float4 v = *reinterpret_cast<const float4 *>(&trace[y][c]);
+            v.y += v.x;
+            v.z += v.y;
+            v.w += v.z;
+            float incl = v.w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                float t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o)
+                    incl += t;
+            }
+            float ex = incl - v.w + carry;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+            if (c < wpad) {
+                float4 o4;
+                o4.x = fill_rule_apply(v.x + ex, m.fill_rule);
+                o4.y = fill_rule_apply(v.y + ex, m.fill_rule);
+                o4.z = fill_rule_apply(v.z + ex, m.fill_rule);
+                o4.w = fill_rule_apply(v.w + ex, m.fill_rule);
+                *reinterpret_cast<float4 *>(dst + c) = o4;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------------------------
+void svgr_launch_bin_count(const double *edges, const uint32_t *edge_path, unsigned long long n_edges,
+                           const MaskRec *masks, int *band_count, int sm_count, cudaStream_t s)
+{
+    if (n_edges == 0)
+        return;
+    unsigned long long blocks = (n_edges + 255) / 256;
+    if (blocks > (unsigned long long)sm_count * 16)
+        blocks = (unsigned long long)sm_count * 16;
+    bin_count_kernel<<<(unsigned)blocks, 256, 0, s>>>(edges, edge_path, n_edges, masks, band_count);
+}
+
+void svgr_launch_bin_fill(const double *edges, const uint32_t *edge_path, unsigned long long n_edges,
+                          const MaskRec *masks, const int *band_off, int *band_cursor, uint32_t *bin_edges,
+                          int sm_count, cudaStream_t s)
+{
+    if (n_edges == 0)
+        return;
+    unsigned long long blocks = (n_edges + 255) / 256;
+    if (blocks > (unsigned long long)sm_count * 16)
+        blocks = (unsigned long long)sm_count * 16;
+    bin_fill_kernel<<<(unsigned)blocks, 256, 0, s>>>(edges, edge_path, n_edges, masks, band_off, band_cursor, bin_edges);
+}
+
+void svgr_launch_coverage(const double *edges, const MaskRec *masks, int n_masks, int n_tiles, const int *band_off,
+                          const int *band_cnt, const uint32_t *bin_edges, float *cov, cudaStream_t s)
+{
+    if (n_tiles <= 0)
+        return;
+    coverage_kernel<<<n_tiles, COV_THREADS, 0, s>>>(edges, masks, n_masks, band_off, band_cnt, bin_edges, cov);
+}

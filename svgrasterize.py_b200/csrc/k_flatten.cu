@@ -1,0 +1,364 @@
+// k_flatten.cu -- curve flattening + path bounds (subsystem 1 of the hot path).
+//
+// Replaces, for a whole batch of paths in one launch:
+//   Path.mask segment loop           svgrasterize.py:930-945
+//   bezier2_to_bezier3               svgrasterize.py:2182-2184 (matrix :2052)
+//   Transform.__call__               svgrasterize.py:531-534
+//   bezier3_flatness_batch           svgrasterize.py:2071-2088
+//   bezier3_split_batch              svgrasterize.py:2066-2068
+//   bezier3_flatten_batch            svgrasterize.py:2091-2098
+//   mask sizing                      svgrasterize.py:961-975
+//
+// Bit-exactness: the reference's numpy contractions run through OpenBLAS with
+// a fixed fused-multiply-add order.  This file is
+// compiled with -fmad=false and spells every fma() explicitly, so each control
+// point, flatness value and emitted end point has the reference's bits.  The
+// edge ORDER differs (the reference is breadth-first per path, this kernel is
+// warp-cooperative depth-first); parity is defined on the per-path multiset.
+//
+// Kernel shape: one warp owns a LIFO work list of cubics in shared memory.
+// Each round every lane pops one cubic, tests flatness, and either emits the
+// chord [p0, p3] (warp-aggregated append to the global edge list) or splits it
+// at t = 1/2 and pushes both halves.  Lanes therefore stay busy regardless of
+// how unevenly the subdivision depth is distributed over the input curves.
+#include "svgr_kernels.h"
+
+#define FLAT_WARPS 4
+#define FLAT_Q 160       // work-list slots per warp
+#define FLAT_MAXD 24     // subdivision depth cap (the reference has none and spins on NaN)
+#define FLAT_QCAP (FLAT_Q - FLAT_MAXD)
+
+__device__ __forceinline__ double dot4(double m0, double m1, double m2, double m3, double b0, double b1, double b2,
+                                       double b3)
+{
+    // strided ddot with two accumulators: fma(m0,b0, m2*b2) + fma(m1,b1, m3*b3)
+    return fma(m0, b0, m2 * b2) + fma(m1, b1, m3 * b3);
+}
+
+__device__ __forceinline__ unsigned long long key_of(double v)
+{
+    // order-preserving map double -> u64
+    long long b = __double_as_longlong(v);
+    return b < 0 ? ~(unsigned long long)b : ((unsigned long long)b | 0x8000000000000000ull);
+}
+
+__device__ __forceinline__ double of_key(unsigned long long k)
+{
+    long long b = (k & 0x8000000000000000ull) ? (long long)(k & 0x7fffffffffffffffull) : (long long)~k;
+    return __longlong_as_double(b);
+}
+
+// minmax[path] = {min r, min c, max r, max c} as ordered keys
+__device__ __forceinline__ void bounds_update(unsigned long long *minmax, uint32_t path, double r0, double c0,
+                                              double r1, double c1)
+{
+    unsigned long long *mm = minmax + 4ull * path;
+    atomicMin(mm + 0, key_of(r0 < r1 ? r0 : r1));
+    atomicMin(mm + 1, key_of(c0 < c1 ? c0 : c1));
+    atomicMax(mm + 2, key_of(r0 < r1 ? r1 : r0));
+    atomicMax(mm + 3, key_of(c0 < c1 ? c1 : c0));
+}
+
+__device__ __forceinline__ void emit_edges(bool has, double r0, double c0, double r1, double c1, uint32_t path,
+                                           double *edges, uint32_t *edge_path, unsigned long long cap,
+                                           unsigned long long *n_edges, unsigned long long *minmax, int lane)
+{
+    unsigned m = __ballot_sync(0xffffffffu, has);
+    if (!m)
+        return;
+    unsigned long long base = 0;
+    int leader = __ffs(m) - 1;
+    if (lane == leader)
+        base = atomicAdd(n_edges, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (has) {
+        unsigned long long idx = base + __popc(m & ((1u << lane) - 1));
+        if (idx < cap) {
+            double2 *e = reinterpret_cast<double2 *>(edges + 4 * idx);
+            e[0] = make_double2(r0, c0);
+            e[1] = make_double2(r1, c1);
+            edge_path[idx] = path;
+        }
+        bounds_update(minmax, path, r0, c0, r1, c1);
+    }
+}
+
+__global__ void __launch_bounds__(FLAT_WARPS * 32)
+flatten_kernel(const uint8_t *__restrict__ seg_tag, const double *__restrict__ seg_data,
+               const uint32_t *__restrict__ seg_path, long long n_seg_host, const int *__restrict__ n_seg_dev,
+               const PathRec *__restrict__ paths, double thr, double *__restrict__ edges,
+               uint32_t *__restrict__ edge_path, unsigned long long cap, unsigned long long *n_edges,
+               unsigned long long *minmax)
+{
+    __shared__ double st[FLAT_WARPS][8][FLAT_Q];
+    __shared__ uint32_t st_path[FLAT_WARPS][FLAT_Q];
+    __shared__ uint8_t st_depth[FLAT_WARPS][FLAT_Q];
+
+    const int lane = threadIdx.x & 31;
+    const int w = threadIdx.x >> 5;
+    long long n_seg = n_seg_host;
+    if (n_seg_dev) {
+        long long nd = *n_seg_dev;
+        n_seg = nd < n_seg ? nd : n_seg;
+    }
+    const long long n_chunks = (n_seg + 31) >> 5;
+    long long chunk = (long long)blockIdx.x * FLAT_WARPS + w;
+    const long long chunk_step = (long long)gridDim.x * FLAT_WARPS;
+    int count = 0;
+
+    for (;;) {
+        // ---- refill: take the next 32 segments while there is room for 32 cubics
+        if (count <= FLAT_QCAP - 64 && chunk < n_chunks) {
+            long long i = (chunk << 5) + lane;
+            chunk += chunk_step;
+            int tag = SEG_NOP;
+            double p[8];
+            uint32_t path = 0;
+            if (i < n_seg)
+                tag = seg_tag[i];
+            bool is_line = tag == SEG_LINE || tag == SEG_CLOSED || tag == SEG_UNCLOSED;
+            bool is_curve = tag == SEG_QUAD || tag == SEG_CUBIC;
+            if (is_line || is_curve) {
+                const double2 *d = reinterpret_cast<const double2 *>(seg_data + 8 * i);
+                double2 a = d[0], b = d[1];
+                p[0] = a.x, p[1] = a.y, p[2] = b.x, p[3] = b.y;
+                if (is_curve) {
+                    double2 c = d[2], e = d[3];
+                    p[4] = c.x, p[5] = c.y, p[6] = e.x, p[7] = e.y;
+                }
+                path = seg_path[i];
+                if (tag == SEG_QUAD) {
+                    // bezier2_to_bezier3: out = fma(m2,p2, fma(m1,p1, m0*p0)), rows of
+                    // [[1,0,0],[1/3,2/3,0],[0,2/3,1/3],[0,0,1]]
+                    const double t1 = 1.0 / 3, t2 = 2.0 / 3;
+                    double q[6] = {p[0], p[1], p[2], p[3], p[4], p[5]};
+#pragma unroll
+                    for (int k = 0; k < 2; k++) {
+                        p[0 + k] = fma(0.0, q[4 + k], fma(0.0, q[2 + k], 1.0 * q[k]));
+                        p[2 + k] = fma(0.0, q[4 + k], fma(t2, q[2 + k], t1 * q[k]));
+                        p[4 + k] = fma(t1, q[4 + k], fma(t2, q[2 + k], 0.0 * q[k]));
+                        p[6 + k] = fma(1.0, q[4 + k], fma(0.0, q[2 + k], 0.0 * q[k]));
+                    }
+                }
+                // Transform.__call__: out_c = fma(y, M[c][1], x*M[c][0]) + M[c][2]
+                const double *m = paths[path].m;
+                double m0 = m[0], m1 = m[1], m2 = m[2], m3 = m[3], m4 = m[4], m5 = m[5];
+                int np = is_line ? 2 : 4;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (k < np) {
+                        double x = p[2 * k], y = p[2 * k + 1];
+                        p[2 * k] = fma(y, m1, x * m0) + m2;
+                        p[2 * k + 1] = fma(y, m4, x * m3) + m5;
+                    }
+                }
+            }
+            emit_edges(is_line, p[0], p[1], p[2], p[3], path, edges, edge_path, cap, n_edges, minmax, lane);
+            unsigned mc = __ballot_sync(0xffffffffu, is_curve);
+            if (is_curve) {
+                int pos = count + __popc(mc & ((1u << lane) - 1));
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    st[w][k][pos] = p[k];
+                st_path[w][pos] = path;
+                st_depth[w][pos] = 0;
+            }
+            count += __popc(mc);
+            __syncwarp();
+            continue;
+        }
+        if (count == 0)
+            break;
+
+        // ---- pop up to 32 cubics from the top of the list
+        int room = FLAT_QCAP - count;
+        int k = count < 32 ? count : 32;
+        if (k > room)
+            k = room > 1 ? room : 1;  // depth-first on one entry may use the MAXD head-room
+        bool active = lane < k;
+        double c[8];
+        uint32_t path = 0;
+        int depth = 0;
+        if (active) {
+            int pos = count - 1 - lane;
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                c[j] = st[w][j][pos];
+            path = st_path[w][pos];
+            depth = st_depth[w][pos];
+        }
+        count -= k;
+        __syncwarp();
+
+        bool flat = false;
+        if (active) {
+            // bezier3_flatness_batch: rows [-2,3,0,-1] and [-1,0,3,-2]
+            double ux = dot4(-2.0, 3.0, 0.0, -1.0, c[0], c[2], c[4], c[6]);
+            double uy = dot4(-2.0, 3.0, 0.0, -1.0, c[1], c[3], c[5], c[7]);
+            double vx = dot4(-1.0, 0.0, 3.0, -2.0, c[0], c[2], c[4], c[6]);
+            double vy = dot4(-1.0, 0.0, 3.0, -2.0, c[1], c[3], c[5], c[7]);
+            ux = ux * ux, uy = uy * uy, vx = vx * vx, vy = vy * vy;
+            double f = (ux > uy ? ux : uy) + (vx > vy ? vx : vy);
+            flat = (f < thr) || depth >= FLAT_MAXD;
+        }
+        emit_edges(active && flat, c[0], c[1], c[6], c[7], path, edges, edge_path, cap, n_edges, minmax, lane);
+
+        bool split = active && !flat;
+        unsigned ms = __ballot_sync(0xffffffffu, split);
+        if (split) {
+            int pos = count + 2 * __popc(ms & ((1u << lane) - 1));
+            // bezier3_split_batch: rows of the 8x4 de Casteljau matrix, dot4 recipe
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                double b0 = c[j], b1 = c[2 + j], b2 = c[4 + j], b3 = c[6 + j];
+                double mid = dot4(0.125, 0.375, 0.375, 0.125, b0, b1, b2, b3);
+                st[w][0 + j][pos] = dot4(1.0, 0.0, 0.0, 0.0, b0, b1, b2, b3);
+                st[w][2 + j][pos] = dot4(0.5, 0.5, 0.0, 0.0, b0, b1, b2, b3);
+                st[w][4 + j][pos] = dot4(0.25, 0.5, 0.25, 0.0, b0, b1, b2, b3);
+                st[w][6 + j][pos] = mid;
+                st[w][0 + j][pos + 1] = mid;
+                st[w][2 + j][pos + 1] = dot4(0.0, 0.25, 0.5, 0.25, b0, b1, b2, b3);
+                st[w][4 + j][pos + 1] = dot4(0.0, 0.0, 0.5, 0.5, b0, b1, b2, b3);
+                st[w][6 + j][pos + 1] = dot4(0.0, 0.0, 0.0, 1.0, b0, b1, b2, b3);
+            }
+            st_path[w][pos] = path;
+            st_path[w][pos + 1] = path;
+            st_depth[w][pos] = (uint8_t)(depth + 1);
+            st_depth[w][pos + 1] = (uint8_t)(depth + 1);
+        }
+        count += 2 * __popc(ms);
+        __syncwarp();
+    }
+}
+
+__global__ void minmax_init_kernel(unsigned long long *minmax, int n_paths)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_paths) {
+        minmax[4 * i + 0] = ~0ull;
+        minmax[4 * i + 1] = ~0ull;
+        minmax[4 * i + 2] = 0ull;
+        minmax[4 * i + 3] = 0ull;
+    }
+}
+
+// Mask sizing (svgrasterize.py:961-975): floor(min) - 1, ceil(max) + 1, clipped to the viewport.
+__global__ void bounds_kernel(const unsigned long long *__restrict__ minmax, const PathRec *__restrict__ paths,
+                              int n_paths, PathBox *__restrict__ boxes, double *__restrict__ minmax_f64)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_paths)
+        return;
+    PathBox b = {0, 0, 0, 0};
+    if (minmax[4 * i + 0] != ~0ull) {
+        double mn_r = of_key(minmax[4 * i + 0]), mn_c = of_key(minmax[4 * i + 1]);
+        double mx_r = of_key(minmax[4 * i + 2]), mx_c = of_key(minmax[4 * i + 3]);
+        if (minmax_f64) {
+            minmax_f64[4 * i + 0] = mn_r, minmax_f64[4 * i + 1] = mn_c;
+            minmax_f64[4 * i + 2] = mx_r, minmax_f64[4 * i + 3] = mx_c;
+        }
+        const double lim = 1.0e9;  // keep the int conversion defined for wild inputs
+        mn_r = fmax(-lim, fmin(lim, mn_r)), mn_c = fmax(-lim, fmin(lim, mn_c));
+        mx_r = fmax(-lim, fmin(lim, mx_r)), mx_c = fmax(-lim, fmin(lim, mx_c));
+        long long min_r = (long long)floor(mn_r) - 1, min_c = (long long)floor(mn_c) - 1;
+        long long max_r = (long long)ceil(mx_r) + 1, max_c = (long long)ceil(mx_c) + 1;
+        const PathRec &p = paths[i];
+        if (p.has_viewport) {
+            long long vx = p.viewport[0], vy = p.viewport[1], vw = p.viewport[2], vh = p.viewport[3];
+            if (min_r < vx) min_r = vx;
+            if (min_c < vy) min_c = vy;
+            if (max_r > vx + vw) max_r = vx + vw;
+            if (max_c > vy + vh) max_c = vy + vh;
+        }
+        long long rows = max_r - min_r, cols = max_c - min_c;
+        if (rows > 0 && cols > 0) {
+            b.r0 = (int32_t)min_r, b.c0 = (int32_t)min_c;
+            b.rows = (int32_t)(rows < 0x7fffffff ? rows : 0x7fffffff);
+            b.cols = (int32_t)(cols < 0x7fffffff ? cols : 0x7fffffff);
+        }
+    } else if (minmax_f64) {
+        minmax_f64[4 * i + 0] = minmax_f64[4 * i + 1] = minmax_f64[4 * i + 2] = minmax_f64[4 * i + 3] = 0.0;
+    }
+    boxes[i] = b;
+}
+
+// User-space bounding box of a set of paths' end points: ConvexHull.bbox
+// (svgrasterize.py:2002-2007) -- the extremes of transform.invert(points) are
+// attained on hull vertices, so the Graham scan is not needed.  One query =
+// (inverse matrix, list of paths); q_of_path is a CSR path -> queries.
+__global__ void cloud_bounds_kernel(const double *__restrict__ edges, const uint32_t *__restrict__ edge_path,
+                                    const unsigned long long *__restrict__ n_edges, unsigned long long cap,
+                                    const int *__restrict__ pq_off, const int *__restrict__ pq_idx,
+                                    const double *__restrict__ q_inv, unsigned long long *q_minmax)
+{
+    unsigned long long n = *n_edges < cap ? *n_edges : cap;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        uint32_t path = edge_path[i];
+        int a = pq_off[path], b = pq_off[path + 1];
+        if (a == b)
+            continue;
+        const double2 *e = reinterpret_cast<const double2 *>(edges + 4 * i);
+        double2 p0 = e[0], p1 = e[1];
+        for (int j = a; j < b; j++) {
+            int q = pq_idx[j];
+            const double *m = q_inv + 6 * q;
+            double x0 = fma(p0.y, m[1], p0.x * m[0]) + m[2], y0 = fma(p0.y, m[4], p0.x * m[3]) + m[5];
+            double x1 = fma(p1.y, m[1], p1.x * m[0]) + m[2], y1 = fma(p1.y, m[4], p1.x * m[3]) + m[5];
+            bounds_update(q_minmax, (uint32_t)q, x0, y0, x1, y1);
+        }
+    }
+}
+
+__global__ void keys_to_f64_kernel(const unsigned long long *__restrict__ keys, double *__restrict__ out, int n4)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n4) {
+        bool empty = keys[4 * i] == ~0ull;
+        for (int k = 0; k < 4; k++)
+            out[4 * i + k] = empty ? 0.0 : of_key(keys[4 * i + k]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------------------------
+void svgr_launch_minmax_init(unsigned long long *minmax, int n, cudaStream_t s)
+{
+    if (n > 0)
+        minmax_init_kernel<<<(n + 255) / 256, 256, 0, s>>>(minmax, n);
+}
+
+void svgr_launch_flatten(const uint8_t *seg_tag, const double *seg_data, const uint32_t *seg_path, long long n_seg,
+                         const int *n_seg_dev, const PathRec *paths, double thr, double *edges, uint32_t *edge_path,
+                         unsigned long long cap, unsigned long long *n_edges, unsigned long long *minmax, int sm_count,
+                         cudaStream_t s)
+{
+    if (n_seg <= 0)
+        return;
+    long long chunks = (n_seg + 31) / 32;
+    long long blocks = (chunks + FLAT_WARPS - 1) / FLAT_WARPS;
+    long long max_blocks = (long long)sm_count * 8;
+    if (blocks > max_blocks)
+        blocks = max_blocks;
+    flatten_kernel<<<(unsigned)blocks, FLAT_WARPS * 32, 0, s>>>(seg_tag, seg_data, seg_path, n_seg, n_seg_dev, paths, thr,
+                                                                edges, edge_path, cap, n_edges, minmax);
+}
+
+void svgr_launch_bounds(const unsigned long long *minmax, const PathRec *paths, int n_paths, PathBox *boxes,
+                        double *minmax_f64, cudaStream_t s)
+{
+    if (n_paths > 0)
+        bounds_kernel<<<(n_paths + 255) / 256, 256, 0, s>>>(minmax, paths, n_paths, boxes, minmax_f64);
+}
+
+void svgr_launch_cloud_bounds(const double *edges, const uint32_t *edge_path, const unsigned long long *n_edges,
+                              unsigned long long cap, const int *pq_off, const int *pq_idx, const double *q_inv,
+                              unsigned long long *q_minmax, double *q_out, int n_q, int sm_count, cudaStream_t s)
+{
+    if (n_q <= 0)
+        return;
+    minmax_init_kernel<<<(n_q + 255) / 256, 256, 0, s>>>(q_minmax, n_q);
+    cloud_bounds_kernel<<<sm_count * 4, 256, 0, s>>>(edges, edge_path, n_edges, cap, pq_off, pq_idx, q_inv, q_minmax);
+    keys_to_f64_kernel<<<(n_q + 255) / 256, 256, 0, s>>>(q_minmax, q_out, n_q);
+}

@@ -1,0 +1,223 @@
+// svgr_device.cuh -- device helpers shared by the compose and filter kernels:
+// colour-space / alpha conversions (svgrasterize.py:471-503, Layer.convert :129-164),
+// paint evaluation (svgrasterize.py:1553-1650, :1661-1683, pattern gather :1074-1094)
+// and the source fetch that turns any layer-like value into an RGBA pixel.
+#pragma once
+#include "svgr_kernels.h"
+
+
+__device__ __forceinline__ float4 f4(float x, float y, float z, float w) { return make_float4(x, y, z, w); }
+
+__device__ __forceinline__ float clip01(float v) { return fminf(fmaxf(v, 0.f), 1.f); }
+
+__device__ __forceinline__ float lin_to_srgb1(float v)
+{
+    return v <= 0.0031308f ? v * 12.92f : 1.055f * powf(v, 1.0f / 2.4f) - 0.055f;
+}
+
+__device__ __forceinline__ float srgb_to_lin1(float v)
+{
+    return v <= 0.04045f ? v / 12.92f : powf((v + 0.055f) / 1.055f, 2.4f);
+}
+
+// color_pre_to_straight_alpha (svgrasterize.py:471-477): divide where alpha > 1e-4, clip all to [0, 1]
+__device__ __forceinline__ float4 unpremultiply(float4 v)
+{
+    if (v.w > 0.0001f) {
+        v.x = v.x / v.w;
+        v.y = v.y / v.w;
+        v.z = v.z / v.w;
+    }
+    return f4(clip01(v.x), clip01(v.y), clip01(v.z), clip01(v.w));
+}
+
+__device__ __forceinline__ float4 premultiply(float4 v) { return f4(v.x * v.w, v.y * v.w, v.z * v.w, v.w); }
+
+// Layer.convert (svgrasterize.py:129-164) on one RGBA pixel; code = SVGR_CONV(src pre, src lin, dst pre, dst lin)
+__device__ __forceinline__ float4 convert_px(float4 v, int code)
+{
+    bool pre = code & 1, lin = code & 2, tpre = code & 4, tlin = code & 8;
+    if (lin != tlin) {
+        if (pre) {
+            v = unpremultiply(v);
+            pre = false;
+        }
+        if (tlin)
+            v = f4(srgb_to_lin1(v.x), srgb_to_lin1(v.y), srgb_to_lin1(v.z), v.w);
+        else
+            v = f4(lin_to_srgb1(v.x), lin_to_srgb1(v.y), lin_to_srgb1(v.z), v.w);
+    }
+    if (pre != tpre)
+        v = tpre ? premultiply(v) : unpremultiply(v);
+    return v;
+}
+
+__device__ __forceinline__ bool conv_is_identity(int code) { return (code & 3) == ((code >> 2) & 3); }
+
+// np.remainder for doubles (floored modulo)
+__device__ __forceinline__ double floored_mod(double a, double b)
+{
+    double r = fmod(a, b);
+    if (r != 0.0) {
+        if ((r < 0.0) != (b < 0.0))
+            r += b;
+    } else {
+        r = copysign(0.0, b);
+    }
+    return r;
+}
+
+// grad_spread (svgrasterize.py:1661-1668)
+__device__ __forceinline__ double grad_spread(double t, int spread)
+{
+    if (spread == 1) {
+        double ip;
+        return modf(t, &ip);  // keeps the sign: repeat degenerates to pad for t < 0
+    }
+    if (spread == 2)
+        return fabs(floored_mod(t + 1.0, 2.0) - 1.0);
+    return t;
+}
+
+// grad_interpolate (svgrasterize.py:1671-1683); stops premultiplied in the target colour space
+__device__ __forceinline__ float4 grad_color(double v, const StopRec *__restrict__ st, int n)
+{
+    if (v <= st[0].offset)
+        return f4(st[0].color[0], st[0].color[1], st[0].color[2], st[0].color[3]);
+    if (v > st[n - 1].offset)
+        return f4(st[n - 1].color[0], st[n - 1].color[1], st[n - 1].color[2], st[n - 1].color[3]);
+    float4 o = f4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k + 1 < n; k++) {
+        double o0 = st[k].offset, o1 = st[k + 1].offset;
+        if (v > o0 && v <= o1) {
+            float ratio = (float)((v - o0) / (o1 - o0));
+            float ir = 1.0f - ratio;
+            o.x += ir * st[k].color[0] + ratio * st[k + 1].color[0];
+            o.y += ir * st[k].color[1] + ratio * st[k + 1].color[1];
+            o.z += ir * st[k].color[2] + ratio * st[k + 1].color[2];
+            o.w += ir * st[k].color[3] + ratio * st[k + 1].color[3];
+        }
+    }
+    return o;  // NaN offsets match no interval: transparent black
+}
+
+__device__ __forceinline__ void px_to_user(const PaintRec &p, int r, int c, double *ux, double *uy)
+{
+    // grad_pixels (svgrasterize.py:1653-1658): pixel centres; then transform.invert and
+    // the inverse gradientTransform, each as Transform.__call__ (:531-534)
+    double x = (double)r + 0.5, y = (double)c + 0.5;
+    double ax = fma(y, p.m1[1], x * p.m1[0]) + p.m1[2];
+    double ay = fma(y, p.m1[4], x * p.m1[3]) + p.m1[5];
+    if (p.has_m2) {
+        double bx = fma(ay, p.m2[1], ax * p.m2[0]) + p.m2[2];
+        double by = fma(ay, p.m2[4], ax * p.m2[3]) + p.m2[5];
+        ax = bx, ay = by;
+    }
+    *ux = ax, *uy = ay;
+}
+
+// det = b^2 - a c of the two-circle gradient (svgrasterize.py:1612-1620); returns t through *t
+__device__ __forceinline__ double focal_det(const PaintRec &p, double ux, double uy, double *b_out, double *a_out)
+{
+    double cx = p.g[0], cy = p.g[1], radius = p.g[2], fx = p.g[3], fy = p.g[4], fr = p.g[5];
+    double cdx = cx - fx, cdy = cy - fy;
+    double rd = radius - fr;
+    double a = (cdx * cdx + cdy * cdy) - rd * rd;
+    double pdx = ux - fx, pdy = uy - fy;
+    double b = (pdx * cdx + pdy * cdy) + fr * rd;
+    double cc = (pdx * pdx + pdy * pdy) - fr * fr;
+    *b_out = b;
+    *a_out = a;
+    return b * b - a * cc;
+}
+
+// paint colour at the pixel (r, c) (global layer coordinates): premultiplied RGBA
+__device__ __forceinline__ float4 paint_eval(const RenderTables &T, const SrcRec &s, int r, int c)
+{
+    const PaintRec &p = T.paints[s.paint];
+    if (p.kind == PAINT_SOLID)
+        return f4(p.color[0], p.color[1], p.color[2], p.color[3]);
+    double ux, uy;
+    if (p.kind == PAINT_PATTERN) {
+        // Path.fill pattern branch (svgrasterize.py:1074-1094)
+        double x = (double)r + 0.5, y = (double)c + 0.5;
+        double ax = fma(y, p.m1[1], x * p.m1[0]) + p.m1[2];
+        double ay = fma(y, p.m1[4], x * p.m1[3]) + p.m1[5];
+        ax = floored_mod(ax - p.g[0], p.g[2]);
+        ay = floored_mod(ay - p.g[1], p.g[3]);
+        double bx = fma(ay, p.m2[1], ax * p.m2[0]) + p.m2[2];
+        double by = fma(ay, p.m2[4], ax * p.m2[3]) + p.m2[5];
+        long long ir = (long long)bx - p.pat_r0, ic = (long long)by - p.pat_c0;  // astype(int): truncation
+        if (ir < 0) ir += p.pat_rows;  // numpy negative indices wrap
+        if (ic < 0) ic += p.pat_cols;
+        if (ir < 0 || ic < 0 || ir >= p.pat_rows || ic >= p.pat_cols)
+            return f4(0.f, 0.f, 0.f, 0.f);
+        const float4 *pat = reinterpret_cast<const float4 *>(T.layers + s.off2);
+        return pat[ir * s.stride2 + ic];
+    }
+    px_to_user(p, r, c, &ux, &uy);
+    double t;
+    if (p.kind == PAINT_LINEAR) {
+        double vx = p.g[2] - p.g[0], vy = p.g[3] - p.g[1];
+        double vv = fma(vy, vy, vx * vx);
+        double dx = ux - p.g[0], dy = uy - p.g[1];
+        t = fma(dy, vy, dx * vx) / vv;
+    } else if (p.kind == PAINT_RADIAL) {
+        double ox = (ux - p.g[0]) / p.g[2], oy = (uy - p.g[1]) / p.g[2];
+        t = sqrt(ox * ox + oy * oy);
+    } else {
+        double b, a;
+        double det = focal_det(p, ux, uy, &b, &a);
+        bool any_neg = T.focal_flags[p.flag] != 0;
+        if (any_neg && det < 0)
+            return f4(0.f, 0.f, 0.f, 0.f);
+        double sq = sqrt(det);
+        double t1 = (b + sq) / a, t2 = (b - sq) / a;
+        t = (t1 != t1 || t2 != t2) ? __longlong_as_double(0x7ff8000000000000ll) : (t1 > t2 ? t1 : t2);
+        if (any_neg && p.g[5] != p.g[2]) {
+            double lim = p.g[5] / (p.g[5] - p.g[2]);
+            if (!(t > lim))
+                return f4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    return grad_color(grad_spread(t, p.spread), T.stops + p.stop_off, p.stop_cnt);
+}
+
+// Value of a source at global pixel (r, c), which must lie inside its bbox.
+__device__ __forceinline__ float4 fetch_src(const RenderTables &T, const SrcRec &s, int r, int c)
+{
+    long long idx = (long long)(r - s.r0) * s.stride + (c - s.c0);
+    float4 v;
+    switch (s.kind) {
+    case SRC_L4:
+        v = __ldg(reinterpret_cast<const float4 *>(T.layers + s.off) + idx);
+        break;
+    case SRC_L1: {
+        float a = __ldg(T.layers + s.off + idx);
+        v = f4(a, a, a, a);
+        break;
+    }
+    case SRC_COV: {
+        float a = __ldg(T.cov + s.off + idx);
+        v = f4(a, a, a, a);
+        break;
+    }
+    case SRC_COVPAINT: {
+        float a = __ldg(T.cov + s.off + idx);
+        if (a == 0.f) {
+            v = f4(0.f, 0.f, 0.f, 0.f);
+        } else {
+            float4 p = paint_eval(T, s, r, c);
+            v = f4(p.x * a, p.y * a, p.z * a, p.w * a);
+        }
+        break;
+    }
+    default:
+        v = f4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (s.mul != 1.0f)
+        v = f4(v.x * s.mul, v.y * s.mul, v.z * s.mul, v.w * s.mul);
+    if (s.kind != SRC_L1 && s.kind != SRC_COV && !conv_is_identity(s.conv))
+        v = convert_px(v, s.conv);
+    return v;
+}

@@ -1,0 +1,68 @@
+// svgr_kernels.h -- internal: launcher prototypes shared by the kernel files and the host engine.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "svgr_types.h"
+
+#define SVGR_MAX_DYN_SMEM (200 * 1024)
+
+struct RenderTables {
+    const SrcRec *srcs;
+    const PaintRec *paints;
+    const StopRec *stops;
+    const int *focal_flags;  // any(det < 0) per focal radial paint (svgrasterize.py:1622)
+    const float *cov;        // coverage arena
+    const float *layers;     // layer arena (read side)
+    const float *matrices;   // 20 floats per feColorMatrix
+    const float *weights;    // stencil / convolution weights
+};
+
+// k_flatten.cu
+void svgr_launch_minmax_init(unsigned long long *minmax, int n, cudaStream_t s);
+void svgr_launch_flatten(const uint8_t *seg_tag, const double *seg_data, const uint32_t *seg_path, long long n_seg,
+                         const int *n_seg_dev, const PathRec *paths, double thr, double *edges, uint32_t *edge_path,
+                         unsigned long long cap, unsigned long long *n_edges, unsigned long long *minmax, int sm_count,
+                         cudaStream_t s);
+void svgr_launch_bounds(const unsigned long long *minmax, const PathRec *paths, int n_paths, PathBox *boxes,
+                        double *minmax_f64, cudaStream_t s);
+void svgr_launch_cloud_bounds(const double *edges, const uint32_t *edge_path, const unsigned long long *n_edges,
+                              unsigned long long cap, const int *pq_off, const int *pq_idx, const double *q_inv,
+                              unsigned long long *q_minmax, double *q_out, int n_q, int sm_count, cudaStream_t s);
+
+// k_coverage.cu
+void svgr_launch_exclusive_scan(const int *in, int *out, long long n, int *tmp, int *total_out, cudaStream_t s);
+void svgr_launch_bin_count(const double *edges, const uint32_t *edge_path, unsigned long long n_edges,
+                           const MaskRec *masks, int *band_count, int sm_count, cudaStream_t s);
+void svgr_launch_bin_fill(const double *edges, const uint32_t *edge_path, unsigned long long n_edges,
+                          const MaskRec *masks, const int *band_off, int *band_cursor, uint32_t *bin_edges,
+                          int sm_count, cudaStream_t s);
+void svgr_launch_coverage(const double *edges, const MaskRec *masks, int n_masks, int n_tiles, const int *band_off,
+                          const int *band_cnt, const uint32_t *bin_edges, float *cov, cudaStream_t s);
+
+// k_compose.cu
+void svgr_launch_compose(const RenderTables &T, const OpRec *ops, int n_ops, int n_tiles, float *layers_out,
+                         cudaStream_t s);
+void svgr_launch_canvas(const RenderTables &T, const OpRec *ops, int n_ops, int n_tiles, uint8_t *out, cudaStream_t s);
+void svgr_launch_focal_flags(const RenderTables &T, const void *jobs, int n_jobs, int n_blocks, int *flags,
+                             cudaStream_t s);
+
+// k_filters.cu
+int svgr_launch_stencil(const RenderTables &T, const OpRec *ops, int n_ops, int n_tiles, size_t smem_bytes,
+                        float *layers_out, cudaStream_t s);
+int svgr_launch_conv2d(const RenderTables &T, const OpRec *ops, int n_ops, int n_tiles, size_t smem_bytes,
+                       float *layers_out, cudaStream_t s);
+
+// k_stroke.cu
+size_t svgr_stroke_curve_bytes();
+void svgr_launch_stroke_count(const uint8_t *tag, const double *data, const int *seg_job, const StrokeRec *jobs,
+                              int n_seg, int *counts, int *err, cudaStream_t s);
+void svgr_launch_stroke_emit(const uint8_t *tag, const double *data, const int *seg_job, const StrokeRec *jobs,
+                             int n_seg, const int *offs, void *pool, int pool_cap, cudaStream_t s);
+void svgr_launch_stroke_bound(const int *sub_off, int n_sub, int n_seg, const int *offs, int *bound, cudaStream_t s);
+void svgr_launch_stroke_assemble(const uint8_t *in_tag, const int *sub_off, const int *sub_job, const StrokeRec *jobs,
+                                 int n_sub, int n_seg, const int *offs, const void *pool, const int *bound,
+                                 const int *out_off, const int *out_total, long long out_base, long long out_cap,
+                                 uint8_t *out_tag, double *out_data, uint32_t *out_path, int32_t *out_sub,
+                                 int *n_out_dev, int *err, cudaStream_t s);

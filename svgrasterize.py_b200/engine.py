@@ -1,0 +1,197 @@
+"""Engine: one svgr_ctx (one GPU, one stream) behind a small Python class.
+
+PyTorch is used only for what it is good at here: picking the device, handing
+over the current CUDA stream and owning output tensors that stay on the GPU.
+Every pixel is produced by libsvgr_b200.so; if the library or the GPU is missing
+the constructor raises (there is no CPU fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .encode import Program
+
+_ERRORS = {
+    _lib.E_INVALID: ValueError,
+    _lib.E_CUDA: RuntimeError,
+    _lib.E_NOMEM: MemoryError,
+    _lib.E_UNSUPPORTED: NotImplementedError,
+    _lib.E_STROKE: TypeError,
+}
+
+
+class Engine:
+    def __init__(self, device: int = 0):
+        self.L = _lib.lib()
+        ctx = C.c_void_p()
+        rc = self.L.svgr_create(int(device), C.byref(ctx))
+        if rc != 0 or not ctx.value:
+            raise RuntimeError(
+                f"svgr_create(device={device}) failed ({rc}): the svgrasterize B200 core needs a CUDA device "
+                "(no CPU fallback)")
+        self.ctx = ctx
+        self.device = int(device)
+        self.program = None
+        self.last_stats = None
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.L.svgr_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = self.L.svgr_last_error(self.ctx)
+            msg = msg.decode() if msg else f"error {rc}"
+            raise _ERRORS.get(rc, RuntimeError)(msg)
+
+    @staticmethod
+    def _stream(stream):
+        if stream is None:
+            return None
+        if isinstance(stream, int):
+            return C.c_void_p(stream)
+        return C.c_void_p(stream.cuda_stream)  # torch.cuda.Stream
+
+    # -- rendering -----------------------------------------------------------------------------
+    def render(self, program: Program, stop: int = _lib.STOP_NONE, out=None, timing: bool = False, stream=None):
+        """Run the pipeline on `program` (host arrays are copied to the device inside the call).
+
+        out: None | numpy uint8 array (host, canvas_bytes long) | torch CUDA uint8 tensor.  Returns the
+        stats dict; with out=None and canvases present the RGBA8 bytes are returned as `stats["canvas"]`."""
+        cprog, keep = program.to_c()
+        self.program, self._keep = program, keep
+        stats = _lib.Stats()
+        out_ptr, on_dev, host_out = None, 0, None
+        if stop == _lib.STOP_NONE and program.canvas_bytes > 0:
+            if out is None:
+                host_out = np.empty(program.canvas_bytes, dtype=np.uint8)
+                out_ptr = host_out.ctypes.data
+            elif isinstance(out, np.ndarray):
+                assert out.dtype == np.uint8 and out.flags.c_contiguous and out.nbytes >= program.canvas_bytes
+                out_ptr = out.ctypes.data
+            else:  # torch tensor
+                assert out.is_cuda and out.is_contiguous() and out.numel() * out.element_size() >= program.canvas_bytes
+                out_ptr, on_dev = out.data_ptr(), 1
+        rc = self.L.svgr_render(self.ctx, C.byref(cprog), self._stream(stream), int(stop), out_ptr, on_dev,
+                                int(bool(timing)), C.byref(stats))
+        self._check(rc)
+        res = stats.as_dict()
+        if host_out is not None:
+            res["canvas"] = host_out
+        self.last_stats = res
+        return res
+
+    def render_resident(self, out_device=None, timing: bool = False, stream=None):
+        """Re-run the device pipeline on the program left resident by the last render()."""
+        stats = _lib.Stats()
+        ptr = None if out_device is None else out_device.data_ptr()
+        self._check(self.L.svgr_render_resident(self.ctx, self._stream(stream), ptr, int(bool(timing)), C.byref(stats)))
+        return stats.as_dict()
+
+    def canvas(self, program: Program, raw: np.ndarray, index: int = 0) -> np.ndarray:
+        _node, off, rows, cols = program.canvases[index]
+        return raw[off: off + 4 * rows * cols].reshape(rows, cols, 4)
+
+    # -- taps ---------------------------------------------------------------------------------
+    def edges(self):
+        """-> (edges (E, 4) float64 [r0, c0, r1, c1], edge_path (E,) uint32) of the last render."""
+        n = C.c_int64()
+        self._check(self.L.svgr_read_edges(self.ctx, None, None, 0, C.byref(n)))
+        e = np.empty((n.value, 4), dtype=np.float64)
+        p = np.empty(n.value, dtype=np.uint32)
+        if n.value:
+            self._check(self.L.svgr_read_edges(self.ctx, e.ctypes.data, p.ctypes.data, n.value, C.byref(n)))
+        return e, p
+
+    def boxes(self, minmax: bool = False):
+        n = len(self.program.paths)
+        b = np.zeros((n, 4), dtype=np.int32)
+        mm = np.zeros((n, 4), dtype=np.float64) if minmax else None
+        self._check(self.L.svgr_read_boxes(self.ctx, b.ctypes.data, None if mm is None else mm.ctypes.data))
+        return (b, mm) if minmax else b
+
+    def mask(self, path: int, box) -> np.ndarray:
+        rows, cols = int(box[2]), int(box[3])
+        out = np.zeros((max(rows, 0), max(cols, 0)), dtype=np.float32)
+        if out.size:
+            self._check(self.L.svgr_read_mask(self.ctx, int(path), out.ctypes.data))
+        return out
+
+    def bins(self, path: int, box):
+        nb = (max(int(box[2]), 0) + 15) // 16
+        off = np.zeros(nb + 1, dtype=np.int32)
+        n = C.c_int64()
+        self._check(self.L.svgr_read_bins(self.ctx, int(path), off.ctypes.data, None, 0, C.byref(n)))
+        ids = np.zeros(n.value, dtype=np.uint32)
+        if n.value:
+            self._check(self.L.svgr_read_bins(self.ctx, int(path), off.ctypes.data, ids.ctypes.data, n.value, C.byref(n)))
+        return off, ids
+
+    def outline(self):
+        """Outline segments of the last render's strokes: (tag, data (n, 8), path, sub) without padding."""
+        n = C.c_int64()
+        self._check(self.L.svgr_read_outline(self.ctx, None, None, None, None, 0, C.byref(n)))
+        tag = np.empty(n.value, dtype=np.uint8)
+        data = np.empty((n.value, 8), dtype=np.float64)
+        path = np.empty(n.value, dtype=np.uint32)
+        sub = np.empty(n.value, dtype=np.int32)
+        if n.value:
+            self._check(self.L.svgr_read_outline(self.ctx, tag.ctypes.data, data.ctypes.data, path.ctypes.data,
+                                                 sub.ctypes.data, n.value, C.byref(n)))
+        keep = tag != _lib.SEG_NOP
+        return tag[keep], data[keep], path[keep], sub[keep]
+
+    def node_info(self, node: int):
+        """-> (kind 0 empty / 1 RGBA / 2 one channel, r0, c0, rows, cols, pre_alpha, linear_rgb, virtual)"""
+        info = (C.c_int32 * 8)()
+        self._check(self.L.svgr_node_info(self.ctx, int(node), info))
+        return tuple(info)
+
+    def node(self, node: int):
+        """Layer of a node after a full render: (image float32 (rows, cols, ch), (r0, c0), pre, lin) or None."""
+        kind, r0, c0, rows, cols, pre, lin, _virtual = self.node_info(node)
+        if kind == 0:
+            return None
+        ch = 4 if kind == 1 else 1
+        img = np.empty((rows, cols, ch), dtype=np.float32)
+        self._check(self.L.svgr_read_node(self.ctx, int(node), img.ctypes.data))
+        return img, (r0, c0), bool(pre), bool(lin)
+
+    def cloud_bounds(self, path_lists, inverses):
+        """ConvexHull.bbox reductions: per query (list of path ids, inverse 2x3) -> (minx, miny, maxx, maxy)."""
+        nq = len(path_lists)
+        off = np.zeros(nq + 1, dtype=np.int32)
+        off[1:] = np.cumsum([len(p) for p in path_lists])
+        paths = np.asarray([p for ps in path_lists for p in ps], dtype=np.int32)
+        inv = np.ascontiguousarray(np.asarray(inverses, dtype=np.float64).reshape(nq, 6))
+        out = np.zeros((nq, 4), dtype=np.float64)
+        self._check(self.L.svgr_cloud_bounds(self.ctx, nq, off.ctypes.data, paths.ctypes.data if len(paths) else None,
+                                             inv.ctypes.data, out.ctypes.data))
+        return out
+
+
+_default = {}
+
+
+def default_engine(device: int | None = None) -> Engine:
+    """Process-wide engine for the eager API (one per device)."""
+    if device is None:
+        import torch
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("svgrasterize B200 core: no CUDA device available (there is no CPU fallback)")
+        device = torch.cuda.current_device()
+    if device not in _default:
+        _default[device] = Engine(device)
+    return _default[device]

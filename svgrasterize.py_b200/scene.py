@@ -137,11 +137,12 @@ class Path:
     (svgrasterize.py:896-913).  ``mask`` / ``fill`` / ``stroke`` are attached
     by ``api.py`` and run on the device."""
 
-    __slots__ = ("subpaths", "_enc")
+    __slots__ = ("subpaths", "_enc", "_flat")
 
     def __init__(self, subpaths):
         self.subpaths = subpaths
         self._enc = None
+        self._flat = None
 
     def __iter__(self):
         return iter(self.subpaths)

@@ -1,0 +1,153 @@
+"""GPU parity tests: the CUDA core (through the C-ABI) against the golden vectors recorded from the
+unmodified reference (tests/golden, tools/make_golden.py) and against the CPU oracle.
+
+Tolerances are BASELINE.json's: bit-exact edge lists (as per-path multisets), exact boxes and bins,
+coverage within 1e-5 absolute, final RGBA8 within +-1 LSB per channel.
+"""
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+
+ALL = golden_names()
+STAGED = [n for n in ALL if "leaf_edge_off" in load_golden(n)[3].files]
+ROOTED = [n for n in ALL if "root_image" in load_golden(n)[3].files]
+STROKED = [n for n in ALL if "stroke_off" in load_golden(n)[3].files]
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from svgrasterize_b200.engine import Engine
+
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def _program(name, eng):
+    from svgrasterize_b200 import encode
+
+    scene, size, linear_rgb, z = load_golden(name)
+    enc = encode.Encoder(eng)
+    enc.add_scene(scene, size, linear_rgb)
+    return enc.finish(), z, size
+
+
+def _sorted_rows(e):
+    return e[np.lexsort(e.T[::-1])]
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_canvas_within_one_lsb(name, eng):
+    """Final image (svgrasterize.py:3870-3881, :263): +-1 LSB per channel against the reference's bytes."""
+    prog, z, _size = _program(name, eng)
+    res = eng.render(prog)
+    got = eng.canvas(prog, res["canvas"])
+    ref = z["canvas_u8"]
+    assert got.shape == ref.shape
+    diff = np.abs(got.astype(np.int16) - ref.astype(np.int16))
+    assert diff.max() <= 1, f"max diff {diff.max()} at {np.argwhere(diff > 1)[:5]}"
+
+
+@pytest.mark.parametrize("name", STAGED)
+def test_leaf_stages(name, eng):
+    """Per Path.mask call: box exact, edge multiset bit-exact, coverage within 1e-5."""
+    from svgrasterize_b200 import _lib
+
+    prog, z, _size = _program(name, eng)
+    eng.render(prog, stop=_lib.STOP_COVERAGE)
+    boxes = eng.boxes()
+    edges, edge_path = eng.edges()
+    ref_box, eoff, moff = z["leaf_bbox"], z["leaf_edge_off"], z["leaf_mask_off"]
+    assert len(boxes) == len(ref_box)
+    order = np.argsort(edge_path, kind="stable")
+    edges, edge_path = edges[order], edge_path[order]
+    starts = np.searchsorted(edge_path, np.arange(len(boxes) + 1))
+    worst = 0.0
+    for i in range(len(boxes)):
+        if ref_box[i][2] < 0:
+            assert boxes[i][2] <= 0 or boxes[i][3] <= 0
+            continue
+        assert tuple(boxes[i]) == tuple(ref_box[i])
+        mine = _sorted_rows(edges[starts[i]: starts[i + 1]])
+        ref_e = z["edges"][eoff[i]: eoff[i + 1]]
+        assert mine.shape == ref_e.shape
+        assert np.array_equal(mine.view(np.uint64), ref_e.view(np.uint64))
+        mask = eng.mask(i, boxes[i])
+        ref_m = z["masks"][moff[i]: moff[i + 1]].reshape(mask.shape)
+        worst = max(worst, float(np.abs(mask - ref_m).max()))
+    assert worst <= 1e-5, worst
+
+
+@pytest.mark.parametrize("name", STAGED)
+def test_bins_match_cpu_restatement(name, eng):
+    """Bins are exact sets: edge e is in band b of its path iff line_signed_coverage visits a row of
+    that band (rows int(max(0, r0)) .. min(h, ceil(r1)) - 1, svgrasterize.py:2239-2243) and the edge is
+    not entirely right of the mask."""
+    from svgrasterize_b200 import _lib
+
+    prog, z, _size = _program(name, eng)
+    eng.render(prog, stop=_lib.STOP_COVERAGE)
+    boxes = eng.boxes()
+    edges, edge_path = eng.edges()
+    for i in range(0, len(boxes), max(1, len(boxes) // 40)):
+        r0, c0, rows, cols = (int(v) for v in boxes[i])
+        if rows <= 0 or cols <= 0:
+            continue
+        off, ids = eng.bins(i, boxes[i])
+        idx = np.nonzero(edge_path == i)[0]
+        e = edges[idx]
+        ra, rb = e[:, 0] - r0, e[:, 2] - r0
+        lo, hi = np.minimum(ra, rb), np.maximum(ra, rb)
+        cmin = np.minimum(e[:, 1], e[:, 3]) - c0
+        y0 = np.maximum(lo, 0).astype(np.int64)
+        y1 = np.minimum(np.ceil(hi), rows).astype(np.int64)
+        ok = (ra != rb) & (cmin < cols + 1) & (np.maximum(lo, 0) < rows) & (y0 < y1)
+        nb = (rows + 15) // 16
+        for b in range(nb):
+            want = set(idx[ok & (y0 < (b + 1) * 16) & (y1 > b * 16)].tolist())
+            got = ids[off[b]: off[b + 1]].tolist()
+            assert len(got) == len(set(got))
+            assert set(got) == want
+
+
+@pytest.mark.parametrize("name", STROKED)
+def test_stroke_outlines_bit_exact(name, eng):
+    """Path.stroke (svgrasterize.py:1105-1180): outline segments identical to the reference's, bit for bit."""
+    from svgrasterize_b200 import _lib
+
+    prog, z, _size = _program(name, eng)
+    eng.render(prog, stop=_lib.STOP_STROKE)
+    tag, data, path, sub = eng.outline()
+    so, ss = z["stroke_off"], z["stroke_sub_idx"]
+    jobs = prog.strokes
+    assert len(jobs) == len(so) - 1
+    for k in range(len(jobs)):
+        sel = path == jobs[k]["path"]
+        t, d, s = tag[sel], data[sel], sub[sel]
+        ref_t = z["stroke_tag"][so[k]: so[k + 1]]
+        ref_d = z["stroke_data"][so[k]: so[k + 1]]
+        ref_s = z["stroke_sub_off"][ss[k]: ss[k + 1]]
+        assert np.array_equal(t, ref_t)
+        assert np.array_equal(d.view(np.uint64), ref_d.view(np.uint64))
+        bounds = np.concatenate([[0], np.nonzero(np.diff(s))[0] + 1, [len(s)]]) if len(s) else np.zeros(1, int)
+        assert np.array_equal(bounds, ref_s)
+
+
+@pytest.mark.parametrize("name", ROOTED)
+def test_root_layer(name, eng):
+    """Layer returned by Scene.render: offset, shape, flags exact; pixels within 1e-5 of the reference."""
+    from svgrasterize_b200 import encode
+
+    scene, size, linear_rgb, z = load_golden(name)
+    enc = encode.Encoder(eng)
+    root = enc.add_root(scene, encode.canvas_transform(), False, [0, 0, int(size[1]), int(size[0])], linear_rgb)
+    prog = enc.finish()
+    eng.render(prog)
+    img, offset, pre, lin = eng.node(root)
+    assert tuple(z["root_offset"]) == tuple(offset)
+    assert tuple(z["root_flags"]) == (pre, lin)
+    assert z["root_image"].shape == img.shape
+    assert np.abs(img - z["root_image"]).max() < 2e-5
