@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on its workload: Mpixels/s rendered for a batch of synthetic
+256 px icon SVGs (config 5: gradients, clip, mask, strokes), whole-job over N GPUs (weak scaling: every
+rank renders its own `--icons` icons per step; whole SVGs are the shard unit, no data-path collective).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--icons B] [--impl reference]
+
+A step is one pass of the hot path (stroke outlines -> flatten -> bounds -> bin -> coverage ->
+paint + compose -> quantise) over one batch.
+  value  device timing, scene program resident in HBM, RGBA8 result left in HBM
+  e2e    the same through the C-ABI call a user makes (svgr_render): host (pinned) program arrays in,
+         host RGBA8 out, copies inside the timed region
+  --impl reference   the CPU restatement of the reference's numpy path (oracle/, pinned bit-exactly to
+         the unmodified reference by tests/test_oracle_pins.py) on all host cores, same metric.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Mpixels/sec rendered (icon batch)"
+UNIT = "Mpx/s"
+ICON_PX = 256
+
+
+def workload_name(icons):
+    return (f"c5: batch of {icons} synthetic icon SVGs per GPU per step at {ICON_PX}x{ICON_PX} px "
+            "(12 masks, ~1040 edges, 3 strokes, 3 gradients, clip + luminance mask per icon; seed = icon index)")
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle restatement of the reference, one process per host core
+# ---------------------------------------------------------------------------------------------
+def _cpu_render(seed):
+    import svgrasterize_b200  # noqa: F401
+    from oracle import render as O
+    from svgrasterize_b200 import synth
+
+    img = O.render_canvas(synth.icon_scene(seed), synth.icon_size())
+    return int(img.shape[0] * img.shape[1])
+
+
+def cpu_throughput(n_icons, cores, seed0=0):
+    """-> (Mpx/s, seconds) rendering n_icons with `cores` processes."""
+    import multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_render, range(cores))  # start-up + library load, untimed
+        t0 = time.perf_counter()
+        px = sum(pool.map(_cpu_render, range(seed0, seed0 + n_icons), chunksize=max(1, n_icons // (cores * 8))))
+        dt = time.perf_counter() - t0
+    return px / dt / 1e6, dt
+
+
+def run_reference(opts):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_icons = max(cores * 32, 256)
+    vals = []
+    for step in range(opts.warmup + opts.steps):
+        v, dt = cpu_throughput(n_icons, cores, seed0=step * n_icons)
+        if step >= opts.warmup:
+            vals.append((v, dt))
+    value = float(np.mean([v for v, _ in vals]))
+    ms = float(np.mean([dt for _, dt in vals]) * 1e3)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": opts.gpus, "steps": opts.steps, "warmup": opts.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "impl": "reference",
+        "config": {"workload": workload_name(opts.icons), "sample": f"{n_icons} icons per step on {cores} processes"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{n_icons} icons of the workload per step, one process per core, oracle/ "
+                                   "(C + numpy restatement pinned to the unmodified reference)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self.stop_flag = index, [], set(), None, False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    NAMES = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+             0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+             0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def run(self):
+        if self.nv is None:
+            return
+        while not self.stop_flag:
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.NAMES.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def pin_program(prog):
+    """Re-home the program's arrays in pinned host memory (what a serving process would keep them in)."""
+    import torch
+
+    keep = []
+    for name in prog.ARRAYS:
+        arr = np.ascontiguousarray(getattr(prog, name))
+        if arr.nbytes == 0:
+            continue
+        t = torch.empty(arr.nbytes, dtype=torch.uint8, pin_memory=True)
+        view = t.numpy().view(arr.dtype).reshape(arr.shape)
+        view[...] = arr
+        setattr(prog, name, view)
+        keep.append(t)
+    return keep
+
+
+def build_batch(icons, seed0, engine):
+    from svgrasterize_b200 import encode, synth
+
+    progs = [encode.encode_scene(synth.icon_scene(seed0 + i), synth.icon_size(), engine=engine) for i in range(icons)]
+    return encode.Program.concat(progs)
+
+
+def run_gpu(opts):
+    import torch
+
+    import svgrasterize_b200  # noqa: F401
+    from svgrasterize_b200.engine import Engine
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    eng = Engine(local)
+    stream = torch.cuda.current_stream()
+
+    t0 = time.perf_counter()
+    prog = build_batch(opts.icons, rank * opts.icons, eng)
+    t_encode = time.perf_counter() - t0
+    pins = pin_program(prog)
+    n_px = opts.icons * ICON_PX * ICON_PX
+    out_dev = torch.empty(prog.canvas_bytes, dtype=torch.uint8, device="cuda")
+    out_host = torch.empty(prog.canvas_bytes, dtype=torch.uint8, pin_memory=True)
+    out_host_np = out_host.numpy()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- first render: uploads the program, sizes every buffer
+    eng.render(prog, out=out_dev, stream=stream)
+    for _ in range(opts.warmup):
+        eng.render_resident(out_dev, stream=stream)
+
+    # ---- value: resident program, device timing
+    sampler = ClockSampler(local)
+    sampler.start()
+    acc = {}
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(opts.steps):
+        st = eng.render_resident(out_dev, timing=True, stream=stream)
+        for k, v in st.items():
+            if k.startswith("ms_"):
+                acc[k] = acc.get(k, 0.0) + v
+    e1.record(stream)
+    barrier()
+    sampler.stop_flag = True
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    sampler.join()
+    ms_step = ms_total / opts.steps
+    value = world * n_px / (ms_step * 1e-3) / 1e6
+
+    # ---- e2e: svgr_render with host buffers (H2D of the program, D2H of the RGBA8 result inside)
+    for _ in range(min(opts.warmup, 2)):
+        eng.render(prog, out=out_host_np, stream=stream)
+    barrier()
+    e0.record(stream)
+    for _ in range(opts.steps):
+        eng.render(prog, out=out_host_np, stream=stream)
+    e1.record(stream)
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / opts.steps
+    e2e_value = world * n_px / (ms_e2e * 1e-3) / 1e6
+    check = int(out_host_np[:: max(1, len(out_host_np) // 4096)].astype(np.int64).sum())
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (stage times are CUDA events on the launch stream)
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    ms_cov = acc.get("ms_coverage", 0.0) / opts.steps
+    ms_cmp = acc.get("ms_compose", 0.0) / opts.steps
+    cov_gbs = st["coverage_bytes"] / (ms_cov * 1e-3) / 1e9 if ms_cov > 0 else 0.0
+    cmp_gbs = st["compose_bytes"] / (ms_cmp * 1e-3) / 1e9 if ms_cmp > 0 else 0.0
+    traffic = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f)
+    except Exception:
+        pass
+    kernels = {
+        "compose_kernel": {"bound": "hbm", "achieved": cmp_gbs, "peak": peak, "unit": "GB/s", "frac": cmp_gbs / peak,
+                           "traffic": traffic.get("compose_kernel"), "ms_per_step": ms_cmp,
+                           "launches_per_step": st["n_launches"] - 1, "algorithmic_bytes_per_step": st["compose_bytes"]},
+        "coverage_kernel": {"bound": "hbm", "achieved": cov_gbs, "peak": peak, "unit": "GB/s", "frac": cov_gbs / peak,
+                            "traffic": traffic.get("coverage_kernel"), "ms_per_step": ms_cov, "launches_per_step": 1,
+                            "algorithmic_bytes_per_step": st["coverage_bytes"]},
+    }
+    dominant = "compose_kernel" if ms_cmp >= ms_cov else "coverage_kernel"
+    roofline = dict(kernels[dominant], kernel=dominant, peak_source=peak_src)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": opts.steps, "warmup": opts.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": workload_name(opts.icons), "icons_per_gpu_per_step": opts.icons,
+                   "canvas_px_per_step_per_gpu": n_px, "mask_px_per_step_per_gpu": st["mask_pixels"],
+                   "paths_per_step_per_gpu": int(len(prog.paths)), "edges_per_step_per_gpu": st["n_edges"],
+                   "l2": "inputs larger than L2 (coverage + layer arenas of "
+                         f"{(st['cov_floats'] + st['layer_floats']) * 4 / 2**30:.1f} GiB per step)",
+                   "parallelism": f"whole SVGs sharded over {world} GPU(s), no collective",
+                   "arithmetic": "geometry f64, coverage/compose f32"},
+        "clocks": sampler.summary(),
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": prog.h2d_bytes(),
+                "d2h_bytes_per_step": int(prog.canvas_bytes), "checksum": check},
+        "gpu_launches": int(st["n_kernels"]) * opts.steps,
+        "paths_per_s": world * len(prog.paths) / (ms_step * 1e-3),
+        "stage_ms_per_step": {k: v / opts.steps for k, v in sorted(acc.items())},
+        "roofline": roofline,
+        "roofline_other": {k: v for k, v in kernels.items() if k != dominant},
+        "host_encode_s_per_batch": t_encode,
+    }
+    if world == 1 and not opts.no_cpu:
+        cores = os.cpu_count() or 1
+        n = max(cores * 48, 512)
+        v, dt = cpu_throughput(n, cores, seed0=0)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"{n} icons of the same workload in {dt:.1f} s wall, one process per core, "
+                                          "oracle/ (C + numpy restatement pinned to the unmodified reference)"}
+    del pins
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--icons", type=int, default=2048, help="icons per GPU per step")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    opts = ap.parse_args()
+    if opts.impl == "reference":
+        run_reference(opts)
+    else:
+        run_gpu(opts)
+
+
+if __name__ == "__main__":
+    main()

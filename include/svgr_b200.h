@@ -156,6 +156,11 @@ typedef struct svgr_stats {
     int64_t cov_floats, layer_floats; /* arena sizes */
     int64_t n_ops, n_levels, n_launches;
     int64_t mask_pixels, layer_pixels;
+    int64_t coverage_bytes; /* algorithmic bytes of the coverage launch: 4 B per mask pixel + 36 B per binned edge */
+    int64_t compose_bytes;  /* algorithmic bytes of the compose launches: every source pixel read once, every
+                               output pixel written once */
+    int64_t canvas_pixels;  /* pixels quantised by the canvas launch (16 B read + 4 B written each) */
+    int64_t n_kernels;      /* kernel launches issued by this call */
     float ms_total, ms_h2d, ms_stroke, ms_flatten, ms_plan, ms_bin, ms_coverage, ms_compose, ms_canvas, ms_d2h;
     int32_t retries;
     int32_t pad;

@@ -63,7 +63,8 @@ class Program(C.Structure):
 class Stats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("n_edges", "n_outline_segs", "n_bands", "n_cov_tiles", "n_binned", "cov_floats",
                                          "layer_floats", "n_ops", "n_levels", "n_launches", "mask_pixels",
-                                         "layer_pixels")] + \
+                                         "layer_pixels", "coverage_bytes", "compose_bytes", "canvas_pixels",
+                                         "n_kernels")] + \
                [(n, C.c_float) for n in ("ms_total", "ms_h2d", "ms_stroke", "ms_flatten", "ms_plan", "ms_bin",
                                          "ms_coverage", "ms_compose", "ms_canvas", "ms_d2h")] + \
                [("retries", C.c_int32), ("pad", C.c_int32)]

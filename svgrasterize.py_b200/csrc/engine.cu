@@ -177,7 +177,7 @@ struct svgr_ctx {
     std::vector<Launch> launches;
     int n_focal_blocks = 0;
     long long n_bands = 0, n_cov_tiles = 0, cov_floats = 0, layer_floats = 0;
-    long long mask_pixels = 0, layer_pixels = 0;
+    long long mask_pixels = 0, layer_pixels = 0, compose_bytes = 0, canvas_pixels = 0;
     int n_levels = 0;
     DevBuf d_masks, d_band_cnt, d_band_off, d_band_cur, d_bin_edges, d_cov, d_layers, d_ops, d_srcs, d_focal_jobs,
         d_focal_flags, d_canvas, d_q;
@@ -677,6 +677,28 @@ struct Planner {
             i = j;
         }
         c->n_levels = nl;
+        // algorithmic traffic of the compose-class launches
+        c->compose_bytes = 0, c->canvas_pixels = 0;
+        for (auto &po : c->ops) {
+            const OpRec &o = po.op;
+            if (po.cls == 3) {
+                c->canvas_pixels += (long long)o.rows * o.cols;
+                continue;
+            }
+            c->compose_bytes += (long long)o.rows * o.cols * o.out_ch * 4;
+            for (int k = 0; k < o.src_cnt; k++) {
+                const SrcRec &sr = c->srcs[o.src_off + k];
+                long long rr, cc;
+                if (po.cls == 0) {
+                    rr = std::min(o.r0 + o.rows, sr.r0 + sr.rows) - std::max(o.r0, sr.r0);
+                    cc = std::min(o.c0 + o.cols, sr.c0 + sr.cols) - std::max(o.c0, sr.c0);
+                } else {
+                    rr = sr.rows, cc = sr.cols;
+                }
+                if (rr > 0 && cc > 0)
+                    c->compose_bytes += rr * cc * (sr.kind == SRC_L4 ? 16 : 4);
+            }
+        }
         return true;
     }
 };
@@ -772,6 +794,7 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
         FAIL(SVGR_E_INVALID, "no program loaded");
     const int SM = ctx->sm_count;
     int retries = 0;
+    long long n_kernels = 0;
     float ms_stroke = 0, ms_flatten = 0, ms_plan = 0, ms_bin = 0, ms_cov = 0, ms_cmp = 0, ms_canvas = 0, ms_d2h = 0;
     ctx->planned = ctx->covered = ctx->composed = false;
     auto mark = [&](int i) {
@@ -806,6 +829,7 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
         CK(ctx->d_edge_path.ensure((size_t)ctx->edge_cap * 4));
         CK(cudaMemsetAsync(d_st, 0, sizeof(StatusBlock), s));
         svgr_launch_minmax_init(ctx->d_minmax.as<unsigned long long>(), ctx->n_path, s);
+        n_kernels += 1;
         mark(0);
         // ---- stroke outlines
         if (S > 0) {
@@ -839,6 +863,8 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
                                         ctx->outline_cap, ctx->d_otag.as<uint8_t>(), ctx->d_odata.as<double>(),
                                         ctx->d_opath.as<uint32_t>(), ctx->d_osub.as<int32_t>(), &d_st->outline_count,
                                         &d_st->stroke_err, s);
+            // count, 2 x (scan: local, sums[, add]), emit, bound, assemble
+            n_kernels += 4 + 2 + 2 + ((2 * nS + 1) > 2048 ? 1 : 0) + (nSub > 2048 ? 1 : 0);
         }
         mark(1);
         // ---- flatten + bounds
@@ -857,6 +883,7 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
                                     ctx->d_minmax.as<unsigned long long>(), SM, s);
             svgr_launch_bounds(ctx->d_minmax.as<unsigned long long>(), ctx->d_paths.as<PathRec>(), ctx->n_path,
                                ctx->d_boxes.as<PathBox>(), ctx->d_minmax_f64.as<double>(), s);
+            n_kernels += (ctx->n_seg > 0) + (S > 0) + (ctx->n_path > 0);
             if (ctx->n_path > 0)
                 CK(cudaMemcpyAsync(ctx->pin_boxes.p, ctx->d_boxes.p, (size_t)ctx->n_path * sizeof(PathBox),
                                    cudaMemcpyDeviceToHost, s));
@@ -972,6 +999,7 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
         svgr_launch_bin_fill(ctx->d_edges.as<double>(), ctx->d_edge_path.as<uint32_t>(), (unsigned long long)ctx->n_edges,
                              ctx->d_masks.as<MaskRec>(), ctx->d_band_off.as<int>(), ctx->d_band_cur.as<int>(),
                              ctx->d_bin_edges.as<uint32_t>(), SM, s);
+        n_kernels += 4 + ((NB + 1) > 2048 ? 1 : 0);
     } else if (NB > 0) {
         CK(ctx->d_band_cnt.ensure((size_t)(NB + 1) * 4));
         CK(ctx->d_band_off.ensure((size_t)(NB + 1) * 4));
@@ -986,6 +1014,7 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
                          ctx->d_band_off.as<int>(), ctx->d_band_cnt.as<int>(), ctx->d_bin_edges.as<uint32_t>(),
                          ctx->d_cov.as<float>(), s);
     ctx->covered = true;
+    n_kernels += ctx->n_cov_tiles > 0;
     mark(6);
     int n_launches = 0;
     if (stop_after != SVGR_STOP_COVERAGE) {
@@ -997,6 +1026,7 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
             CK(cudaMemsetAsync(ctx->d_focal_flags.p, 0, (size_t)ctx->n_focal * 4, s));
             svgr_launch_focal_flags(T, ctx->d_focal_jobs.p, (int)ctx->focal_jobs.size(), ctx->n_focal_blocks,
                                     ctx->d_focal_flags.as<int>(), s);
+            n_kernels += ctx->n_focal_blocks > 0;
         }
         // external layers
         for (int i = 0; i < ctx->n_node; i++) {
@@ -1038,6 +1068,7 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
             } else
                 svgr_launch_canvas(T, ops, L.op_count, L.n_tiles, canvas, s);
             n_launches++;
+            n_kernels += L.n_tiles > 0;
         }
         if (!has_canvas)
             mark(7);
@@ -1065,6 +1096,9 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
         stats->n_ops = (int64_t)ctx->ops.size(), stats->n_levels = ctx->n_levels;
         stats->n_launches = n_launches;
         stats->mask_pixels = ctx->mask_pixels, stats->layer_pixels = ctx->layer_pixels;
+        stats->coverage_bytes = ctx->cov_floats * 4 + ctx->n_binned * 36;
+        stats->compose_bytes = ctx->compose_bytes, stats->canvas_pixels = ctx->canvas_pixels;
+        stats->n_kernels = n_kernels;
         stats->ms_plan = ms_plan, stats->ms_bin = ms_bin, stats->ms_coverage = ms_cov, stats->ms_compose = ms_cmp;
         stats->ms_canvas = ms_canvas, stats->ms_d2h = ms_d2h;
         stats->ms_total = ms_stroke + ms_flatten + ms_plan + ms_bin + ms_cov + ms_cmp + ms_canvas + ms_d2h;
