@@ -180,7 +180,7 @@ struct svgr_ctx {
     long long mask_pixels = 0, layer_pixels = 0, compose_bytes = 0, canvas_pixels = 0;
     int n_levels = 0;
     DevBuf d_masks, d_band_cnt, d_band_off, d_band_cur, d_bin_edges, d_cov, d_layers, d_ops, d_srcs, d_focal_jobs,
-        d_focal_flags, d_canvas, d_q;
+        d_focal_flags, d_canvas, d_q, d_tile_map;
     long long bin_cap = 0;
     long long n_binned = 0;
     bool planned = false, covered = false, composed = false;
@@ -557,7 +557,7 @@ struct Planner {
             memset(&p, 0, sizeof p);
             p.level = 1 << 30, p.cls = 3;
             OpRec &o = p.op;
-            o.kind = OP_CANVAS, o.mode = lin;
+            o.kind = OP_CANVAS, o.mode = MODE_OVER, o.aux = lin;
             o.r0 = 0, o.c0 = 0, o.rows = n.a, o.cols = n.b, o.stride = n.b, o.out_ch = 4;
             o.out_off = (long long)n.f[0];
             o.src_off = (int)ctx->srcs.size();
@@ -654,7 +654,8 @@ struct Planner {
                     tr = SVGR_STV_TR, tc = SVGR_STV_TC;
                     smem = (size_t)(SVGR_STV_TR + o.k0 - 1) * SVGR_STV_TC * 16;
                 } else if (o.kind == OP_CONV2D) {
-                    smem = (size_t)(SVGR_CMP_TR + o.k0 - 1) * (SVGR_CMP_TC + o.k1 - 1) * 16;
+                    tr = SVGR_C2D_TR, tc = SVGR_C2D_TC;
+                    smem = (size_t)(SVGR_C2D_TR + o.k0 - 1) * (SVGR_C2D_TC + o.k1 - 1) * 16;
                 }
                 o.ntile_c = std::max(1, ceil_div(o.cols, tc));
                 o.tile_base = (int)tiles;
@@ -1010,11 +1011,17 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
     }
     mark(5);
     // ---- coverage
+    {
+        long long max_tiles = ctx->n_cov_tiles;
+        for (auto &L : ctx->launches)
+            max_tiles = std::max<long long>(max_tiles, L.n_tiles);
+        CK(ctx->d_tile_map.ensure((size_t)std::max<long long>(max_tiles, 1) * 4));
+    }
     svgr_launch_coverage(ctx->d_edges.as<double>(), ctx->d_masks.as<MaskRec>(), ctx->n_path, (int)ctx->n_cov_tiles,
-                         ctx->d_band_off.as<int>(), ctx->d_band_cnt.as<int>(), ctx->d_bin_edges.as<uint32_t>(),
+                         ctx->d_tile_map.as<int>(), ctx->d_band_off.as<int>(), ctx->d_band_cnt.as<int>(), ctx->d_bin_edges.as<uint32_t>(),
                          ctx->d_cov.as<float>(), s);
     ctx->covered = true;
-    n_kernels += ctx->n_cov_tiles > 0;
+    n_kernels += ctx->n_cov_tiles > 0 ? 2 : 0;
     mark(6);
     int n_launches = 0;
     if (stop_after != SVGR_STOP_COVERAGE) {
@@ -1057,18 +1064,20 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
             const OpRec *ops = ctx->d_ops.as<OpRec>() + L.op_begin;
             if (L.cls == 3)
                 mark(7);
+            const int *tile_op = ctx->d_tile_map.as<int>();
+            svgr_launch_expand_ops(ops, L.op_count, L.n_tiles, ctx->d_tile_map.as<int>(), s);
             if (L.cls == 0)
-                svgr_launch_compose(T, ops, L.op_count, L.n_tiles, ctx->d_layers.as<float>(), s);
+                svgr_launch_compose(T, ops, tile_op, L.n_tiles, ctx->d_layers.as<float>(), nullptr, s);
             else if (L.cls == 1) {
-                if (svgr_launch_stencil(T, ops, L.op_count, L.n_tiles, L.smem, ctx->d_layers.as<float>(), s))
+                if (svgr_launch_stencil(T, ops, tile_op, L.n_tiles, L.smem, ctx->d_layers.as<float>(), s))
                     FAIL(SVGR_E_UNSUPPORTED, "stencil needs more shared memory than available");
             } else if (L.cls == 2) {
-                if (svgr_launch_conv2d(T, ops, L.op_count, L.n_tiles, L.smem, ctx->d_layers.as<float>(), s))
+                if (svgr_launch_conv2d(T, ops, tile_op, L.n_tiles, L.smem, ctx->d_layers.as<float>(), s))
                     FAIL(SVGR_E_UNSUPPORTED, "convolution needs more shared memory than available");
             } else
-                svgr_launch_canvas(T, ops, L.op_count, L.n_tiles, canvas, s);
+                svgr_launch_compose(T, ops, tile_op, L.n_tiles, ctx->d_layers.as<float>(), canvas, s);
             n_launches++;
-            n_kernels += L.n_tiles > 0;
+            n_kernels += L.n_tiles > 0 ? 2 : 0;
         }
         if (!has_canvas)
             mark(7);
@@ -1167,7 +1176,7 @@ void svgr_destroy(svgr_ctx *ctx)
                       &ctx->d_osub, &ctx->d_ocount, &ctx->d_edges, &ctx->d_edge_path, &ctx->d_minmax, &ctx->d_boxes,
                       &ctx->d_minmax_f64, &ctx->d_status, &ctx->d_masks, &ctx->d_band_cnt, &ctx->d_band_off,
                       &ctx->d_band_cur, &ctx->d_bin_edges, &ctx->d_cov, &ctx->d_layers, &ctx->d_ops, &ctx->d_srcs,
-                      &ctx->d_focal_jobs, &ctx->d_focal_flags, &ctx->d_canvas, &ctx->d_q};
+                      &ctx->d_focal_jobs, &ctx->d_focal_flags, &ctx->d_canvas, &ctx->d_q, &ctx->d_tile_map};
     for (DevBuf *b : bufs)
         b->release();
     ctx->pin_boxes.release(), ctx->pin_status.release(), ctx->pin_plan.release(), ctx->pin_out.release();

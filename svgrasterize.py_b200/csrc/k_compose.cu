@@ -25,10 +25,10 @@
 // against the tile rectangle into shared memory, preserving order.
 #include "svgr_device.cuh"
 
-#define CMP_TR 8
-#define CMP_TC 32
-#define CMP_CULL_MIN 8
-#define CMP_LIST 1024
+#define CMP_TR SVGR_CMP_TR   // 32 rows: 4 pixels per thread, 8 rows apart
+#define CMP_TC SVGR_CMP_TC   // 32 columns: one warp = 512 contiguous bytes of an RGBA row
+#define CMP_PX (CMP_TR / 8)
+#define CMP_CAP 48           // sources staged per round
 
 __device__ __forceinline__ float4 blend_px(int mode, const float *k, float4 d, float4 s)
 {
@@ -60,166 +60,179 @@ __device__ __forceinline__ float4 blend_px(int mode, const float *k, float4 d, f
     }
 }
 
-__device__ __forceinline__ int find_op(const OpRec *__restrict__ ops, int n_ops, int tile)
+template <class T>
+__device__ __forceinline__ void copy16(T *dst, const T *src, int part)
 {
-    int lo = 0, hi = n_ops - 1;
-    while (lo < hi) {
-        int mid = (lo + hi + 1) >> 1;
-        if (ops[mid].tile_base <= tile)
-            lo = mid;
-        else
-            hi = mid - 1;
-    }
-    return lo;
+    reinterpret_cast<uint4 *>(dst)[part] = __ldg(reinterpret_cast<const uint4 *>(src) + part);
 }
 
-__device__ __forceinline__ bool src_hits(const SrcRec &s, int r, int c)
+// One kernel for layer ops (float output) and canvas ops (RGBA8 output).  Per CTA:
+//   1. the op of this tile comes from the tile -> op table; its record is staged in shared memory
+//      (one 8-byte piece per thread) so that nobody chases it through global memory again;
+//   2. rounds: warp 0 culls the next sources against the tile rectangle (order preserved) and copies
+//      up to CMP_CAP surviving SrcRecs into shared memory; all threads then copy the PaintRecs those
+//      sources need; every thread folds the staged sources into its 4 pixels, issuing the 4 loads of a
+//      source back to back before using any of them.
+__global__ void __launch_bounds__(256, 3)
+compose_kernel(RenderTables T, const OpRec *__restrict__ ops, const int *__restrict__ tile_op,
+               float *__restrict__ layers_out, uint8_t *__restrict__ canvas_out)
 {
-    return r >= s.r0 && r < s.r0 + s.rows && c >= s.c0 && c < s.c0 + s.cols;
-}
-
-__global__ void __launch_bounds__(CMP_TR *CMP_TC)
-compose_kernel(RenderTables T, const OpRec *__restrict__ ops, int n_ops, float *__restrict__ layers_out)
-{
-    __shared__ int s_op;
-    __shared__ int s_list[CMP_LIST];
+    __shared__ __align__(16) OpRec s_op;
+    __shared__ __align__(16) SrcRec s_src[CMP_CAP];
+    __shared__ __align__(16) PaintRec s_paint[CMP_CAP];
+    __shared__ int s_idx[CMP_CAP];
     __shared__ int s_n, s_next;
 
-    if (threadIdx.x == 0)
-        s_op = find_op(ops, n_ops, blockIdx.x);
+    const int tid = threadIdx.x;
+    static_assert(sizeof(OpRec) % 8 == 0, "OpRec must be a multiple of 8 bytes");
+    if (tid < (int)(sizeof(OpRec) / 8)) {
+        const int opi = __ldg(tile_op + blockIdx.x);  // tile -> op table written by expand_ops_kernel
+        reinterpret_cast<uint2 *>(&s_op)[tid] = __ldg(reinterpret_cast<const uint2 *>(ops + opi) + tid);
+    }
+    if (tid == 0)
+        s_next = 0;
     __syncthreads();
-    const OpRec &op = ops[s_op];
+    const OpRec &op = s_op;
     const int local = blockIdx.x - op.tile_base;
     const int tr = local / op.ntile_c, tc = local - tr * op.ntile_c;
-    const int ty = threadIdx.x >> 5, tx = threadIdx.x & 31;
-    const int lr = tr * CMP_TR + ty, lc = tc * CMP_TC + tx;  // output-local
-    const int r = op.r0 + lr, c = op.c0 + lc;
-    const bool live = lr < op.rows && lc < op.cols;
+    const int ty = tid >> 5, tx = tid & 31;
+    const int lr0 = tr * CMP_TR + ty, lc = tc * CMP_TC + tx;  // output-local; pixel k is 8 k rows further down
+    const int r0 = op.r0 + lr0, c = op.c0 + lc;
+    const int tile_r0 = op.r0 + tr * CMP_TR, tile_c0 = op.c0 + tc * CMP_TC;
+    const int tile_r1 = min(tile_r0 + CMP_TR, op.r0 + op.rows), tile_c1 = min(tile_c0 + CMP_TC, op.c0 + op.cols);
+    const bool col_live = lc < op.cols;
     const SrcRec *srcs = T.srcs + op.src_off;
     const int mode = op.mode;
     const bool skip_outside = (mode == MODE_OVER);  // blending a zero source is the identity for OVER
+    const double x0 = (double)r0 + 0.5, y0 = (double)c + 0.5;  // pixel centre of pixel 0
 
-    float4 acc = f4(0.f, 0.f, 0.f, 0.f);
-    if (op.src_cnt <= CMP_CULL_MIN) {
-        if (live) {
-            for (int k = 0; k < op.src_cnt; k++) {
-                const SrcRec &s = srcs[k];
-                bool in = src_hits(s, r, c);
-                if (k > 0 && !in && skip_outside)
-                    continue;
-                float4 v = in ? fetch_src(T, s, r, c) : f4(0.f, 0.f, 0.f, 0.f);
-                acc = (k == 0) ? v : blend_px(mode, op.k, acc, v);
-            }
-        }
-    } else {
-        // order-preserving cull of the source list against the tile rectangle (warp 0), in rounds
-        const int tr0 = op.r0 + tr * CMP_TR, tc0 = op.c0 + tc * CMP_TC;
-        if (threadIdx.x == 0)
-            s_next = 0;
+    float4 acc[CMP_PX];
+#pragma unroll
+    for (int k = 0; k < CMP_PX; k++)
+        acc[k] = f4(0.f, 0.f, 0.f, 0.f);
+
+    for (;;) {
+        const int start = s_next;
         __syncthreads();
-        for (;;) {
-            int start = s_next;
-            __syncthreads();
-            if (start >= op.src_cnt)
-                break;
-            if (threadIdx.x < 32) {
-                int n = 0, k = start;
-                for (; k < op.src_cnt && n <= CMP_LIST - 32; k += 32) {
-                    int i = k + tx;
-                    bool hit = false;
-                    if (i < op.src_cnt) {
-                        const SrcRec &s = srcs[i];
-                        hit = (i == 0 || !skip_outside) ||
-                              (s.r0 < tr0 + CMP_TR && s.r0 + s.rows > tr0 && s.c0 < tc0 + CMP_TC && s.c0 + s.cols > tc0);
-                    }
-                    unsigned m = __ballot_sync(0xffffffffu, hit);
-                    if (hit)
-                        s_list[n + __popc(m & ((1u << tx) - 1))] = i;
-                    n += __popc(m);
+        if (start >= op.src_cnt)
+            break;
+        // ---- stage: order-preserving cull + copy of SrcRecs (warp 0)
+        if (tid < 32) {
+            int n = 0, k = start;
+            for (; k < op.src_cnt && n + 32 <= CMP_CAP; k += 32) {
+                int i = k + tx;
+                bool hit = false;
+                SrcRec rec;
+                if (i < op.src_cnt) {
+                    const uint4 *g = reinterpret_cast<const uint4 *>(srcs + i);
+                    uint4 *d = reinterpret_cast<uint4 *>(&rec);
+                    d[0] = __ldg(g), d[1] = __ldg(g + 1), d[2] = __ldg(g + 2), d[3] = __ldg(g + 3);
+                    hit = (i == 0 || !skip_outside) ||
+                          (rec.r0 < tile_r1 && rec.r0 + rec.rows > tile_r0 && rec.c0 < tile_c1 && rec.c0 + rec.cols > tile_c0);
                 }
-                if (tx == 0) {
-                    s_n = n;
-                    s_next = k < op.src_cnt ? k : op.src_cnt;
+                unsigned m = __ballot_sync(0xffffffffu, hit);
+                if (hit) {
+                    int pos = n + __popc(m & ((1u << tx) - 1));
+                    s_src[pos] = rec;
+                    s_idx[pos] = i;
+                }
+                n += __popc(m);
+            }
+            if (tx == 0) {
+                s_n = n;
+                s_next = k < op.src_cnt ? k : op.src_cnt;
+            }
+        }
+        __syncthreads();
+        const int n = s_n;
+        // ---- stage: paint records of the staged COVPAINT sources (14 x 16 bytes each)
+        {
+            static_assert(sizeof(PaintRec) == 224, "PaintRec layout");
+            const int part = tid & 15;
+            for (int j = tid >> 4; j < n; j += 16)
+                if (part < 14 && s_src[j].kind == SRC_COVPAINT)
+                    copy16(&s_paint[j], T.paints + s_src[j].paint, part);
+        }
+        __syncthreads();
+        // ---- fold
+        if (col_live) {
+            for (int j = 0; j < n; j++) {
+                const SrcRec &s = s_src[j];
+                const bool first = s_idx[j] == 0;
+                const bool cin = c >= s.c0 && c < s.c0 + s.cols;
+                bool in[CMP_PX];
+                float4 v[CMP_PX];
+                bool any = false;
+#pragma unroll
+                for (int k = 0; k < CMP_PX; k++) {
+                    int r = r0 + 8 * k;
+                    in[k] = cin && r >= s.r0 && r < s.r0 + s.rows && (lr0 + 8 * k) < op.rows;
+                    any |= in[k];
+                }
+                if (!any && skip_outside && !first)
+                    continue;
+#pragma unroll
+                for (int k = 0; k < CMP_PX; k++)
+                    v[k] = in[k] ? src_load(T, s, r0 + 8 * k, c) : f4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int k = 0; k < CMP_PX; k++) {
+                    if (in[k])
+                        v[k] = src_finish(T, s, &s_paint[j], v[k], x0 + 8.0 * k, y0);
+                    if (first)
+                        acc[k] = v[k];
+                    else if (in[k] || !skip_outside)
+                        acc[k] = blend_px(mode, op.k, acc[k], v[k]);
                 }
             }
-            __syncthreads();
-            if (live) {
-                int n = s_n;
-                for (int j = 0; j < n; j++) {
-                    int k = s_list[j];
-                    const SrcRec &s = srcs[k];
-                    bool in = src_hits(s, r, c);
-                    if (k > 0 && !in && skip_outside)
-                        continue;
-                    float4 v = in ? fetch_src(T, s, r, c) : f4(0.f, 0.f, 0.f, 0.f);
-                    acc = (k == 0) ? v : blend_px(mode, op.k, acc, v);
-                }
-            }
-            __syncthreads();
         }
+        __syncthreads();
     }
-    if (!live)
+    if (!col_live)
         return;
 
-    if (op.mul != 1.0f)
-        acc = f4(acc.x * op.mul, acc.y * op.mul, acc.z * op.mul, acc.w * op.mul);
-    if (op.post & POST_CLIP01)
-        acc = f4(clip01(acc.x), clip01(acc.y), clip01(acc.z), clip01(acc.w));
-    if (op.post & POST_ALPHA)
-        acc = f4(0.f, 0.f, 0.f, acc.w);
-    if (op.post & POST_MATRIX) {
-        const float *M = T.matrices + 20 * op.aux;  // row-major 4x5
-        float4 v = acc;
-        acc.x = clip01(M[0] * v.x + M[1] * v.y + M[2] * v.z + M[3] * v.w + M[4]);
-        acc.y = clip01(M[5] * v.x + M[6] * v.y + M[7] * v.z + M[8] * v.w + M[9]);
-        acc.z = clip01(M[10] * v.x + M[11] * v.y + M[12] * v.z + M[13] * v.w + M[14]);
-        acc.w = clip01(M[15] * v.x + M[16] * v.y + M[17] * v.z + M[18] * v.w + M[19]);
-    }
-    long long idx = (long long)lr * op.stride + lc;
-    if (op.post & POST_LUMA) {
-        // Scene.render mask branch: luma . rgb * alpha on the straight-alpha image (svgrasterize.py:734-736)
-        float l = (acc.x * 0.2125f + acc.y * 0.7154f + acc.z * 0.072f) * acc.w;
-        layers_out[op.out_off + idx] = l;
-    } else if (op.out_ch == 1) {
-        layers_out[op.out_off + idx] = acc.w;
-    } else {
-        reinterpret_cast<float4 *>(layers_out + op.out_off)[idx] = acc;
-    }
-}
-
-// Final step of a render (svgrasterize.py:3870-3881): the root layer, converted to the render's
-// premultiplied colour space, is blitted over a zero canvas and clipped to [0, 1] (canvas_merge_at),
-// converted to straight-alpha sRGB and quantised.  op.mode carries the render's linear_rgb flag,
-// op.src_cnt == 0 means "nothing rendered" (the canvas stays transparent).
-__global__ void __launch_bounds__(CMP_TR *CMP_TC)
-canvas_kernel(RenderTables T, const OpRec *__restrict__ ops, int n_ops, uint8_t *__restrict__ out)
-{
-    __shared__ int s_op;
-    if (threadIdx.x == 0)
-        s_op = find_op(ops, n_ops, blockIdx.x);
-    __syncthreads();
-    const OpRec &op = ops[s_op];
-    const int local = blockIdx.x - op.tile_base;
-    const int tr = local / op.ntile_c, tc = local - tr * op.ntile_c;
-    const int lr = tr * CMP_TR + (threadIdx.x >> 5), lc = tc * CMP_TC + (threadIdx.x & 31);
-    if (lr >= op.rows || lc >= op.cols)
-        return;
-    const int r = op.r0 + lr, c = op.c0 + lc;
-    float4 v = f4(0.f, 0.f, 0.f, 0.f);
-    if (op.src_cnt > 0) {
-        const SrcRec &s = T.srcs[op.src_off];
-        if (src_hits(s, r, c)) {
-            v = fetch_src(T, s, r, c);
-            v = f4(clip01(v.x), clip01(v.y), clip01(v.z), clip01(v.w));
+#pragma unroll
+    for (int k = 0; k < CMP_PX; k++) {
+        const int lr = lr0 + 8 * k;
+        if (lr >= op.rows)
+            continue;
+        float4 a = acc[k];
+        if (op.mul != 1.0f)
+            a = f4(a.x * op.mul, a.y * op.mul, a.z * op.mul, a.w * op.mul);
+        if (op.post & POST_CLIP01)
+            a = f4(clip01(a.x), clip01(a.y), clip01(a.z), clip01(a.w));
+        if (op.post & POST_ALPHA)
+            a = f4(0.f, 0.f, 0.f, a.w);
+        if (op.post & POST_MATRIX) {
+            const float *M = T.matrices + 20 * op.aux;  // row-major 4x5
+            float4 v = a;
+            a.x = clip01(M[0] * v.x + M[1] * v.y + M[2] * v.z + M[3] * v.w + M[4]);
+            a.y = clip01(M[5] * v.x + M[6] * v.y + M[7] * v.z + M[8] * v.w + M[9]);
+            a.z = clip01(M[10] * v.x + M[11] * v.y + M[12] * v.z + M[13] * v.w + M[14]);
+            a.w = clip01(M[15] * v.x + M[16] * v.y + M[17] * v.z + M[18] * v.w + M[19]);
+        }
+        const long long idx = (long long)lr * op.stride + lc;
+        if (op.kind == OP_CANVAS) {
+            // main() :3870-3881: the premultiplied result over a zero canvas, clipped to [0, 1]
+            // (canvas_merge_at :326), converted to straight-alpha sRGB (Layer.write_png :212) and quantised
+            // with round-half-even (np.round, :263).  op.aux carries the render's linear_rgb flag.
+            a = f4(clip01(a.x), clip01(a.y), clip01(a.z), clip01(a.w));
+            a = convert_px(a, SVGR_CONV(1, op.aux != 0, 0, 0));
+            // x * 255 + 1.5 * 2^23 leaves round-half-even(x * 255) in the low mantissa bits
+            uchar4 q;
+            q.x = (unsigned char)(__float_as_uint(a.x * 255.0f + 12582912.0f) & 0xffu);
+            q.y = (unsigned char)(__float_as_uint(a.y * 255.0f + 12582912.0f) & 0xffu);
+            q.z = (unsigned char)(__float_as_uint(a.z * 255.0f + 12582912.0f) & 0xffu);
+            q.w = (unsigned char)(__float_as_uint(a.w * 255.0f + 12582912.0f) & 0xffu);
+            reinterpret_cast<uchar4 *>(canvas_out + op.out_off)[idx] = q;
+        } else if (op.post & POST_LUMA) {
+            // Scene.render mask branch: luma . rgb * alpha on the straight-alpha image (svgrasterize.py:734-736)
+            layers_out[op.out_off + idx] = (a.x * 0.2125f + a.y * 0.7154f + a.z * 0.072f) * a.w;
+        } else if (op.out_ch == 1) {
+            layers_out[op.out_off + idx] = a.w;
+        } else {
+            reinterpret_cast<float4 *>(layers_out + op.out_off)[idx] = a;
         }
     }
-    v = convert_px(v, SVGR_CONV(1, op.mode != 0, 0, 0));
-    uchar4 q;
-    q.x = (unsigned char)__float2int_rn(v.x * 255.0f);
-    q.y = (unsigned char)__float2int_rn(v.y * 255.0f);
-    q.z = (unsigned char)__float2int_rn(v.z * 255.0f);
-    q.w = (unsigned char)__float2int_rn(v.w * 255.0f);
-    reinterpret_cast<uchar4 *>(out + op.out_off)[(long long)lr * op.stride + lc] = q;
 }
 
 // any(det < 0) over the mask bbox of a two-circle gradient fill (svgrasterize.py:1621-1622): the
@@ -249,7 +262,7 @@ __global__ void focal_flag_kernel(RenderTables T, const FocalJob *__restrict__ j
         if (i < n) {
             int r = j.r0 + (int)(i / j.cols), c = j.c0 + (int)(i % j.cols);
             double ux, uy, b, a;
-            px_to_user(p, r, c, &ux, &uy);
+            px_to_user(p, (double)r + 0.5, (double)c + 0.5, &ux, &uy);
             if (focal_det(p, ux, uy, &b, &a) < 0)
                 neg = true;
         }
@@ -259,17 +272,28 @@ __global__ void focal_flag_kernel(RenderTables T, const FocalJob *__restrict__ j
 }
 
 // ---------------------------------------------------------------------------------------------
-void svgr_launch_compose(const RenderTables &T, const OpRec *ops, int n_ops, int n_tiles, float *layers_out,
-                         cudaStream_t s)
+void svgr_launch_compose(const RenderTables &T, const OpRec *ops, const int *tile_op, int n_tiles, float *layers_out,
+                         uint8_t *canvas_out, cudaStream_t s)
 {
     if (n_tiles > 0)
-        compose_kernel<<<n_tiles, CMP_TR * CMP_TC, 0, s>>>(T, ops, n_ops, layers_out);
+        compose_kernel<<<n_tiles, 256, 0, s>>>(T, ops, tile_op, layers_out, canvas_out);
 }
 
-void svgr_launch_canvas(const RenderTables &T, const OpRec *ops, int n_ops, int n_tiles, uint8_t *out, cudaStream_t s)
+// tile -> op table of one launch: op i owns tiles [ops[i].tile_base, ops[i + 1].tile_base)
+__global__ void expand_ops_kernel(const OpRec *__restrict__ ops, int n_ops, int n_tiles, int *__restrict__ tile_op)
 {
-    if (n_tiles > 0)
-        canvas_kernel<<<n_tiles, CMP_TR * CMP_TC, 0, s>>>(T, ops, n_ops, out);
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_ops)
+        return;
+    int a = ops[i].tile_base, b = (i + 1 < n_ops) ? ops[i + 1].tile_base : n_tiles;
+    for (int t = a; t < b; t++)
+        tile_op[t] = i;
+}
+
+void svgr_launch_expand_ops(const OpRec *ops, int n_ops, int n_tiles, int *tile_op, cudaStream_t s)
+{
+    if (n_ops > 0 && n_tiles > 0)
+        expand_ops_kernel<<<(n_ops + 127) / 128, 128, 0, s>>>(ops, n_ops, n_tiles, tile_op);
 }
 
 void svgr_launch_focal_flags(const RenderTables &T, const void *jobs, int n_jobs, int n_blocks, int *flags,

@@ -285,28 +285,15 @@ __device__ __forceinline__ float fill_rule_apply(float m, int rule)
 }
 
 __global__ void __launch_bounds__(COV_THREADS)
-coverage_kernel(const double *__restrict__ edges, const MaskRec *__restrict__ masks, int n_masks,
-                const int *__restrict__ band_off, const int *__restrict__ band_cnt,
-                const uint32_t *__restrict__ bin_edges, float *__restrict__ cov)
+coverage_kernel(const double *__restrict__ edges, const MaskRec *__restrict__ masks,
+                const int *__restrict__ tile_mask, const int *__restrict__ band_off,
+                const int *__restrict__ band_cnt, const uint32_t *__restrict__ bin_edges, float *__restrict__ cov)
 {
     __shared__ __align__(16) float trace[SVGR_BAND_ROWS][SVGR_TILE_COLS];
-    __shared__ int s_mask;
 
-    // ---- tile -> (mask, band, column chunk): binary search in the tile_base prefix
+    // ---- tile -> (mask, band, column chunk) through the tile -> mask table (expand_masks_kernel)
     const int tile = blockIdx.x;
-    if (threadIdx.x == 0) {
-        int lo = 0, hi = n_masks - 1;
-        while (lo < hi) {
-            int mid = (lo + hi + 1) >> 1;
-            if (masks[mid].tile_base <= tile)
-                lo = mid;
-            else
-                hi = mid - 1;
-        }
-        s_mask = lo;
-    }
-    __syncthreads();
-    const MaskRec m = masks[s_mask];
+    const MaskRec m = masks[__ldg(tile_mask + tile)];
     const int local = tile - m.tile_base;
     const int band_local = local / m.ntile_c;
     const int chunk = local - band_local * m.ntile_c;
@@ -418,10 +405,23 @@ void svgr_launch_bin_fill(const double *edges, const uint32_t *edge_path, unsign
     bin_fill_kernel<<<(unsigned)blocks, 256, 0, s>>>(edges, edge_path, n_edges, masks, band_off, band_cursor, bin_edges);
 }
 
-void svgr_launch_coverage(const double *edges, const MaskRec *masks, int n_masks, int n_tiles, const int *band_off,
-                          const int *band_cnt, const uint32_t *bin_edges, float *cov, cudaStream_t s)
+__global__ void expand_masks_kernel(const MaskRec *__restrict__ masks, int n_masks, int n_tiles,
+                                    int *__restrict__ tile_mask)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_masks)
+        return;
+    int a = masks[i].tile_base, b = (i + 1 < n_masks) ? masks[i + 1].tile_base : n_tiles;
+    for (int t = a; t < b; t++)
+        tile_mask[t] = i;
+}
+
+void svgr_launch_coverage(const double *edges, const MaskRec *masks, int n_masks, int n_tiles, int *tile_mask,
+                          const int *band_off, const int *band_cnt, const uint32_t *bin_edges, float *cov,
+                          cudaStream_t s)
 {
     if (n_tiles <= 0)
         return;
-    coverage_kernel<<<n_tiles, COV_THREADS, 0, s>>>(edges, masks, n_masks, band_off, band_cnt, bin_edges, cov);
+    expand_masks_kernel<<<(n_masks + 127) / 128, 128, 0, s>>>(masks, n_masks, n_tiles, tile_mask);
+    coverage_kernel<<<n_tiles, COV_THREADS, 0, s>>>(edges, masks, tile_mask, band_off, band_cnt, bin_edges, cov);
 }

@@ -43,19 +43,6 @@ __device__ __forceinline__ void stencil_acc(float4 &a, float w, float4 v)
     }
 }
 
-__device__ __forceinline__ int find_op_f(const OpRec *__restrict__ ops, int n_ops, int tile)
-{
-    int lo = 0, hi = n_ops - 1;
-    while (lo < hi) {
-        int mid = (lo + hi + 1) >> 1;
-        if (ops[mid].tile_base <= tile)
-            lo = mid;
-        else
-            hi = mid - 1;
-    }
-    return lo;
-}
-
 // source pixel at source-local (i, j), zero outside
 __device__ __forceinline__ float4 load_local(const RenderTables &T, const SrcRec &s, int i, int j)
 {
@@ -146,15 +133,12 @@ __device__ __forceinline__ void stencil_v_body(const RenderTables &T, const OpRe
 }
 
 __global__ void __launch_bounds__(256)
-stencil_kernel(RenderTables T, const OpRec *__restrict__ ops, int n_ops, float *__restrict__ layers_out)
+stencil_kernel(RenderTables T, const OpRec *__restrict__ ops, const int *__restrict__ tile_op,
+               float *__restrict__ layers_out)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *sm = reinterpret_cast<float4 *>(smem_raw);
-    __shared__ int s_op;
-    if (threadIdx.x == 0)
-        s_op = find_op_f(ops, n_ops, blockIdx.x);
-    __syncthreads();
-    const OpRec &op = ops[s_op];
+    const OpRec &op = ops[__ldg(tile_op + blockIdx.x)];
     const int local = blockIdx.x - op.tile_base;
     if (op.kind == OP_STENCIL_H) {
         if (op.stencil == STENCIL_CONV)
@@ -175,21 +159,18 @@ stencil_kernel(RenderTables T, const OpRec *__restrict__ ops, int n_ops, float *
 
 // Direct 2-D "full" convolution: out[i, j] = sum_{a, b} k[a, b] . in[i - a, j - b]; tile 8 x 32.
 __global__ void __launch_bounds__(256)
-conv2d_kernel(RenderTables T, const OpRec *__restrict__ ops, int n_ops, float *__restrict__ layers_out)
+conv2d_kernel(RenderTables T, const OpRec *__restrict__ ops, const int *__restrict__ tile_op,
+              float *__restrict__ layers_out)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *sm = reinterpret_cast<float4 *>(smem_raw);
-    __shared__ int s_op;
-    if (threadIdx.x == 0)
-        s_op = find_op_f(ops, n_ops, blockIdx.x);
-    __syncthreads();
-    const OpRec &op = ops[s_op];
+    const OpRec &op = ops[__ldg(tile_op + blockIdx.x)];
     const SrcRec &s = T.srcs[op.src_off];
     const int local = blockIdx.x - op.tile_base;
     const int tr = local / op.ntile_c, tc = local - tr * op.ntile_c;
     const int kr = op.k0, kc = op.k1;
-    const int row0 = tr * SVGR_CMP_TR, col0 = tc * SVGR_CMP_TC;
-    const int srows = SVGR_CMP_TR + kr - 1, scols = SVGR_CMP_TC + kc - 1;
+    const int row0 = tr * SVGR_C2D_TR, col0 = tc * SVGR_C2D_TC;
+    const int srows = SVGR_C2D_TR + kr - 1, scols = SVGR_C2D_TC + kc - 1;
     for (int i = threadIdx.x; i < srows * scols; i += 256) {
         int rr = i / scols, cc = i - rr * scols;
         sm[i] = load_local(T, s, row0 - kr + 1 + rr, col0 - kc + 1 + cc);
@@ -222,7 +203,7 @@ static void ensure_attrs()
     }
 }
 
-int svgr_launch_stencil(const RenderTables &T, const OpRec *ops, int n_ops, int n_tiles, size_t smem_bytes,
+int svgr_launch_stencil(const RenderTables &T, const OpRec *ops, const int *tile_op, int n_tiles, size_t smem_bytes,
                         float *layers_out, cudaStream_t s)
 {
     if (n_tiles <= 0)
@@ -230,11 +211,11 @@ int svgr_launch_stencil(const RenderTables &T, const OpRec *ops, int n_ops, int 
     if (smem_bytes > SVGR_MAX_DYN_SMEM)
         return -1;
     ensure_attrs();
-    stencil_kernel<<<n_tiles, 256, smem_bytes, s>>>(T, ops, n_ops, layers_out);
+    stencil_kernel<<<n_tiles, 256, smem_bytes, s>>>(T, ops, tile_op, layers_out);
     return 0;
 }
 
-int svgr_launch_conv2d(const RenderTables &T, const OpRec *ops, int n_ops, int n_tiles, size_t smem_bytes,
+int svgr_launch_conv2d(const RenderTables &T, const OpRec *ops, const int *tile_op, int n_tiles, size_t smem_bytes,
                        float *layers_out, cudaStream_t s)
 {
     if (n_tiles <= 0)
@@ -242,6 +223,6 @@ int svgr_launch_conv2d(const RenderTables &T, const OpRec *ops, int n_ops, int n
     if (smem_bytes > SVGR_MAX_DYN_SMEM)
         return -1;
     ensure_attrs();
-    conv2d_kernel<<<n_tiles, 256, smem_bytes, s>>>(T, ops, n_ops, layers_out);
+    conv2d_kernel<<<n_tiles, 256, smem_bytes, s>>>(T, ops, tile_op, layers_out);
     return 0;
 }

@@ -24,9 +24,10 @@ __device__ __forceinline__ float srgb_to_lin1(float v)
 __device__ __forceinline__ float4 unpremultiply(float4 v)
 {
     if (v.w > 0.0001f) {
-        v.x = v.x / v.w;
-        v.y = v.y / v.w;
-        v.z = v.z / v.w;
+        float inv = __frcp_rn(v.w);  // one reciprocal instead of three divides (<= 1 ulp apart)
+        v.x = v.x * inv;
+        v.y = v.y * inv;
+        v.z = v.z * inv;
     }
     return f4(clip01(v.x), clip01(v.y), clip01(v.z), clip01(v.w));
 }
@@ -101,11 +102,10 @@ __device__ __forceinline__ float4 grad_color(double v, const StopRec *__restrict
     return o;  // NaN offsets match no interval: transparent black
 }
 
-__device__ __forceinline__ void px_to_user(const PaintRec &p, int r, int c, double *ux, double *uy)
+__device__ __forceinline__ void px_to_user(const PaintRec &p, double x, double y, double *ux, double *uy)
 {
-    // grad_pixels (svgrasterize.py:1653-1658): pixel centres; then transform.invert and
-    // the inverse gradientTransform, each as Transform.__call__ (:531-534)
-    double x = (double)r + 0.5, y = (double)c + 0.5;
+    // (x, y) = pixel centre (row + .5, col + .5) of grad_pixels (svgrasterize.py:1653-1658); then
+    // transform.invert and the inverse gradientTransform, each as Transform.__call__ (:531-534)
     double ax = fma(y, p.m1[1], x * p.m1[0]) + p.m1[2];
     double ay = fma(y, p.m1[4], x * p.m1[3]) + p.m1[5];
     if (p.has_m2) {
@@ -116,7 +116,7 @@ __device__ __forceinline__ void px_to_user(const PaintRec &p, int r, int c, doub
     *ux = ax, *uy = ay;
 }
 
-// det = b^2 - a c of the two-circle gradient (svgrasterize.py:1612-1620); returns t through *t
+// det = b^2 - a c of the two-circle gradient (svgrasterize.py:1612-1620)
 __device__ __forceinline__ double focal_det(const PaintRec &p, double ux, double uy, double *b_out, double *a_out)
 {
     double cx = p.g[0], cy = p.g[1], radius = p.g[2], fx = p.g[3], fy = p.g[4], fr = p.g[5];
@@ -131,16 +131,15 @@ __device__ __forceinline__ double focal_det(const PaintRec &p, double ux, double
     return b * b - a * cc;
 }
 
-// paint colour at the pixel (r, c) (global layer coordinates): premultiplied RGBA
-__device__ __forceinline__ float4 paint_eval(const RenderTables &T, const SrcRec &s, int r, int c)
+// Paint colour at the pixel centre (x, y) = (row + .5, col + .5): premultiplied RGBA.
+// `p` may live in shared memory.  pat/pat_stride: the pattern tile image (PAINT_PATTERN only).
+__device__ __forceinline__ float4 paint_eval(const RenderTables &T, const PaintRec &p, double x, double y,
+                                             const float4 *pat, int pat_stride)
 {
-    const PaintRec &p = T.paints[s.paint];
     if (p.kind == PAINT_SOLID)
         return f4(p.color[0], p.color[1], p.color[2], p.color[3]);
-    double ux, uy;
     if (p.kind == PAINT_PATTERN) {
         // Path.fill pattern branch (svgrasterize.py:1074-1094)
-        double x = (double)r + 0.5, y = (double)c + 0.5;
         double ax = fma(y, p.m1[1], x * p.m1[0]) + p.m1[2];
         double ay = fma(y, p.m1[4], x * p.m1[3]) + p.m1[5];
         ax = floored_mod(ax - p.g[0], p.g[2]);
@@ -152,10 +151,10 @@ __device__ __forceinline__ float4 paint_eval(const RenderTables &T, const SrcRec
         if (ic < 0) ic += p.pat_cols;
         if (ir < 0 || ic < 0 || ir >= p.pat_rows || ic >= p.pat_cols)
             return f4(0.f, 0.f, 0.f, 0.f);
-        const float4 *pat = reinterpret_cast<const float4 *>(T.layers + s.off2);
-        return pat[ir * s.stride2 + ic];
+        return __ldg(pat + ir * pat_stride + ic);
     }
-    px_to_user(p, r, c, &ux, &uy);
+    double ux, uy;
+    px_to_user(p, x, y, &ux, &uy);
     double t;
     if (p.kind == PAINT_LINEAR) {
         double vx = p.g[2] - p.g[0], vy = p.g[3] - p.g[1];
@@ -183,41 +182,45 @@ __device__ __forceinline__ float4 paint_eval(const RenderTables &T, const SrcRec
     return grad_color(grad_spread(t, p.spread), T.stops + p.stop_off, p.stop_cnt);
 }
 
-// Value of a source at global pixel (r, c), which must lie inside its bbox.
-__device__ __forceinline__ float4 fetch_src(const RenderTables &T, const SrcRec &s, int r, int c)
+// ---- source access, split so that a thread can issue the loads of several pixels before using them
+__device__ __forceinline__ bool src_hits(const SrcRec &s, int r, int c)
+{
+    return r >= s.r0 && r < s.r0 + s.rows && c >= s.c0 && c < s.c0 + s.cols;
+}
+
+// raw memory value of the source at (r, c) (inside its bbox): RGBA for SRC_L4, (a, a, a, a) otherwise
+__device__ __forceinline__ float4 src_load(const RenderTables &T, const SrcRec &s, int r, int c)
 {
     long long idx = (long long)(r - s.r0) * s.stride + (c - s.c0);
-    float4 v;
-    switch (s.kind) {
-    case SRC_L4:
-        v = __ldg(reinterpret_cast<const float4 *>(T.layers + s.off) + idx);
-        break;
-    case SRC_L1: {
-        float a = __ldg(T.layers + s.off + idx);
-        v = f4(a, a, a, a);
-        break;
-    }
-    case SRC_COV: {
-        float a = __ldg(T.cov + s.off + idx);
-        v = f4(a, a, a, a);
-        break;
-    }
-    case SRC_COVPAINT: {
-        float a = __ldg(T.cov + s.off + idx);
-        if (a == 0.f) {
-            v = f4(0.f, 0.f, 0.f, 0.f);
-        } else {
-            float4 p = paint_eval(T, s, r, c);
-            v = f4(p.x * a, p.y * a, p.z * a, p.w * a);
-        }
-        break;
-    }
-    default:
-        v = f4(0.f, 0.f, 0.f, 0.f);
+    if (s.kind == SRC_L4)
+        return __ldg(reinterpret_cast<const float4 *>(T.layers + s.off) + idx);
+    const float *base = (s.kind == SRC_L1) ? T.layers : T.cov;
+    float a = __ldg(base + s.off + idx);
+    return f4(a, a, a, a);
+}
+
+// paint, folded opacity and Layer.convert applied to a loaded value; (x, y) = pixel centre
+__device__ __forceinline__ float4 src_finish(const RenderTables &T, const SrcRec &s, const PaintRec *paint, float4 v,
+                                             double x, double y)
+{
+    if (s.kind == SRC_COVPAINT) {
+        if (v.w == 0.f)
+            return f4(0.f, 0.f, 0.f, 0.f);
+        float a = v.w;
+        float4 p = paint_eval(T, *paint, x, y, reinterpret_cast<const float4 *>(T.layers + s.off2), s.stride2);
+        v = f4(p.x * a, p.y * a, p.z * a, p.w * a);
     }
     if (s.mul != 1.0f)
         v = f4(v.x * s.mul, v.y * s.mul, v.z * s.mul, v.w * s.mul);
     if (s.kind != SRC_L1 && s.kind != SRC_COV && !conv_is_identity(s.conv))
         v = convert_px(v, s.conv);
     return v;
+}
+
+// Value of a source at global pixel (r, c), which must lie inside its bbox.
+__device__ __forceinline__ float4 fetch_src(const RenderTables &T, const SrcRec &s, int r, int c)
+{
+    float4 v = src_load(T, s, r, c);
+    const PaintRec *p = s.kind == SRC_COVPAINT ? T.paints + s.paint : nullptr;
+    return src_finish(T, s, p, v, (double)r + 0.5, (double)c + 0.5);
 }

@@ -38,20 +38,21 @@ void svgr_launch_bin_count(const double *edges, const uint32_t *edge_path, unsig
 void svgr_launch_bin_fill(const double *edges, const uint32_t *edge_path, unsigned long long n_edges,
                           const MaskRec *masks, const int *band_off, int *band_cursor, uint32_t *bin_edges,
                           int sm_count, cudaStream_t s);
-void svgr_launch_coverage(const double *edges, const MaskRec *masks, int n_masks, int n_tiles, const int *band_off,
-                          const int *band_cnt, const uint32_t *bin_edges, float *cov, cudaStream_t s);
+void svgr_launch_coverage(const double *edges, const MaskRec *masks, int n_masks, int n_tiles, int *tile_mask,
+                          const int *band_off, const int *band_cnt, const uint32_t *bin_edges, float *cov,
+                          cudaStream_t s);
 
 // k_compose.cu
-void svgr_launch_compose(const RenderTables &T, const OpRec *ops, int n_ops, int n_tiles, float *layers_out,
-                         cudaStream_t s);
-void svgr_launch_canvas(const RenderTables &T, const OpRec *ops, int n_ops, int n_tiles, uint8_t *out, cudaStream_t s);
+void svgr_launch_expand_ops(const OpRec *ops, int n_ops, int n_tiles, int *tile_op, cudaStream_t s);
+void svgr_launch_compose(const RenderTables &T, const OpRec *ops, const int *tile_op, int n_tiles, float *layers_out,
+                         uint8_t *canvas_out, cudaStream_t s);
 void svgr_launch_focal_flags(const RenderTables &T, const void *jobs, int n_jobs, int n_blocks, int *flags,
                              cudaStream_t s);
 
 // k_filters.cu
-int svgr_launch_stencil(const RenderTables &T, const OpRec *ops, int n_ops, int n_tiles, size_t smem_bytes,
+int svgr_launch_stencil(const RenderTables &T, const OpRec *ops, const int *tile_op, int n_tiles, size_t smem_bytes,
                         float *layers_out, cudaStream_t s);
-int svgr_launch_conv2d(const RenderTables &T, const OpRec *ops, int n_ops, int n_tiles, size_t smem_bytes,
+int svgr_launch_conv2d(const RenderTables &T, const OpRec *ops, const int *tile_op, int n_tiles, size_t smem_bytes,
                        float *layers_out, cudaStream_t s);
 
 // k_stroke.cu

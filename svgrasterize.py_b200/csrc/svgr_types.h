@@ -112,7 +112,9 @@ struct SrcRec {
     int32_t stride2; // pattern paint: pixels per row of the `pat` image
     int64_t off;     // float offset into the arena (coverage arena for SRC_COV*)
     int64_t off2;    // pattern paint: float offset of the `pat` image in the layer arena
+    int32_t pad[2];  // 64 bytes: staged into shared memory as four 16-byte pieces
 };
+static_assert(sizeof(SrcRec) == 64, "SrcRec must be 64 bytes");
 
 enum : int32_t {
     MODE_OVER = 0,
@@ -169,8 +171,10 @@ struct FocalJob {
 };
 
 // tile shapes (rows x cols of output pixels per CTA)
-#define SVGR_CMP_TR 8
+#define SVGR_CMP_TR 32
 #define SVGR_CMP_TC 32
+#define SVGR_C2D_TR 8
+#define SVGR_C2D_TC 32
 #define SVGR_STH_TR 8
 #define SVGR_STH_TC 128
 #define SVGR_STV_TR 64
