@@ -69,7 +69,8 @@ enum {
     SVGR_N_CMATRIX = 11,  /* Layer.color_matrix with matrix a */
     SVGR_N_OFFSET = 12,   /* feOffset: f[0..1] = (dx, dy), a = index into the offset-transform table */
     SVGR_N_MERGE_AT = 13, /* canvas_merge_at of child 0 onto zeros of bbox (a, b, c, d) */
-    SVGR_N_CANVAS = 14,   /* final canvas: a = rows, b = cols, flags bit0 = linear_rgb, f[0] = byte offset in the output */
+    SVGR_N_CANVAS = 14,   /* final canvas: a = rows, b = cols, (c, d) = first row / column (row-band renders),
+                             flags bit0 = linear_rgb, f[0] = byte offset in the output */
     SVGR_N_EXTERNAL = 15, /* a = index into the external layer table (host images handed in by the eager API) */
 };
 

@@ -558,7 +558,7 @@ struct Planner {
             p.level = 1 << 30, p.cls = 3;
             OpRec &o = p.op;
             o.kind = OP_CANVAS, o.mode = MODE_OVER, o.aux = lin;
-            o.r0 = 0, o.c0 = 0, o.rows = n.a, o.cols = n.b, o.stride = n.b, o.out_ch = 4;
+            o.r0 = n.c, o.c0 = n.d, o.rows = n.a, o.cols = n.b, o.stride = n.b, o.out_ch = 4;
             o.out_off = (long long)n.f[0];
             o.src_off = (int)ctx->srcs.size();
             o.src_cnt = v.kind == VAL_EMPTY ? 0 : 1;

@@ -73,7 +73,7 @@ __device__ __forceinline__ void copy16(T *dst, const T *src, int part)
 //      up to CMP_CAP surviving SrcRecs into shared memory; all threads then copy the PaintRecs those
 //      sources need; every thread folds the staged sources into its 4 pixels, issuing the 4 loads of a
 //      source back to back before using any of them.
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 4)
 compose_kernel(RenderTables T, const OpRec *__restrict__ ops, const int *__restrict__ tile_op,
                float *__restrict__ layers_out, uint8_t *__restrict__ canvas_out)
 {
@@ -154,33 +154,90 @@ compose_kernel(RenderTables T, const OpRec *__restrict__ ops, const int *__restr
                     copy16(&s_paint[j], T.paints + s_src[j].paint, part);
         }
         __syncthreads();
-        // ---- fold
+        // ---- fold: everything that does not depend on the pixel is hoisted out of the 4-pixel loops
         if (col_live) {
             for (int j = 0; j < n; j++) {
                 const SrcRec &s = s_src[j];
                 const bool first = s_idx[j] == 0;
-                const bool cin = c >= s.c0 && c < s.c0 + s.cols;
-                bool in[CMP_PX];
-                float4 v[CMP_PX];
-                bool any = false;
+                const int dr = r0 - s.r0, dc = c - s.c0;
+                unsigned live = 0;
+                if ((unsigned)dc < (unsigned)s.cols) {
 #pragma unroll
-                for (int k = 0; k < CMP_PX; k++) {
-                    int r = r0 + 8 * k;
-                    in[k] = cin && r >= s.r0 && r < s.r0 + s.rows && (lr0 + 8 * k) < op.rows;
-                    any |= in[k];
+                    for (int k = 0; k < CMP_PX; k++)
+                        if ((unsigned)(dr + 8 * k) < (unsigned)s.rows && lr0 + 8 * k < op.rows)
+                            live |= 1u << k;
                 }
-                if (!any && skip_outside && !first)
+                if (!live && skip_outside && !first)
                     continue;
+                const int base = dr * s.stride + dc, step = 8 * s.stride;  // a layer has < 2^31 pixels
+                float4 v[CMP_PX];
+                if (s.kind == SRC_L4) {
+                    const float4 *p = reinterpret_cast<const float4 *>(T.layers + s.off);
 #pragma unroll
-                for (int k = 0; k < CMP_PX; k++)
-                    v[k] = in[k] ? src_load(T, s, r0 + 8 * k, c) : f4(0.f, 0.f, 0.f, 0.f);
+                    for (int k = 0; k < CMP_PX; k++)
+                        v[k] = (live >> k & 1) ? __ldg(p + (base + k * step)) : f4(0.f, 0.f, 0.f, 0.f);
+                } else {
+                    const float *p = (s.kind == SRC_L1 ? T.layers : T.cov) + s.off;
+                    float a[CMP_PX];
 #pragma unroll
-                for (int k = 0; k < CMP_PX; k++) {
-                    if (in[k])
-                        v[k] = src_finish(T, s, &s_paint[j], v[k], x0 + 8.0 * k, y0);
-                    if (first)
+                    for (int k = 0; k < CMP_PX; k++)
+                        a[k] = (live >> k & 1) ? __ldg(p + (base + k * step)) : 0.f;
+                    if (s.kind == SRC_COVPAINT) {
+                        const PaintRec &pr = s_paint[j];
+                        if (pr.kind == PAINT_SOLID) {
+                            const float4 col = f4(pr.color[0], pr.color[1], pr.color[2], pr.color[3]);
+#pragma unroll
+                            for (int k = 0; k < CMP_PX; k++)
+                                v[k] = f4(col.x * a[k], col.y * a[k], col.z * a[k], col.w * a[k]);
+                        } else {
+                            const float4 *pat = reinterpret_cast<const float4 *>(T.layers + s.off2);
+#pragma unroll
+                            for (int k = 0; k < CMP_PX; k++) {
+                                v[k] = f4(0.f, 0.f, 0.f, 0.f);
+                                if (a[k] != 0.f) {
+                                    float4 q = paint_eval(T, pr, x0 + 8.0 * k, y0, pat, s.stride2);
+                                    v[k] = f4(q.x * a[k], q.y * a[k], q.z * a[k], q.w * a[k]);
+                                }
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < CMP_PX; k++)
+                            v[k] = f4(a[k], a[k], a[k], a[k]);
+                    }
+                }
+                if (s.mul != 1.0f) {
+                    const float m = s.mul;
+#pragma unroll
+                    for (int k = 0; k < CMP_PX; k++)
+                        v[k] = f4(v[k].x * m, v[k].y * m, v[k].z * m, v[k].w * m);
+                }
+                if (s.kind != SRC_L1 && s.kind != SRC_COV && !conv_is_identity(s.conv)) {
+#pragma unroll
+                    for (int k = 0; k < CMP_PX; k++)
+                        if (live >> k & 1)
+                            v[k] = convert_px(v[k], s.conv);
+                }
+                if (first) {
+#pragma unroll
+                    for (int k = 0; k < CMP_PX; k++)
                         acc[k] = v[k];
-                    else if (in[k] || !skip_outside)
+                } else if (mode == MODE_OVER) {
+#pragma unroll
+                    for (int k = 0; k < CMP_PX; k++) {
+                        const float q = 1.0f - v[k].w;  // a dead pixel has v = 0: the blend is the identity
+                        acc[k] = f4(v[k].x + acc[k].x * q, v[k].y + acc[k].y * q, v[k].z + acc[k].z * q,
+                                    v[k].w + acc[k].w * q);
+                    }
+                } else if (mode == MODE_IN) {
+#pragma unroll
+                    for (int k = 0; k < CMP_PX; k++) {
+                        const float da = acc[k].w;
+                        acc[k] = f4(v[k].x * da, v[k].y * da, v[k].z * da, v[k].w * da);
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < CMP_PX; k++)
                         acc[k] = blend_px(mode, op.k, acc[k], v[k]);
                 }
             }

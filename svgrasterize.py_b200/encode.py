@@ -311,6 +311,12 @@ class Encoder:
         self.canvases, self.canvas_bytes = [], 0
         self.roots = []
         self.cloud = {}  # node -> list of (node, path) pairs contributing end points when the node is non-empty
+        # row-band renders clip masks to the band but must resolve objectBoundingBox units against the
+        # whole canvas (a path outside the band still belongs to its group's bounding box)
+        self.cloud_viewport = None
+
+    def _cv(self, viewport):
+        return viewport if self.cloud_viewport is None else self.cloud_viewport
 
     # -- tables ------------------------------------------------------------------------------
     def _node(self, tag, a=0, b=0, c=0, d=0, children=(), flags=0, f=(0.0, 0.0, 0.0, 0.0)) -> int:
@@ -381,6 +387,7 @@ class Encoder:
         if self.engine is None:
             raise RuntimeError("objectBoundingBox units need an Engine (Encoder(engine=...))")
         sub = Encoder(self.engine)
+        sub.cloud_viewport = self.cloud_viewport
         root = build(sub)
         if sub._is_empty(root):
             return None
@@ -577,8 +584,8 @@ class Encoder:
                 return self._empty()
             pid = self.add_fill_path(path, transform, rule, viewport)
             own = lambda: self._cloud_bbox(  # noqa: E731
-                lambda e: e._leaf(e.add_fill_path(path, transform, rule, viewport), None, transform, True, linear_rgb,
-                                  None), transform)
+                lambda e: e._leaf(e.add_fill_path(path, transform, rule, self._cv(viewport)), None, transform, True,
+                                  linear_rgb, None), transform)
             return self._leaf(pid, paint, transform, mask_only, linear_rgb, own)
         if tag == S.RENDER_STROKE:
             path, paint, width, cap, join = args
@@ -588,8 +595,8 @@ class Encoder:
                 return self._empty()
             pid = self.add_stroke_path(path, transform, width, cap, join, viewport)
             own = lambda: self._cloud_bbox(  # noqa: E731
-                lambda e: e._leaf(e.add_stroke_path(path, transform, width, cap, join, viewport), None, transform, True,
-                                  linear_rgb, None), transform)
+                lambda e: e._leaf(e.add_stroke_path(path, transform, width, cap, join, self._cv(viewport)), None,
+                                  transform, True, linear_rgb, None), transform)
             return self._leaf(pid, paint, transform, mask_only, linear_rgb, own)
         if tag == S.RENDER_GROUP:
             kids = [self.encode(c, transform, mask_only, viewport, linear_rgb) for c in args]
@@ -618,7 +625,8 @@ class Encoder:
             if self._is_empty(t):
                 return t
             if bbox_units:
-                bbox = self._cloud_bbox(lambda e: e.encode(target, transform, mask_only, viewport, linear_rgb), transform)
+                bbox = self._cloud_bbox(
+                    lambda e: e.encode(target, transform, mask_only, self._cv(viewport), linear_rgb), transform)
                 if bbox is None:
                     return self._empty()
                 transform = self._bbox_transform(bbox, transform)
@@ -674,6 +682,38 @@ class Encoder:
         self.canvas_bytes += 4 * int(h) * int(w)
         self.roots.append(root)
         return len(self.canvases) - 1
+
+    def add_scene_band(self, scene, size, rows, halo=0, linear_rgb=False, transform=None) -> int:
+        """One row band [rows[0], rows[1]) of add_scene's canvas: masks are clipped to the band
+        plus `halo` rows (what filters inside the scene reach across), the canvas node writes only the band."""
+        w, h = int(size[0]), int(size[1])
+        a, b = max(0, int(rows[0])), min(h, int(rows[1]))
+        tr = canvas_transform() if transform is None else transform
+        lo, hi = max(0, a - int(halo)), min(h, b + int(halo))
+        self.cloud_viewport = [0, 0, h, w]
+        root = self.encode(scene, tr, False, [lo, 0, hi - lo, w], linear_rgb)
+        self.cloud_viewport = None
+        kids = [] if self._is_empty(root) else [root]
+        node = self._node(_lib.N_CANVAS, b - a, w, a, 0, children=kids, flags=int(bool(linear_rgb)),
+                          f=(self.canvas_bytes, 0, 0, 0))
+        self.canvases.append((node, self.canvas_bytes, b - a, w))
+        self.canvas_bytes += 4 * (b - a) * w
+        self.roots.append(root)
+        return len(self.canvases) - 1
+
+    def filter_reach(self) -> int:
+        """Upper bound of how many rows the filters recorded so far can carry a pixel: blur kernel rows,
+        morphology windows and feOffset shifts, summed over all filter nodes (conservative)."""
+        reach = 0
+        for tag, a, b, c, d, off, cnt, flags, f in self.nodes:
+            if tag == _lib.N_BLUR:
+                reach += self.kernels[a][0]
+            elif tag == _lib.N_MORPH:
+                reach += a
+            elif tag == _lib.N_OFFSET:
+                tr = self.offset_tr[a]
+                reach += int(abs(tr[0] * f[0]) + abs(tr[1] * f[1])) + 2
+        return reach
 
     def add_external(self, image, offset, pre_alpha, linear_rgb) -> int:
         img = np.ascontiguousarray(image, dtype=np.float32)

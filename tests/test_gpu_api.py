@@ -1,0 +1,180 @@
+"""The reference's call surface (svgrasterize_b200.api) on the GPU against the CPU oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def B():
+    import svgrasterize_b200 as B
+
+    return B
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import render as O
+
+    return O
+
+
+def _tr(B):
+    return B.Transform().matrix(0, 1, 0, 1, 0, 0) @ B.Transform().scale(3.0).rotate(0.15).translate(2, 1)
+
+
+def _olayer(O, layer):
+    return O.OLayer(layer.image.astype(np.float64), tuple(layer.offset), layer.pre_alpha, layer.linear_rgb)
+
+
+def test_path_mask_fill_stroke(B, O):
+    from oracle import geometry
+    from oracle.stroke import stroke_path
+    from svgrasterize_b200 import synth
+
+    path = synth._blob(np.random.default_rng(5), 30, 28, 14)
+    tr = _tr(B)
+    for rule in (None, "evenodd"):
+        layer, hull = path.mask(tr, rule, viewport=[0, 0, 120, 150])
+        ref_mask, ref_off, ref_edges = geometry.path_mask(path, tr, rule, [0, 0, 120, 150])
+        assert tuple(layer.offset) == tuple(ref_off) and layer.image.shape == (*ref_mask.shape, 1)
+        assert (layer.pre_alpha, layer.linear_rgb) == (True, True)
+        assert np.abs(layer.image[..., 0] - ref_mask).max() <= 1e-5
+        assert np.allclose(hull.bbox(tr), O.Cloud(ref_edges).bbox(tr), rtol=0, atol=0)
+    assert path.mask(tr, None, viewport=[500, 500, 10, 10]) is None
+    with pytest.raises(ValueError):
+        path.mask(tr, "bogus")
+    # gradient fill
+    stops = [(0.0, synth.color(1, 0, 0)), (1.0, synth.color(0, 0, 1, 0.5))]
+    grad = B.GradLinear(np.array([10.0, 10.0]), np.array([50.0, 40.0]), stops, None, "reflect", False, None)
+    got, _ = path.fill(tr, grad, None, None, linear_rgb=False)
+    ref, _ = O.fill_path(path, tr, grad, None, None, False)
+    assert tuple(got.offset) == tuple(ref.offset) and np.abs(got.image - ref.image).max() <= 1e-5
+    assert path.fill(tr, None) is None
+    # stroke outline: bit-exact
+    out = path.stroke(2.5, "round", "round")
+    ref = stroke_path(path, 2.5, "round", "round")
+    assert len(out.subpaths) == len(ref.subpaths)
+    for a, b in zip(out.subpaths, ref.subpaths):
+        assert len(a) == len(b)
+        for (ta, pa), (tb, pb) in zip(a, b):
+            assert ta == tb and np.array_equal(np.asarray(pa), np.asarray(pb))
+    with pytest.raises(ValueError):
+        path.stroke(1.0, "bogus")
+
+
+def test_flatten_batch_is_the_reference_set(B):
+    from oracle import geometry
+
+    rng = np.random.default_rng(11)
+    cubics = rng.uniform(0, 300, size=(200, 4, 2))
+    got = B.bezier3_flatten_batch(cubics, 0.1).reshape(-1, 4)
+    ref = geometry.flatten_cubics(cubics).reshape(-1, 4)
+    got = got[np.lexsort(got.T[::-1])]
+    ref = ref[np.lexsort(ref.T[::-1])]
+    assert got.shape == ref.shape and np.array_equal(got.view(np.uint64), ref.view(np.uint64))
+    assert B.bezier3_flatten_batch(np.zeros((0, 4, 2))).shape == (0, 2, 2)
+
+
+def test_layer_ops(B, O):
+    rng = np.random.default_rng(3)
+    a = rng.uniform(0, 1, size=(40, 50, 4))
+    a[..., :3] *= a[..., 3:]
+    b = rng.uniform(0, 1, size=(30, 45, 4))
+    b[..., :3] *= b[..., 3:]
+    m = rng.uniform(0, 1, size=(35, 35, 1))
+    la, lb = B.Layer(a.astype(np.float32), (3, 4), True, False), B.Layer(b.astype(np.float32), (10, -5), True, False)
+    lm = B.Layer(m.astype(np.float32), (0, 0), True, True)
+    oa, ob, om = _olayer(O, la), _olayer(O, lb), _olayer(O, lm)
+    for mode in (0, 1, 2, 3, 4, (0.3, 0.5, 0.4, 0.05)):
+        got = B.Layer.compose([la, lb], mode, linear_rgb=False)
+        ref = O.compose([oa, ob], mode, False)
+        assert tuple(got.offset) == tuple(ref.offset) and got.image.shape == ref.image.shape
+        assert (got.pre_alpha, got.linear_rgb) == (ref.pre_alpha, ref.linear_rgb)
+        assert np.abs(got.image - ref.image).max() <= 2e-5, mode
+    got, ref = B.Layer.compose([lm, la], 2, True), O.compose([om, oa], 2, True)
+    assert tuple(got.offset) == tuple(ref.offset) and np.abs(got.image - ref.image).max() <= 2e-5
+    assert B.Layer.compose([la, B.Layer(b.astype(np.float32), (500, 500), True, False)], 2) is None
+    assert B.Layer.compose([la]) is la and B.Layer.compose([]) is None
+    with pytest.raises(ValueError):
+        B.Layer.compose([la, lb], 9)
+    # convert round trip, opacity
+    for pre, lin in ((False, True), (True, True), (False, False)):
+        got, ref = la.convert(pre, lin), O.convert(oa, pre, lin)
+        assert (got.pre_alpha, got.linear_rgb) == (pre, lin) and np.abs(got.image - ref.image).max() <= 2e-5
+    got, ref = la.opacity(0.4, True), O.opacity(oa, 0.4, True)
+    assert np.abs(got.image - ref.image).max() <= 2e-5
+    # filters
+    mat = np.eye(4, 5)
+    mat[0, 1], mat[2, 4], mat[3, 3] = 0.4, 0.1, 0.8
+    got, ref = la.color_matrix(mat), O.color_matrix(oa, mat)
+    assert (got.pre_alpha, got.linear_rgb) == (False, True) and np.abs(got.image - ref.image).max() <= 2e-5
+    with pytest.raises(ValueError):
+        la.color_matrix(np.eye(4))
+    for k0, k1, method in ((3, 5, "max"), (4, 2, "min")):
+        got, ref = la.morphology(k0, k1, method), O.morphology(oa, k0, k1, method)
+        assert got.image.shape == ref.image.shape and tuple(got.offset) == tuple(ref.offset)
+        assert np.abs(got.image - ref.image).max() <= 2e-5
+    with pytest.raises(ValueError):
+        la.morphology(2, 2, "avg")
+    sep = B.blur_kernel(B.Transform().matrix(0, 1, 0, 1, 0, 0).scale(2.0), (1.5, 2.5))
+    rot = B.blur_kernel(B.Transform().rotate(0.5).scale(2.0, 1.3), (2.0, 0.8))
+    assert np.allclose(sep, O.blur_kernel(B.Transform().matrix(0, 1, 0, 1, 0, 0).scale(2.0), (1.5, 2.5)), atol=0, rtol=0)
+    for kern in (sep, rot):
+        got, ref = la.convolve(kern), O.convolve(oa, kern)
+        assert got.image.shape == ref.image.shape and tuple(got.offset) == tuple(ref.offset)
+        assert np.abs(got.image - ref.image).max() <= 2e-5
+
+
+def test_scene_render_and_canvas(B, O):
+    from svgrasterize_b200 import synth
+
+    scene, size = synth.icon_scene(4), synth.icon_size()
+    tr = B.Transform().matrix(0, 1, 0, 1, 0, 0)
+    vp = [0, 0, size[1], size[0]]
+    got, hull = scene.render(tr, viewport=vp)
+    ref, cloud = O.render(scene, tr, viewport=vp)
+    assert tuple(got.offset) == tuple(ref.offset) and got.image.shape == ref.image.shape
+    assert np.abs(got.image - ref.image).max() <= 2e-5
+    assert np.array_equal(np.asarray(hull.bbox(tr)), np.asarray(cloud.bbox(tr)))
+    mask, _ = scene.render(tr, mask_only=True, viewport=vp)
+    mref, _ = O.render(scene, tr, True, vp)
+    assert mask.image.shape == mref.image.shape and np.abs(mask.image - mref.image).max() <= 2e-5
+    u8 = B.render_canvas(scene, size)
+    assert np.abs(u8.astype(int) - O.render_canvas(scene, size).astype(int)).max() <= 1
+    png = B.canvas_to_png(u8)
+    assert png[:8] == b"\x89PNG\r\n\x1a\n"
+
+
+def test_canvas_helpers(B, O):
+    rng = np.random.default_rng(8)
+    base = rng.uniform(0, 1, size=(20, 30, 4)).astype(np.float32)
+    base[..., :3] *= base[..., 3:]
+    over = rng.uniform(0, 1, size=(12, 40, 4)).astype(np.float32)
+    over[..., :3] *= over[..., 3:]
+    ref = O.merge_at(base.astype(np.float64).copy(), over.astype(np.float64), (15, -4))
+    got = B.canvas_merge_at(base.copy(), over, (15, -4))
+    assert np.abs(got - ref).max() <= 2e-5
+    pooled = B.pooling(base, (3, 2), method="max")
+    want = O.morphology(O.OLayer(base.astype(np.float64), (0, 0), True, True), 3, 2, "max").image
+    assert np.abs(pooled - want).max() <= 1e-6
+    img, off = B.canvas_merge_union([(base, (0, 0)), (over, (5, 5))], full=False)
+    want, woff = O.merge_over([(base.astype(np.float64), (0, 0)), (over.astype(np.float64), (5, 5))], 0)
+    assert tuple(off) == tuple(woff) and np.abs(img - want).max() <= 2e-5
+
+
+def test_row_bands_reassemble_to_the_full_render(B, O):
+    """Single huge render sharded by row bands: each band rendered on its own must equal
+    the same rows of the full render -- including under a blur + dilate filter stack (halo by redundant
+    compute) -- so that the NCCL gather of bands is the only multi-GPU step."""
+    from svgrasterize_b200 import parallel as P, synth
+    from svgrasterize_b200.engine import default_engine
+
+    eng = default_engine()
+    for scene, size in ((synth.filter_stack_scene(160), (160, 160)), (synth.icon_scene(1), synth.icon_size())):
+        full = B.render_canvas(scene, size)
+        for world in (2, 3):
+            bands = [P.render_band(eng, scene, size, world, r) for r in range(world)]
+            got = np.concatenate(bands, axis=0)
+            assert got.shape == full.shape
+            assert np.abs(got.astype(int) - full.astype(int)).max() <= 1

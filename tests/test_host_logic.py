@@ -1,0 +1,161 @@
+"""CPU tests of the host side: the C-ABI library loads and exports what include/svgr_b200.h declares,
+record layouts agree, the encoder lowers scenes the way Scene.render walks them, and the multi-GPU
+partitioning reassembles a canvas (world_size 2 over gloo).  No GPU compute is called here."""
+import os
+import re
+import socket
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden_names, load_golden
+
+
+def test_library_exports_every_declared_symbol():
+    from svgrasterize_b200 import _lib
+
+    L = _lib.lib()  # also checks sizeof() of every record against the numpy / ctypes layouts
+    header = open(os.path.join(ROOT, "include", "svgr_b200.h")).read()
+    declared = set(re.findall(r"\b(svgr_[a-z_0-9]+)\s*\(", header))
+    assert declared, "no declarations found"
+    for name in declared:
+        assert hasattr(L, name), name
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    assert L.svgr_version() == 100
+
+
+def test_arc_expansion_is_bit_exact():
+    """svgr_arc_to_cubics (host, libm) against the oracle's arc_to_bezier3 restatement."""
+    from oracle import geometry
+    from svgrasterize_b200 import encode, synth
+
+    path = synth.rect_path(3, 4, 40, 30, 7.5, 5.25)
+    tags, data, sub = encode.device_path(path)
+    assert (tags != 3).all() and sub[-1] == len(tags)
+    _lines, cubics = geometry.path_lines_cubics(path)
+    got = data[tags == 2].reshape(-1, 4, 2)
+    assert got.shape == cubics.shape and np.array_equal(got.view(np.uint64), cubics.view(np.uint64))
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if n.startswith(("demo_prompt", "icon_", "synth_icon", "demo_icons_w512"))])
+def test_encoder_visits_leaves_in_reference_order(name):
+    """One path record per Path.mask call of the reference, in call order (tests/golden leaf_bbox)."""
+    from svgrasterize_b200 import encode
+
+    scene, size, linear_rgb, z = load_golden(name)
+    prog = encode.encode_scene(scene, size, linear_rgb)
+    assert len(prog.paths) == len(z["leaf_bbox"])
+    assert prog.canvas_bytes == 4 * int(size[0]) * int(size[1])
+    nodes = prog.nodes
+    for i, n in enumerate(nodes):  # children precede parents
+        kids = prog.children[n["child_off"]: n["child_off"] + n["child_cnt"]]
+        assert (kids < i).all()
+
+
+def test_program_concat_shifts_every_index_space():
+    from svgrasterize_b200 import _lib, encode, synth
+
+    progs = [encode.encode_scene(synth.icon_scene(s), synth.icon_size()) for s in range(3)]
+    cat = encode.Program.concat(progs)
+    assert len(cat.paths) == sum(len(p.paths) for p in progs)
+    assert cat.canvas_bytes == sum(p.canvas_bytes for p in progs)
+    assert max(int(cat.seg_path.max()), int(cat.strokes["path"].max())) == len(cat.paths) - 1
+    assert int(cat.stroke_sub_off[-1]) == len(cat.stroke_tag) and (np.diff(cat.stroke_sub_off) >= 0).all()
+    assert int(cat.strokes["path"].max()) < len(cat.paths)
+    leaf = cat.nodes["tag"] == _lib.N_LEAF
+    assert int(cat.nodes["a"][leaf].max()) == len(cat.paths) - 1
+    assert int(cat.nodes["b"][leaf].max()) == len(cat.paints) - 1
+    assert int(cat.paints["flag"].max()) == cat.n_focal - 1
+    canv = cat.nodes[cat.nodes["tag"] == _lib.N_CANVAS]
+    assert list(canv["f"][:, 0]) == [0.0, progs[0].canvas_bytes, progs[0].canvas_bytes + progs[1].canvas_bytes]
+    for i, n in enumerate(cat.nodes):
+        kids = cat.children[n["child_off"]: n["child_off"] + n["child_cnt"]]
+        assert (kids < i).all() and (kids >= 0).all()
+
+
+def test_blur_kernel_matches_oracle():
+    from oracle import render as O
+    from svgrasterize_b200 import encode
+    from svgrasterize_b200.scene import Transform
+
+    for tr, sigma in ((Transform().matrix(0, 1, 0, 1, 0, 0).scale(2.0), (2.0, 2.0)),
+                      (Transform().rotate(0.4).scale(1.5, 0.8), (3.0, 1.0)),
+                      (Transform().scale(0.1), (2.0, 2.0))):
+        a, b = encode.blur_kernel(tr, sigma), O.blur_kernel(tr, sigma)
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert a.shape == b.shape and np.array_equal(a, b)
+
+
+def test_shard_and_band_arithmetic():
+    from svgrasterize_b200 import parallel as P
+
+    for n, world in ((100000, 8), (7, 4), (3, 8)):
+        spans = [P.shard_range(n, world, r) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
+    for h, world in ((4096, 8), (131, 4), (30, 8)):
+        bands = [P.band_rows(h, world, r) for r in range(world)]
+        assert bands[0][0] == 0 and max(b for _, b in bands) == h
+        assert all(a[1] == b[0] or b[0] == h for a, b in zip(bands, bands[1:]))
+
+
+def _gloo_worker(rank, world, port, height, width, q):
+    import torch
+    import torch.distributed as dist
+
+    from svgrasterize_b200 import parallel as P
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    a, b = P.band_rows(height, world, rank)
+    rows = torch.arange(a, b, dtype=torch.int64).view(-1, 1, 1)
+    band = ((rows * 7 + torch.arange(width).view(1, -1, 1) * 3 + torch.arange(4).view(1, 1, -1)) % 251).to(torch.uint8)
+    out = P.gather_bands(band, height, width, world, rank, dist)
+    if rank == 0:
+        q.put(out.numpy())
+    dist.destroy_process_group()
+
+
+def test_band_gather_world_size_2_gloo():
+    """The N > 1 path of a single huge render: two ranks each produce a band, rank 0 reassembles."""
+    import torch.multiprocessing as mp
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    height, width, world = 37, 16, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, world, port, height, width, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rows = np.arange(height).reshape(-1, 1, 1)
+    want = ((rows * 7 + np.arange(width).reshape(1, -1, 1) * 3 + np.arange(4).reshape(1, 1, -1)) % 251).astype(np.uint8)
+    assert got.shape == want.shape and np.array_equal(got, want)
+
+
+def test_band_encoding_covers_the_canvas():
+    from svgrasterize_b200 import _lib, encode, parallel as P, synth
+
+    scene, size = synth.filter_stack_scene(96), (96, 96)
+    probe = encode.Encoder()
+    probe.add_scene(scene, size)
+    halo = probe.filter_reach()
+    assert halo >= 21 + 6  # 21-row Gaussian + 6-row dilate window at identity scale
+    total = 0
+    for r in range(3):
+        a, b = P.band_rows(96, 3, r)
+        enc = encode.Encoder()
+        enc.add_scene_band(scene, size, (a, b), halo)
+        prog = enc.finish()
+        canv = prog.nodes[prog.nodes["tag"] == _lib.N_CANVAS][0]
+        assert (canv["a"], canv["b"], canv["c"]) == (b - a, 96, a)
+        vp = prog.paths[0]["viewport"]
+        assert vp[0] == max(0, a - halo) and vp[0] + vp[2] == min(96, b + halo)
+        total += prog.canvas_bytes
+    assert total == 96 * 96 * 4
