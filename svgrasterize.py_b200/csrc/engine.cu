@@ -92,11 +92,14 @@ struct PinBuf {
     }
 };
 
-enum { VAL_EMPTY = 0 };  // otherwise SRC_L4 / SRC_L1 / SRC_COV / SRC_COVPAINT
+// Value of a node: VAL_EMPTY, one of SRC_L4 / SRC_L1 / SRC_COV / SRC_COVPAINT, or VAL_LUMA (planner only:
+// the luminance mask of a materialised RGBA layer that has not been written out as a layer of its own).
+enum { VAL_EMPTY = 0, VAL_LUMA = 100 };
 
 struct Val {
     int kind = VAL_EMPTY;
-    int r0 = 0, c0 = 0, rows = 0, cols = 0;
+    int r0 = 0, c0 = 0, rows = 0, cols = 0;  // valid region
+    int br0 = 0, bc0 = 0;                    // global coordinates of storage element 0
     int stride = 0;
     int paint = -1;
     float mul = 1.0f;
@@ -105,7 +108,16 @@ struct Val {
     long long off2 = 0;
     int stride2 = 0;
     int level = 0;
-    bool one_channel() const { return kind == SRC_L1 || kind == SRC_COV; }
+    int luma_conv = 0;  // VAL_LUMA: Layer.convert code applied before the luminance
+    // stencil: the value is multiplied by a one-channel view (a fused compose IN)
+    int st_kind = 0;  // 0 none, else SRC_MOD_*
+    int st_br0 = 0, st_bc0 = 0, st_stride = 0, st_conv = 0;
+    long long st_off = 0;
+    float st_mul = 1.0f;
+    // producer (for the canvas fusion)
+    int op_index = -1, owner = -1;
+    bool one_channel() const { return kind == SRC_L1 || kind == SRC_COV || kind == VAL_LUMA; }
+    bool is_virtual() const { return kind == SRC_COVPAINT || kind == VAL_LUMA || mul != 1.0f || st_kind != 0; }
 };
 
 struct PlannedOp {
@@ -200,6 +212,7 @@ struct Planner {
     svgr_ctx *ctx;
     std::string err;
     long long layer_top = 0;
+    std::vector<int> uses;  // how many nodes read each node
 
     explicit Planner(svgr_ctx *c) : ctx(c) {}
 
@@ -207,6 +220,7 @@ struct Planner {
     {
         Val v;
         v.kind = kind, v.r0 = r0, v.c0 = c0, v.rows = rows, v.cols = cols, v.pre = pre, v.lin = lin, v.level = level;
+        v.br0 = r0, v.bc0 = c0;
         layer_top = align4(layer_top);
         v.off = layer_top;
         if (kind == SRC_L4) {
@@ -226,6 +240,7 @@ struct Planner {
         memset(&s, 0, sizeof s);
         s.kind = v.kind;
         s.r0 = v.r0, s.c0 = v.c0, s.rows = v.rows, s.cols = v.cols;
+        s.br0 = v.br0, s.bc0 = v.bc0;
         s.stride = v.stride;
         s.paint = v.paint;
         s.conv = v.one_channel() ? 0 : SVGR_CONV(v.pre, v.lin, want_pre, want_lin);
@@ -234,6 +249,32 @@ struct Planner {
         s.off2 = v.off2, s.stride2 = v.stride2;
         return s;
     }
+
+    // Appends the source entries of `v` as seen by a consumer that wants (want_pre, want_lin): one entry,
+    // plus a stencil modifier entry when v carries a fused compose-IN.  A stencil cannot be combined with a
+    // pending colour conversion (the reference converts the already clipped layer), and a deferred luminance
+    // is only usable as a stencil: both cases are written out as layers first.  Returns the level of v.
+    int push_src(std::vector<SrcRec> &ss, Val v, int want_pre, int want_lin)
+    {
+        if (v.kind == VAL_LUMA)
+            v = materialize(v);
+        if (v.st_kind && !v.one_channel() && !(v.pre == want_pre && v.lin == want_lin))
+            v = materialize(v);
+        ss.push_back(src_of(v, want_pre, want_lin));
+        if (v.st_kind) {
+            SrcRec m;
+            memset(&m, 0, sizeof m);
+            m.kind = v.st_kind;
+            m.r0 = v.r0, m.c0 = v.c0, m.rows = v.rows, m.cols = v.cols;  // same rectangle as the owner: culled together
+            m.br0 = v.st_br0, m.bc0 = v.st_bc0, m.stride = v.st_stride;
+            m.off = v.st_off, m.mul = v.st_mul, m.conv = v.st_conv;
+            ss.push_back(m);
+        }
+        return v.level;
+    }
+
+    // a view the single-source stencil kernels can read: no modifier, no deferred luminance
+    Val plain(const Val &v) { return (v.st_kind || v.kind == VAL_LUMA) ? materialize(v) : v; }
 
     // emits an op producing `out` from srcs
     void emit(int cls, int kind, const Val &out, const std::vector<SrcRec> &ss, int mode, int post, float mul, int level,
@@ -263,18 +304,32 @@ struct Planner {
     Val unary(const Val &v, int out_kind, int want_pre, int want_lin, int out_pre, int out_lin, int post, float mul,
               int aux = 0)
     {
-        Val out = alloc(out_kind, v.r0, v.c0, v.rows, v.cols, out_pre, out_lin, v.level + 1);
-        emit(0, OP_COMPOSE, out, {src_of(v, want_pre, want_lin)}, MODE_OVER, post, mul, out.level, nullptr, aux);
+        std::vector<SrcRec> ss;
+        int level = push_src(ss, v, want_pre, want_lin) + 1;
+        Val out = alloc(out_kind, v.r0, v.c0, v.rows, v.cols, out_pre, out_lin, level);
+        emit(0, OP_COMPOSE, out, ss, MODE_OVER, post, mul, out.level, nullptr, aux);
         return out;
     }
 
     Val materialize(const Val &v)
     {
-        if (v.kind == VAL_EMPTY || ((v.kind == SRC_L4 || v.kind == SRC_L1) && v.mul == 1.0f))
+        if (v.kind == VAL_EMPTY || !v.is_virtual())
             return v;
-        if (v.one_channel())
-            return unary(v, SRC_L1, v.pre, v.lin, v.pre, v.lin, POST_NONE, 1.0f);
-        return unary(v, SRC_L4, v.pre, v.lin, v.pre, v.lin, POST_NONE, 1.0f);
+        if (v.kind == VAL_LUMA) {
+            // Scene.render mask branch (svgrasterize.py:733-737): luminance of the straight-alpha image
+            Val l4 = v;
+            l4.kind = SRC_L4;
+            SrcRec s = src_of(l4, 0, 0);
+            s.conv = v.luma_conv;
+            Val out = alloc(SRC_L1, v.r0, v.c0, v.rows, v.cols, v.pre, v.lin, v.level + 1);
+            emit(0, OP_COMPOSE, out, {s}, MODE_OVER, POST_LUMA, 1.0f, out.level);
+            return out;
+        }
+        std::vector<SrcRec> ss;
+        push_src(ss, v, v.pre, v.lin);  // identity conversion: never recurses into materialize
+        Val out = alloc(v.one_channel() ? SRC_L1 : SRC_L4, v.r0, v.c0, v.rows, v.cols, v.pre, v.lin, v.level + 1);
+        emit(0, OP_COMPOSE, out, ss, MODE_OVER, POST_NONE, 1.0f, out.level);
+        return out;
     }
 
     // Layer.compose (svgrasterize.py:178-207)
@@ -285,10 +340,6 @@ struct Planner {
         if (layers.size() == 1)
             return layers[0];
         int pre = mode != MODE_ARITH;
-        int level = 0;
-        for (auto &l : layers)
-            level = std::max(level, l.level);
-        level += 1;
         int r0, c0, r1, c1;
         if (mode == MODE_IN) {
             r0 = c0 = INT32_MIN, r1 = c1 = INT32_MAX;
@@ -305,11 +356,14 @@ struct Planner {
                 r1 = std::max(r1, l.r0 + l.rows), c1 = std::max(c1, l.c0 + l.cols);
             }
         }
-        Val out = alloc(SRC_L4, r0, c0, r1 - r0, c1 - c0, pre, lin, level);
         std::vector<SrcRec> ss;
-        ss.reserve(layers.size());
+        ss.reserve(layers.size() + 2);
+        int level = 0;
         for (auto &l : layers)
-            ss.push_back(src_of(l, pre, lin));
+            level = std::max(level, push_src(ss, l, pre, lin));
+        level += 1;
+        Val out = alloc(SRC_L4, r0, c0, r1 - r0, c1 - c0, pre, lin, level);
+        out.op_index = (int)ctx->ops.size();
         emit(0, OP_COMPOSE, out, ss, mode, POST_NONE, 1.0f, level, k);
         return out;
     }
@@ -341,6 +395,7 @@ struct Planner {
                 break;
             out.kind = n.b < 0 ? SRC_COV : SRC_COVPAINT;
             out.r0 = m.r0, out.c0 = m.c0, out.rows = m.rows, out.cols = m.cols, out.stride = m.stride;
+            out.br0 = m.r0, out.bc0 = m.c0;
             out.off = m.off;
             out.paint = n.b;
             out.pre = 1, out.lin = n.b < 0 ? 1 : (n.c != 0);
@@ -383,9 +438,11 @@ struct Planner {
             break;
         }
         case SVGR_N_OPACITY: {
-            const Val &v = child(0);
+            Val v = child(0);
             if (v.kind == VAL_EMPTY)
                 break;
+            if (v.kind == VAL_LUMA)
+                v = materialize(v);
             float value = (float)n.f[0];
             if (v.one_channel() || (v.pre == 1 && v.lin == lin)) {
                 out = v;  // Layer.opacity: convert is a relabel here, the multiply folds into the source
@@ -403,6 +460,32 @@ struct Planner {
             }
             if (child(0).kind == VAL_EMPTY || child(1).kind == VAL_EMPTY)
                 break;
+            {
+                // compose([stencil, image], IN) = image x stencil alpha on the intersection
+                // (svgrasterize.py:382-416 with :290).  When the image needs no conversion the product is not
+                // written out: the image keeps its storage and gains a stencil that its consumer applies.
+                const Val &S = child(0), &I = child(1);
+                bool img_ok = (I.kind == SRC_L4 || I.kind == SRC_COVPAINT) && I.st_kind == 0 && I.pre == 1 && I.lin == lin;
+                bool st_ok = S.st_kind == 0 && (S.kind == SRC_COV || S.kind == SRC_L1 || S.kind == VAL_LUMA ||
+                                                (S.kind == SRC_L4 && S.pre == 1 && S.lin == lin));
+                if (img_ok && st_ok) {
+                    int r0 = std::max(S.r0, I.r0), c0 = std::max(S.c0, I.c0);
+                    int r1 = std::min(S.r0 + S.rows, I.r0 + I.rows), c1 = std::min(S.c0 + S.cols, I.c0 + I.cols);
+                    if (r1 - r0 <= 0 || c1 - c0 <= 0)
+                        break;
+                    out = I;
+                    out.r0 = r0, out.c0 = c0, out.rows = r1 - r0, out.cols = c1 - c0;
+                    out.st_kind = S.kind == SRC_COV ? SRC_MOD_COV
+                                  : S.kind == SRC_L1 ? SRC_MOD_L1
+                                  : S.kind == SRC_L4 ? SRC_MOD_L4A
+                                                     : SRC_MOD_LUMA;
+                    out.st_br0 = S.br0, out.st_bc0 = S.bc0, out.st_stride = S.stride, out.st_off = S.off;
+                    out.st_mul = S.mul, out.st_conv = S.luma_conv;
+                    out.level = std::max(I.level, S.level);
+                    out.op_index = -1;
+                    break;
+                }
+            }
             out = compose({child(0), child(1)}, MODE_IN, nullptr, lin);
             break;
         }
@@ -413,6 +496,14 @@ struct Planner {
             if (v.one_channel()) {
                 err = "luminance mask of a one-channel layer (the reference raises here)";
                 return false;
+            }
+            if (v.kind == SRC_L4 && v.st_kind == 0 && !(n.flags & 2)) {
+                out = v;  // deferred: becomes a stencil modifier of the masked layer, or a layer on demand
+                out.kind = VAL_LUMA;
+                out.luma_conv = SVGR_CONV(v.pre, v.lin, 0, lin);
+                out.pre = 0, out.lin = lin;
+                out.op_index = -1;
+                break;
             }
             out = unary(v, SRC_L1, 0, lin, 0, lin, POST_LUMA, 1.0f);
             break;
@@ -445,7 +536,10 @@ struct Planner {
             if (v.kind == VAL_EMPTY)
                 break;
             int pre = n.a < 0 ? v.pre : (n.a != 0), l = n.b < 0 ? v.lin : (n.b != 0);
-            if (v.one_channel() || (v.pre == pre && v.lin == l)) {
+            if (v.kind == VAL_LUMA) {
+                out = materialize(v);
+                out.pre = pre, out.lin = l;
+            } else if (v.one_channel() || (v.pre == pre && v.lin == l)) {
                 out = v;
                 out.pre = pre, out.lin = l;
             } else {
@@ -454,7 +548,7 @@ struct Planner {
             break;
         }
         case SVGR_N_BLUR: {
-            const Val &v = child(0);
+            const Val v = plain(child(0));
             if (v.kind == VAL_EMPTY)
                 break;
             if (n.a < 0 || n.a >= (int)ctx->h_kernels.size()) {
@@ -479,7 +573,7 @@ struct Planner {
             break;
         }
         case SVGR_N_MORPH: {
-            const Val &v = child(0);
+            const Val v = plain(child(0));
             if (v.kind == VAL_EMPTY)
                 break;
             int k0 = n.a, k1 = n.b;
@@ -524,14 +618,11 @@ struct Planner {
             double ux = fma(x, inv[0], y * inv[1]) + inv[2], uy = fma(x, inv[3], y * inv[4]) + inv[5];
             ux = ux + n.f[0], uy = uy + n.f[1];
             double tx = fma(ux, f[0], uy * f[1]) + f[2], ty = fma(ux, f[3], uy * f[4]) + f[5];
-            out = v;
-            out.r0 = v.r0 + (py_int(tx) - v.r0);
-            out.c0 = v.c0 + (py_int(ty) - v.c0);
-            if (v.kind == SRC_COVPAINT || v.kind == SRC_COV) {  // keep mask-relative sources anchored: materialise first
-                Val mat = materialize(v);
-                out = mat;
-                out.r0 = mat.r0 + (py_int(tx) - v.r0);
-                out.c0 = mat.c0 + (py_int(ty) - v.c0);
+            // paint is evaluated at global pixel centres and stencils are anchored: move only real layers
+            out = (v.kind == SRC_COVPAINT || v.kind == VAL_LUMA || v.st_kind) ? materialize(v) : v;
+            {
+                int dr = py_int(tx) - v.r0, dc = py_int(ty) - v.c0;
+                out.r0 += dr, out.c0 += dc, out.br0 += dr, out.bc0 += dc;
             }
             break;
         }
@@ -542,9 +633,14 @@ struct Planner {
             if (n.c <= 0 || n.d <= 0)
                 break;
             // canvas_merge_at onto zeros (svgrasterize.py:304-327): no conversion, result clipped to [0, 1]
-            Val o2 = alloc(SRC_L4, n.a, n.b, n.c, n.d, v.pre, v.lin, v.level + 1);
-            emit(0, OP_COMPOSE, o2, {src_of(v, v.pre, v.lin)}, MODE_OVER, POST_CLIP01, 1.0f, o2.level);
-            out = o2;
+            {
+                Val vv = v.kind == VAL_LUMA ? materialize(v) : v;
+                std::vector<SrcRec> ss;
+                int level = push_src(ss, vv, vv.pre, vv.lin) + 1;
+                Val o2 = alloc(SRC_L4, n.a, n.b, n.c, n.d, vv.pre, vv.lin, level);
+                emit(0, OP_COMPOSE, o2, ss, MODE_OVER, POST_CLIP01, 1.0f, o2.level);
+                out = o2;
+            }
             break;
         }
         case SVGR_N_CANVAS: {
@@ -553,22 +649,45 @@ struct Planner {
                 err = "Only RGBA layers are supported";
                 return false;
             }
-            PlannedOp p;
-            memset(&p, 0, sizeof p);
-            p.level = 1 << 30, p.cls = 3;
-            OpRec &o = p.op;
-            o.kind = OP_CANVAS, o.mode = MODE_OVER, o.aux = lin;
-            o.r0 = n.c, o.c0 = n.d, o.rows = n.a, o.cols = n.b, o.stride = n.b, o.out_ch = 4;
-            o.out_off = (long long)n.f[0];
-            o.src_off = (int)ctx->srcs.size();
-            o.src_cnt = v.kind == VAL_EMPTY ? 0 : 1;
-            o.mul = 1.0f;
-            if (v.kind != VAL_EMPTY)
-                ctx->srcs.push_back(src_of(v, 1, lin));
-            if (o.rows < 0 || o.cols < 0 || o.out_off < 0 || o.out_off + 4ll * o.rows * o.cols > ctx->canvas_bytes) {
+            long long out_off = (long long)n.f[0];
+            if (n.a < 0 || n.b < 0 || out_off < 0 || out_off + 4ll * n.a * n.b > ctx->canvas_bytes) {
                 err = "canvas node outside the output buffer";
                 return false;
             }
+            // When the root is an over-group that nobody else reads, its fold writes the canvas directly
+            // (clip, straight-alpha sRGB, RGBA8) instead of a float layer that is read back once.
+            if (v.kind == SRC_L4 && !v.is_virtual() && v.op_index >= 0 && v.owner == ch[0] && uses[ch[0]] == 1 &&
+                v.pre == 1 && v.lin == lin) {
+                PlannedOp &po = ctx->ops[v.op_index];
+                if (po.cls == 0 && po.op.kind == OP_COMPOSE && po.op.mode == MODE_OVER && po.op.post == POST_NONE &&
+                    po.op.mul == 1.0f) {
+                    po.cls = 3;
+                    OpRec &o = po.op;
+                    o.kind = OP_CANVAS, o.aux = lin;
+                    o.r0 = n.c, o.c0 = n.d, o.rows = n.a, o.cols = n.b, o.stride = n.b, o.out_ch = 4;
+                    o.out_off = out_off;
+                    ctx->layer_pixels -= (long long)v.rows * v.cols;
+                    out = Val();
+                    break;
+                }
+            }
+            PlannedOp p;
+            memset(&p, 0, sizeof p);
+            p.cls = 3;
+            OpRec &o = p.op;
+            o.kind = OP_CANVAS, o.mode = MODE_OVER, o.aux = lin;
+            o.r0 = n.c, o.c0 = n.d, o.rows = n.a, o.cols = n.b, o.stride = n.b, o.out_ch = 4;
+            o.out_off = out_off;
+            o.mul = 1.0f;
+            std::vector<SrcRec> ss;
+            int level = 0;
+            if (v.kind != VAL_EMPTY)
+                level = push_src(ss, v, 1, lin);
+            p.level = level + 1;
+            o.src_off = (int)ctx->srcs.size();
+            o.src_cnt = (int)ss.size();
+            for (auto &sr : ss)
+                ctx->srcs.push_back(sr);
             ctx->ops.push_back(p);
             out = v;
             break;
@@ -591,6 +710,8 @@ struct Planner {
         }
         if ((n.flags & 2) && out.kind != VAL_EMPTY)
             out = materialize(out);
+        if (out.op_index >= 0 && out.owner < 0)
+            out.owner = i;
         return true;
     }
 
@@ -627,6 +748,19 @@ struct Planner {
         }
         c->n_bands = band, c->n_cov_tiles = tile, c->cov_floats = cov_top;
         // ---- nodes
+        uses.assign(c->n_node, 0);
+        for (int i = 0; i < c->n_node; i++) {
+            const svgr_node &n = c->h_nodes[i];
+            for (int k = 0; k < n.child_cnt; k++) {
+                int ch = c->h_children[n.child_off + k];
+                if (ch >= 0 && ch < c->n_node)
+                    uses[ch]++;
+            }
+            if (n.tag == SVGR_N_LEAF && n.d >= 0 && n.d < c->n_node)
+                uses[n.d]++;
+            if (n.flags & 2)
+                uses[i]++;  // read back by the caller
+        }
         c->vals.assign(c->n_node, Val());
         for (int i = 0; i < c->n_node; i++)
             if (!node(i, c->vals[i]))
@@ -684,20 +818,21 @@ struct Planner {
             const OpRec &o = po.op;
             if (po.cls == 3) {
                 c->canvas_pixels += (long long)o.rows * o.cols;
-                continue;
+                c->compose_bytes += (long long)o.rows * o.cols * 4;  // RGBA8 out
+            } else {
+                c->compose_bytes += (long long)o.rows * o.cols * o.out_ch * 4;
             }
-            c->compose_bytes += (long long)o.rows * o.cols * o.out_ch * 4;
             for (int k = 0; k < o.src_cnt; k++) {
                 const SrcRec &sr = c->srcs[o.src_off + k];
                 long long rr, cc;
-                if (po.cls == 0) {
+                if (po.cls == 0 || po.cls == 3) {
                     rr = std::min(o.r0 + o.rows, sr.r0 + sr.rows) - std::max(o.r0, sr.r0);
                     cc = std::min(o.c0 + o.cols, sr.c0 + sr.cols) - std::max(o.c0, sr.c0);
                 } else {
                     rr = sr.rows, cc = sr.cols;
                 }
                 if (rr > 0 && cc > 0)
-                    c->compose_bytes += rr * cc * (sr.kind == SRC_L4 ? 16 : 4);
+                    c->compose_bytes += rr * cc * ((sr.kind == SRC_L4 || sr.kind == SRC_MOD_L4A || sr.kind == SRC_MOD_LUMA) ? 16 : 4);
             }
         }
         return true;
@@ -1062,8 +1197,6 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
         }
         for (auto &L : ctx->launches) {
             const OpRec *ops = ctx->d_ops.as<OpRec>() + L.op_begin;
-            if (L.cls == 3)
-                mark(7);
             const int *tile_op = ctx->d_tile_map.as<int>();
             svgr_launch_expand_ops(ops, L.op_count, L.n_tiles, ctx->d_tile_map.as<int>(), s);
             if (L.cls == 0)
@@ -1079,8 +1212,7 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
             n_launches++;
             n_kernels += L.n_tiles > 0 ? 2 : 0;
         }
-        if (!has_canvas)
-            mark(7);
+        mark(7);
         mark(8);
         if (has_canvas && out && !out_on_device)
             CK(cudaMemcpyAsync(out, canvas, (size_t)ctx->canvas_bytes, cudaMemcpyDeviceToHost, s));
@@ -1319,7 +1451,7 @@ int svgr_node_info(svgr_ctx *ctx, int32_t node, int32_t *info)
     info[0] = v.kind == VAL_EMPTY ? 0 : (v.one_channel() ? 2 : 1);
     info[1] = v.r0, info[2] = v.c0, info[3] = v.rows, info[4] = v.cols;
     info[5] = v.pre, info[6] = v.lin;
-    info[7] = (v.kind == SRC_COVPAINT || v.mul != 1.0f) ? 1 : 0;  // 1: not materialised, svgr_read_node refuses
+    info[7] = v.is_virtual() ? 1 : 0;  // 1: not materialised, svgr_read_node refuses
     return SVGR_OK;
 }
 
@@ -1332,7 +1464,7 @@ int svgr_read_node(svgr_ctx *ctx, int32_t node, float *out)
     const Val &v = ctx->vals[node];
     if (v.kind == VAL_EMPTY)
         return SVGR_OK;
-    if (v.kind == SRC_COVPAINT || v.mul != 1.0f)
+    if (v.is_virtual())
         FAIL(SVGR_E_INVALID, "node is not materialised (set flags bit 1 on it)");
     if (v.kind == SRC_L4) {
         CK(cudaMemcpy(out, ctx->d_layers.as<float>() + v.off, (size_t)v.rows * v.cols * 16, cudaMemcpyDeviceToHost));

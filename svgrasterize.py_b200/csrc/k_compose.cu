@@ -106,10 +106,42 @@ compose_kernel(RenderTables T, const OpRec *__restrict__ ops, const int *__restr
     const bool skip_outside = (mode == MODE_OVER);  // blending a zero source is the identity for OVER
     const double x0 = (double)r0 + 0.5, y0 = (double)c + 0.5;  // pixel centre of pixel 0
 
-    float4 acc[CMP_PX];
+    // acc = fold so far; pend = the source being assembled (it may still be multiplied by stencil
+    // modifier entries that follow it) and is blended into acc when the next source starts
+    float4 acc[CMP_PX], pend[CMP_PX];
+    unsigned pend_live = 0;
+    bool have_pend = false, pend_first = false;
 #pragma unroll
     for (int k = 0; k < CMP_PX; k++)
-        acc[k] = f4(0.f, 0.f, 0.f, 0.f);
+        acc[k] = f4(0.f, 0.f, 0.f, 0.f), pend[k] = f4(0.f, 0.f, 0.f, 0.f);
+
+    auto flush = [&]() {
+        if (!have_pend)
+            return;
+        have_pend = false;
+        if (pend_first) {
+#pragma unroll
+            for (int k = 0; k < CMP_PX; k++)
+                acc[k] = pend[k];
+        } else if (mode == MODE_OVER) {
+#pragma unroll
+            for (int k = 0; k < CMP_PX; k++) {
+                const float q = 1.0f - pend[k].w;  // a dead pixel has pend = 0: the blend is the identity
+                acc[k] = f4(pend[k].x + acc[k].x * q, pend[k].y + acc[k].y * q, pend[k].z + acc[k].z * q,
+                            pend[k].w + acc[k].w * q);
+            }
+        } else if (mode == MODE_IN) {
+#pragma unroll
+            for (int k = 0; k < CMP_PX; k++) {
+                const float da = acc[k].w;
+                acc[k] = f4(pend[k].x * da, pend[k].y * da, pend[k].z * da, pend[k].w * da);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < CMP_PX; k++)
+                acc[k] = blend_px(mode, op.k, acc[k], pend[k]);
+        }
+    };
 
     for (;;) {
         const int start = s_next;
@@ -158,6 +190,19 @@ compose_kernel(RenderTables T, const OpRec *__restrict__ ops, const int *__restr
         if (col_live) {
             for (int j = 0; j < n; j++) {
                 const SrcRec &s = s_src[j];
+                if (s.kind >= SRC_MOD_COV) {
+                    // stencil modifier of the pending source (clip / luminance mask that is never materialised)
+                    if (have_pend && pend_live) {
+#pragma unroll
+                        for (int k = 0; k < CMP_PX; k++)
+                            if (pend_live >> k & 1) {
+                                const float m = mod_value(T, s, r0 + 8 * k, c);
+                                pend[k] = f4(pend[k].x * m, pend[k].y * m, pend[k].z * m, pend[k].w * m);
+                            }
+                    }
+                    continue;
+                }
+                flush();
                 const bool first = s_idx[j] == 0;
                 const int dr = r0 - s.r0, dc = c - s.c0;
                 unsigned live = 0;
@@ -169,8 +214,8 @@ compose_kernel(RenderTables T, const OpRec *__restrict__ ops, const int *__restr
                 }
                 if (!live && skip_outside && !first)
                     continue;
-                const int base = dr * s.stride + dc, step = 8 * s.stride;  // a layer has < 2^31 pixels
-                float4 v[CMP_PX];
+                const int base = (r0 - s.br0) * s.stride + (c - s.bc0), step = 8 * s.stride;  // a layer has < 2^31 px
+                float4 *v = pend;
                 if (s.kind == SRC_L4) {
                     const float4 *p = reinterpret_cast<const float4 *>(T.layers + s.off);
 #pragma unroll
@@ -218,34 +263,14 @@ compose_kernel(RenderTables T, const OpRec *__restrict__ ops, const int *__restr
                         if (live >> k & 1)
                             v[k] = convert_px(v[k], s.conv);
                 }
-                if (first) {
-#pragma unroll
-                    for (int k = 0; k < CMP_PX; k++)
-                        acc[k] = v[k];
-                } else if (mode == MODE_OVER) {
-#pragma unroll
-                    for (int k = 0; k < CMP_PX; k++) {
-                        const float q = 1.0f - v[k].w;  // a dead pixel has v = 0: the blend is the identity
-                        acc[k] = f4(v[k].x + acc[k].x * q, v[k].y + acc[k].y * q, v[k].z + acc[k].z * q,
-                                    v[k].w + acc[k].w * q);
-                    }
-                } else if (mode == MODE_IN) {
-#pragma unroll
-                    for (int k = 0; k < CMP_PX; k++) {
-                        const float da = acc[k].w;
-                        acc[k] = f4(v[k].x * da, v[k].y * da, v[k].z * da, v[k].w * da);
-                    }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < CMP_PX; k++)
-                        acc[k] = blend_px(mode, op.k, acc[k], v[k]);
-                }
+                have_pend = true, pend_first = first, pend_live = live;
             }
         }
         __syncthreads();
     }
     if (!col_live)
         return;
+    flush();
 
 #pragma unroll
     for (int k = 0; k < CMP_PX; k++) {

@@ -191,7 +191,7 @@ __device__ __forceinline__ bool src_hits(const SrcRec &s, int r, int c)
 // raw memory value of the source at (r, c) (inside its bbox): RGBA for SRC_L4, (a, a, a, a) otherwise
 __device__ __forceinline__ float4 src_load(const RenderTables &T, const SrcRec &s, int r, int c)
 {
-    long long idx = (long long)(r - s.r0) * s.stride + (c - s.c0);
+    long long idx = (long long)(r - s.br0) * s.stride + (c - s.bc0);
     if (s.kind == SRC_L4)
         return __ldg(reinterpret_cast<const float4 *>(T.layers + s.off) + idx);
     const float *base = (s.kind == SRC_L1) ? T.layers : T.cov;
@@ -223,4 +223,25 @@ __device__ __forceinline__ float4 fetch_src(const RenderTables &T, const SrcRec 
     float4 v = src_load(T, s, r, c);
     const PaintRec *p = s.kind == SRC_COVPAINT ? T.paints + s.paint : nullptr;
     return src_finish(T, s, p, v, (double)r + 0.5, (double)c + 0.5);
+}
+
+// one-channel value of a stencil modifier entry at (r, c) (inside the owner's valid region)
+__device__ __forceinline__ float mod_value(const RenderTables &T, const SrcRec &s, int r, int c)
+{
+    long long idx = (long long)(r - s.br0) * s.stride + (c - s.bc0);
+    float m;
+    if (s.kind == SRC_MOD_COV) {
+        m = __ldg(T.cov + s.off + idx);
+    } else if (s.kind == SRC_MOD_L1) {
+        m = __ldg(T.layers + s.off + idx);
+    } else if (s.kind == SRC_MOD_L4A) {
+        m = __ldg(T.layers + s.off + 4 * idx + 3);
+    } else {
+        float4 v = __ldg(reinterpret_cast<const float4 *>(T.layers + s.off) + idx);
+        if (s.mul != 1.0f)
+            v = f4(v.x * s.mul, v.y * s.mul, v.z * s.mul, v.w * s.mul);
+        v = convert_px(v, s.conv);
+        return (v.x * 0.2125f + v.y * 0.7154f + v.z * 0.072f) * v.w;  // svgrasterize.py:734-736
+    }
+    return m * s.mul;
 }

@@ -97,6 +97,12 @@ enum : int32_t {
     SRC_L1 = 2,        // one-channel f32 layer (alpha is the image, svgrasterize.py:283-284)
     SRC_COV = 3,       // coverage mask used as a one-channel layer (mask_only leaves)
     SRC_COVPAINT = 4,  // coverage x paint: a Path.fill layer that is never materialised
+    // stencil modifiers: an entry of these kinds multiplies the source entry before it by a one-channel
+    // value (compose IN of a clip / mask that is never materialised, svgrasterize.py:698-741)
+    SRC_MOD_COV = 8,    // coverage mask (clip path rendered mask-only)
+    SRC_MOD_L1 = 9,     // one-channel layer
+    SRC_MOD_L4A = 10,   // alpha of an RGBA layer
+    SRC_MOD_LUMA = 11,  // luminance x alpha of an RGBA layer after Layer.convert (conv)
 };
 
 // conversion codes: bit0 source pre_alpha, bit1 source linear, bit2 target pre, bit3 target linear
@@ -104,7 +110,7 @@ enum : int32_t {
 
 struct SrcRec {
     int32_t kind;
-    int32_t r0, c0, rows, cols;
+    int32_t r0, c0, rows, cols;  // valid region (global coordinates)
     int32_t stride;  // pixels per row
     int32_t paint;   // SRC_COVPAINT
     int32_t conv;    // SVGR_CONV code; identity when source == target flags
@@ -112,8 +118,8 @@ struct SrcRec {
     int32_t stride2; // pattern paint: pixels per row of the `pat` image
     int64_t off;     // float offset into the arena (coverage arena for SRC_COV*)
     int64_t off2;    // pattern paint: float offset of the `pat` image in the layer arena
-    int32_t pad[2];  // 64 bytes: staged into shared memory as four 16-byte pieces
-};
+    int32_t br0, bc0;  // global coordinates of element 0 of the storage (>= valid region origin for clipped views)
+};  // 64 bytes: staged into shared memory as four 16-byte pieces
 static_assert(sizeof(SrcRec) == 64, "SrcRec must be 64 bytes");
 
 enum : int32_t {
