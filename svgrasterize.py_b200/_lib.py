@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsvgr_b200.so")
+LIB_PATH = os.environ.get("SVGR_LIB") or os.path.join(HERE, "libsvgr_b200.so")  # SVGR_LIB: A/B builds
 
 # ---- record layouts (must match csrc/svgr_types.h and include/svgr_b200.h) ----------------
 PATH_DT = np.dtype([("m", "<f8", 6), ("viewport", "<i4", 4), ("has_viewport", "<i4"), ("fill_rule", "<i4"),

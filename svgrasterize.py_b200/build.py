@@ -19,9 +19,13 @@ LIB = os.path.join(HERE, "libsvgr_b200.so")
 SOURCES = ["engine.cu", "k_flatten.cu", "k_stroke.cu", "k_coverage.cu", "k_compose.cu", "k_filters.cu"]
 HEADERS = ["svgr_types.h", "svgr_kernels.h", "svgr_device.cuh", os.path.join("..", "..", "include", "svgr_b200.h")]
 NVCC_FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden,-Wall", "--cudart", "static",
 ]
+# Geometry (flatten, stroke, coverage edge math, the planner) reproduces the reference's float64 roundings and
+# must not have multiplies and adds contracted behind its back; the pixel kernels are float32 work within a
+# 1e-5 tolerance and keep the default contraction (FFMA).
+FMAD = {"k_compose.cu": "true", "k_filters.cu": "true"}
 
 
 def _nvcc() -> str:
@@ -39,8 +43,11 @@ def stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not stale():
+EXTRA = os.environ.get("SVGR_NVCC_EXTRA", "").split()
+
+
+def build(force: bool = False, verbose: bool = False, lib: str = LIB) -> str:
+    if not force and lib == LIB and not stale():
         return LIB
     nvcc = _nvcc()
     objs = []
@@ -48,7 +55,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(os.path.join(CSRC, "build"), exist_ok=True)
     for src in SOURCES:
         obj = os.path.join(CSRC, "build", src[:-3] + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, f"-fmad={FMAD.get(src, 'false')}", *EXTRA, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -59,10 +66,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"nvcc failed on {src}:\n{out}")
         if verbose and out:
             print(out)
-    cmd = [nvcc, "-shared", "--cudart", "static", "-o", LIB, *objs]
+    cmd = [nvcc, "-shared", "--cudart", "static", "-Wno-deprecated-gpu-targets", "-o", lib, *objs]
     subprocess.run(cmd, check=True)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    out = [a for a in sys.argv[1:] if a.endswith(".so")]
+    print(build(force="--force" in sys.argv or bool(out), verbose="-v" in sys.argv, lib=os.path.abspath(out[0]) if out else LIB))

@@ -178,7 +178,7 @@ struct svgr_ctx {
     long long edge_cap = 0;
     long long n_edges = 0;
     std::vector<PathBox> h_boxes;
-    PinBuf pin_boxes, pin_status, pin_plan, pin_out;
+    PinBuf pin_boxes, pin_status, pin_plan, pin_out, pin_masks;
 
     // ---- plan state
     std::vector<MaskRec> h_masks;
@@ -192,12 +192,12 @@ struct svgr_ctx {
     long long mask_pixels = 0, layer_pixels = 0, compose_bytes = 0, canvas_pixels = 0;
     int n_levels = 0;
     DevBuf d_masks, d_band_cnt, d_band_off, d_band_cur, d_bin_edges, d_cov, d_layers, d_ops, d_srcs, d_focal_jobs,
-        d_focal_flags, d_canvas, d_q, d_tile_map;
+        d_focal_flags, d_canvas, d_q, d_tile_map, d_tile_mask;
     long long bin_cap = 0;
     long long n_binned = 0;
     bool planned = false, covered = false, composed = false;
 
-    cudaEvent_t ev[12] = {nullptr};
+    cudaEvent_t ev[16] = {nullptr};
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -715,13 +715,13 @@ struct Planner {
         return true;
     }
 
-    bool run()
+    bool run() { return plan_masks() && plan_nodes(); }
+
+    // masks, bands and coverage tiles: all the binning and coverage launches need
+    bool plan_masks()
     {
         svgr_ctx *c = ctx;
-        c->ops.clear(), c->srcs.clear(), c->focal_jobs.clear(), c->launches.clear();
-        c->n_focal_blocks = 0;
-        c->layer_pixels = 0, c->mask_pixels = 0;
-        // ---- masks, bands, tiles
+        c->mask_pixels = 0;
         c->h_masks.assign(c->n_path, MaskRec());
         long long cov_top = 0, band = 0, tile = 0;
         for (int i = 0; i < c->n_path; i++) {
@@ -747,7 +747,17 @@ struct Planner {
             }
         }
         c->n_bands = band, c->n_cov_tiles = tile, c->cov_floats = cov_top;
-        // ---- nodes
+        return true;
+    }
+
+    // the scene program: node values, layer arena, ops per level (runs on the host while the GPU bins and
+    // rasterises coverage)
+    bool plan_nodes()
+    {
+        svgr_ctx *c = ctx;
+        c->ops.clear(), c->srcs.clear(), c->focal_jobs.clear(), c->launches.clear();
+        c->n_focal_blocks = 0;
+        c->layer_pixels = 0;
         uses.assign(c->n_node, 0);
         for (int i = 0; i < c->n_node; i++) {
             const svgr_node &n = c->h_nodes[i];
@@ -924,7 +934,7 @@ static int load_program(svgr_ctx *ctx, const svgr_program *p, cudaStream_t s)
 }
 
 static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *out, int out_on_device, int timing,
-                        svgr_stats *stats)
+                        svgr_stats *stats, int depth = 0)
 {
     if (!ctx->have_program)
         FAIL(SVGR_E_INVALID, "no program loaded");
@@ -1074,90 +1084,92 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
         return SVGR_OK;
     }
 
-    // ---- plan
+    // ---- plan, part 1: masks -> binning + coverage are launched before the node plan is made
     mark(3);
     Planner pl(ctx);
-    if (!pl.run())
+    if (!pl.plan_masks())
         FAIL(SVGR_E_INVALID, pl.err);
-    ctx->planned = true;
     {
-        // one pinned staging buffer for all plan tables
         size_t b_masks = (size_t)ctx->n_path * sizeof(MaskRec);
-        size_t b_ops = ctx->ops.size() * sizeof(OpRec);
-        size_t b_srcs = ctx->srcs.size() * sizeof(SrcRec);
-        size_t b_focal = ctx->focal_jobs.size() * sizeof(FocalJob);
-        CK(ctx->pin_plan.ensure(b_masks + b_ops + b_srcs + b_focal + 64));
-        char *pp = (char *)ctx->pin_plan.p;
-        if (b_masks)
-            memcpy(pp, ctx->h_masks.data(), b_masks);
-        OpRec *po = (OpRec *)(pp + b_masks);
-        for (size_t i = 0; i < ctx->ops.size(); i++)
-            po[i] = ctx->ops[i].op;
-        if (b_srcs)
-            memcpy(pp + b_masks + b_ops, ctx->srcs.data(), b_srcs);
-        if (b_focal)
-            memcpy(pp + b_masks + b_ops + b_srcs, ctx->focal_jobs.data(), b_focal);
+        CK(ctx->pin_masks.ensure(b_masks + 64));
         CK(ctx->d_masks.ensure(std::max<size_t>(b_masks, 16)));
-        CK(ctx->d_ops.ensure(std::max<size_t>(b_ops, 16)));
-        CK(ctx->d_srcs.ensure(std::max<size_t>(b_srcs, 16)));
-        CK(ctx->d_focal_jobs.ensure(std::max<size_t>(b_focal, 16)));
-        if (b_masks)
-            CK(cudaMemcpyAsync(ctx->d_masks.p, pp, b_masks, cudaMemcpyHostToDevice, s));
-        if (b_ops)
-            CK(cudaMemcpyAsync(ctx->d_ops.p, pp + b_masks, b_ops, cudaMemcpyHostToDevice, s));
-        if (b_srcs)
-            CK(cudaMemcpyAsync(ctx->d_srcs.p, pp + b_masks + b_ops, b_srcs, cudaMemcpyHostToDevice, s));
-        if (b_focal)
-            CK(cudaMemcpyAsync(ctx->d_focal_jobs.p, pp + b_masks + b_ops + b_srcs, b_focal, cudaMemcpyHostToDevice, s));
+        if (b_masks) {
+            memcpy(ctx->pin_masks.p, ctx->h_masks.data(), b_masks);
+            CK(cudaMemcpyAsync(ctx->d_masks.p, ctx->pin_masks.p, b_masks, cudaMemcpyHostToDevice, s));
+        }
     }
     CK(ctx->d_cov.ensure((size_t)std::max<long long>(ctx->cov_floats, 4) * 4));
-    CK(ctx->d_layers.ensure((size_t)std::max<long long>(ctx->layer_floats, 4) * 4));
-    CK(ctx->d_focal_flags.ensure((size_t)std::max(ctx->n_focal, 1) * 4));
     mark(4);
 
-    // ---- binning
+    // ---- binning (count -> scan -> fill).  The bin list capacity is a grow-only guess that is checked
+    // after the fact (status block read at the end of the call): no host round trip in the middle.
     const long long NB = ctx->n_bands;
+    ctx->bin_cap = std::max(ctx->bin_cap, 3 * ctx->n_edges + 1024);
+    CK(ctx->d_band_cnt.ensure((size_t)(NB + 1) * 4));
+    CK(ctx->d_band_off.ensure((size_t)(NB + 1) * 4));
+    CK(ctx->d_band_cur.ensure((size_t)(NB + 1) * 4));
+    CK(ctx->d_scan_tmp.ensure((size_t)(NB / 2048 + 4) * 4));
+    CK(ctx->d_bin_edges.ensure((size_t)ctx->bin_cap * 4));
+    CK(ctx->d_tile_mask.ensure((size_t)std::max<long long>(ctx->n_cov_tiles, 1) * 4));
+    CK(cudaMemsetAsync(ctx->d_band_cnt.p, 0, (size_t)(NB + 1) * 4, s));
+    CK(cudaMemsetAsync(ctx->d_band_cur.p, 0, (size_t)(NB + 1) * 4, s));
     if (NB > 0 && ctx->n_edges > 0) {
-        CK(ctx->d_band_cnt.ensure((size_t)(NB + 1) * 4));
-        CK(ctx->d_band_off.ensure((size_t)(NB + 1) * 4));
-        CK(ctx->d_band_cur.ensure((size_t)(NB + 1) * 4));
-        CK(ctx->d_scan_tmp.ensure((size_t)(NB / 2048 + 4) * 4));
-        CK(cudaMemsetAsync(ctx->d_band_cnt.p, 0, (size_t)(NB + 1) * 4, s));
-        CK(cudaMemsetAsync(ctx->d_band_cur.p, 0, (size_t)(NB + 1) * 4, s));
         svgr_launch_bin_count(ctx->d_edges.as<double>(), ctx->d_edge_path.as<uint32_t>(), (unsigned long long)ctx->n_edges,
                               ctx->d_masks.as<MaskRec>(), ctx->d_band_cnt.as<int>(), SM, s);
         svgr_launch_exclusive_scan(ctx->d_band_cnt.as<int>(), ctx->d_band_off.as<int>(), NB + 1, ctx->d_scan_tmp.as<int>(),
                                    &d_st->binned_total, s);
-        CK(cudaMemcpyAsync(ctx->pin_status.p, d_st, sizeof(StatusBlock), cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        ctx->n_binned = ((StatusBlock *)ctx->pin_status.p)->binned_total;
-        CK(ctx->d_bin_edges.ensure((size_t)std::max<long long>(ctx->n_binned, 1) * 4));
         svgr_launch_bin_fill(ctx->d_edges.as<double>(), ctx->d_edge_path.as<uint32_t>(), (unsigned long long)ctx->n_edges,
                              ctx->d_masks.as<MaskRec>(), ctx->d_band_off.as<int>(), ctx->d_band_cur.as<int>(),
-                             ctx->d_bin_edges.as<uint32_t>(), SM, s);
+                             ctx->d_bin_edges.as<uint32_t>(), ctx->bin_cap, SM, s);
         n_kernels += 4 + ((NB + 1) > 2048 ? 1 : 0);
-    } else if (NB > 0) {
-        CK(ctx->d_band_cnt.ensure((size_t)(NB + 1) * 4));
-        CK(ctx->d_band_off.ensure((size_t)(NB + 1) * 4));
-        CK(ctx->d_bin_edges.ensure(16));
-        CK(cudaMemsetAsync(ctx->d_band_cnt.p, 0, (size_t)(NB + 1) * 4, s));
+    } else {
         CK(cudaMemsetAsync(ctx->d_band_off.p, 0, (size_t)(NB + 1) * 4, s));
-        ctx->n_binned = 0;
     }
     mark(5);
     // ---- coverage
-    {
-        long long max_tiles = ctx->n_cov_tiles;
-        for (auto &L : ctx->launches)
-            max_tiles = std::max<long long>(max_tiles, L.n_tiles);
-        CK(ctx->d_tile_map.ensure((size_t)std::max<long long>(max_tiles, 1) * 4));
-    }
     svgr_launch_coverage(ctx->d_edges.as<double>(), ctx->d_masks.as<MaskRec>(), ctx->n_path, (int)ctx->n_cov_tiles,
-                         ctx->d_tile_map.as<int>(), ctx->d_band_off.as<int>(), ctx->d_band_cnt.as<int>(), ctx->d_bin_edges.as<uint32_t>(),
-                         ctx->d_cov.as<float>(), s);
+                         ctx->d_tile_mask.as<int>(), ctx->d_band_off.as<int>(), ctx->d_band_cnt.as<int>(),
+                         ctx->d_bin_edges.as<uint32_t>(), ctx->bin_cap, ctx->d_cov.as<float>(), s);
     ctx->covered = true;
     n_kernels += ctx->n_cov_tiles > 0 ? 2 : 0;
     mark(6);
+
+    // ---- plan, part 2 (host, concurrent with the launches above): nodes -> ops, then the op tables go up
+    if (!pl.plan_nodes())
+        FAIL(SVGR_E_INVALID, pl.err);
+    ctx->planned = true;
+    {
+        size_t b_ops = ctx->ops.size() * sizeof(OpRec);
+        size_t b_srcs = ctx->srcs.size() * sizeof(SrcRec);
+        size_t b_focal = ctx->focal_jobs.size() * sizeof(FocalJob);
+        CK(ctx->pin_plan.ensure(b_ops + b_srcs + b_focal + 64));
+        char *pp = (char *)ctx->pin_plan.p;
+        OpRec *po = (OpRec *)pp;
+        for (size_t i = 0; i < ctx->ops.size(); i++)
+            po[i] = ctx->ops[i].op;
+        if (b_srcs)
+            memcpy(pp + b_ops, ctx->srcs.data(), b_srcs);
+        if (b_focal)
+            memcpy(pp + b_ops + b_srcs, ctx->focal_jobs.data(), b_focal);
+        CK(ctx->d_ops.ensure(std::max<size_t>(b_ops, 16)));
+        CK(ctx->d_srcs.ensure(std::max<size_t>(b_srcs, 16)));
+        CK(ctx->d_focal_jobs.ensure(std::max<size_t>(b_focal, 16)));
+        if (b_ops)
+            CK(cudaMemcpyAsync(ctx->d_ops.p, pp, b_ops, cudaMemcpyHostToDevice, s));
+        if (b_srcs)
+            CK(cudaMemcpyAsync(ctx->d_srcs.p, pp + b_ops, b_srcs, cudaMemcpyHostToDevice, s));
+        if (b_focal)
+            CK(cudaMemcpyAsync(ctx->d_focal_jobs.p, pp + b_ops + b_srcs, b_focal, cudaMemcpyHostToDevice, s));
+    }
+    CK(ctx->d_layers.ensure((size_t)std::max<long long>(ctx->layer_floats, 4) * 4));
+    CK(ctx->d_focal_flags.ensure((size_t)std::max(ctx->n_focal, 1) * 4));
+    {
+        long long max_tiles = 1;
+        for (auto &L : ctx->launches)
+            max_tiles = std::max<long long>(max_tiles, L.n_tiles);
+        CK(ctx->d_tile_map.ensure((size_t)max_tiles * 4));
+    }
+    mark(10);
     int n_launches = 0;
     if (stop_after != SVGR_STOP_COVERAGE) {
         RenderTables T;
@@ -1219,14 +1231,26 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
         mark(9);
         ctx->composed = true;
     }
+    CK(cudaMemcpyAsync(ctx->pin_status.p, d_st, sizeof(StatusBlock), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
+    ctx->n_binned = ((StatusBlock *)ctx->pin_status.p)->binned_total;
+    if (ctx->n_binned > ctx->bin_cap) {
+        // the guess was too small: the masks of the overflowing bands are wrong.  Grow and run again.
+        ctx->bin_cap = ctx->n_binned + ctx->n_binned / 8 + 1024;
+        if (depth >= 2)
+            FAIL(SVGR_E_NOMEM, "bin list capacity retry limit reached");
+        int rc = run_pipeline(ctx, s, stop_after, out, out_on_device, timing, stats, depth + 1);
+        if (rc == SVGR_OK && stats)
+            stats->retries += 1;
+        return rc;
+    }
     if (timing) {
-        ms_plan = ev_ms(ctx->ev[3], ctx->ev[4]);
+        ms_plan = ev_ms(ctx->ev[3], ctx->ev[4]) + ev_ms(ctx->ev[6], ctx->ev[10]);
         ms_bin = ev_ms(ctx->ev[4], ctx->ev[5]);
         ms_cov = ev_ms(ctx->ev[5], ctx->ev[6]);
         if (stop_after != SVGR_STOP_COVERAGE) {
-            ms_cmp = ev_ms(ctx->ev[6], ctx->ev[7]);
+            ms_cmp = ev_ms(ctx->ev[10], ctx->ev[7]);
             ms_canvas = ev_ms(ctx->ev[7], ctx->ev[8]);
             ms_d2h = ev_ms(ctx->ev[8], ctx->ev[9]);
         }
@@ -1308,10 +1332,11 @@ void svgr_destroy(svgr_ctx *ctx)
                       &ctx->d_osub, &ctx->d_ocount, &ctx->d_edges, &ctx->d_edge_path, &ctx->d_minmax, &ctx->d_boxes,
                       &ctx->d_minmax_f64, &ctx->d_status, &ctx->d_masks, &ctx->d_band_cnt, &ctx->d_band_off,
                       &ctx->d_band_cur, &ctx->d_bin_edges, &ctx->d_cov, &ctx->d_layers, &ctx->d_ops, &ctx->d_srcs,
-                      &ctx->d_focal_jobs, &ctx->d_focal_flags, &ctx->d_canvas, &ctx->d_q, &ctx->d_tile_map};
+                      &ctx->d_focal_jobs, &ctx->d_focal_flags, &ctx->d_canvas, &ctx->d_q, &ctx->d_tile_map, &ctx->d_tile_mask};
     for (DevBuf *b : bufs)
         b->release();
     ctx->pin_boxes.release(), ctx->pin_status.release(), ctx->pin_plan.release(), ctx->pin_out.release();
+    ctx->pin_masks.release();
     for (auto &e : ctx->ev)
         if (e)
             cudaEventDestroy(e);

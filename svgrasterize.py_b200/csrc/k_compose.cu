@@ -73,14 +73,17 @@ __device__ __forceinline__ void copy16(T *dst, const T *src, int part)
 //      up to CMP_CAP surviving SrcRecs into shared memory; all threads then copy the PaintRecs those
 //      sources need; every thread folds the staged sources into its 4 pixels, issuing the 4 loads of a
 //      source back to back before using any of them.
-__global__ void __launch_bounds__(256, 4)
+#ifndef SVGR_CMP_OCC
+#define SVGR_CMP_OCC 4
+#endif
+__global__ void __launch_bounds__(256, SVGR_CMP_OCC)
 compose_kernel(RenderTables T, const OpRec *__restrict__ ops, const int *__restrict__ tile_op,
                float *__restrict__ layers_out, uint8_t *__restrict__ canvas_out)
 {
     __shared__ __align__(16) OpRec s_op;
-    __shared__ __align__(16) SrcRec s_src[CMP_CAP];
-    __shared__ __align__(16) PaintRec s_paint[CMP_CAP];
-    __shared__ int s_idx[CMP_CAP];
+    __shared__ __align__(16) SrcRec s_src[CMP_CAP + 1];
+    __shared__ __align__(16) PaintRec s_paint[CMP_CAP + 1];
+    __shared__ int s_idx[CMP_CAP + 1];
     __shared__ int s_n, s_next;
 
     const int tid = threadIdx.x;
@@ -106,42 +109,10 @@ compose_kernel(RenderTables T, const OpRec *__restrict__ ops, const int *__restr
     const bool skip_outside = (mode == MODE_OVER);  // blending a zero source is the identity for OVER
     const double x0 = (double)r0 + 0.5, y0 = (double)c + 0.5;  // pixel centre of pixel 0
 
-    // acc = fold so far; pend = the source being assembled (it may still be multiplied by stencil
-    // modifier entries that follow it) and is blended into acc when the next source starts
-    float4 acc[CMP_PX], pend[CMP_PX];
-    unsigned pend_live = 0;
-    bool have_pend = false, pend_first = false;
+    float4 acc[CMP_PX];
 #pragma unroll
     for (int k = 0; k < CMP_PX; k++)
-        acc[k] = f4(0.f, 0.f, 0.f, 0.f), pend[k] = f4(0.f, 0.f, 0.f, 0.f);
-
-    auto flush = [&]() {
-        if (!have_pend)
-            return;
-        have_pend = false;
-        if (pend_first) {
-#pragma unroll
-            for (int k = 0; k < CMP_PX; k++)
-                acc[k] = pend[k];
-        } else if (mode == MODE_OVER) {
-#pragma unroll
-            for (int k = 0; k < CMP_PX; k++) {
-                const float q = 1.0f - pend[k].w;  // a dead pixel has pend = 0: the blend is the identity
-                acc[k] = f4(pend[k].x + acc[k].x * q, pend[k].y + acc[k].y * q, pend[k].z + acc[k].z * q,
-                            pend[k].w + acc[k].w * q);
-            }
-        } else if (mode == MODE_IN) {
-#pragma unroll
-            for (int k = 0; k < CMP_PX; k++) {
-                const float da = acc[k].w;
-                acc[k] = f4(pend[k].x * da, pend[k].y * da, pend[k].z * da, pend[k].w * da);
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < CMP_PX; k++)
-                acc[k] = blend_px(mode, op.k, acc[k], pend[k]);
-        }
-    };
+        acc[k] = f4(0.f, 0.f, 0.f, 0.f);
 
     for (;;) {
         const int start = s_next;
@@ -170,6 +141,17 @@ compose_kernel(RenderTables T, const OpRec *__restrict__ ops, const int *__restr
                 }
                 n += __popc(m);
             }
+            // a stencil modifier must be staged in the same round as the source it belongs to
+            if (k < op.src_cnt && n > 0) {
+                int kind = __ldg(&srcs[k].kind);
+                if (kind >= SRC_MOD_COV && s_idx[n - 1] == k - 1) {
+                    if (tx < 4)
+                        copy16(&s_src[n], srcs + k, tx);
+                    if (tx == 0)
+                        s_idx[n] = k;
+                    n++, k++;
+                }
+            }
             if (tx == 0) {
                 s_n = n;
                 s_next = k < op.src_cnt ? k : op.src_cnt;
@@ -190,19 +172,8 @@ compose_kernel(RenderTables T, const OpRec *__restrict__ ops, const int *__restr
         if (col_live) {
             for (int j = 0; j < n; j++) {
                 const SrcRec &s = s_src[j];
-                if (s.kind >= SRC_MOD_COV) {
-                    // stencil modifier of the pending source (clip / luminance mask that is never materialised)
-                    if (have_pend && pend_live) {
-#pragma unroll
-                        for (int k = 0; k < CMP_PX; k++)
-                            if (pend_live >> k & 1) {
-                                const float m = mod_value(T, s, r0 + 8 * k, c);
-                                pend[k] = f4(pend[k].x * m, pend[k].y * m, pend[k].z * m, pend[k].w * m);
-                            }
-                    }
-                    continue;
-                }
-                flush();
+                if (s.kind >= SRC_MOD_COV)
+                    continue;  // consumed together with its owner below
                 const bool first = s_idx[j] == 0;
                 const int dr = r0 - s.r0, dc = c - s.c0;
                 unsigned live = 0;
@@ -215,7 +186,7 @@ compose_kernel(RenderTables T, const OpRec *__restrict__ ops, const int *__restr
                 if (!live && skip_outside && !first)
                     continue;
                 const int base = (r0 - s.br0) * s.stride + (c - s.bc0), step = 8 * s.stride;  // a layer has < 2^31 px
-                float4 *v = pend;
+                float4 v[CMP_PX];
                 if (s.kind == SRC_L4) {
                     const float4 *p = reinterpret_cast<const float4 *>(T.layers + s.off);
 #pragma unroll
@@ -263,14 +234,44 @@ compose_kernel(RenderTables T, const OpRec *__restrict__ ops, const int *__restr
                         if (live >> k & 1)
                             v[k] = convert_px(v[k], s.conv);
                 }
-                have_pend = true, pend_first = first, pend_live = live;
+                if (j + 1 < n && s_src[j + 1].kind >= SRC_MOD_COV) {
+                    // stencil of a clip / luminance mask that was never written out as a layer
+                    const SrcRec &md = s_src[j + 1];
+#pragma unroll
+                    for (int k = 0; k < CMP_PX; k++)
+                        if (live >> k & 1) {
+                            const float m = mod_value(T, md, r0 + 8 * k, c);
+                            v[k] = f4(v[k].x * m, v[k].y * m, v[k].z * m, v[k].w * m);
+                        }
+                }
+                if (first) {
+#pragma unroll
+                    for (int k = 0; k < CMP_PX; k++)
+                        acc[k] = v[k];
+                } else if (mode == MODE_OVER) {
+#pragma unroll
+                    for (int k = 0; k < CMP_PX; k++) {
+                        const float q = 1.0f - v[k].w;  // a dead pixel has v = 0: the blend is the identity
+                        acc[k] = f4(v[k].x + acc[k].x * q, v[k].y + acc[k].y * q, v[k].z + acc[k].z * q,
+                                    v[k].w + acc[k].w * q);
+                    }
+                } else if (mode == MODE_IN) {
+#pragma unroll
+                    for (int k = 0; k < CMP_PX; k++) {
+                        const float da = acc[k].w;
+                        acc[k] = f4(v[k].x * da, v[k].y * da, v[k].z * da, v[k].w * da);
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < CMP_PX; k++)
+                        acc[k] = blend_px(mode, op.k, acc[k], v[k]);
+                }
             }
         }
         __syncthreads();
     }
     if (!col_live)
         return;
-    flush();
 
 #pragma unroll
     for (int k = 0; k < CMP_PX; k++) {
@@ -343,9 +344,8 @@ __global__ void focal_flag_kernel(RenderTables T, const FocalJob *__restrict__ j
         long long i = base + threadIdx.x + 256 * k;
         if (i < n) {
             int r = j.r0 + (int)(i / j.cols), c = j.c0 + (int)(i % j.cols);
-            double ux, uy, b, a;
-            px_to_user(p, (double)r + 0.5, (double)c + 0.5, &ux, &uy);
-            if (focal_det(p, ux, uy, &b, &a) < 0)
+            double b;
+            if (focal_det(p, (double)r + 0.5, (double)c + 0.5, &b) < 0)
                 neg = true;
         }
     }

@@ -190,7 +190,7 @@ __global__ void bin_count_kernel(const double *__restrict__ edges, const uint32_
 __global__ void bin_fill_kernel(const double *__restrict__ edges, const uint32_t *__restrict__ edge_path,
                                 unsigned long long n_edges, const MaskRec *__restrict__ masks,
                                 const int *__restrict__ band_off, int *__restrict__ band_cursor,
-                                uint32_t *__restrict__ bin_edges)
+                                uint32_t *__restrict__ bin_edges, long long cap)
 {
     for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n_edges;
          i += (unsigned long long)gridDim.x * blockDim.x) {
@@ -203,8 +203,9 @@ __global__ void bin_fill_kernel(const double *__restrict__ edges, const uint32_t
         int b0 = er.y0 / SVGR_BAND_ROWS, b1 = (er.y1 - 1) / SVGR_BAND_ROWS;
         for (int k = b0; k <= b1; k++) {
             int band = m.band_base + k;
-            int pos = atomicAdd(band_cursor + band, 1);
-            bin_edges[band_off[band] + pos] = (uint32_t)i;
+            long long pos = (long long)band_off[band] + atomicAdd(band_cursor + band, 1);
+            if (pos < cap)  // an undersized list is detected and repaired by the host after the fact
+                bin_edges[pos] = (uint32_t)i;
         }
     }
 }
@@ -287,7 +288,8 @@ __device__ __forceinline__ float fill_rule_apply(float m, int rule)
 __global__ void __launch_bounds__(COV_THREADS)
 coverage_kernel(const double *__restrict__ edges, const MaskRec *__restrict__ masks,
                 const int *__restrict__ tile_mask, const int *__restrict__ band_off,
-                const int *__restrict__ band_cnt, const uint32_t *__restrict__ bin_edges, float *__restrict__ cov)
+                const int *__restrict__ band_cnt, const uint32_t *__restrict__ bin_edges, long long bin_cap,
+                float *__restrict__ cov)
 {
     __shared__ __align__(16) float trace[SVGR_BAND_ROWS][SVGR_TILE_COLS];
 
@@ -314,7 +316,8 @@ coverage_kernel(const double *__restrict__ edges, const MaskRec *__restrict__ ma
 
     // ---- 2. accumulate the signed areas of this band's edges
     const int band = m.band_base + band_local;
-    const int e_off = band_off[band], e_cnt = band_cnt[band];
+    const int e_off = band_off[band];
+    const int e_cnt = (int)max(0ll, min((long long)band_cnt[band], bin_cap - e_off));
     for (int i = threadIdx.x; i < e_cnt; i += COV_THREADS) {
         const double2 *e = reinterpret_cast<const double2 *>(edges + 4ull * bin_edges[e_off + i]);
         double2 pa = e[0], pb = e[1];
@@ -395,14 +398,14 @@ void svgr_launch_bin_count(const double *edges, const uint32_t *edge_path, unsig
 
 void svgr_launch_bin_fill(const double *edges, const uint32_t *edge_path, unsigned long long n_edges,
                           const MaskRec *masks, const int *band_off, int *band_cursor, uint32_t *bin_edges,
-                          int sm_count, cudaStream_t s)
+                          long long cap, int sm_count, cudaStream_t s)
 {
     if (n_edges == 0)
         return;
     unsigned long long blocks = (n_edges + 255) / 256;
     if (blocks > (unsigned long long)sm_count * 16)
         blocks = (unsigned long long)sm_count * 16;
-    bin_fill_kernel<<<(unsigned)blocks, 256, 0, s>>>(edges, edge_path, n_edges, masks, band_off, band_cursor, bin_edges);
+    bin_fill_kernel<<<(unsigned)blocks, 256, 0, s>>>(edges, edge_path, n_edges, masks, band_off, band_cursor, bin_edges, cap);
 }
 
 __global__ void expand_masks_kernel(const MaskRec *__restrict__ masks, int n_masks, int n_tiles,
@@ -417,11 +420,11 @@ __global__ void expand_masks_kernel(const MaskRec *__restrict__ masks, int n_mas
 }
 
 void svgr_launch_coverage(const double *edges, const MaskRec *masks, int n_masks, int n_tiles, int *tile_mask,
-                          const int *band_off, const int *band_cnt, const uint32_t *bin_edges, float *cov,
-                          cudaStream_t s)
+                          const int *band_off, const int *band_cnt, const uint32_t *bin_edges, long long bin_cap,
+                          float *cov, cudaStream_t s)
 {
     if (n_tiles <= 0)
         return;
     expand_masks_kernel<<<(n_masks + 127) / 128, 128, 0, s>>>(masks, n_masks, n_tiles, tile_mask);
-    coverage_kernel<<<n_tiles, COV_THREADS, 0, s>>>(edges, masks, tile_mask, band_off, band_cnt, bin_edges, cov);
+    coverage_kernel<<<n_tiles, COV_THREADS, 0, s>>>(edges, masks, tile_mask, band_off, band_cnt, bin_edges, bin_cap, cov);
 }

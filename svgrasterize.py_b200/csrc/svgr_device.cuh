@@ -102,44 +102,33 @@ __device__ __forceinline__ float4 grad_color(double v, const StopRec *__restrict
     return o;  // NaN offsets match no interval: transparent black
 }
 
-__device__ __forceinline__ void px_to_user(const PaintRec &p, double x, double y, double *ux, double *uy)
+// Gradient parameter of a pixel centre (x, y) = (row + .5, col + .5).  The reference maps the centre through
+// transform.invert and the inverse gradientTransform (svgrasterize.py:1022-1031, :1558, :1602) and then applies
+// the gradient's own formula; both maps are affine, so the host encoder composes them (float64) into the
+// coefficients below and the device evaluates one fused expression per pixel:
+//   linear        t  = g[0] x + g[1] y + g[2]                              (svgrasterize.py:1561-1562)
+//   radial        o  = (m1[0] x + m1[1] y + m1[2],  m1[3] x + m1[4] y + m1[5]) = (p - c) / r,  t = |o|   (:1605-1607)
+//   two-circle    pd = (m1[0] x + m1[1] y + m1[2],  m1[3] x + m1[4] y + m1[5]) = p - f
+//                 g = [cdx, cdy, fr * rd, a, fr^2, fr / (fr - r), fr != r, 1 / a]                          (:1612-1644)
+__device__ __forceinline__ double focal_det(const PaintRec &p, double x, double y, double *b_out)
 {
-    // (x, y) = pixel centre (row + .5, col + .5) of grad_pixels (svgrasterize.py:1653-1658); then
-    // transform.invert and the inverse gradientTransform, each as Transform.__call__ (:531-534)
-    double ax = fma(y, p.m1[1], x * p.m1[0]) + p.m1[2];
-    double ay = fma(y, p.m1[4], x * p.m1[3]) + p.m1[5];
-    if (p.has_m2) {
-        double bx = fma(ay, p.m2[1], ax * p.m2[0]) + p.m2[2];
-        double by = fma(ay, p.m2[4], ax * p.m2[3]) + p.m2[5];
-        ax = bx, ay = by;
-    }
-    *ux = ax, *uy = ay;
-}
-
-// det = b^2 - a c of the two-circle gradient (svgrasterize.py:1612-1620)
-__device__ __forceinline__ double focal_det(const PaintRec &p, double ux, double uy, double *b_out, double *a_out)
-{
-    double cx = p.g[0], cy = p.g[1], radius = p.g[2], fx = p.g[3], fy = p.g[4], fr = p.g[5];
-    double cdx = cx - fx, cdy = cy - fy;
-    double rd = radius - fr;
-    double a = (cdx * cdx + cdy * cdy) - rd * rd;
-    double pdx = ux - fx, pdy = uy - fy;
-    double b = (pdx * cdx + pdy * cdy) + fr * rd;
-    double cc = (pdx * pdx + pdy * pdy) - fr * fr;
+    double pdx = fma(p.m1[0], x, fma(p.m1[1], y, p.m1[2]));
+    double pdy = fma(p.m1[3], x, fma(p.m1[4], y, p.m1[5]));
+    double b = fma(pdx, p.g[0], fma(pdy, p.g[1], p.g[2]));
+    double cc = fma(pdx, pdx, fma(pdy, pdy, -p.g[4]));
     *b_out = b;
-    *a_out = a;
-    return b * b - a * cc;
+    return fma(b, b, -p.g[3] * cc);
 }
 
-// Paint colour at the pixel centre (x, y) = (row + .5, col + .5): premultiplied RGBA.
-// `p` may live in shared memory.  pat/pat_stride: the pattern tile image (PAINT_PATTERN only).
+// Paint colour at the pixel centre (x, y): premultiplied RGBA.  `p` may live in shared memory.
+// pat / pat_stride: the pattern tile image (PAINT_PATTERN only).
 __device__ __forceinline__ float4 paint_eval(const RenderTables &T, const PaintRec &p, double x, double y,
                                              const float4 *pat, int pat_stride)
 {
     if (p.kind == PAINT_SOLID)
         return f4(p.color[0], p.color[1], p.color[2], p.color[3]);
     if (p.kind == PAINT_PATTERN) {
-        // Path.fill pattern branch (svgrasterize.py:1074-1094)
+        // Path.fill pattern branch (svgrasterize.py:1074-1094); Transform.__call__ roundings (:531-534)
         double ax = fma(y, p.m1[1], x * p.m1[0]) + p.m1[2];
         double ay = fma(y, p.m1[4], x * p.m1[3]) + p.m1[5];
         ax = floored_mod(ax - p.g[0], p.g[2]);
@@ -153,31 +142,24 @@ __device__ __forceinline__ float4 paint_eval(const RenderTables &T, const PaintR
             return f4(0.f, 0.f, 0.f, 0.f);
         return __ldg(pat + ir * pat_stride + ic);
     }
-    double ux, uy;
-    px_to_user(p, x, y, &ux, &uy);
     double t;
     if (p.kind == PAINT_LINEAR) {
-        double vx = p.g[2] - p.g[0], vy = p.g[3] - p.g[1];
-        double vv = fma(vy, vy, vx * vx);
-        double dx = ux - p.g[0], dy = uy - p.g[1];
-        t = fma(dy, vy, dx * vx) / vv;
+        t = fma(p.g[0], x, fma(p.g[1], y, p.g[2]));
     } else if (p.kind == PAINT_RADIAL) {
-        double ox = (ux - p.g[0]) / p.g[2], oy = (uy - p.g[1]) / p.g[2];
-        t = sqrt(ox * ox + oy * oy);
+        double ox = fma(p.m1[0], x, fma(p.m1[1], y, p.m1[2]));
+        double oy = fma(p.m1[3], x, fma(p.m1[4], y, p.m1[5]));
+        t = sqrt(fma(ox, ox, oy * oy));
     } else {
-        double b, a;
-        double det = focal_det(p, ux, uy, &b, &a);
+        double b;
+        double det = focal_det(p, x, y, &b);
         bool any_neg = T.focal_flags[p.flag] != 0;
         if (any_neg && det < 0)
             return f4(0.f, 0.f, 0.f, 0.f);
         double sq = sqrt(det);
-        double t1 = (b + sq) / a, t2 = (b - sq) / a;
+        double t1 = (b + sq) * p.g[7], t2 = (b - sq) * p.g[7];
         t = (t1 != t1 || t2 != t2) ? __longlong_as_double(0x7ff8000000000000ll) : (t1 > t2 ? t1 : t2);
-        if (any_neg && p.g[5] != p.g[2]) {
-            double lim = p.g[5] / (p.g[5] - p.g[2]);
-            if (!(t > lim))
-                return f4(0.f, 0.f, 0.f, 0.f);
-        }
+        if (any_neg && p.g[6] != 0.0 && !(t > p.g[5]))
+            return f4(0.f, 0.f, 0.f, 0.f);
     }
     return grad_color(grad_spread(t, p.spread), T.stops + p.stop_off, p.stop_cnt);
 }

@@ -79,9 +79,12 @@ struct PaintRec {
     int32_t pat_node;                            // PAINT_PATTERN: node holding the pat image
     int32_t pad;
     float color[4];  // PAINT_SOLID: premultiplied colour in the layer's colour space
-    double m1[6];    // pixel centre -> user space (inverse presentation transform)
-    double m2[6];    // inverse gradientTransform | pattern: forward `rep` matrix
-    double g[8];     // linear: p0x p0y p1x p1y | radial: cx cy r fx fy fr | pattern: x y w h
+    // Gradients: the affine maps pixel centre -> user space -> gradient space are composed on the host, see
+    // paint_eval in svgr_device.cuh for the meaning of m1 / g per kind.  Pattern: m1 = inverse `rep` matrix,
+    // m2 = forward `rep` matrix, g = x y w h of the tile (svgrasterize.py:1074-1094).
+    double m1[6];
+    double m2[6];
+    double g[8];
 };
 
 struct StopRec {

@@ -442,21 +442,40 @@ class Encoder:
                 tr = self._bbox_transform(bbox, transform)
             lin = linear_rgb if paint.linear_rgb is None else bool(paint.linear_rgb)
             stop_off, stop_cnt = self._stops(paint, lin)
-            rec = dict(spread=SPREAD[paint.spread], stop_off=stop_off, stop_cnt=stop_cnt, m1=m6(tr.invert))
+            rec = dict(spread=SPREAD[paint.spread], stop_off=stop_off, stop_cnt=stop_cnt)
+            # pixel centre -> gradient space: transform.invert, then the inverse gradientTransform
+            # (svgrasterize.py:1022-1031, :1558, :1602); composed here so that the device evaluates one
+            # affine expression per pixel
+            to_user = tr.invert.m
             if paint.transform is not None:
-                rec.update(has_m2=1, m2=m6(paint.transform.invert))
-            g = np.zeros(8)
+                to_user = paint.transform.invert.m @ to_user
+            A, T = to_user[:2, :2], to_user[:2, 2]
+            g, m1 = np.zeros(8), np.zeros(6)
             if kind == "linear":
-                g[0:2], g[2:4] = paint.p0, paint.p1
+                p0, vec = np.asarray(paint.p0, dtype=np.float64), np.asarray(paint.p1, dtype=np.float64) - paint.p0
+                vv = float(np.dot(vec, vec))
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    g[0:2] = (vec @ A) / vv
+                    g[2] = np.dot(T - p0, vec) / vv
                 rec.update(kind=_lib.PAINT_LINEAR, g=g)
             elif paint.fcenter is None and paint.fradius is None:
-                g[0:2], g[2] = paint.center, paint.radius
-                rec.update(kind=_lib.PAINT_RADIAL, g=g)
+                c, r = np.asarray(paint.center, dtype=np.float64), float(paint.radius)
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    m1[0:2], m1[3:5] = A[0] / r, A[1] / r
+                    m1[2], m1[5] = (T - c) / r
+                rec.update(kind=_lib.PAINT_RADIAL, m1=m1)
             else:
-                g[0:2], g[2] = paint.center, paint.radius
-                g[3:5] = paint.center if paint.fcenter is None else paint.fcenter
-                g[5] = float(paint.fradius or 0)
-                rec.update(kind=_lib.PAINT_RADIAL_FOCAL, g=g, flag=self.n_focal)
+                c, r = np.asarray(paint.center, dtype=np.float64), float(paint.radius)
+                f = c if paint.fcenter is None else np.asarray(paint.fcenter, dtype=np.float64)
+                fr = float(paint.fradius or 0)
+                cd, rd = c - f, r - fr
+                a = float((cd ** 2).sum() - rd ** 2)
+                m1[0:2], m1[3:5] = A[0], A[1]
+                m1[2], m1[5] = T - f
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    g[:] = (cd[0], cd[1], fr * rd, a, fr * fr, np.float64(fr) / np.float64(fr - r), float(fr != r),
+                            np.float64(1.0) / np.float64(a))
+                rec.update(kind=_lib.PAINT_RADIAL_FOCAL, m1=m1, g=g, flag=self.n_focal)
                 self.n_focal += 1
             pidx = self._paint_record(**rec)
             node = self._node(_lib.N_LEAF, pid, pidx, int(lin), -1)
