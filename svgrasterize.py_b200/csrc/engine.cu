@@ -772,9 +772,15 @@ struct Planner {
                 uses[i]++;  // read back by the caller
         }
         c->vals.assign(c->n_node, Val());
-        for (int i = 0; i < c->n_node; i++)
+        for (int i = 0; i < c->n_node; i++) {
+            // a value nobody reads is not computed (SourceAlpha of a filter that only uses SourceGraphic,
+            // svgrasterize.py:1803-1809, is the common case)
+            const svgr_node &n = c->h_nodes[i];
+            if (uses[i] == 0 && n.tag != SVGR_N_CANVAS && n.tag != SVGR_N_LEAF && i != c->n_node - 1)
+                continue;
             if (!node(i, c->vals[i]))
                 return false;
+        }
         c->layer_floats = align4(layer_top);
         // ---- order ops by (level, class); stable so that srcs stay valid
         std::stable_sort(c->ops.begin(), c->ops.end(), [](const PlannedOp &a, const PlannedOp &b) {
