@@ -207,7 +207,7 @@ def run_gpu(opts):
     for _ in range(opts.steps):
         st = eng.render_resident(out_dev, timing=True, stream=stream)
         for k, v in st.items():
-            if k.startswith("ms_"):
+            if k.startswith("ms_") or k.startswith("host_"):
                 acc[k] = acc.get(k, 0.0) + v
     e1.record(stream)
     barrier()

@@ -165,6 +165,7 @@ typedef struct svgr_stats {
     float ms_total, ms_h2d, ms_stroke, ms_flatten, ms_plan, ms_bin, ms_coverage, ms_compose, ms_canvas, ms_d2h;
     int32_t retries;
     int32_t pad;
+    float host_plan_masks_ms, host_plan_nodes_ms; /* wall time of the two host planning phases */
 } svgr_stats;
 
 typedef struct svgr_ctx svgr_ctx;

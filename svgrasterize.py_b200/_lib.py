@@ -23,7 +23,7 @@ PAINT_DT = np.dtype([("kind", "<i4"), ("spread", "<i4"), ("stop_off", "<i4"), ("
                      ("flag", "<i4"), ("pat_r0", "<i4"), ("pat_c0", "<i4"), ("pat_rows", "<i4"), ("pat_cols", "<i4"),
                      ("pat_node", "<i4"), ("pad", "<i4"), ("color", "<f4", 4), ("m1", "<f8", 6), ("m2", "<f8", 6),
                      ("g", "<f8", 8)], align=True)
-STOP_DT = np.dtype([("offset", "<f8"), ("color", "<f4", 4), ("pad", "<f4", 2)], align=True)
+STOP_DT = np.dtype([("offset", "<f8"), ("color", "<f4", 4), ("inv_span", "<f8")], align=True)
 NODE_DT = np.dtype([("tag", "<i4"), ("a", "<i4"), ("b", "<i4"), ("c", "<i4"), ("d", "<i4"), ("child_off", "<i4"),
                     ("child_cnt", "<i4"), ("flags", "<i4"), ("f", "<f8", 4)], align=True)
 KERNEL_DT = np.dtype([("rows", "<i4"), ("cols", "<i4"), ("separable", "<i4"), ("weight_off", "<i4")], align=True)
@@ -67,7 +67,8 @@ class Stats(C.Structure):
                                          "n_kernels")] + \
                [(n, C.c_float) for n in ("ms_total", "ms_h2d", "ms_stroke", "ms_flatten", "ms_plan", "ms_bin",
                                          "ms_coverage", "ms_compose", "ms_canvas", "ms_d2h")] + \
-               [("retries", C.c_int32), ("pad", C.c_int32)]
+               [("retries", C.c_int32), ("pad", C.c_int32), ("host_plan_masks_ms", C.c_float),
+                ("host_plan_nodes_ms", C.c_float)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_ if n != "pad"}

@@ -13,6 +13,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -213,6 +214,8 @@ struct Planner {
     std::string err;
     long long layer_top = 0;
     std::vector<int> uses;  // how many nodes read each node
+    std::vector<PlannedOp> sorted_ops;
+    std::vector<Val> scratch_vals;
 
     explicit Planner(svgr_ctx *c) : ctx(c) {}
 
@@ -333,7 +336,7 @@ struct Planner {
     }
 
     // Layer.compose (svgrasterize.py:178-207)
-    Val compose(std::vector<Val> layers, int mode, const float *k, int lin)
+    Val compose(const std::vector<Val> &layers, int mode, const float *k, int lin)
     {
         if (layers.empty())
             return Val();
@@ -357,7 +360,7 @@ struct Planner {
             }
         }
         std::vector<SrcRec> ss;
-        ss.reserve(layers.size() + 2);
+        ss.reserve(layers.size() * 2);
         int level = 0;
         for (auto &l : layers)
             level = std::max(level, push_src(ss, l, pre, lin));
@@ -430,7 +433,8 @@ struct Planner {
             break;
         }
         case SVGR_N_GROUP: {
-            std::vector<Val> ls;
+            std::vector<Val> &ls = scratch_vals;
+            ls.clear();
             for (int k = 0; k < n.child_cnt; k++)
                 if (child(k).kind != VAL_EMPTY)
                     ls.push_back(child(k));
@@ -783,9 +787,26 @@ struct Planner {
         }
         c->layer_floats = align4(layer_top);
         // ---- order ops by (level, class); stable so that srcs stay valid
-        std::stable_sort(c->ops.begin(), c->ops.end(), [](const PlannedOp &a, const PlannedOp &b) {
-            return a.level != b.level ? a.level < b.level : a.cls < b.cls;
-        });
+        {
+            int max_level = 0;
+            for (auto &po : c->ops)
+                max_level = std::max(max_level, po.level);
+            if (max_level < (1 << 20)) {  // counting sort: a batch has a handful of levels and many ops
+                std::vector<int> start((size_t)(max_level + 1) * 4 + 1, 0);
+                for (auto &po : c->ops)
+                    start[(size_t)po.level * 4 + po.cls + 1]++;
+                for (size_t k = 1; k < start.size(); k++)
+                    start[k] += start[k - 1];
+                sorted_ops.resize(c->ops.size());
+                for (auto &po : c->ops)
+                    sorted_ops[start[(size_t)po.level * 4 + po.cls]++] = po;
+                c->ops.swap(sorted_ops);
+            } else {
+                std::stable_sort(c->ops.begin(), c->ops.end(), [](const PlannedOp &a, const PlannedOp &b) {
+                    return a.level != b.level ? a.level < b.level : a.cls < b.cls;
+                });
+            }
+        }
         int nl = 0, last_level = -1;
         size_t i = 0;
         while (i < c->ops.size()) {
@@ -1093,8 +1114,10 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
     // ---- plan, part 1: masks -> binning + coverage are launched before the node plan is made
     mark(3);
     Planner pl(ctx);
+    auto t_h0 = std::chrono::steady_clock::now();
     if (!pl.plan_masks())
         FAIL(SVGR_E_INVALID, pl.err);
+    auto t_h1 = std::chrono::steady_clock::now();
     {
         size_t b_masks = (size_t)ctx->n_path * sizeof(MaskRec);
         CK(ctx->pin_masks.ensure(b_masks + 64));
@@ -1141,8 +1164,10 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
     mark(6);
 
     // ---- plan, part 2 (host, concurrent with the launches above): nodes -> ops, then the op tables go up
+    auto t_h2 = std::chrono::steady_clock::now();
     if (!pl.plan_nodes())
         FAIL(SVGR_E_INVALID, pl.err);
+    auto t_h3 = std::chrono::steady_clock::now();
     ctx->planned = true;
     {
         size_t b_ops = ctx->ops.size() * sizeof(OpRec);
@@ -1270,6 +1295,8 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
         stats->coverage_bytes = ctx->cov_floats * 4 + ctx->n_binned * 36;
         stats->compose_bytes = ctx->compose_bytes, stats->canvas_pixels = ctx->canvas_pixels;
         stats->n_kernels = n_kernels;
+        stats->host_plan_masks_ms = std::chrono::duration<float, std::milli>(t_h1 - t_h0).count();
+        stats->host_plan_nodes_ms = std::chrono::duration<float, std::milli>(t_h3 - t_h2).count();
         stats->ms_plan = ms_plan, stats->ms_bin = ms_bin, stats->ms_coverage = ms_cov, stats->ms_compose = ms_cmp;
         stats->ms_canvas = ms_canvas, stats->ms_d2h = ms_d2h;
         stats->ms_total = ms_stroke + ms_flatten + ms_plan + ms_bin + ms_cov + ms_cmp + ms_canvas + ms_d2h;

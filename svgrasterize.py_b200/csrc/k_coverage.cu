@@ -292,6 +292,9 @@ coverage_kernel(const double *__restrict__ edges, const MaskRec *__restrict__ ma
                 float *__restrict__ cov)
 {
     __shared__ __align__(16) float trace[SVGR_BAND_ROWS][SVGR_TILE_COLS];
+    __shared__ double s_r0[COV_THREADS], s_r1[COV_THREADS], s_c0[COV_THREADS], s_dxdy[COV_THREADS];
+    __shared__ float s_dir[COV_THREADS];
+    __shared__ short2 s_rows[COV_THREADS];
 
     // ---- tile -> (mask, band, column chunk) through the tile -> mask table (expand_masks_kernel)
     const int tile = blockIdx.x;
@@ -305,47 +308,67 @@ coverage_kernel(const double *__restrict__ edges, const MaskRec *__restrict__ ma
     const int w = min(SVGR_TILE_COLS, m.cols - col0);     // columns that exist in the mask
     const int wpad = min(SVGR_TILE_COLS, m.stride - col0);  // columns that exist in memory (multiple of 4)
 
-    // ---- 1. zero the trace tile
+    // ---- 1. zero the part of the trace tile this band uses
     {
-        float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 *t4 = reinterpret_cast<float4 *>(&trace[0][0]);
-        for (int i = threadIdx.x; i < SVGR_BAND_ROWS * SVGR_TILE_COLS / 4; i += COV_THREADS)
-            t4[i] = z;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int q = wpad >> 2;  // float4 per row
+        for (int i = threadIdx.x; i < nrows * q; i += COV_THREADS) {
+            int y = i / q, x = i - y * q;
+            reinterpret_cast<float4 *>(&trace[y][0])[x] = z;
+        }
     }
-    __syncthreads();
 
-    // ---- 2. accumulate the signed areas of this band's edges
+    // ---- 2. accumulate the signed areas of this band's edges.  Two steps per chunk of COV_THREADS edges:
+    // (a) one thread per edge orients it and stores slope / row range in shared memory, (b) the (edge, row)
+    // pairs are spread over all threads -- 16 consecutive threads take the 16 rows of one edge -- so a steep
+    // edge costs one row's latency instead of sixteen.
     const int band = m.band_base + band_local;
     const int e_off = band_off[band];
     const int e_cnt = (int)max(0ll, min((long long)band_cnt[band], bin_cap - e_off));
-    for (int i = threadIdx.x; i < e_cnt; i += COV_THREADS) {
-        const double2 *e = reinterpret_cast<const double2 *>(edges + 4ull * bin_edges[e_off + i]);
-        double2 pa = e[0], pb = e[1];
-        double r0 = pa.x - (double)m.r0, c0 = pa.y - (double)m.c0;
-        double r1 = pb.x - (double)m.r0, c1 = pb.y - (double)m.c0;
-        double dir = 1.0;
-        if (!(r0 < r1)) {
-            double t;
-            dir = -1.0;
-            t = r0, r0 = r1, r1 = t;
-            t = c0, c0 = c1, c1 = t;
+    for (int chunk0 = 0; chunk0 < e_cnt; chunk0 += COV_THREADS) {
+        const int n_chunk = min(COV_THREADS, e_cnt - chunk0);
+        __syncthreads();  // trace zeroed / previous chunk consumed
+        if ((int)threadIdx.x < n_chunk) {
+            const double2 *e = reinterpret_cast<const double2 *>(edges + 4ull * bin_edges[e_off + chunk0 + threadIdx.x]);
+            double2 pa = e[0], pb = e[1];
+            double r0 = pa.x - (double)m.r0, c0 = pa.y - (double)m.c0;
+            double r1 = pb.x - (double)m.r0, c1 = pb.y - (double)m.c0;
+            float dir = 1.0f;
+            if (!(r0 < r1)) {
+                double t;
+                dir = -1.0f;
+                t = r0, r0 = r1, r1 = t;
+                t = c0, c0 = c1, c1 = t;
+            }
+            int ya = 0, yz = 0;
+            double dxdy = 0.0;
+            if (r0 != r1) {
+                dxdy = (c1 - c0) / (r1 - r0);
+                c0 -= (double)col0;
+                double ys = r0 > 0.0 ? r0 : 0.0;
+                int y_first = (int)ys;
+                double yend_f = ceil(r1);
+                int y_last = yend_f < (double)m.rows ? (int)yend_f : m.rows;
+                ya = max(y_first, yb), yz = min(y_last, yb + nrows);
+            }
+            s_r0[threadIdx.x] = r0, s_r1[threadIdx.x] = r1, s_c0[threadIdx.x] = c0, s_dxdy[threadIdx.x] = dxdy;
+            s_dir[threadIdx.x] = dir;
+            s_rows[threadIdx.x] = make_short2((short)(ya - yb), (short)(yz - yb));
         }
-        if (r0 == r1)
-            continue;
-        double dxdy = (c1 - c0) / (r1 - r0);
-        c0 -= (double)col0;
-        double ys = r0 > 0.0 ? r0 : 0.0;
-        int y_first = (int)ys;
-        double yend_f = ceil(r1);
-        int y_last = yend_f < (double)m.rows ? (int)yend_f : m.rows;
-        int ya = max(y_first, yb), yz = min(y_last, yb + nrows);
-        for (int y = ya; y < yz; y++) {
+        __syncthreads();
+        for (int p = threadIdx.x; p < n_chunk * SVGR_BAND_ROWS; p += COV_THREADS) {
+            const int ei = p >> 4, yl = p & (SVGR_BAND_ROWS - 1);
+            const short2 rr = s_rows[ei];
+            if (yl < rr.x || yl >= rr.y)
+                continue;
+            const double r0 = s_r0[ei], r1 = s_r1[ei], dxdy = s_dxdy[ei];
+            const int y = yb + yl;
             double ytop = (double)(y + 1) < r1 ? (double)(y + 1) : r1;
             double ybot = (double)y > r0 ? (double)y : r0;
             double dy = ytop - ybot;
-            double x = c0 + dxdy * (ybot - r0);
+            double x = s_c0[ei] + dxdy * (ybot - r0);
             double x_next = x + dxdy * dy;
-            edge_row(trace[y - yb], w, x, x_next, dir * dy);
+            edge_row(trace[yl], w, x, x_next, (double)s_dir[ei] * dy);
         }
     }
     __syncthreads();

@@ -91,7 +91,7 @@ __device__ __forceinline__ float4 grad_color(double v, const StopRec *__restrict
     for (int k = 0; k + 1 < n; k++) {
         double o0 = st[k].offset, o1 = st[k + 1].offset;
         if (v > o0 && v <= o1) {
-            float ratio = (float)((v - o0) / (o1 - o0));
+            float ratio = (float)((v - o0) * st[k].inv_span);
             float ir = 1.0f - ratio;
             o.x += ir * st[k].color[0] + ratio * st[k + 1].color[0];
             o.y += ir * st[k].color[1] + ratio * st[k + 1].color[1];

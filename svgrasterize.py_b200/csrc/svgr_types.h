@@ -89,8 +89,8 @@ struct PaintRec {
 
 struct StopRec {
     double offset;
-    float color[4];  // premultiplied, already in the target colour space
-    float pad[2];
+    float color[4];   // premultiplied, already in the target colour space
+    double inv_span;  // 1 / (next offset - offset): the interpolation ratio is a multiply on the device
 };
 
 // ---- layers and ops ----------------------------------------------------------------

@@ -366,11 +366,14 @@ class Encoder:
 
     def _stops(self, paint, lin) -> tuple:
         off = len(self.stops)
-        for o, c in paint.stops:
-            col = np.asarray(c, dtype=np.float64) if lin else paint_to_srgb(c)
-            self.stops.append((float(o), tuple(float(v) for v in col)))
         if not paint.stops:
             raise ValueError("gradient without stops")
+        offs = [float(o) for o, _ in paint.stops]
+        for k, (o, c) in enumerate(paint.stops):
+            col = np.asarray(c, dtype=np.float64) if lin else paint_to_srgb(c)
+            with np.errstate(divide="ignore"):
+                inv = float(np.float64(1.0) / np.float64(offs[k + 1] - offs[k])) if k + 1 < len(offs) else 0.0
+            self.stops.append((float(o), tuple(float(v) for v in col), inv))
         return off, len(paint.stops)
 
     def _paint_record(self, **kw) -> int:
@@ -770,9 +773,10 @@ class Encoder:
             for k, v in rec.items():
                 row[k] = v
         p.stops = np.zeros(len(self.stops), _lib.STOP_DT)
-        for i, (o, c) in enumerate(self.stops):
+        for i, (o, c, inv) in enumerate(self.stops):
             p.stops[i]["offset"] = o
             p.stops[i]["color"] = c
+            p.stops[i]["inv_span"] = inv
         p.n_focal = self.n_focal
         p.nodes = np.zeros(len(self.nodes), _lib.NODE_DT)
         for i, (tag, a, b, c, d, off, cnt, flags, f) in enumerate(self.nodes):
