@@ -198,6 +198,10 @@ compose_kernel(RenderTables T, const OpRec *__restrict__ ops, const int *__restr
 #pragma unroll
                     for (int k = 0; k < CMP_PX; k++)
                         a[k] = (live >> k & 1) ? __ldg(p + (base + k * step)) : 0.f;
+                    // nothing of the path in these four pixels (the inside of a stroked ring, the corners of a
+                    // blob's box): an all-zero source is the identity of the over blend
+                    if (skip_outside && !first && a[0] == 0.f && a[1] == 0.f && a[2] == 0.f && a[3] == 0.f)
+                        continue;
                     if (s.kind == SRC_COVPAINT) {
                         const PaintRec &pr = s_paint[j];
                         if (pr.kind == PAINT_SOLID) {
