@@ -365,21 +365,29 @@ void svgr_launch_compose(const RenderTables &T, const OpRec *ops, const int *til
         compose_kernel<<<n_tiles, 256, 0, s>>>(T, ops, tile_op, layers_out, canvas_out);
 }
 
-// tile -> op table of one launch: op i owns tiles [ops[i].tile_base, ops[i + 1].tile_base)
+// tile -> op table of one launch: op i owns tiles [ops[i].tile_base, ops[i + 1].tile_base).  One thread per
+// tile, binary search over the ops (their tile_base column stays in L1/L2): a single 8192 x 8192 op has 65 536
+// tiles, so this must not be a per-op loop.
 __global__ void expand_ops_kernel(const OpRec *__restrict__ ops, int n_ops, int n_tiles, int *__restrict__ tile_op)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_ops)
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles)
         return;
-    int a = ops[i].tile_base, b = (i + 1 < n_ops) ? ops[i + 1].tile_base : n_tiles;
-    for (int t = a; t < b; t++)
-        tile_op[t] = i;
+    int lo = 0, hi = n_ops - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (__ldg(&ops[mid].tile_base) <= t)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    tile_op[t] = lo;
 }
 
 void svgr_launch_expand_ops(const OpRec *ops, int n_ops, int n_tiles, int *tile_op, cudaStream_t s)
 {
     if (n_ops > 0 && n_tiles > 0)
-        expand_ops_kernel<<<(n_ops + 127) / 128, 128, 0, s>>>(ops, n_ops, n_tiles, tile_op);
+        expand_ops_kernel<<<(n_tiles + 255) / 256, 256, 0, s>>>(ops, n_ops, n_tiles, tile_op);
 }
 
 void svgr_launch_focal_flags(const RenderTables &T, const void *jobs, int n_jobs, int n_blocks, int *flags,

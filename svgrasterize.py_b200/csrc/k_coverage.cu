@@ -434,12 +434,18 @@ void svgr_launch_bin_fill(const double *edges, const uint32_t *edge_path, unsign
 __global__ void expand_masks_kernel(const MaskRec *__restrict__ masks, int n_masks, int n_tiles,
                                     int *__restrict__ tile_mask)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_masks)
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles)
         return;
-    int a = masks[i].tile_base, b = (i + 1 < n_masks) ? masks[i + 1].tile_base : n_tiles;
-    for (int t = a; t < b; t++)
-        tile_mask[t] = i;
+    int lo = 0, hi = n_masks - 1;
+    while (lo < hi) {  // last mask with tile_base <= t (empty masks share their successor's base and sort before it)
+        int mid = (lo + hi + 1) >> 1;
+        if (__ldg(&masks[mid].tile_base) <= t)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    tile_mask[t] = lo;
 }
 
 void svgr_launch_coverage(const double *edges, const MaskRec *masks, int n_masks, int n_tiles, int *tile_mask,
@@ -448,6 +454,6 @@ void svgr_launch_coverage(const double *edges, const MaskRec *masks, int n_masks
 {
     if (n_tiles <= 0)
         return;
-    expand_masks_kernel<<<(n_masks + 127) / 128, 128, 0, s>>>(masks, n_masks, n_tiles, tile_mask);
+    expand_masks_kernel<<<(n_tiles + 255) / 256, 256, 0, s>>>(masks, n_masks, n_tiles, tile_mask);
     coverage_kernel<<<n_tiles, COV_THREADS, 0, s>>>(edges, masks, tile_mask, band_off, band_cnt, bin_edges, bin_cap, cov);
 }

@@ -10,14 +10,19 @@ __device__ __forceinline__ float4 f4(float x, float y, float z, float w) { retur
 
 __device__ __forceinline__ float clip01(float v) { return fminf(fmaxf(v, 0.f), 1.f); }
 
+// x^y for x in (0, 1], y a constant: exp2(y log2 x) on the special function unit.  __log2f is accurate to
+// 2^-21.4 absolute near 1 and a few ulp elsewhere, so the result is within ~2e-6 relative of powf -- inside
+// the 1e-5 layer tolerance and far inside +-1 LSB -- at a fifth of its instruction count.
+__device__ __forceinline__ float pow_unit(float x, float y) { return exp2f(y * __log2f(x)); }
+
 __device__ __forceinline__ float lin_to_srgb1(float v)
 {
-    return v <= 0.0031308f ? v * 12.92f : 1.055f * powf(v, 1.0f / 2.4f) - 0.055f;
+    return v <= 0.0031308f ? v * 12.92f : 1.055f * pow_unit(v, 1.0f / 2.4f) - 0.055f;
 }
 
 __device__ __forceinline__ float srgb_to_lin1(float v)
 {
-    return v <= 0.04045f ? v / 12.92f : powf((v + 0.055f) / 1.055f, 2.4f);
+    return v <= 0.04045f ? v * (1.0f / 12.92f) : pow_unit((v + 0.055f) * (1.0f / 1.055f), 2.4f);
 }
 
 // color_pre_to_straight_alpha (svgrasterize.py:471-477): divide where alpha > 1e-4, clip all to [0, 1]

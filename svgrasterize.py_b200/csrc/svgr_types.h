@@ -180,7 +180,9 @@ struct FocalJob {
 };
 
 // tile shapes (rows x cols of output pixels per CTA)
+#ifndef SVGR_CMP_TR
 #define SVGR_CMP_TR 32
+#endif
 #define SVGR_CMP_TC 32
 #define SVGR_C2D_TR 8
 #define SVGR_C2D_TC 32
