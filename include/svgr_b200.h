@@ -189,6 +189,12 @@ int svgr_render(svgr_ctx *ctx, const svgr_program *prog, void *stream, int stop_
  * (no host->device copy of the program); used for kernel-only throughput measurements. */
 int svgr_render_resident(svgr_ctx *ctx, void *stream, uint8_t *out_device, int timing, svgr_stats *stats);
 
+/* Host-only: plan `prog` for the given path boxes (n_path x 4 int32) `reps` times without touching CUDA;
+ * reports the best wall time of the two planning phases and info = {ops, sources, launches, levels,
+ * layer arena floats, compose bytes}.  For profiling and CPU tests of the planner. */
+int svgr_debug_plan(const svgr_program *prog, const int32_t *boxes, int reps, float *ms_masks, float *ms_nodes,
+                    int64_t *info);
+
 /* ---- taps on the state left by the last svgr_render ------------------------------------- */
 int svgr_read_edges(svgr_ctx *ctx, double *edges, uint32_t *edge_path, int64_t cap, int64_t *n_edges);
 int svgr_read_boxes(svgr_ctx *ctx, int32_t *boxes /* n_path x 4 */, double *minmax /* n_path x 4 or NULL */);

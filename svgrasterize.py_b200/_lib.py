@@ -84,6 +84,8 @@ SYMBOLS = {
     "svgr_render": (C.c_int, [C.c_void_p, C.POINTER(Program), C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
                               C.POINTER(Stats)]),
     "svgr_render_resident": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Stats)]),
+    "svgr_debug_plan": (C.c_int, [C.POINTER(Program), C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                  C.c_void_p]),
     "svgr_read_edges": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
     "svgr_read_boxes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "svgr_read_mask": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),

@@ -10,6 +10,7 @@
 //   -> canvas quantise -> (D2H RGBA8)
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -213,11 +214,18 @@ struct Planner {
     svgr_ctx *ctx;
     std::string err;
     long long layer_top = 0;
-    std::vector<int> uses;  // how many nodes read each node
+    std::vector<int> uses_own;
+    const std::vector<int> *uses_p = nullptr;  // how many nodes read each node (shared, read-only while planning)
     std::vector<PlannedOp> sorted_ops;
     std::vector<Val> scratch_vals;
+    // outputs: the context's tables, or thread-local ones when the node range is planned by several threads
+    std::vector<PlannedOp> *ops_p;
+    std::vector<SrcRec> *srcs_p;
+    std::vector<FocalJob> *focal_p;
+    int n_focal_blocks = 0;
+    long long layer_pixels = 0;
 
-    explicit Planner(svgr_ctx *c) : ctx(c) {}
+    explicit Planner(svgr_ctx *c) : ctx(c), ops_p(&c->ops), srcs_p(&c->srcs), focal_p(&c->focal_jobs) {}
 
     Val alloc(int kind, int r0, int c0, int rows, int cols, int pre, int lin, int level)
     {
@@ -233,7 +241,7 @@ struct Planner {
             v.stride = (int)align4(cols);
             layer_top += (long long)rows * v.stride;
         }
-        ctx->layer_pixels += (long long)rows * cols;
+        layer_pixels += (long long)rows * cols;
         return v;
     }
 
@@ -292,15 +300,15 @@ struct Planner {
         o.stride = out.stride;
         o.out_ch = out.kind == SRC_L4 ? 4 : 1;
         o.out_off = out.off;
-        o.src_off = (int)ctx->srcs.size(), o.src_cnt = (int)ss.size();
+        o.src_off = (int)srcs_p->size(), o.src_cnt = (int)ss.size();
         o.post = post, o.aux = aux, o.k0 = k0, o.k1 = k1, o.stencil = stencil;
         o.mul = mul;
         if (k)
             for (int i = 0; i < 4; i++)
                 o.k[i] = k[i];
         for (auto &s : ss)
-            ctx->srcs.push_back(s);
-        ctx->ops.push_back(p);
+            srcs_p->push_back(s);
+        ops_p->push_back(p);
     }
 
     // single-source pass: convert / multiply / post-process into a fresh layer
@@ -366,7 +374,7 @@ struct Planner {
             level = std::max(level, push_src(ss, l, pre, lin));
         level += 1;
         Val out = alloc(SRC_L4, r0, c0, r1 - r0, c1 - c0, pre, lin, level);
-        out.op_index = (int)ctx->ops.size();
+        out.op_index = (int)ops_p->size();
         emit(0, OP_COMPOSE, out, ss, mode, POST_NONE, 1.0f, level, k);
         return out;
     }
@@ -425,9 +433,9 @@ struct Planner {
                 } else if (p.kind == PAINT_RADIAL_FOCAL) {
                     FocalJob j;
                     j.paint = n.b, j.r0 = m.r0, j.c0 = m.c0, j.rows = m.rows, j.cols = m.cols;
-                    j.block_base = ctx->n_focal_blocks;
-                    ctx->n_focal_blocks += (int)(((long long)m.rows * m.cols + 1023) / 1024);
-                    ctx->focal_jobs.push_back(j);
+                    j.block_base = n_focal_blocks;
+                    n_focal_blocks += (int)(((long long)m.rows * m.cols + 1023) / 1024);
+                    focal_p->push_back(j);
                 }
             }
             break;
@@ -660,9 +668,9 @@ struct Planner {
             }
             // When the root is an over-group that nobody else reads, its fold writes the canvas directly
             // (clip, straight-alpha sRGB, RGBA8) instead of a float layer that is read back once.
-            if (v.kind == SRC_L4 && !v.is_virtual() && v.op_index >= 0 && v.owner == ch[0] && uses[ch[0]] == 1 &&
+            if (v.kind == SRC_L4 && !v.is_virtual() && v.op_index >= 0 && v.owner == ch[0] && (*uses_p)[ch[0]] == 1 &&
                 v.pre == 1 && v.lin == lin) {
-                PlannedOp &po = ctx->ops[v.op_index];
+                PlannedOp &po = (*ops_p)[v.op_index];
                 if (po.cls == 0 && po.op.kind == OP_COMPOSE && po.op.mode == MODE_OVER && po.op.post == POST_NONE &&
                     po.op.mul == 1.0f) {
                     po.cls = 3;
@@ -670,7 +678,7 @@ struct Planner {
                     o.kind = OP_CANVAS, o.aux = lin;
                     o.r0 = n.c, o.c0 = n.d, o.rows = n.a, o.cols = n.b, o.stride = n.b, o.out_ch = 4;
                     o.out_off = out_off;
-                    ctx->layer_pixels -= (long long)v.rows * v.cols;
+                    layer_pixels -= (long long)v.rows * v.cols;
                     out = Val();
                     break;
                 }
@@ -688,11 +696,11 @@ struct Planner {
             if (v.kind != VAL_EMPTY)
                 level = push_src(ss, v, 1, lin);
             p.level = level + 1;
-            o.src_off = (int)ctx->srcs.size();
+            o.src_off = (int)srcs_p->size();
             o.src_cnt = (int)ss.size();
             for (auto &sr : ss)
-                ctx->srcs.push_back(sr);
-            ctx->ops.push_back(p);
+                srcs_p->push_back(sr);
+            ops_p->push_back(p);
             out = v;
             break;
         }
@@ -754,15 +762,22 @@ struct Planner {
         return true;
     }
 
-    // the scene program: node values, layer arena, ops per level (runs on the host while the GPU bins and
-    // rasterises coverage)
-    bool plan_nodes()
+    // ---- the scene program.  Planning is incremental: the node table is cut at scene boundaries (right after
+    // canvas nodes) into chunks, and every chunk yields its own ops and launches, so that the pipeline can
+    // upload and launch chunk k while the host plans chunk k + 1.
+    std::vector<int> chunk_bounds;
+
+    bool begin_nodes()
     {
         svgr_ctx *c = ctx;
         c->ops.clear(), c->srcs.clear(), c->focal_jobs.clear(), c->launches.clear();
-        c->n_focal_blocks = 0;
-        c->layer_pixels = 0;
+        c->n_focal_blocks = 0, c->layer_pixels = 0, c->n_levels = 0;
+        c->compose_bytes = 0, c->canvas_pixels = 0;
+        n_focal_blocks = 0, layer_pixels = 0, layer_top = 0;
+        std::vector<int> &uses = uses_own;
         uses.assign(c->n_node, 0);
+        uses_p = &uses;
+        std::vector<int> cuts;  // indices right after a canvas node: candidate scene boundaries
         for (int i = 0; i < c->n_node; i++) {
             const svgr_node &n = c->h_nodes[i];
             for (int k = 0; k < n.child_cnt; k++) {
@@ -774,41 +789,95 @@ struct Planner {
                 uses[n.d]++;
             if (n.flags & 2)
                 uses[i]++;  // read back by the caller
+            if (n.tag == SVGR_N_CANVAS)
+                cuts.push_back(i + 1);
         }
-        c->vals.assign(c->n_node, Val());
-        for (int i = 0; i < c->n_node; i++) {
+        c->vals.resize(c->n_node);  // every entry is assigned by plan_range before anyone reads it
+        // chunks of at least 4096 nodes, at most 8 of them, cut where no reference crosses
+        chunk_bounds.assign(1, 0);
+        const int want_chunks = std::min(8, c->n_node / 4096);
+        if (want_chunks >= 2 && !cuts.empty()) {
+            std::vector<int> min_ref(c->n_node + 1, c->n_node);  // smallest index referenced at or after i
+            for (int i = c->n_node - 1; i >= 0; i--) {
+                const svgr_node &n = c->h_nodes[i];
+                int m = min_ref[i + 1];
+                for (int k = 0; k < n.child_cnt; k++)
+                    m = std::min(m, c->h_children[n.child_off + k]);
+                if (n.tag == SVGR_N_LEAF && n.d >= 0)
+                    m = std::min(m, n.d);
+                min_ref[i] = m;
+            }
+            for (int t = 1; t < want_chunks; t++) {
+                int want = (int)((long long)c->n_node * t / want_chunks);
+                auto it = std::lower_bound(cuts.begin(), cuts.end(), want);
+                if (it == cuts.end())
+                    break;
+                int cut = *it;
+                if (cut > chunk_bounds.back() && cut < c->n_node && min_ref[cut] >= cut)
+                    chunk_bounds.push_back(cut);
+            }
+        }
+        chunk_bounds.push_back(c->n_node);
+        return true;
+    }
+
+    int n_chunks() const { return (int)chunk_bounds.size() - 1; }
+
+    bool plan_range(int a, int b)
+    {
+        svgr_ctx *c = ctx;
+        for (int i = a; i < b; i++) {
             // a value nobody reads is not computed (SourceAlpha of a filter that only uses SourceGraphic,
             // svgrasterize.py:1803-1809, is the common case)
             const svgr_node &n = c->h_nodes[i];
-            if (uses[i] == 0 && n.tag != SVGR_N_CANVAS && n.tag != SVGR_N_LEAF && i != c->n_node - 1)
+            if ((*uses_p)[i] == 0 && n.tag != SVGR_N_CANVAS && n.tag != SVGR_N_LEAF && i != c->n_node - 1) {
+                c->vals[i] = Val();
                 continue;
+            }
             if (!node(i, c->vals[i]))
                 return false;
         }
+        return true;
+    }
+
+    // Plans chunk k.  On return ctx->ops[op_begin ..] are the chunk's ops, grouped by (level, class), and
+    // ctx->launches[launch_begin ..] its launches (op_begin absolute).
+    bool plan_chunk(int k, int *op_begin_out, int *launch_begin_out)
+    {
+        svgr_ctx *c = ctx;
+        const size_t op_begin = c->ops.size();
+        const size_t launch_begin = c->launches.size();
+        *op_begin_out = (int)op_begin, *launch_begin_out = (int)launch_begin;
+        if (!plan_range(chunk_bounds[k], chunk_bounds[k + 1]))
+            return false;
+        c->n_focal_blocks = n_focal_blocks, c->layer_pixels = layer_pixels;
         c->layer_floats = align4(layer_top);
-        // ---- order ops by (level, class); stable so that srcs stay valid
+        const size_t n_new = c->ops.size() - op_begin;
+        if (n_new == 0)
+            return true;
+        // ---- order the chunk's ops by (level, class)
         {
             int max_level = 0;
-            for (auto &po : c->ops)
-                max_level = std::max(max_level, po.level);
-            if (max_level < (1 << 20)) {  // counting sort: a batch has a handful of levels and many ops
+            for (size_t q = op_begin; q < c->ops.size(); q++)
+                max_level = std::max(max_level, c->ops[q].level);
+            if (max_level < (1 << 20)) {  // counting sort: a chunk has a handful of levels and many ops
                 std::vector<int> start((size_t)(max_level + 1) * 4 + 1, 0);
-                for (auto &po : c->ops)
-                    start[(size_t)po.level * 4 + po.cls + 1]++;
-                for (size_t k = 1; k < start.size(); k++)
-                    start[k] += start[k - 1];
-                sorted_ops.resize(c->ops.size());
-                for (auto &po : c->ops)
-                    sorted_ops[start[(size_t)po.level * 4 + po.cls]++] = po;
-                c->ops.swap(sorted_ops);
+                for (size_t q = op_begin; q < c->ops.size(); q++)
+                    start[(size_t)c->ops[q].level * 4 + c->ops[q].cls + 1]++;
+                for (size_t q = 1; q < start.size(); q++)
+                    start[q] += start[q - 1];
+                sorted_ops.resize(n_new);
+                for (size_t q = op_begin; q < c->ops.size(); q++)
+                    sorted_ops[start[(size_t)c->ops[q].level * 4 + c->ops[q].cls]++] = c->ops[q];
+                std::copy(sorted_ops.begin(), sorted_ops.end(), c->ops.begin() + op_begin);
             } else {
-                std::stable_sort(c->ops.begin(), c->ops.end(), [](const PlannedOp &a, const PlannedOp &b) {
+                std::stable_sort(c->ops.begin() + op_begin, c->ops.end(), [](const PlannedOp &a, const PlannedOp &b) {
                     return a.level != b.level ? a.level < b.level : a.cls < b.cls;
                 });
             }
         }
         int nl = 0, last_level = -1;
-        size_t i = 0;
+        size_t i = op_begin;
         while (i < c->ops.size()) {
             size_t j = i;
             Launch L;
@@ -832,6 +901,27 @@ struct Planner {
                 o.tile_base = (int)tiles;
                 tiles += (long long)ceil_div(o.rows, tr) * ceil_div(o.cols, tc);
                 L.smem = std::max(L.smem, smem);
+                // algorithmic traffic: every output pixel written once, every source pixel read once
+                const PlannedOp &po = c->ops[j];
+                if (po.cls == 3) {
+                    c->canvas_pixels += (long long)o.rows * o.cols;
+                    c->compose_bytes += (long long)o.rows * o.cols * 4;  // RGBA8 out
+                } else {
+                    c->compose_bytes += (long long)o.rows * o.cols * o.out_ch * 4;
+                }
+                for (int q = 0; q < o.src_cnt; q++) {
+                    const SrcRec &sr = c->srcs[o.src_off + q];
+                    long long rr, cc;
+                    if (po.cls == 0 || po.cls == 3) {
+                        rr = std::min(o.r0 + o.rows, sr.r0 + sr.rows) - std::max(o.r0, sr.r0);
+                        cc = std::min(o.c0 + o.cols, sr.c0 + sr.cols) - std::max(o.c0, sr.c0);
+                    } else {
+                        rr = sr.rows, cc = sr.cols;
+                    }
+                    if (rr > 0 && cc > 0)
+                        c->compose_bytes +=
+                            rr * cc * ((sr.kind == SRC_L4 || sr.kind == SRC_MOD_L4A || sr.kind == SRC_MOD_LUMA) ? 16 : 4);
+                }
                 j++;
             }
             if (tiles > 0x7fffff00ll) {
@@ -848,29 +938,19 @@ struct Planner {
                 nl++, last_level = c->ops[i].level;
             i = j;
         }
-        c->n_levels = nl;
-        // algorithmic traffic of the compose-class launches
-        c->compose_bytes = 0, c->canvas_pixels = 0;
-        for (auto &po : c->ops) {
-            const OpRec &o = po.op;
-            if (po.cls == 3) {
-                c->canvas_pixels += (long long)o.rows * o.cols;
-                c->compose_bytes += (long long)o.rows * o.cols * 4;  // RGBA8 out
-            } else {
-                c->compose_bytes += (long long)o.rows * o.cols * o.out_ch * 4;
-            }
-            for (int k = 0; k < o.src_cnt; k++) {
-                const SrcRec &sr = c->srcs[o.src_off + k];
-                long long rr, cc;
-                if (po.cls == 0 || po.cls == 3) {
-                    rr = std::min(o.r0 + o.rows, sr.r0 + sr.rows) - std::max(o.r0, sr.r0);
-                    cc = std::min(o.c0 + o.cols, sr.c0 + sr.cols) - std::max(o.c0, sr.c0);
-                } else {
-                    rr = sr.rows, cc = sr.cols;
-                }
-                if (rr > 0 && cc > 0)
-                    c->compose_bytes += rr * cc * ((sr.kind == SRC_L4 || sr.kind == SRC_MOD_L4A || sr.kind == SRC_MOD_LUMA) ? 16 : 4);
-            }
+        c->n_levels = std::max(c->n_levels, nl);
+        return true;
+    }
+
+    // everything at once (taps, CPU tests)
+    bool plan_nodes()
+    {
+        if (!begin_nodes())
+            return false;
+        for (int k = 0; k < n_chunks(); k++) {
+            int a, b;
+            if (!plan_chunk(k, &a, &b))
+                return false;
         }
         return true;
     }
@@ -897,7 +977,7 @@ float ev_ms(cudaEvent_t a, cudaEvent_t b)
 // ---------------------------------------------------------------------------------------------
 // pipeline
 // ---------------------------------------------------------------------------------------------
-static int load_program(svgr_ctx *ctx, const svgr_program *p, cudaStream_t s)
+static int load_program(svgr_ctx *ctx, const svgr_program *p, cudaStream_t s, bool host_only = false)
 {
     if (!p)
         FAIL(SVGR_E_INVALID, "null program");
@@ -907,6 +987,7 @@ static int load_program(svgr_ctx *ctx, const svgr_program *p, cudaStream_t s)
     ctx->n_stroke_seg = p->n_stroke_seg, ctx->n_paint = p->n_paint, ctx->n_stop = p->n_stop, ctx->n_focal = p->n_focal;
     ctx->n_node = p->n_node, ctx->canvas_bytes = p->canvas_bytes;
     ctx->n_weight = p->n_weight, ctx->n_matrix = p->n_matrix;
+    if (!host_only) {
     CK(upload(ctx->d_seg_tag, p->seg_tag, (size_t)p->n_seg, s));
     CK(upload(ctx->d_seg_data, p->seg_data, (size_t)p->n_seg * 8, s));
     CK(upload(ctx->d_seg_path, p->seg_path, (size_t)p->n_seg, s));
@@ -921,6 +1002,7 @@ static int load_program(svgr_ctx *ctx, const svgr_program *p, cudaStream_t s)
     CK(upload(ctx->d_stops, p->stops, (size_t)p->n_stop, s));
     CK(upload(ctx->d_matrices, p->matrices, (size_t)p->n_matrix * 20, s));
     CK(upload(ctx->d_weights, p->weights, (size_t)p->n_weight, s));
+    }
     ctx->h_paths.assign(p->paths, p->paths + p->n_path);
     ctx->h_paints.assign(p->paints, p->paints + p->n_paint);
     ctx->h_nodes.assign(p->nodes, p->nodes + p->n_node);
@@ -1163,74 +1245,30 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
     n_kernels += ctx->n_cov_tiles > 0 ? 2 : 0;
     mark(6);
 
-    // ---- plan, part 2 (host, concurrent with the launches above): nodes -> ops, then the op tables go up
+    // ---- plan, part 2 + pixels, interleaved: the node table is planned chunk by chunk (host); as soon as a
+    // chunk's op tables exist they are copied up and its launches are issued, so the GPU composes chunk k
+    // while the host plans chunk k + 1 (and bins / rasterises coverage while it plans chunk 0).
     auto t_h2 = std::chrono::steady_clock::now();
-    if (!pl.plan_nodes())
-        FAIL(SVGR_E_INVALID, pl.err);
-    auto t_h3 = std::chrono::steady_clock::now();
-    ctx->planned = true;
-    {
-        size_t b_ops = ctx->ops.size() * sizeof(OpRec);
-        size_t b_srcs = ctx->srcs.size() * sizeof(SrcRec);
-        size_t b_focal = ctx->focal_jobs.size() * sizeof(FocalJob);
-        CK(ctx->pin_plan.ensure(b_ops + b_srcs + b_focal + 64));
-        char *pp = (char *)ctx->pin_plan.p;
-        OpRec *po = (OpRec *)pp;
-        for (size_t i = 0; i < ctx->ops.size(); i++)
-            po[i] = ctx->ops[i].op;
-        if (b_srcs)
-            memcpy(pp + b_ops, ctx->srcs.data(), b_srcs);
-        if (b_focal)
-            memcpy(pp + b_ops + b_srcs, ctx->focal_jobs.data(), b_focal);
-        CK(ctx->d_ops.ensure(std::max<size_t>(b_ops, 16)));
-        CK(ctx->d_srcs.ensure(std::max<size_t>(b_srcs, 16)));
-        CK(ctx->d_focal_jobs.ensure(std::max<size_t>(b_focal, 16)));
-        if (b_ops)
-            CK(cudaMemcpyAsync(ctx->d_ops.p, pp, b_ops, cudaMemcpyHostToDevice, s));
-        if (b_srcs)
-            CK(cudaMemcpyAsync(ctx->d_srcs.p, pp + b_ops, b_srcs, cudaMemcpyHostToDevice, s));
-        if (b_focal)
-            CK(cudaMemcpyAsync(ctx->d_focal_jobs.p, pp + b_ops + b_srcs, b_focal, cudaMemcpyHostToDevice, s));
-    }
-    CK(ctx->d_layers.ensure((size_t)std::max<long long>(ctx->layer_floats, 4) * 4));
-    CK(ctx->d_focal_flags.ensure((size_t)std::max(ctx->n_focal, 1) * 4));
-    {
-        long long max_tiles = 1;
-        for (auto &L : ctx->launches)
-            max_tiles = std::max<long long>(max_tiles, L.n_tiles);
-        CK(ctx->d_tile_map.ensure((size_t)max_tiles * 4));
-    }
-    mark(10);
+    float host_nodes_ms = 0.f;
     int n_launches = 0;
-    if (stop_after != SVGR_STOP_COVERAGE) {
-        RenderTables T;
-        T.srcs = ctx->d_srcs.as<SrcRec>(), T.paints = ctx->d_paints.as<PaintRec>(), T.stops = ctx->d_stops.as<StopRec>();
-        T.focal_flags = ctx->d_focal_flags.as<int>(), T.cov = ctx->d_cov.as<float>(), T.layers = ctx->d_layers.as<float>();
-        T.matrices = ctx->d_matrices.as<float>(), T.weights = ctx->d_weights.as<float>();
-        if (ctx->n_focal > 0) {
+    if (!pl.begin_nodes())
+        FAIL(SVGR_E_INVALID, pl.err);
+    {
+        // capacities that hold for every chunk: device tables must not move while launches are in flight
+        const size_t ops_cap = (size_t)ctx->n_node * 3 + 64, srcs_cap = ((size_t)ctx->h_children.size() + ctx->n_node) * 3 + 64;
+        const size_t focal_cap = (size_t)ctx->n_path + 16;
+        CK(ctx->d_ops.ensure(ops_cap * sizeof(OpRec)));
+        CK(ctx->d_srcs.ensure(srcs_cap * sizeof(SrcRec)));
+        CK(ctx->d_focal_jobs.ensure(focal_cap * sizeof(FocalJob)));
+        CK(ctx->pin_plan.ensure(ops_cap * sizeof(OpRec) + srcs_cap * sizeof(SrcRec) + focal_cap * sizeof(FocalJob) + 64));
+        CK(ctx->d_focal_flags.ensure((size_t)std::max(ctx->n_focal, 1) * 4));
+        if (ctx->n_focal > 0)
             CK(cudaMemsetAsync(ctx->d_focal_flags.p, 0, (size_t)ctx->n_focal * 4, s));
-            svgr_launch_focal_flags(T, ctx->d_focal_jobs.p, (int)ctx->focal_jobs.size(), ctx->n_focal_blocks,
-                                    ctx->d_focal_flags.as<int>(), s);
-            n_kernels += ctx->n_focal_blocks > 0;
-        }
-        // external layers
-        for (int i = 0; i < ctx->n_node; i++) {
-            const svgr_node &n = ctx->h_nodes[i];
-            if (n.tag != SVGR_N_EXTERNAL || ctx->vals[i].kind == VAL_EMPTY)
-                continue;
-            const Val &v = ctx->vals[i];
-            const std::vector<float> &src = ctx->h_ext_data[n.a];
-            if (v.kind == SRC_L4)
-                CK(cudaMemcpyAsync(ctx->d_layers.as<float>() + v.off, src.data(), src.size() * 4, cudaMemcpyHostToDevice, s));
-            else
-                CK(cudaMemcpy2DAsync(ctx->d_layers.as<float>() + v.off, (size_t)v.stride * 4, src.data(), (size_t)v.cols * 4,
-                                     (size_t)v.cols * 4, v.rows, cudaMemcpyHostToDevice, s));
-        }
+        char *pin_ops = (char *)ctx->pin_plan.p;
+        char *pin_srcs = pin_ops + ops_cap * sizeof(OpRec);
+        char *pin_focal = pin_srcs + srcs_cap * sizeof(SrcRec);
         uint8_t *canvas = nullptr;
-        bool has_canvas = false;
-        for (auto &L : ctx->launches)
-            has_canvas |= (L.cls == 3);
-        if (has_canvas) {
+        if (ctx->canvas_bytes > 0) {
             if (out_on_device && out) {
                 canvas = out;
             } else {
@@ -1238,30 +1276,109 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
                 canvas = ctx->d_canvas.as<uint8_t>();
             }
         }
-        for (auto &L : ctx->launches) {
-            const OpRec *ops = ctx->d_ops.as<OpRec>() + L.op_begin;
-            const int *tile_op = ctx->d_tile_map.as<int>();
-            svgr_launch_expand_ops(ops, L.op_count, L.n_tiles, ctx->d_tile_map.as<int>(), s);
-            if (L.cls == 0)
-                svgr_launch_compose(T, ops, tile_op, L.n_tiles, ctx->d_layers.as<float>(), nullptr, s);
-            else if (L.cls == 1) {
-                if (svgr_launch_stencil(T, ops, tile_op, L.n_tiles, L.smem, ctx->d_layers.as<float>(), s))
-                    FAIL(SVGR_E_UNSUPPORTED, "stencil needs more shared memory than available");
-            } else if (L.cls == 2) {
-                if (svgr_launch_conv2d(T, ops, tile_op, L.n_tiles, L.smem, ctx->d_layers.as<float>(), s))
-                    FAIL(SVGR_E_UNSUPPORTED, "convolution needs more shared memory than available");
-            } else
-                svgr_launch_compose(T, ops, tile_op, L.n_tiles, ctx->d_layers.as<float>(), canvas, s);
-            n_launches++;
-            n_kernels += L.n_tiles > 0 ? 2 : 0;
+        size_t up_ops = 0, up_srcs = 0, up_focal = 0;  // records already uploaded
+        int focal_blocks_done = 0;
+        bool externals_up = false;
+        mark(10);
+        for (int k = 0; k < pl.n_chunks(); k++) {
+            int op_begin = 0, launch_begin = 0;
+            auto t_c0 = std::chrono::steady_clock::now();
+            if (!pl.plan_chunk(k, &op_begin, &launch_begin))
+                FAIL(SVGR_E_INVALID, pl.err);
+            host_nodes_ms += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_c0).count();
+            if (stop_after == SVGR_STOP_COVERAGE)
+                continue;
+            if (ctx->ops.size() > ops_cap || ctx->srcs.size() > srcs_cap || ctx->focal_jobs.size() > focal_cap)
+                FAIL(SVGR_E_NOMEM, "plan tables larger than their bound");
+            // the layer arena may only grow while nothing is running (first render of a new size)
+            if ((size_t)ctx->layer_floats * 4 > ctx->d_layers.cap) {
+                CK(cudaStreamSynchronize(s));
+                CK(ctx->d_layers.ensure((size_t)ctx->layer_floats * 4 + ((size_t)ctx->layer_floats * 4) / 2, true));
+            }
+            long long max_tiles = 1;
+            for (size_t q = launch_begin; q < ctx->launches.size(); q++)
+                max_tiles = std::max<long long>(max_tiles, ctx->launches[q].n_tiles);
+            if ((size_t)max_tiles * 4 > ctx->d_tile_map.cap) {
+                CK(cudaStreamSynchronize(s));
+                CK(ctx->d_tile_map.ensure((size_t)max_tiles * 4 * 2));
+            }
+            // stage + upload the new records
+            const size_t n_ops = ctx->ops.size() - up_ops, n_srcs = ctx->srcs.size() - up_srcs;
+            const size_t n_focal = ctx->focal_jobs.size() - up_focal;
+            OpRec *po = (OpRec *)pin_ops + up_ops;
+            for (size_t q = 0; q < n_ops; q++)
+                po[q] = ctx->ops[up_ops + q].op;
+            if (n_ops)
+                CK(cudaMemcpyAsync(ctx->d_ops.as<OpRec>() + up_ops, po, n_ops * sizeof(OpRec), cudaMemcpyHostToDevice, s));
+            if (n_srcs) {
+                memcpy(pin_srcs + up_srcs * sizeof(SrcRec), ctx->srcs.data() + up_srcs, n_srcs * sizeof(SrcRec));
+                CK(cudaMemcpyAsync(ctx->d_srcs.as<SrcRec>() + up_srcs, pin_srcs + up_srcs * sizeof(SrcRec),
+                                   n_srcs * sizeof(SrcRec), cudaMemcpyHostToDevice, s));
+            }
+            if (n_focal) {
+                memcpy(pin_focal + up_focal * sizeof(FocalJob), ctx->focal_jobs.data() + up_focal, n_focal * sizeof(FocalJob));
+                CK(cudaMemcpyAsync(ctx->d_focal_jobs.as<FocalJob>() + up_focal, pin_focal + up_focal * sizeof(FocalJob),
+                                   n_focal * sizeof(FocalJob), cudaMemcpyHostToDevice, s));
+            }
+            RenderTables T;
+            T.srcs = ctx->d_srcs.as<SrcRec>(), T.paints = ctx->d_paints.as<PaintRec>(), T.stops = ctx->d_stops.as<StopRec>();
+            T.focal_flags = ctx->d_focal_flags.as<int>(), T.cov = ctx->d_cov.as<float>(), T.layers = ctx->d_layers.as<float>();
+            T.matrices = ctx->d_matrices.as<float>(), T.weights = ctx->d_weights.as<float>();
+            if (n_focal) {
+                // block numbers of this chunk's jobs start at focal_blocks_done: rebase through the launch offset
+                svgr_launch_focal_flags(T, ctx->d_focal_jobs.as<FocalJob>() + up_focal, (int)n_focal, focal_blocks_done,
+                                        ctx->n_focal_blocks - focal_blocks_done, ctx->d_focal_flags.as<int>(), s);
+                n_kernels += 1;
+                focal_blocks_done = ctx->n_focal_blocks;
+            }
+            if (!externals_up) {
+                externals_up = true;  // programs with external layers are planned as a single chunk
+                for (int i = 0; i < ctx->n_node; i++) {
+                    const svgr_node &n = ctx->h_nodes[i];
+                    if (n.tag != SVGR_N_EXTERNAL || ctx->vals[i].kind == VAL_EMPTY)
+                        continue;
+                    const Val &v = ctx->vals[i];
+                    const std::vector<float> &src = ctx->h_ext_data[n.a];
+                    if (v.kind == SRC_L4)
+                        CK(cudaMemcpyAsync(ctx->d_layers.as<float>() + v.off, src.data(), src.size() * 4,
+                                           cudaMemcpyHostToDevice, s));
+                    else
+                        CK(cudaMemcpy2DAsync(ctx->d_layers.as<float>() + v.off, (size_t)v.stride * 4, src.data(),
+                                             (size_t)v.cols * 4, (size_t)v.cols * 4, v.rows, cudaMemcpyHostToDevice, s));
+                }
+            }
+            for (size_t q = launch_begin; q < ctx->launches.size(); q++) {
+                const Launch &L = ctx->launches[q];
+                const OpRec *ops = ctx->d_ops.as<OpRec>() + L.op_begin;
+                const int *tile_op = ctx->d_tile_map.as<int>();
+                svgr_launch_expand_ops(ops, L.op_count, L.n_tiles, ctx->d_tile_map.as<int>(), s);
+                if (L.cls == 0)
+                    svgr_launch_compose(T, ops, tile_op, L.n_tiles, ctx->d_layers.as<float>(), nullptr, s);
+                else if (L.cls == 1) {
+                    if (svgr_launch_stencil(T, ops, tile_op, L.n_tiles, L.smem, ctx->d_layers.as<float>(), s))
+                        FAIL(SVGR_E_UNSUPPORTED, "stencil needs more shared memory than available");
+                } else if (L.cls == 2) {
+                    if (svgr_launch_conv2d(T, ops, tile_op, L.n_tiles, L.smem, ctx->d_layers.as<float>(), s))
+                        FAIL(SVGR_E_UNSUPPORTED, "convolution needs more shared memory than available");
+                } else
+                    svgr_launch_compose(T, ops, tile_op, L.n_tiles, ctx->d_layers.as<float>(), canvas, s);
+                n_launches++;
+                n_kernels += L.n_tiles > 0 ? 2 : 0;
+            }
+            up_ops = ctx->ops.size(), up_srcs = ctx->srcs.size(), up_focal = ctx->focal_jobs.size();
         }
-        mark(7);
-        mark(8);
-        if (has_canvas && out && !out_on_device)
-            CK(cudaMemcpyAsync(out, canvas, (size_t)ctx->canvas_bytes, cudaMemcpyDeviceToHost, s));
-        mark(9);
-        ctx->composed = true;
+        ctx->planned = true;
+        if (stop_after != SVGR_STOP_COVERAGE) {
+            mark(7);
+            mark(8);
+            if (canvas && out && !out_on_device)
+                CK(cudaMemcpyAsync(out, canvas, (size_t)ctx->canvas_bytes, cudaMemcpyDeviceToHost, s));
+            mark(9);
+            ctx->composed = true;
+        }
     }
+    auto t_h3 = std::chrono::steady_clock::now();
+    (void)t_h2, (void)t_h3;
     CK(cudaMemcpyAsync(ctx->pin_status.p, d_st, sizeof(StatusBlock), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
@@ -1277,11 +1394,11 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
         return rc;
     }
     if (timing) {
-        ms_plan = ev_ms(ctx->ev[3], ctx->ev[4]) + ev_ms(ctx->ev[6], ctx->ev[10]);
+        ms_plan = ev_ms(ctx->ev[3], ctx->ev[4]);
         ms_bin = ev_ms(ctx->ev[4], ctx->ev[5]);
         ms_cov = ev_ms(ctx->ev[5], ctx->ev[6]);
         if (stop_after != SVGR_STOP_COVERAGE) {
-            ms_cmp = ev_ms(ctx->ev[10], ctx->ev[7]);
+            ms_cmp = ev_ms(ctx->ev[6], ctx->ev[7]);  // includes whatever host planning the launches had to wait for
             ms_canvas = ev_ms(ctx->ev[7], ctx->ev[8]);
             ms_d2h = ev_ms(ctx->ev[8], ctx->ev[9]);
         }
@@ -1296,7 +1413,7 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
         stats->compose_bytes = ctx->compose_bytes, stats->canvas_pixels = ctx->canvas_pixels;
         stats->n_kernels = n_kernels;
         stats->host_plan_masks_ms = std::chrono::duration<float, std::milli>(t_h1 - t_h0).count();
-        stats->host_plan_nodes_ms = std::chrono::duration<float, std::milli>(t_h3 - t_h2).count();
+        stats->host_plan_nodes_ms = host_nodes_ms;
         stats->ms_plan = ms_plan, stats->ms_bin = ms_bin, stats->ms_coverage = ms_cov, stats->ms_compose = ms_cmp;
         stats->ms_canvas = ms_canvas, stats->ms_d2h = ms_d2h;
         stats->ms_total = ms_stroke + ms_flatten + ms_plan + ms_bin + ms_cov + ms_cmp + ms_canvas + ms_d2h;
@@ -1404,6 +1521,42 @@ int svgr_render(svgr_ctx *ctx, const svgr_program *prog, void *stream, int stop_
         }
         cudaEventDestroy(e0), cudaEventDestroy(e1);
     }
+    return rc;
+}
+
+// Host-only: runs the planner `reps` times on a program and given path boxes without touching CUDA
+// (profiling and CPU tests of the planner).  info = {ops, srcs, launches, levels, layer floats (low 31 bits)}.
+int svgr_debug_plan(const svgr_program *prog, const int32_t *boxes, int reps, float *ms_masks, float *ms_nodes,
+                    int64_t *info)
+{
+    svgr_ctx *ctx = new svgr_ctx();
+    int rc = load_program(ctx, prog, nullptr, true);
+    if (rc == SVGR_OK) {
+        ctx->h_boxes.assign((const PathBox *)boxes, (const PathBox *)boxes + ctx->n_path);
+        float best_m = 1e30f, best_n = 1e30f;
+        for (int r = 0; r < reps && rc == SVGR_OK; r++) {
+            Planner pl(ctx);
+            auto t0 = std::chrono::steady_clock::now();
+            bool ok = pl.plan_masks();
+            auto t1 = std::chrono::steady_clock::now();
+            ok = ok && pl.plan_nodes();
+            auto t2 = std::chrono::steady_clock::now();
+            if (!ok)
+                rc = SVGR_E_INVALID;
+            best_m = std::min(best_m, std::chrono::duration<float, std::milli>(t1 - t0).count());
+            best_n = std::min(best_n, std::chrono::duration<float, std::milli>(t2 - t1).count());
+        }
+        if (ms_masks)
+            *ms_masks = best_m;
+        if (ms_nodes)
+            *ms_nodes = best_n;
+        if (info) {
+            info[0] = (int64_t)ctx->ops.size(), info[1] = (int64_t)ctx->srcs.size();
+            info[2] = (int64_t)ctx->launches.size(), info[3] = ctx->n_levels, info[4] = ctx->layer_floats;
+            info[5] = ctx->compose_bytes;
+        }
+    }
+    delete ctx;
     return rc;
 }
 

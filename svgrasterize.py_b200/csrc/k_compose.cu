@@ -324,14 +324,16 @@ compose_kernel(RenderTables T, const OpRec *__restrict__ ops, const int *__restr
 
 // any(det < 0) over the mask bbox of a two-circle gradient fill (svgrasterize.py:1621-1622): the
 // reference masks invalid pixels only when at least one exists anywhere in the layer.
-__global__ void focal_flag_kernel(RenderTables T, const FocalJob *__restrict__ jobs, int n_jobs, int *__restrict__ flags)
+__global__ void focal_flag_kernel(RenderTables T, const FocalJob *__restrict__ jobs, int n_jobs, int block0,
+                                  int *__restrict__ flags)
 {
+    const int bid = (int)blockIdx.x + block0;  // block numbers are global over the render, launches cover ranges
     __shared__ int s_job;
     if (threadIdx.x == 0) {
         int lo = 0, hi = n_jobs - 1;
         while (lo < hi) {
             int mid = (lo + hi + 1) >> 1;
-            if (jobs[mid].block_base <= (int)blockIdx.x)
+            if (jobs[mid].block_base <= bid)
                 lo = mid;
             else
                 hi = mid - 1;
@@ -341,7 +343,7 @@ __global__ void focal_flag_kernel(RenderTables T, const FocalJob *__restrict__ j
     __syncthreads();
     const FocalJob &j = jobs[s_job];
     const PaintRec &p = T.paints[j.paint];
-    long long base = (long long)(blockIdx.x - j.block_base) * 1024;
+    long long base = (long long)(bid - j.block_base) * 1024;
     long long n = (long long)j.rows * j.cols;
     bool neg = false;
     for (int k = 0; k < 4; k++) {
@@ -390,9 +392,9 @@ void svgr_launch_expand_ops(const OpRec *ops, int n_ops, int n_tiles, int *tile_
         expand_ops_kernel<<<(n_tiles + 255) / 256, 256, 0, s>>>(ops, n_ops, n_tiles, tile_op);
 }
 
-void svgr_launch_focal_flags(const RenderTables &T, const void *jobs, int n_jobs, int n_blocks, int *flags,
+void svgr_launch_focal_flags(const RenderTables &T, const void *jobs, int n_jobs, int block0, int n_blocks, int *flags,
                              cudaStream_t s)
 {
     if (n_blocks > 0)
-        focal_flag_kernel<<<n_blocks, 256, 0, s>>>(T, (const FocalJob *)jobs, n_jobs, flags);
+        focal_flag_kernel<<<n_blocks, 256, 0, s>>>(T, (const FocalJob *)jobs, n_jobs, block0, flags);
 }
