@@ -66,7 +66,7 @@ def run_reference(opts):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = min(os.cpu_count() or 1, 64)
     n_icons = max(cores * 32, 256)
     vals = []
     for step in range(opts.warmup + opts.steps):
@@ -338,7 +338,7 @@ def run_gpu(opts):
         "host_encode_s_per_batch": t_encode,
     }
     if world == 1 and not opts.no_cpu:
-        cores = os.cpu_count() or 1
+        cores = min(os.cpu_count() or 1, 32)
         n = max(cores * 48, 512)
         v, dt = cpu_throughput(n, cores, seed0=0)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",

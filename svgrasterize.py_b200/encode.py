@@ -807,3 +807,24 @@ def encode_scene(scene, size, linear_rgb=False, engine=None) -> Program:
     enc = Encoder(engine)
     enc.add_scene(scene, size, linear_rgb)
     return enc.finish()
+
+
+def _encode_job(job):
+    scene, size, linear_rgb = job
+    return encode_scene(scene, size, linear_rgb)
+
+
+def encode_batch(jobs, processes: int = 0) -> Program:
+    """Encode many (scene, size, linear_rgb) jobs into one program.  Encoding is pure host work (a tree walk
+    per SVG, ~3 ms for a c5 icon), independent per scene and therefore the natural thing to spread over
+    worker processes when batches are large.  Scenes that use objectBoundingBox units need
+    the device at encode time and must be encoded in the rendering process (processes = 0)."""
+    jobs = list(jobs)
+    if processes and processes > 1 and len(jobs) > 1:
+        import multiprocessing as mp
+
+        with mp.get_context("spawn").Pool(processes) as pool:
+            progs = pool.map(_encode_job, jobs, chunksize=max(1, len(jobs) // (processes * 4)))
+    else:
+        progs = [_encode_job(j) for j in jobs]
+    return Program.concat(progs)

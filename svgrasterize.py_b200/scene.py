@@ -266,6 +266,9 @@ class Scene(tuple):
     def __new__(cls, tag, args):
         return tuple.__new__(cls, (tag, args))
 
+    def __reduce__(self):  # tuple subclasses with a custom __new__ need this to cross process boundaries
+        return (Scene, (self[0], self[1]))
+
     @classmethod
     def fill(cls, path, paint, fill_rule=None):
         return cls(RENDER_FILL, (path, paint, fill_rule))

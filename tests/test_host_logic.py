@@ -159,3 +159,37 @@ def test_band_encoding_covers_the_canvas():
         assert vp[0] == max(0, a - halo) and vp[0] + vp[2] == min(96, b + halo)
         total += prog.canvas_bytes
     assert total == 96 * 96 * 4
+
+
+def test_encode_batch_in_worker_processes_matches_serial():
+    from svgrasterize_b200 import encode, synth
+
+    jobs = [(synth.icon_scene(s), synth.icon_size(), False) for s in range(6)]
+    a = encode.encode_batch(jobs)
+    b = encode.encode_batch(jobs, processes=2)
+    for name in encode.Program.ARRAYS:
+        x, y = getattr(a, name), getattr(b, name)
+        assert x.dtype == y.dtype and x.shape == y.shape and x.tobytes() == y.tobytes(), name
+    assert a.canvas_bytes == b.canvas_bytes and a.canvases == b.canvases
+
+
+def test_planner_runs_without_a_gpu():
+    """svgr_debug_plan: the host planner on fabricated path boxes (full-canvas masks): ops, launches and the
+    fused canvas op are produced without touching CUDA."""
+    import ctypes as C
+
+    from svgrasterize_b200 import _lib, encode, synth
+
+    progs = [encode.encode_scene(synth.icon_scene(s), synth.icon_size()) for s in range(8)]
+    prog = encode.Program.concat(progs)
+    boxes = np.tile(np.array([[0, 0, 256, 256]], dtype=np.int32), (len(prog.paths), 1))
+    cprog, keep = prog.to_c()
+    a, b = C.c_float(), C.c_float()
+    info = (C.c_int64 * 8)()
+    rc = _lib.lib().svgr_debug_plan(C.byref(cprog), boxes.ctypes.data, 1, C.byref(a), C.byref(b), info)
+    assert rc == 0
+    n_ops, n_srcs, n_launch, n_levels = info[0], info[1], info[2], info[3]
+    assert n_ops == 3 * len(progs)      # two inner groups + the root folded straight into RGBA8, per icon
+    assert n_launch == 2 and n_levels == 2
+    assert n_srcs >= 12 * len(progs)    # every mask is read by exactly one op (+ stencil modifiers)
+    assert info[5] > 0
