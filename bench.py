@@ -302,16 +302,26 @@ def run_gpu(opts):
             traffic = json.load(f)
     except Exception:
         pass
+    def traffic_of(name):
+        """Measured DRAM bytes per step of this kernel (ncu capture committed under profiles/), scaled to the
+        batch size of this run when it differs from the captured one."""
+        rec = traffic.get(name)
+        if not isinstance(rec, dict) or not traffic.get("icons"):
+            return None
+        return rec["bytes_per_step"] * opts.icons / traffic["icons"]
+
     kernels = {
         "compose_kernel": {"bound": "hbm", "achieved": cmp_gbs, "peak": peak, "unit": "GB/s", "frac": cmp_gbs / peak,
-                           "traffic": traffic.get("compose_kernel"), "ms_per_step": ms_cmp,
+                           "traffic": traffic_of("compose_kernel"), "ms_per_step": ms_cmp,
                            "launches_per_step": st["n_launches"] - 1, "algorithmic_bytes_per_step": st["compose_bytes"]},
         "coverage_kernel": {"bound": "hbm", "achieved": cov_gbs, "peak": peak, "unit": "GB/s", "frac": cov_gbs / peak,
-                            "traffic": traffic.get("coverage_kernel"), "ms_per_step": ms_cov, "launches_per_step": 1,
+                            "traffic": traffic_of("coverage_kernel"), "ms_per_step": ms_cov, "launches_per_step": 1,
                             "algorithmic_bytes_per_step": st["coverage_bytes"]},
     }
     dominant = "compose_kernel" if ms_cmp >= ms_cov else "coverage_kernel"
-    roofline = dict(kernels[dominant], kernel=dominant, peak_source=peak_src)
+    roofline = dict(kernels[dominant], kernel=dominant, peak_source=peak_src,
+                    note="achieved = algorithmic bytes per step / CUDA-event time of the kernel's launches in a step "
+                         "(includes waits for the host planner between chunks); traffic = measured DRAM bytes per step")
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": opts.steps, "warmup": opts.warmup,

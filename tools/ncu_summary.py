@@ -76,8 +76,41 @@ def full(src, dst, traffic=None):
         json.dump(js, open(traffic, "w"), indent=1)
 
 
+def traffic(src, dst, icons, skip):
+    """src: csv of `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum` over
+    tools/one_step.py; the first `skip` launches (the warm-up render) are dropped, the rest is one step."""
+    rows = [r for r in csv.reader(open(src)) if len(r) > 5]
+    start = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
+    hdr = rows[start]
+    ki, mi, vi, ui, ii = (hdr.index(n) for n in ("Kernel Name", "Metric Name", "Metric Value", "Metric Unit", "ID"))
+    per = collections.OrderedDict()
+    for r in rows[start + 1:]:
+        if int(r[ii]) < skip:
+            continue
+        name = r[ki].split("(")[0]
+        d = per.setdefault(name, {"launches": set(), "bytes": 0.0, "us": 0.0})
+        d["launches"].add(r[ii])
+        v = float(r[vi].replace(",", ""))
+        if r[mi].startswith("dram__bytes"):
+            d["bytes"] += to_bytes(r[vi], r[ui])
+        else:
+            d["us"] += v / 1e3 if r[ui] == "ns" else (v * 1e3 if r[ui] == "ms" else v)
+    out = {"_note": f"per-step DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum summed over the launches of "
+                    f"one resident step) of the bench workload with {icons} icons; ncu times are cold-cache / serialised",
+           "icons": int(icons)}
+    for k, d in per.items():
+        out[k] = {"bytes_per_step": d["bytes"], "launches_per_step": len(d["launches"]), "ncu_us_per_step": d["us"]}
+    json.dump(out, open(dst, "w"), indent=1)
+    tot = sum(d["us"] for d in per.values())
+    for k, d in sorted(per.items(), key=lambda kv: -kv[1]["us"]):
+        print(f"{k[:40]:40s} n={len(d['launches']):3d} {d['us']:10.1f} us {d['us'] / tot * 100:5.1f}%  "
+              f"{d['bytes'] / 1e6:10.1f} MB")
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3])
+    elif sys.argv[1] == "traffic":
+        traffic(sys.argv[2], sys.argv[3], sys.argv[4], int(sys.argv[5]))
     else:
         full(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else None)
