@@ -293,7 +293,7 @@ def run_gpu(opts):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     ms_cov = acc.get("ms_coverage", 0.0) / opts.steps
-    ms_cmp = acc.get("ms_compose", 0.0) / opts.steps
+    ms_cmp = acc.get("ms_compose_busy", 0.0) / opts.steps  # device time of the compose launches themselves
     cov_gbs = st["coverage_bytes"] / (ms_cov * 1e-3) / 1e9 if ms_cov > 0 else 0.0
     cmp_gbs = st["compose_bytes"] / (ms_cmp * 1e-3) / 1e9 if ms_cmp > 0 else 0.0
     traffic = {}
@@ -321,7 +321,8 @@ def run_gpu(opts):
     dominant = "compose_kernel" if ms_cmp >= ms_cov else "coverage_kernel"
     roofline = dict(kernels[dominant], kernel=dominant, peak_source=peak_src,
                     note="achieved = algorithmic bytes per step / CUDA-event time of the kernel's launches in a step "
-                         "(includes waits for the host planner between chunks); traffic = measured DRAM bytes per step")
+                         "(first to last launch of every plan chunk, on the launch stream); traffic = measured DRAM "
+                         "bytes per step (ncu, profiles/traffic.json)")
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": opts.steps, "warmup": opts.warmup,

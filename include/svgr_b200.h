@@ -166,6 +166,9 @@ typedef struct svgr_stats {
     int32_t retries;
     int32_t pad;
     float host_plan_masks_ms, host_plan_nodes_ms; /* wall time of the two host planning phases */
+    float ms_compose_busy; /* sum over plan chunks of first-launch -> last-launch device time: ms_compose minus
+                              the waits for the host planner */
+    float pad2;
 } svgr_stats;
 
 typedef struct svgr_ctx svgr_ctx;

@@ -200,6 +200,7 @@ struct svgr_ctx {
     bool planned = false, covered = false, composed = false;
 
     cudaEvent_t ev[16] = {nullptr};
+    cudaEvent_t ev_chunk[16][2] = {{nullptr}};
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -795,7 +796,10 @@ struct Planner {
         c->vals.resize(c->n_node);  // every entry is assigned by plan_range before anyone reads it
         // chunks of at least 4096 nodes, at most 8 of them, cut where no reference crosses
         chunk_bounds.assign(1, 0);
-        const int want_chunks = std::min(8, c->n_node / 4096);
+        int max_chunks = 8;
+        if (const char *e = getenv("SVGR_CHUNKS"))  // 1: plan everything before the first compose launch (clean kernel timings)
+            max_chunks = std::max(1, atoi(e));
+        const int want_chunks = std::min(max_chunks, c->n_node / 4096);
         if (want_chunks >= 2 && !cuts.empty()) {
             std::vector<int> min_ref(c->n_node + 1, c->n_node);  // smallest index referenced at or after i
             for (int i = c->n_node - 1; i >= 0; i--) {
@@ -1250,7 +1254,7 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
     // while the host plans chunk k + 1 (and bins / rasterises coverage while it plans chunk 0).
     auto t_h2 = std::chrono::steady_clock::now();
     float host_nodes_ms = 0.f;
-    int n_launches = 0;
+    int n_launches = 0, timed_chunks = 0;
     if (!pl.begin_nodes())
         FAIL(SVGR_E_INVALID, pl.err);
     {
@@ -1347,6 +1351,8 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
                                              (size_t)v.cols * 4, (size_t)v.cols * 4, v.rows, cudaMemcpyHostToDevice, s));
                 }
             }
+            if (timing && k < 16)
+                cudaEventRecord(ctx->ev_chunk[k][0], s);
             for (size_t q = launch_begin; q < ctx->launches.size(); q++) {
                 const Launch &L = ctx->launches[q];
                 const OpRec *ops = ctx->d_ops.as<OpRec>() + L.op_begin;
@@ -1365,6 +1371,9 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
                 n_launches++;
                 n_kernels += L.n_tiles > 0 ? 2 : 0;
             }
+            if (timing && k < 16)
+                cudaEventRecord(ctx->ev_chunk[k][1], s);
+            timed_chunks = std::min(k + 1, 16);
             up_ops = ctx->ops.size(), up_srcs = ctx->srcs.size(), up_focal = ctx->focal_jobs.size();
         }
         ctx->planned = true;
@@ -1414,6 +1423,10 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
         stats->n_kernels = n_kernels;
         stats->host_plan_masks_ms = std::chrono::duration<float, std::milli>(t_h1 - t_h0).count();
         stats->host_plan_nodes_ms = host_nodes_ms;
+        stats->ms_compose_busy = 0.f;
+        if (timing && stop_after != SVGR_STOP_COVERAGE)
+            for (int k = 0; k < timed_chunks; k++)
+                stats->ms_compose_busy += ev_ms(ctx->ev_chunk[k][0], ctx->ev_chunk[k][1]);
         stats->ms_plan = ms_plan, stats->ms_bin = ms_bin, stats->ms_coverage = ms_cov, stats->ms_compose = ms_cmp;
         stats->ms_canvas = ms_canvas, stats->ms_d2h = ms_d2h;
         stats->ms_total = ms_stroke + ms_flatten + ms_plan + ms_bin + ms_cov + ms_cmp + ms_canvas + ms_d2h;
@@ -1466,6 +1479,8 @@ int svgr_create(int device, svgr_ctx **out)
     }
     for (auto &e : ctx->ev)
         cudaEventCreate(&e);
+    for (auto &e : ctx->ev_chunk)
+        cudaEventCreate(&e[0]), cudaEventCreate(&e[1]);
     *out = ctx;
     return SVGR_OK;
 }
@@ -1490,6 +1505,12 @@ void svgr_destroy(svgr_ctx *ctx)
     for (auto &e : ctx->ev)
         if (e)
             cudaEventDestroy(e);
+    for (auto &e : ctx->ev_chunk) {
+        if (e[0])
+            cudaEventDestroy(e[0]);
+        if (e[1])
+            cudaEventDestroy(e[1]);
+    }
     if (ctx->own_stream)
         cudaStreamDestroy(ctx->own_stream);
     delete ctx;

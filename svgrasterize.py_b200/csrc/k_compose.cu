@@ -211,11 +211,12 @@ compose_kernel(RenderTables T, const OpRec *__restrict__ ops, const int *__restr
                                 v[k] = f4(col.x * a[k], col.y * a[k], col.z * a[k], col.w * a[k]);
                         } else {
                             const float4 *pat = reinterpret_cast<const float4 *>(T.layers + s.off2);
+                            const StopRec *st = T.stops + pr.stop_off;
 #pragma unroll
                             for (int k = 0; k < CMP_PX; k++) {
                                 v[k] = f4(0.f, 0.f, 0.f, 0.f);
                                 if (a[k] != 0.f) {
-                                    float4 q = paint_eval(T, pr, x0 + 8.0 * k, y0, pat, s.stride2);
+                                    float4 q = paint_eval(T, pr, st, x0 + 8.0 * k, y0, pat, s.stride2);
                                     v[k] = f4(q.x * a[k], q.y * a[k], q.z * a[k], q.w * a[k]);
                                 }
                             }
@@ -303,7 +304,10 @@ compose_kernel(RenderTables T, const OpRec *__restrict__ ops, const int *__restr
             // (canvas_merge_at :326), converted to straight-alpha sRGB (Layer.write_png :212) and quantised
             // with round-half-even (np.round, :263).  op.aux carries the render's linear_rgb flag.
             a = f4(clip01(a.x), clip01(a.y), clip01(a.z), clip01(a.w));
-            a = convert_px(a, SVGR_CONV(1, op.aux != 0, 0, 0));
+            if (op.aux != 0)
+                a = convert_px(a, SVGR_CONV(1, 1, 0, 0));
+            else
+                a = unpremultiply(a);  // sRGB render mode: Layer.convert is the alpha division only
             // x * 255 + 1.5 * 2^23 leaves round-half-even(x * 255) in the low mantissa bits
             uchar4 q;
             q.x = (unsigned char)(__float_as_uint(a.x * 255.0f + 12582912.0f) & 0xffu);

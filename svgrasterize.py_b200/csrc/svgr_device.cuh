@@ -97,11 +97,10 @@ __device__ __forceinline__ float4 grad_color(double v, const StopRec *__restrict
         double o0 = st[k].offset, o1 = st[k + 1].offset;
         if (v > o0 && v <= o1) {
             float ratio = (float)((v - o0) * st[k].inv_span);
-            float ir = 1.0f - ratio;
-            o.x += ir * st[k].color[0] + ratio * st[k + 1].color[0];
-            o.y += ir * st[k].color[1] + ratio * st[k + 1].color[1];
-            o.z += ir * st[k].color[2] + ratio * st[k + 1].color[2];
-            o.w += ir * st[k].color[3] + ratio * st[k + 1].color[3];
+            o.x += fmaf(ratio, st[k + 1].color[0] - st[k].color[0], st[k].color[0]);
+            o.y += fmaf(ratio, st[k + 1].color[1] - st[k].color[1], st[k].color[1]);
+            o.z += fmaf(ratio, st[k + 1].color[2] - st[k].color[2], st[k].color[2]);
+            o.w += fmaf(ratio, st[k + 1].color[3] - st[k].color[3], st[k].color[3]);
         }
     }
     return o;  // NaN offsets match no interval: transparent black
@@ -127,8 +126,9 @@ __device__ __forceinline__ double focal_det(const PaintRec &p, double x, double 
 
 // Paint colour at the pixel centre (x, y): premultiplied RGBA.  `p` may live in shared memory.
 // pat / pat_stride: the pattern tile image (PAINT_PATTERN only).
-__device__ __forceinline__ float4 paint_eval(const RenderTables &T, const PaintRec &p, double x, double y,
-                                             const float4 *pat, int pat_stride)
+// `stops`: the paint's StopRec array (global memory, or a shared-memory copy staged by the caller).
+__device__ __forceinline__ float4 paint_eval(const RenderTables &T, const PaintRec &p, const StopRec *stops, double x,
+                                             double y, const float4 *pat, int pat_stride)
 {
     if (p.kind == PAINT_SOLID)
         return f4(p.color[0], p.color[1], p.color[2], p.color[3]);
@@ -166,7 +166,7 @@ __device__ __forceinline__ float4 paint_eval(const RenderTables &T, const PaintR
         if (any_neg && p.g[6] != 0.0 && !(t > p.g[5]))
             return f4(0.f, 0.f, 0.f, 0.f);
     }
-    return grad_color(grad_spread(t, p.spread), T.stops + p.stop_off, p.stop_cnt);
+    return grad_color(grad_spread(t, p.spread), stops, p.stop_cnt);
 }
 
 // ---- source access, split so that a thread can issue the loads of several pixels before using them
@@ -194,7 +194,8 @@ __device__ __forceinline__ float4 src_finish(const RenderTables &T, const SrcRec
         if (v.w == 0.f)
             return f4(0.f, 0.f, 0.f, 0.f);
         float a = v.w;
-        float4 p = paint_eval(T, *paint, x, y, reinterpret_cast<const float4 *>(T.layers + s.off2), s.stride2);
+        float4 p = paint_eval(T, *paint, T.stops + paint->stop_off, x, y,
+                              reinterpret_cast<const float4 *>(T.layers + s.off2), s.stride2);
         v = f4(p.x * a, p.y * a, p.z * a, p.w * a);
     }
     if (s.mul != 1.0f)

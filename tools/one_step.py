@@ -19,4 +19,5 @@ st = eng.render(prog, out=out)
 print("kernels per render:", st["n_kernels"], flush=True)
 for _ in range(steps):
     st = eng.render_resident(out, timing=True)
-print({k: round(v, 3) for k, v in st.items() if k.startswith("ms_")}, st["compose_bytes"], st["coverage_bytes"])
+print({k: round(v, 3) for k, v in st.items() if k.startswith("ms_") or k.startswith("host_")}, st["compose_bytes"],
+      st["coverage_bytes"])
