@@ -125,8 +125,7 @@ struct Val {
 struct PlannedOp {
     OpRec op;
     int level;
-    int cls;  // 0 compose, 1 stencil, 2 conv2d, 3 canvas, 4 folded inside its only consumer (no launch of its own)
-    int id;   // position before the (level, class) ordering
+    int cls;  // 0 compose, 1 stencil, 2 conv2d, 3 canvas
 };
 
 struct Launch {
@@ -192,7 +191,7 @@ struct svgr_ctx {
     std::vector<Launch> launches;
     int n_focal_blocks = 0;
     long long n_bands = 0, n_cov_tiles = 0, cov_floats = 0, layer_floats = 0;
-    long long mask_pixels = 0, layer_pixels = 0, compose_bytes = 0, canvas_pixels = 0, layer_pixels_virtual = 0;
+    long long mask_pixels = 0, layer_pixels = 0, compose_bytes = 0, canvas_pixels = 0;
     int n_levels = 0;
     DevBuf d_masks, d_band_cnt, d_band_off, d_band_cur, d_bin_edges, d_cov, d_layers, d_ops, d_srcs, d_focal_jobs,
         d_focal_flags, d_canvas, d_q, d_tile_map, d_tile_mask;
@@ -220,8 +219,6 @@ struct Planner {
     const std::vector<int> *uses_p = nullptr;  // how many nodes read each node (shared, read-only while planning)
     std::vector<PlannedOp> sorted_ops;
     std::vector<Val> scratch_vals;
-    std::vector<int> scratch_pos, scratch_refs;
-    std::vector<std::pair<long long, int>> scratch_prod;
     // outputs: the context's tables, or thread-local ones when the node range is planned by several threads
     std::vector<PlannedOp> *ops_p;
     std::vector<SrcRec> *srcs_p;
@@ -776,7 +773,7 @@ struct Planner {
         svgr_ctx *c = ctx;
         c->ops.clear(), c->srcs.clear(), c->focal_jobs.clear(), c->launches.clear();
         c->n_focal_blocks = 0, c->layer_pixels = 0, c->n_levels = 0;
-        c->compose_bytes = 0, c->canvas_pixels = 0, c->layer_pixels_virtual = 0;
+        c->compose_bytes = 0, c->canvas_pixels = 0;
         n_focal_blocks = 0, layer_pixels = 0, layer_top = 0;
         std::vector<int> &uses = uses_own;
         uses.assign(c->n_node, 0);
@@ -847,102 +844,6 @@ struct Planner {
         return true;
     }
 
-    // bytes an op reads from one of its sources (clipped to the op's rectangle for compose-class ops)
-    static long long src_bytes(const SrcRec &sr, const OpRec &o, bool clip)
-    {
-        if (sr.kind & SRC_SLOT_FLAG)
-            return 0;  // stays in shared memory
-        long long rr = sr.rows, cc = sr.cols;
-        if (clip) {
-            rr = std::min(o.r0 + o.rows, sr.r0 + sr.rows) - std::max(o.r0, sr.r0);
-            cc = std::min(o.c0 + o.cols, sr.c0 + sr.cols) - std::max(o.c0, sr.c0);
-        }
-        if (rr <= 0 || cc <= 0)
-            return 0;
-        return rr * cc * ((sr.kind == SRC_L4 || sr.kind == SRC_MOD_L4A || sr.kind == SRC_MOD_LUMA) ? 16 : 4);
-    }
-
-    // An RGBA / one-channel layer that exactly one compose-class op reads (an inner group under a clip, the
-    // content of a luminance mask) does not need to exist in HBM: its fold is run by the consumer's CTAs over
-    // the consumer's own pixels and handed over in a shared-memory slot (compose_kernel, "sub-ops").  At most
-    // SVGR_MAX_SLOTS per consumer, one level deep; everything else keeps its layer.
-    void inline_single_use_ops(size_t op_begin, int node_a, int node_b)
-    {
-        svgr_ctx *c = ctx;
-        auto is_layer_ref = [](int kind) {
-            return kind == SRC_L4 || kind == SRC_L1 || kind == SRC_MOD_L1 || kind == SRC_MOD_L4A || kind == SRC_MOD_LUMA;
-        };
-        // producers of layers in this chunk, by arena offset
-        std::vector<std::pair<long long, int>> &prod = scratch_prod;
-        prod.clear();
-        for (size_t q = op_begin; q < c->ops.size(); q++) {
-            const PlannedOp &po = c->ops[q];
-            if (po.cls == 0 && po.op.kind == OP_COMPOSE)
-                prod.emplace_back(po.op.out_off, (int)q);
-        }
-        if (prod.empty())
-            return;
-        std::sort(prod.begin(), prod.end());
-        auto find = [&](long long off) -> int {
-            auto it = std::lower_bound(prod.begin(), prod.end(), std::make_pair(off, -1));
-            return (it != prod.end() && it->first == off) ? (int)(it - prod.begin()) : -1;
-        };
-        std::vector<int> &refs = scratch_refs;
-        refs.assign(prod.size(), 0);
-        const size_t src_begin = c->ops[op_begin].op.src_off;
-        size_t src_lo = c->srcs.size();
-        for (size_t q = op_begin; q < c->ops.size(); q++)
-            src_lo = std::min(src_lo, (size_t)c->ops[q].op.src_off);
-        (void)src_begin;
-        for (size_t q = src_lo; q < c->srcs.size(); q++) {
-            const SrcRec &sr = c->srcs[q];
-            int p = -1;
-            if (is_layer_ref(sr.kind))
-                p = find(sr.off);
-            if (p >= 0)
-                refs[p]++;
-            if (sr.kind == SRC_COVPAINT && sr.stride2 != 0 && (p = find(sr.off2)) >= 0)
-                refs[p] += 2;  // pattern tile image: gathered at arbitrary pixels, must be a real layer
-        }
-        // layers the caller can read back stay real
-        for (int i = node_a; i < node_b; i++) {
-            const svgr_node &n = c->h_nodes[i];
-            const Val &v = c->vals[i];
-            if (((n.flags & 2) || i == c->n_node - 1) && (v.kind == SRC_L4 || v.kind == SRC_L1 || v.kind == VAL_LUMA)) {
-                int p = find(v.off);
-                if (p >= 0)
-                    refs[p] += 2;
-            }
-        }
-        for (size_t q = op_begin; q < c->ops.size(); q++) {
-            PlannedOp &y = c->ops[q];
-            if ((y.cls != 0 && y.cls != 3) || (y.op.kind != OP_COMPOSE && y.op.kind != OP_CANVAS))
-                continue;
-            for (int e = 0; e < y.op.src_cnt && y.op.pre_cnt < SVGR_MAX_SLOTS; e++) {
-                SrcRec &sr = c->srcs[y.op.src_off + e];
-                if (!is_layer_ref(sr.kind))
-                    continue;
-                int p = find(sr.off);
-                if (p < 0 || refs[p] != 1)
-                    continue;
-                PlannedOp &x = c->ops[prod[p].second];
-                if (x.cls != 0 || x.op.pre_cnt != 0 || prod[p].second == (int)q)
-                    continue;
-                // the slot holds the consumer's tile: the view of x must be addressed from x's own origin
-                if (sr.br0 != x.op.r0 || sr.bc0 != x.op.c0)
-                    continue;
-                x.cls = 4;
-                c->layer_pixels_virtual += (long long)x.op.rows * x.op.cols;
-                sr.kind |= SRC_SLOT_FLAG;
-                sr.off = y.op.pre_cnt;
-                int *box = y.op.pre_box[y.op.pre_cnt];
-                box[0] = sr.r0, box[1] = sr.c0, box[2] = sr.rows, box[3] = sr.cols;
-                y.op.pre[y.op.pre_cnt++] = prod[p].second;
-                y.level = std::max(y.level, x.level);
-            }
-        }
-    }
-
     // Plans chunk k.  On return ctx->ops[op_begin ..] are the chunk's ops, grouped by (level, class), and
     // ctx->launches[launch_begin ..] its launches (op_begin absolute).
     bool plan_chunk(int k, int *op_begin_out, int *launch_begin_out)
@@ -958,24 +859,20 @@ struct Planner {
         const size_t n_new = c->ops.size() - op_begin;
         if (n_new == 0)
             return true;
-        inline_single_use_ops(op_begin, chunk_bounds[k], chunk_bounds[k + 1]);
-        for (size_t q = op_begin; q < c->ops.size(); q++)
-            c->ops[q].id = (int)q;
         // ---- order the chunk's ops by (level, class)
         {
             int max_level = 0;
             for (size_t q = op_begin; q < c->ops.size(); q++)
                 max_level = std::max(max_level, c->ops[q].level);
             if (max_level < (1 << 20)) {  // counting sort: a chunk has a handful of levels and many ops
-                const size_t NC = 5;  // classes per level
-                std::vector<int> start((size_t)(max_level + 1) * NC + 1, 0);
+                std::vector<int> start((size_t)(max_level + 1) * 4 + 1, 0);
                 for (size_t q = op_begin; q < c->ops.size(); q++)
-                    start[(size_t)c->ops[q].level * NC + c->ops[q].cls + 1]++;
+                    start[(size_t)c->ops[q].level * 4 + c->ops[q].cls + 1]++;
                 for (size_t q = 1; q < start.size(); q++)
                     start[q] += start[q - 1];
                 sorted_ops.resize(n_new);
                 for (size_t q = op_begin; q < c->ops.size(); q++)
-                    sorted_ops[start[(size_t)c->ops[q].level * NC + c->ops[q].cls]++] = c->ops[q];
+                    sorted_ops[start[(size_t)c->ops[q].level * 4 + c->ops[q].cls]++] = c->ops[q];
                 std::copy(sorted_ops.begin(), sorted_ops.end(), c->ops.begin() + op_begin);
             } else {
                 std::stable_sort(c->ops.begin() + op_begin, c->ops.end(), [](const PlannedOp &a, const PlannedOp &b) {
@@ -983,29 +880,10 @@ struct Planner {
                 });
             }
         }
-        {
-            // pre-op references were recorded as positions before the ordering
-            std::vector<int> &pos = scratch_pos;
-            pos.assign(n_new, -1);
-            for (size_t q = op_begin; q < c->ops.size(); q++)
-                pos[c->ops[q].id - op_begin] = (int)q;
-            for (size_t q = op_begin; q < c->ops.size(); q++) {
-                OpRec &o = c->ops[q].op;
-                for (int t = 0; t < o.pre_cnt; t++)
-                    o.pre[t] = pos[o.pre[t] - op_begin];
-            }
-        }
         int nl = 0, last_level = -1;
         size_t i = op_begin;
         while (i < c->ops.size()) {
             size_t j = i;
-            if (c->ops[i].cls == 4) {  // folded inside its consumer: only its source reads count
-                const OpRec &o = c->ops[i].op;
-                for (int q = 0; q < o.src_cnt; q++)
-                    c->compose_bytes += src_bytes(c->srcs[o.src_off + q], o, true);
-                i++;
-                continue;
-            }
             Launch L;
             L.cls = c->ops[i].cls, L.op_begin = (int)i, L.n_tiles = 0, L.smem = 0;
             long long tiles = 0;
@@ -1035,8 +913,19 @@ struct Planner {
                 } else {
                     c->compose_bytes += (long long)o.rows * o.cols * o.out_ch * 4;
                 }
-                for (int q = 0; q < o.src_cnt; q++)
-                    c->compose_bytes += src_bytes(c->srcs[o.src_off + q], o, po.cls == 0 || po.cls == 3);
+                for (int q = 0; q < o.src_cnt; q++) {
+                    const SrcRec &sr = c->srcs[o.src_off + q];
+                    long long rr, cc;
+                    if (po.cls == 0 || po.cls == 3) {
+                        rr = std::min(o.r0 + o.rows, sr.r0 + sr.rows) - std::max(o.r0, sr.r0);
+                        cc = std::min(o.c0 + o.cols, sr.c0 + sr.cols) - std::max(o.c0, sr.c0);
+                    } else {
+                        rr = sr.rows, cc = sr.cols;
+                    }
+                    if (rr > 0 && cc > 0)
+                        c->compose_bytes +=
+                            rr * cc * ((sr.kind == SRC_L4 || sr.kind == SRC_MOD_L4A || sr.kind == SRC_MOD_LUMA) ? 16 : 4);
+                }
                 j++;
             }
             if (tiles > 0x7fffff00ll) {
@@ -1470,7 +1359,7 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
                 const int *tile_op = ctx->d_tile_map.as<int>();
                 svgr_launch_expand_ops(ops, L.op_count, L.n_tiles, ctx->d_tile_map.as<int>(), s);
                 if (L.cls == 0)
-                    svgr_launch_compose(T, ctx->d_ops.as<OpRec>(), ops, tile_op, L.n_tiles, ctx->d_layers.as<float>(), nullptr, s);
+                    svgr_launch_compose(T, ops, tile_op, L.n_tiles, ctx->d_layers.as<float>(), nullptr, s);
                 else if (L.cls == 1) {
                     if (svgr_launch_stencil(T, ops, tile_op, L.n_tiles, L.smem, ctx->d_layers.as<float>(), s))
                         FAIL(SVGR_E_UNSUPPORTED, "stencil needs more shared memory than available");
@@ -1478,7 +1367,7 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
                     if (svgr_launch_conv2d(T, ops, tile_op, L.n_tiles, L.smem, ctx->d_layers.as<float>(), s))
                         FAIL(SVGR_E_UNSUPPORTED, "convolution needs more shared memory than available");
                 } else
-                    svgr_launch_compose(T, ctx->d_ops.as<OpRec>(), ops, tile_op, L.n_tiles, ctx->d_layers.as<float>(), canvas, s);
+                    svgr_launch_compose(T, ops, tile_op, L.n_tiles, ctx->d_layers.as<float>(), canvas, s);
                 n_launches++;
                 n_kernels += L.n_tiles > 0 ? 2 : 0;
             }

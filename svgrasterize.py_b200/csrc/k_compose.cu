@@ -69,30 +69,20 @@ __device__ __forceinline__ void copy16(T *dst, const T *src, int part)
 // One kernel for layer ops (float output) and canvas ops (RGBA8 output).  Per CTA:
 //   1. the op of this tile comes from the tile -> op table; its record is staged in shared memory
 //      (one 8-byte piece per thread) so that nobody chases it through global memory again;
-//   2. sub-ops: an op may name up to SVGR_MAX_SLOTS "pre" ops -- inner groups (a clipped group, the
-//      content of a luminance mask) that only this op reads.  They are folded by the same CTA first, over
-//      the same pixels, and their result stays in a shared-memory slot instead of going through HBM: every
-//      thread later reads back exactly the pixels it wrote, so no barrier is needed for the slots;
-//   3. per sub-op, rounds: warp 0 culls the next sources against the tile rectangle (order preserved) and
-//      copies up to CMP_CAP surviving SrcRecs into shared memory; all threads then copy the PaintRecs those
+//   2. rounds: warp 0 culls the next sources against the tile rectangle (order preserved) and copies
+//      up to CMP_CAP surviving SrcRecs into shared memory; all threads then copy the PaintRecs those
 //      sources need; every thread folds the staged sources into its 4 pixels, issuing the 4 loads of a
 //      source back to back before using any of them.
 #ifndef SVGR_CMP_OCC
 #define SVGR_CMP_OCC 4
 #endif
-#define SRC_BASE(k) ((k) & 15)
-#define SRC_IS_MOD(k) (SRC_BASE(k) >= SRC_MOD_COV)
-#define SRC_IS_SLOT(k) (((k) & SRC_SLOT_FLAG) != 0)
-
 __global__ void __launch_bounds__(256, SVGR_CMP_OCC)
-compose_kernel(RenderTables T, const OpRec *__restrict__ all_ops, const OpRec *__restrict__ ops,
-               const int *__restrict__ tile_op, float *__restrict__ layers_out, uint8_t *__restrict__ canvas_out)
+compose_kernel(RenderTables T, const OpRec *__restrict__ ops, const int *__restrict__ tile_op,
+               float *__restrict__ layers_out, uint8_t *__restrict__ canvas_out)
 {
-    __shared__ __align__(16) OpRec s_top;  // the op that owns this tile
-    __shared__ __align__(16) OpRec s_sub;  // the pre-op being folded
+    __shared__ __align__(16) OpRec s_op;
     __shared__ __align__(16) SrcRec s_src[CMP_CAP + 1];
     __shared__ __align__(16) PaintRec s_paint[CMP_CAP + 1];
-    __shared__ __align__(16) float4 s_slot[SVGR_MAX_SLOTS][CMP_PX][256];
     __shared__ int s_idx[CMP_CAP + 1];
     __shared__ int s_n, s_next;
 
@@ -100,282 +90,238 @@ compose_kernel(RenderTables T, const OpRec *__restrict__ all_ops, const OpRec *_
     static_assert(sizeof(OpRec) % 8 == 0, "OpRec must be a multiple of 8 bytes");
     if (tid < (int)(sizeof(OpRec) / 8)) {
         const int opi = __ldg(tile_op + blockIdx.x);  // tile -> op table written by expand_ops_kernel
-        reinterpret_cast<uint2 *>(&s_top)[tid] = __ldg(reinterpret_cast<const uint2 *>(ops + opi) + tid);
+        reinterpret_cast<uint2 *>(&s_op)[tid] = __ldg(reinterpret_cast<const uint2 *>(ops + opi) + tid);
     }
+    if (tid == 0)
+        s_next = 0;
     __syncthreads();
-    const OpRec &top = s_top;
-    const int local = blockIdx.x - top.tile_base;
-    const int tr = local / top.ntile_c, tc = local - tr * top.ntile_c;
+    const OpRec &op = s_op;
+    const int local = blockIdx.x - op.tile_base;
+    const int tr = local / op.ntile_c, tc = local - tr * op.ntile_c;
     const int ty = tid >> 5, tx = tid & 31;
     const int lr0 = tr * CMP_TR + ty, lc = tc * CMP_TC + tx;  // output-local; pixel k is 8 k rows further down
-    const int r0 = top.r0 + lr0, c = top.c0 + lc;
-    const int tile_r0 = top.r0 + tr * CMP_TR, tile_c0 = top.c0 + tc * CMP_TC;
-    const int tile_r1 = min(tile_r0 + CMP_TR, top.r0 + top.rows), tile_c1 = min(tile_c0 + CMP_TC, top.c0 + top.cols);
-    const bool col_live = lc < top.cols;
+    const int r0 = op.r0 + lr0, c = op.c0 + lc;
+    const int tile_r0 = op.r0 + tr * CMP_TR, tile_c0 = op.c0 + tc * CMP_TC;
+    const int tile_r1 = min(tile_r0 + CMP_TR, op.r0 + op.rows), tile_c1 = min(tile_c0 + CMP_TC, op.c0 + op.cols);
+    const bool col_live = lc < op.cols;
+    const SrcRec *srcs = T.srcs + op.src_off;
+    const int mode = op.mode;
+    const bool skip_outside = (mode == MODE_OVER);  // blending a zero source is the identity for OVER
     const double x0 = (double)r0 + 0.5, y0 = (double)c + 0.5;  // pixel centre of pixel 0
-    const int n_pre = top.pre_cnt;
 
-    for (int sub = 0; sub <= n_pre; sub++) {
-        // ---- the record of this sub-op
-        if (sub < n_pre) {
-            // the consumer reads slot `sub` only inside pre_box: a tile that misses it skips the pre-op
-            const int *b = top.pre_box[sub];
-            if (!(b[0] < tile_r1 && b[0] + b[2] > tile_r0 && b[1] < tile_c1 && b[1] + b[3] > tile_c0))
-                continue;
-            __syncthreads();  // everybody is done with the previous s_sub
-            if (tid < (int)(sizeof(OpRec) / 8))
-                reinterpret_cast<uint2 *>(&s_sub)[tid] =
-                    __ldg(reinterpret_cast<const uint2 *>(all_ops + top.pre[sub]) + tid);
-        }
-        if (tid == 0)
-            s_next = 0;
+    float4 acc[CMP_PX];
+#pragma unroll
+    for (int k = 0; k < CMP_PX; k++)
+        acc[k] = f4(0.f, 0.f, 0.f, 0.f);
+
+    for (;;) {
+        const int start = s_next;
         __syncthreads();
-        const OpRec &op = (sub < n_pre) ? s_sub : s_top;
-        const SrcRec *srcs = T.srcs + op.src_off;
-        const int mode = op.mode;
-        const bool skip_outside = (mode == MODE_OVER);  // blending a zero source is the identity for OVER
-
-        float4 acc[CMP_PX];
-#pragma unroll
-        for (int k = 0; k < CMP_PX; k++)
-            acc[k] = f4(0.f, 0.f, 0.f, 0.f);
-
-        for (;;) {
-            const int start = s_next;
-            __syncthreads();
-            if (start >= op.src_cnt)
-                break;
-            // ---- stage: order-preserving cull + copy of SrcRecs (warp 0)
-            if (tid < 32) {
-                int n = 0, k = start;
-                for (; k < op.src_cnt && n + 32 <= CMP_CAP; k += 32) {
-                    int i = k + tx;
-                    bool hit = false;
-                    SrcRec rec;
-                    if (i < op.src_cnt) {
-                        const uint4 *g = reinterpret_cast<const uint4 *>(srcs + i);
-                        uint4 *d = reinterpret_cast<uint4 *>(&rec);
-                        d[0] = __ldg(g), d[1] = __ldg(g + 1), d[2] = __ldg(g + 2), d[3] = __ldg(g + 3);
-                        hit = (i == 0 || !skip_outside) || (rec.r0 < tile_r1 && rec.r0 + rec.rows > tile_r0 &&
-                                                            rec.c0 < tile_c1 && rec.c0 + rec.cols > tile_c0);
-                    }
-                    unsigned m = __ballot_sync(0xffffffffu, hit);
-                    if (hit) {
-                        int pos = n + __popc(m & ((1u << tx) - 1));
-                        s_src[pos] = rec;
-                        s_idx[pos] = i;
-                    }
-                    n += __popc(m);
+        if (start >= op.src_cnt)
+            break;
+        // ---- stage: order-preserving cull + copy of SrcRecs (warp 0)
+        if (tid < 32) {
+            int n = 0, k = start;
+            for (; k < op.src_cnt && n + 32 <= CMP_CAP; k += 32) {
+                int i = k + tx;
+                bool hit = false;
+                SrcRec rec;
+                if (i < op.src_cnt) {
+                    const uint4 *g = reinterpret_cast<const uint4 *>(srcs + i);
+                    uint4 *d = reinterpret_cast<uint4 *>(&rec);
+                    d[0] = __ldg(g), d[1] = __ldg(g + 1), d[2] = __ldg(g + 2), d[3] = __ldg(g + 3);
+                    hit = (i == 0 || !skip_outside) ||
+                          (rec.r0 < tile_r1 && rec.r0 + rec.rows > tile_r0 && rec.c0 < tile_c1 && rec.c0 + rec.cols > tile_c0);
                 }
-                // a stencil modifier must be staged in the same round as the source it belongs to
-                if (k < op.src_cnt && n > 0) {
-                    int kind = __ldg(&srcs[k].kind);
-                    if (SRC_IS_MOD(kind) && s_idx[n - 1] == k - 1) {
-                        if (tx < 4)
-                            copy16(&s_src[n], srcs + k, tx);
-                        if (tx == 0)
-                            s_idx[n] = k;
-                        n++, k++;
-                    }
+                unsigned m = __ballot_sync(0xffffffffu, hit);
+                if (hit) {
+                    int pos = n + __popc(m & ((1u << tx) - 1));
+                    s_src[pos] = rec;
+                    s_idx[pos] = i;
                 }
-                if (tx == 0) {
-                    s_n = n;
-                    s_next = k < op.src_cnt ? k : op.src_cnt;
+                n += __popc(m);
+            }
+            // a stencil modifier must be staged in the same round as the source it belongs to
+            if (k < op.src_cnt && n > 0) {
+                int kind = __ldg(&srcs[k].kind);
+                if (kind >= SRC_MOD_COV && s_idx[n - 1] == k - 1) {
+                    if (tx < 4)
+                        copy16(&s_src[n], srcs + k, tx);
+                    if (tx == 0)
+                        s_idx[n] = k;
+                    n++, k++;
                 }
             }
-            __syncthreads();
-            const int n = s_n;
-            // ---- stage: paint records of the staged COVPAINT sources (14 x 16 bytes each)
-            {
-                static_assert(sizeof(PaintRec) == 224, "PaintRec layout");
-                const int part = tid & 15;
-                for (int j = tid >> 4; j < n; j += 16)
-                    if (part < 14 && s_src[j].kind == SRC_COVPAINT)
-                        copy16(&s_paint[j], T.paints + s_src[j].paint, part);
+            if (tx == 0) {
+                s_n = n;
+                s_next = k < op.src_cnt ? k : op.src_cnt;
             }
-            __syncthreads();
-            // ---- fold: everything that does not depend on the pixel is hoisted out of the 4-pixel loops
-            if (col_live) {
-                for (int j = 0; j < n; j++) {
-                    const SrcRec &s = s_src[j];
-                    if (SRC_IS_MOD(s.kind))
-                        continue;  // consumed together with its owner below
-                    const bool first = s_idx[j] == 0;
-                    const int dr = r0 - s.r0, dc = c - s.c0;
-                    unsigned live = 0;
-                    if ((unsigned)dc < (unsigned)s.cols) {
+        }
+        __syncthreads();
+        const int n = s_n;
+        // ---- stage: paint records of the staged COVPAINT sources (14 x 16 bytes each)
+        {
+            static_assert(sizeof(PaintRec) == 224, "PaintRec layout");
+            const int part = tid & 15;
+            for (int j = tid >> 4; j < n; j += 16)
+                if (part < 14 && s_src[j].kind == SRC_COVPAINT)
+                    copy16(&s_paint[j], T.paints + s_src[j].paint, part);
+        }
+        __syncthreads();
+        // ---- fold: everything that does not depend on the pixel is hoisted out of the 4-pixel loops
+        if (col_live) {
+            for (int j = 0; j < n; j++) {
+                const SrcRec &s = s_src[j];
+                if (s.kind >= SRC_MOD_COV)
+                    continue;  // consumed together with its owner below
+                const bool first = s_idx[j] == 0;
+                const int dr = r0 - s.r0, dc = c - s.c0;
+                unsigned live = 0;
+                if ((unsigned)dc < (unsigned)s.cols) {
 #pragma unroll
-                        for (int k = 0; k < CMP_PX; k++)
-                            if ((unsigned)(dr + 8 * k) < (unsigned)s.rows && lr0 + 8 * k < top.rows)
-                                live |= 1u << k;
-                    }
-                    if (!live && skip_outside && !first)
+                    for (int k = 0; k < CMP_PX; k++)
+                        if ((unsigned)(dr + 8 * k) < (unsigned)s.rows && lr0 + 8 * k < op.rows)
+                            live |= 1u << k;
+                }
+                if (!live && skip_outside && !first)
+                    continue;
+                const int base = (r0 - s.br0) * s.stride + (c - s.bc0), step = 8 * s.stride;  // a layer has < 2^31 px
+                float4 v[CMP_PX];
+                if (s.kind == SRC_L4) {
+                    const float4 *p = reinterpret_cast<const float4 *>(T.layers + s.off);
+#pragma unroll
+                    for (int k = 0; k < CMP_PX; k++)
+                        v[k] = (live >> k & 1) ? __ldg(p + (base + k * step)) : f4(0.f, 0.f, 0.f, 0.f);
+                } else {
+                    const float *p = (s.kind == SRC_L1 ? T.layers : T.cov) + s.off;
+                    float a[CMP_PX];
+#pragma unroll
+                    for (int k = 0; k < CMP_PX; k++)
+                        a[k] = (live >> k & 1) ? __ldg(p + (base + k * step)) : 0.f;
+                    // nothing of the path in these four pixels (the inside of a stroked ring, the corners of a
+                    // blob's box): an all-zero source is the identity of the over blend
+                    if (skip_outside && !first && a[0] == 0.f && a[1] == 0.f && a[2] == 0.f && a[3] == 0.f)
                         continue;
-                    const int base = (r0 - s.br0) * s.stride + (c - s.bc0), step = 8 * s.stride;  // a layer has < 2^31 px
-                    const int kind = SRC_BASE(s.kind);
-                    float4 v[CMP_PX];
-                    if (SRC_IS_SLOT(s.kind)) {
-                        // result of a pre-op folded by this CTA: this thread's own pixels, from shared memory
-#pragma unroll
-                        for (int k = 0; k < CMP_PX; k++) {
-                            float4 q = s_slot[s.off][k][tid];
-                            if (kind == SRC_L1)
-                                q = f4(q.x, q.x, q.x, q.x);
-                            v[k] = (live >> k & 1) ? q : f4(0.f, 0.f, 0.f, 0.f);
-                        }
-                    } else if (kind == SRC_L4) {
-                        const float4 *p = reinterpret_cast<const float4 *>(T.layers + s.off);
-#pragma unroll
-                        for (int k = 0; k < CMP_PX; k++)
-                            v[k] = (live >> k & 1) ? __ldg(p + (base + k * step)) : f4(0.f, 0.f, 0.f, 0.f);
-                    } else {
-                        const float *p = (kind == SRC_L1 ? T.layers : T.cov) + s.off;
-                        float a[CMP_PX];
-#pragma unroll
-                        for (int k = 0; k < CMP_PX; k++)
-                            a[k] = (live >> k & 1) ? __ldg(p + (base + k * step)) : 0.f;
-                        // nothing of the path in these four pixels (the inside of a stroked ring, the corners of
-                        // a blob's box): an all-zero source is the identity of the over blend
-                        bool any_cov = false;
-#pragma unroll
-                        for (int k = 0; k < CMP_PX; k++)
-                            any_cov |= a[k] != 0.f;
-                        if (skip_outside && !first && !any_cov)
-                            continue;
-                        if (kind == SRC_COVPAINT) {
-                            const PaintRec &pr = s_paint[j];
-                            if (pr.kind == PAINT_SOLID) {
-                                const float4 col = f4(pr.color[0], pr.color[1], pr.color[2], pr.color[3]);
-#pragma unroll
-                                for (int k = 0; k < CMP_PX; k++)
-                                    v[k] = f4(col.x * a[k], col.y * a[k], col.z * a[k], col.w * a[k]);
-                            } else {
-                                const float4 *pat = reinterpret_cast<const float4 *>(T.layers + s.off2);
-                                const StopRec *st = T.stops + pr.stop_off;
-#pragma unroll
-                                for (int k = 0; k < CMP_PX; k++) {
-                                    v[k] = f4(0.f, 0.f, 0.f, 0.f);
-                                    if (a[k] != 0.f) {
-                                        float4 q = paint_eval(T, pr, st, x0 + 8.0 * k, y0, pat, s.stride2);
-                                        v[k] = f4(q.x * a[k], q.y * a[k], q.z * a[k], q.w * a[k]);
-                                    }
-                                }
-                            }
-                        } else {
+                    if (s.kind == SRC_COVPAINT) {
+                        const PaintRec &pr = s_paint[j];
+                        if (pr.kind == PAINT_SOLID) {
+                            const float4 col = f4(pr.color[0], pr.color[1], pr.color[2], pr.color[3]);
 #pragma unroll
                             for (int k = 0; k < CMP_PX; k++)
-                                v[k] = f4(a[k], a[k], a[k], a[k]);
-                        }
-                    }
-                    if (s.mul != 1.0f) {
-                        const float m = s.mul;
+                                v[k] = f4(col.x * a[k], col.y * a[k], col.z * a[k], col.w * a[k]);
+                        } else {
+                            const float4 *pat = reinterpret_cast<const float4 *>(T.layers + s.off2);
+                            const StopRec *st = T.stops + pr.stop_off;
 #pragma unroll
-                        for (int k = 0; k < CMP_PX; k++)
-                            v[k] = f4(v[k].x * m, v[k].y * m, v[k].z * m, v[k].w * m);
-                    }
-                    if (kind != SRC_L1 && kind != SRC_COV && !conv_is_identity(s.conv)) {
-#pragma unroll
-                        for (int k = 0; k < CMP_PX; k++)
-                            if (live >> k & 1)
-                                v[k] = convert_px(v[k], s.conv);
-                    }
-                    if (j + 1 < n && SRC_IS_MOD(s_src[j + 1].kind)) {
-                        // stencil of a clip / luminance mask that was never written out as a layer
-                        const SrcRec &md = s_src[j + 1];
-#pragma unroll
-                        for (int k = 0; k < CMP_PX; k++)
-                            if (live >> k & 1) {
-                                float m;
-                                if (SRC_IS_SLOT(md.kind))
-                                    m = mod_of_pixel(s_slot[md.off][k][tid], md);
-                                else
-                                    m = mod_value(T, md, r0 + 8 * k, c);
-                                v[k] = f4(v[k].x * m, v[k].y * m, v[k].z * m, v[k].w * m);
+                            for (int k = 0; k < CMP_PX; k++) {
+                                v[k] = f4(0.f, 0.f, 0.f, 0.f);
+                                if (a[k] != 0.f) {
+                                    float4 q = paint_eval(T, pr, st, x0 + 8.0 * k, y0, pat, s.stride2);
+                                    v[k] = f4(q.x * a[k], q.y * a[k], q.z * a[k], q.w * a[k]);
+                                }
                             }
-                    }
-                    if (first) {
-#pragma unroll
-                        for (int k = 0; k < CMP_PX; k++)
-                            acc[k] = v[k];
-                    } else if (mode == MODE_OVER) {
-#pragma unroll
-                        for (int k = 0; k < CMP_PX; k++) {
-                            const float q = 1.0f - v[k].w;  // a dead pixel has v = 0: the blend is the identity
-                            acc[k] = f4(v[k].x + acc[k].x * q, v[k].y + acc[k].y * q, v[k].z + acc[k].z * q,
-                                        v[k].w + acc[k].w * q);
-                        }
-                    } else if (mode == MODE_IN) {
-#pragma unroll
-                        for (int k = 0; k < CMP_PX; k++) {
-                            const float da = acc[k].w;
-                            acc[k] = f4(v[k].x * da, v[k].y * da, v[k].z * da, v[k].w * da);
                         }
                     } else {
 #pragma unroll
                         for (int k = 0; k < CMP_PX; k++)
-                            acc[k] = blend_px(mode, op.k, acc[k], v[k]);
+                            v[k] = f4(a[k], a[k], a[k], a[k]);
                     }
                 }
-            }
-            __syncthreads();
-        }
-        if (!col_live)
-            continue;  // (keeps taking part in the barriers of the remaining sub-ops)
-
-        // ---- epilogue of this sub-op
+                if (s.mul != 1.0f) {
+                    const float m = s.mul;
 #pragma unroll
-        for (int k = 0; k < CMP_PX; k++) {
-            const int lr = lr0 + 8 * k;
-            float4 a = acc[k];
-            if (op.mul != 1.0f)
-                a = f4(a.x * op.mul, a.y * op.mul, a.z * op.mul, a.w * op.mul);
-            if (op.post & POST_CLIP01)
-                a = f4(clip01(a.x), clip01(a.y), clip01(a.z), clip01(a.w));
-            if (op.post & POST_ALPHA)
-                a = f4(0.f, 0.f, 0.f, a.w);
-            if (op.post & POST_MATRIX) {
-                const float *M = T.matrices + 20 * op.aux;  // row-major 4x5
-                float4 v = a;
-                a.x = clip01(M[0] * v.x + M[1] * v.y + M[2] * v.z + M[3] * v.w + M[4]);
-                a.y = clip01(M[5] * v.x + M[6] * v.y + M[7] * v.z + M[8] * v.w + M[9]);
-                a.z = clip01(M[10] * v.x + M[11] * v.y + M[12] * v.z + M[13] * v.w + M[14]);
-                a.w = clip01(M[15] * v.x + M[16] * v.y + M[17] * v.z + M[18] * v.w + M[19]);
+                    for (int k = 0; k < CMP_PX; k++)
+                        v[k] = f4(v[k].x * m, v[k].y * m, v[k].z * m, v[k].w * m);
+                }
+                if (s.kind != SRC_L1 && s.kind != SRC_COV && !conv_is_identity(s.conv)) {
+#pragma unroll
+                    for (int k = 0; k < CMP_PX; k++)
+                        if (live >> k & 1)
+                            v[k] = convert_px(v[k], s.conv);
+                }
+                if (j + 1 < n && s_src[j + 1].kind >= SRC_MOD_COV) {
+                    // stencil of a clip / luminance mask that was never written out as a layer
+                    const SrcRec &md = s_src[j + 1];
+#pragma unroll
+                    for (int k = 0; k < CMP_PX; k++)
+                        if (live >> k & 1) {
+                            const float m = mod_value(T, md, r0 + 8 * k, c);
+                            v[k] = f4(v[k].x * m, v[k].y * m, v[k].z * m, v[k].w * m);
+                        }
+                }
+                if (first) {
+#pragma unroll
+                    for (int k = 0; k < CMP_PX; k++)
+                        acc[k] = v[k];
+                } else if (mode == MODE_OVER) {
+#pragma unroll
+                    for (int k = 0; k < CMP_PX; k++) {
+                        const float q = 1.0f - v[k].w;  // a dead pixel has v = 0: the blend is the identity
+                        acc[k] = f4(v[k].x + acc[k].x * q, v[k].y + acc[k].y * q, v[k].z + acc[k].z * q,
+                                    v[k].w + acc[k].w * q);
+                    }
+                } else if (mode == MODE_IN) {
+#pragma unroll
+                    for (int k = 0; k < CMP_PX; k++) {
+                        const float da = acc[k].w;
+                        acc[k] = f4(v[k].x * da, v[k].y * da, v[k].z * da, v[k].w * da);
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < CMP_PX; k++)
+                        acc[k] = blend_px(mode, op.k, acc[k], v[k]);
+                }
             }
-            if (op.post & POST_LUMA) {
-                // Scene.render mask branch: luma . rgb * alpha on the straight-alpha image (svgrasterize.py:734-736)
-                const float l = (a.x * 0.2125f + a.y * 0.7154f + a.z * 0.072f) * a.w;
-                a = f4(l, l, l, l);
-            } else if (op.out_ch == 1) {
-                a = f4(a.w, a.w, a.w, a.w);
-            }
-            if (sub < n_pre) {
-                s_slot[sub][k][tid] = a;  // stays on chip: read back by this same thread
-                continue;
-            }
-            if (lr >= op.rows)
-                continue;
-            const long long idx = (long long)lr * op.stride + lc;
-            if (op.kind == OP_CANVAS) {
-                // main() :3870-3881: the premultiplied result over a zero canvas, clipped to [0, 1]
-                // (canvas_merge_at :326), converted to straight-alpha sRGB (Layer.write_png :212) and quantised
-                // with round-half-even (np.round, :263).  op.aux carries the render's linear_rgb flag.
-                a = f4(clip01(a.x), clip01(a.y), clip01(a.z), clip01(a.w));
-                if (op.aux != 0)
-                    a = convert_px(a, SVGR_CONV(1, 1, 0, 0));
-                else
-                    a = unpremultiply(a);  // sRGB render mode: Layer.convert is the alpha division only
-                // x * 255 + 1.5 * 2^23 leaves round-half-even(x * 255) in the low mantissa bits
-                uchar4 q;
-                q.x = (unsigned char)(__float_as_uint(a.x * 255.0f + 12582912.0f) & 0xffu);
-                q.y = (unsigned char)(__float_as_uint(a.y * 255.0f + 12582912.0f) & 0xffu);
-                q.z = (unsigned char)(__float_as_uint(a.z * 255.0f + 12582912.0f) & 0xffu);
-                q.w = (unsigned char)(__float_as_uint(a.w * 255.0f + 12582912.0f) & 0xffu);
-                reinterpret_cast<uchar4 *>(canvas_out + op.out_off)[idx] = q;
-            } else if (op.out_ch == 1) {
-                layers_out[op.out_off + idx] = a.x;
-            } else {
-                reinterpret_cast<float4 *>(layers_out + op.out_off)[idx] = a;
-            }
+        }
+        __syncthreads();
+    }
+    if (!col_live)
+        return;
+
+#pragma unroll
+    for (int k = 0; k < CMP_PX; k++) {
+        const int lr = lr0 + 8 * k;
+        if (lr >= op.rows)
+            continue;
+        float4 a = acc[k];
+        if (op.mul != 1.0f)
+            a = f4(a.x * op.mul, a.y * op.mul, a.z * op.mul, a.w * op.mul);
+        if (op.post & POST_CLIP01)
+            a = f4(clip01(a.x), clip01(a.y), clip01(a.z), clip01(a.w));
+        if (op.post & POST_ALPHA)
+            a = f4(0.f, 0.f, 0.f, a.w);
+        if (op.post & POST_MATRIX) {
+            const float *M = T.matrices + 20 * op.aux;  // row-major 4x5
+            float4 v = a;
+            a.x = clip01(M[0] * v.x + M[1] * v.y + M[2] * v.z + M[3] * v.w + M[4]);
+            a.y = clip01(M[5] * v.x + M[6] * v.y + M[7] * v.z + M[8] * v.w + M[9]);
+            a.z = clip01(M[10] * v.x + M[11] * v.y + M[12] * v.z + M[13] * v.w + M[14]);
+            a.w = clip01(M[15] * v.x + M[16] * v.y + M[17] * v.z + M[18] * v.w + M[19]);
+        }
+        const long long idx = (long long)lr * op.stride + lc;
+        if (op.kind == OP_CANVAS) {
+            // main() :3870-3881: the premultiplied result over a zero canvas, clipped to [0, 1]
+            // (canvas_merge_at :326), converted to straight-alpha sRGB (Layer.write_png :212) and quantised
+            // with round-half-even (np.round, :263).  op.aux carries the render's linear_rgb flag.
+            a = f4(clip01(a.x), clip01(a.y), clip01(a.z), clip01(a.w));
+            if (op.aux != 0)
+                a = convert_px(a, SVGR_CONV(1, 1, 0, 0));
+            else
+                a = unpremultiply(a);  // sRGB render mode: Layer.convert is the alpha division only
+            // x * 255 + 1.5 * 2^23 leaves round-half-even(x * 255) in the low mantissa bits
+            uchar4 q;
+            q.x = (unsigned char)(__float_as_uint(a.x * 255.0f + 12582912.0f) & 0xffu);
+            q.y = (unsigned char)(__float_as_uint(a.y * 255.0f + 12582912.0f) & 0xffu);
+            q.z = (unsigned char)(__float_as_uint(a.z * 255.0f + 12582912.0f) & 0xffu);
+            q.w = (unsigned char)(__float_as_uint(a.w * 255.0f + 12582912.0f) & 0xffu);
+            reinterpret_cast<uchar4 *>(canvas_out + op.out_off)[idx] = q;
+        } else if (op.post & POST_LUMA) {
+            // Scene.render mask branch: luma . rgb * alpha on the straight-alpha image (svgrasterize.py:734-736)
+            layers_out[op.out_off + idx] = (a.x * 0.2125f + a.y * 0.7154f + a.z * 0.072f) * a.w;
+        } else if (op.out_ch == 1) {
+            layers_out[op.out_off + idx] = a.w;
+        } else {
+            reinterpret_cast<float4 *>(layers_out + op.out_off)[idx] = a;
         }
     }
 }
@@ -418,16 +364,11 @@ __global__ void focal_flag_kernel(RenderTables T, const FocalJob *__restrict__ j
 }
 
 // ---------------------------------------------------------------------------------------------
-void svgr_launch_compose(const RenderTables &T, const OpRec *all_ops, const OpRec *ops, const int *tile_op, int n_tiles,
-                         float *layers_out, uint8_t *canvas_out, cudaStream_t s)
+void svgr_launch_compose(const RenderTables &T, const OpRec *ops, const int *tile_op, int n_tiles, float *layers_out,
+                         uint8_t *canvas_out, cudaStream_t s)
 {
-    static bool carveout_set = false;
-    if (!carveout_set) {  // 47 KB of static shared memory per CTA: ask for the largest carve-out so 4 CTAs fit
-        cudaFuncSetAttribute(compose_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        carveout_set = true;
-    }
     if (n_tiles > 0)
-        compose_kernel<<<n_tiles, 256, 0, s>>>(T, all_ops, ops, tile_op, layers_out, canvas_out);
+        compose_kernel<<<n_tiles, 256, 0, s>>>(T, ops, tile_op, layers_out, canvas_out);
 }
 
 // tile -> op table of one launch: op i owns tiles [ops[i].tile_base, ops[i + 1].tile_base).  One thread per

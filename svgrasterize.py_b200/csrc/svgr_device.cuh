@@ -233,18 +233,3 @@ __device__ __forceinline__ float mod_value(const RenderTables &T, const SrcRec &
     }
     return m * s.mul;
 }
-
-// the same for a pixel that is already in registers (result of a pre-op kept in a shared-memory slot);
-// one-channel results are replicated over the four channels of their slot
-__device__ __forceinline__ float mod_of_pixel(float4 v, const SrcRec &s)
-{
-    const int kind = s.kind & 15;
-    if (kind == SRC_MOD_L1)
-        return v.x * s.mul;
-    if (kind == SRC_MOD_L4A)
-        return v.w * s.mul;
-    if (s.mul != 1.0f)
-        v = f4(v.x * s.mul, v.y * s.mul, v.z * s.mul, v.w * s.mul);
-    v = convert_px(v, s.conv);
-    return (v.x * 0.2125f + v.y * 0.7154f + v.z * 0.072f) * v.w;
-}

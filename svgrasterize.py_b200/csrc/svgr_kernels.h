@@ -44,8 +44,8 @@ void svgr_launch_coverage(const double *edges, const MaskRec *masks, int n_masks
 
 // k_compose.cu
 void svgr_launch_expand_ops(const OpRec *ops, int n_ops, int n_tiles, int *tile_op, cudaStream_t s);
-void svgr_launch_compose(const RenderTables &T, const OpRec *all_ops, const OpRec *ops, const int *tile_op, int n_tiles,
-                         float *layers_out, uint8_t *canvas_out, cudaStream_t s);
+void svgr_launch_compose(const RenderTables &T, const OpRec *ops, const int *tile_op, int n_tiles, float *layers_out,
+                         uint8_t *canvas_out, cudaStream_t s);
 void svgr_launch_focal_flags(const RenderTables &T, const void *jobs, int n_jobs, int block0, int n_blocks, int *flags,
                              cudaStream_t s);
 

@@ -106,9 +106,6 @@ enum : int32_t {
     SRC_MOD_L1 = 9,     // one-channel layer
     SRC_MOD_L4A = 10,   // alpha of an RGBA layer
     SRC_MOD_LUMA = 11,  // luminance x alpha of an RGBA layer after Layer.convert (conv)
-    // the same, reading the result of an op that was folded inside the consumer's CTA (off = slot index):
-    // an inner group / mask group that never reaches HBM
-    SRC_SLOT_FLAG = 16,  // OR-ed onto SRC_L4, SRC_L1, SRC_MOD_L1, SRC_MOD_L4A, SRC_MOD_LUMA
 };
 
 // conversion codes: bit0 source pre_alpha, bit1 source linear, bit2 target pre, bit3 target linear
@@ -169,15 +166,11 @@ struct OpRec {
     int32_t stencil; // STENCIL_*
     int32_t tile_base;  // first tile id of this op inside its launch
     int32_t ntile_c;    // tiles per tile-row
-    int32_t pre_cnt;    // ops folded inside this op's CTAs first, their results kept in shared-memory slots
+    int32_t pad;
     float mul;    // opacity (applied after the fold)
     float k[4];   // arithmetic coefficients
-    int32_t pre[2];     // absolute indices (into the op table) of those ops; slot i holds the result of pre[i]
-    int32_t pad;
-    int32_t pre_box[2][4];  // (r0, c0, rows, cols) of the region this op reads from slot i: tiles outside skip the pre-op
+    float pad2;
 };
-static_assert(sizeof(OpRec) == 144, "OpRec layout");
-#define SVGR_MAX_SLOTS 2
 
 // any(det < 0) pre-pass of a two-circle gradient fill (svgrasterize.py:1621-1622)
 struct FocalJob {

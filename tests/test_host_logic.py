@@ -190,6 +190,6 @@ def test_planner_runs_without_a_gpu():
     assert rc == 0
     n_ops, n_srcs, n_launch, n_levels = info[0], info[1], info[2], info[3]
     assert n_ops == 3 * len(progs)      # two inner groups + the root folded straight into RGBA8, per icon
-    assert n_launch == 1                # ... and the inner groups are folded inside the root's CTAs
+    assert n_launch == 2 and n_levels == 2
     assert n_srcs >= 12 * len(progs)    # every mask is read by exactly one op (+ stencil modifiers)
     assert info[5] > 0
