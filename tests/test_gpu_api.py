@@ -181,3 +181,61 @@ def test_row_bands_reassemble_to_the_full_render(B, O):
             got = np.concatenate(bands, axis=0)
             assert got.shape == full.shape
             assert int(np.abs(got.astype(int) - full.astype(int)).max()) <= 1, (world, size)
+
+
+def test_empty_and_degenerate_inputs(B, O):
+    """What the reference answers with None / an all-transparent canvas (svgrasterize.py:958-959, :974-975,
+    :1004-1010, :686-687, :403-404)."""
+    from svgrasterize_b200 import synth
+
+    tr = B.Transform().matrix(0, 1, 0, 1, 0, 0)
+    assert B.Path([]).mask(tr) is None                      # no segments
+    assert B.Path([[]]).mask(tr) is None                    # an empty sub-path
+    dot = synth.PathBuilder().move_to(5, 5).line_to(5, 5).close().path()
+    res = dot.mask(tr)                                       # zero-area path: a (tiny) mask of zeros, like the reference
+    ref = O.mask_path(dot, tr)
+    assert (res is None) == (ref is None)
+    if res is not None:
+        assert res[0].image.shape == ref[0].image.shape and float(np.abs(res[0].image).max()) == 0.0
+    sq = synth.rect_path(10, 10, 20, 20)
+    assert sq.mask(tr, viewport=[100, 100, 10, 10]) is None  # clipped away by the viewport
+    nothing = B.Scene.fill(sq, None)                          # fill without paint renders nothing
+    assert nothing.render(tr) is None
+    u8 = B.render_canvas(B.Scene.group([nothing, B.Scene.fill(sq, None)]), (32, 24))
+    assert u8.shape == (24, 32, 4) and not u8.any()
+    # a clip that misses its target: compose IN with an empty intersection -> None
+    far = synth.rect_path(200, 200, 5, 5)
+    clipped = B.Scene.fill(sq, synth.color(1, 0, 0)).clip(B.Scene.fill(far, np.ones(4)))
+    assert clipped.render(tr) is None and O.render(clipped, tr) is None
+    # a huge coordinate range is clipped by the viewport, not allocated
+    big = synth.rect_path(-1e6, -1e6, 2e6, 2e6)
+    layer, _ = big.mask(tr, viewport=[0, 0, 16, 16])
+    assert layer.image.shape == (16, 16, 1) and float(layer.image.min()) == 1.0
+
+
+def test_background_intersect_and_png(B, O):
+    import io
+    import zlib
+
+    rng = np.random.default_rng(21)
+    a = rng.uniform(0, 1, size=(20, 24, 4)).astype(np.float32)
+    a[..., :3] *= a[..., 3:]
+    la = B.Layer(a, (2, 3), True, True)
+    bg = np.array([0.2, 0.4, 0.1, 1.0])
+    got = la.background(bg)
+    want = O.blend(0, np.broadcast_to(bg, a.shape).astype(np.float64), a.astype(np.float64))
+    assert got.image.shape == a.shape and np.abs(got.image - want).max() <= 2e-5
+    m = rng.uniform(0, 1, size=(30, 30, 1)).astype(np.float32)
+    res = B.canvas_merge_intersect([(m, (0, 0)), (a, (2, 3))])
+    ref = O.merge_intersect([(m.astype(np.float64), (0, 0)), (a.astype(np.float64), (2, 3))], 2)
+    assert tuple(res[1]) == tuple(ref[1]) and np.abs(res[0] - ref[0]).max() <= 2e-5
+    assert B.canvas_merge_intersect([(m, (0, 0)), (a, (100, 100))]) is None
+    buf = io.BytesIO()
+    la.convert(pre_alpha=True, linear_rgb=False).write_png(buf)
+    png = buf.getvalue()
+    assert png[:8] == b"\x89PNG\r\n\x1a\n" and png[12:16] == b"IHDR"
+    width, height = int.from_bytes(png[16:20], "big"), int.from_bytes(png[20:24], "big")
+    assert (width, height) == (24, 20)
+    idat = png[png.index(b"IDAT") + 4: png.index(b"IEND") - 8]
+    raw = zlib.decompress(idat)
+    assert len(raw) == height * (1 + 4 * width)
