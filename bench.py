@@ -271,8 +271,10 @@ def run_gpu(opts):
 
     # ---- e2e: svgr_render with host buffers (H2D of the program, D2H of the RGBA8 result inside)
     barrier()
-    sec_e2e, h2d_bytes = run_e2e(icon_progs, out_host_np, local, opts.steps, opts.warmup, opts.e2e_workers,
-                                 opts.e2e_chunks)
+    # every host thread of the e2e leg needs a core to itself (it plans on the host between its launches)
+    workers = max(1, min(opts.e2e_workers, (os.cpu_count() or 1) // max(world, 1) - 1))
+    chunks = max(workers, opts.e2e_chunks if opts.e2e_chunks % workers == 0 else workers)
+    sec_e2e, h2d_bytes = run_e2e(icon_progs, out_host_np, local, opts.steps, opts.warmup, workers, chunks)
     barrier()
     ms_e2e = max_over_ranks(sec_e2e * 1e3)
     e2e_value = world * n_px / (ms_e2e * 1e-3) / 1e6
@@ -339,7 +341,7 @@ def run_gpu(opts):
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(h2d_bytes),
                 "d2h_bytes_per_step": int(prog.canvas_bytes), "checksum": check,
                 "how": f"Engine.render (svgr_render) on pinned host buffers; the batch goes through "
-                       f"{opts.e2e_chunks} calls on {opts.e2e_workers} host threads (one context + stream each) "
+                       f"{chunks} calls on {workers} host threads (one context + stream each) "
                        "so that copies overlap compute; wall clock between device synchronisations"},
         "gpu_launches": int(st["n_kernels"]) * opts.steps,
         "paths_per_s": world * len(prog.paths) / (ms_step * 1e-3),
