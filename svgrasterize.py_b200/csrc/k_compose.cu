@@ -208,7 +208,7 @@ compose_kernel(RenderTables T, const OpRec *__restrict__ ops, const int *__restr
                             const float4 col = f4(pr.color[0], pr.color[1], pr.color[2], pr.color[3]);
 #pragma unroll
                             for (int k = 0; k < CMP_PX; k++)
-                                v[k] = f4(col.x * a[k], col.y * a[k], col.z * a[k], col.w * a[k]);
+                                v[k] = scale4(col, a[k]);
                         } else {
                             const float4 *pat = reinterpret_cast<const float4 *>(T.layers + s.off2);
                             const StopRec *st = T.stops + pr.stop_off;
@@ -217,7 +217,7 @@ compose_kernel(RenderTables T, const OpRec *__restrict__ ops, const int *__restr
                                 v[k] = f4(0.f, 0.f, 0.f, 0.f);
                                 if (a[k] != 0.f) {
                                     float4 q = paint_eval(T, pr, st, x0 + 8.0 * k, y0, pat, s.stride2);
-                                    v[k] = f4(q.x * a[k], q.y * a[k], q.z * a[k], q.w * a[k]);
+                                    v[k] = scale4(q, a[k]);
                                 }
                             }
                         }
@@ -231,7 +231,7 @@ compose_kernel(RenderTables T, const OpRec *__restrict__ ops, const int *__restr
                     const float m = s.mul;
 #pragma unroll
                     for (int k = 0; k < CMP_PX; k++)
-                        v[k] = f4(v[k].x * m, v[k].y * m, v[k].z * m, v[k].w * m);
+                        v[k] = scale4(v[k], m);
                 }
                 if (s.kind != SRC_L1 && s.kind != SRC_COV && !conv_is_identity(s.conv)) {
 #pragma unroll
@@ -246,7 +246,7 @@ compose_kernel(RenderTables T, const OpRec *__restrict__ ops, const int *__restr
                     for (int k = 0; k < CMP_PX; k++)
                         if (live >> k & 1) {
                             const float m = mod_value(T, md, r0 + 8 * k, c);
-                            v[k] = f4(v[k].x * m, v[k].y * m, v[k].z * m, v[k].w * m);
+                            v[k] = scale4(v[k], m);
                         }
                 }
                 if (first) {
@@ -256,15 +256,13 @@ compose_kernel(RenderTables T, const OpRec *__restrict__ ops, const int *__restr
                 } else if (mode == MODE_OVER) {
 #pragma unroll
                     for (int k = 0; k < CMP_PX; k++) {
-                        const float q = 1.0f - v[k].w;  // a dead pixel has v = 0: the blend is the identity
-                        acc[k] = f4(v[k].x + acc[k].x * q, v[k].y + acc[k].y * q, v[k].z + acc[k].z * q,
-                                    v[k].w + acc[k].w * q);
+                        // a dead pixel has v = 0: the blend is the identity
+                        acc[k] = madd4(acc[k], 1.0f - v[k].w, v[k]);
                     }
                 } else if (mode == MODE_IN) {
 #pragma unroll
                     for (int k = 0; k < CMP_PX; k++) {
-                        const float da = acc[k].w;
-                        acc[k] = f4(v[k].x * da, v[k].y * da, v[k].z * da, v[k].w * da);
+                        acc[k] = scale4(v[k], acc[k].w);
                     }
                 } else {
 #pragma unroll
@@ -285,7 +283,7 @@ compose_kernel(RenderTables T, const OpRec *__restrict__ ops, const int *__restr
             continue;
         float4 a = acc[k];
         if (op.mul != 1.0f)
-            a = f4(a.x * op.mul, a.y * op.mul, a.z * op.mul, a.w * op.mul);
+            a = scale4(a, op.mul);
         if (op.post & POST_CLIP01)
             a = f4(clip01(a.x), clip01(a.y), clip01(a.z), clip01(a.w));
         if (op.post & POST_ALPHA)

@@ -35,7 +35,7 @@ template <int ST>
 __device__ __forceinline__ void stencil_acc(float4 &a, float w, float4 v)
 {
     if (ST == STENCIL_CONV) {
-        a.x += w * v.x, a.y += w * v.y, a.z += w * v.z, a.w += w * v.w;
+        a = madd4(v, w, a);  // two FFMA2
     } else if (ST == STENCIL_MAX) {
         a.x = nanmax1(a.x, v.x), a.y = nanmax1(a.y, v.y), a.z = nanmax1(a.z, v.z), a.w = nanmax1(a.w, v.w);
     } else {
@@ -186,7 +186,7 @@ conv2d_kernel(RenderTables T, const OpRec *__restrict__ ops, const int *__restri
         for (int b = 0; b < kc; b++) {
             float wt = w[a * kc + b];
             float4 v = sm[(ty + kr - 1 - a) * scols + (tx + kc - 1 - b)];
-            acc.x += wt * v.x, acc.y += wt * v.y, acc.z += wt * v.z, acc.w += wt * v.w;
+            acc = madd4(v, wt, acc);
         }
     reinterpret_cast<float4 *>(layers_out + op.out_off)[(long long)lr * op.stride + lc] = acc;
 }

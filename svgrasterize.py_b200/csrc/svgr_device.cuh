@@ -8,7 +8,52 @@
 
 __device__ __forceinline__ float4 f4(float x, float y, float z, float w) { return make_float4(x, y, z, w); }
 
-__device__ __forceinline__ float clip01(float v) { return fminf(fmaxf(v, 0.f), 1.f); }
+__device__ __forceinline__ float clip01(float v) { return __saturatef(v); }  // one instruction; NaN -> 0 like fmax/fmin
+
+// Packed float32 pairs (Blackwell FFMA2 / FMUL2): an RGBA pixel is two instructions instead of four.
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c)
+{
+    float2 d;
+    asm("{.reg .b64 ra, rb, rc, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\t"
+        "mov.b64 rb, {%4, %5};\n\t"
+        "mov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+        "mov.b64 {%0, %1}, rd;}\n"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+
+__device__ __forceinline__ float2 mul2(float2 a, float2 b)
+{
+    float2 d;
+    asm("{.reg .b64 ra, rb, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\t"
+        "mov.b64 rb, {%4, %5};\n\t"
+        "mul.rn.f32x2 rd, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rd;}\n"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+
+// v * m
+__device__ __forceinline__ float4 scale4(float4 v, float m)
+{
+    const float2 mm = make_float2(m, m);
+    const float2 lo = mul2(make_float2(v.x, v.y), mm), hi = mul2(make_float2(v.z, v.w), mm);
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+
+// s + d * q
+__device__ __forceinline__ float4 madd4(float4 d, float q, float4 s)
+{
+    const float2 qq = make_float2(q, q);
+    const float2 lo = fma2(make_float2(d.x, d.y), qq, make_float2(s.x, s.y));
+    const float2 hi = fma2(make_float2(d.z, d.w), qq, make_float2(s.z, s.w));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
 
 // x^y for x in (0, 1], y a constant: exp2(y log2 x) on the special function unit.  __log2f is accurate to
 // 2^-21.4 absolute near 1 and a few ulp elsewhere, so the result is within ~2e-6 relative of powf -- inside
