@@ -251,9 +251,9 @@ def run_gpu(opts):
 
     # ---- value: resident program, device timing
     sampler = ClockSampler(local)
-    sampler.start()
     acc = {}
     barrier()
+    sampler.start()  # clocks are sampled during the timed region only
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(opts.steps):
@@ -262,8 +262,9 @@ def run_gpu(opts):
             if k.startswith("ms_") or k.startswith("host_"):
                 acc[k] = acc.get(k, 0.0) + v
     e1.record(stream)
-    barrier()
+    torch.cuda.synchronize()
     sampler.stop_flag = True
+    barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     sampler.join()
     ms_step = ms_total / opts.steps
