@@ -150,6 +150,8 @@ struct svgr_ctx {
     int device = 0;
     int sm_count = 148;
     cudaStream_t own_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // device -> host copies of finished canvases, overlapped with later chunks
+    cudaEvent_t ev_copy[16] = {nullptr};
     std::string err;
 
     // ---- resident program (device) + host copies of what the planner needs
@@ -1255,6 +1257,8 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
     auto t_h2 = std::chrono::steady_clock::now();
     float host_nodes_ms = 0.f;
     int n_launches = 0, timed_chunks = 0;
+    bool early_copy_ok = true;
+    long long copied_bytes = 0, copied_hi = 0;
     if (!pl.begin_nodes())
         FAIL(SVGR_E_INVALID, pl.err);
     {
@@ -1374,14 +1378,45 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
             if (timing && k < 16)
                 cudaEventRecord(ctx->ev_chunk[k][1], s);
             timed_chunks = std::min(k + 1, 16);
+            // host output: the canvases this chunk finished go down on the copy stream while the next chunk
+            // is planned and composed (chunks own increasing, disjoint byte ranges of the output)
+            if (canvas && out && !out_on_device && early_copy_ok && k < 16) {
+                long long lo = -1, hi = -1;
+                for (size_t q = (size_t)op_begin; q < ctx->ops.size(); q++) {
+                    const PlannedOp &po = ctx->ops[q];
+                    if (po.cls != 3)
+                        continue;
+                    long long a = po.op.out_off, b = a + 4ll * po.op.rows * po.op.cols;
+                    lo = lo < 0 ? a : std::min(lo, a);
+                    hi = std::max(hi, b);
+                }
+                if (lo >= 0) {
+                    if (lo < copied_hi) {
+                        early_copy_ok = false;  // canvases not laid out in node order: one copy at the end
+                    } else {
+                        CK(cudaEventRecord(ctx->ev_copy[k], s));
+                        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy[k], 0));
+                        CK(cudaMemcpyAsync(out + lo, canvas + lo, (size_t)(hi - lo), cudaMemcpyDeviceToHost,
+                                           ctx->copy_stream));
+                        copied_bytes += hi - lo;
+                        copied_hi = hi;
+                    }
+                }
+            }
             up_ops = ctx->ops.size(), up_srcs = ctx->srcs.size(), up_focal = ctx->focal_jobs.size();
         }
         ctx->planned = true;
         if (stop_after != SVGR_STOP_COVERAGE) {
             mark(7);
             mark(8);
-            if (canvas && out && !out_on_device)
-                CK(cudaMemcpyAsync(out, canvas, (size_t)ctx->canvas_bytes, cudaMemcpyDeviceToHost, s));
+            if (canvas && out && !out_on_device) {
+                if (early_copy_ok && copied_bytes == ctx->canvas_bytes)
+                    CK(cudaStreamSynchronize(ctx->copy_stream));  // everything already went down chunk by chunk
+                else {
+                    CK(cudaStreamSynchronize(ctx->copy_stream));
+                    CK(cudaMemcpyAsync(out, canvas, (size_t)ctx->canvas_bytes, cudaMemcpyDeviceToHost, s));
+                }
+            }
             mark(9);
             ctx->composed = true;
         }
@@ -1479,6 +1514,9 @@ int svgr_create(int device, svgr_ctx **out)
     }
     for (auto &e : ctx->ev)
         cudaEventCreate(&e);
+    cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    for (auto &e : ctx->ev_copy)
+        cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     for (auto &e : ctx->ev_chunk)
         cudaEventCreate(&e[0]), cudaEventCreate(&e[1]);
     *out = ctx;
@@ -1511,6 +1549,11 @@ void svgr_destroy(svgr_ctx *ctx)
         if (e[1])
             cudaEventDestroy(e[1]);
     }
+    for (auto &e : ctx->ev_copy)
+        if (e)
+            cudaEventDestroy(e);
+    if (ctx->copy_stream)
+        cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream)
         cudaStreamDestroy(ctx->own_stream);
     delete ctx;
