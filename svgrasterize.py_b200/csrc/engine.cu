@@ -156,6 +156,7 @@ struct svgr_ctx {
 
     // ---- resident program (device) + host copies of what the planner needs
     bool have_program = false;
+    const svgr_program *pending = nullptr;  // host tables of this program still to be copied (finish_load)
     long long n_seg = 0;
     int n_path = 0, n_stroke = 0, n_stroke_sub = 0, n_paint = 0, n_stop = 0, n_focal = 0, n_node = 0;
     long long n_stroke_seg = 0;
@@ -983,6 +984,33 @@ float ev_ms(cudaEvent_t a, cudaEvent_t b)
 // ---------------------------------------------------------------------------------------------
 // pipeline
 // ---------------------------------------------------------------------------------------------
+// Host copies of the tables the planner reads.  Deferred: svgr_render enqueues the uploads and the geometry
+// kernels first and makes these copies while the GPU is busy (ctx->pending points at the caller's program,
+// which outlives the call).
+static int finish_load(svgr_ctx *ctx)
+{
+    const svgr_program *p = ctx->pending;
+    if (!p)
+        return SVGR_OK;
+    ctx->pending = nullptr;
+    ctx->h_paths.assign(p->paths, p->paths + p->n_path);
+    ctx->h_paints.assign(p->paints, p->paints + p->n_paint);
+    ctx->h_nodes.assign(p->nodes, p->nodes + p->n_node);
+    ctx->h_children.assign(p->children, p->children + p->n_child);
+    ctx->h_kernels.assign(p->kernels, p->kernels + p->n_kernel);
+    ctx->h_offset_tr.assign(p->offset_tr, p->offset_tr + (size_t)p->n_offset_tr * 12);
+    ctx->h_ext.assign(p->externals, p->externals + p->n_external);
+    ctx->h_ext_data.clear();
+    for (int i = 0; i < p->n_external; i++) {
+        const svgr_external &e = p->externals[i];
+        if (e.channels != 1 && e.channels != 4)
+            FAIL(SVGR_E_INVALID, "external layer must have 1 or 4 channels");
+        size_t n = (size_t)std::max(e.rows, 0) * std::max(e.cols, 0) * e.channels;
+        ctx->h_ext_data.emplace_back(e.image, e.image + n);
+    }
+    return SVGR_OK;
+}
+
 static int load_program(svgr_ctx *ctx, const svgr_program *p, cudaStream_t s, bool host_only = false)
 {
     if (!p)
@@ -1009,21 +1037,6 @@ static int load_program(svgr_ctx *ctx, const svgr_program *p, cudaStream_t s, bo
     CK(upload(ctx->d_matrices, p->matrices, (size_t)p->n_matrix * 20, s));
     CK(upload(ctx->d_weights, p->weights, (size_t)p->n_weight, s));
     }
-    ctx->h_paths.assign(p->paths, p->paths + p->n_path);
-    ctx->h_paints.assign(p->paints, p->paints + p->n_paint);
-    ctx->h_nodes.assign(p->nodes, p->nodes + p->n_node);
-    ctx->h_children.assign(p->children, p->children + p->n_child);
-    ctx->h_kernels.assign(p->kernels, p->kernels + p->n_kernel);
-    ctx->h_offset_tr.assign(p->offset_tr, p->offset_tr + (size_t)p->n_offset_tr * 12);
-    ctx->h_ext.assign(p->externals, p->externals + p->n_external);
-    ctx->h_ext_data.clear();
-    for (int i = 0; i < p->n_external; i++) {
-        const svgr_external &e = p->externals[i];
-        if (e.channels != 1 && e.channels != 4)
-            FAIL(SVGR_E_INVALID, "external layer must have 1 or 4 channels");
-        size_t n = (size_t)std::max(e.rows, 0) * std::max(e.cols, 0) * e.channels;
-        ctx->h_ext_data.emplace_back(e.image, e.image + n);
-    }
     for (int i = 0; i < p->n_node; i++) {
         const svgr_node &n = p->nodes[i];
         if (n.child_cnt < 0 || n.child_off < 0 || (long long)n.child_off + n.child_cnt > p->n_child)
@@ -1045,6 +1058,9 @@ static int load_program(svgr_ctx *ctx, const svgr_program *p, cudaStream_t s, bo
     }
     ctx->have_program = true;
     ctx->planned = ctx->covered = ctx->composed = false;
+    ctx->pending = p;
+    if (host_only)
+        return finish_load(ctx);
     return SVGR_OK;
 }
 
@@ -1151,6 +1167,11 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
         }
         CK(cudaMemcpyAsync(ctx->pin_status.p, d_st, sizeof(StatusBlock), cudaMemcpyDeviceToHost, s));
         mark(2);
+        {
+            int rc_load = finish_load(ctx);  // host-side table copies overlap the geometry kernels
+            if (rc_load != SVGR_OK)
+                return rc_load;
+        }
         CK(cudaStreamSynchronize(s));
         st = *(StatusBlock *)ctx->pin_status.p;
         if (timing) {
@@ -1578,6 +1599,10 @@ int svgr_render(svgr_ctx *ctx, const svgr_program *prog, void *stream, int stop_
         cudaEventRecord(e1, s);
     if (rc == SVGR_OK)
         rc = run_pipeline(ctx, s, stop_after, out, out_on_device, timing, stats);
+    if (ctx->pending) {  // the call failed before the host tables were copied: nothing resident to re-render
+        ctx->pending = nullptr;
+        ctx->have_program = false;
+    }
     if (timing) {
         if (rc == SVGR_OK && stats) {
             stats->ms_h2d = ev_ms(e0, e1);
