@@ -222,6 +222,24 @@ struct Planner {
     const std::vector<int> *uses_p = nullptr;  // how many nodes read each node (shared, read-only while planning)
     std::vector<PlannedOp> sorted_ops;
     std::vector<Val> scratch_vals;
+    // source lists under construction: ops nest (a consumer may have to materialise one of its inputs first),
+    // so the scratch vectors form a small stack instead of being allocated per op
+    std::vector<std::vector<SrcRec>> ss_pool;
+    int ss_depth = 0;
+    struct SrcList {
+        Planner &pl;
+        std::vector<SrcRec> &v;
+        explicit SrcList(Planner &p) : pl(p), v(p.take()) {}
+        ~SrcList() { pl.ss_depth--; }
+    };
+    std::vector<SrcRec> &take()
+    {
+        if (ss_depth >= (int)ss_pool.size())
+            ss_depth = (int)ss_pool.size() - 1;  // cannot happen (nesting is two deep); never grow while lists are live
+        std::vector<SrcRec> &v = ss_pool[ss_depth++];
+        v.clear();
+        return v;
+    }
     // outputs: the context's tables, or thread-local ones when the node range is planned by several threads
     std::vector<PlannedOp> *ops_p;
     std::vector<SrcRec> *srcs_p;
@@ -229,7 +247,10 @@ struct Planner {
     int n_focal_blocks = 0;
     long long layer_pixels = 0;
 
-    explicit Planner(svgr_ctx *c) : ctx(c), ops_p(&c->ops), srcs_p(&c->srcs), focal_p(&c->focal_jobs) {}
+    explicit Planner(svgr_ctx *c) : ctx(c), ops_p(&c->ops), srcs_p(&c->srcs), focal_p(&c->focal_jobs)
+    {
+        ss_pool.resize(64);  // deeper nesting than this does not occur (materialise -> unary is two levels)
+    }
 
     Val alloc(int kind, int r0, int c0, int rows, int cols, int pre, int lin, int level)
     {
@@ -319,7 +340,8 @@ struct Planner {
     Val unary(const Val &v, int out_kind, int want_pre, int want_lin, int out_pre, int out_lin, int post, float mul,
               int aux = 0)
     {
-        std::vector<SrcRec> ss;
+        SrcList sl(*this);
+        std::vector<SrcRec> &ss = sl.v;
         int level = push_src(ss, v, want_pre, want_lin) + 1;
         Val out = alloc(out_kind, v.r0, v.c0, v.rows, v.cols, out_pre, out_lin, level);
         emit(0, OP_COMPOSE, out, ss, MODE_OVER, post, mul, out.level, nullptr, aux);
@@ -340,7 +362,8 @@ struct Planner {
             emit(0, OP_COMPOSE, out, {s}, MODE_OVER, POST_LUMA, 1.0f, out.level);
             return out;
         }
-        std::vector<SrcRec> ss;
+        SrcList sl(*this);
+        std::vector<SrcRec> &ss = sl.v;
         push_src(ss, v, v.pre, v.lin);  // identity conversion: never recurses into materialize
         Val out = alloc(v.one_channel() ? SRC_L1 : SRC_L4, v.r0, v.c0, v.rows, v.cols, v.pre, v.lin, v.level + 1);
         emit(0, OP_COMPOSE, out, ss, MODE_OVER, POST_NONE, 1.0f, out.level);
@@ -371,8 +394,8 @@ struct Planner {
                 r1 = std::max(r1, l.r0 + l.rows), c1 = std::max(c1, l.c0 + l.cols);
             }
         }
-        std::vector<SrcRec> ss;
-        ss.reserve(layers.size() * 2);
+        SrcList sl(*this);
+        std::vector<SrcRec> &ss = sl.v;
         int level = 0;
         for (auto &l : layers)
             level = std::max(level, push_src(ss, l, pre, lin));
@@ -651,7 +674,8 @@ struct Planner {
             // canvas_merge_at onto zeros (svgrasterize.py:304-327): no conversion, result clipped to [0, 1]
             {
                 Val vv = v.kind == VAL_LUMA ? materialize(v) : v;
-                std::vector<SrcRec> ss;
+                SrcList sl(*this);
+        std::vector<SrcRec> &ss = sl.v;
                 int level = push_src(ss, vv, vv.pre, vv.lin) + 1;
                 Val o2 = alloc(SRC_L4, n.a, n.b, n.c, n.d, vv.pre, vv.lin, level);
                 emit(0, OP_COMPOSE, o2, ss, MODE_OVER, POST_CLIP01, 1.0f, o2.level);
@@ -695,7 +719,8 @@ struct Planner {
             o.r0 = n.c, o.c0 = n.d, o.rows = n.a, o.cols = n.b, o.stride = n.b, o.out_ch = 4;
             o.out_off = out_off;
             o.mul = 1.0f;
-            std::vector<SrcRec> ss;
+            SrcList sl(*this);
+        std::vector<SrcRec> &ss = sl.v;
             int level = 0;
             if (v.kind != VAL_EMPTY)
                 level = push_src(ss, v, 1, lin);
@@ -1628,8 +1653,18 @@ int svgr_debug_plan(const svgr_program *prog, const int32_t *boxes, int reps, fl
             auto t0 = std::chrono::steady_clock::now();
             bool ok = pl.plan_masks();
             auto t1 = std::chrono::steady_clock::now();
-            ok = ok && pl.plan_nodes();
+            auto tb0 = std::chrono::steady_clock::now();
+            ok = ok && pl.begin_nodes();
+            auto tb1 = std::chrono::steady_clock::now();
+            for (int k = 0; ok && k < pl.n_chunks(); k++) {
+                int a, b;
+                ok = pl.plan_chunk(k, &a, &b);
+            }
             auto t2 = std::chrono::steady_clock::now();
+            if (getenv("SVGR_PLAN_DEBUG"))
+                fprintf(stderr, "[plan] begin_nodes %.3f ms, chunks %.3f ms (%d chunks)\n",
+                        std::chrono::duration<float, std::milli>(tb1 - tb0).count(),
+                        std::chrono::duration<float, std::milli>(t2 - tb1).count(), pl.n_chunks());
             if (!ok)
                 rc = SVGR_E_INVALID;
             best_m = std::min(best_m, std::chrono::duration<float, std::milli>(t1 - t0).count());
