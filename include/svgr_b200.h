@@ -222,6 +222,12 @@ int svgr_cloud_bounds(svgr_ctx *ctx, int32_t n_query, const int32_t *q_off, cons
 int64_t svgr_arc_to_cubics(double cx, double cy, double rx, double ry, double phi, double eta, double eta_delta,
                            double *out, int64_t cap);
 
+/* The same for a whole segment list: every SEG_ARC row (cx, cy, rx, ry, phi, eta, eta_delta) is replaced by
+ * its cubic pieces, all other rows are copied.  new_index has n + 1 entries (input position -> output
+ * position).  Returns the output length or a negative code (SVGR_E_NOMEM: cap too small). */
+int64_t svgr_expand_arcs(const uint8_t *tags, const double *data, int64_t n, uint8_t *out_tags, double *out_data,
+                         int64_t cap, int64_t *new_index);
+
 #ifdef __cplusplus
 }
 #endif

@@ -96,6 +96,7 @@ SYMBOLS = {
     "svgr_read_node": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "svgr_cloud_bounds": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "svgr_arc_to_cubics": (C.c_int64, [C.c_double] * 7 + [C.c_void_p, C.c_int64]),
+    "svgr_expand_arcs": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
 }
 
 _lib = None

@@ -11,16 +11,14 @@ import numpy as np
 
 
 def paint_to_srgb(color) -> np.ndarray:
-    """Premultiplied linear RGBA -> premultiplied sRGB RGBA (float64)."""
-    c = np.array(color, dtype=np.float64)
-    a = c[3]
+    """Premultiplied linear RGBA -> premultiplied sRGB RGBA (float64).  Scalar Python floats: the same IEEE
+    double operations as the reference's numpy calls on a 4-vector, without their per-call overhead."""
+    r, g, b, a = (float(v) for v in color)
     if a > 0.0001:
-        c[:3] = c[:3] / a
-    c = np.clip(c, 0.0, 1.0)
-    rgb = c[:3]
-    low = rgb <= 0.0031308
-    out = np.empty(3)
-    out[low] = rgb[low] * 12.92
-    out[~low] = 1.055 * np.power(rgb[~low], 1.0 / 2.4) - 0.055
-    c[:3] = out * c[3]
-    return c
+        r, g, b = r / a, g / a, b / a
+    r, g, b, a = (min(max(v, 0.0), 1.0) for v in (r, g, b, a))
+
+    def enc(v):
+        return v * 12.92 if v <= 0.0031308 else 1.055 * float(np.power(v, 1.0 / 2.4)) - 0.055
+
+    return np.array([enc(r) * a, enc(g) * a, enc(b) * a, a], dtype=np.float64)

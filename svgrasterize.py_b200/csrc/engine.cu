@@ -1853,6 +1853,40 @@ int svgr_cloud_bounds(svgr_ctx *ctx, int32_t n_query, const int32_t *q_off, cons
 }
 
 int64_t svgr_arc_to_cubics(double cx, double cy, double rx, double ry, double phi, double eta, double eta_delta,
+                           double *out, int64_t cap);
+
+// Expands every SEG_ARC row of a segment list into its cubic pieces in one call (arc rows hold
+// cx, cy, rx, ry, phi, eta, eta_delta).  new_index[i] = position of input segment i in the output
+// (n + 1 entries, so sub-path offsets can be mapped).  Returns the output length, or a negative code.
+int64_t svgr_expand_arcs(const uint8_t *tags, const double *data, int64_t n, uint8_t *out_tags, double *out_data,
+                         int64_t cap, int64_t *new_index)
+{
+    int64_t m = 0;
+    for (int64_t i = 0; i < n; i++) {
+        new_index[i] = m;
+        const double *d = data + 8 * i;
+        if (tags[i] == SEG_ARC) {
+            if (m + 64 > cap)
+                return SVGR_E_NOMEM;
+            int64_t k = svgr_arc_to_cubics(d[0], d[1], d[2], d[3], d[4], d[5], d[6], out_data + 8 * m, 64);
+            if (k < 0)
+                return k;
+            for (int64_t j = 0; j < k; j++)
+                out_tags[m + j] = SEG_CUBIC;
+            m += k;
+        } else {
+            if (m + 1 > cap)
+                return SVGR_E_NOMEM;
+            out_tags[m] = tags[i];
+            memcpy(out_data + 8 * m, d, 64);
+            m++;
+        }
+    }
+    new_index[n] = m;
+    return m;
+}
+
+int64_t svgr_arc_to_cubics(double cx, double cy, double rx, double ry, double phi, double eta, double eta_delta,
                            double *out, int64_t cap)
 {
     // arc_to_bezier3 (svgrasterize.py:2355-2394): pieces of at most pi/4; np.linspace gives

@@ -46,32 +46,21 @@ def m6(transform) -> np.ndarray:
 def expand_arcs(tags, data, sub_off):
     """Replace PATH_ARC rows by their cubic pieces (arc_to_bezier3, svgrasterize.py:2355, evaluated on
     the host with the C library's libm so the control points have the reference's bits)."""
-    arcs = np.nonzero(tags == S.PATH_ARC)[0]
-    if len(arcs) == 0:
+    n_arc = int(np.count_nonzero(tags == S.PATH_ARC))
+    if n_arc == 0:
         return tags, data, sub_off
-    L = _lib.lib()
-    out_t, out_d, new_index = [], [], np.zeros(len(tags) + 1, dtype=np.int64)
-    buf = np.empty((64, 8))
-    prev = 0
-    n_out = 0
-    for i in arcs:
-        out_t.append(tags[prev:i])
-        out_d.append(data[prev:i])
-        new_index[prev:i + 1] = np.arange(n_out, n_out + (i - prev) + 1)
-        n_out += i - prev
-        row = data[i]
-        k = L.svgr_arc_to_cubics(*map(float, row[:7]), buf.ctypes.data, 64)
-        if k < 0:
-            raise ValueError("arc sweeps more than 16 pi")
-        out_t.append(np.full(k, S.PATH_CUBIC, dtype=np.uint8))
-        out_d.append(buf[:k].copy())
-        n_out += k
-        prev = i + 1
-    out_t.append(tags[prev:])
-    out_d.append(data[prev:])
-    new_index[prev:] = np.arange(n_out, n_out + (len(tags) - prev) + 1)
-    return (np.concatenate(out_t), np.concatenate(out_d).reshape(-1, 8),
-            new_index[np.asarray(sub_off, dtype=np.int64)].astype(np.int32))
+    n = len(tags)
+    cap = n + 64 * n_arc
+    out_t = np.empty(cap, dtype=np.uint8)
+    out_d = np.empty((cap, 8), dtype=np.float64)
+    new_index = np.empty(n + 1, dtype=np.int64)
+    tags = np.ascontiguousarray(tags, dtype=np.uint8)
+    data = np.ascontiguousarray(data, dtype=np.float64)
+    m = _lib.lib().svgr_expand_arcs(tags.ctypes.data, data.ctypes.data, n, out_t.ctypes.data, out_d.ctypes.data, cap,
+                                    new_index.ctypes.data)
+    if m < 0:
+        raise ValueError("arc sweeps more than 16 pi")
+    return out_t[:m].copy(), out_d[:m].copy(), new_index[np.asarray(sub_off, dtype=np.int64)].astype(np.int32)
 
 
 def device_path(path):
@@ -750,37 +739,45 @@ class Encoder:
             p.seg_tag = np.concatenate(self.seg_tag)
             p.seg_data = np.ascontiguousarray(np.concatenate(self.seg_data).reshape(-1, 8))
             p.seg_path = np.concatenate(self.seg_path)
-        p.paths = np.zeros(len(self.paths), _lib.PATH_DT)
-        for i, (m, vp, rule) in enumerate(self.paths):
-            rec = p.paths[i]
-            rec["m"] = m
-            if vp is not None:
-                rec["viewport"] = vp
-                rec["has_viewport"] = 1
-            rec["fill_rule"] = rule
-        p.strokes = np.zeros(len(self.strokes), _lib.STROKE_DT)
-        for i, (hw, sb, se, cap, join, pid) in enumerate(self.strokes):
-            p.strokes[i] = (hw, sb, se, cap, join, pid, 0)
+        # records are built column-wise: one numpy call per field instead of one per record
+        n = len(self.paths)
+        p.paths = np.zeros(n, _lib.PATH_DT)
+        if n:
+            p.paths["m"] = np.asarray([m for m, _vp, _r in self.paths], dtype=np.float64).reshape(n, 6)
+            p.paths["has_viewport"] = [vp is not None for _m, vp, _r in self.paths]
+            p.paths["viewport"] = [vp if vp is not None else (0, 0, 0, 0) for _m, vp, _r in self.paths]
+            p.paths["fill_rule"] = [r for _m, _vp, r in self.paths]
+        n = len(self.strokes)
+        p.strokes = np.zeros(n, _lib.STROKE_DT)
+        if n:
+            cols = list(zip(*self.strokes))
+            for name, col in zip(("half_width", "sub_begin", "sub_end", "cap", "join", "path"), cols):
+                p.strokes[name] = col
         p.stroke_sub_off = np.asarray(self.s_sub_off, dtype=np.int32)
         p.stroke_sub_job = np.asarray(self.s_sub_job, dtype=np.int32)
         if self.s_tag:
             p.stroke_tag = np.concatenate(self.s_tag)
             p.stroke_data = np.ascontiguousarray(np.concatenate(self.s_data).reshape(-1, 8))
             p.stroke_seg_job = np.concatenate(self.s_seg_job)
-        p.paints = np.zeros(len(self.paints), _lib.PAINT_DT)
-        for i, rec in enumerate(self.paints):
-            row = p.paints[i]
-            for k, v in rec.items():
-                row[k] = v
-        p.stops = np.zeros(len(self.stops), _lib.STOP_DT)
-        for i, (o, c, inv) in enumerate(self.stops):
-            p.stops[i]["offset"] = o
-            p.stops[i]["color"] = c
-            p.stops[i]["inv_span"] = inv
+        n = len(self.paints)
+        p.paints = np.zeros(n, _lib.PAINT_DT)
+        if n:
+            for name in ("kind", "spread", "stop_off", "stop_cnt", "has_m2", "flag", "pat_r0", "pat_c0", "pat_rows",
+                         "pat_cols", "pat_node", "color", "m1", "m2", "g"):
+                p.paints[name] = [rec[name] for rec in self.paints]
+        n = len(self.stops)
+        p.stops = np.zeros(n, _lib.STOP_DT)
+        if n:
+            p.stops["offset"] = [o for o, _c, _i in self.stops]
+            p.stops["color"] = [c for _o, c, _i in self.stops]
+            p.stops["inv_span"] = [i for _o, _c, i in self.stops]
         p.n_focal = self.n_focal
-        p.nodes = np.zeros(len(self.nodes), _lib.NODE_DT)
-        for i, (tag, a, b, c, d, off, cnt, flags, f) in enumerate(self.nodes):
-            p.nodes[i] = (tag, a, b, c, d, off, cnt, flags, f)
+        n = len(self.nodes)
+        p.nodes = np.zeros(n, _lib.NODE_DT)
+        if n:
+            cols = list(zip(*self.nodes))
+            for name, col in zip(("tag", "a", "b", "c", "d", "child_off", "child_cnt", "flags", "f"), cols):
+                p.nodes[name] = col
         p.children = np.asarray(self.children, dtype=np.int32)
         p.kernels = np.zeros(len(self.kernels), _lib.KERNEL_DT)
         for i, k in enumerate(self.kernels):
