@@ -210,15 +210,29 @@ compose_kernel(RenderTables T, const OpRec *__restrict__ ops, const int *__restr
                             for (int k = 0; k < CMP_PX; k++)
                                 v[k] = scale4(col, a[k]);
                         } else {
-                            const float4 *pat = reinterpret_cast<const float4 *>(T.layers + s.off2);
                             const StopRec *st = T.stops + pr.stop_off;
+                            if (pr.kind == PAINT_PATTERN) {
+                                const float4 *pat = reinterpret_cast<const float4 *>(T.layers + s.off2);
 #pragma unroll
-                            for (int k = 0; k < CMP_PX; k++) {
-                                v[k] = f4(0.f, 0.f, 0.f, 0.f);
-                                if (a[k] != 0.f) {
-                                    float4 q = paint_eval(T, pr, st, x0 + 8.0 * k, y0, pat, s.stride2);
-                                    v[k] = scale4(q, a[k]);
+                                for (int k = 0; k < CMP_PX; k++) {
+                                    v[k] = f4(0.f, 0.f, 0.f, 0.f);
+                                    if (a[k] != 0.f)
+                                        v[k] = scale4(paint_eval(T, pr, st, x0 + 8.0 * k, y0, pat, s.stride2), a[k]);
                                 }
+                            } else {
+                                // gradient: parameters of the covered pixels first, then one pass over the stops
+                                double t[CMP_PX];
+                                bool need[CMP_PX];
+#pragma unroll
+                                for (int k = 0; k < CMP_PX; k++) {
+                                    t[k] = 0.0, need[k] = false;
+                                    if (a[k] != 0.f)
+                                        t[k] = grad_param(T, pr, x0 + 8.0 * k, y0, &need[k]);
+                                }
+                                grad_colors<CMP_PX>(t, need, st, pr.stop_cnt, v);
+#pragma unroll
+                                for (int k = 0; k < CMP_PX; k++)
+                                    v[k] = scale4(v[k], a[k]);
                             }
                         }
                     } else {

@@ -214,6 +214,76 @@ __device__ __forceinline__ float4 paint_eval(const RenderTables &T, const PaintR
     return grad_color(grad_spread(t, p.spread), stops, p.stop_cnt);
 }
 
+// Gradient parameter only (after spread), or NaN-free "invalid" -> *ok = false (transparent pixel)
+__device__ __forceinline__ double grad_param(const RenderTables &T, const PaintRec &p, double x, double y, bool *ok)
+{
+    *ok = true;
+    double t;
+    if (p.kind == PAINT_LINEAR) {
+        t = fma(p.g[0], x, fma(p.g[1], y, p.g[2]));
+    } else if (p.kind == PAINT_RADIAL) {
+        double ox = fma(p.m1[0], x, fma(p.m1[1], y, p.m1[2]));
+        double oy = fma(p.m1[3], x, fma(p.m1[4], y, p.m1[5]));
+        t = sqrt(fma(ox, ox, oy * oy));
+    } else {
+        double b;
+        double det = focal_det(p, x, y, &b);
+        bool any_neg = T.focal_flags[p.flag] != 0;
+        if (any_neg && det < 0) {
+            *ok = false;
+            return 0.0;
+        }
+        double sq = sqrt(det);
+        double t1 = (b + sq) * p.g[7], t2 = (b - sq) * p.g[7];
+        t = (t1 != t1 || t2 != t2) ? __longlong_as_double(0x7ff8000000000000ll) : (t1 > t2 ? t1 : t2);
+        if (any_neg && p.g[6] != 0.0 && !(t > p.g[5])) {
+            *ok = false;
+            return 0.0;
+        }
+    }
+    return grad_spread(t, p.spread);
+}
+
+// grad_interpolate for N pixels at once with the stop loop outermost: a stop's offsets and colours are
+// loaded once for all N pixels of the thread instead of once per pixel.  t: spread parameter, need[k]:
+// pixel k wants a colour.  out[k] is written for every k (zero when !need[k] or no interval matches).
+template <int N>
+__device__ __forceinline__ void grad_colors(const double *t, const bool *need, const StopRec *__restrict__ st, int n,
+                                            float4 *out)
+{
+    bool open[N];  // still looking for its interval
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+        out[k] = f4(0.f, 0.f, 0.f, 0.f);
+        open[k] = need[k];
+    }
+    {
+        const double o_min = st[0].offset, o_max = st[n - 1].offset;
+        const float4 c_min = f4(st[0].color[0], st[0].color[1], st[0].color[2], st[0].color[3]);
+        const float4 c_max = f4(st[n - 1].color[0], st[n - 1].color[1], st[n - 1].color[2], st[n - 1].color[3]);
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+            if (open[k] && t[k] <= o_min)
+                out[k] = c_min, open[k] = false;
+            else if (open[k] && t[k] > o_max)
+                out[k] = c_max, open[k] = false;
+        }
+    }
+    for (int j = 0; j + 1 < n; j++) {
+        const double o0 = st[j].offset, o1 = st[j + 1].offset, inv = st[j].inv_span;
+        const float4 c0 = f4(st[j].color[0], st[j].color[1], st[j].color[2], st[j].color[3]);
+        const float4 dc = f4(st[j + 1].color[0] - c0.x, st[j + 1].color[1] - c0.y, st[j + 1].color[2] - c0.z,
+                             st[j + 1].color[3] - c0.w);
+#pragma unroll
+        for (int k = 0; k < N; k++)
+            if (open[k] && t[k] > o0 && t[k] <= o1) {
+                const float ratio = (float)((t[k] - o0) * inv);
+                float4 q = madd4(dc, ratio, c0);
+                out[k] = f4(out[k].x + q.x, out[k].y + q.y, out[k].z + q.z, out[k].w + q.w);
+            }
+    }
+}
+
 // ---- source access, split so that a thread can issue the loads of several pixels before using them
 __device__ __forceinline__ bool src_hits(const SrcRec &s, int r, int c)
 {
