@@ -21,7 +21,6 @@ or a GPU they raise.
 from __future__ import annotations
 
 import struct
-import warnings
 import zlib
 from typing import NamedTuple
 
@@ -162,7 +161,7 @@ class Layer(NamedTuple):
         return canvas_to_png(layer.image, output)
 
 
-def _read(eng, enc, node, hull_paths=None):
+def _read(eng, enc, node):
     """Materialise `node`, run the program, read the layer back."""
     if enc._is_empty(node):
         return None

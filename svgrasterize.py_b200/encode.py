@@ -16,7 +16,6 @@ asks the engine to flatten the target and reduce its end points
 from __future__ import annotations
 
 import ctypes as C
-import math
 import warnings
 
 import numpy as np
