@@ -156,7 +156,9 @@ struct svgr_ctx {
 
     // ---- resident program (device) + host copies of what the planner needs
     bool have_program = false;
-    const svgr_program *pending = nullptr;  // host tables of this program still to be copied (finish_load)
+    const svgr_program *pending = nullptr;
+    bool structure_ready = false;  // node_uses / chunk_bounds computed for the loaded program
+    std::vector<int> node_uses, chunk_bounds;  // host tables of this program still to be copied (finish_load)
     long long n_seg = 0;
     int n_path = 0, n_stroke = 0, n_stroke_sub = 0, n_paint = 0, n_stop = 0, n_focal = 0, n_node = 0;
     long long n_stroke_seg = 0;
@@ -218,7 +220,6 @@ struct Planner {
     svgr_ctx *ctx;
     std::string err;
     long long layer_top = 0;
-    std::vector<int> uses_own;
     const std::vector<int> *uses_p = nullptr;  // how many nodes read each node (shared, read-only while planning)
     std::vector<PlannedOp> sorted_ops;
     std::vector<Val> scratch_vals;
@@ -803,9 +804,20 @@ struct Planner {
         c->n_focal_blocks = 0, c->layer_pixels = 0, c->n_levels = 0;
         c->compose_bytes = 0, c->canvas_pixels = 0;
         n_focal_blocks = 0, layer_pixels = 0, layer_top = 0;
-        std::vector<int> &uses = uses_own;
+        // reference counts and chunk boundaries depend on the program only: computed once per program
+        if (!c->structure_ready)
+            analyse_structure();
+        uses_p = &c->node_uses;
+        chunk_bounds = c->chunk_bounds;
+        c->vals.resize(c->n_node);  // every entry is assigned by plan_range before anyone reads it
+        return true;
+    }
+
+    void analyse_structure()
+    {
+        svgr_ctx *c = ctx;
+        std::vector<int> &uses = c->node_uses;
         uses.assign(c->n_node, 0);
-        uses_p = &uses;
         std::vector<int> cuts;  // indices right after a canvas node: candidate scene boundaries
         for (int i = 0; i < c->n_node; i++) {
             const svgr_node &n = c->h_nodes[i];
@@ -821,9 +833,9 @@ struct Planner {
             if (n.tag == SVGR_N_CANVAS)
                 cuts.push_back(i + 1);
         }
-        c->vals.resize(c->n_node);  // every entry is assigned by plan_range before anyone reads it
         // chunks of at least 4096 nodes, at most 8 of them, cut where no reference crosses
-        chunk_bounds.assign(1, 0);
+        std::vector<int> &bounds = c->chunk_bounds;
+        bounds.assign(1, 0);
         int max_chunks = 8;
         if (const char *e = getenv("SVGR_CHUNKS"))  // 1: plan everything before the first compose launch (clean kernel timings)
             max_chunks = std::max(1, atoi(e));
@@ -845,12 +857,12 @@ struct Planner {
                 if (it == cuts.end())
                     break;
                 int cut = *it;
-                if (cut > chunk_bounds.back() && cut < c->n_node && min_ref[cut] >= cut)
-                    chunk_bounds.push_back(cut);
+                if (cut > bounds.back() && cut < c->n_node && min_ref[cut] >= cut)
+                    bounds.push_back(cut);
             }
         }
-        chunk_bounds.push_back(c->n_node);
-        return true;
+        bounds.push_back(c->n_node);
+        c->structure_ready = true;
     }
 
     int n_chunks() const { return (int)chunk_bounds.size() - 1; }
@@ -1083,6 +1095,7 @@ static int load_program(svgr_ctx *ctx, const svgr_program *p, cudaStream_t s, bo
     }
     ctx->have_program = true;
     ctx->planned = ctx->covered = ctx->composed = false;
+    ctx->structure_ready = false;
     ctx->pending = p;
     if (host_only)
         return finish_load(ctx);
