@@ -131,3 +131,48 @@ def test_random_scene_matches_oracle(seed):
         return
     diff = np.abs(got.astype(int) - ref.astype(int))
     assert diff.max() <= 1, (seed, int(diff.max()), int((diff > 1).sum()))  # 400 seeds measured: worst 1 LSB
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_geometry_is_bit_exact(seed):
+    """Edge lists (per-path multisets) and stroke outlines of random paths under random transforms are
+    bit-identical to the oracle's (which is pinned bit-exactly to the reference)."""
+    from oracle import geometry
+    from oracle.stroke import stroke_path
+    from svgrasterize_b200 import _lib, encode, scene as S, synth
+    from svgrasterize_b200.engine import default_engine
+
+    rng = np.random.default_rng(9000 + seed)
+    eng = default_engine()
+    paths = [_rand_path(rng, S, synth) for _ in range(6)]
+    trs = [S.Transform().matrix(0, 1, 0, 1, 0, 0) @ S.Transform().translate(*rng.uniform(-20, 20, 2))
+           .rotate(rng.uniform(-3, 3)).scale(*rng.uniform(0.3, 9.0, 2)).skew(rng.uniform(-0.3, 0.3), 0.0) for _ in paths]
+    enc = encode.Encoder(eng)
+    for p, t in zip(paths, trs):
+        enc.add_fill_path(p, t, None, None)
+    strokes = [(paths[i], float(rng.uniform(0.2, 8)), (None, "round", "square")[i % 3], (None, "round", "bevel")[(i // 2) % 3])
+               for i in range(3)]
+    for p, w, cap, join in strokes:
+        enc.add_stroke_path(p, S.Transform(), w, cap, join, None)
+    prog = enc.finish()
+    try:
+        eng.render(prog, stop=_lib.STOP_FLATTEN)
+    except TypeError:
+        for p, w, cap, join in strokes:  # at least one of them must be the reference's degenerate case
+            try:
+                stroke_path(p, w, cap, join)
+            except TypeError:
+                return
+        raise
+    edges, edge_path = eng.edges()
+    for i, (p, t) in enumerate(zip(paths, trs)):
+        mine = edges[edge_path == i]
+        ref = geometry.path_edges(p, t).reshape(-1, 4)
+        mine = mine[np.lexsort(mine.T[::-1])]
+        ref = ref[np.lexsort(ref.T[::-1])]
+        assert mine.shape == ref.shape and np.array_equal(mine.view(np.uint64), ref.view(np.uint64)), (seed, i)
+    tag, data, path, sub = eng.outline()
+    for k, (p, w, cap, join) in enumerate(strokes):
+        sel = path == len(paths) + k
+        rt, rd, _rs = encode.path_arrays(stroke_path(p, w, cap, join))
+        assert np.array_equal(tag[sel], rt) and np.array_equal(data[sel].view(np.uint64), rd.view(np.uint64)), (seed, k)
