@@ -298,7 +298,11 @@ def run_gpu(opts):
     ms_cov = acc.get("ms_coverage", 0.0) / opts.steps
     ms_cmp = acc.get("ms_compose_busy", 0.0) / opts.steps  # device time of the compose launches themselves
     cov_gbs = st["coverage_bytes"] / (ms_cov * 1e-3) / 1e9 if ms_cov > 0 else 0.0
-    cmp_gbs = st["compose_bytes"] / (ms_cmp * 1e-3) / 1e9 if ms_cmp > 0 else 0.0
+    # compose: SURVEY 8(d) counts one HBM pass per layer (36 B per layer pixel composited + 20 B per quantised
+    # canvas pixel); the fold keeps the destination in registers, so the bytes it must move are fewer -- both
+    # are reported, `achieved` is the 8(d) figure the contract asks for, `achieved_moved` the stricter one
+    cmp_gbs = st["compose_bytes_8d"] / (ms_cmp * 1e-3) / 1e9 if ms_cmp > 0 else 0.0
+    cmp_moved_gbs = st["compose_bytes"] / (ms_cmp * 1e-3) / 1e9 if ms_cmp > 0 else 0.0
     traffic = {}
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
@@ -316,16 +320,22 @@ def run_gpu(opts):
     kernels = {
         "compose_kernel": {"bound": "hbm", "achieved": cmp_gbs, "peak": peak, "unit": "GB/s", "frac": cmp_gbs / peak,
                            "traffic": traffic_of("compose_kernel"), "ms_per_step": ms_cmp,
-                           "launches_per_step": st["n_launches"] - 1, "algorithmic_bytes_per_step": st["compose_bytes"]},
+                           "launches_per_step": st["n_launches"] - 1,
+                           "algorithmic_bytes_per_step": st["compose_bytes_8d"],
+                           "achieved_moved": cmp_moved_gbs, "frac_moved": cmp_moved_gbs / peak,
+                           "moved_bytes_per_step": st["compose_bytes"]},
         "coverage_kernel": {"bound": "hbm", "achieved": cov_gbs, "peak": peak, "unit": "GB/s", "frac": cov_gbs / peak,
                             "traffic": traffic_of("coverage_kernel"), "ms_per_step": ms_cov, "launches_per_step": 1,
                             "algorithmic_bytes_per_step": st["coverage_bytes"]},
     }
     dominant = "compose_kernel" if ms_cmp >= ms_cov else "coverage_kernel"
     roofline = dict(kernels[dominant], kernel=dominant, peak_source=peak_src,
-                    note="achieved = algorithmic bytes per step / CUDA-event time of the kernel's launches in a step "
-                         "(first to last launch of every plan chunk, on the launch stream); traffic = measured DRAM "
-                         "bytes per step (ncu, profiles/traffic.json)")
+                    note="achieved = algorithmic bytes per step (SURVEY 8(d): compose 36 B per layer pixel composited "
+                         "+ 20 B per canvas pixel quantised; coverage 36 B per binned edge + 4 B per mask pixel) / "
+                         "CUDA-event time of the kernel's launches in a step (first to last launch of every plan "
+                         "chunk, on the launch stream); achieved_moved = the bytes the fused fold must actually move "
+                         "(every source pixel read once, every output pixel written once) / the same time; traffic "
+                         "= measured DRAM bytes per step (ncu, profiles/traffic.json)")
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": opts.steps, "warmup": opts.warmup,

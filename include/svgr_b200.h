@@ -169,6 +169,10 @@ typedef struct svgr_stats {
     float ms_compose_busy; /* sum over plan chunks of first-launch -> last-launch device time: ms_compose minus
                               the waits for the host planner */
     float pad2;
+    int64_t compose_bytes_8d; /* the same compose work in SURVEY.md 8(d)'s units: 36 B per layer pixel composited
+                                 (one HBM pass per layer: 4 B coverage + 16 B destination read + 16 B written) + 20 B
+                                 per quantised canvas pixel; compose_bytes is less because the fold keeps the
+                                 destination in registers */
 } svgr_stats;
 
 typedef struct svgr_ctx svgr_ctx;

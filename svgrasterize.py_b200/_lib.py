@@ -68,7 +68,8 @@ class Stats(C.Structure):
                [(n, C.c_float) for n in ("ms_total", "ms_h2d", "ms_stroke", "ms_flatten", "ms_plan", "ms_bin",
                                          "ms_coverage", "ms_compose", "ms_canvas", "ms_d2h")] + \
                [("retries", C.c_int32), ("pad", C.c_int32), ("host_plan_masks_ms", C.c_float),
-                ("host_plan_nodes_ms", C.c_float), ("ms_compose_busy", C.c_float), ("pad2", C.c_float)]
+                ("host_plan_nodes_ms", C.c_float), ("ms_compose_busy", C.c_float), ("pad2", C.c_float),
+                ("compose_bytes_8d", C.c_int64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_ if not n.startswith("pad")}

@@ -196,7 +196,7 @@ struct svgr_ctx {
     std::vector<Launch> launches;
     int n_focal_blocks = 0;
     long long n_bands = 0, n_cov_tiles = 0, cov_floats = 0, layer_floats = 0;
-    long long mask_pixels = 0, layer_pixels = 0, compose_bytes = 0, canvas_pixels = 0;
+    long long mask_pixels = 0, layer_pixels = 0, compose_bytes = 0, compose_bytes_8d = 0, canvas_pixels = 0;
     int n_levels = 0;
     DevBuf d_masks, d_band_cnt, d_band_off, d_band_cur, d_bin_edges, d_cov, d_layers, d_ops, d_srcs, d_focal_jobs,
         d_focal_flags, d_canvas, d_q, d_tile_map, d_tile_mask;
@@ -802,7 +802,7 @@ struct Planner {
         svgr_ctx *c = ctx;
         c->ops.clear(), c->srcs.clear(), c->focal_jobs.clear(), c->launches.clear();
         c->n_focal_blocks = 0, c->layer_pixels = 0, c->n_levels = 0;
-        c->compose_bytes = 0, c->canvas_pixels = 0;
+        c->compose_bytes = 0, c->compose_bytes_8d = 0, c->canvas_pixels = 0;
         n_focal_blocks = 0, layer_pixels = 0, layer_top = 0;
         // reference counts and chunk boundaries depend on the program only: computed once per program
         if (!c->structure_ready)
@@ -947,11 +947,18 @@ struct Planner {
                 L.smem = std::max(L.smem, smem);
                 // algorithmic traffic: every output pixel written once, every source pixel read once
                 const PlannedOp &po = c->ops[j];
+                // ... and the same work in SURVEY 8(d)'s units: 36 B per layer pixel composited (4 B coverage +
+                // 16 B destination read + 16 B written, one pass per layer), 20 B per quantised canvas pixel;
+                // stencil passes move what they must either way
+                const bool fold = po.cls == 0 || po.cls == 3;
                 if (po.cls == 3) {
                     c->canvas_pixels += (long long)o.rows * o.cols;
                     c->compose_bytes += (long long)o.rows * o.cols * 4;  // RGBA8 out
+                    c->compose_bytes_8d += (long long)o.rows * o.cols * 20;
                 } else {
                     c->compose_bytes += (long long)o.rows * o.cols * o.out_ch * 4;
+                    if (!fold)
+                        c->compose_bytes_8d += (long long)o.rows * o.cols * o.out_ch * 4;
                 }
                 for (int q = 0; q < o.src_cnt; q++) {
                     const SrcRec &sr = c->srcs[o.src_off + q];
@@ -962,9 +969,12 @@ struct Planner {
                     } else {
                         rr = sr.rows, cc = sr.cols;
                     }
-                    if (rr > 0 && cc > 0)
-                        c->compose_bytes +=
+                    if (rr > 0 && cc > 0) {
+                        const long long moved =
                             rr * cc * ((sr.kind == SRC_L4 || sr.kind == SRC_MOD_L4A || sr.kind == SRC_MOD_LUMA) ? 16 : 4);
+                        c->compose_bytes += moved;
+                        c->compose_bytes_8d += fold ? rr * cc * 36 : moved;  // a fused clip / mask is a layer pass too
+                    }
                 }
                 j++;
             }
@@ -1514,6 +1524,7 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
         stats->mask_pixels = ctx->mask_pixels, stats->layer_pixels = ctx->layer_pixels;
         stats->coverage_bytes = ctx->cov_floats * 4 + ctx->n_binned * 36;
         stats->compose_bytes = ctx->compose_bytes, stats->canvas_pixels = ctx->canvas_pixels;
+        stats->compose_bytes_8d = ctx->compose_bytes_8d;
         stats->n_kernels = n_kernels;
         stats->host_plan_masks_ms = std::chrono::duration<float, std::milli>(t_h1 - t_h0).count();
         stats->host_plan_nodes_ms = host_nodes_ms;

@@ -84,6 +84,10 @@ compose_kernel(RenderTables T, const OpRec *__restrict__ ops, const int *__restr
     __shared__ __align__(16) SrcRec s_src[CMP_CAP + 1];
     __shared__ __align__(16) PaintRec s_paint[CMP_CAP + 1];
     __shared__ int s_idx[CMP_CAP + 1];
+    // per staged source, relative to this tile: bit r of s_rm = tile row r is inside the source (and the op), bit c
+    // of s_cm likewise for columns, s_toff = element offset of the tile's top-left pixel in the source's storage
+    __shared__ unsigned s_rm[CMP_CAP + 1], s_cm[CMP_CAP + 1];
+    __shared__ int s_toff[CMP_CAP + 1];
     __shared__ int s_n, s_next;
 
     const int tid = threadIdx.x;
@@ -138,6 +142,11 @@ compose_kernel(RenderTables T, const OpRec *__restrict__ ops, const int *__restr
                     int pos = n + __popc(m & ((1u << tx) - 1));
                     s_src[pos] = rec;
                     s_idx[pos] = i;
+                    const int ra = max(rec.r0, tile_r0), rb = min(rec.r0 + rec.rows, tile_r1);
+                    const int ca = max(rec.c0, tile_c0), cb = min(rec.c0 + rec.cols, tile_c1);
+                    s_rm[pos] = rb > ra ? (0xffffffffu >> (32 - (rb - ra))) << (ra - tile_r0) : 0u;
+                    s_cm[pos] = cb > ca ? (0xffffffffu >> (32 - (cb - ca))) << (ca - tile_c0) : 0u;
+                    s_toff[pos] = (tile_r0 - rec.br0) * rec.stride + (tile_c0 - rec.bc0);
                 }
                 n += __popc(m);
             }
@@ -175,29 +184,23 @@ compose_kernel(RenderTables T, const OpRec *__restrict__ ops, const int *__restr
                 if (s.kind >= SRC_MOD_COV)
                     continue;  // consumed together with its owner below
                 const bool first = s_idx[j] == 0;
-                const int dr = r0 - s.r0, dc = c - s.c0;
-                unsigned live = 0;
-                if ((unsigned)dc < (unsigned)s.cols) {
-#pragma unroll
-                    for (int k = 0; k < CMP_PX; k++)
-                        if ((unsigned)(dr + 8 * k) < (unsigned)s.rows && lr0 + 8 * k < op.rows)
-                            live |= 1u << k;
-                }
+                // pixel k of this thread (row ty + 8 k of the tile) is inside the source: bit 8 k of `live`
+                const unsigned live = ((s_rm[j] >> ty) & 0x01010101u) * ((s_cm[j] >> tx) & 1u);
                 if (!live && skip_outside && !first)
                     continue;
-                const int base = (r0 - s.br0) * s.stride + (c - s.bc0), step = 8 * s.stride;  // a layer has < 2^31 px
+                const int base = s_toff[j] + ty * s.stride + tx, step = 8 * s.stride;  // a layer has < 2^31 px
                 float4 v[CMP_PX];
                 if (s.kind == SRC_L4) {
                     const float4 *p = reinterpret_cast<const float4 *>(T.layers + s.off);
 #pragma unroll
                     for (int k = 0; k < CMP_PX; k++)
-                        v[k] = (live >> k & 1) ? __ldg(p + (base + k * step)) : f4(0.f, 0.f, 0.f, 0.f);
+                        v[k] = (live >> (8 * k) & 1) ? __ldg(p + (base + k * step)) : f4(0.f, 0.f, 0.f, 0.f);
                 } else {
                     const float *p = (s.kind == SRC_L1 ? T.layers : T.cov) + s.off;
                     float a[CMP_PX];
 #pragma unroll
                     for (int k = 0; k < CMP_PX; k++)
-                        a[k] = (live >> k & 1) ? __ldg(p + (base + k * step)) : 0.f;
+                        a[k] = (live >> (8 * k) & 1) ? __ldg(p + (base + k * step)) : 0.f;
                     // nothing of the path in these four pixels (the inside of a stroked ring, the corners of a
                     // blob's box): an all-zero source is the identity of the over blend
                     if (skip_outside && !first && a[0] == 0.f && a[1] == 0.f && a[2] == 0.f && a[3] == 0.f)
@@ -250,7 +253,7 @@ compose_kernel(RenderTables T, const OpRec *__restrict__ ops, const int *__restr
                 if (s.kind != SRC_L1 && s.kind != SRC_COV && !conv_is_identity(s.conv)) {
 #pragma unroll
                     for (int k = 0; k < CMP_PX; k++)
-                        if (live >> k & 1)
+                        if (live >> (8 * k) & 1)
                             v[k] = convert_px(v[k], s.conv);
                 }
                 if (j + 1 < n && s_src[j + 1].kind >= SRC_MOD_COV) {
@@ -258,7 +261,7 @@ compose_kernel(RenderTables T, const OpRec *__restrict__ ops, const int *__restr
                     const SrcRec &md = s_src[j + 1];
 #pragma unroll
                     for (int k = 0; k < CMP_PX; k++)
-                        if (live >> k & 1) {
+                        if (live >> (8 * k) & 1) {
                             const float m = mod_value(T, md, r0 + 8 * k, c);
                             v[k] = scale4(v[k], m);
                         }
