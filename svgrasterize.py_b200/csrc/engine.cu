@@ -199,7 +199,7 @@ struct svgr_ctx {
     long long mask_pixels = 0, layer_pixels = 0, compose_bytes = 0, compose_bytes_8d = 0, canvas_pixels = 0;
     int n_levels = 0;
     DevBuf d_masks, d_band_cnt, d_band_off, d_band_cur, d_bin_edges, d_cov, d_layers, d_ops, d_srcs, d_focal_jobs,
-        d_focal_flags, d_canvas, d_q, d_tile_map, d_tile_mask;
+        d_focal_flags, d_canvas, d_q, d_tile_map, d_tile_rec, d_bin_data;
     long long bin_cap = 0;
     long long n_binned = 0;
     bool planned = false, covered = false, composed = false;
@@ -1296,7 +1296,8 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
     CK(ctx->d_band_cur.ensure((size_t)(NB + 1) * 4));
     CK(ctx->d_scan_tmp.ensure((size_t)(NB / 2048 + 4) * 4));
     CK(ctx->d_bin_edges.ensure((size_t)ctx->bin_cap * 4));
-    CK(ctx->d_tile_mask.ensure((size_t)std::max<long long>(ctx->n_cov_tiles, 1) * 4));
+    CK(ctx->d_bin_data.ensure((size_t)ctx->bin_cap * 32));
+    CK(ctx->d_tile_rec.ensure((size_t)std::max<long long>(ctx->n_cov_tiles, 1) * sizeof(TileRec)));
     CK(cudaMemsetAsync(ctx->d_band_cnt.p, 0, (size_t)(NB + 1) * 4, s));
     CK(cudaMemsetAsync(ctx->d_band_cur.p, 0, (size_t)(NB + 1) * 4, s));
     if (NB > 0 && ctx->n_edges > 0) {
@@ -1306,16 +1307,16 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
                                    &d_st->binned_total, s);
         svgr_launch_bin_fill(ctx->d_edges.as<double>(), ctx->d_edge_path.as<uint32_t>(), (unsigned long long)ctx->n_edges,
                              ctx->d_masks.as<MaskRec>(), ctx->d_band_off.as<int>(), ctx->d_band_cur.as<int>(),
-                             ctx->d_bin_edges.as<uint32_t>(), ctx->bin_cap, SM, s);
+                             ctx->d_bin_edges.as<uint32_t>(), ctx->d_bin_data.as<double>(), ctx->bin_cap, SM, s);
         n_kernels += 4 + ((NB + 1) > 2048 ? 1 : 0);
     } else {
         CK(cudaMemsetAsync(ctx->d_band_off.p, 0, (size_t)(NB + 1) * 4, s));
     }
     mark(5);
     // ---- coverage
-    svgr_launch_coverage(ctx->d_edges.as<double>(), ctx->d_masks.as<MaskRec>(), ctx->n_path, (int)ctx->n_cov_tiles,
-                         ctx->d_tile_mask.as<int>(), ctx->d_band_off.as<int>(), ctx->d_band_cnt.as<int>(),
-                         ctx->d_bin_edges.as<uint32_t>(), ctx->bin_cap, ctx->d_cov.as<float>(), s);
+    svgr_launch_coverage(ctx->d_masks.as<MaskRec>(), ctx->n_path, (int)ctx->n_cov_tiles, ctx->d_tile_rec.as<TileRec>(),
+                         ctx->d_band_off.as<int>(), ctx->d_band_cnt.as<int>(), ctx->d_bin_data.as<double>(), ctx->bin_cap,
+                         ctx->d_cov.as<float>(), s);
     ctx->covered = true;
     n_kernels += ctx->n_cov_tiles > 0 ? 2 : 0;
     mark(6);
@@ -1605,7 +1606,7 @@ void svgr_destroy(svgr_ctx *ctx)
                       &ctx->d_osub, &ctx->d_ocount, &ctx->d_edges, &ctx->d_edge_path, &ctx->d_minmax, &ctx->d_boxes,
                       &ctx->d_minmax_f64, &ctx->d_status, &ctx->d_masks, &ctx->d_band_cnt, &ctx->d_band_off,
                       &ctx->d_band_cur, &ctx->d_bin_edges, &ctx->d_cov, &ctx->d_layers, &ctx->d_ops, &ctx->d_srcs,
-                      &ctx->d_focal_jobs, &ctx->d_focal_flags, &ctx->d_canvas, &ctx->d_q, &ctx->d_tile_map, &ctx->d_tile_mask};
+                      &ctx->d_focal_jobs, &ctx->d_focal_flags, &ctx->d_canvas, &ctx->d_q, &ctx->d_tile_map, &ctx->d_tile_rec, &ctx->d_bin_data};
     for (DevBuf *b : bufs)
         b->release();
     ctx->pin_boxes.release(), ctx->pin_status.release(), ctx->pin_plan.release(), ctx->pin_out.release();

@@ -190,7 +190,7 @@ __global__ void bin_count_kernel(const double *__restrict__ edges, const uint32_
 __global__ void bin_fill_kernel(const double *__restrict__ edges, const uint32_t *__restrict__ edge_path,
                                 unsigned long long n_edges, const MaskRec *__restrict__ masks,
                                 const int *__restrict__ band_off, int *__restrict__ band_cursor,
-                                uint32_t *__restrict__ bin_edges, long long cap)
+                                uint32_t *__restrict__ bin_edges, double2 *__restrict__ bin_data, long long cap)
 {
     for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n_edges;
          i += (unsigned long long)gridDim.x * blockDim.x) {
@@ -204,8 +204,12 @@ __global__ void bin_fill_kernel(const double *__restrict__ edges, const uint32_t
         for (int k = b0; k <= b1; k++) {
             int band = m.band_base + k;
             long long pos = (long long)band_off[band] + atomicAdd(band_cursor + band, 1);
-            if (pos < cap)  // an undersized list is detected and repaired by the host after the fact
+            if (pos < cap) {  // an undersized list is detected and repaired by the host after the fact
                 bin_edges[pos] = (uint32_t)i;
+                // the edge itself travels with its index: the coverage CTA reads its band's edges as one
+                // contiguous run (32 B each) instead of gathering them through the index list
+                bin_data[2 * pos] = a, bin_data[2 * pos + 1] = b;
+            }
         }
     }
 }
@@ -286,25 +290,23 @@ __device__ __forceinline__ float fill_rule_apply(float m, int rule)
 }
 
 __global__ void __launch_bounds__(COV_THREADS)
-coverage_kernel(const double *__restrict__ edges, const MaskRec *__restrict__ masks,
-                const int *__restrict__ tile_mask, const int *__restrict__ band_off,
-                const int *__restrict__ band_cnt, const uint32_t *__restrict__ bin_edges, long long bin_cap,
-                float *__restrict__ cov)
+coverage_kernel(const TileRec *__restrict__ tiles, const double2 *__restrict__ bin_data, float *__restrict__ cov)
 {
     __shared__ __align__(16) float trace[SVGR_BAND_ROWS][SVGR_TILE_COLS];
     __shared__ double s_r0[COV_THREADS], s_r1[COV_THREADS], s_c0[COV_THREADS], s_dxdy[COV_THREADS];
     __shared__ float s_dir[COV_THREADS];
-    __shared__ short2 s_rows[COV_THREADS];
+    __shared__ uint16_t s_pairs[COV_THREADS * SVGR_BAND_ROWS];  // (edge << 4) | row of the band, compacted
+    __shared__ int s_wsum[COV_THREADS / 32];
 
-    // ---- tile -> (mask, band, column chunk) through the tile -> mask table (expand_masks_kernel)
-    const int tile = blockIdx.x;
-    const MaskRec m = masks[__ldg(tile_mask + tile)];
-    const int local = tile - m.tile_base;
-    const int band_local = local / m.ntile_c;
-    const int chunk = local - band_local * m.ntile_c;
-    const int yb = band_local * SVGR_BAND_ROWS;
+    // ---- the tile record (expand_masks_kernel): mask geometry, tile position, the band's slice of the bins
+    TileRec m;
+    {
+        const uint4 *g = reinterpret_cast<const uint4 *>(tiles + blockIdx.x);
+        uint4 *d = reinterpret_cast<uint4 *>(&m);
+        d[0] = __ldg(g), d[1] = __ldg(g + 1), d[2] = __ldg(g + 2);
+    }
+    const int yb = m.yb, col0 = m.col0;
     const int nrows = min(SVGR_BAND_ROWS, m.rows - yb);
-    const int col0 = chunk * SVGR_TILE_COLS;
     const int w = min(SVGR_TILE_COLS, m.cols - col0);     // columns that exist in the mask
     const int wpad = min(SVGR_TILE_COLS, m.stride - col0);  // columns that exist in memory (multiple of 4)
 
@@ -312,25 +314,24 @@ coverage_kernel(const double *__restrict__ edges, const MaskRec *__restrict__ ma
     {
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
         const int q = wpad >> 2;  // float4 per row
-        for (int i = threadIdx.x; i < nrows * q; i += COV_THREADS) {
-            int y = i / q, x = i - y * q;
-            reinterpret_cast<float4 *>(&trace[y][0])[x] = z;
-        }
+        for (int y = threadIdx.x >> 5; y < nrows; y += COV_THREADS / 32)
+            for (int x = threadIdx.x & 31; x < q; x += 32)
+                reinterpret_cast<float4 *>(&trace[y][0])[x] = z;
     }
 
-    // ---- 2. accumulate the signed areas of this band's edges.  Two steps per chunk of COV_THREADS edges:
-    // (a) one thread per edge orients it and stores slope / row range in shared memory, (b) the (edge, row)
-    // pairs are spread over all threads -- 16 consecutive threads take the 16 rows of one edge -- so a steep
-    // edge costs one row's latency instead of sixteen.
-    const int band = m.band_base + band_local;
-    const int e_off = band_off[band];
-    const int e_cnt = (int)max(0ll, min((long long)band_cnt[band], bin_cap - e_off));
+    // ---- 2. accumulate the signed areas of this band's edges.  Per chunk of COV_THREADS edges: (a) one thread
+    // per edge orients it, stores slope / start in shared memory and counts the rows of the band it crosses,
+    // (b) a block scan of the counts compacts the (edge, row) pairs into a list, (c) the pairs are spread over
+    // all threads.  Flattened edges are short (2-3 rows): without the compaction a warp would run the row
+    // arithmetic with 4 of its 32 lanes active.
+    const int e_off = m.e_off, e_cnt = m.e_cnt;
     for (int chunk0 = 0; chunk0 < e_cnt; chunk0 += COV_THREADS) {
         const int n_chunk = min(COV_THREADS, e_cnt - chunk0);
         __syncthreads();  // trace zeroed / previous chunk consumed
+        int row_a = 0, row_n = 0;
         if ((int)threadIdx.x < n_chunk) {
-            const double2 *e = reinterpret_cast<const double2 *>(edges + 4ull * bin_edges[e_off + chunk0 + threadIdx.x]);
-            double2 pa = e[0], pb = e[1];
+            const double2 *e = bin_data + 2ull * (unsigned)(e_off + chunk0 + threadIdx.x);
+            double2 pa = __ldg(e), pb = __ldg(e + 1);
             double r0 = pa.x - (double)m.r0, c0 = pa.y - (double)m.c0;
             double r1 = pb.x - (double)m.r0, c1 = pb.y - (double)m.c0;
             float dir = 1.0f;
@@ -353,14 +354,33 @@ coverage_kernel(const double *__restrict__ edges, const MaskRec *__restrict__ ma
             }
             s_r0[threadIdx.x] = r0, s_r1[threadIdx.x] = r1, s_c0[threadIdx.x] = c0, s_dxdy[threadIdx.x] = dxdy;
             s_dir[threadIdx.x] = dir;
-            s_rows[threadIdx.x] = make_short2((short)(ya - yb), (short)(yz - yb));
+            row_a = ya - yb, row_n = max(0, yz - ya);
         }
+        // exclusive scan of the row counts over the block: warp scan + the totals of the warps before this one
+        const int lane_e = threadIdx.x & 31, warp_e = threadIdx.x >> 5;
+        int incl = row_n;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane_e >= o)
+                incl += t;
+        }
+        if (lane_e == 31)
+            s_wsum[warp_e] = incl;
         __syncthreads();
-        for (int p = threadIdx.x; p < n_chunk * SVGR_BAND_ROWS; p += COV_THREADS) {
-            const int ei = p >> 4, yl = p & (SVGR_BAND_ROWS - 1);
-            const short2 rr = s_rows[ei];
-            if (yl < rr.x || yl >= rr.y)
-                continue;
+        int pair0 = incl - row_n, n_pairs = 0;
+#pragma unroll
+        for (int k = 0; k < COV_THREADS / 32; k++) {
+            const int t = s_wsum[k];
+            pair0 += k < warp_e ? t : 0;
+            n_pairs += t;
+        }
+        for (int k = 0; k < row_n; k++)
+            s_pairs[pair0 + k] = (uint16_t)((threadIdx.x << 4) | (row_a + k));
+        __syncthreads();
+        for (int p = threadIdx.x; p < n_pairs; p += COV_THREADS) {
+            const int pr = s_pairs[p];
+            const int ei = pr >> 4, yl = pr & (SVGR_BAND_ROWS - 1);
             const double r0 = s_r0[ei], r1 = s_r1[ei], dxdy = s_dxdy[ei];
             const int y = yb + yl;
             double ytop = (double)(y + 1) < r1 ? (double)(y + 1) : r1;
@@ -421,18 +441,20 @@ void svgr_launch_bin_count(const double *edges, const uint32_t *edge_path, unsig
 
 void svgr_launch_bin_fill(const double *edges, const uint32_t *edge_path, unsigned long long n_edges,
                           const MaskRec *masks, const int *band_off, int *band_cursor, uint32_t *bin_edges,
-                          long long cap, int sm_count, cudaStream_t s)
+                          double *bin_data, long long cap, int sm_count, cudaStream_t s)
 {
     if (n_edges == 0)
         return;
     unsigned long long blocks = (n_edges + 255) / 256;
     if (blocks > (unsigned long long)sm_count * 16)
         blocks = (unsigned long long)sm_count * 16;
-    bin_fill_kernel<<<(unsigned)blocks, 256, 0, s>>>(edges, edge_path, n_edges, masks, band_off, band_cursor, bin_edges, cap);
+    bin_fill_kernel<<<(unsigned)blocks, 256, 0, s>>>(edges, edge_path, n_edges, masks, band_off, band_cursor, bin_edges,
+                                                     reinterpret_cast<double2 *>(bin_data), cap);
 }
 
 __global__ void expand_masks_kernel(const MaskRec *__restrict__ masks, int n_masks, int n_tiles,
-                                    int *__restrict__ tile_mask)
+                                    const int *__restrict__ band_off, const int *__restrict__ band_cnt, long long bin_cap,
+                                    TileRec *__restrict__ tiles)
 {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tiles)
@@ -445,15 +467,25 @@ __global__ void expand_masks_kernel(const MaskRec *__restrict__ masks, int n_mas
         else
             hi = mid - 1;
     }
-    tile_mask[t] = lo;
+    const MaskRec m = masks[lo];
+    const int local = t - m.tile_base;
+    const int band_local = local / m.ntile_c;
+    const int band = m.band_base + band_local;
+    TileRec r;
+    r.r0 = m.r0, r.c0 = m.c0, r.rows = m.rows, r.cols = m.cols;
+    r.stride = m.stride, r.fill_rule = m.fill_rule;
+    r.yb = band_local * SVGR_BAND_ROWS, r.col0 = (local - band_local * m.ntile_c) * SVGR_TILE_COLS;
+    r.off = m.off;
+    r.e_off = band_off[band];
+    r.e_cnt = (int)max(0ll, min((long long)band_cnt[band], bin_cap - r.e_off));
+    tiles[t] = r;
 }
 
-void svgr_launch_coverage(const double *edges, const MaskRec *masks, int n_masks, int n_tiles, int *tile_mask,
-                          const int *band_off, const int *band_cnt, const uint32_t *bin_edges, long long bin_cap,
-                          float *cov, cudaStream_t s)
+void svgr_launch_coverage(const MaskRec *masks, int n_masks, int n_tiles, TileRec *tiles, const int *band_off,
+                          const int *band_cnt, const double *bin_data, long long bin_cap, float *cov, cudaStream_t s)
 {
     if (n_tiles <= 0)
         return;
-    expand_masks_kernel<<<(n_tiles + 255) / 256, 256, 0, s>>>(masks, n_masks, n_tiles, tile_mask);
-    coverage_kernel<<<n_tiles, COV_THREADS, 0, s>>>(edges, masks, tile_mask, band_off, band_cnt, bin_edges, bin_cap, cov);
+    expand_masks_kernel<<<(n_tiles + 255) / 256, 256, 0, s>>>(masks, n_masks, n_tiles, band_off, band_cnt, bin_cap, tiles);
+    coverage_kernel<<<n_tiles, COV_THREADS, 0, s>>>(tiles, reinterpret_cast<const double2 *>(bin_data), cov);
 }

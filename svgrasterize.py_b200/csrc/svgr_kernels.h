@@ -37,10 +37,10 @@ void svgr_launch_bin_count(const double *edges, const uint32_t *edge_path, unsig
                            const MaskRec *masks, int *band_count, int sm_count, cudaStream_t s);
 void svgr_launch_bin_fill(const double *edges, const uint32_t *edge_path, unsigned long long n_edges,
                           const MaskRec *masks, const int *band_off, int *band_cursor, uint32_t *bin_edges,
+                          double *bin_data,
                           long long cap, int sm_count, cudaStream_t s);
-void svgr_launch_coverage(const double *edges, const MaskRec *masks, int n_masks, int n_tiles, int *tile_mask,
-                          const int *band_off, const int *band_cnt, const uint32_t *bin_edges, long long bin_cap,
-                          float *cov, cudaStream_t s);
+void svgr_launch_coverage(const MaskRec *masks, int n_masks, int n_tiles, TileRec *tiles, const int *band_off,
+                          const int *band_cnt, const double *bin_data, long long bin_cap, float *cov, cudaStream_t s);
 
 // k_compose.cu
 void svgr_launch_expand_ops(const OpRec *ops, int n_ops, int n_tiles, int *tile_op, cudaStream_t s);

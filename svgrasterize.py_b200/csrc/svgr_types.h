@@ -60,6 +60,18 @@ struct MaskRec {
     int32_t pad;
 };
 
+// One coverage tile (band of SVGR_BAND_ROWS rows x chunk of SVGR_TILE_COLS columns of one mask), written on the
+// device after binning so that a coverage CTA starts from a single 48-byte load instead of chasing
+// tile -> mask -> band -> bin through four dependent ones.
+struct TileRec {
+    int32_t r0, c0, rows, cols;  // of the mask
+    int32_t stride, fill_rule;
+    int32_t yb, col0;            // first row / column of the tile inside the mask
+    int64_t off;                 // float offset of the mask in the coverage arena
+    int32_t e_off, e_cnt;        // the band's slice of the bin arrays
+};
+static_assert(sizeof(TileRec) == 48, "TileRec is loaded as three 16-byte pieces");
+
 // ---- paint (svgrasterize.py:995-1103, :1544-1695) ---------------------------------
 enum : int32_t {
     PAINT_SOLID = 0,
