@@ -289,139 +289,170 @@ __device__ __forceinline__ float fill_rule_apply(float m, int rule)
     return v < 1e-6f ? 0.0f : v;
 }
 
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Persistent: the grid is one wave of CTAs, each walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  A tile is a
+// short job (a few microseconds) that starts with two dependent global loads (its record, then its edges);
+// walking lets the next tile's record (cp.async into shared memory) and the first 128 of its edges (registers)
+// arrive while the current tile is being scanned and stored.
 __global__ void __launch_bounds__(COV_THREADS)
-coverage_kernel(const TileRec *__restrict__ tiles, const double2 *__restrict__ bin_data, float *__restrict__ cov)
+coverage_kernel(const TileRec *__restrict__ tiles, int n_tiles, const double2 *__restrict__ bin_data,
+                float *__restrict__ cov)
 {
     __shared__ __align__(16) float trace[SVGR_BAND_ROWS][SVGR_TILE_COLS];
     __shared__ double s_r0[COV_THREADS], s_r1[COV_THREADS], s_c0[COV_THREADS], s_dxdy[COV_THREADS];
     __shared__ float s_dir[COV_THREADS];
     __shared__ uint16_t s_pairs[COV_THREADS * SVGR_BAND_ROWS];  // (edge << 4) | row of the band, compacted
     __shared__ int s_wsum[COV_THREADS / 32];
+    __shared__ __align__(16) TileRec s_tile[2];
 
-    // ---- the tile record (expand_masks_kernel): mask geometry, tile position, the band's slice of the bins
-    TileRec m;
-    {
-        const uint4 *g = reinterpret_cast<const uint4 *>(tiles + blockIdx.x);
-        uint4 *d = reinterpret_cast<uint4 *>(&m);
-        d[0] = __ldg(g), d[1] = __ldg(g + 1), d[2] = __ldg(g + 2);
-    }
-    const int yb = m.yb, col0 = m.col0;
-    const int nrows = min(SVGR_BAND_ROWS, m.rows - yb);
-    const int w = min(SVGR_TILE_COLS, m.cols - col0);     // columns that exist in the mask
-    const int wpad = min(SVGR_TILE_COLS, m.stride - col0);  // columns that exist in memory (multiple of 4)
-
-    // ---- 1. zero the part of the trace tile this band uses
-    {
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int q = wpad >> 2;  // float4 per row
-        for (int y = threadIdx.x >> 5; y < nrows; y += COV_THREADS / 32)
-            for (int x = threadIdx.x & 31; x < q; x += 32)
-                reinterpret_cast<float4 *>(&trace[y][0])[x] = z;
-    }
-
-    // ---- 2. accumulate the signed areas of this band's edges.  Per chunk of COV_THREADS edges: (a) one thread
-    // per edge orients it, stores slope / start in shared memory and counts the rows of the band it crosses,
-    // (b) a block scan of the counts compacts the (edge, row) pairs into a list, (c) the pairs are spread over
-    // all threads.  Flattened edges are short (2-3 rows): without the compaction a warp would run the row
-    // arithmetic with 4 of its 32 lanes active.
-    const int e_off = m.e_off, e_cnt = m.e_cnt;
-    for (int chunk0 = 0; chunk0 < e_cnt; chunk0 += COV_THREADS) {
-        const int n_chunk = min(COV_THREADS, e_cnt - chunk0);
-        __syncthreads();  // trace zeroed / previous chunk consumed
-        int row_a = 0, row_n = 0;
-        if ((int)threadIdx.x < n_chunk) {
-            const double2 *e = bin_data + 2ull * (unsigned)(e_off + chunk0 + threadIdx.x);
-            double2 pa = __ldg(e), pb = __ldg(e + 1);
-            double r0 = pa.x - (double)m.r0, c0 = pa.y - (double)m.c0;
-            double r1 = pb.x - (double)m.r0, c1 = pb.y - (double)m.c0;
-            float dir = 1.0f;
-            if (!(r0 < r1)) {
-                double t;
-                dir = -1.0f;
-                t = r0, r0 = r1, r1 = t;
-                t = c0, c0 = c1, c1 = t;
-            }
-            int ya = 0, yz = 0;
-            double dxdy = 0.0;
-            if (r0 != r1) {
-                dxdy = (c1 - c0) / (r1 - r0);
-                c0 -= (double)col0;
-                double ys = r0 > 0.0 ? r0 : 0.0;
-                int y_first = (int)ys;
-                double yend_f = ceil(r1);
-                int y_last = yend_f < (double)m.rows ? (int)yend_f : m.rows;
-                ya = max(y_first, yb), yz = min(y_last, yb + nrows);
-            }
-            s_r0[threadIdx.x] = r0, s_r1[threadIdx.x] = r1, s_c0[threadIdx.x] = c0, s_dxdy[threadIdx.x] = dxdy;
-            s_dir[threadIdx.x] = dir;
-            row_a = ya - yb, row_n = max(0, yz - ya);
-        }
-        // exclusive scan of the row counts over the block: warp scan + the totals of the warps before this one
-        const int lane_e = threadIdx.x & 31, warp_e = threadIdx.x >> 5;
-        int incl = row_n;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane_e >= o)
-                incl += t;
-        }
-        if (lane_e == 31)
-            s_wsum[warp_e] = incl;
-        __syncthreads();
-        int pair0 = incl - row_n, n_pairs = 0;
-#pragma unroll
-        for (int k = 0; k < COV_THREADS / 32; k++) {
-            const int t = s_wsum[k];
-            pair0 += k < warp_e ? t : 0;
-            n_pairs += t;
-        }
-        for (int k = 0; k < row_n; k++)
-            s_pairs[pair0 + k] = (uint16_t)((threadIdx.x << 4) | (row_a + k));
-        __syncthreads();
-        for (int p = threadIdx.x; p < n_pairs; p += COV_THREADS) {
-            const int pr = s_pairs[p];
-            const int ei = pr >> 4, yl = pr & (SVGR_BAND_ROWS - 1);
-            const double r0 = s_r0[ei], r1 = s_r1[ei], dxdy = s_dxdy[ei];
-            const int y = yb + yl;
-            double ytop = (double)(y + 1) < r1 ? (double)(y + 1) : r1;
-            double ybot = (double)y > r0 ? (double)y : r0;
-            double dy = ytop - ybot;
-            double x = s_c0[ei] + dxdy * (ybot - r0);
-            double x_next = x + dxdy * dy;
-            edge_row(trace[yl], w, x, x_next, (double)s_dir[ei] * dy);
-        }
-    }
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // the trace tile starts zeroed and every tile leaves it zeroed again (the scan clears what it reads)
+    for (int i = tid; i < SVGR_BAND_ROWS * SVGR_TILE_COLS / 4; i += COV_THREADS)
+        reinterpret_cast<float4 *>(&trace[0][0])[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int tile = blockIdx.x, cur = 0;
+    if (tile < n_tiles && tid < 3)
+        reinterpret_cast<uint4 *>(&s_tile[0])[tid] = __ldg(reinterpret_cast<const uint4 *>(tiles + tile) + tid);
     __syncthreads();
+    double2 pa = make_double2(0.0, 0.0), pb = pa;  // this thread's edge of the first chunk of the tile
+    if (tile < n_tiles && tid < s_tile[0].e_cnt) {
+        const double2 *e = bin_data + 2ull * (unsigned)(s_tile[0].e_off + tid);
+        pa = __ldg(e), pb = __ldg(e + 1);
+    }
 
-    // ---- 3. prefix sum along columns, fill rule, 128-bit stores
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int y = warp; y < nrows; y += COV_THREADS / 32) {
-        float carry = 0.f;
-        float *dst = cov + m.off + (long long)(yb + y) * m.stride + col0;
-        for (int cb = 0; cb < wpad; cb += 128) {
-            int c = cb + 4 * lane;
-            float4 v = *reinterpret_cast<const float4 *>(&trace[y][c]);
-            v.y += v.x;
-            v.z += v.y;
-            v.w += v.z;
-            float incl = v.w;
+    for (; tile < n_tiles; tile += gridDim.x, cur ^= 1) {
+        // ---- the tile record (expand_masks_kernel): mask geometry, tile position, the band's slice of the bins
+        const TileRec m = s_tile[cur];
+        const int next = tile + gridDim.x;
+        if (next < n_tiles && tid < 3)
+            cp_async16(reinterpret_cast<uint4 *>(&s_tile[cur ^ 1]) + tid, reinterpret_cast<const uint4 *>(tiles + next) + tid);
+        const int yb = m.yb, col0 = m.col0;
+        const int nrows = min(SVGR_BAND_ROWS, m.rows - yb);
+        const int w = min(SVGR_TILE_COLS, m.cols - col0);     // columns that exist in the mask
+        const int wpad = min(SVGR_TILE_COLS, m.stride - col0);  // columns that exist in memory (multiple of 4)
+
+        // ---- 1. accumulate the signed areas of this band's edges.  Per chunk of COV_THREADS edges: (a) one
+        // thread per edge orients it, stores slope / start in shared memory and counts the rows of the band it
+        // crosses, (b) a block scan of the counts compacts the (edge, row) pairs into a list, (c) the pairs are
+        // spread over all threads.  Flattened edges are short (2-3 rows): without the compaction a warp would
+        // run the row arithmetic with 4 of its 32 lanes active.
+        const int e_off = m.e_off, e_cnt = m.e_cnt;
+        for (int chunk0 = 0; chunk0 < e_cnt; chunk0 += COV_THREADS) {
+            const int n_chunk = min(COV_THREADS, e_cnt - chunk0);
+            if (chunk0 > 0)
+                __syncthreads();  // previous chunk consumed
+            int row_a = 0, row_n = 0;
+            if (tid < n_chunk) {
+                if (chunk0 > 0) {
+                    const double2 *e = bin_data + 2ull * (unsigned)(e_off + chunk0 + tid);
+                    pa = __ldg(e), pb = __ldg(e + 1);
+                }
+                double r0 = pa.x - (double)m.r0, c0 = pa.y - (double)m.c0;
+                double r1 = pb.x - (double)m.r0, c1 = pb.y - (double)m.c0;
+                float dir = 1.0f;
+                if (!(r0 < r1)) {
+                    double t;
+                    dir = -1.0f;
+                    t = r0, r0 = r1, r1 = t;
+                    t = c0, c0 = c1, c1 = t;
+                }
+                int ya = 0, yz = 0;
+                double dxdy = 0.0;
+                if (r0 != r1) {
+                    dxdy = (c1 - c0) / (r1 - r0);
+                    c0 -= (double)col0;
+                    double ys = r0 > 0.0 ? r0 : 0.0;
+                    int y_first = (int)ys;
+                    double yend_f = ceil(r1);
+                    int y_last = yend_f < (double)m.rows ? (int)yend_f : m.rows;
+                    ya = max(y_first, yb), yz = min(y_last, yb + nrows);
+                }
+                s_r0[tid] = r0, s_r1[tid] = r1, s_c0[tid] = c0, s_dxdy[tid] = dxdy;
+                s_dir[tid] = dir;
+                row_a = ya - yb, row_n = max(0, yz - ya);
+            }
+            // exclusive scan of the row counts over the block: warp scan + the totals of the warps before this one
+            int incl = row_n;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                float t = __shfl_up_sync(0xffffffffu, incl, o);
+                int t = __shfl_up_sync(0xffffffffu, incl, o);
                 if (lane >= o)
                     incl += t;
             }
-            float ex = incl - v.w + carry;
-            carry += __shfl_sync(0xffffffffu, incl, 31);
-            if (c < wpad) {
-                float4 o4;
-                o4.x = fill_rule_apply(v.x + ex, m.fill_rule);
-                o4.y = fill_rule_apply(v.y + ex, m.fill_rule);
-                o4.z = fill_rule_apply(v.z + ex, m.fill_rule);
-                o4.w = fill_rule_apply(v.w + ex, m.fill_rule);
-                *reinterpret_cast<float4 *>(dst + c) = o4;
+            if (lane == 31)
+                s_wsum[warp] = incl;
+            __syncthreads();
+            int pair0 = incl - row_n, n_pairs = 0;
+#pragma unroll
+            for (int k = 0; k < COV_THREADS / 32; k++) {
+                const int t = s_wsum[k];
+                pair0 += k < warp ? t : 0;
+                n_pairs += t;
+            }
+            for (int k = 0; k < row_n; k++)
+                s_pairs[pair0 + k] = (uint16_t)((tid << 4) | (row_a + k));
+            __syncthreads();
+            for (int p = tid; p < n_pairs; p += COV_THREADS) {
+                const int pr = s_pairs[p];
+                const int ei = pr >> 4, yl = pr & (SVGR_BAND_ROWS - 1);
+                const double r0 = s_r0[ei], r1 = s_r1[ei], dxdy = s_dxdy[ei];
+                const int y = yb + yl;
+                double ytop = (double)(y + 1) < r1 ? (double)(y + 1) : r1;
+                double ybot = (double)y > r0 ? (double)y : r0;
+                double dy = ytop - ybot;
+                double x = s_c0[ei] + dxdy * (ybot - r0);
+                double x_next = x + dxdy * dy;
+                edge_row(trace[yl], w, x, x_next, (double)s_dir[ei] * dy);
             }
         }
+        cp_async_wait_all();
+        __syncthreads();  // trace complete, the next tile's record has landed
+
+        // ---- the first chunk of the next tile's edges starts its trip now and lands during the scan
+        if (next < n_tiles && tid < s_tile[cur ^ 1].e_cnt) {
+            const double2 *e = bin_data + 2ull * (unsigned)(s_tile[cur ^ 1].e_off + tid);
+            pa = __ldg(e), pb = __ldg(e + 1);
+        }
+
+        // ---- 2. prefix sum along columns, fill rule, 128-bit stores; the trace is cleared as it is read
+        for (int y = warp; y < nrows; y += COV_THREADS / 32) {
+            float carry = 0.f;
+            float *dst = cov + m.off + (long long)(yb + y) * m.stride + col0;
+            for (int cb = 0; cb < wpad; cb += 128) {
+                int c = cb + 4 * lane;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c < wpad) {
+                    v = *reinterpret_cast<const float4 *>(&trace[y][c]);
+                    *reinterpret_cast<float4 *>(&trace[y][c]) = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                v.y += v.x;
+                v.z += v.y;
+                v.w += v.z;
+                float incl = v.w;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    float t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o)
+                        incl += t;
+                }
+                float ex = incl - v.w + carry;
+                carry += __shfl_sync(0xffffffffu, incl, 31);
+                if (c < wpad) {
+                    float4 o4;
+                    o4.x = fill_rule_apply(v.x + ex, m.fill_rule);
+                    o4.y = fill_rule_apply(v.y + ex, m.fill_rule);
+                    o4.z = fill_rule_apply(v.z + ex, m.fill_rule);
+                    o4.w = fill_rule_apply(v.w + ex, m.fill_rule);
+                    *reinterpret_cast<float4 *>(dst + c) = o4;
+                }
+            }
+        }
+        __syncthreads();  // trace cleared before the next tile accumulates into it
     }
 }
 
@@ -487,5 +518,14 @@ void svgr_launch_coverage(const MaskRec *masks, int n_masks, int n_tiles, TileRe
     if (n_tiles <= 0)
         return;
     expand_masks_kernel<<<(n_tiles + 255) / 256, 256, 0, s>>>(masks, n_masks, n_tiles, band_off, band_cnt, bin_cap, tiles);
-    coverage_kernel<<<n_tiles, COV_THREADS, 0, s>>>(tiles, reinterpret_cast<const double2 *>(bin_data), cov);
+    static int wave = 0;  // CTAs of one full wave on this device
+    if (wave == 0) {
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, coverage_kernel, COV_THREADS, 0);
+        wave = std::max(1, sms * std::max(1, per_sm));
+    }
+    coverage_kernel<<<std::min(n_tiles, wave), COV_THREADS, 0, s>>>(tiles, n_tiles, reinterpret_cast<const double2 *>(bin_data),
+                                                                  cov);
 }
