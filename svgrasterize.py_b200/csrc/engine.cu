@@ -152,6 +152,9 @@ struct svgr_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t copy_stream = nullptr;  // device -> host copies of finished canvases, overlapped with later chunks
     cudaEvent_t ev_copy[16] = {nullptr};
+    cudaStream_t up_stream = nullptr;  // plan tables of the next chunk go up (and its focal flags are computed)
+    cudaEvent_t ev_up[16] = {nullptr}; // while the current chunk composes
+    cudaEvent_t ev_up_begin = nullptr;
     std::string err;
 
     // ---- resident program (device) + host copies of what the planner needs
@@ -1358,6 +1361,10 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
         int focal_blocks_done = 0;
         bool externals_up = false;
         mark(10);
+        // uploads and focal flags of a chunk run on their own stream, behind everything issued so far (paints,
+        // the zeroed flags), so that they overlap the compose launches of the chunk before
+        CK(cudaEventRecord(ctx->ev_up_begin, s));
+        CK(cudaStreamWaitEvent(ctx->up_stream, ctx->ev_up_begin, 0));
         for (int k = 0; k < pl.n_chunks(); k++) {
             int op_begin = 0, launch_begin = 0;
             auto t_c0 = std::chrono::steady_clock::now();
@@ -1386,17 +1393,18 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
             OpRec *po = (OpRec *)pin_ops + up_ops;
             for (size_t q = 0; q < n_ops; q++)
                 po[q] = ctx->ops[up_ops + q].op;
+            cudaStream_t us = k < 16 ? ctx->up_stream : s;
             if (n_ops)
-                CK(cudaMemcpyAsync(ctx->d_ops.as<OpRec>() + up_ops, po, n_ops * sizeof(OpRec), cudaMemcpyHostToDevice, s));
+                CK(cudaMemcpyAsync(ctx->d_ops.as<OpRec>() + up_ops, po, n_ops * sizeof(OpRec), cudaMemcpyHostToDevice, us));
             if (n_srcs) {
                 memcpy(pin_srcs + up_srcs * sizeof(SrcRec), ctx->srcs.data() + up_srcs, n_srcs * sizeof(SrcRec));
                 CK(cudaMemcpyAsync(ctx->d_srcs.as<SrcRec>() + up_srcs, pin_srcs + up_srcs * sizeof(SrcRec),
-                                   n_srcs * sizeof(SrcRec), cudaMemcpyHostToDevice, s));
+                                   n_srcs * sizeof(SrcRec), cudaMemcpyHostToDevice, us));
             }
             if (n_focal) {
                 memcpy(pin_focal + up_focal * sizeof(FocalJob), ctx->focal_jobs.data() + up_focal, n_focal * sizeof(FocalJob));
                 CK(cudaMemcpyAsync(ctx->d_focal_jobs.as<FocalJob>() + up_focal, pin_focal + up_focal * sizeof(FocalJob),
-                                   n_focal * sizeof(FocalJob), cudaMemcpyHostToDevice, s));
+                                   n_focal * sizeof(FocalJob), cudaMemcpyHostToDevice, us));
             }
             RenderTables T;
             T.srcs = ctx->d_srcs.as<SrcRec>(), T.paints = ctx->d_paints.as<PaintRec>(), T.stops = ctx->d_stops.as<StopRec>();
@@ -1405,9 +1413,13 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
             if (n_focal) {
                 // block numbers of this chunk's jobs start at focal_blocks_done: rebase through the launch offset
                 svgr_launch_focal_flags(T, ctx->d_focal_jobs.as<FocalJob>() + up_focal, (int)n_focal, focal_blocks_done,
-                                        ctx->n_focal_blocks - focal_blocks_done, ctx->d_focal_flags.as<int>(), s);
+                                        ctx->n_focal_blocks - focal_blocks_done, ctx->d_focal_flags.as<int>(), us);
                 n_kernels += 1;
                 focal_blocks_done = ctx->n_focal_blocks;
+            }
+            if (us != s) {
+                CK(cudaEventRecord(ctx->ev_up[k], us));
+                CK(cudaStreamWaitEvent(s, ctx->ev_up[k], 0));
             }
             if (!externals_up) {
                 externals_up = true;  // programs with external layers are planned as a single chunk
@@ -1590,6 +1602,10 @@ int svgr_create(int device, svgr_ctx **out)
         cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     for (auto &e : ctx->ev_chunk)
         cudaEventCreate(&e[0]), cudaEventCreate(&e[1]);
+    cudaStreamCreateWithFlags(&ctx->up_stream, cudaStreamNonBlocking);
+    for (auto &e : ctx->ev_up)
+        cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_up_begin, cudaEventDisableTiming);
     *out = ctx;
     return SVGR_OK;
 }
@@ -1625,6 +1641,13 @@ void svgr_destroy(svgr_ctx *ctx)
             cudaEventDestroy(e);
     if (ctx->copy_stream)
         cudaStreamDestroy(ctx->copy_stream);
+    for (auto &e : ctx->ev_up)
+        if (e)
+            cudaEventDestroy(e);
+    if (ctx->ev_up_begin)
+        cudaEventDestroy(ctx->ev_up_begin);
+    if (ctx->up_stream)
+        cudaStreamDestroy(ctx->up_stream);
     if (ctx->own_stream)
         cudaStreamDestroy(ctx->own_stream);
     delete ctx;
