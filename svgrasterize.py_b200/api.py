@@ -362,21 +362,49 @@ def pooling(mat, ksize, stride=None, method="max", pad=False):
     return out[..., 0] if squeeze else out
 
 
-def canvas_to_png(canvas, output=None):
+def _deflate_parallel(raw: bytes, level: int, threads: int, block: int = 1 << 20) -> bytes:
+    """One zlib stream made of independently compressed blocks (the pigz construction): every block but the
+    last ends on a sync flush (byte aligned, not final), the last one finishes the stream; the Adler-32 trailer
+    covers the whole input.  zlib releases the GIL, so the blocks run on `threads` host cores."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    n = max(1, (len(raw) + block - 1) // block)
+    view = memoryview(raw)
+
+    def pack(i):
+        c = zlib.compressobj(level, zlib.DEFLATED, -15)  # raw deflate, no header / trailer
+        body = c.compress(view[i * block: (i + 1) * block])
+        return body + (c.flush(zlib.Z_FINISH) if i == n - 1 else c.flush(zlib.Z_FULL_FLUSH))
+
+    with ThreadPoolExecutor(max_workers=threads) as pool:
+        parts = list(pool.map(pack, range(n)))
+    head = b"\x78\xda" if level >= 7 else (b"\x78\x9c" if level >= 6 else b"\x78\x01" if level < 2 else b"\x78\x5e")
+    return head + b"".join(parts) + struct.pack(">I", zlib.adler32(raw) & 0xFFFFFFFF)
+
+
+def canvas_to_png(canvas, output=None, threads=1, level=9):
     """canvas_to_png (svgrasterize.py:249-274): straight-alpha sRGB float image -> PNG bytes.  The
-    float -> uint8 quantisation (:263) is the in-scope part; deflate stays on the host like the reference."""
+    float -> uint8 quantisation (:263) is the in-scope part; deflate stays on the host like the reference.
+
+    With the defaults the bytes are the reference's (filter 0 rows, one zlib stream at level 9).  `threads`
+    > 1 compresses 1 MiB blocks of the same filtered rows on that many host cores (level 9 on
+    one core takes 6.7 s for a 4096 x 4096 canvas): the file decodes to the same pixels but is not
+    byte-identical and a few percent larger."""
     canvas = np.asarray(canvas)
     if canvas.dtype != np.uint8:
         canvas = np.round(np.clip(canvas, 0, 1) * 255.0).astype(np.uint8)
     height, width = canvas.shape[:2]
-    raw = b"".join(b"\x00" + canvas[r].tobytes() for r in range(height))
+    rows = np.zeros((height, 1 + width * 4), dtype=np.uint8)  # filter type 0 in front of every row
+    rows[:, 1:] = canvas.reshape(height, width * 4)
+    raw = rows.tobytes()
 
     def chunk(tag, data):
         body = tag + data
         return struct.pack(">I", len(data)) + body + struct.pack(">I", zlib.crc32(body) & 0xFFFFFFFF)
 
+    idat = zlib.compress(raw, level) if threads <= 1 else _deflate_parallel(raw, level, int(threads))
     png = b"".join([b"\x89PNG\r\n\x1a\n", chunk(b"IHDR", struct.pack(">2I5B", width, height, 8, 6, 0, 0, 0)),
-                    chunk(b"IDAT", zlib.compress(raw, 9)), chunk(b"IEND", b"")])
+                    chunk(b"IDAT", idat), chunk(b"IEND", b"")])
     if output is not None:
         output.write(png)
         return output

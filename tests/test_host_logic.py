@@ -193,3 +193,38 @@ def test_planner_runs_without_a_gpu():
     assert n_launch == 2 and n_levels == 2
     assert n_srcs >= 12 * len(progs)    # every mask is read by exactly one op (+ stencil modifiers)
     assert info[5] > 0
+
+
+def test_canvas_to_png_parallel_deflate_decodes_to_the_same_pixels():
+    """block-parallel deflate is a valid zlib stream of the same filtered rows; the default
+    stays the reference's single level-9 stream (svgrasterize.py:249-274)."""
+    import struct
+    import zlib
+
+    from svgrasterize_b200 import api
+
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, (300, 1111, 4), dtype=np.uint8)
+    img[50:200, 100:900] = (10, 20, 30, 255)
+
+    def decode(png):
+        assert png[:8] == b"\x89PNG\r\n\x1a\n"
+        pos, idat, size = 8, b"", None
+        while pos < len(png):
+            n = struct.unpack(">I", png[pos:pos + 4])[0]
+            tag, data = png[pos + 4:pos + 8], png[pos + 8:pos + 8 + n]
+            assert zlib.crc32(tag + data) & 0xFFFFFFFF == struct.unpack(">I", png[pos + 8 + n:pos + 12 + n])[0]
+            if tag == b"IHDR":
+                size = struct.unpack(">2I", data[:8])
+            if tag == b"IDAT":
+                idat += data
+            pos += 12 + n
+        raw = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(size[1], 1 + 4 * size[0])
+        assert (raw[:, 0] == 0).all()
+        return raw[:, 1:].reshape(size[1], size[0], 4)
+
+    one = api.canvas_to_png(img)
+    raw = b"".join(b"\x00" + img[r].tobytes() for r in range(img.shape[0]))
+    assert zlib.compress(raw, 9) in one  # the reference's IDAT payload, byte for byte
+    many = api.canvas_to_png(img, threads=4)
+    assert np.array_equal(decode(one), img) and np.array_equal(decode(many), img)
