@@ -132,6 +132,7 @@ struct Launch {
     int cls;
     int op_begin, op_count, n_tiles;
     size_t smem;
+    long long list_slots;  // compose launches: TileEntry slots (sum over ops of tiles x sources)
 };
 
 struct StatusBlock {  // device -> host after flatten
@@ -202,7 +203,7 @@ struct svgr_ctx {
     long long mask_pixels = 0, layer_pixels = 0, compose_bytes = 0, compose_bytes_8d = 0, canvas_pixels = 0;
     int n_levels = 0;
     DevBuf d_masks, d_band_cnt, d_band_off, d_band_cur, d_bin_edges, d_cov, d_layers, d_ops, d_srcs, d_focal_jobs,
-        d_focal_flags, d_canvas, d_q, d_tile_map, d_tile_rec, d_bin_data;
+        d_focal_flags, d_canvas, d_q, d_tile_map, d_tile_rec, d_bin_data, d_tile_list;
     long long bin_cap = 0;
     long long n_binned = 0;
     bool planned = false, covered = false, composed = false;
@@ -928,8 +929,8 @@ struct Planner {
         while (i < c->ops.size()) {
             size_t j = i;
             Launch L;
-            L.cls = c->ops[i].cls, L.op_begin = (int)i, L.n_tiles = 0, L.smem = 0;
-            long long tiles = 0;
+            L.cls = c->ops[i].cls, L.op_begin = (int)i, L.n_tiles = 0, L.smem = 0, L.list_slots = 0;
+            long long tiles = 0, slots = 0;
             while (j < c->ops.size() && c->ops[j].level == c->ops[i].level && c->ops[j].cls == c->ops[i].cls) {
                 OpRec &o = c->ops[j].op;
                 int tr = SVGR_CMP_TR, tc = SVGR_CMP_TC;
@@ -946,7 +947,11 @@ struct Planner {
                 }
                 o.ntile_c = std::max(1, ceil_div(o.cols, tc));
                 o.tile_base = (int)tiles;
-                tiles += (long long)ceil_div(o.rows, tr) * ceil_div(o.cols, tc);
+                const long long op_tiles = (long long)ceil_div(o.rows, tr) * ceil_div(o.cols, tc);
+                tiles += op_tiles;
+                o.list_base = (int)slots;
+                if (o.kind == OP_COMPOSE || o.kind == OP_CANVAS)
+                    slots += op_tiles * o.src_cnt;
                 L.smem = std::max(L.smem, smem);
                 // algorithmic traffic: every output pixel written once, every source pixel read once
                 const PlannedOp &po = c->ops[j];
@@ -981,10 +986,11 @@ struct Planner {
                 }
                 j++;
             }
-            if (tiles > 0x7fffff00ll) {
+            if (tiles > 0x7fffff00ll || slots > 0x7fffff00ll) {
                 err = "too many tiles in one launch";
                 return false;
             }
+            L.list_slots = slots;
             if (L.smem > SVGR_MAX_DYN_SMEM) {
                 err = "stencil too long for shared-memory staging";
                 return false;
@@ -1380,12 +1386,19 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
                 CK(cudaStreamSynchronize(s));
                 CK(ctx->d_layers.ensure((size_t)ctx->layer_floats * 4 + ((size_t)ctx->layer_floats * 4) / 2, true));
             }
-            long long max_tiles = 1;
-            for (size_t q = launch_begin; q < ctx->launches.size(); q++)
+            long long max_tiles = 1, max_slots = 1;
+            for (size_t q = launch_begin; q < ctx->launches.size(); q++) {
                 max_tiles = std::max<long long>(max_tiles, ctx->launches[q].n_tiles);
-            if ((size_t)max_tiles * 4 > ctx->d_tile_map.cap) {
+                max_slots = std::max<long long>(max_slots, ctx->launches[q].list_slots);
+            }
+            // tile heads (16 B per tile; the stencil kernels use the same buffer as a 4-byte tile -> op map)
+            if ((size_t)max_tiles * sizeof(TileHead) > ctx->d_tile_map.cap) {
                 CK(cudaStreamSynchronize(s));
-                CK(ctx->d_tile_map.ensure((size_t)max_tiles * 4 * 2));
+                CK(ctx->d_tile_map.ensure((size_t)max_tiles * sizeof(TileHead) * 2));
+            }
+            if ((size_t)max_slots * sizeof(TileEntry) > ctx->d_tile_list.cap) {
+                CK(cudaStreamSynchronize(s));
+                CK(ctx->d_tile_list.ensure((size_t)max_slots * sizeof(TileEntry) * 3 / 2));
             }
             // stage + upload the new records
             const size_t n_ops = ctx->ops.size() - up_ops, n_srcs = ctx->srcs.size() - up_srcs;
@@ -1443,9 +1456,15 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
                 const Launch &L = ctx->launches[q];
                 const OpRec *ops = ctx->d_ops.as<OpRec>() + L.op_begin;
                 const int *tile_op = ctx->d_tile_map.as<int>();
-                svgr_launch_expand_ops(ops, L.op_count, L.n_tiles, ctx->d_tile_map.as<int>(), s);
+                const TileHead *heads = ctx->d_tile_map.as<TileHead>();
+                const TileEntry *list = ctx->d_tile_list.as<TileEntry>();
+                if (L.cls == 0 || L.cls == 3)
+                    svgr_launch_cull(T, ops, L.op_count, L.n_tiles, ctx->d_tile_map.as<TileHead>(),
+                                     ctx->d_tile_list.as<TileEntry>(), s);
+                else
+                    svgr_launch_expand_ops(ops, L.op_count, L.n_tiles, ctx->d_tile_map.as<int>(), s);
                 if (L.cls == 0)
-                    svgr_launch_compose(T, ops, tile_op, L.n_tiles, ctx->d_layers.as<float>(), nullptr, s);
+                    svgr_launch_compose(T, ops, heads, list, L.n_tiles, ctx->d_layers.as<float>(), nullptr, s);
                 else if (L.cls == 1) {
                     if (svgr_launch_stencil(T, ops, tile_op, L.n_tiles, L.smem, ctx->d_layers.as<float>(), s))
                         FAIL(SVGR_E_UNSUPPORTED, "stencil needs more shared memory than available");
@@ -1453,7 +1472,7 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
                     if (svgr_launch_conv2d(T, ops, tile_op, L.n_tiles, L.smem, ctx->d_layers.as<float>(), s))
                         FAIL(SVGR_E_UNSUPPORTED, "convolution needs more shared memory than available");
                 } else
-                    svgr_launch_compose(T, ops, tile_op, L.n_tiles, ctx->d_layers.as<float>(), canvas, s);
+                    svgr_launch_compose(T, ops, heads, list, L.n_tiles, ctx->d_layers.as<float>(), canvas, s);
                 n_launches++;
                 n_kernels += L.n_tiles > 0 ? 2 : 0;
             }
@@ -1622,7 +1641,7 @@ void svgr_destroy(svgr_ctx *ctx)
                       &ctx->d_osub, &ctx->d_ocount, &ctx->d_edges, &ctx->d_edge_path, &ctx->d_minmax, &ctx->d_boxes,
                       &ctx->d_minmax_f64, &ctx->d_status, &ctx->d_masks, &ctx->d_band_cnt, &ctx->d_band_off,
                       &ctx->d_band_cur, &ctx->d_bin_edges, &ctx->d_cov, &ctx->d_layers, &ctx->d_ops, &ctx->d_srcs,
-                      &ctx->d_focal_jobs, &ctx->d_focal_flags, &ctx->d_canvas, &ctx->d_q, &ctx->d_tile_map, &ctx->d_tile_rec, &ctx->d_bin_data};
+                      &ctx->d_focal_jobs, &ctx->d_focal_flags, &ctx->d_canvas, &ctx->d_q, &ctx->d_tile_map, &ctx->d_tile_rec, &ctx->d_bin_data, &ctx->d_tile_list};
     for (DevBuf *b : bufs)
         b->release();
     ctx->pin_boxes.release(), ctx->pin_status.release(), ctx->pin_plan.release(), ctx->pin_out.release();

@@ -67,37 +67,65 @@ __device__ __forceinline__ void copy16(T *dst, const T *src, int part)
 }
 
 // One kernel for layer ops (float output) and canvas ops (RGBA8 output).  Per CTA:
-//   1. the op of this tile comes from the tile -> op table; its record is staged in shared memory
-//      (one 8-byte piece per thread) so that nobody chases it through global memory again;
-//   2. rounds: warp 0 culls the next sources against the tile rectangle (order preserved) and copies
-//      up to CMP_CAP surviving SrcRecs into shared memory; all threads then copy the PaintRecs those
-//      sources need; every thread folds the staged sources into its 4 pixels, issuing the 4 loads of a
-//      source back to back before using any of them.
+//   1. the tile's head (cull_kernel) names its op and its list of sources; the op record, up to CMP_CAP
+//      SrcRecs and the PaintRecs they need are copied into shared memory by all threads at once -- one
+//      barrier, nobody chases records through global memory afterwards;
+//   2. every thread folds the staged sources into its 4 pixels, issuing the 4 loads of a source back to back
+//      before using any of them;
+//   3. tiles with more than CMP_CAP sources (the 935-layer group of demo/material-design.svg) repeat 1-2.
 #ifndef SVGR_CMP_OCC
 #define SVGR_CMP_OCC 4
 #endif
 __global__ void __launch_bounds__(256, SVGR_CMP_OCC)
-compose_kernel(RenderTables T, const OpRec *__restrict__ ops, const int *__restrict__ tile_op,
-               float *__restrict__ layers_out, uint8_t *__restrict__ canvas_out)
+compose_kernel(RenderTables T, const OpRec *__restrict__ ops, const TileHead *__restrict__ heads,
+               const TileEntry *__restrict__ list, float *__restrict__ layers_out, uint8_t *__restrict__ canvas_out)
 {
     __shared__ __align__(16) OpRec s_op;
     __shared__ __align__(16) SrcRec s_src[CMP_CAP + 1];
     __shared__ __align__(16) PaintRec s_paint[CMP_CAP + 1];
-    __shared__ int s_idx[CMP_CAP + 1];
     // per staged source, relative to this tile: bit r of s_rm = tile row r is inside the source (and the op), bit c
     // of s_cm likewise for columns, s_toff = element offset of the tile's top-left pixel in the source's storage
     __shared__ unsigned s_rm[CMP_CAP + 1], s_cm[CMP_CAP + 1];
     __shared__ int s_toff[CMP_CAP + 1];
-    __shared__ int s_n, s_next;
 
     const int tid = threadIdx.x;
+    const int4 head = __ldg(reinterpret_cast<const int4 *>(heads) + blockIdx.x);  // op, entries, first entry
+    const int n_list = head.y;
+    const TileEntry *entries = list + head.z;
     static_assert(sizeof(OpRec) % 8 == 0, "OpRec must be a multiple of 8 bytes");
-    if (tid < (int)(sizeof(OpRec) / 8)) {
-        const int opi = __ldg(tile_op + blockIdx.x);  // tile -> op table written by expand_ops_kernel
-        reinterpret_cast<uint2 *>(&s_op)[tid] = __ldg(reinterpret_cast<const uint2 *>(ops + opi) + tid);
-    }
-    if (tid == 0)
-        s_next = 0;
+    static_assert(sizeof(PaintRec) == 224, "PaintRec layout");
+    static_assert(4 * (CMP_CAP + 1) <= 256, "one staging pass");
+
+    // `take` entries from `start` on go to shared memory; a stencil modifier stays with the source before it
+    auto round_size = [&](int start) {
+        int take = min(CMP_CAP, n_list - start);
+        if (start + take < n_list && __ldg(&entries[start + take].paint) == -2)
+            take--;
+        return take;
+    };
+    auto stage = [&](int start, int take) {
+        if (tid < 4 * take) {
+            const int j = tid >> 2, part = tid & 3;
+            const TileEntry *e = entries + start + j;
+            const uint4 a = __ldg(reinterpret_cast<const uint4 *>(e));
+            copy16(&s_src[j], T.srcs + (int)a.x, part);
+            if (part == 0) {
+                s_rm[j] = a.z, s_cm[j] = a.w;
+                s_toff[j] = __ldg(&e->toff);
+            }
+        }
+        for (int q = tid; q < take * 14; q += 256) {
+            const int j = q / 14, part = q - j * 14;
+            const int paint = __ldg(&entries[start + j].paint);
+            if (paint >= 0)
+                copy16(&s_paint[j], T.paints + paint, part);
+        }
+    };
+
+    if (tid < (int)(sizeof(OpRec) / 8))
+        reinterpret_cast<uint2 *>(&s_op)[tid] = __ldg(reinterpret_cast<const uint2 *>(ops + head.x) + tid);
+    int start = 0, n = round_size(0);
+    stage(0, n);
     __syncthreads();
     const OpRec &op = s_op;
     const int local = blockIdx.x - op.tile_base;
@@ -105,10 +133,7 @@ compose_kernel(RenderTables T, const OpRec *__restrict__ ops, const int *__restr
     const int ty = tid >> 5, tx = tid & 31;
     const int lr0 = tr * CMP_TR + ty, lc = tc * CMP_TC + tx;  // output-local; pixel k is 8 k rows further down
     const int r0 = op.r0 + lr0, c = op.c0 + lc;
-    const int tile_r0 = op.r0 + tr * CMP_TR, tile_c0 = op.c0 + tc * CMP_TC;
-    const int tile_r1 = min(tile_r0 + CMP_TR, op.r0 + op.rows), tile_c1 = min(tile_c0 + CMP_TC, op.c0 + op.cols);
     const bool col_live = lc < op.cols;
-    const SrcRec *srcs = T.srcs + op.src_off;
     const int mode = op.mode;
     const bool skip_outside = (mode == MODE_OVER);  // blending a zero source is the identity for OVER
     const double x0 = (double)r0 + 0.5, y0 = (double)c + 0.5;  // pixel centre of pixel 0
@@ -119,71 +144,13 @@ compose_kernel(RenderTables T, const OpRec *__restrict__ ops, const int *__restr
         acc[k] = f4(0.f, 0.f, 0.f, 0.f);
 
     for (;;) {
-        const int start = s_next;
-        __syncthreads();
-        if (start >= op.src_cnt)
-            break;
-        // ---- stage: order-preserving cull + copy of SrcRecs (warp 0)
-        if (tid < 32) {
-            int n = 0, k = start;
-            for (; k < op.src_cnt && n + 32 <= CMP_CAP; k += 32) {
-                int i = k + tx;
-                bool hit = false;
-                SrcRec rec;
-                if (i < op.src_cnt) {
-                    const uint4 *g = reinterpret_cast<const uint4 *>(srcs + i);
-                    uint4 *d = reinterpret_cast<uint4 *>(&rec);
-                    d[0] = __ldg(g), d[1] = __ldg(g + 1), d[2] = __ldg(g + 2), d[3] = __ldg(g + 3);
-                    hit = (i == 0 || !skip_outside) ||
-                          (rec.r0 < tile_r1 && rec.r0 + rec.rows > tile_r0 && rec.c0 < tile_c1 && rec.c0 + rec.cols > tile_c0);
-                }
-                unsigned m = __ballot_sync(0xffffffffu, hit);
-                if (hit) {
-                    int pos = n + __popc(m & ((1u << tx) - 1));
-                    s_src[pos] = rec;
-                    s_idx[pos] = i;
-                    const int ra = max(rec.r0, tile_r0), rb = min(rec.r0 + rec.rows, tile_r1);
-                    const int ca = max(rec.c0, tile_c0), cb = min(rec.c0 + rec.cols, tile_c1);
-                    s_rm[pos] = rb > ra ? (0xffffffffu >> (32 - (rb - ra))) << (ra - tile_r0) : 0u;
-                    s_cm[pos] = cb > ca ? (0xffffffffu >> (32 - (cb - ca))) << (ca - tile_c0) : 0u;
-                    s_toff[pos] = (tile_r0 - rec.br0) * rec.stride + (tile_c0 - rec.bc0);
-                }
-                n += __popc(m);
-            }
-            // a stencil modifier must be staged in the same round as the source it belongs to
-            if (k < op.src_cnt && n > 0) {
-                int kind = __ldg(&srcs[k].kind);
-                if (kind >= SRC_MOD_COV && s_idx[n - 1] == k - 1) {
-                    if (tx < 4)
-                        copy16(&s_src[n], srcs + k, tx);
-                    if (tx == 0)
-                        s_idx[n] = k;
-                    n++, k++;
-                }
-            }
-            if (tx == 0) {
-                s_n = n;
-                s_next = k < op.src_cnt ? k : op.src_cnt;
-            }
-        }
-        __syncthreads();
-        const int n = s_n;
-        // ---- stage: paint records of the staged COVPAINT sources (14 x 16 bytes each)
-        {
-            static_assert(sizeof(PaintRec) == 224, "PaintRec layout");
-            const int part = tid & 15;
-            for (int j = tid >> 4; j < n; j += 16)
-                if (part < 14 && s_src[j].kind == SRC_COVPAINT)
-                    copy16(&s_paint[j], T.paints + s_src[j].paint, part);
-        }
-        __syncthreads();
         // ---- fold: everything that does not depend on the pixel is hoisted out of the 4-pixel loops
         if (col_live) {
             for (int j = 0; j < n; j++) {
                 const SrcRec &s = s_src[j];
                 if (s.kind >= SRC_MOD_COV)
                     continue;  // consumed together with its owner below
-                const bool first = s_idx[j] == 0;
+                const bool first = start + j == 0;  // source 0 of the op is always listed first
                 // pixel k of this thread (row ty + 8 k of the tile) is inside the source: bit 8 k of `live`
                 const unsigned live = ((s_rm[j] >> ty) & 0x01010101u) * ((s_cm[j] >> tx) & 1u);
                 if (!live && skip_outside && !first)
@@ -288,6 +255,12 @@ compose_kernel(RenderTables T, const OpRec *__restrict__ ops, const int *__restr
                 }
             }
         }
+        start += n;
+        if (start >= n_list)
+            break;
+        __syncthreads();  // everybody is done with the staged records
+        n = round_size(start);
+        stage(start, n);
         __syncthreads();
     }
     if (!col_live)
@@ -379,11 +352,78 @@ __global__ void focal_flag_kernel(RenderTables T, const FocalJob *__restrict__ j
 }
 
 // ---------------------------------------------------------------------------------------------
-void svgr_launch_compose(const RenderTables &T, const OpRec *ops, const int *tile_op, int n_tiles, float *layers_out,
-                         uint8_t *canvas_out, cudaStream_t s)
+void svgr_launch_compose(const RenderTables &T, const OpRec *ops, const TileHead *heads, const TileEntry *list, int n_tiles,
+                         float *layers_out, uint8_t *canvas_out, cudaStream_t s)
 {
     if (n_tiles > 0)
-        compose_kernel<<<n_tiles, 256, 0, s>>>(T, ops, tile_op, layers_out, canvas_out);
+        compose_kernel<<<n_tiles, 256, 0, s>>>(T, ops, heads, list, layers_out, canvas_out);
+}
+
+// Source lists of the tiles of one compose launch, one warp per tile: the op of the tile (binary search over the
+// launch's ops, their tile_base column stays in L1/L2), then an order-preserving cull of the op's sources against
+// the tile rectangle (ballots).  What the fold needs per (source, tile) and not per pixel -- row / column masks,
+// the storage offset of the tile's corner, the paint index -- is computed here once instead of by 256 threads.
+// A blend other than OVER keeps every source (a zero source is not its identity); source 0 is always kept.
+__global__ void __launch_bounds__(256)
+cull_kernel(RenderTables T, const OpRec *__restrict__ ops, int n_ops, int n_tiles, TileHead *__restrict__ heads,
+            TileEntry *__restrict__ list)
+{
+    const int t = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (t >= n_tiles)
+        return;
+    int lo = 0, hi = n_ops - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (__ldg(&ops[mid].tile_base) <= t)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    const OpRec *op = ops + lo;
+    const int o_r0 = __ldg(&op->r0), o_c0 = __ldg(&op->c0), o_rows = __ldg(&op->rows), o_cols = __ldg(&op->cols);
+    const int src_off = __ldg(&op->src_off), src_cnt = __ldg(&op->src_cnt), ntile_c = __ldg(&op->ntile_c);
+    const bool keep_all = __ldg(&op->mode) != MODE_OVER;
+    const int local = t - __ldg(&op->tile_base);
+    const int tr = local / ntile_c, tc = local - tr * ntile_c;
+    const int tile_r0 = o_r0 + tr * CMP_TR, tile_c0 = o_c0 + tc * CMP_TC;
+    const int tile_r1 = min(tile_r0 + CMP_TR, o_r0 + o_rows), tile_c1 = min(tile_c0 + CMP_TC, o_c0 + o_cols);
+    const int first = __ldg(&op->list_base) + local * src_cnt;
+    TileEntry *out = list + first;
+    int n = 0;
+    for (int k = 0; k < src_cnt; k += 32) {
+        const int i = k + lane;
+        bool hit = false;
+        TileEntry e;
+        e.src = src_off + i, e.paint = -1, e.rm = 0u, e.cm = 0u, e.toff = 0, e.pad[0] = e.pad[1] = e.pad[2] = 0;
+        if (i < src_cnt) {
+            const int4 *g = reinterpret_cast<const int4 *>(T.srcs + src_off + i);
+            const int4 a = __ldg(g), b = __ldg(g + 1), d = __ldg(g + 3);  // kind r0 c0 rows | cols stride paint conv | .. br0 bc0
+            const int ra = max(a.y, tile_r0), rb = min(a.y + a.w, tile_r1);
+            const int ca = max(a.z, tile_c0), cb = min(a.z + b.x, tile_c1);
+            e.rm = rb > ra ? (0xffffffffu >> (32 - (rb - ra))) << (ra - tile_r0) : 0u;
+            e.cm = cb > ca ? (0xffffffffu >> (32 - (cb - ca))) << (ca - tile_c0) : 0u;
+            e.toff = (tile_r0 - d.z) * b.y + (tile_c0 - d.w);
+            e.paint = a.x >= SRC_MOD_COV ? -2 : (a.x == SRC_COVPAINT ? b.z : -1);
+            // a modifier carries its owner's rectangle: the two are kept or dropped together
+            hit = i == 0 || keep_all || (e.rm != 0u && e.cm != 0u);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (hit) {
+            uint4 *dst = reinterpret_cast<uint4 *>(out + n + __popc(m & ((1u << lane) - 1)));
+            dst[0] = make_uint4((unsigned)e.src, (unsigned)e.paint, e.rm, e.cm);
+            dst[1] = make_uint4((unsigned)e.toff, 0u, 0u, 0u);
+        }
+        n += __popc(m);
+    }
+    if (lane == 0)
+        reinterpret_cast<int4 *>(heads)[t] = make_int4(lo, n, first, 0);
+}
+
+void svgr_launch_cull(const RenderTables &T, const OpRec *ops, int n_ops, int n_tiles, TileHead *heads, TileEntry *list,
+                      cudaStream_t s)
+{
+    if (n_ops > 0 && n_tiles > 0)
+        cull_kernel<<<(n_tiles + 7) / 8, 256, 0, s>>>(T, ops, n_ops, n_tiles, heads, list);
 }
 
 // tile -> op table of one launch: op i owns tiles [ops[i].tile_base, ops[i + 1].tile_base).  One thread per

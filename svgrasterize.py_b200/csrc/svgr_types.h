@@ -178,10 +178,27 @@ struct OpRec {
     int32_t stencil; // STENCIL_*
     int32_t tile_base;  // first tile id of this op inside its launch
     int32_t ntile_c;    // tiles per tile-row
-    int32_t pad;
+    int32_t list_base;  // compose ops: first TileEntry slot of this op's tiles (src_cnt slots per tile)
     float mul;    // opacity (applied after the fold)
     float k[4];   // arithmetic coefficients
     float pad2;
+};
+
+// Per-tile source list of a compose launch (cull_kernel -> compose_kernel): the sources of the tile's op that
+// touch the tile, in order, with everything about the pair (source, tile) that does not depend on the pixel.
+struct TileEntry {
+    int32_t src;     // index into the SrcRec table
+    int32_t paint;   // PaintRec index of a SRC_COVPAINT source, -1 none, -2 the entry is a stencil modifier
+    uint32_t rm, cm; // bit r / c: tile row r / column c lies inside the source's valid region (and the op)
+    int32_t toff;    // element offset of the tile's top-left pixel in the source's storage
+    int32_t pad[3];
+};
+static_assert(sizeof(TileEntry) == 32, "TileEntry is read as two 16-byte pieces");
+struct TileHead {
+    int32_t op;      // index of the tile's op inside the launch
+    int32_t n;       // entries
+    int32_t first;   // first entry in the launch's list
+    int32_t pad;
 };
 
 // any(det < 0) pre-pass of a two-circle gradient fill (svgrasterize.py:1621-1622)
