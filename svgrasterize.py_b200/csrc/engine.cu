@@ -133,6 +133,7 @@ struct Launch {
     int op_begin, op_count, n_tiles;
     size_t smem;
     long long list_slots;  // compose launches: TileEntry slots (sum over ops of tiles x sources)
+    long long head_off = 0, list_off = 0;  // where this launch's tile heads / entries start in the chunk's buffers
 };
 
 struct StatusBlock {  // device -> host after flatten
@@ -156,6 +157,7 @@ struct svgr_ctx {
     cudaStream_t up_stream = nullptr;  // plan tables of the next chunk go up (and its focal flags are computed)
     cudaEvent_t ev_up[16] = {nullptr}; // while the current chunk composes
     cudaEvent_t ev_up_begin = nullptr;
+    cudaEvent_t ev_done[16] = {nullptr};  // a chunk's launches have finished (its list buffers may be rewritten)
     std::string err;
 
     // ---- resident program (device) + host copies of what the planner needs
@@ -203,7 +205,7 @@ struct svgr_ctx {
     long long mask_pixels = 0, layer_pixels = 0, compose_bytes = 0, compose_bytes_8d = 0, canvas_pixels = 0;
     int n_levels = 0;
     DevBuf d_masks, d_band_cnt, d_band_off, d_band_cur, d_bin_edges, d_cov, d_layers, d_ops, d_srcs, d_focal_jobs,
-        d_focal_flags, d_canvas, d_q, d_tile_map, d_tile_rec, d_bin_data, d_tile_list;
+        d_focal_flags, d_canvas, d_q, d_tile_map, d_tile_rec, d_bin_data, d_heads[2], d_lists[2];
     long long bin_cap = 0;
     long long n_binned = 0;
     bool planned = false, covered = false, composed = false;
@@ -1386,19 +1388,30 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
                 CK(cudaStreamSynchronize(s));
                 CK(ctx->d_layers.ensure((size_t)ctx->layer_floats * 4 + ((size_t)ctx->layer_floats * 4) / 2, true));
             }
-            long long max_tiles = 1, max_slots = 1;
+            // tile -> op map of the stencil launches; tile heads and source lists of the compose launches.  The
+            // lists of a whole chunk are written on the side stream while the chunk before it composes, so they
+            // live in two buffers used by alternate chunks.
+            const int par = k & 1;
+            long long max_tiles = 1, n_heads = 0, n_slots = 0;
             for (size_t q = launch_begin; q < ctx->launches.size(); q++) {
-                max_tiles = std::max<long long>(max_tiles, ctx->launches[q].n_tiles);
-                max_slots = std::max<long long>(max_slots, ctx->launches[q].list_slots);
+                Launch &L = ctx->launches[q];
+                if (L.cls == 0 || L.cls == 3) {
+                    L.head_off = n_heads, L.list_off = n_slots;
+                    n_heads += L.n_tiles, n_slots += L.list_slots;
+                } else {
+                    max_tiles = std::max<long long>(max_tiles, L.n_tiles);
+                }
             }
-            // tile heads (16 B per tile; the stencil kernels use the same buffer as a 4-byte tile -> op map)
-            if ((size_t)max_tiles * sizeof(TileHead) > ctx->d_tile_map.cap) {
+            if ((size_t)max_tiles * 4 > ctx->d_tile_map.cap) {
                 CK(cudaStreamSynchronize(s));
-                CK(ctx->d_tile_map.ensure((size_t)max_tiles * sizeof(TileHead) * 2));
+                CK(ctx->d_tile_map.ensure((size_t)max_tiles * 4 * 2));
             }
-            if ((size_t)max_slots * sizeof(TileEntry) > ctx->d_tile_list.cap) {
+            if ((size_t)n_heads * sizeof(TileHead) > ctx->d_heads[par].cap ||
+                (size_t)n_slots * sizeof(TileEntry) > ctx->d_lists[par].cap) {
                 CK(cudaStreamSynchronize(s));
-                CK(ctx->d_tile_list.ensure((size_t)max_slots * sizeof(TileEntry) * 3 / 2));
+                CK(cudaStreamSynchronize(ctx->up_stream));
+                CK(ctx->d_heads[par].ensure((size_t)std::max<long long>(n_heads, 1) * sizeof(TileHead) * 3 / 2));
+                CK(ctx->d_lists[par].ensure((size_t)std::max<long long>(n_slots, 1) * sizeof(TileEntry) * 3 / 2));
             }
             // stage + upload the new records
             const size_t n_ops = ctx->ops.size() - up_ops, n_srcs = ctx->srcs.size() - up_srcs;
@@ -1430,6 +1443,16 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
                 n_kernels += 1;
                 focal_blocks_done = ctx->n_focal_blocks;
             }
+            // per-tile source lists of this chunk's compose launches: they depend on the tables only
+            if (us != s && k >= 2)
+                CK(cudaStreamWaitEvent(us, ctx->ev_done[k - 2], 0));  // the chunk that used these buffers last
+            for (size_t q = launch_begin; q < ctx->launches.size(); q++) {
+                const Launch &L = ctx->launches[q];
+                if (L.cls == 0 || L.cls == 3)
+                    svgr_launch_cull(T, ctx->d_ops.as<OpRec>() + L.op_begin, L.op_count, L.n_tiles,
+                                     ctx->d_heads[par].as<TileHead>() + L.head_off,
+                                     ctx->d_lists[par].as<TileEntry>() + L.list_off, us);
+            }
             if (us != s) {
                 CK(cudaEventRecord(ctx->ev_up[k], us));
                 CK(cudaStreamWaitEvent(s, ctx->ev_up[k], 0));
@@ -1456,12 +1479,9 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
                 const Launch &L = ctx->launches[q];
                 const OpRec *ops = ctx->d_ops.as<OpRec>() + L.op_begin;
                 const int *tile_op = ctx->d_tile_map.as<int>();
-                const TileHead *heads = ctx->d_tile_map.as<TileHead>();
-                const TileEntry *list = ctx->d_tile_list.as<TileEntry>();
-                if (L.cls == 0 || L.cls == 3)
-                    svgr_launch_cull(T, ops, L.op_count, L.n_tiles, ctx->d_tile_map.as<TileHead>(),
-                                     ctx->d_tile_list.as<TileEntry>(), s);
-                else
+                const TileHead *heads = ctx->d_heads[par].as<TileHead>() + L.head_off;
+                const TileEntry *list = ctx->d_lists[par].as<TileEntry>() + L.list_off;
+                if (L.cls == 1 || L.cls == 2)
                     svgr_launch_expand_ops(ops, L.op_count, L.n_tiles, ctx->d_tile_map.as<int>(), s);
                 if (L.cls == 0)
                     svgr_launch_compose(T, ops, heads, list, L.n_tiles, ctx->d_layers.as<float>(), nullptr, s);
@@ -1478,6 +1498,8 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
             }
             if (timing && k < 16)
                 cudaEventRecord(ctx->ev_chunk[k][1], s);
+            if (k < 16)
+                CK(cudaEventRecord(ctx->ev_done[k], s));
             timed_chunks = std::min(k + 1, 16);
             // host output: the canvases this chunk finished go down on the copy stream while the next chunk
             // is planned and composed (chunks own increasing, disjoint byte ranges of the output)
@@ -1625,6 +1647,8 @@ int svgr_create(int device, svgr_ctx **out)
     for (auto &e : ctx->ev_up)
         cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_up_begin, cudaEventDisableTiming);
+    for (auto &e : ctx->ev_done)
+        cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     *out = ctx;
     return SVGR_OK;
 }
@@ -1641,7 +1665,8 @@ void svgr_destroy(svgr_ctx *ctx)
                       &ctx->d_osub, &ctx->d_ocount, &ctx->d_edges, &ctx->d_edge_path, &ctx->d_minmax, &ctx->d_boxes,
                       &ctx->d_minmax_f64, &ctx->d_status, &ctx->d_masks, &ctx->d_band_cnt, &ctx->d_band_off,
                       &ctx->d_band_cur, &ctx->d_bin_edges, &ctx->d_cov, &ctx->d_layers, &ctx->d_ops, &ctx->d_srcs,
-                      &ctx->d_focal_jobs, &ctx->d_focal_flags, &ctx->d_canvas, &ctx->d_q, &ctx->d_tile_map, &ctx->d_tile_rec, &ctx->d_bin_data, &ctx->d_tile_list};
+                      &ctx->d_focal_jobs, &ctx->d_focal_flags, &ctx->d_canvas, &ctx->d_q, &ctx->d_tile_map, &ctx->d_tile_rec, &ctx->d_bin_data, &ctx->d_heads[0], &ctx->d_heads[1], &ctx->d_lists[0],
+                      &ctx->d_lists[1]};
     for (DevBuf *b : bufs)
         b->release();
     ctx->pin_boxes.release(), ctx->pin_status.release(), ctx->pin_plan.release(), ctx->pin_out.release();
@@ -1665,6 +1690,9 @@ void svgr_destroy(svgr_ctx *ctx)
             cudaEventDestroy(e);
     if (ctx->ev_up_begin)
         cudaEventDestroy(ctx->ev_up_begin);
+    for (auto &e : ctx->ev_done)
+        if (e)
+            cudaEventDestroy(e);
     if (ctx->up_stream)
         cudaStreamDestroy(ctx->up_stream);
     if (ctx->own_stream)
