@@ -19,16 +19,18 @@
 // evaluated in registers while compositing, so a child costs 4 B/px of reads and
 // the output is written exactly once (16 B/px).
 //
-// Tiling: CTA = 8 rows x 32 columns, one pixel (one float4, 16 B) per thread, a
-// warp covers 512 contiguous bytes of a row.  When an op has many sources (the
-// 935-layer group of demo/material-design.svg) warp 0 first culls the source list
-// against the tile rectangle into shared memory, preserving order.
+// Tiling: CTA = 32 rows x 32 columns of output, 256 threads, 4 pixels per thread (rows 8 apart), a warp covers
+// 512 contiguous bytes of an RGBA row.  cull_kernel (one warp per tile) first writes, for every tile, the list of
+// the op's sources that touch it, order preserved; the compose CTA copies its op, those sources and their paints
+// into shared memory in one pass and folds them in registers.
 #include "svgr_device.cuh"
 
 #define CMP_TR SVGR_CMP_TR   // 32 rows: 4 pixels per thread, 8 rows apart
 #define CMP_TC SVGR_CMP_TC   // 32 columns: one warp = 512 contiguous bytes of an RGBA row
 #define CMP_PX (CMP_TR / 8)
+#ifndef CMP_CAP
 #define CMP_CAP 48           // sources staged per round
+#endif
 
 __device__ __forceinline__ float4 blend_px(int mode, const float *k, float4 d, float4 s)
 {
