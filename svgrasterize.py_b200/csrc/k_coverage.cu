@@ -308,14 +308,16 @@ coverage_kernel(const TileRec *__restrict__ tiles, int n_tiles, const double2 *_
     __shared__ double s_r0[COV_THREADS], s_r1[COV_THREADS], s_c0[COV_THREADS], s_dxdy[COV_THREADS];
     __shared__ float s_dir[COV_THREADS];
     __shared__ uint16_t s_pairs[COV_THREADS * SVGR_BAND_ROWS];  // (edge << 4) | row of the band, compacted
-    __shared__ int s_wsum[COV_THREADS / 32];
+    __shared__ int s_npairs[2];
     __shared__ __align__(16) TileRec s_tile[2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // the trace tile starts zeroed and every tile leaves it zeroed again (the scan clears what it reads)
     for (int i = tid; i < SVGR_BAND_ROWS * SVGR_TILE_COLS / 4; i += COV_THREADS)
         reinterpret_cast<float4 *>(&trace[0][0])[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    int tile = blockIdx.x, cur = 0;
+    int tile = blockIdx.x, cur = 0, chunk_no = 0;
+    if (tid < 2)
+        s_npairs[tid] = 0;
     if (tile < n_tiles && tid < 3)
         reinterpret_cast<uint4 *>(&s_tile[0])[tid] = __ldg(reinterpret_cast<const uint4 *>(tiles + tile) + tid);
     __syncthreads();
@@ -338,7 +340,7 @@ coverage_kernel(const TileRec *__restrict__ tiles, int n_tiles, const double2 *_
 
         // ---- 1. accumulate the signed areas of this band's edges.  Per chunk of COV_THREADS edges: (a) one
         // thread per edge orients it, stores slope / start in shared memory and counts the rows of the band it
-        // crosses, (b) a block scan of the counts compacts the (edge, row) pairs into a list, (c) the pairs are
+        // crosses, (b) a shared counter hands out the slots of a compact (edge, row) pair list, (c) the pairs are
         // spread over all threads.  Flattened edges are short (2-3 rows): without the compaction a warp would
         // run the row arithmetic with 4 of its 32 lanes active.
         const int e_off = m.e_off, e_cnt = m.e_cnt;
@@ -376,27 +378,20 @@ coverage_kernel(const TileRec *__restrict__ tiles, int n_tiles, const double2 *_
                 s_dir[tid] = dir;
                 row_a = ya - yb, row_n = max(0, yz - ya);
             }
-            // exclusive scan of the row counts over the block: warp scan + the totals of the warps before this one
-            int incl = row_n;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o)
-                    incl += t;
+            // slots of the pair list are handed out by a shared counter (the order of the pairs does not matter:
+            // they are accumulated with atomics anyway); the counters of consecutive chunks alternate so that the
+            // reset of one never races with the readers of the other
+            int *counter = &s_npairs[chunk_no & 1];
+            if (row_n > 0) {
+                const int pair0 = atomicAdd(counter, row_n);
+                for (int k = 0; k < row_n; k++)
+                    s_pairs[pair0 + k] = (uint16_t)((tid << 4) | (row_a + k));
             }
-            if (lane == 31)
-                s_wsum[warp] = incl;
+            if (tid == 0)
+                s_npairs[(chunk_no + 1) & 1] = 0;
             __syncthreads();
-            int pair0 = incl - row_n, n_pairs = 0;
-#pragma unroll
-            for (int k = 0; k < COV_THREADS / 32; k++) {
-                const int t = s_wsum[k];
-                pair0 += k < warp ? t : 0;
-                n_pairs += t;
-            }
-            for (int k = 0; k < row_n; k++)
-                s_pairs[pair0 + k] = (uint16_t)((tid << 4) | (row_a + k));
-            __syncthreads();
+            const int n_pairs = *counter;
+            chunk_no++;
             for (int p = tid; p < n_pairs; p += COV_THREADS) {
                 const int pr = s_pairs[p];
                 const int ei = pr >> 4, yl = pr & (SVGR_BAND_ROWS - 1);
