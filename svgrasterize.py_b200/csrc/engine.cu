@@ -1702,6 +1702,18 @@ void svgr_destroy(svgr_ctx *ctx)
 
 const char *svgr_last_error(svgr_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
+// A call that failed half way may have left copies and kernels in flight on the side streams: nothing of it
+// may still be running when the caller reuses its buffers or renders again.
+static void drain_after_failure(svgr_ctx *ctx, cudaStream_t s)
+{
+    cudaStreamSynchronize(s);
+    if (ctx->up_stream)
+        cudaStreamSynchronize(ctx->up_stream);
+    if (ctx->copy_stream)
+        cudaStreamSynchronize(ctx->copy_stream);
+    cudaGetLastError();
+}
+
 int svgr_render(svgr_ctx *ctx, const svgr_program *prog, void *stream, int stop_after, uint8_t *out, int out_on_device,
                 int timing, svgr_stats *stats)
 {
@@ -1719,6 +1731,8 @@ int svgr_render(svgr_ctx *ctx, const svgr_program *prog, void *stream, int stop_
         cudaEventRecord(e1, s);
     if (rc == SVGR_OK)
         rc = run_pipeline(ctx, s, stop_after, out, out_on_device, timing, stats);
+    if (rc != SVGR_OK)
+        drain_after_failure(ctx, s);
     if (ctx->pending) {  // the call failed before the host tables were copied: nothing resident to re-render
         ctx->pending = nullptr;
         ctx->have_program = false;
@@ -1785,7 +1799,10 @@ int svgr_render_resident(svgr_ctx *ctx, void *stream, uint8_t *out_device, int t
         return SVGR_E_INVALID;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->own_stream;
-    return run_pipeline(ctx, s, SVGR_STOP_NONE, out_device, 1, timing, stats);
+    const int rc = run_pipeline(ctx, s, SVGR_STOP_NONE, out_device, 1, timing, stats);
+    if (rc != SVGR_OK)
+        drain_after_failure(ctx, s);
+    return rc;
 }
 
 int svgr_read_edges(svgr_ctx *ctx, double *edges, uint32_t *edge_path, int64_t cap, int64_t *n_edges)

@@ -239,3 +239,24 @@ def test_background_intersect_and_png(B, O):
     idat = png[png.index(b"IDAT") + 4: png.index(b"IEND") - 8]
     raw = zlib.decompress(idat)
     assert len(raw) == height * (1 + 4 * width)
+
+
+def test_engine_recovers_after_a_failed_call(B, O):
+    """A degenerate control-polygon leg makes the reference's stroker raise TypeError (bezier3_offset :2157,
+    line_offset returns None); the call fails half way through the pipeline, and the same engine must render
+    the next scene correctly (nothing of the failed call may still be in flight)."""
+    from oracle.stroke import stroke_path
+    from svgrasterize_b200 import synth
+
+    bad = synth.PathBuilder().move_to(0, 0).cubic_to(0, 1.2e-8, 30, 40, 50, 10).path()
+    with pytest.raises(TypeError):
+        stroke_path(bad, 3.0)
+    for _ in range(3):
+        with pytest.raises(TypeError):
+            bad.stroke(3.0)
+        scene = B.Scene.group([synth.icon_scene(5), B.Scene.stroke(bad, synth.color(0, 0, 1), 3.0)])
+        with pytest.raises(TypeError):
+            B.render_canvas(scene, (64, 64))
+        got = B.render_canvas(synth.icon_scene(7), synth.icon_size())
+        want = O.render_canvas(synth.icon_scene(7), synth.icon_size())
+        assert np.abs(got.astype(np.int16) - want.astype(np.int16)).max() <= 1
