@@ -1,5 +1,8 @@
+"""Runs the randomised GPU-vs-oracle comparison of test_gpu_fuzz.py over many more seeds and prints the worst
+difference (test infrastructure: it imports the oracle, so it lives under tests/).  python tests/fuzz_stats.py"""
 import sys, os, warnings
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE)); sys.path.insert(0, HERE)
 import numpy as np
 import svgrasterize_b200 as B
 from oracle import render as O

@@ -2,8 +2,8 @@
 """BASELINE.json's fifth configuration at its full size: 100 000 synthetic icon SVGs (seed = icon index) at
 256 x 256, encoded on the host cores and rendered through the public call (Engine.render, host buffers in and
 out) in batches of 2048.  Prints one JSON line: wall times, Mpx/s with and without the host encoding, a CRC of
-all result bytes, and two checks that do not depend on the size of the run -- sampled icons of the big run are
-byte-identical to the same icons rendered alone, and a few are within 1 LSB of the CPU oracle.
+all result bytes, and a check that does not depend on the size of the run -- sampled icons of the big run are
+byte-identical to the same icons rendered alone (whose parity with the oracle is what tests/ establish).
 
     python tools/run_c5_full.py [icons] [batch]
 """
@@ -71,23 +71,13 @@ def main():
     for i, ref in kept.items():
         single = eng.render(encode.encode_scene(synth.icon_scene(i), synth.icon_size()))["canvas"]
         same += int(np.array_equal(single[: px * 4], ref))
-    worst = None
-    try:
-        from oracle import render as oracle_render
-
-        worst = 0
-        for i in list(kept)[:6]:
-            want = oracle_render.render_canvas(synth.icon_scene(i), synth.icon_size()).reshape(-1)
-            worst = max(worst, int(np.abs(want.astype(np.int16) - kept[i].astype(np.int16)).max()))
-    except ImportError:
-        pass
     print(json.dumps({
         "config": f"c5 full size: {done} synthetic icons at 256 x 256, batches of {batch}", "icons": done,
         "host_encode_processes": procs, "wall_s": round(wall, 3), "render_s": round(t_render, 3),
         "mpx_s_wall_incl_encode": round(done * px / wall / 1e6, 1),
         "mpx_s_render_calls": round(done * px / t_render / 1e6, 1), "crc32_of_all_bytes": crc,
-        "sampled_icons_equal_to_single_renders": f"{same}/{len(kept)}", "worst_lsb_vs_oracle_on_6": worst}))
-    assert done == n and same == len(kept) and (worst is None or worst <= 1)
+        "sampled_icons_equal_to_single_renders": f"{same}/{len(kept)}"}))
+    assert done == n and same == len(kept)
 
 
 if __name__ == "__main__":

@@ -2,7 +2,10 @@
 """Times BASELINE.json's other configurations (they are parity-test cases, not bench lines) on the GPU:
 stage breakdown from svgr_render's CUDA events, resident re-render time, and checks against the golden bytes.
 
-    python tools/time_configs.py [--filter-n 8192] [--oracle]
+    python tools/time_configs.py [--filter-n 8192]
+
+The CPU oracle's time on the same scenes is measured by tests/time_oracle_configs.py (only tests/, smoke() and
+bench.py's CPU legs touch oracle/).
 """
 import argparse
 import json
@@ -43,7 +46,6 @@ def time_program(eng, prog, reps=5):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--filter-n", type=int, default=8192)
-    ap.add_argument("--oracle", action="store_true", help="also time the CPU oracle (1 core)")
     opts = ap.parse_args()
     eng = Engine(0)
     rows = []
@@ -62,12 +64,6 @@ def main():
                "mpx_s": round(size[0] * size[1] / ms / 1e3, 1), "encode_s": round(t_enc, 3),
                "max_lsb_vs_reference": diff,
                "stages_ms": {k[3:]: round(v, 3) for k, v in st.items() if k.startswith("ms_") and v > 0.0005}}
-        if opts.oracle:
-            from oracle import render as O
-
-            t0 = time.perf_counter()
-            O.render_canvas(scene, size, lin)
-            row["oracle_1core_s"] = round(time.perf_counter() - t0, 3)
         rows.append(row)
         print(json.dumps(row), flush=True)
     n = opts.filter_n
