@@ -224,7 +224,7 @@ def run_gpu(opts):
     stream = torch.cuda.current_stream()
 
     t0 = time.perf_counter()
-    prog, icon_progs = build_batch(opts.icons, rank * opts.icons, eng)
+    prog, icon_progs = build_batch(opts.icons, opts.seed0 + rank * opts.icons, eng)
     t_encode = time.perf_counter() - t0
     pins = pin_program(prog)
     n_px = opts.icons * ICON_PX * ICON_PX
@@ -262,7 +262,14 @@ def run_gpu(opts):
     torch.cuda.synchronize()
     sampler.stop_flag = True
     barrier()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_local = e0.elapsed_time(e1)
+    ms_total = max_over_ranks(ms_local)
+    ranks_ms = [ms_local / opts.steps]
+    if dist is not None:  # diagnostic only: the spread over ranks behind the max
+        t = torch.zeros(world, dtype=torch.float64, device="cuda")
+        t[rank] = ms_local / opts.steps
+        dist.all_reduce(t)
+        ranks_ms = [round(float(v), 3) for v in t.tolist()]
     sampler.join()
     ms_step = ms_total / opts.steps
     value = world * n_px / (ms_step * 1e-3) / 1e6
@@ -363,6 +370,7 @@ def run_gpu(opts):
         "gpu_launches": int(st["n_kernels"]) * opts.steps,
         "paths_per_s": world * len(prog.paths) / (ms_step * 1e-3),
         "stage_ms_per_step": {k: v / opts.steps for k, v in sorted(acc.items())},
+        "ranks_ms_per_step": ranks_ms,
         "roofline": roofline,
         "roofline_other": {k: v for k, v in kernels.items() if k != dominant},
         "host_encode_s_per_batch": t_encode,
@@ -386,6 +394,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--icons", type=int, default=2048, help="icons per GPU per step")
+    ap.add_argument("--seed0", type=int, default=0, help="first icon seed (diagnostics: render another rank's batch)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--e2e-workers", type=int, default=3, help="host threads (contexts) of the e2e leg")

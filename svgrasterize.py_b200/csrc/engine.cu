@@ -205,7 +205,8 @@ struct svgr_ctx {
     long long mask_pixels = 0, layer_pixels = 0, compose_bytes = 0, compose_bytes_8d = 0, canvas_pixels = 0;
     int n_levels = 0;
     DevBuf d_masks, d_band_cnt, d_band_off, d_band_cur, d_bin_edges, d_cov, d_layers, d_ops, d_srcs, d_focal_jobs,
-        d_focal_flags, d_canvas, d_q, d_tile_map, d_tile_rec, d_bin_data, d_heads[2], d_lists[2];
+        d_focal_flags, d_canvas, d_q, d_tile_map, d_tile_rec, d_bin_data, d_heads[2], d_lists[2], d_ovf_cubic[2],
+        d_ovf_path[2], d_ovf_depth[2], d_ovf_counts;
     long long bin_cap = 0;
     long long n_binned = 0;
     bool planned = false, covered = false, composed = false;
@@ -1207,16 +1208,35 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
         if (stop_after != SVGR_STOP_STROKE) {
             const double tol = 0.1;  // literal flatness of Path.mask (svgrasterize.py:955/:957)
             const double thr = (tol * tol) * 16;
+            // overflow lists of the multi-pass flatten (deep subdivision trees are re-spread over all warps)
+            svgr_flat_overflow ovf;
+            ovf.cap = 1 << 18;
+            for (int q = 0; q < 2; q++) {
+                CK(ctx->d_ovf_cubic[q].ensure((size_t)ovf.cap * 64));
+                CK(ctx->d_ovf_path[q].ensure((size_t)ovf.cap * 4));
+                CK(ctx->d_ovf_depth[q].ensure((size_t)ovf.cap));
+                ovf.cubic[q] = ctx->d_ovf_cubic[q].as<double>(), ovf.path[q] = ctx->d_ovf_path[q].as<uint32_t>();
+                ovf.depth[q] = ctx->d_ovf_depth[q].as<uint8_t>();
+            }
+            CK(ctx->d_ovf_counts.ensure(SVGR_FLAT_PASSES * sizeof(int)));
+            ovf.counts = ctx->d_ovf_counts.as<int>();
+            CK(cudaMemsetAsync(ovf.counts, 0, SVGR_FLAT_PASSES * sizeof(int), s));
             svgr_launch_flatten(ctx->d_seg_tag.as<uint8_t>(), ctx->d_seg_data.as<double>(), ctx->d_seg_path.as<uint32_t>(),
                                 ctx->n_seg, nullptr, ctx->d_paths.as<PathRec>(), thr, ctx->d_edges.as<double>(),
                                 ctx->d_edge_path.as<uint32_t>(), (unsigned long long)ctx->edge_cap, &d_st->n_edges,
-                                ctx->d_minmax.as<unsigned long long>(), SM, s);
+                                ctx->d_minmax.as<unsigned long long>(), SM, &ovf, s);
             if (S > 0)
                 svgr_launch_flatten(ctx->d_otag.as<uint8_t>(), ctx->d_odata.as<double>(), ctx->d_opath.as<uint32_t>(),
                                     ctx->outline_cap, &d_st->outline_count, ctx->d_paths.as<PathRec>(), thr,
                                     ctx->d_edges.as<double>(), ctx->d_edge_path.as<uint32_t>(),
                                     (unsigned long long)ctx->edge_cap, &d_st->n_edges,
-                                    ctx->d_minmax.as<unsigned long long>(), SM, s);
+                                    ctx->d_minmax.as<unsigned long long>(), SM, &ovf, s);
+            if (ctx->n_seg > 0 || S > 0) {
+                svgr_launch_flatten_overflow(ctx->d_paths.as<PathRec>(), thr, ctx->d_edges.as<double>(),
+                                             ctx->d_edge_path.as<uint32_t>(), (unsigned long long)ctx->edge_cap,
+                                             &d_st->n_edges, ctx->d_minmax.as<unsigned long long>(), SM, &ovf, s);
+                n_kernels += SVGR_FLAT_PASSES - 1;
+            }
             svgr_launch_bounds(ctx->d_minmax.as<unsigned long long>(), ctx->d_paths.as<PathRec>(), ctx->n_path,
                                ctx->d_boxes.as<PathBox>(), ctx->d_minmax_f64.as<double>(), s);
             n_kernels += (ctx->n_seg > 0) + (S > 0) + (ctx->n_path > 0);
@@ -1550,6 +1570,14 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
     ctx->n_binned = ((StatusBlock *)ctx->pin_status.p)->binned_total;
+    if (getenv("SVGR_FLAT_DEBUG") && ctx->d_ovf_counts.p) {  // nodes deferred by each flatten pass
+        int counts[SVGR_FLAT_PASSES] = {0};
+        cudaMemcpy(counts, ctx->d_ovf_counts.p, sizeof counts, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "flatten overflow per pass:");
+        for (int q = 0; q < SVGR_FLAT_PASSES; q++)
+            fprintf(stderr, " %d", counts[q]);
+        fprintf(stderr, "\n");
+    }
     if (ctx->n_binned > ctx->bin_cap) {
         // the guess was too small: the masks of the overflowing bands are wrong.  Grow and run again.
         ctx->bin_cap = ctx->n_binned + ctx->n_binned / 8 + 1024;
@@ -1666,7 +1694,8 @@ void svgr_destroy(svgr_ctx *ctx)
                       &ctx->d_minmax_f64, &ctx->d_status, &ctx->d_masks, &ctx->d_band_cnt, &ctx->d_band_off,
                       &ctx->d_band_cur, &ctx->d_bin_edges, &ctx->d_cov, &ctx->d_layers, &ctx->d_ops, &ctx->d_srcs,
                       &ctx->d_focal_jobs, &ctx->d_focal_flags, &ctx->d_canvas, &ctx->d_q, &ctx->d_tile_map, &ctx->d_tile_rec, &ctx->d_bin_data, &ctx->d_heads[0], &ctx->d_heads[1], &ctx->d_lists[0],
-                      &ctx->d_lists[1]};
+                      &ctx->d_lists[1], &ctx->d_ovf_cubic[0], &ctx->d_ovf_cubic[1], &ctx->d_ovf_path[0], &ctx->d_ovf_path[1],
+                      &ctx->d_ovf_depth[0], &ctx->d_ovf_depth[1], &ctx->d_ovf_counts};
     for (DevBuf *b : bufs)
         b->release();
     ctx->pin_boxes.release(), ctx->pin_status.release(), ctx->pin_plan.release(), ctx->pin_out.release();

@@ -22,6 +22,7 @@
 // at t = 1/2 and pushes both halves.  Lanes therefore stay busy regardless of
 // how unevenly the subdivision depth is distributed over the input curves.
 #include "svgr_kernels.h"
+#include <algorithm>
 
 #define FLAT_WARPS 4
 #define FLAT_Q 160       // work-list slots per warp
@@ -59,9 +60,30 @@ __device__ __forceinline__ void bounds_update(unsigned long long *minmax, uint32
     atomicMax(mm + 3, key_of(c0 < c1 ? c1 : c0));
 }
 
+// Per-lane running bounds of the path the lane is emitting edges for: the global min / max atomics are issued
+// when the lane moves on to another path (and at the end), not per edge.  A path whose outline explodes into
+// thousands of edges (a stroke offset near a cusp) would otherwise serialise 4 atomics per edge on the same four
+// addresses.
+struct LaneBounds {
+    uint32_t path;
+    double mn_r, mn_c, mx_r, mx_c;
+};
+
+__device__ __forceinline__ void bounds_flush(unsigned long long *minmax, const LaneBounds &b)
+{
+    if (b.path == 0xffffffffu)
+        return;
+    unsigned long long *mm = minmax + 4ull * b.path;
+    atomicMin(mm + 0, key_of(b.mn_r));
+    atomicMin(mm + 1, key_of(b.mn_c));
+    atomicMax(mm + 2, key_of(b.mx_r));
+    atomicMax(mm + 3, key_of(b.mx_c));
+}
+
 __device__ __forceinline__ void emit_edges(bool has, double r0, double c0, double r1, double c1, uint32_t path,
                                            double *edges, uint32_t *edge_path, unsigned long long cap,
-                                           unsigned long long *n_edges, unsigned long long *minmax, int lane)
+                                           unsigned long long *n_edges, unsigned long long *minmax, int lane,
+                                           LaneBounds &lb)
 {
     unsigned m = __ballot_sync(0xffffffffu, has);
     if (!m)
@@ -79,16 +101,41 @@ __device__ __forceinline__ void emit_edges(bool has, double r0, double c0, doubl
             e[1] = make_double2(r1, c1);
             edge_path[idx] = path;
         }
-        bounds_update(minmax, path, r0, c0, r1, c1);
+        const double lo_r = r0 < r1 ? r0 : r1, hi_r = r0 < r1 ? r1 : r0;
+        const double lo_c = c0 < c1 ? c0 : c1, hi_c = c0 < c1 ? c1 : c0;
+        if (lb.path != path) {
+            bounds_flush(minmax, lb);
+            lb.path = path, lb.mn_r = lo_r, lb.mn_c = lo_c, lb.mx_r = hi_r, lb.mx_c = hi_c;
+        } else {
+            // key order: the comparisons below pick what atomicMin / atomicMax on the ordered keys would keep
+            lb.mn_r = key_of(lo_r) < key_of(lb.mn_r) ? lo_r : lb.mn_r;
+            lb.mn_c = key_of(lo_c) < key_of(lb.mn_c) ? lo_c : lb.mn_c;
+            lb.mx_r = key_of(hi_r) > key_of(lb.mx_r) ? hi_r : lb.mx_r;
+            lb.mx_c = key_of(hi_c) > key_of(lb.mx_c) ? hi_c : lb.mx_c;
+        }
     }
 }
+
+// A warp works through the subdivision tree of its 32 segments alone.  That is fine for ordinary curves (depth
+// 3-5), but one curve that needs depth 12 (a stroke outline blown up by a cusp: thousands of edges) kept a single
+// warp busy for 0.8 ms while the rest of the GPU had finished.  So the tree is cut every FLAT_PASS_DEPTH levels:
+// a node that is still not flat at the pass's depth limit is appended to a global overflow list instead of being
+// split locally, and the next pass (same kernel, reading that list: `in`) spreads those nodes over all warps
+// again.  The splits are the same de Casteljau steps in the same arithmetic, so the edges are bit-identical.
+struct FlatOverflow {
+    double *cubic;    // 8 doubles per node (already in presentation space)
+    uint32_t *path;
+    uint8_t *depth;
+    int *count;       // nodes appended (may exceed cap: the excess was split locally instead)
+    int cap;
+};
 
 __global__ void __launch_bounds__(FLAT_WARPS * 32)
 flatten_kernel(const uint8_t *__restrict__ seg_tag, const double *__restrict__ seg_data,
                const uint32_t *__restrict__ seg_path, long long n_seg_host, const int *__restrict__ n_seg_dev,
                const PathRec *__restrict__ paths, double thr, double *__restrict__ edges,
                uint32_t *__restrict__ edge_path, unsigned long long cap, unsigned long long *n_edges,
-               unsigned long long *minmax)
+               unsigned long long *minmax, FlatOverflow in, FlatOverflow out, int depth_limit)
 {
     __shared__ double st[FLAT_WARPS][8][FLAT_Q];
     __shared__ uint32_t st_path[FLAT_WARPS][FLAT_Q];
@@ -101,24 +148,50 @@ flatten_kernel(const uint8_t *__restrict__ seg_tag, const double *__restrict__ s
         long long nd = *n_seg_dev;
         n_seg = nd < n_seg ? nd : n_seg;
     }
-    const long long n_chunks = (n_seg + 31) >> 5;
+    if (in.cubic) {
+        long long nd = *in.count;
+        n_seg = nd < in.cap ? nd : in.cap;
+    }
+    // segments per warp and refill: 32, except that a short overflow list is spread one node (or a few) per warp --
+    // 32 deferred nodes in one warp would be the same lonely tree again, 5 levels further down
+    int per = 32;
+    if (in.cubic) {
+        const long long warps = (long long)gridDim.x * FLAT_WARPS;
+        const long long fair = (n_seg + warps - 1) / warps;
+        per = (int)(fair < 1 ? 1 : (fair > 32 ? 32 : fair));
+    }
+    const long long n_chunks = (n_seg + per - 1) / per;
     long long chunk = (long long)blockIdx.x * FLAT_WARPS + w;
     const long long chunk_step = (long long)gridDim.x * FLAT_WARPS;
     int count = 0;
+    LaneBounds lb;
+    lb.path = 0xffffffffu, lb.mn_r = lb.mn_c = lb.mx_r = lb.mx_c = 0.0;
 
     for (;;) {
         // ---- refill: take the next 32 segments while there is room for 32 cubics
         if (count <= FLAT_QCAP - 64 && chunk < n_chunks) {
-            long long i = (chunk << 5) + lane;
+            // input segments: 32 consecutive ones per warp (coalesced).  Deferred nodes: lane l of chunk c takes node
+            // c + l * n_chunks -- the children of one exploding curve sit next to each other in the list and must
+            // not end up in the same warp again (a node is a 64-byte record: the strided read costs nothing)
+            long long i = in.cubic ? chunk + (long long)lane * n_chunks : (chunk << 5) + lane;
+            if (lane >= per)
+                i = n_seg;
             chunk += chunk_step;
             int tag = SEG_NOP;
             double p[8];
             uint32_t path = 0;
+            int depth0 = 0;
             if (i < n_seg)
-                tag = seg_tag[i];
+                tag = in.cubic ? -1 : seg_tag[i];
             bool is_line = tag == SEG_LINE || tag == SEG_CLOSED || tag == SEG_UNCLOSED;
-            bool is_curve = tag == SEG_QUAD || tag == SEG_CUBIC;
-            if (is_line || is_curve) {
+            bool is_curve = tag == SEG_QUAD || tag == SEG_CUBIC || tag == -1;
+            if (tag == -1) {  // a node deferred by the pass before: transformed cubic, its path and depth
+                const double2 *d = reinterpret_cast<const double2 *>(in.cubic + 8 * i);
+                double2 a = d[0], b = d[1], c = d[2], e = d[3];
+                p[0] = a.x, p[1] = a.y, p[2] = b.x, p[3] = b.y, p[4] = c.x, p[5] = c.y, p[6] = e.x, p[7] = e.y;
+                path = in.path[i];
+                depth0 = in.depth[i];
+            } else if (is_line || is_curve) {
                 const double2 *d = reinterpret_cast<const double2 *>(seg_data + 8 * i);
                 double2 a = d[0], b = d[1];
                 p[0] = a.x, p[1] = a.y, p[2] = b.x, p[3] = b.y;
@@ -153,7 +226,7 @@ flatten_kernel(const uint8_t *__restrict__ seg_tag, const double *__restrict__ s
                     }
                 }
             }
-            emit_edges(is_line, p[0], p[1], p[2], p[3], path, edges, edge_path, cap, n_edges, minmax, lane);
+            emit_edges(is_line, p[0], p[1], p[2], p[3], path, edges, edge_path, cap, n_edges, minmax, lane, lb);
             unsigned mc = __ballot_sync(0xffffffffu, is_curve);
             if (is_curve) {
                 int pos = count + __popc(mc & ((1u << lane) - 1));
@@ -161,7 +234,7 @@ flatten_kernel(const uint8_t *__restrict__ seg_tag, const double *__restrict__ s
                 for (int k = 0; k < 8; k++)
                     st[w][k][pos] = p[k];
                 st_path[w][pos] = path;
-                st_depth[w][pos] = 0;
+                st_depth[w][pos] = (uint8_t)depth0;
             }
             count += __popc(mc);
             __syncwarp();
@@ -201,9 +274,30 @@ flatten_kernel(const uint8_t *__restrict__ seg_tag, const double *__restrict__ s
             double f = (ux > uy ? ux : uy) + (vx > vy ? vx : vy);
             flat = (f < thr) || depth >= FLAT_MAXD;
         }
-        emit_edges(active && flat, c[0], c[1], c[6], c[7], path, edges, edge_path, cap, n_edges, minmax, lane);
+        emit_edges(active && flat, c[0], c[1], c[6], c[7], path, edges, edge_path, cap, n_edges, minmax, lane, lb);
 
         bool split = active && !flat;
+        // at the pass's depth limit a node goes to the overflow list (if there is room) instead of being split here
+        if (out.cubic) {
+            const bool defer = split && depth >= depth_limit;
+            const unsigned md = __ballot_sync(0xffffffffu, defer);
+            if (md) {
+                int base = 0;
+                const int leader = __ffs(md) - 1;
+                if (lane == leader)
+                    base = atomicAdd(out.count, __popc(md));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                const int idx = base + __popc(md & ((1u << lane) - 1));
+                if (defer && idx < out.cap) {
+                    double2 *d = reinterpret_cast<double2 *>(out.cubic + 8ll * idx);
+                    d[0] = make_double2(c[0], c[1]), d[1] = make_double2(c[2], c[3]);
+                    d[2] = make_double2(c[4], c[5]), d[3] = make_double2(c[6], c[7]);
+                    out.path[idx] = path;
+                    out.depth[idx] = (uint8_t)depth;
+                    split = false;
+                }
+            }
+        }
         unsigned ms = __ballot_sync(0xffffffffu, split);
         if (split) {
             int pos = count + 2 * __popc(ms & ((1u << lane) - 1));
@@ -229,6 +323,7 @@ flatten_kernel(const uint8_t *__restrict__ seg_tag, const double *__restrict__ s
         count += 2 * __popc(ms);
         __syncwarp();
     }
+    bounds_flush(minmax, lb);
 }
 
 __global__ void minmax_init_kernel(unsigned long long *minmax, int n_paths)
@@ -332,7 +427,7 @@ void svgr_launch_minmax_init(unsigned long long *minmax, int n, cudaStream_t s)
 void svgr_launch_flatten(const uint8_t *seg_tag, const double *seg_data, const uint32_t *seg_path, long long n_seg,
                          const int *n_seg_dev, const PathRec *paths, double thr, double *edges, uint32_t *edge_path,
                          unsigned long long cap, unsigned long long *n_edges, unsigned long long *minmax, int sm_count,
-                         cudaStream_t s)
+                         const svgr_flat_overflow *ovf, cudaStream_t s)
 {
     if (n_seg <= 0)
         return;
@@ -341,8 +436,32 @@ void svgr_launch_flatten(const uint8_t *seg_tag, const double *seg_data, const u
     long long max_blocks = (long long)sm_count * 8;
     if (blocks > max_blocks)
         blocks = max_blocks;
+    FlatOverflow none = {nullptr, nullptr, nullptr, nullptr, 0}, out = none;
+    if (ovf)
+        out = {ovf->cubic[0], ovf->path[0], ovf->depth[0], ovf->counts + 0, ovf->cap};
     flatten_kernel<<<(unsigned)blocks, FLAT_WARPS * 32, 0, s>>>(seg_tag, seg_data, seg_path, n_seg, n_seg_dev, paths, thr,
-                                                                edges, edge_path, cap, n_edges, minmax);
+                                                                edges, edge_path, cap, n_edges, minmax, none, out,
+                                                                SVGR_FLAT_PASS_DEPTH);
+}
+
+// The passes behind the first one: pass k reads the nodes pass k - 1 deferred (counts[k - 1], buffers alternate) and
+// defers what is still not flat SVGR_FLAT_PASS_DEPTH levels further down.  The host does not know the counts: every
+// pass is launched, an empty one costs a launch of idle blocks.
+void svgr_launch_flatten_overflow(const PathRec *paths, double thr, double *edges, uint32_t *edge_path,
+                                  unsigned long long cap, unsigned long long *n_edges, unsigned long long *minmax,
+                                  int sm_count, const svgr_flat_overflow *ovf, cudaStream_t s)
+{
+    for (int k = 1; k < SVGR_FLAT_PASSES; k++) {
+        FlatOverflow in = {ovf->cubic[(k - 1) & 1], ovf->path[(k - 1) & 1], ovf->depth[(k - 1) & 1], ovf->counts + (k - 1),
+                           ovf->cap};
+        FlatOverflow out = {ovf->cubic[k & 1], ovf->path[k & 1], ovf->depth[k & 1], ovf->counts + k, ovf->cap};
+        if (k == SVGR_FLAT_PASSES - 1)
+            out.cubic = nullptr;  // the last pass finishes everything locally (depth cap FLAT_MAXD)
+        int blocks = sm_count * 4;
+        flatten_kernel<<<blocks, FLAT_WARPS * 32, 0, s>>>(nullptr, nullptr, nullptr, (long long)ovf->cap, nullptr, paths, thr,
+                                                          edges, edge_path, cap, n_edges, minmax, in, out,
+                                                          SVGR_FLAT_PASS_DEPTH * (k + 1));
+    }
 }
 
 void svgr_launch_bounds(const unsigned long long *minmax, const PathRec *paths, int n_paths, PathBox *boxes,

@@ -21,10 +21,23 @@ struct RenderTables {
 
 // k_flatten.cu
 void svgr_launch_minmax_init(unsigned long long *minmax, int n, cudaStream_t s);
+// overflow lists of the multi-pass flatten (k_flatten.cu): two buffers used alternately, one counter per pass
+#define SVGR_FLAT_PASS_DEPTH 5
+#define SVGR_FLAT_PASSES 5  // depth limits 5, 10, 15, 20, then the depth cap
+struct svgr_flat_overflow {
+    double *cubic[2];
+    uint32_t *path[2];
+    uint8_t *depth[2];
+    int *counts;  // SVGR_FLAT_PASSES ints, zeroed before the first pass
+    int cap;
+};
 void svgr_launch_flatten(const uint8_t *seg_tag, const double *seg_data, const uint32_t *seg_path, long long n_seg,
                          const int *n_seg_dev, const PathRec *paths, double thr, double *edges, uint32_t *edge_path,
                          unsigned long long cap, unsigned long long *n_edges, unsigned long long *minmax, int sm_count,
-                         cudaStream_t s);
+                         const svgr_flat_overflow *ovf, cudaStream_t s);
+void svgr_launch_flatten_overflow(const PathRec *paths, double thr, double *edges, uint32_t *edge_path,
+                                  unsigned long long cap, unsigned long long *n_edges, unsigned long long *minmax,
+                                  int sm_count, const svgr_flat_overflow *ovf, cudaStream_t s);
 void svgr_launch_bounds(const unsigned long long *minmax, const PathRec *paths, int n_paths, PathBox *boxes,
                         double *minmax_f64, cudaStream_t s);
 void svgr_launch_cloud_bounds(const double *edges, const uint32_t *edge_path, const unsigned long long *n_edges,
