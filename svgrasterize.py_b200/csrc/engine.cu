@@ -170,6 +170,9 @@ struct svgr_ctx {
     long long n_stroke_seg = 0;
     long long canvas_bytes = 0;
     DevBuf d_seg_tag, d_seg_data, d_seg_path, d_paths, d_strokes, d_ssub_off, d_ssub_job, d_stag, d_sdata, d_sseg_job;
+    DevBuf d_sitems;            // stroke assembly work items: (sub-path, first segment, end segment), <= 256 segments each
+    std::vector<int> h_sitems;
+    int n_sitems = 0;
     DevBuf d_paints, d_stops, d_matrices, d_weights;
     std::vector<PathRec> h_paths;
     std::vector<PaintRec> h_paints;
@@ -1088,6 +1091,19 @@ static int load_program(svgr_ctx *ctx, const svgr_program *p, cudaStream_t s, bo
     CK(upload(ctx->d_strokes, p->strokes, (size_t)p->n_stroke, s));
     CK(upload(ctx->d_ssub_off, p->stroke_sub_off, p->n_stroke_sub > 0 ? (size_t)p->n_stroke_sub + 1 : 0, s));
     CK(upload(ctx->d_ssub_job, p->stroke_sub_job, (size_t)p->n_stroke_sub, s));
+    {   // one warp assembles the outline of at most 256 consecutive segments of a sub-path
+        ctx->h_sitems.clear();
+        for (int q = 0; q < p->n_stroke_sub; q++) {
+            const int a = p->stroke_sub_off[q], b = p->stroke_sub_off[q + 1];
+            for (int x = a; x < b; x += 256) {
+                ctx->h_sitems.push_back(q);
+                ctx->h_sitems.push_back(x);
+                ctx->h_sitems.push_back(std::min(x + 256, b));
+            }
+        }
+        ctx->n_sitems = (int)(ctx->h_sitems.size() / 3);
+        CK(upload(ctx->d_sitems, ctx->h_sitems.data(), ctx->h_sitems.size(), s));
+    }
     CK(upload(ctx->d_stag, p->stroke_tag, (size_t)p->n_stroke_seg, s));
     CK(upload(ctx->d_sdata, p->stroke_data, (size_t)p->n_stroke_seg * 8, s));
     CK(upload(ctx->d_sseg_job, p->stroke_seg_job, (size_t)p->n_stroke_seg, s));
@@ -1195,7 +1211,8 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
             svgr_launch_exclusive_scan(ctx->d_sbound.as<int>(), ctx->d_sout_off.as<int>(), nSub, ctx->d_scan_tmp.as<int>(),
                                        &d_st->outline_total, s);
             svgr_launch_stroke_assemble(ctx->d_stag.as<uint8_t>(), ctx->d_ssub_off.as<int>(), ctx->d_ssub_job.as<int>(),
-                                        ctx->d_strokes.as<StrokeRec>(), nSub, nS, ctx->d_soffs.as<int>(), ctx->d_pool.p,
+                                        ctx->d_strokes.as<StrokeRec>(), nSub, nS, ctx->d_sitems.as<int>(), ctx->n_sitems,
+                                        ctx->d_soffs.as<int>(), ctx->d_pool.p,
                                         ctx->d_sbound.as<int>(), ctx->d_sout_off.as<int>(), &d_st->outline_total, 0,
                                         ctx->outline_cap, ctx->d_otag.as<uint8_t>(), ctx->d_odata.as<double>(),
                                         ctx->d_opath.as<uint32_t>(), ctx->d_osub.as<int32_t>(), &d_st->outline_count,
@@ -1686,7 +1703,7 @@ void svgr_destroy(svgr_ctx *ctx)
     if (!ctx)
         return;
     cudaSetDevice(ctx->device);
-    DevBuf *bufs[] = {&ctx->d_seg_tag, &ctx->d_seg_data, &ctx->d_seg_path, &ctx->d_paths, &ctx->d_strokes, &ctx->d_ssub_off,
+    DevBuf *bufs[] = {&ctx->d_sitems, &ctx->d_seg_tag, &ctx->d_seg_data, &ctx->d_seg_path, &ctx->d_paths, &ctx->d_strokes, &ctx->d_ssub_off,
                       &ctx->d_ssub_job, &ctx->d_stag, &ctx->d_sdata, &ctx->d_sseg_job, &ctx->d_paints, &ctx->d_stops,
                       &ctx->d_matrices, &ctx->d_weights, &ctx->d_scounts, &ctx->d_soffs, &ctx->d_scan_tmp, &ctx->d_pool,
                       &ctx->d_sbound, &ctx->d_sout_off, &ctx->d_sout_total, &ctx->d_otag, &ctx->d_odata, &ctx->d_opath,

@@ -424,22 +424,22 @@ __global__ void stroke_bound_kernel(const int *__restrict__ sub_off, int n_sub, 
     bound[s] = nc == 0 ? 0 : 3 * nc + 10;
 }
 
-struct SegSink {
+// Output of the assembly: every curve of a sub-path owns three consecutive outline slots (at most two join curves
+// before it, then the curve itself), the cap / closing join after the forward side and the one at the end own
+// three each; unused slots are SEG_NOP (skipped by the flattener and by svgr_read_outline).  With fixed slots a
+// curve's output depends on its neighbour only, so the lanes of a warp assemble one sub-path together.
+struct OutlineOut {
     uint8_t *tag;
     double *data;
     uint32_t *path;
     int32_t *sub;  // output sub-path id (2 * input sub-path + part), may be null
-    long long base;
-    long long cap;  // global capacity of the outline buffers
-    int n, limit;
+    long long base, cap;
+    int limit;
     uint32_t path_id;
-    int sub_id;
-    DCurve last, first;
-    int n_in_sub;
-    __device__ __forceinline__ void push(const DCurve &c)
+    __device__ __forceinline__ void put(int k, const DCurve &c, int sub_id) const
     {
-        long long i = base + n;
-        if (n < limit && i < cap) {
+        const long long i = base + k;
+        if (k < limit && i < cap) {
             tag[i] = (uint8_t)(c.n - 2);
             double2 *d = reinterpret_cast<double2 *>(data + 8 * i);
             d[0] = make_double2(c.p[0], c.p[1]);
@@ -450,35 +450,34 @@ struct SegSink {
             if (sub)
                 sub[i] = sub_id;
         }
-        if (n_in_sub == 0)
-            first = c;
-        n++;
-        n_in_sub++;
-        last = c;
+    }
+    __device__ __forceinline__ void nop(int k) const
+    {
+        const long long i = base + k;
+        if (k < limit && i < cap) {
+            tag[i] = SEG_NOP;
+            path[i] = path_id;
+            if (sub)
+                sub[i] = -1;
+        }
+    }
+    // slots k .. k + 2: the join from `prev` (if any) and then the curve; returns nothing
+    __device__ __forceinline__ void curve_with_join(int k, const DCurve *prev, const DCurve &c, int join, int sub_id) const
+    {
+        int n = 0;
+        if (prev) {
+            Sink t = {nullptr, 0, 0, {}};
+            DCurve tmp[2];
+            t.out = tmp, t.cap = 2;
+            stroke_join(*prev, c, join, t);
+            for (int q = 0; q < t.n && q < 2; q++)
+                put(k + n++, tmp[q], sub_id);
+        }
+        put(k + n++, c, sub_id);
+        for (; n < 3; n++)
+            nop(k + n);
     }
 };
-
-// adapter: joins / caps push through a Sink interface
-__device__ __forceinline__ void seg_join(SegSink &o, const DCurve &next, int join)
-{
-    Sink t = {nullptr, 0, 0, {}};
-    DCurve tmp[2];
-    t.out = tmp, t.cap = 2;
-    stroke_join(o.last, next, join, t);
-    for (int k = 0; k < t.n && k < 2; k++)
-        o.push(tmp[k]);
-}
-
-__device__ __forceinline__ bool seg_cap(SegSink &o, const double *p0, const double *p1, int cap)
-{
-    Sink t = {nullptr, 0, 0, {}};
-    DCurve tmp[3];
-    t.out = tmp, t.cap = 3;
-    bool ok = stroke_cap(p0, p1, cap, t);
-    for (int k = 0; k < t.n && k < 3; k++)
-        o.push(tmp[k]);
-    return ok;
-}
 
 __device__ __forceinline__ DCurve reversed(const DCurve &c)
 {
@@ -493,78 +492,144 @@ __device__ __forceinline__ DCurve reversed(const DCurve &c)
     return r;
 }
 
-// Phase B: Path.stroke's per-sub-path assembly (svgrasterize.py:1147-1178)
+// Phase B: Path.stroke's per-sub-path assembly (svgrasterize.py:1147-1178), one warp per sub-path.  The reference
+// walks: forward offset curves with a join before each but the first; then, closed: the join back to the first
+// curve (and the backward side starts a new sub-path), open: the cap over to the end of the backward side; the
+// backward curves reversed, in reverse order, a join before each (the first one joins to the cap's last curve);
+// finally closed: the join back to the first backward curve, open: the cap back to the start.
 __global__ void stroke_assemble_kernel(const uint8_t *__restrict__ in_tag, const int *__restrict__ sub_off,
                                        const int *__restrict__ sub_job, const StrokeRec *__restrict__ jobs, int n_sub,
-                                       int n_seg, const int *__restrict__ offs, const DCurve *__restrict__ pool, const int *__restrict__ bound,
+                                       int n_seg, const int *__restrict__ items, int n_items,
+                                       const int *__restrict__ offs, const DCurve *__restrict__ pool, const int *__restrict__ bound,
                                        const int *__restrict__ out_off, const int *__restrict__ out_total,
                                        long long out_base, long long out_cap, uint8_t *__restrict__ out_tag,
                                        double *__restrict__ out_data, uint32_t *__restrict__ out_path,
                                        int32_t *__restrict__ out_sub, int *__restrict__ n_out_dev, int *__restrict__ err)
 {
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s == 0 && n_out_dev)
+    // work item = (sub-path, segment range): a long polyline is cut into ranges of <= 256 segments, a warp each
+    const int item = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n_out_dev)
         *n_out_dev = (int)min((long long)*out_total + out_base, out_cap);
-    if (s >= n_sub)
+    if (item >= n_items)
         return;
-    int a = sub_off[s], b = sub_off[s + 1];
-    int limit = bound[s];
+    const int s = items[3 * item], ia = items[3 * item + 1], ib = items[3 * item + 2];
+    const int a = sub_off[s], b = sub_off[s + 1];
+    const int limit = bound[s];
     if (b <= a || limit == 0)
         return;
+    const bool first_range = ia == a, last_range = ib == b;
     const StrokeRec &job = jobs[sub_job[s]];
-    int f0 = offs[a], f1 = offs[b];
-    int b0 = offs[n_seg + a], b1 = offs[n_seg + b];
-    int nf = f1 - f0, nb = b1 - b0;
-    SegSink o;
+    const int f0 = offs[a], f1 = offs[b];
+    const int b0 = offs[n_seg + a], b1 = offs[n_seg + b];
+    const int nf = f1 - f0, nb = b1 - b0;
+    OutlineOut o;
     o.tag = out_tag, o.data = out_data, o.path = out_path, o.sub = out_sub;
-    o.base = out_base + out_off[s], o.cap = out_cap, o.n = 0, o.limit = limit;
-    o.path_id = (uint32_t)job.path, o.sub_id = 2 * s, o.n_in_sub = 0;
-    bool closed = in_tag[b - 1] == SEG_CLOSED;
+    o.base = out_base + out_off[s], o.cap = out_cap, o.limit = limit, o.path_id = (uint32_t)job.path;
+    if (nf == 0) {
+        if (first_range)
+            for (int k = lane; k < limit; k += 32)
+                o.nop(k);
+        return;
+    }
+    // this range's curves on both sides
+    const int fi0 = offs[ia] - f0, fi1 = offs[ib] - f0;
+    const int bm0 = offs[n_seg + ia] - b0, bm1 = offs[n_seg + ib] - b0;
+    const bool closed = in_tag[b - 1] == SEG_CLOSED;
+    const int join = job.join, sub_f = 2 * s, sub_b = closed ? 2 * s + 1 : 2 * s;
     bool ok = true;
-    if (nf > 0) {
-        for (int i = 0; i < nf; i++) {
-            DCurve c = pool[f0 + i];
-            if (o.n_in_sub > 0)
-                seg_join(o, c, job.join);
-            o.push(c);
+    // ---- forward side: curve i owns slots 3 i .. 3 i + 2
+    for (int i = fi0 + lane; i < fi1; i += 32) {
+        const DCurve c = pool[f0 + i];
+        if (i > 0) {
+            const DCurve prev = pool[f0 + i - 1];
+            o.curve_with_join(3 * i, &prev, c, join, sub_f);
+        } else {
+            o.curve_with_join(0, nullptr, c, join, sub_f);
         }
+    }
+    // ---- between the sides: slots 3 nf .. 3 nf + 2 (lane 0 of the last range)
+    const int kmid = 3 * nf;
+    if (lane == 0 && last_range) {
+        const DCurve last_fwd = pool[f1 - 1];
+        int n = 0;
         if (closed) {
-            seg_join(o, o.first, job.join);
-            o.sub_id = 2 * s + 1;  // forward and backward outlines are separate sub-paths (:1159-1162)
-            o.n_in_sub = 0;
+            Sink t = {nullptr, 0, 0, {}};
+            DCurve tmp[2];
+            t.out = tmp, t.cap = 2;
+            stroke_join(last_fwd, pool[f0], join, t);
+            for (int q = 0; q < t.n && q < 2; q++)
+                o.put(kmid + n++, tmp[q], sub_f);
         } else if (nb > 0) {
-            DCurve lb = pool[b0 + nb - 1];
-            double p0[2] = {o.last.p[2 * (o.last.n - 1)], o.last.p[2 * (o.last.n - 1) + 1]};
-            double p1[2] = {lb.p[2 * (lb.n - 1)], lb.p[2 * (lb.n - 1) + 1]};
-            ok = seg_cap(o, p0, p1, job.cap) && ok;
+            const DCurve lb = pool[b0 + nb - 1];
+            const double p0[2] = {last_fwd.p[2 * (last_fwd.n - 1)], last_fwd.p[2 * (last_fwd.n - 1) + 1]};
+            const double p1[2] = {lb.p[2 * (lb.n - 1)], lb.p[2 * (lb.n - 1) + 1]};
+            Sink t = {nullptr, 0, 0, {}};
+            DCurve tmp[3];
+            t.out = tmp, t.cap = 3;
+            ok = stroke_cap(p0, p1, job.cap, t) && ok;
+            for (int q = 0; q < t.n && q < 3; q++)
+                o.put(kmid + n++, tmp[q], sub_f);
         }
-        for (int i = nb - 1; i >= 0; i--) {
-            DCurve r = reversed(pool[b0 + i]);
-            if (o.n_in_sub > 0)
-                seg_join(o, r, job.join);
-            o.push(r);
+        for (; n < 3; n++)
+            o.nop(kmid + n);
+    }
+    // ---- backward side, reversed curves in reverse order: the j-th one owns slots 3 nf + 3 + 3 j ..
+    for (int m = bm1 - 1 - lane; m >= bm0; m -= 32) {
+        const int j = nb - 1 - m;  // position on the backward side
+        const DCurve r = reversed(pool[b0 + m]);
+        const int k = kmid + 3 + 3 * j;
+        if (j > 0) {
+            const DCurve prev = reversed(pool[b0 + nb - j]);
+            o.curve_with_join(k, &prev, r, join, sub_b);
+        } else if (!closed) {
+            // the first backward curve joins to the last curve of the cap (recomputed here: whichever lane owns
+            // j == 0 -- trailing degenerate segments have no curves -- need not be the one that wrote the cap)
+            const DCurve last_fwd = pool[f1 - 1], lb = pool[b0 + nb - 1];
+            const double p0[2] = {last_fwd.p[2 * (last_fwd.n - 1)], last_fwd.p[2 * (last_fwd.n - 1) + 1]};
+            const double p1[2] = {lb.p[2 * (lb.n - 1)], lb.p[2 * (lb.n - 1) + 1]};
+            Sink t = {nullptr, 0, 0, {}};
+            DCurve tmp[3];
+            t.out = tmp, t.cap = 3;
+            stroke_cap(p0, p1, job.cap, t);
+            const DCurve before_back = t.n > 0 ? tmp[min(t.n, 3) - 1] : last_fwd;
+            o.curve_with_join(k, &before_back, r, join, sub_b);
+        } else {
+            o.curve_with_join(k, nullptr, r, join, sub_b);  // the backward side of a closed sub-path starts afresh
         }
-        if (o.n_in_sub > 0) {
-            if (closed) {
-                seg_join(o, o.first, job.join);
-            } else {
-                double p0[2] = {o.last.p[2 * (o.last.n - 1)], o.last.p[2 * (o.last.n - 1) + 1]};
-                double p1[2] = {o.first.p[0], o.first.p[1]};
-                ok = seg_cap(o, p0, p1, job.cap) && ok;
+    }
+    // ---- the end: slots 3 (nf + nb) + 3 ..
+    const int kend = kmid + 3 + 3 * nb;
+    if (lane == 0 && first_range) {
+        int n = 0;
+        if (closed) {
+            if (nb > 0) {
+                Sink t = {nullptr, 0, 0, {}};
+                DCurve tmp[2];
+                t.out = tmp, t.cap = 2;
+                stroke_join(reversed(pool[b0]), reversed(pool[b0 + nb - 1]), join, t);
+                for (int q = 0; q < t.n && q < 2; q++)
+                    o.put(kend + n++, tmp[q], sub_b);
             }
+        } else {
+            const DCurve last = nb > 0 ? reversed(pool[b0]) : pool[f1 - 1];
+            const DCurve first = pool[f0];
+            const double p0[2] = {last.p[2 * (last.n - 1)], last.p[2 * (last.n - 1) + 1]};
+            const double p1[2] = {first.p[0], first.p[1]};
+            Sink t = {nullptr, 0, 0, {}};
+            DCurve tmp[3];
+            t.out = tmp, t.cap = 3;
+            ok = stroke_cap(p0, p1, job.cap, t) && ok;
+            for (int q = 0; q < t.n && q < 3; q++)
+                o.put(kend + n++, tmp[q], sub_b);
         }
+        for (; n < 3; n++)
+            o.nop(kend + n);
     }
-    if (!ok || o.n > limit)
+    if (first_range)
+        for (int k = kend + 3 + lane; k < limit; k += 32)
+            o.nop(k);
+    if (!ok || kend + 3 > limit)
         atomicOr(err, 2);
-    for (int k = o.n; k < limit; k++) {
-        long long i = o.base + k;
-        if (i < out_cap) {
-            out_tag[i] = SEG_NOP;
-            out_path[i] = o.path_id;
-            if (out_sub)
-                out_sub[i] = -1;
-        }
-    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -592,13 +657,13 @@ void svgr_launch_stroke_bound(const int *sub_off, int n_sub, int n_seg, const in
 }
 
 void svgr_launch_stroke_assemble(const uint8_t *in_tag, const int *sub_off, const int *sub_job, const StrokeRec *jobs,
-                                 int n_sub, int n_seg, const int *offs, const void *pool, const int *bound, const int *out_off, const int *out_total, long long out_base,
+                                 int n_sub, int n_seg, const int *items, int n_items, const int *offs, const void *pool,
+                                 const int *bound, const int *out_off, const int *out_total, long long out_base,
                                  long long out_cap, uint8_t *out_tag, double *out_data, uint32_t *out_path,
                                  int32_t *out_sub, int *n_out_dev, int *err, cudaStream_t s)
 {
-    if (n_sub > 0)
-        stroke_assemble_kernel<<<(n_sub + 63) / 64, 64, 0, s>>>(in_tag, sub_off, sub_job, jobs, n_sub, n_seg, offs,
-                                                                (const DCurve *)pool, bound, out_off,
-                                                                out_total, out_base, out_cap, out_tag, out_data, out_path,
-                                                                out_sub, n_out_dev, err);
+    if (n_sub > 0 && n_items > 0)
+        stroke_assemble_kernel<<<(unsigned)(((long long)n_items * 32 + 127) / 128), 128, 0, s>>>(
+            in_tag, sub_off, sub_job, jobs, n_sub, n_seg, items, n_items, offs, (const DCurve *)pool, bound, out_off, out_total,
+            out_base, out_cap, out_tag, out_data, out_path, out_sub, n_out_dev, err);
 }

@@ -78,7 +78,7 @@ void svgr_launch_stroke_emit(const uint8_t *tag, const double *data, const int *
                              int n_seg, const int *offs, void *pool, int pool_cap, cudaStream_t s);
 void svgr_launch_stroke_bound(const int *sub_off, int n_sub, int n_seg, const int *offs, int *bound, cudaStream_t s);
 void svgr_launch_stroke_assemble(const uint8_t *in_tag, const int *sub_off, const int *sub_job, const StrokeRec *jobs,
-                                 int n_sub, int n_seg, const int *offs, const void *pool, const int *bound,
-                                 const int *out_off, const int *out_total, long long out_base, long long out_cap,
-                                 uint8_t *out_tag, double *out_data, uint32_t *out_path, int32_t *out_sub,
-                                 int *n_out_dev, int *err, cudaStream_t s);
+                                 int n_sub, int n_seg, const int *items, int n_items, const int *offs, const void *pool,
+                                 const int *bound, const int *out_off, const int *out_total, long long out_base,
+                                 long long out_cap, uint8_t *out_tag, double *out_data, uint32_t *out_path,
+                                 int32_t *out_sub, int *n_out_dev, int *err, cudaStream_t s);

@@ -176,3 +176,39 @@ def test_random_geometry_is_bit_exact(seed):
         sel = path == len(paths) + k
         rt, rd, _rs = encode.path_arrays(stroke_path(p, w, cap, join))
         assert np.array_equal(tag[sel], rt) and np.array_equal(data[sel].view(np.uint64), rd.view(np.uint64)), (seed, k)
+
+
+@pytest.mark.parametrize("closed", [False, True])
+def test_long_polyline_stroke_is_bit_exact(closed):
+    """A sub-path of 1 500 segments (lines, quads, repeated points) is assembled by several warps, each a range of
+    256 segments: the outline must still be the oracle's, segment for segment, in order."""
+    from oracle.stroke import stroke_path
+    from svgrasterize_b200 import _lib, encode, scene as S, synth
+    from svgrasterize_b200.engine import default_engine
+
+    rng = np.random.default_rng(77)
+    n = 1500
+    xs = np.linspace(5, 250, n)
+    ys = 128 + 100 * np.sin(xs / 7.0) * rng.uniform(0.5, 1.0, n)
+    pb = synth.PathBuilder().move_to(float(xs[0]), float(ys[0]))
+    for k in range(1, n):
+        if k % 97 == 0:
+            pb.line_to(float(xs[k - 1]), float(ys[k - 1]))  # a zero-length segment
+        if k % 3:
+            pb.line_to(float(xs[k]), float(ys[k]))
+        else:
+            pb.quad_to(float(xs[k] - 0.1), float(ys[k] + 3), float(xs[k]), float(ys[k]))
+    if closed:
+        pb.close()
+    path = pb.path()
+    eng = default_engine()
+    for width, cap, join in ((1.5, "round", "round"), (3.0, None, None), (0.7, "square", "bevel")):
+        enc = encode.Encoder(eng)
+        enc.add_stroke_path(path, S.Transform(), width, cap, join, None)
+        eng.render(enc.finish(), stop=_lib.STOP_STROKE)
+        tag, data, _path, sub = eng.outline()
+        want = stroke_path(path, width, cap, join)
+        rt, rd, rs = encode.path_arrays(want)
+        assert np.array_equal(tag, rt) and np.array_equal(data.view(np.uint64), rd.view(np.uint64)), (closed, cap, join)
+        # the sub-path structure (forward / backward outlines of a closed path are separate sub-paths)
+        assert len(np.unique(sub)) == len(rs) - 1
