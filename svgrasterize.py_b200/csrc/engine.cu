@@ -197,7 +197,8 @@ struct svgr_ctx {
     PinBuf pin_boxes, pin_status, pin_plan, pin_out, pin_masks;
 
     // ---- plan state
-    std::vector<MaskRec> h_masks;
+    MaskRec *h_masks = nullptr;  // n_path records, built by plan_masks directly in pinned memory (pin_masks) ...
+    std::vector<MaskRec> h_masks_store;  // ... or here, where no copy to the device follows (plan-only calls)
     std::vector<Val> vals;
     std::vector<PlannedOp> ops;
     std::vector<SrcRec> srcs;
@@ -774,7 +775,6 @@ struct Planner {
     {
         svgr_ctx *c = ctx;
         c->mask_pixels = 0;
-        c->h_masks.assign(c->n_path, MaskRec());
         long long cov_top = 0, band = 0, tile = 0;
         for (int i = 0; i < c->n_path; i++) {
             MaskRec &m = c->h_masks[i];
@@ -1309,6 +1309,8 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
     if (stop_after == SVGR_STOP_STROKE || stop_after == SVGR_STOP_FLATTEN)
         return SVGR_OK;
     if (stop_after == SVGR_STOP_PLAN) {
+        ctx->h_masks_store.resize((size_t)ctx->n_path + 1);
+        ctx->h_masks = ctx->h_masks_store.data();
         Planner pl0(ctx);
         if (!pl0.run())
             FAIL(SVGR_E_INVALID, pl0.err);
@@ -1319,19 +1321,16 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
     // ---- plan, part 1: masks -> binning + coverage are launched before the node plan is made
     mark(3);
     Planner pl(ctx);
+    const size_t b_masks = (size_t)ctx->n_path * sizeof(MaskRec);
+    CK(ctx->pin_masks.ensure(b_masks + 64));  // the GPU waits for this table: it is written where it is copied from
+    ctx->h_masks = (MaskRec *)ctx->pin_masks.p;
     auto t_h0 = std::chrono::steady_clock::now();
     if (!pl.plan_masks())
         FAIL(SVGR_E_INVALID, pl.err);
     auto t_h1 = std::chrono::steady_clock::now();
-    {
-        size_t b_masks = (size_t)ctx->n_path * sizeof(MaskRec);
-        CK(ctx->pin_masks.ensure(b_masks + 64));
-        CK(ctx->d_masks.ensure(std::max<size_t>(b_masks, 16)));
-        if (b_masks) {
-            memcpy(ctx->pin_masks.p, ctx->h_masks.data(), b_masks);
-            CK(cudaMemcpyAsync(ctx->d_masks.p, ctx->pin_masks.p, b_masks, cudaMemcpyHostToDevice, s));
-        }
-    }
+    CK(ctx->d_masks.ensure(std::max<size_t>(b_masks, 16)));
+    if (b_masks)
+        CK(cudaMemcpyAsync(ctx->d_masks.p, ctx->pin_masks.p, b_masks, cudaMemcpyHostToDevice, s));
     CK(ctx->d_cov.ensure((size_t)std::max<long long>(ctx->cov_floats, 4) * 4));
     mark(4);
 
@@ -1802,6 +1801,8 @@ int svgr_debug_plan(const svgr_program *prog, const int32_t *boxes, int reps, fl
     int rc = load_program(ctx, prog, nullptr, true);
     if (rc == SVGR_OK) {
         ctx->h_boxes.assign((const PathBox *)boxes, (const PathBox *)boxes + ctx->n_path);
+        ctx->h_masks_store.resize((size_t)ctx->n_path + 1);
+        ctx->h_masks = ctx->h_masks_store.data();
         float best_m = 1e30f, best_n = 1e30f;
         for (int r = 0; r < reps && rc == SVGR_OK; r++) {
             Planner pl(ctx);
