@@ -134,6 +134,7 @@ struct Launch {
     size_t smem;
     long long list_slots;  // compose launches: TileEntry slots (sum over ops of tiles x sources)
     long long head_off = 0, list_off = 0;  // where this launch's tile heads / entries start in the chunk's buffers
+    bool simple = true;  // compose launches: only OVER folds without conversions, patterns or special outputs
 };
 
 struct StatusBlock {  // device -> host after flatten
@@ -965,6 +966,20 @@ struct Planner {
                 // 16 B destination read + 16 B written, one pass per layer), 20 B per quantised canvas pixel;
                 // stencil passes move what they must either way
                 const bool fold = po.cls == 0 || po.cls == 3;
+                if (fold) {
+                    if (o.mode != MODE_OVER || (o.post & (POST_ALPHA | POST_MATRIX | POST_LUMA)) ||
+                        (po.cls == 3 ? o.aux != 0 : o.out_ch != 4))
+                        L.simple = false;
+                    for (int q = 0; q < o.src_cnt && L.simple; q++) {
+                        const SrcRec &sr = c->srcs[o.src_off + q];
+                        if (sr.kind == SRC_L4 || sr.kind == SRC_COVPAINT) {
+                            if ((sr.conv & 3) != ((sr.conv >> 2) & 3))
+                                L.simple = false;
+                            if (sr.kind == SRC_COVPAINT && c->h_paints[sr.paint].kind == PAINT_PATTERN)
+                                L.simple = false;
+                        }
+                    }
+                }
                 if (po.cls == 3) {
                     c->canvas_pixels += (long long)o.rows * o.cols;
                     c->compose_bytes += (long long)o.rows * o.cols * 4;  // RGBA8 out
@@ -1520,7 +1535,7 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
                 if (L.cls == 1 || L.cls == 2)
                     svgr_launch_expand_ops(ops, L.op_count, L.n_tiles, ctx->d_tile_map.as<int>(), s);
                 if (L.cls == 0)
-                    svgr_launch_compose(T, ops, heads, list, L.n_tiles, ctx->d_layers.as<float>(), nullptr, s);
+                    svgr_launch_compose(T, ops, heads, list, L.n_tiles, L.simple, ctx->d_layers.as<float>(), nullptr, s);
                 else if (L.cls == 1) {
                     if (svgr_launch_stencil(T, ops, tile_op, L.n_tiles, L.smem, ctx->d_layers.as<float>(), s))
                         FAIL(SVGR_E_UNSUPPORTED, "stencil needs more shared memory than available");
@@ -1528,7 +1543,7 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
                     if (svgr_launch_conv2d(T, ops, tile_op, L.n_tiles, L.smem, ctx->d_layers.as<float>(), s))
                         FAIL(SVGR_E_UNSUPPORTED, "convolution needs more shared memory than available");
                 } else
-                    svgr_launch_compose(T, ops, heads, list, L.n_tiles, ctx->d_layers.as<float>(), canvas, s);
+                    svgr_launch_compose(T, ops, heads, list, L.n_tiles, L.simple, ctx->d_layers.as<float>(), canvas, s);
                 n_launches++;
                 n_kernels += L.n_tiles > 0 ? 2 : 0;
             }

@@ -78,6 +78,9 @@ __device__ __forceinline__ void copy16(T *dst, const T *src, int part)
 #ifndef SVGR_CMP_OCC
 #define SVGR_CMP_OCC 4
 #endif
+// SIMPLE: every op of the launch is an OVER fold whose sources need no colour conversion and no pattern gather
+// (what an icon batch consists of); the rare branches are compiled out, which keeps the hot loop's code compact.
+template <bool SIMPLE>
 __global__ void __launch_bounds__(256, SVGR_CMP_OCC)
 compose_kernel(RenderTables T, const OpRec *__restrict__ ops, const TileHead *__restrict__ heads,
                const TileEntry *__restrict__ list, float *__restrict__ layers_out, uint8_t *__restrict__ canvas_out)
@@ -137,7 +140,7 @@ compose_kernel(RenderTables T, const OpRec *__restrict__ ops, const TileHead *__
     const int r0 = op.r0 + lr0, c = op.c0 + lc;
     const bool col_live = lc < op.cols;
     const int mode = op.mode;
-    const bool skip_outside = (mode == MODE_OVER);  // blending a zero source is the identity for OVER
+    const bool skip_outside = SIMPLE || (mode == MODE_OVER);  // blending a zero source is the identity for OVER
     const double x0 = (double)r0 + 0.5, y0 = (double)c + 0.5;  // pixel centre of pixel 0
 
     float4 acc[CMP_PX];
@@ -183,7 +186,7 @@ compose_kernel(RenderTables T, const OpRec *__restrict__ ops, const TileHead *__
                                 v[k] = scale4(col, a[k]);
                         } else {
                             const StopRec *st = T.stops + pr.stop_off;
-                            if (pr.kind == PAINT_PATTERN) {
+                            if (!SIMPLE && pr.kind == PAINT_PATTERN) {
                                 const float4 *pat = reinterpret_cast<const float4 *>(T.layers + s.off2);
 #pragma unroll
                                 for (int k = 0; k < CMP_PX; k++) {
@@ -219,7 +222,7 @@ compose_kernel(RenderTables T, const OpRec *__restrict__ ops, const TileHead *__
                     for (int k = 0; k < CMP_PX; k++)
                         v[k] = scale4(v[k], m);
                 }
-                if (s.kind != SRC_L1 && s.kind != SRC_COV && !conv_is_identity(s.conv)) {
+                if (!SIMPLE && s.kind != SRC_L1 && s.kind != SRC_COV && !conv_is_identity(s.conv)) {
 #pragma unroll
                     for (int k = 0; k < CMP_PX; k++)
                         if (live >> (8 * k) & 1)
@@ -239,7 +242,7 @@ compose_kernel(RenderTables T, const OpRec *__restrict__ ops, const TileHead *__
 #pragma unroll
                     for (int k = 0; k < CMP_PX; k++)
                         acc[k] = v[k];
-                } else if (mode == MODE_OVER) {
+                } else if (SIMPLE || mode == MODE_OVER) {
 #pragma unroll
                     for (int k = 0; k < CMP_PX; k++) {
                         // a dead pixel has v = 0: the blend is the identity
@@ -278,9 +281,9 @@ compose_kernel(RenderTables T, const OpRec *__restrict__ ops, const TileHead *__
             a = scale4(a, op.mul);
         if (op.post & POST_CLIP01)
             a = f4(clip01(a.x), clip01(a.y), clip01(a.z), clip01(a.w));
-        if (op.post & POST_ALPHA)
+        if (!SIMPLE && (op.post & POST_ALPHA))
             a = f4(0.f, 0.f, 0.f, a.w);
-        if (op.post & POST_MATRIX) {
+        if (!SIMPLE && (op.post & POST_MATRIX)) {
             const float *M = T.matrices + 20 * op.aux;  // row-major 4x5
             float4 v = a;
             a.x = clip01(M[0] * v.x + M[1] * v.y + M[2] * v.z + M[3] * v.w + M[4]);
@@ -294,7 +297,7 @@ compose_kernel(RenderTables T, const OpRec *__restrict__ ops, const TileHead *__
             // (canvas_merge_at :326), converted to straight-alpha sRGB (Layer.write_png :212) and quantised
             // with round-half-even (np.round, :263).  op.aux carries the render's linear_rgb flag.
             a = f4(clip01(a.x), clip01(a.y), clip01(a.z), clip01(a.w));
-            if (op.aux != 0)
+            if (!SIMPLE && op.aux != 0)
                 a = convert_px(a, SVGR_CONV(1, 1, 0, 0));
             else
                 a = unpremultiply(a);  // sRGB render mode: Layer.convert is the alpha division only
@@ -305,10 +308,10 @@ compose_kernel(RenderTables T, const OpRec *__restrict__ ops, const TileHead *__
             q.z = (unsigned char)(__float_as_uint(a.z * 255.0f + 12582912.0f) & 0xffu);
             q.w = (unsigned char)(__float_as_uint(a.w * 255.0f + 12582912.0f) & 0xffu);
             reinterpret_cast<uchar4 *>(canvas_out + op.out_off)[idx] = q;
-        } else if (op.post & POST_LUMA) {
+        } else if (!SIMPLE && (op.post & POST_LUMA)) {
             // Scene.render mask branch: luma . rgb * alpha on the straight-alpha image (svgrasterize.py:734-736)
             layers_out[op.out_off + idx] = (a.x * 0.2125f + a.y * 0.7154f + a.z * 0.072f) * a.w;
-        } else if (op.out_ch == 1) {
+        } else if (!SIMPLE && op.out_ch == 1) {
             layers_out[op.out_off + idx] = a.w;
         } else {
             reinterpret_cast<float4 *>(layers_out + op.out_off)[idx] = a;
@@ -355,10 +358,14 @@ __global__ void focal_flag_kernel(RenderTables T, const FocalJob *__restrict__ j
 
 // ---------------------------------------------------------------------------------------------
 void svgr_launch_compose(const RenderTables &T, const OpRec *ops, const TileHead *heads, const TileEntry *list, int n_tiles,
-                         float *layers_out, uint8_t *canvas_out, cudaStream_t s)
+                         bool simple, float *layers_out, uint8_t *canvas_out, cudaStream_t s)
 {
-    if (n_tiles > 0)
-        compose_kernel<<<n_tiles, 256, 0, s>>>(T, ops, heads, list, layers_out, canvas_out);
+    if (n_tiles <= 0)
+        return;
+    if (simple)
+        compose_kernel<true><<<n_tiles, 256, 0, s>>>(T, ops, heads, list, layers_out, canvas_out);
+    else
+        compose_kernel<false><<<n_tiles, 256, 0, s>>>(T, ops, heads, list, layers_out, canvas_out);
 }
 
 // Source lists of the tiles of one compose launch, one warp per tile: the op of the tile (binary search over the

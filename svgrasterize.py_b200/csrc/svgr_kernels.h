@@ -60,7 +60,7 @@ void svgr_launch_expand_ops(const OpRec *ops, int n_ops, int n_tiles, int *tile_
 void svgr_launch_cull(const RenderTables &T, const OpRec *ops, int n_ops, int n_tiles, TileHead *heads, TileEntry *list,
                       cudaStream_t s);
 void svgr_launch_compose(const RenderTables &T, const OpRec *ops, const TileHead *heads, const TileEntry *list, int n_tiles,
-                         float *layers_out, uint8_t *canvas_out, cudaStream_t s);
+                         bool simple, float *layers_out, uint8_t *canvas_out, cudaStream_t s);
 void svgr_launch_focal_flags(const RenderTables &T, const void *jobs, int n_jobs, int block0, int n_blocks, int *flags,
                              cudaStream_t s);
 
