@@ -6,9 +6,17 @@
 """
 import collections
 import csv
+import re
 import json
 import subprocess
 import sys
+
+
+def kernel_name(full):
+    """'void compose_kernel<1>(RenderTables, ...)' -> 'compose_kernel' (template instantiations count as one kernel)"""
+    name = full.split("(")[0].strip()
+    name = re.sub(r"^void\s+", "", name)
+    return re.sub(r"<.*>$", "", name)
 
 
 def launches(src, dst):
@@ -18,7 +26,7 @@ def launches(src, dst):
     ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
     agg = collections.OrderedDict()
     for r in rows[start + 1:]:
-        name = r[ki].split("(")[0]
+        name = kernel_name(r[ki])
         v = float(r[vi].replace(",", ""))
         v = v / 1e3 if r[ui] == "ns" else (v * 1e3 if r[ui] == "ms" else v)
         a = agg.setdefault(name, [0, 0.0])
@@ -57,7 +65,7 @@ def full(src, dst, traffic=None):
     with open(dst, "w") as f:
         f.write(f"# ncu --set full --clock-control none --import-source on: {src}\n")
         for r in data:
-            name = r[col["Kernel Name"]].split("(")[0]
+            name = kernel_name(r[col["Kernel Name"]])
             f.write(f"\n== {name}\n")
             for m in METRICS:
                 if m in col:
@@ -87,7 +95,7 @@ def traffic(src, dst, icons, skip):
     for r in rows[start + 1:]:
         if int(r[ii]) < skip:
             continue
-        name = r[ki].split("(")[0]
+        name = kernel_name(r[ki])
         d = per.setdefault(name, {"launches": set(), "bytes": 0.0, "us": 0.0})
         d["launches"].add(r[ii])
         v = float(r[vi].replace(",", ""))
