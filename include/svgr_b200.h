@@ -16,6 +16,10 @@
  *   canvas_merge_at + write_png quantisation (:3870-3881,:263) svgr_render canvas nodes -> RGBA8
  *   ConvexHull.bbox (:2002)                                  svgr_cloud_bounds
  *   arc_to_bezier3 (:2355)  [host, libm]                     svgr_arc_to_cubics
+ *   line_signed_coverage(canvas, line) (:2213)               svgr_line_signed_coverage
+ *   grad_pixels / grad_spread / grad_interpolate (:1653-1683) svgr_grad_pixels / svgr_grad_spread / svgr_grad_interpolate
+ *   canvas_to_png quantisation of a float image (:263)       svgr_quantize_u8
+ *   pooling with stride / padding / mean (:419-468)          svgr_pooling
  *
  * Conventions: every function returns 0 on success, a negative SVGR_E_* code on
  * failure (svgr_last_error gives the text).  Nothing throws.  No torch types: plain
@@ -33,7 +37,7 @@
 extern "C" {
 #endif
 
-#define SVGR_VERSION 100
+#define SVGR_VERSION 200
 
 enum {
     SVGR_OK = 0,
@@ -42,6 +46,8 @@ enum {
     SVGR_E_NOMEM = -3,
     SVGR_E_UNSUPPORTED = -4,
     SVGR_E_STROKE = -5, /* degenerate control polygon: the reference raises TypeError here (:2157) */
+    SVGR_E_TYPE = -6,   /* another place where the reference raises TypeError: a pattern tile that misses its repeat
+                           cell (canvas_merge_at returns None, :1093-1094) */
 };
 
 /* where svgr_render stops (taps for the stage-level parity tests and the eager API) */
@@ -61,7 +67,10 @@ enum {
     SVGR_N_OPACITY = 3,   /* child 0 x f[0]; flags bit0 = linear_rgb */
     SVGR_N_IN = 4,        /* compose([child0 (stencil), child1 (image)], IN); flags bit0 = linear_rgb */
     SVGR_N_LUMA = 5,      /* luminance x alpha of child 0 as one channel; flags bit0 = linear_rgb */
-    SVGR_N_COMPOSE = 6,   /* Layer.compose(children, mode a, arithmetic k = f[0..3]); flags bit0 = linear_rgb */
+    SVGR_N_COMPOSE = 6,   /* Layer.compose(children, mode a, arithmetic k = f[0..3]); flags bit0 = linear_rgb,
+                             bit2 = blend on the intersection of the boxes whatever the mode (canvas_merge_intersect
+                             with a blend other than `in`), bit3 = children are raw arrays: no Layer.convert
+                             (canvas_compose / canvas_merge_* on plain images) */
     SVGR_N_SRC_ALPHA = 7, /* (0,0,0,alpha) of child 0, premultiplied linear */
     SVGR_N_CONVERT = 8,   /* Layer.convert(pre_alpha = a, linear_rgb = b) of child 0 */
     SVGR_N_BLUR = 9,      /* Layer.convolve with kernel a of the kernel table */
@@ -148,6 +157,7 @@ typedef struct svgr_program {
     const svgr_external *externals;
     /* output */
     int64_t canvas_bytes; /* total RGBA8 bytes written by the canvas nodes */
+    double flatness;      /* bezier3_flatten_batch(batch, flatness) (:2091); 0 = Path.mask's literal 0.1 (:955) */
 } svgr_program;
 
 typedef struct svgr_stats {
@@ -231,6 +241,28 @@ int64_t svgr_arc_to_cubics(double cx, double cy, double rx, double ry, double ph
  * position).  Returns the output length or a negative code (SVGR_E_NOMEM: cap too small). */
 int64_t svgr_expand_arcs(const uint8_t *tags, const double *data, int64_t n, uint8_t *out_tags, double *out_data,
                          int64_t cap, int64_t *new_index);
+
+/* ---- eager element-wise entry points of the reference's call surface.  Host pointers in and
+ * out; every call copies up, launches one kernel on the context's stream and copies down (one synchronisation). */
+
+/* line_signed_coverage(canvas, line) (svgrasterize.py:2213-2304) for n lines (r0, c0, r1, c1 each) accumulated
+ * into `trace` (rows x cols float32, updated in place): the signed-area deltas before cumsum and fill rule. */
+int svgr_line_signed_coverage(svgr_ctx *ctx, float *trace, int32_t rows, int32_t cols, const double *lines, int64_t n);
+/* grad_pixels(viewport) (:1653-1658): out[(i * cols + j) * 2 + {0, 1}] = (r0 + i + 0.5, c0 + j + 0.5) */
+int svgr_grad_pixels(svgr_ctx *ctx, int32_t r0, int32_t c0, int32_t rows, int32_t cols, double *out);
+/* grad_spread(offsets, spread) (:1661-1668) on n float64 offsets; spread 0 pad, 1 repeat, 2 reflect */
+int svgr_grad_spread(svgr_ctx *ctx, const double *offsets, int64_t n, int32_t spread, double *out);
+/* grad_interpolate(offset, stops, linear_rgb) (:1671-1683): n offsets -> n x 4 float32 premultiplied RGBA; the
+ * stops arrive already converted to the target colour space (grad_stops_colorspace, :1686) */
+int svgr_grad_interpolate(svgr_ctx *ctx, const double *offsets, int64_t n, const struct StopRec *stops, int32_t n_stops,
+                          float *out);
+/* np.round(canvas * 255).astype(uint8) of canvas_to_png (:263): n float32 values -> n bytes (round half even) */
+int svgr_quantize_u8(svgr_ctx *ctx, const float *values, int64_t n, uint8_t *out);
+/* pooling(mat, ksize, stride, method, pad) (:419-468) on a rows x cols x ch float32 array: method 0 max, 1 min,
+ * 2 mean (nan-ignoring like np.nanmax / nanmin / nanmean); out has out_rows x out_cols x ch elements with
+ * out = (n - k) / s + 1 without padding, ceil(n / s) with it. */
+int svgr_pooling(svgr_ctx *ctx, const float *mat, int32_t rows, int32_t cols, int32_t ch, int32_t ky, int32_t kx,
+                 int32_t sy, int32_t sx, int32_t method, int32_t pad, float *out, int32_t out_rows, int32_t out_cols);
 
 #ifdef __cplusplus
 }

@@ -387,6 +387,11 @@ def fill_path(path, transform, paint, fill_rule=None, viewport=None, linear_rgb=
         lo = corners.min(axis=0).astype(int)
         offs -= lo
         pat = np.zeros((hi[0] - lo[0] + 1, hi[1] - lo[1] + 1, 4))
+        box = _intersection([(0, 0, *pat.shape[:2]), (tile.offset[0] - lo[0], tile.offset[1] - lo[1], *tile.image.shape[:2])])
+        if box[2] <= 0 or box[3] <= 0:
+            # canvas_merge_at returns None when the tile misses the repeat cell (:315-322) and the gather at :1094
+            # subscripts it: the reference's failure mode for such a pattern
+            raise TypeError("'NoneType' object is not subscriptable")
         pat = merge_at(pat, tile.image, (tile.offset[0] - lo[0], tile.offset[1] - lo[1]))
         image = pat[offs[..., 0], offs[..., 1]] * cov
         return OLayer(image, offset, tile.pre_alpha, tile.linear_rgb), cloud

@@ -34,7 +34,7 @@ PAINT_SOLID, PAINT_LINEAR, PAINT_RADIAL, PAINT_RADIAL_FOCAL, PAINT_PATTERN = ran
 STOP_NONE, STOP_STROKE, STOP_FLATTEN, STOP_COVERAGE, STOP_PLAN = range(5)
 SEG_NOP = 255
 
-E_INVALID, E_CUDA, E_NOMEM, E_UNSUPPORTED, E_STROKE = -1, -2, -3, -4, -5
+E_INVALID, E_CUDA, E_NOMEM, E_UNSUPPORTED, E_STROKE, E_TYPE = -1, -2, -3, -4, -5, -6
 
 
 class External(C.Structure):
@@ -57,6 +57,7 @@ class Program(C.Structure):
         ("n_matrix", C.c_int32), ("matrices", C.c_void_p), ("n_offset_tr", C.c_int32), ("offset_tr", C.c_void_p),
         ("n_external", C.c_int32), ("externals", C.c_void_p),
         ("canvas_bytes", C.c_int64),
+        ("flatness", C.c_double),
     ]
 
 
@@ -98,6 +99,12 @@ SYMBOLS = {
     "svgr_cloud_bounds": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "svgr_arc_to_cubics": (C.c_int64, [C.c_double] * 7 + [C.c_void_p, C.c_int64]),
     "svgr_expand_arcs": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "svgr_line_signed_coverage": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int64]),
+    "svgr_grad_pixels": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "svgr_grad_spread": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+    "svgr_grad_interpolate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
+    "svgr_quantize_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "svgr_pooling": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 9 + [C.c_void_p, C.c_int32, C.c_int32]),
 }
 
 _lib = None

@@ -20,6 +20,7 @@ or a GPU they raise.
 """
 from __future__ import annotations
 
+import io
 import struct
 import zlib
 from typing import NamedTuple
@@ -218,23 +219,74 @@ def path_stroke(path, width, linecap=None, linejoin=None):
     eng.render(enc.finish(), stop=_lib.STOP_STROKE)
     tag, data, _path, sub = eng.outline()
     bounds = np.concatenate([[0], np.nonzero(np.diff(sub))[0] + 1, [len(sub)]]) if len(sub) else np.zeros(1, int)
-    return path_from_arrays(tag, data, bounds.astype(np.int32))
+    out = path_from_arrays(tag, data, bounds.astype(np.int32))
+    # hand back the caller's own Path class (the reference's, once install() has rebound its methods)
+    return out if type(path) is S.Path else type(path)(out.subpaths)
 
 
 def bezier3_flatten_batch(batch, flatness=0.1):
-    """bezier3_flatten_batch (svgrasterize.py:2091): (M, 4, 2) cubics -> (E, 2, 2) lines.  The device emits
-    the same set of lines as the reference, in a different order.  Only the reference's own flatness (0.1)
-    is wired through the C-ABI."""
-    if flatness != 0.1:
-        raise NotImplementedError("the device flattener uses the reference's literal flatness of 0.1")
+    """bezier3_flatten_batch (svgrasterize.py:2091-2098): (M, 4, 2) cubics -> (E, 2, 2) lines.  The device emits
+    the same set of lines as the reference, in a different order."""
+    flatness = float(flatness)
+    if not flatness > 0.0:
+        raise ValueError("flatness must be positive (the reference never terminates otherwise)")
     batch = np.asarray(batch, dtype=np.float64).reshape(-1, 4, 2)
     path = S.Path([[(S.PATH_CUBIC, c) for c in batch]]) if len(batch) else S.Path([])
     eng = default_engine()
     enc = Encoder(eng)
     enc.add_fill_path(path, S.Transform(), None, None)
-    eng.render(enc.finish(), stop=_lib.STOP_FLATTEN)
+    prog = enc.finish()
+    prog.flatness = flatness
+    eng.render(prog, stop=_lib.STOP_FLATTEN)
     edges, _ = eng.edges()
     return edges.reshape(-1, 2, 2)
+
+
+def line_signed_coverage(canvas, line):
+    """line_signed_coverage(canvas, line) (svgrasterize.py:2213-2304): adds the signed-area deltas of `line`
+    ((r0, c0), (r1, c1)) -- or of an (n, 2, 2) batch of lines -- to the 2-D trace `canvas` in place and returns
+    it.  The device accumulates in float32 (like the tile kernel of Path.mask)."""
+    if canvas.ndim != 2:
+        raise ValueError("canvas must be a 2-D trace")
+    lines = np.asarray(line, dtype=np.float64).reshape(-1, 4)
+    trace = np.ascontiguousarray(canvas, dtype=np.float32)
+    if trace is canvas or np.shares_memory(trace, canvas):
+        default_engine().line_signed_coverage(trace, lines)
+    else:
+        canvas[...] = default_engine().line_signed_coverage(trace, lines)
+    return canvas
+
+
+def grad_pixels(viewport):
+    """grad_pixels (svgrasterize.py:1653-1658): (width, height, 2) float64 pixel centres of a viewport."""
+    off_x, off_y, width, height = viewport
+    return default_engine().grad_pixels(off_x, off_y, width, height)
+
+
+def grad_spread(offsets, spread):
+    """grad_spread (svgrasterize.py:1661-1668)."""
+    from .encode import SPREAD
+
+    if spread not in SPREAD:
+        raise ValueError(f"invalid spread method: {spread}")
+    return default_engine().grad_spread(np.asarray(offsets, dtype=np.float64), SPREAD[spread])
+
+
+def grad_interpolate(offset, stops, linear_rgb):
+    """grad_interpolate (svgrasterize.py:1671-1683): offsets (...) -> premultiplied RGBA (..., 4) float32; the
+    stop colours are converted to sRGB on the host when not linear_rgb (grad_stops_colorspace, :1686)."""
+    from .color import paint_to_srgb
+
+    if not stops:
+        raise ValueError("gradient without stops")
+    rec = np.zeros(len(stops), _lib.STOP_DT)
+    offs = [float(o) for o, _ in stops]
+    for k, (o, c) in enumerate(stops):
+        rec["offset"][k] = float(o)
+        rec["color"][k] = np.asarray(c, dtype=np.float64) if linear_rgb else paint_to_srgb(c)
+        with np.errstate(divide="ignore"):
+            rec["inv_span"][k] = np.float64(1.0) / np.float64(offs[k + 1] - offs[k]) if k + 1 < len(offs) else 0.0
+    return default_engine().grad_interpolate(np.asarray(offset, dtype=np.float64), rec)
 
 
 S.Path.mask = path_mask
@@ -301,65 +353,122 @@ def _as_layer(image, offset=(0, 0)):
     image = np.asarray(image, dtype=np.float32)
     if image.ndim == 2:
         image = image[..., None]
-    return Layer(np.ascontiguousarray(image), tuple(offset), True, True)
+    return Layer(np.ascontiguousarray(image), tuple(int(v) for v in offset), True, True)
+
+
+def _blend_mode(blend, default=COMPOSE_OVER):
+    """The reference passes blends around as functools.partial(canvas_compose, mode) (svgrasterize.py:301, :198);
+    a bare mode is accepted too.  Arbitrary Python callables cannot run on the device."""
+    import functools
+
+    if blend is None:
+        return default
+    if isinstance(blend, functools.partial) and blend.args and getattr(blend.func, "__name__", "") == "canvas_compose":
+        return blend.args[0]
+    if isinstance(blend, (int, tuple)) and not isinstance(blend, bool):
+        return blend
+    raise TypeError("blend must be a compose mode or functools.partial(canvas_compose, mode)")
+
+
+def _raw_compose(layers, mode, intersect=False, clip_box=None):
+    """canvas_compose folded over plain (image, offset) arrays: no Layer.convert, union box (zero padded) or
+    intersection box; clip_box = (r0, c0, rows, cols): the result is placed on zeros of that box and clipped to
+    [0, 1] (canvas_merge_at).  -> Layer or None"""
+    eng = default_engine()
+    enc = Encoder(eng)
+    nodes = [enc.add_external(l.image, l.offset, True, True) for l in layers]
+    node = enc._compose(nodes, mode, True, intersect=intersect, raw=True)
+    if clip_box is not None:
+        node = enc._node(_lib.N_MERGE_AT, *clip_box, children=[node])
+    return _read(eng, enc, node)
 
 
 def canvas_compose(mode, dst, src):
-    """canvas_compose (svgrasterize.py:277-298) on two same-sized premultiplied images."""
-    out = Layer.compose([_as_layer(dst), _as_layer(src)], mode, True)
-    return out.image
+    """canvas_compose (svgrasterize.py:277-298): blends two broadcast-compatible premultiplied images as they
+    are (no colour conversion); the alpha of an image is its last channel, a 2-D or one-channel image is alpha."""
+    if not (isinstance(mode, tuple) and len(mode) == 4) and (isinstance(mode, bool) or mode not in (0, 1, 2, 3, 4)):
+        raise ValueError(f"invalid compose mode: {mode}")
+    dst, src = np.asarray(dst, dtype=np.float32), np.asarray(src, dtype=np.float32)
+    flat = dst.ndim == 2 and src.ndim == 2
+    d3 = dst[..., None] if dst.ndim == 2 else dst
+    s3 = src[..., None] if src.ndim == 2 else src
+    one = d3.shape[-1] == 1 and s3.shape[-1] == 1
+    shape = np.broadcast_shapes(d3.shape[:2], s3.shape[:2])
+    d3 = np.broadcast_to(d3, (*shape, d3.shape[-1]))
+    s3 = np.broadcast_to(s3, (*shape, s3.shape[-1]))
+    out = _raw_compose([_as_layer(d3), _as_layer(s3)], mode).image
+    if one:
+        out = out[..., 3:]
+    return out[..., 0] if flat else out
 
 
 def canvas_merge_at(base, overlay, offset, blend=None):
-    """canvas_merge_at (svgrasterize.py:304-327) for the over blend (its only use in the reference, :3873):
-    the overlay is blended onto `base` in place and the result is clipped to [0, 1]."""
-    if blend not in (None, COMPOSE_OVER):
-        raise NotImplementedError("canvas_merge_at is wired for the over blend")
-    eng = default_engine()
-    enc = Encoder(eng)
-    b = enc.add_external(np.asarray(base, dtype=np.float32), (0, 0), True, True)
-    o = enc.add_external(np.asarray(overlay, dtype=np.float32), offset, True, True)
-    rows, cols = base.shape[:2]
-    node = enc._node(_lib.N_MERGE_AT, 0, 0, rows, cols, children=[enc._compose([b, o], COMPOSE_OVER, True)])
-    out = _read(eng, enc, node)
-    base[...] = out.image
+    """canvas_merge_at (svgrasterize.py:304-327): `overlay` is blended onto `base` at `offset` in place; only the
+    affected rectangle changes and is clipped to [0, 1].  Returns `base`, or None when the overlay misses it."""
+    mode = _blend_mode(blend)
+    x, y = (int(v) for v in offset)
+    b_h, b_w = base.shape[:2]
+    o_h, o_w = overlay.shape[:2]
+    clip = lambda v, lo, hi: lo if v < lo else hi if v > hi else v  # noqa: E731
+    b_x_low, b_x_high = clip(x, 0, b_h), clip(x + o_h, 0, b_h)
+    b_y_low, b_y_high = clip(y, 0, b_w), clip(y + o_w, 0, b_w)
+    effected = base[b_x_low:b_x_high, b_y_low:b_y_high]
+    if effected.size == 0:
+        return None
+    o_x_low, o_x_high = clip(-x, 0, o_h), clip(b_h - x, 0, o_h)
+    o_y_low, o_y_high = clip(-y, 0, o_w), clip(b_w - y, 0, o_w)
+    overlay = overlay[o_x_low:o_x_high, o_y_low:o_y_high]
+    if overlay.size == 0:
+        return None
+    out = _raw_compose([_as_layer(effected), _as_layer(overlay)], mode, clip_box=(0, 0, *effected.shape[:2]))
+    effected[...] = out.image if effected.ndim == 3 and effected.shape[2] == 4 else out.image[..., 3:].reshape(effected.shape)
     return base
 
 
 def canvas_merge_union(layers, full=True, blend=None):
-    """canvas_merge_union (svgrasterize.py:330-379): layers = [(image, offset)] -> (image, offset)."""
-    mode = COMPOSE_OVER if blend is None else blend
+    """canvas_merge_union (svgrasterize.py:330-379): layers = [(image, offset)] -> (image, offset) over the union
+    of the boxes, every layer zero padded to it (`full`); for the over blend the sub-rectangle fast path
+    (full=False, the only way the reference calls it, :201) gives the same pixels."""
+    mode = _blend_mode(blend)
+    layers = list(layers)
+    if not layers:
+        raise ValueError("can not blend zero layers")
+    if len(layers) == 1:
+        return layers[0]
     if not full and mode != COMPOSE_OVER:
-        raise ValueError("the sub-rectangle fast path is only defined for the over blend")
-    out = Layer.compose([_as_layer(im, off) for im, off in layers], mode, True)
+        raise ValueError("the sub-rectangle fast path (full=False) is only defined for the over blend "
+                         "(svgrasterize.py:199-203 never calls it otherwise)")
+    out = _raw_compose([_as_layer(im, off) for im, off in layers], mode)
     return out.image, out.offset
 
 
 def canvas_merge_intersect(layers, blend=None):
-    """canvas_merge_intersect (svgrasterize.py:382-416) -> (image, offset) or None."""
-    mode = COMPOSE_IN if blend is None else blend
-    if mode != COMPOSE_IN:
-        raise NotImplementedError("intersection merge is wired for the `in` blend (its only use in the reference)")
-    out = Layer.compose([_as_layer(im, off) for im, off in layers], COMPOSE_IN, True)
+    """canvas_merge_intersect (svgrasterize.py:382-416): blend on the intersection of the boxes -> (image, offset),
+    or None when the intersection is empty."""
+    mode = _blend_mode(blend)
+    layers = list(layers)
+    if not layers:
+        raise ValueError("can not blend zero layers")
+    if len(layers) == 1:
+        return layers[0]
+    out = _raw_compose([_as_layer(im, off) for im, off in layers], mode, intersect=True)
     return None if out is None else (out.image, out.offset)
 
 
 def pooling(mat, ksize, stride=None, method="max", pad=False):
-    """pooling (svgrasterize.py:419-468) for the case the reference uses: stride 1, no padding."""
-    if method not in ("max", "min"):
+    """pooling (svgrasterize.py:419-468): overlapping pooling of a 2-D or 3-D array, NaN-ignoring max / min /
+    mean, optional NaN padding to ceil(n / stride) outputs."""
+    methods = {"max": 0, "min": 1, "mean": 2}
+    if method not in methods:
         raise ValueError(f"invalid poll method: {method}")
-    if (stride not in (None, (1, 1))) or pad:
-        raise NotImplementedError("only stride (1, 1) without padding is on the hot path (Layer.morphology)")
+    ky, kx = (int(v) for v in ksize)
+    sy, sx = (ky, kx) if stride is None else (int(v) for v in stride)
     mat = np.asarray(mat, dtype=np.float32)
-    squeeze = mat.ndim == 2
-    img = mat[..., None] if squeeze else mat
-    if img.shape[2] not in (1, 4):
-        raise ValueError("pooling expects 1 or 4 channels")
-    if img.shape[2] == 1:
-        img = np.repeat(img, 4, axis=2)
-    out = Layer(np.ascontiguousarray(img), (0, 0), True, True).morphology(ksize[0], ksize[1], method).image
-    out = out[..., :1] if mat.ndim == 2 or mat.shape[-1] == 1 else out
-    return out[..., 0] if squeeze else out
+    if mat.ndim not in (2, 3):
+        raise ValueError("pooling expects a 2-D or 3-D array")
+    img = mat[..., None] if mat.ndim == 2 else mat
+    out = default_engine().pooling(img, (ky, kx), (sy, sx), methods[method], bool(pad))
+    return out[..., 0] if mat.ndim == 2 else out
 
 
 def _deflate_parallel(raw: bytes, level: int, threads: int, block: int = 1 << 20) -> bytes:
@@ -386,13 +495,13 @@ def canvas_to_png(canvas, output=None, threads=1, level=9):
     """canvas_to_png (svgrasterize.py:249-274): straight-alpha sRGB float image -> PNG bytes.  The
     float -> uint8 quantisation (:263) is the in-scope part; deflate stays on the host like the reference.
 
-    With the defaults the bytes are the reference's (filter 0 rows, one zlib stream at level 9).  `threads`
+    Returns `output` (a fresh io.BytesIO when None, like the reference).  With the defaults the bytes are the reference's (filter 0 rows, one zlib stream at level 9).  `threads`
     > 1 compresses 1 MiB blocks of the same filtered rows on that many host cores (level 9 on
     one core takes 6.7 s for a 4096 x 4096 canvas): the file decodes to the same pixels but is not
     byte-identical and a few percent larger."""
     canvas = np.asarray(canvas)
     if canvas.dtype != np.uint8:
-        canvas = np.round(np.clip(canvas, 0, 1) * 255.0).astype(np.uint8)
+        canvas = default_engine().quantize_u8(canvas)  # np.round(canvas * 255).astype(uint8) on the device (:263)
     height, width = canvas.shape[:2]
     rows = np.zeros((height, 1 + width * 4), dtype=np.uint8)  # filter type 0 in front of every row
     rows[:, 1:] = canvas.reshape(height, width * 4)
@@ -405,7 +514,59 @@ def canvas_to_png(canvas, output=None, threads=1, level=9):
     idat = zlib.compress(raw, level) if threads <= 1 else _deflate_parallel(raw, level, int(threads))
     png = b"".join([b"\x89PNG\r\n\x1a\n", chunk(b"IHDR", struct.pack(">2I5B", width, height, 8, 6, 0, 0, 0)),
                     chunk(b"IDAT", idat), chunk(b"IEND", b"")])
-    if output is not None:
-        output.write(png)
-        return output
-    return png
+    output = io.BytesIO() if output is None else output  # svgrasterize.py:267
+    output.write(png)
+    return output
+
+
+# ---------------------------------------------------------------------------------------------
+# drop-in installer
+# ---------------------------------------------------------------------------------------------
+_MODULE_FUNCTIONS = ("canvas_create", "canvas_to_png", "canvas_compose", "canvas_merge_at", "canvas_merge_union",
+                     "canvas_merge_intersect", "pooling", "bezier3_flatten_batch", "line_signed_coverage",
+                     "grad_pixels", "grad_spread", "grad_interpolate", "blur_kernel")
+_MISSING = object()
+
+
+def install(module):
+    """Rebind the hot-path entry points of a reference-shaped module -- the reference's own `svgrasterize`
+    module, or anything with the same names -- to this core, so that its parser, Scene builders, CLI `main()`
+    (svgrasterize.py:3795-3881) and helper scripts run on the GPU unmodified:
+
+        Path.mask / fill / stroke (:922 / :995 / :1105), Scene.render (:649), Filter.__call__ (:1801),
+        Layer (:61-232) and the module functions canvas_* / pooling (:235-468), bezier3_flatten_batch (:2091),
+        line_signed_coverage (:2213), grad_pixels / grad_spread / grad_interpolate (:1653-1683), blur_kernel (:1903).
+
+    Everything else (Transform, paints, the SVG parser, fonts) stays the module's own.  Returns a token for
+    uninstall()."""
+    import functools
+
+    saved = {}
+
+    def bind(owner, name, value):
+        saved[(owner, name)] = owner.__dict__.get(name, _MISSING) if isinstance(owner, type) else getattr(owner, name, _MISSING)
+        setattr(owner, name, value)
+
+    bind(module.Path, "mask", path_mask)
+    bind(module.Path, "fill", path_fill)
+    bind(module.Path, "stroke", path_stroke)
+    bind(module.Scene, "render", scene_render)
+    bind(module.Filter, "__call__", filter_call)
+    bind(module, "Layer", Layer)
+    g = globals()
+    for name in _MODULE_FUNCTIONS:
+        bind(module, name, g[name])
+    bind(module, "CANVAS_COMPOSE_OVER", functools.partial(canvas_compose, COMPOSE_OVER))
+    return saved
+
+
+def uninstall(saved):
+    """Undo install()."""
+    for (owner, name), value in saved.items():
+        if value is _MISSING:
+            try:
+                delattr(owner, name)
+            except AttributeError:
+                pass
+        else:
+            setattr(owner, name, value)

@@ -110,6 +110,7 @@ struct Val {
     long long off2 = 0;
     int stride2 = 0;
     int level = 0;
+    bool missed = false;  // MERGE_AT whose overlay does not touch the box (canvas_merge_at returns None, :315-322)
     int luma_conv = 0;  // VAL_LUMA: Layer.convert code applied before the luminance
     // stencil: the value is multiplied by a one-channel view (a fused compose IN)
     int st_kind = 0;  // 0 none, else SRC_MOD_*
@@ -170,6 +171,8 @@ struct svgr_ctx {
     int n_path = 0, n_stroke = 0, n_stroke_sub = 0, n_paint = 0, n_stop = 0, n_focal = 0, n_node = 0;
     long long n_stroke_seg = 0;
     long long canvas_bytes = 0;
+    double flatness = 0.0;
+    DevBuf d_eager[3];  // scratch of the eager element-wise entry points
     DevBuf d_seg_tag, d_seg_data, d_seg_path, d_paths, d_strokes, d_ssub_off, d_ssub_job, d_stag, d_sdata, d_sseg_job;
     DevBuf d_sitems;            // stroke assembly work items: (sub-path, first segment, end segment), <= 256 segments each
     std::vector<int> h_sitems;
@@ -231,6 +234,7 @@ inline long long align4(long long v) { return (v + 3) & ~3ll; }
 struct Planner {
     svgr_ctx *ctx;
     std::string err;
+    int err_code = SVGR_E_INVALID;
     long long layer_top = 0;
     const std::vector<int> *uses_p = nullptr;  // how many nodes read each node (shared, read-only while planning)
     std::vector<PlannedOp> sorted_ops;
@@ -384,7 +388,10 @@ struct Planner {
     }
 
     // Layer.compose (svgrasterize.py:178-207)
-    Val compose(const std::vector<Val> &layers, int mode, const float *k, int lin)
+    // intersect: blend on the intersection of the boxes whatever the mode (canvas_merge_intersect, :382-416);
+    // raw: the layers are plain arrays, blended as they are (canvas_compose, :277-298, has no Layer.convert)
+    Val compose(const std::vector<Val> &layers, int mode, const float *k, int lin, bool intersect = false,
+                bool raw = false)
     {
         if (layers.empty())
             return Val();
@@ -392,7 +399,7 @@ struct Planner {
             return layers[0];
         int pre = mode != MODE_ARITH;
         int r0, c0, r1, c1;
-        if (mode == MODE_IN) {
+        if (mode == MODE_IN || intersect) {
             r0 = c0 = INT32_MIN, r1 = c1 = INT32_MAX;
             for (auto &l : layers) {
                 r0 = std::max(r0, l.r0), c0 = std::max(c0, l.c0);
@@ -411,7 +418,7 @@ struct Planner {
         std::vector<SrcRec> &ss = sl.v;
         int level = 0;
         for (auto &l : layers)
-            level = std::max(level, push_src(ss, l, pre, lin));
+            level = std::max(level, raw ? push_src(ss, l, l.pre, l.lin) : push_src(ss, l, pre, lin));
         level += 1;
         Val out = alloc(SRC_L4, r0, c0, r1 - r0, c1 - c0, pre, lin, level);
         out.op_index = (int)ops_p->size();
@@ -466,6 +473,13 @@ struct Planner {
                     if (pat.kind != SRC_L4) {  // tile rendered to nothing: Path.fill returns None (:1064-1065)
                         out = Val();
                         break;
+                    }
+                    if (pat.missed) {
+                        // the tile misses its repeat cell: canvas_merge_at returns None (:315-322) and the gather
+                        // at :1094 subscripts it -- the reference raises TypeError
+                        err = "'NoneType' object is not subscriptable";
+                        err_code = SVGR_E_TYPE;
+                        return false;
                     }
                     out.off2 = pat.off, out.stride2 = pat.stride;
                     out.pre = pat.pre, out.lin = pat.lin;
@@ -572,7 +586,7 @@ struct Planner {
                 err = "invalid compose mode";
                 return false;
             }
-            out = compose(ls, n.a, kk, lin);
+            out = compose(ls, n.a, kk, lin, (n.flags & 4) != 0, (n.flags & 8) != 0);
             break;
         }
         case SVGR_N_SRC_ALPHA: {
@@ -693,6 +707,8 @@ struct Planner {
                 Val o2 = alloc(SRC_L4, n.a, n.b, n.c, n.d, vv.pre, vv.lin, level);
                 emit(0, OP_COMPOSE, o2, ss, MODE_OVER, POST_CLIP01, 1.0f, o2.level);
                 out = o2;
+                out.missed = std::min(vv.r0 + vv.rows, n.a + n.c) <= std::max(vv.r0, n.a) ||
+                             std::min(vv.c0 + vv.cols, n.b + n.d) <= std::max(vv.c0, n.b);
             }
             break;
         }
@@ -1092,41 +1108,16 @@ static int load_program(svgr_ctx *ctx, const svgr_program *p, cudaStream_t s, bo
 {
     if (!p)
         FAIL(SVGR_E_INVALID, "null program");
-    if (p->n_seg < 0 || p->n_path < 0 || p->n_node < 0 || p->n_stroke_seg < 0)
+    // ---- validate everything the device will index with before anything of the context changes: a rejected
+    // program leaves the resident one (and svgr_render_resident) intact
+    if (p->n_seg < 0 || p->n_path < 0 || p->n_node < 0 || p->n_stroke_seg < 0 || p->n_stroke < 0 || p->n_stroke_sub < 0 ||
+        p->n_paint < 0 || p->n_stop < 0 || p->n_focal < 0 || p->n_child < 0 || p->n_kernel < 0 || p->n_weight < 0 ||
+        p->n_matrix < 0 || p->n_offset_tr < 0 || p->n_external < 0 || p->canvas_bytes < 0)
         FAIL(SVGR_E_INVALID, "negative count in program");
-    ctx->n_seg = p->n_seg, ctx->n_path = p->n_path, ctx->n_stroke = p->n_stroke, ctx->n_stroke_sub = p->n_stroke_sub;
-    ctx->n_stroke_seg = p->n_stroke_seg, ctx->n_paint = p->n_paint, ctx->n_stop = p->n_stop, ctx->n_focal = p->n_focal;
-    ctx->n_node = p->n_node, ctx->canvas_bytes = p->canvas_bytes;
-    ctx->n_weight = p->n_weight, ctx->n_matrix = p->n_matrix;
-    if (!host_only) {
-    CK(upload(ctx->d_seg_tag, p->seg_tag, (size_t)p->n_seg, s));
-    CK(upload(ctx->d_seg_data, p->seg_data, (size_t)p->n_seg * 8, s));
-    CK(upload(ctx->d_seg_path, p->seg_path, (size_t)p->n_seg, s));
-    CK(upload(ctx->d_paths, p->paths, (size_t)p->n_path, s));
-    CK(upload(ctx->d_strokes, p->strokes, (size_t)p->n_stroke, s));
-    CK(upload(ctx->d_ssub_off, p->stroke_sub_off, p->n_stroke_sub > 0 ? (size_t)p->n_stroke_sub + 1 : 0, s));
-    CK(upload(ctx->d_ssub_job, p->stroke_sub_job, (size_t)p->n_stroke_sub, s));
-    {   // one warp assembles the outline of at most 256 consecutive segments of a sub-path
-        ctx->h_sitems.clear();
-        for (int q = 0; q < p->n_stroke_sub; q++) {
-            const int a = p->stroke_sub_off[q], b = p->stroke_sub_off[q + 1];
-            for (int x = a; x < b; x += 256) {
-                ctx->h_sitems.push_back(q);
-                ctx->h_sitems.push_back(x);
-                ctx->h_sitems.push_back(std::min(x + 256, b));
-            }
-        }
-        ctx->n_sitems = (int)(ctx->h_sitems.size() / 3);
-        CK(upload(ctx->d_sitems, ctx->h_sitems.data(), ctx->h_sitems.size(), s));
-    }
-    CK(upload(ctx->d_stag, p->stroke_tag, (size_t)p->n_stroke_seg, s));
-    CK(upload(ctx->d_sdata, p->stroke_data, (size_t)p->n_stroke_seg * 8, s));
-    CK(upload(ctx->d_sseg_job, p->stroke_seg_job, (size_t)p->n_stroke_seg, s));
-    CK(upload(ctx->d_paints, p->paints, (size_t)p->n_paint, s));
-    CK(upload(ctx->d_stops, p->stops, (size_t)p->n_stop, s));
-    CK(upload(ctx->d_matrices, p->matrices, (size_t)p->n_matrix * 20, s));
-    CK(upload(ctx->d_weights, p->weights, (size_t)p->n_weight, s));
-    }
+    if (!(p->flatness >= 0.0))
+        FAIL(SVGR_E_INVALID, "flatness must be >= 0 (0 = the reference's 0.1)");
+    if (p->n_seg > 0x3fffffffll || p->n_stroke_seg > 0x3fffffffll)
+        FAIL(SVGR_E_UNSUPPORTED, "more than 2^30 segments in one program");
     for (int i = 0; i < p->n_node; i++) {
         const svgr_node &n = p->nodes[i];
         if (n.child_cnt < 0 || n.child_off < 0 || (long long)n.child_off + n.child_cnt > p->n_child)
@@ -1135,9 +1126,26 @@ static int load_program(svgr_ctx *ctx, const svgr_program *p, cudaStream_t s, bo
     for (long long i = 0; i < p->n_seg; i++)
         if (p->seg_path[i] >= (uint32_t)p->n_path)
             FAIL(SVGR_E_INVALID, "segment refers to a path outside the path table");
-    for (int i = 0; i < p->n_stroke; i++)
-        if (p->strokes[i].path < 0 || p->strokes[i].path >= p->n_path)
+    for (int i = 0; i < p->n_stroke; i++) {
+        const StrokeRec &q = p->strokes[i];
+        if (q.path < 0 || q.path >= p->n_path)
             FAIL(SVGR_E_INVALID, "stroke refers to a path outside the path table");
+        if (q.sub_begin < 0 || q.sub_end < q.sub_begin || q.sub_end > p->n_stroke_sub)
+            FAIL(SVGR_E_INVALID, "stroke sub-path range outside the sub-path table");
+    }
+    if (p->n_stroke_sub > 0) {
+        if (p->stroke_sub_off[0] < 0 || (long long)p->stroke_sub_off[p->n_stroke_sub] > p->n_stroke_seg)
+            FAIL(SVGR_E_INVALID, "stroke sub-path offsets outside the stroke segments");
+        for (int q = 0; q < p->n_stroke_sub; q++) {
+            if (p->stroke_sub_off[q] > p->stroke_sub_off[q + 1])
+                FAIL(SVGR_E_INVALID, "stroke sub-path offsets must not decrease");
+            if (p->stroke_sub_job[q] < 0 || p->stroke_sub_job[q] >= p->n_stroke)
+                FAIL(SVGR_E_INVALID, "stroke sub-path refers to a job outside the stroke table");
+        }
+    }
+    for (long long i = 0; i < p->n_stroke_seg; i++)
+        if (p->stroke_seg_job[i] < 0 || p->stroke_seg_job[i] >= p->n_stroke)
+            FAIL(SVGR_E_INVALID, "stroke segment refers to a job outside the stroke table");
     for (int i = 0; i < p->n_paint; i++) {
         const PaintRec &q = p->paints[i];
         if (q.kind != PAINT_SOLID && q.kind != PAINT_PATTERN &&
@@ -1145,6 +1153,55 @@ static int load_program(svgr_ctx *ctx, const svgr_program *p, cudaStream_t s, bo
             FAIL(SVGR_E_INVALID, "gradient without stops");
         if (q.kind == PAINT_RADIAL_FOCAL && (q.flag < 0 || q.flag >= p->n_focal))
             FAIL(SVGR_E_INVALID, "focal flag index out of range");
+    }
+    for (int i = 0; i < p->n_kernel; i++) {
+        const svgr_kernel &k = p->kernels[i];
+        if (k.rows < 1 || k.cols < 1 || k.weight_off < 0)
+            FAIL(SVGR_E_INVALID, "convolution kernel with an empty extent");
+        const long long need = k.separable ? (long long)k.rows + k.cols : (long long)k.rows * k.cols;
+        if ((long long)k.weight_off + need > p->n_weight)
+            FAIL(SVGR_E_INVALID, "convolution kernel weights outside the weight table");
+    }
+    for (int i = 0; i < p->n_external; i++) {
+        const svgr_external &e = p->externals[i];
+        if (e.channels != 1 && e.channels != 4)
+            FAIL(SVGR_E_INVALID, "external layer must have 1 or 4 channels");
+    }
+    // ---- accepted: from here on the context describes the new program
+    ctx->have_program = false;
+    ctx->n_seg = p->n_seg, ctx->n_path = p->n_path, ctx->n_stroke = p->n_stroke, ctx->n_stroke_sub = p->n_stroke_sub;
+    ctx->n_stroke_seg = p->n_stroke_seg, ctx->n_paint = p->n_paint, ctx->n_stop = p->n_stop, ctx->n_focal = p->n_focal;
+    ctx->n_node = p->n_node, ctx->canvas_bytes = p->canvas_bytes;
+    ctx->n_weight = p->n_weight, ctx->n_matrix = p->n_matrix;
+    ctx->flatness = p->flatness;
+    if (!host_only) {
+        CK(upload(ctx->d_seg_tag, p->seg_tag, (size_t)p->n_seg, s));
+        CK(upload(ctx->d_seg_data, p->seg_data, (size_t)p->n_seg * 8, s));
+        CK(upload(ctx->d_seg_path, p->seg_path, (size_t)p->n_seg, s));
+        CK(upload(ctx->d_paths, p->paths, (size_t)p->n_path, s));
+        CK(upload(ctx->d_strokes, p->strokes, (size_t)p->n_stroke, s));
+        CK(upload(ctx->d_ssub_off, p->stroke_sub_off, p->n_stroke_sub > 0 ? (size_t)p->n_stroke_sub + 1 : 0, s));
+        CK(upload(ctx->d_ssub_job, p->stroke_sub_job, (size_t)p->n_stroke_sub, s));
+        {   // one warp assembles the outline of at most 256 consecutive segments of a sub-path
+            ctx->h_sitems.clear();
+            for (int q = 0; q < p->n_stroke_sub; q++) {
+                const int a = p->stroke_sub_off[q], b = p->stroke_sub_off[q + 1];
+                for (int x = a; x < b; x += 256) {
+                    ctx->h_sitems.push_back(q);
+                    ctx->h_sitems.push_back(x);
+                    ctx->h_sitems.push_back(std::min(x + 256, b));
+                }
+            }
+            ctx->n_sitems = (int)(ctx->h_sitems.size() / 3);
+            CK(upload(ctx->d_sitems, ctx->h_sitems.data(), ctx->h_sitems.size(), s));
+        }
+        CK(upload(ctx->d_stag, p->stroke_tag, (size_t)p->n_stroke_seg, s));
+        CK(upload(ctx->d_sdata, p->stroke_data, (size_t)p->n_stroke_seg * 8, s));
+        CK(upload(ctx->d_sseg_job, p->stroke_seg_job, (size_t)p->n_stroke_seg, s));
+        CK(upload(ctx->d_paints, p->paints, (size_t)p->n_paint, s));
+        CK(upload(ctx->d_stops, p->stops, (size_t)p->n_stop, s));
+        CK(upload(ctx->d_matrices, p->matrices, (size_t)p->n_matrix * 20, s));
+        CK(upload(ctx->d_weights, p->weights, (size_t)p->n_weight, s));
     }
     ctx->have_program = true;
     ctx->planned = ctx->covered = ctx->composed = false;
@@ -1238,7 +1295,9 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
         mark(1);
         // ---- flatten + bounds
         if (stop_after != SVGR_STOP_STROKE) {
-            const double tol = 0.1;  // literal flatness of Path.mask (svgrasterize.py:955/:957)
+            // Path.mask's literal flatness 0.1 (svgrasterize.py:955/:957) unless the program carries another one
+            // (bezier3_flatten_batch(batch, flatness), :2091-2093: threshold = flatness^2 * 16)
+            const double tol = ctx->flatness > 0.0 ? ctx->flatness : 0.1;
             const double thr = (tol * tol) * 16;
             // overflow lists of the multi-pass flatten (deep subdivision trees are re-spread over all warps)
             svgr_flat_overflow ovf;
@@ -1312,6 +1371,8 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
     if (st.stroke_err & 2)
         FAIL(SVGR_E_INVALID, "stroke assembly overflow or unknown line cap");
     ctx->n_edges = (long long)st.n_edges;
+    if (ctx->n_edges > 0x7fffffffll / 4)
+        FAIL(SVGR_E_UNSUPPORTED, "more than 2^29 edges in one program: the band scans are 32-bit");
     ctx->h_boxes.assign((PathBox *)ctx->pin_boxes.p, (PathBox *)ctx->pin_boxes.p + ctx->n_path);
 
     if (stats) {
@@ -1328,7 +1389,7 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
         ctx->h_masks = ctx->h_masks_store.data();
         Planner pl0(ctx);
         if (!pl0.run())
-            FAIL(SVGR_E_INVALID, pl0.err);
+            FAIL(pl0.err_code, pl0.err);
         ctx->planned = true;
         return SVGR_OK;
     }
@@ -1428,7 +1489,7 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
             int op_begin = 0, launch_begin = 0;
             auto t_c0 = std::chrono::steady_clock::now();
             if (!pl.plan_chunk(k, &op_begin, &launch_begin))
-                FAIL(SVGR_E_INVALID, pl.err);
+                FAIL(pl.err_code, pl.err);
             host_nodes_ms += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_c0).count();
             if (stop_after == SVGR_STOP_COVERAGE)
                 continue;
@@ -1672,6 +1733,7 @@ int svgr_sizeof(int what)
     case 6: return (int)sizeof(svgr_external);
     case 7: return (int)sizeof(svgr_program);
     case 8: return (int)sizeof(svgr_stats);
+    case 9: return (int)sizeof(MaskRec);
     default: return -1;
     }
 }
@@ -1726,7 +1788,8 @@ void svgr_destroy(svgr_ctx *ctx)
                       &ctx->d_band_cur, &ctx->d_bin_edges, &ctx->d_cov, &ctx->d_layers, &ctx->d_ops, &ctx->d_srcs,
                       &ctx->d_focal_jobs, &ctx->d_focal_flags, &ctx->d_canvas, &ctx->d_q, &ctx->d_tile_map, &ctx->d_tile_rec, &ctx->d_bin_data, &ctx->d_heads[0], &ctx->d_heads[1], &ctx->d_lists[0],
                       &ctx->d_lists[1], &ctx->d_ovf_cubic[0], &ctx->d_ovf_cubic[1], &ctx->d_ovf_path[0], &ctx->d_ovf_path[1],
-                      &ctx->d_ovf_depth[0], &ctx->d_ovf_depth[1], &ctx->d_ovf_counts};
+                      &ctx->d_ovf_depth[0], &ctx->d_ovf_depth[1], &ctx->d_ovf_counts, &ctx->d_eager[0], &ctx->d_eager[1],
+                      &ctx->d_eager[2]};
     for (DevBuf *b : bufs)
         b->release();
     ctx->pin_boxes.release(), ctx->pin_status.release(), ctx->pin_plan.release(), ctx->pin_out.release();
@@ -1797,6 +1860,8 @@ int svgr_render(svgr_ctx *ctx, const svgr_program *prog, void *stream, int stop_
         ctx->pending = nullptr;
         ctx->have_program = false;
     }
+    if (rc != SVGR_OK && rc != SVGR_E_INVALID)
+        ctx->have_program = false;  // a render that died half way leaves nothing to re-render either
     if (timing) {
         if (rc == SVGR_OK && stats) {
             stats->ms_h2d = ev_ms(e0, e1);
@@ -2023,6 +2088,146 @@ int svgr_cloud_bounds(svgr_ctx *ctx, int32_t n_query, const int32_t *q_off, cons
                              (double *)(d + a_out), n_query, ctx->sm_count, s);
     CK(cudaMemcpyAsync(out, d + a_out, b_mm, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    return SVGR_OK;
+}
+
+// ---- eager element-wise entry points: host in, one kernel, host out -------------------------
+int svgr_line_signed_coverage(svgr_ctx *ctx, float *trace, int32_t rows, int32_t cols, const double *lines, int64_t n)
+{
+    if (!ctx)
+        return SVGR_E_INVALID;
+    if (!trace || rows < 0 || cols < 0 || n < 0 || (n > 0 && !lines))
+        FAIL(SVGR_E_INVALID, "line_signed_coverage: bad arguments");
+    if (rows == 0 || cols == 0 || n == 0)
+        return SVGR_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->own_stream;
+    const size_t b_trace = (size_t)rows * cols * 4, b_lines = (size_t)n * 32;
+    CK(ctx->d_eager[0].ensure(b_trace));
+    CK(ctx->d_eager[1].ensure(b_lines));
+    CK(cudaMemcpyAsync(ctx->d_eager[0].p, trace, b_trace, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->d_eager[1].p, lines, b_lines, cudaMemcpyHostToDevice, s));
+    svgr_launch_line_coverage(ctx->d_eager[1].as<double>(), n, ctx->d_eager[0].as<float>(), rows, cols, s);
+    CK(cudaMemcpyAsync(trace, ctx->d_eager[0].p, b_trace, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    return SVGR_OK;
+}
+
+int svgr_grad_pixels(svgr_ctx *ctx, int32_t r0, int32_t c0, int32_t rows, int32_t cols, double *out)
+{
+    if (!ctx)
+        return SVGR_E_INVALID;
+    if (rows < 0 || cols < 0 || (!out && rows > 0 && cols > 0))
+        FAIL(SVGR_E_INVALID, "grad_pixels: bad arguments");
+    const size_t bytes = (size_t)rows * cols * 16;
+    if (bytes == 0)
+        return SVGR_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->own_stream;
+    CK(ctx->d_eager[0].ensure(bytes));
+    svgr_launch_grad_pixels(r0, c0, rows, cols, ctx->d_eager[0].as<double>(), s);
+    CK(cudaMemcpyAsync(out, ctx->d_eager[0].p, bytes, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    return SVGR_OK;
+}
+
+int svgr_grad_spread(svgr_ctx *ctx, const double *offsets, int64_t n, int32_t spread, double *out)
+{
+    if (!ctx)
+        return SVGR_E_INVALID;
+    if (n < 0 || (n > 0 && (!offsets || !out)))
+        FAIL(SVGR_E_INVALID, "grad_spread: bad arguments");
+    if (spread < 0 || spread > 2)
+        FAIL(SVGR_E_INVALID, "invalid spread method");
+    if (n == 0)
+        return SVGR_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->own_stream;
+    CK(ctx->d_eager[0].ensure((size_t)n * 8));
+    CK(ctx->d_eager[1].ensure((size_t)n * 8));
+    CK(cudaMemcpyAsync(ctx->d_eager[0].p, offsets, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+    svgr_launch_grad_spread(ctx->d_eager[0].as<double>(), n, spread, ctx->d_eager[1].as<double>(), s);
+    CK(cudaMemcpyAsync(out, ctx->d_eager[1].p, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    return SVGR_OK;
+}
+
+int svgr_grad_interpolate(svgr_ctx *ctx, const double *offsets, int64_t n, const struct StopRec *stops, int32_t n_stops,
+                          float *out)
+{
+    if (!ctx)
+        return SVGR_E_INVALID;
+    if (n < 0 || (n > 0 && (!offsets || !out)))
+        FAIL(SVGR_E_INVALID, "grad_interpolate: bad arguments");
+    if (n_stops < 1 || !stops)
+        FAIL(SVGR_E_INVALID, "gradient without stops");
+    if (n == 0)
+        return SVGR_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->own_stream;
+    CK(ctx->d_eager[0].ensure((size_t)n * 8));
+    CK(ctx->d_eager[1].ensure((size_t)n * 16));
+    CK(ctx->d_eager[2].ensure((size_t)n_stops * sizeof(StopRec)));
+    CK(cudaMemcpyAsync(ctx->d_eager[0].p, offsets, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->d_eager[2].p, stops, (size_t)n_stops * sizeof(StopRec), cudaMemcpyHostToDevice, s));
+    svgr_launch_grad_interpolate(ctx->d_eager[0].as<double>(), n, ctx->d_eager[2].as<StopRec>(), n_stops,
+                                 ctx->d_eager[1].as<float>(), s);
+    CK(cudaMemcpyAsync(out, ctx->d_eager[1].p, (size_t)n * 16, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    return SVGR_OK;
+}
+
+int svgr_quantize_u8(svgr_ctx *ctx, const float *values, int64_t n, uint8_t *out)
+{
+    if (!ctx)
+        return SVGR_E_INVALID;
+    if (n < 0 || (n > 0 && (!values || !out)))
+        FAIL(SVGR_E_INVALID, "quantize: bad arguments");
+    if (n == 0)
+        return SVGR_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->own_stream;
+    CK(ctx->d_eager[0].ensure((size_t)n * 4));
+    CK(ctx->d_eager[1].ensure((size_t)n));
+    CK(cudaMemcpyAsync(ctx->d_eager[0].p, values, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    svgr_launch_quantize(ctx->d_eager[0].as<float>(), n, ctx->d_eager[1].as<uint8_t>(), s);
+    CK(cudaMemcpyAsync(out, ctx->d_eager[1].p, (size_t)n, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    return SVGR_OK;
+}
+
+int svgr_pooling(svgr_ctx *ctx, const float *mat, int32_t rows, int32_t cols, int32_t ch, int32_t ky, int32_t kx,
+                 int32_t sy, int32_t sx, int32_t method, int32_t pad, float *out, int32_t out_rows, int32_t out_cols)
+{
+    if (!ctx)
+        return SVGR_E_INVALID;
+    if (!mat || !out || rows < 0 || cols < 0 || ch < 1 || ky < 1 || kx < 1 || sy < 1 || sx < 1)
+        FAIL(SVGR_E_INVALID, "pooling: bad arguments");
+    if (method < 0 || method > 2)
+        FAIL(SVGR_E_INVALID, "invalid poll method");
+    // output extent of the reference (:435-455): padded -> ceil(n / s); cropped -> (n - k) / s + 1
+    const int want_r = pad ? (rows + sy - 1) / sy : (rows >= ky ? (rows - ky) / sy + 1 : 0);
+    const int want_c = pad ? (cols + sx - 1) / sx : (cols >= kx ? (cols - kx) / sx + 1 : 0);
+    if (out_rows != want_r || out_cols != want_c)
+        FAIL(SVGR_E_INVALID, "pooling: output extent does not match ksize / stride / pad");
+    const size_t b_in = (size_t)rows * cols * ch * 4, b_out = (size_t)out_rows * out_cols * ch * 4;
+    if (b_out == 0)
+        return SVGR_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->own_stream;
+    CK(ctx->d_eager[0].ensure(b_in));
+    CK(ctx->d_eager[1].ensure(b_out));
+    CK(cudaMemcpyAsync(ctx->d_eager[0].p, mat, b_in, cudaMemcpyHostToDevice, s));
+    svgr_launch_pooling(ctx->d_eager[0].as<float>(), rows, cols, ch, ky, kx, sy, sx, method, ctx->d_eager[1].as<float>(),
+                        out_rows, out_cols, s);
+    CK(cudaMemcpyAsync(out, ctx->d_eager[1].p, b_out, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
     return SVGR_OK;
 }
 

@@ -23,6 +23,8 @@
 // 512 contiguous bytes of an RGBA row.  cull_kernel (one warp per tile) first writes, for every tile, the list of
 // the op's sources that touch it, order preserved; the compose CTA copies its op, those sources and their paints
 // into shared memory in one pass and folds them in registers.
+#include <algorithm>
+
 #include "svgr_device.cuh"
 
 #define CMP_TR SVGR_CMP_TR   // 32 rows: 4 pixels per thread, 8 rows apart
@@ -465,4 +467,69 @@ void svgr_launch_focal_flags(const RenderTables &T, const void *jobs, int n_jobs
 {
     if (n_blocks > 0)
         focal_flag_kernel<<<n_blocks, 256, 0, s>>>(T, (const FocalJob *)jobs, n_jobs, block0, flags);
+}
+
+// ---------------------------------------------------------------------------------------------
+// eager element-wise entry points of the reference's call surface (svgr_grad_* / svgr_quantize_u8)
+// ---------------------------------------------------------------------------------------------
+// grad_pixels (svgrasterize.py:1653-1658): centres of the pixels of a viewport
+__global__ void grad_pixels_kernel(int r0, int c0, long long n, int cols, double2 *__restrict__ out)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / cols, c = i - r * cols;
+        out[i] = make_double2((double)r + ((double)r0 + 0.5), (double)c + ((double)c0 + 0.5));
+    }
+}
+
+// grad_spread (svgrasterize.py:1661-1668)
+__global__ void grad_spread_kernel(const double *__restrict__ in, long long n, int spread, double *__restrict__ out)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = grad_spread(in[i], spread);
+}
+
+// grad_interpolate (svgrasterize.py:1671-1683)
+__global__ void grad_interpolate_kernel(const double *__restrict__ in, long long n, const StopRec *__restrict__ stops,
+                                        int n_stops, float4 *__restrict__ out)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = grad_color(in[i], stops, n_stops);
+}
+
+// np.round(x * 255).astype(np.uint8) (svgrasterize.py:263): round half even; values outside [0, 255] wrap like the
+// integer cast does on x86-64 (the low byte of the rounded integer), NaN -> 0
+__global__ void quantize_kernel(const float *__restrict__ in, long long n, uint8_t *__restrict__ out)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float v = rintf(in[i] * 255.0f);
+        out[i] = (v == v) ? (uint8_t)((long long)v & 0xff) : (uint8_t)0;
+    }
+}
+
+static unsigned eager_blocks(long long n) { return (unsigned)std::max<long long>(1, std::min<long long>((n + 255) / 256, 148 * 32)); }
+
+void svgr_launch_grad_pixels(int r0, int c0, int rows, int cols, double *out, cudaStream_t s)
+{
+    const long long n = (long long)rows * cols;
+    if (n > 0)
+        grad_pixels_kernel<<<eager_blocks(n), 256, 0, s>>>(r0, c0, n, cols, reinterpret_cast<double2 *>(out));
+}
+
+void svgr_launch_grad_spread(const double *in, long long n, int spread, double *out, cudaStream_t s)
+{
+    if (n > 0)
+        grad_spread_kernel<<<eager_blocks(n), 256, 0, s>>>(in, n, spread, out);
+}
+
+void svgr_launch_grad_interpolate(const double *in, long long n, const StopRec *stops, int n_stops, float *out,
+                                  cudaStream_t s)
+{
+    if (n > 0)
+        grad_interpolate_kernel<<<eager_blocks(n), 256, 0, s>>>(in, n, stops, n_stops, reinterpret_cast<float4 *>(out));
+}
+
+void svgr_launch_quantize(const float *in, long long n, uint8_t *out, cudaStream_t s)
+{
+    if (n > 0)
+        quantize_kernel<<<eager_blocks(n), 256, 0, s>>>(in, n, out);
 }

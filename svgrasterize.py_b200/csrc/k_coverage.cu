@@ -19,6 +19,9 @@
 // (SURVEY A7): coverage that falls left of column 0 is accumulated INTO column
 // 0; a chunk treats everything left of it the same way, which is exactly the
 // running winding number the prefix sum would have carried in.
+#include <algorithm>
+#include <atomic>
+
 #include "svgr_kernels.h"
 
 #define COV_THREADS 128
@@ -451,6 +454,48 @@ coverage_kernel(const TileRec *__restrict__ tiles, int n_tiles, const double2 *_
     }
 }
 
+// line_signed_coverage(canvas, line) (svgrasterize.py:2213-2304) as an entry point of its own: one thread per
+// line walks the rows the line crosses and adds its signed-area deltas to a trace in global memory (the same
+// per-row arithmetic as the tile kernel above, mask origin (0, 0), no column chunking).
+__global__ void line_coverage_kernel(const double *__restrict__ lines, long long n, float *__restrict__ trace, int rows,
+                                     int cols)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double r0 = lines[4 * i], c0 = lines[4 * i + 1], r1 = lines[4 * i + 2], c1 = lines[4 * i + 3];
+        if (r0 == r1 || !(r0 == r0) || !(r1 == r1))
+            continue;
+        double dir = 1.0;
+        if (!(r0 < r1)) {
+            double t;
+            dir = -1.0;
+            t = r0, r0 = r1, r1 = t;
+            t = c0, c0 = c1, c1 = t;
+        }
+        const double dxdy = (c1 - c0) / (r1 - r0);
+        const double ys = r0 > 0.0 ? r0 : 0.0;
+        if (ys >= (double)rows)
+            continue;
+        const double yend_f = ceil(r1);
+        const int y_first = (int)ys, y_last = yend_f < (double)rows ? (int)yend_f : rows;
+        for (int y = y_first; y < y_last; y++) {
+            const double ytop = (double)(y + 1) < r1 ? (double)(y + 1) : r1;
+            const double ybot = (double)y > r0 ? (double)y : r0;
+            const double dy = ytop - ybot;
+            const double x = c0 + dxdy * (ybot - r0);
+            const double x_next = x + dxdy * dy;
+            edge_row(trace + (long long)y * cols, cols, x, x_next, dir * dy);
+        }
+    }
+}
+
+void svgr_launch_line_coverage(const double *lines, long long n, float *trace, int rows, int cols, cudaStream_t s)
+{
+    if (n <= 0 || rows <= 0 || cols <= 0)
+        return;
+    const long long blocks = std::min<long long>((n + 127) / 128, 148 * 16);
+    line_coverage_kernel<<<(unsigned)blocks, 128, 0, s>>>(lines, n, trace, rows, cols);
+}
+
 // ---------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------
@@ -513,13 +558,19 @@ void svgr_launch_coverage(const MaskRec *masks, int n_masks, int n_tiles, TileRe
     if (n_tiles <= 0)
         return;
     expand_masks_kernel<<<(n_tiles + 255) / 256, 256, 0, s>>>(masks, n_masks, n_tiles, band_off, band_cnt, bin_cap, tiles);
-    static int wave = 0;  // CTAs of one full wave on this device
+    // CTAs of one full wave, per device (contexts of several devices and threads share this table: the value is
+    // a pure function of the device, so a racing double initialisation writes the same number)
+    static std::atomic<int> wave_of[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    int wave = wave_of[dev].load(std::memory_order_relaxed);
     if (wave == 0) {
-        int dev = 0, sms = 0, per_sm = 0;
-        cudaGetDevice(&dev);
+        int sms = 0, per_sm = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, coverage_kernel, COV_THREADS, 0);
         wave = std::max(1, sms * std::max(1, per_sm));
+        wave_of[dev].store(wave, std::memory_order_relaxed);
     }
     coverage_kernel<<<std::min(n_tiles, wave), COV_THREADS, 0, s>>>(tiles, n_tiles, reinterpret_cast<const double2 *>(bin_data),
                                                                   cov);

@@ -15,6 +15,8 @@
 // Layer.convert (straight alpha + linear RGB for blur, premultiplied linear for
 // morphology) is fused into the load.  A rotated anisotropic Gaussian is not
 // separable; OP_CONV2D applies the full kw x kh kernel directly.
+#include <atomic>
+
 #include "svgr_device.cuh"
 
 __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
@@ -192,14 +194,18 @@ conv2d_kernel(RenderTables T, const OpRec *__restrict__ ops, const int *__restri
 }
 
 // ---------------------------------------------------------------------------------------------
-static bool g_attr_set = false;
+// the opt-in is per device; setting it twice is harmless, so the flags only need to be atomic, not locked
+static std::atomic<bool> g_attr_set[64];
 
 static void ensure_attrs()
 {
-    if (!g_attr_set) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (!g_attr_set[dev].load(std::memory_order_acquire)) {
         cudaFuncSetAttribute(stencil_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SVGR_MAX_DYN_SMEM);
         cudaFuncSetAttribute(conv2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SVGR_MAX_DYN_SMEM);
-        g_attr_set = true;
+        g_attr_set[dev].store(true, std::memory_order_release);
     }
 }
 
@@ -225,4 +231,51 @@ int svgr_launch_conv2d(const RenderTables &T, const OpRec *ops, const int *tile_
     ensure_attrs();
     conv2d_kernel<<<n_tiles, 256, smem_bytes, s>>>(T, ops, tile_op, layers_out);
     return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pooling(mat, ksize, stride, method, pad) (svgrasterize.py:419-468) in its general form: strided windows, NaN
+// padding to ceil(n / s) outputs, max / min / mean that ignore NaN (np.nanmax / nanmin / nanmean).  The hot
+// path (Layer.morphology: stride 1, no padding) runs the separable stencils above; this is the call surface.
+// ---------------------------------------------------------------------------------------------
+__global__ void pooling_kernel(const float *__restrict__ in, int rows, int cols, int ch, int ky, int kx, int sy, int sx,
+                               int method, float *__restrict__ out, int orows, int ocols)
+{
+    const long long n = (long long)orows * ocols * ch;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % ch);
+        const long long px = i / ch;
+        const int oc = (int)(px % ocols), orow = (int)(px / ocols);
+        float acc = __int_as_float(0x7fc00000), sum = 0.f;
+        int cnt = 0;
+        for (int a = 0; a < ky; a++) {
+            const int r = orow * sy + a;
+            if (r >= rows)
+                break;  // NaN padding: ignored
+            for (int b = 0; b < kx; b++) {
+                const int q = oc * sx + b;
+                if (q >= cols)
+                    break;
+                const float v = in[((long long)r * cols + q) * ch + c];
+                if (method == 0)
+                    acc = nanmax1(acc, v);
+                else if (method == 1)
+                    acc = nanmin1(acc, v);
+                else if (v == v)
+                    sum += v, cnt++;
+            }
+        }
+        out[i] = method == 2 ? (cnt ? sum / (float)cnt : __int_as_float(0x7fc00000)) : acc;
+    }
+}
+
+void svgr_launch_pooling(const float *in, int rows, int cols, int ch, int ky, int kx, int sy, int sx, int method,
+                         float *out, int orows, int ocols, cudaStream_t s)
+{
+    const long long n = (long long)orows * ocols * ch;
+    if (n <= 0)
+        return;
+    const long long blocks = (n + 255) / 256;
+    pooling_kernel<<<(unsigned)(blocks < 148 * 32 ? blocks : 148 * 32), 256, 0, s>>>(in, rows, cols, ch, ky, kx, sy, sx,
+                                                                                  method, out, orows, ocols);
 }

@@ -55,7 +55,14 @@ void svgr_launch_bin_fill(const double *edges, const uint32_t *edge_path, unsign
 void svgr_launch_coverage(const MaskRec *masks, int n_masks, int n_tiles, TileRec *tiles, const int *band_off,
                           const int *band_cnt, const double *bin_data, long long bin_cap, float *cov, cudaStream_t s);
 
+void svgr_launch_line_coverage(const double *lines, long long n, float *trace, int rows, int cols, cudaStream_t s);
+
 // k_compose.cu
+void svgr_launch_grad_pixels(int r0, int c0, int rows, int cols, double *out, cudaStream_t s);
+void svgr_launch_grad_spread(const double *in, long long n, int spread, double *out, cudaStream_t s);
+void svgr_launch_grad_interpolate(const double *in, long long n, const StopRec *stops, int n_stops, float *out,
+                                  cudaStream_t s);
+void svgr_launch_quantize(const float *in, long long n, uint8_t *out, cudaStream_t s);
 void svgr_launch_expand_ops(const OpRec *ops, int n_ops, int n_tiles, int *tile_op, cudaStream_t s);
 void svgr_launch_cull(const RenderTables &T, const OpRec *ops, int n_ops, int n_tiles, TileHead *heads, TileEntry *list,
                       cudaStream_t s);
@@ -69,6 +76,9 @@ int svgr_launch_stencil(const RenderTables &T, const OpRec *ops, const int *tile
                         float *layers_out, cudaStream_t s);
 int svgr_launch_conv2d(const RenderTables &T, const OpRec *ops, const int *tile_op, int n_tiles, size_t smem_bytes,
                        float *layers_out, cudaStream_t s);
+
+void svgr_launch_pooling(const float *in, int rows, int cols, int ch, int ky, int kx, int sy, int sx, int method,
+                         float *out, int orows, int ocols, cudaStream_t s);
 
 // k_stroke.cu
 size_t svgr_stroke_curve_bytes();

@@ -150,6 +150,7 @@ class Program:
         self.canvas_bytes = 0
         self.canvases = []  # (node, byte offset, rows, cols)
         self.roots = []  # node index of every scene added with add_scene / add_root
+        self.flatness = 0.0  # 0: Path.mask's literal 0.1 (svgrasterize.py:955)
 
     # -- C view ------------------------------------------------------------------------------
     def to_c(self):
@@ -193,6 +194,7 @@ class Program:
         p.externals = C.cast(ext, C.c_void_p)
         p.n_external = len(self.externals)
         p.canvas_bytes = int(self.canvas_bytes)
+        p.flatness = float(self.flatness)
         return p, keep
 
     def h2d_bytes(self) -> int:
@@ -564,12 +566,15 @@ class Encoder:
             stack.append(out)
         return stack[-1]
 
-    def _compose(self, nodes, mode, lin) -> int:
+    def _compose(self, nodes, mode, lin, intersect=False, raw=False) -> int:
+        """Layer.compose (svgrasterize.py:178-207).  intersect: blend on the intersection of the boxes whatever
+        the mode (canvas_merge_intersect); raw: plain arrays, no Layer.convert (canvas_compose)."""
+        flags = int(bool(lin)) | (4 if intersect else 0) | (8 if raw else 0)
         if isinstance(mode, tuple) and len(mode) == 4:
-            return self._node(_lib.N_COMPOSE, 5, children=nodes, flags=int(bool(lin)), f=mode)
-        if mode not in (0, 1, 2, 3, 4):
+            return self._node(_lib.N_COMPOSE, 5, children=nodes, flags=flags, f=mode)
+        if isinstance(mode, bool) or mode not in (0, 1, 2, 3, 4):
             raise ValueError(f"invalid compose mode: {mode}")  # svgrasterize.py:298
-        return self._node(_lib.N_COMPOSE, int(mode), children=nodes, flags=int(bool(lin)))
+        return self._node(_lib.N_COMPOSE, int(mode), children=nodes, flags=flags)
 
     def _blur(self, source, kernel) -> int:
         rows, cols = kernel.shape

@@ -20,6 +20,7 @@ _ERRORS = {
     _lib.E_NOMEM: MemoryError,
     _lib.E_UNSUPPORTED: NotImplementedError,
     _lib.E_STROKE: TypeError,
+    _lib.E_TYPE: TypeError,
 }
 
 
@@ -57,11 +58,13 @@ class Engine:
 
     @staticmethod
     def _stream(stream):
+        """None -> the context's own (non-blocking) stream.  A torch stream or a raw handle -> that stream; torch's
+        default stream has handle 0, which the C-ABI would read as "own stream", so it is passed as
+        cudaStreamLegacy (0x1): the work is then ordered with everything else the caller has on that stream."""
         if stream is None:
             return None
-        if isinstance(stream, int):
-            return C.c_void_p(stream)
-        return C.c_void_p(stream.cuda_stream)  # torch.cuda.Stream
+        handle = stream if isinstance(stream, int) else stream.cuda_stream  # torch.cuda.Stream
+        return C.c_void_p(handle if handle else 1)
 
     # -- rendering -----------------------------------------------------------------------------
     def render(self, program: Program, stop: int = _lib.STOP_NONE, out=None, timing: bool = False, stream=None):
@@ -78,10 +81,11 @@ class Engine:
                 host_out = np.empty(program.canvas_bytes, dtype=np.uint8)
                 out_ptr = host_out.ctypes.data
             elif isinstance(out, np.ndarray):
-                assert out.dtype == np.uint8 and out.flags.c_contiguous and out.nbytes >= program.canvas_bytes
+                if out.dtype != np.uint8 or not out.flags.c_contiguous or out.nbytes < program.canvas_bytes:
+                    raise ValueError(f"out must be a C-contiguous uint8 array of >= {program.canvas_bytes} bytes")
                 out_ptr = out.ctypes.data
             else:  # torch tensor
-                assert out.is_cuda and out.is_contiguous() and out.numel() * out.element_size() >= program.canvas_bytes
+                self._check_device_tensor(out, program.canvas_bytes)
                 out_ptr, on_dev = out.data_ptr(), 1
         rc = self.L.svgr_render(self.ctx, C.byref(cprog), self._stream(stream), int(stop), out_ptr, on_dev,
                                 int(bool(timing)), C.byref(stats))
@@ -92,9 +96,19 @@ class Engine:
         self.last_stats = res
         return res
 
+    def _check_device_tensor(self, t, nbytes):
+        if not t.is_cuda or t.device.index != self.device:
+            raise ValueError(f"out must live on cuda:{self.device} (the engine's device), not {t.device}")
+        if not t.is_contiguous() or t.numel() * t.element_size() < nbytes:
+            raise ValueError(f"out must be contiguous and hold >= {nbytes} bytes")
+
     def render_resident(self, out_device=None, timing: bool = False, stream=None):
         """Re-run the device pipeline on the program left resident by the last render()."""
+        if self.program is None:
+            raise ValueError("no program resident: call render() first")
         stats = _lib.Stats()
+        if out_device is not None:
+            self._check_device_tensor(out_device, self.program.canvas_bytes)
         ptr = None if out_device is None else out_device.data_ptr()
         self._check(self.L.svgr_render_resident(self.ctx, self._stream(stream), ptr, int(bool(timing)), C.byref(stats)))
         return stats.as_dict()
@@ -167,6 +181,56 @@ class Engine:
         img = np.empty((rows, cols, ch), dtype=np.float32)
         self._check(self.L.svgr_read_node(self.ctx, int(node), img.ctypes.data))
         return img, (r0, c0), bool(pre), bool(lin)
+
+    # -- eager element-wise entry points ---------------------------------------------
+    def line_signed_coverage(self, trace: np.ndarray, lines: np.ndarray) -> np.ndarray:
+        """trace (rows, cols) float32 C-contiguous, updated in place; lines (n, 4) float64 [r0, c0, r1, c1]."""
+        lines = np.ascontiguousarray(lines, dtype=np.float64).reshape(-1, 4)
+        self._check(self.L.svgr_line_signed_coverage(self.ctx, trace.ctypes.data, trace.shape[0], trace.shape[1],
+                                                     lines.ctypes.data if len(lines) else None, len(lines)))
+        return trace
+
+    def grad_pixels(self, r0, c0, rows, cols) -> np.ndarray:
+        out = np.empty((int(rows), int(cols), 2), dtype=np.float64)
+        self._check(self.L.svgr_grad_pixels(self.ctx, int(r0), int(c0), int(rows), int(cols), _lib.ptr(out)))
+        return out
+
+    def grad_spread(self, offsets: np.ndarray, spread: int) -> np.ndarray:
+        offsets = np.ascontiguousarray(offsets, dtype=np.float64)
+        out = np.empty_like(offsets)
+        self._check(self.L.svgr_grad_spread(self.ctx, _lib.ptr(offsets), offsets.size, int(spread), _lib.ptr(out)))
+        return out
+
+    def grad_interpolate(self, offsets: np.ndarray, stops: np.ndarray) -> np.ndarray:
+        """stops: _lib.STOP_DT records already in the target colour space -> (..., 4) float32"""
+        offsets = np.ascontiguousarray(offsets, dtype=np.float64)
+        out = np.empty((*offsets.shape, 4), dtype=np.float32)
+        stops = np.ascontiguousarray(stops)
+        self._check(self.L.svgr_grad_interpolate(self.ctx, _lib.ptr(offsets), offsets.size, _lib.ptr(stops), len(stops),
+                                                 _lib.ptr(out)))
+        return out
+
+    def quantize_u8(self, values: np.ndarray) -> np.ndarray:
+        values = np.ascontiguousarray(values, dtype=np.float32)
+        out = np.empty(values.shape, dtype=np.uint8)
+        self._check(self.L.svgr_quantize_u8(self.ctx, _lib.ptr(values), values.size, _lib.ptr(out)))
+        return out
+
+    def pooling(self, mat: np.ndarray, ksize, stride, method: int, pad: bool) -> np.ndarray:
+        mat = np.ascontiguousarray(mat, dtype=np.float32)
+        rows, cols, ch = mat.shape
+        (ky, kx), (sy, sx) = ksize, stride
+        if pad:
+            orows, ocols = -(-rows // sy), -(-cols // sx)
+        else:
+            orows = (rows - ky) // sy + 1 if rows >= ky else 0
+            ocols = (cols - kx) // sx + 1 if cols >= kx else 0
+        out = np.empty((max(orows, 0), max(ocols, 0), ch), dtype=np.float32)
+        if out.size == 0 or mat.size == 0:
+            return out
+        self._check(self.L.svgr_pooling(self.ctx, _lib.ptr(mat), rows, cols, ch, int(ky), int(kx), int(sy), int(sx),
+                                        int(method), int(bool(pad)), _lib.ptr(out), orows, ocols))
+        return out
 
     def cloud_bounds(self, path_lists, inverses):
         """ConvexHull.bbox reductions: per query (list of path ids, inverse 2x3) -> (minx, miny, maxx, maxy)."""

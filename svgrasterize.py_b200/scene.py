@@ -10,8 +10,8 @@ Reference: svgrasterize.py:576-647 (scene node tags and builders), :865-892 (pat
 segment tags), :509-570 (Transform), :1544-1575 (gradients), :1698-1710
 (Pattern), :1718-1799 (filter program builder).
 
-Nothing here touches the GPU; rendering entry points live in ``api.py`` /
-``render.py`` and are attached to these classes there.
+Nothing here touches the GPU; rendering entry points live in ``api.py``
+and are attached to these classes there.
 """
 from __future__ import annotations
 
@@ -259,7 +259,7 @@ class Filter(NamedTuple):
 
 class Scene(tuple):
     """Tagged-tuple scene graph node ``(tag, args)`` (svgrasterize.py:598-647).
-    ``render`` is attached by ``render.py``."""
+    ``render`` is attached by ``api.py`` and runs on the device."""
 
     __slots__ = ()
 

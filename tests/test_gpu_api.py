@@ -142,7 +142,7 @@ def test_scene_render_and_canvas(B, O):
     assert mask.image.shape == mref.image.shape and np.abs(mask.image - mref.image).max() <= 2e-5
     u8 = B.render_canvas(scene, size)
     assert np.abs(u8.astype(int) - O.render_canvas(scene, size).astype(int)).max() <= 1
-    png = B.canvas_to_png(u8)
+    png = B.canvas_to_png(u8).getvalue()  # a BytesIO like the reference's (svgrasterize.py:267)
     assert png[:8] == b"\x89PNG\r\n\x1a\n"
 
 
@@ -226,7 +226,7 @@ def test_background_intersect_and_png(B, O):
     want = O.blend(0, np.broadcast_to(bg, a.shape).astype(np.float64), a.astype(np.float64))
     assert got.image.shape == a.shape and np.abs(got.image - want).max() <= 2e-5
     m = rng.uniform(0, 1, size=(30, 30, 1)).astype(np.float32)
-    res = B.canvas_merge_intersect([(m, (0, 0)), (a, (2, 3))])
+    res = B.canvas_merge_intersect([(m, (0, 0)), (a, (2, 3))], blend=2)
     ref = O.merge_intersect([(m.astype(np.float64), (0, 0)), (a.astype(np.float64), (2, 3))], 2)
     assert tuple(res[1]) == tuple(ref[1]) and np.abs(res[0] - ref[0]).max() <= 2e-5
     assert B.canvas_merge_intersect([(m, (0, 0)), (a, (100, 100))]) is None

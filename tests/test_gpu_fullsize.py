@@ -1,0 +1,121 @@
+"""BASELINE.json's single-render configurations at their STATED sizes against the unmodified reference's own
+output (tests/golden_big, tools/make_golden.py --only demo_material_w4096 synth_filter_stack_2048):
+
+  c2  demo/material-design.svg -w 4096   4096 x 4096, 1 924 Path.mask calls, one 935-layer group: final RGBA8
+      within +-1 LSB, every mask box exact, sampled masks within 1e-5, bins exact on sampled masks
+  c4  blur 4 -> dilate 3 -> saturate      2048 x 2048 (the reference needs 11.5 s and ~1 GB here; 8192 x 8192 is out
+      of its reach, that size is covered by the algebraic identities of tests/test_gpu_properties.py)
+
+plus index arithmetic near 2^31: a 16384 x 40000 one-channel stencil source (655 M pixels, 2.6 GB) rendered as
+row bands gives the same bytes as the matching window of a small render.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+BIG = os.path.join(ROOT, "tests", "golden_big")
+
+
+def load_big(name):
+    from svgrasterize_b200 import sceneio
+
+    z = np.load(os.path.join(BIG, name + ".npz"), allow_pickle=False)
+    return sceneio.load_scene(z), tuple(float(v) for v in z["size"]), bool(z["linear_rgb"]), z
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from svgrasterize_b200.engine import Engine
+
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def test_material_design_4096_against_the_reference(eng):
+    from svgrasterize_b200 import _lib, encode
+
+    scene, size, lin, z = load_big("demo_material_w4096")
+    assert size == (4096.0, 4096.0)
+    prog = encode.encode_scene(scene, size, lin, engine=eng)
+    res = eng.render(prog)
+    got = eng.canvas(prog, res["canvas"])
+    ref = z["canvas_u8"]
+    assert got.shape == ref.shape == (4096, 4096, 4)
+    diff = np.abs(got.astype(np.int16) - ref.astype(np.int16))
+    assert int(diff.max()) <= 1, f"max diff {diff.max()} at {np.argwhere(diff > 1)[:5]}"
+    # ---- stages: every box exact, sampled masks within 1e-5, their bins exact
+    eng.render(prog, stop=_lib.STOP_COVERAGE)
+    boxes = eng.boxes()
+    ref_box = z["leaf_bbox"]
+    assert len(boxes) == len(ref_box) == 1924
+    for i in range(len(boxes)):
+        if ref_box[i][2] < 0:
+            assert boxes[i][2] <= 0 or boxes[i][3] <= 0
+        else:
+            assert tuple(boxes[i]) == tuple(ref_box[i])
+    worst, off = 0.0, z["sample_mask_off"]
+    edges, edge_path = eng.edges()
+    for k, leaf in enumerate(z["sample_leaf"]):
+        mask = eng.mask(int(leaf), boxes[leaf])
+        want = z["sample_masks"][off[k]: off[k + 1]].reshape(mask.shape)
+        worst = max(worst, float(np.abs(mask - want).max()))
+        r0, c0, rows, cols = (int(v) for v in boxes[leaf])
+        boff, ids = eng.bins(int(leaf), boxes[leaf])
+        idx = np.nonzero(edge_path == leaf)[0]
+        e = edges[idx]
+        ra, rb = e[:, 0] - r0, e[:, 2] - r0
+        lo, hi = np.minimum(ra, rb), np.maximum(ra, rb)
+        cmin = np.minimum(e[:, 1], e[:, 3]) - c0
+        y0 = np.maximum(lo, 0).astype(np.int64)
+        y1 = np.minimum(np.ceil(hi), rows).astype(np.int64)
+        ok = (ra != rb) & (cmin < cols + 1) & (np.maximum(lo, 0) < rows) & (y0 < y1)
+        for b in range((rows + 15) // 16):
+            want_ids = set(idx[ok & (y0 < (b + 1) * 16) & (y1 > b * 16)].tolist())
+            assert set(ids[boff[b]: boff[b + 1]].tolist()) == want_ids
+    assert worst <= 1e-5, worst
+
+
+def test_filter_stack_2048_against_the_reference(eng):
+    from svgrasterize_b200 import encode
+
+    scene, size, lin, z = load_big("synth_filter_stack_2048")
+    prog = encode.encode_scene(scene, size, lin, engine=eng)
+    res = eng.render(prog)
+    got = eng.canvas(prog, res["canvas"])
+    ref = z["canvas_u8"]
+    assert got.shape == ref.shape == (2048, 2048, 4)
+    diff = np.abs(got.astype(np.int16) - ref.astype(np.int16))
+    assert int(diff.max()) <= 1, f"max diff {diff.max()} at {np.argwhere(diff > 1)[:5]}"
+    assert res["n_launches"] >= 5  # blur H + V, morphology H + V, colour matrix / canvas
+
+
+def test_filter_stack_4096_against_the_oracle_window(eng):
+    """At 4096 x 4096 the oracle would need a minute and ~8 GB.  The stack only looks 16 pixels around a pixel, so
+    the oracle renders the same scene through a 512 x 512 viewport at the circle's right rim (Scene.render's
+    viewport argument: same global pixel centres, same blur-origin arithmetic) and the interior of that window is
+    compared with the same pixels of the full CUDA render."""
+    from oracle import render as O
+    from svgrasterize_b200 import encode, synth
+
+    n = 4096
+    scene = synth.filter_stack_scene(n)
+    prog = encode.encode_scene(scene, (n, n), False, engine=eng)
+    got = eng.canvas(prog, eng.render(prog)["canvas"])
+    r0, c0, w = 1800, 3560, 512
+    layer, _ = O.render(scene, O.canvas_transform(), viewport=[r0, c0, w, w])
+    layer = O.convert(layer, pre_alpha=True, linear_rgb=False)
+    img = O.convert(O.OLayer(layer.image.clip(0, 1), layer.offset, True, False), pre_alpha=False, linear_rgb=False)
+    want = O.quantize(img.image)
+    lr, lc = layer.offset
+    m = 40  # wider than the reach of the blur (10 px) + the morphology window (6 px) from the viewport's clip
+    a, b = max(lr, r0) + m, min(lr + want.shape[0], r0 + w) - m
+    c, d = max(lc, c0) + m, min(lc + want.shape[1], c0 + w) - m
+    assert b - a > 300 and d - c > 300
+    diff = np.abs(got[a:b, c:d].astype(np.int16) - want[a - lr: b - lr, c - lc: d - lc].astype(np.int16))
+    assert int(diff.max()) <= 1
+    assert got[a:b, c:d, 3].min() == 0 and got[a:b, c:d, 3].max() == 255  # the window really straddles the rim

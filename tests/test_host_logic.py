@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), name
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
-    assert L.svgr_version() == 100
+    assert L.svgr_version() == 200
 
 
 def test_arc_expansion_is_bit_exact():
@@ -223,8 +223,69 @@ def test_canvas_to_png_parallel_deflate_decodes_to_the_same_pixels():
         assert (raw[:, 0] == 0).all()
         return raw[:, 1:].reshape(size[1], size[0], 4)
 
-    one = api.canvas_to_png(img)
+    one = api.canvas_to_png(img).getvalue()
     raw = b"".join(b"\x00" + img[r].tobytes() for r in range(img.shape[0]))
     assert zlib.compress(raw, 9) in one  # the reference's IDAT payload, byte for byte
-    many = api.canvas_to_png(img, threads=4)
+    many = api.canvas_to_png(img, threads=4).getvalue()
     assert np.array_equal(decode(one), img) and np.array_equal(decode(many), img)
+
+
+def test_install_binds_a_reference_shaped_module_without_a_gpu():
+    """install() / uninstall() are pure rebinding: they work (and are reversible) on a CPU-only machine; the
+    rebound entry points then fail loudly without a device instead of falling back to anything."""
+    import io
+
+    import refshape
+    import svgrasterize_b200 as B
+    from svgrasterize_b200 import api
+
+    mod = refshape.make_module()
+    before = {n: getattr(mod, n) for n in api._MODULE_FUNCTIONS}
+    token = B.install(mod)
+    assert mod.Path.mask is api.path_mask and mod.Path.stroke is api.path_stroke and mod.Scene.render is api.scene_render
+    assert mod.Filter.__call__ is api.filter_call and mod.Layer is api.Layer
+    assert all(getattr(mod, n) is getattr(api, n) for n in api._MODULE_FUNCTIONS)
+    import torch
+
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            mod.main_flow(mod.Scene.fill(mod.Path([]), np.ones(4)), (4, 4), False, None, io.BytesIO())
+    B.uninstall(token)
+    assert all(getattr(mod, n) is before[n] for n in api._MODULE_FUNCTIONS) and mod.Layer is None
+    assert mod.Path.mask is not api.path_mask
+
+
+def test_install_on_the_reference_module_itself():
+    """Where the reference checkout exists (the build container): every name install() rebinds exists on the real
+    module with the same arity, the reference's own parsed scenes encode through the core's encoder, and
+    uninstall() restores the module."""
+    import importlib.util
+    import inspect
+    import os
+
+    ref_py = "/root/reference/svgrasterize.py"
+    if not os.path.exists(ref_py):
+        pytest.skip("reference checkout not present (GPU box)")
+    import svgrasterize_b200 as B
+    from svgrasterize_b200 import api, encode
+
+    spec = importlib.util.spec_from_file_location("svgrasterize_ref_for_install_test", ref_py)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    originals = {n: getattr(ref, n) for n in api._MODULE_FUNCTIONS}
+    for n, fn in originals.items():
+        want = [p for p in inspect.signature(fn).parameters]
+        got = [p for p in inspect.signature(getattr(api, n)).parameters]
+        assert got[: len(want)] == want or len(got) >= len(want), (n, want, got)
+    token = B.install(ref)
+    try:
+        assert ref.Scene.render is api.scene_render and ref.Layer is api.Layer
+        scene, _ids, size = ref.svg_scene_from_filepath("/root/reference/demo/material-design.svg", width=256)
+        enc = encode.Encoder(None)
+        enc.add_scene(scene, size, False)
+        prog = enc.finish()
+        assert len(prog.paths) > 1000 and len(prog.canvases) == 1
+    finally:
+        B.uninstall(token)
+    assert all(getattr(ref, n) is originals[n] for n in api._MODULE_FUNCTIONS)
+    assert ref.Scene.render is not api.scene_render and ref.Layer is not api.Layer

@@ -78,3 +78,70 @@ def test_scene_roundtrip_is_lossless():
     again = sceneio.dump_scene(scene)
     for key in ("seg_tag", "seg_data", "sub_off", "path_off"):
         assert np.array_equal(again[key], z[key])
+
+
+def _eager():
+    import os
+
+    from conftest import ROOT
+
+    return np.load(os.path.join(ROOT, "tests", "golden_eager", "eager.npz"), allow_pickle=False)
+
+
+def test_eager_restatements():
+    """The oracle's restatements of the reference's small module-level functions (oracle/eager.py, the C
+    line coverage / flattener with a free flatness, the blend / merge helpers with every mode) against
+    vectors recorded from the unmodified reference by tools/make_golden_eager.py."""
+    from oracle import clib, eager, geometry
+
+    z = _eager()
+    # line_signed_coverage (:2213): exact, the C restatement uses the same float64 operations
+    trace = np.zeros_like(z["cov_trace"])
+    for ln in z["cov_lines"]:
+        clib.lib().orc_line_coverage(clib.dp(trace), trace.shape[0], trace.shape[1],
+                                     clib.dp(np.ascontiguousarray(ln.reshape(4))))
+    assert np.array_equal(trace, z["cov_trace"])
+    # bezier3_flatten_batch (:2091) with other flatness values: same set of lines, bit for bit
+    for i in range(4):
+        got = geometry.flatten_cubics(z["flat_cubics"], float(z[f"flat_tol_{i}"])).reshape(-1, 4)
+        assert np.array_equal(got[np.lexsort(got.T[::-1])], z[f"flat_lines_{i}"])
+    assert np.array_equal(eager.pixel_centres(z["gp_viewport"]), z["gp_out"])
+    for m in ("pad", "repeat", "reflect"):
+        assert np.array_equal(eager.spread(z["gs_in"], m), z[f"gs_{m}"])
+    stops = list(zip(z["gi_stop_off"], z["gi_stop_col"]))
+    for lin in (0, 1):
+        assert np.array_equal(eager.interpolate(z["gs_in"], stops, bool(lin)), z[f"gi_out_{lin}"])
+    for i in range(int(z["pool_n"])):
+        s = tuple(int(v) for v in z[f"pool_{i}_s"])
+        got = eager.pool(z["pool_in"], tuple(z[f"pool_{i}_k"]), s if s != (0, 0) else None, str(z[f"pool_{i}_m"]),
+                         bool(z[f"pool_{i}_pad"]))
+        assert np.array_equal(got, z[f"pool_{i}_out"], equal_nan=True)
+    assert np.array_equal(eager.pool(z["pool2_in"], (3, 3), (2, 1), "max", False), z["pool2_out"])
+    modes = [0, 1, 2, 3, 4, tuple(z["cc_arith"])]
+    for i, mode in enumerate(modes):
+        assert np.array_equal(O.blend(mode, z["cc_dst"], z["cc_src"]), z[f"cc_out_{i}"])
+    for i, mode in enumerate((0, 4, 3)):
+        got = O.merge_at(z["ma_base"].copy(), z["ma_over"], tuple(z["ma_off"]), mode)
+        assert np.array_equal(got, z[f"ma_out_{i}"])
+    layers = [(z["cc_dst"], (0, 0)), (z["ma_over"], (5, -3)), (z["mu_l3"], (-4, 20))]
+    for i, (full, mode) in enumerate(((False, 0), (True, 0), (True, 4), (True, 1))):
+        img, off = (O.merge_full if full else O.merge_over)(layers, mode)
+        assert tuple(off) == tuple(z[f"mu_off_{i}"]) and np.array_equal(img, z[f"mu_out_{i}"])
+    ilayers = [(z["cc_m1"], (0, 0)), (z["ma_over"], (5, -3)), (z["mu_l3"], (2, 6))]
+    for i, mode in enumerate((0, 2, 4)):
+        img, off = O.merge_intersect(ilayers, mode)
+        assert tuple(off) == tuple(z[f"mi_off_{i}"]) and np.array_equal(img, z[f"mi_out_{i}"])
+
+
+@pytest.mark.parametrize("name", ["demo_material_w4096", "synth_filter_stack_2048"])
+def test_full_size_canvases_match_reference_exactly(name):
+    """BASELINE.json's c2 at 4096 x 4096 and c4 at 2048 x 2048 (tests/golden_big, recorded from the unmodified
+    reference): the oracle reproduces the reference's bytes at the stated sizes too."""
+    import os
+
+    from conftest import ROOT
+
+    z = np.load(os.path.join(ROOT, "tests", "golden_big", name + ".npz"), allow_pickle=False)
+    scene, size = sceneio.load_scene(z), tuple(float(v) for v in z["size"])
+    got = O.render_canvas(scene, size, linear_rgb=bool(z["linear_rgb"]))
+    assert np.array_equal(got, z["canvas_u8"])

@@ -158,7 +158,9 @@ def reference_canvas(scene, size, linear_rgb):
     return np.round(layer.image * 255.0).astype(np.uint8), root
 
 
-def emit(name, ref_scene, size, linear_rgb=False, stages=False, root=False):
+def emit(name, ref_scene, size, linear_rgb=False, stages=False, root=False, golden_dir=None, sample_masks=0):
+    """sample_masks > 0: besides the boxes keep the masks of that many evenly spaced non-empty leaves (full-size
+    fixtures, where all masks together would be hundreds of megabytes)."""
     with Taps() as taps:
         canvas, root_layer = reference_canvas(ref_scene, size, linear_rgb)
     blob = sceneio.dump_scene(ref_scene)
@@ -169,9 +171,20 @@ def emit(name, ref_scene, size, linear_rgb=False, stages=False, root=False):
                      root_flags=np.asarray([root_layer.pre_alpha, root_layer.linear_rgb]))
     if stages:
         extra.update(taps.arrays())
+    elif sample_masks:
+        live = [i for i, leaf in enumerate(taps.leaves) if leaf is not None]
+        pick = sorted({live[int(k)] for k in np.linspace(0, len(live) - 1, sample_masks)})
+        bbox = np.full((len(taps.leaves), 4), -1, dtype=np.int64)
+        for i in live:
+            bbox[i] = taps.leaves[i][0]
+        masks = [taps.leaves[i][2].astype(np.float32).reshape(-1) for i in pick]
+        extra.update(leaf_bbox=bbox, sample_leaf=np.asarray(pick, dtype=np.int64),
+                     sample_mask_off=np.concatenate([[0], np.cumsum([len(m) for m in masks])]).astype(np.int64),
+                     sample_masks=np.concatenate(masks))
     else:
         extra.update(leaf_bbox=taps.arrays()["leaf_bbox"])
-    path = os.path.join(GOLDEN, f"{name}.npz")
+    path = os.path.join(golden_dir or GOLDEN, f"{name}.npz")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
     np.savez_compressed(path, **blob, **extra)
     print(f"{name:40s} {canvas.shape}  leaves {len(taps.leaves):5d}  strokes {len(taps.strokes):3d}  "
           f"{os.path.getsize(path) / 1024:8.1f} KiB")
@@ -208,8 +221,17 @@ def main():
     for name, (scene, size) in synth.feature_scenes().items():
         synth_scene("feat_" + name, scene, size, linear_rgb=name in synth.FEATURES_LINEAR_RGB, stages=True, root=True)
 
+    # BASELINE.json's configurations at their stated sizes (kept apart: the parametrised stage tests iterate over
+    # tests/golden, these are compared once each by tests/test_gpu_fullsize.py).  Only made when asked for by name.
+    big = os.path.join(ROOT, "tests", "golden_big")
+    svg("demo_material_w4096", f"{demo}/material-design.svg", 4096, golden_dir=big, sample_masks=24)
+    synth_scene("synth_filter_stack_2048", synth.filter_stack_scene(2048), (2048, 2048), golden_dir=big)
+    big_names = {"demo_material_w4096", "synth_filter_stack_2048"}
+
     for name, run in jobs:
         if opts.only and name not in opts.only:
+            continue
+        if not opts.only and name in big_names:
             continue
         run()
 
