@@ -154,30 +154,36 @@ def build_batch(icons, seed0, engine):
     return encode.Program.concat(progs), progs
 
 
-def run_e2e(progs, out_host_np, device, steps, warmup, workers, chunks):
-    """End to end through the public call (Engine.render -> svgr_render) with host buffers: the batch is
-    cut into `chunks` programs that `workers` host threads (one Engine = one context + stream each) render
-    back to back, so that one chunk's device->host copy overlaps the next chunk's compute.  Returns wall
-    seconds per step (torch.cuda.synchronize on both sides)."""
+def run_e2e(batches, out_host_np, device, steps, warmup, workers, chunks):
+    """End to end through the public call (Engine.render -> svgr_render) with host buffers: step k renders batch
+    k (mod the number of distinct batches), cut into `chunks` programs that `workers` host threads (one Engine =
+    one context + stream each) render back to back, so that one chunk's device->host copy overlaps the next
+    chunk's compute.  Returns wall seconds per step (torch.cuda.synchronize on both sides)."""
     import torch
 
     from svgrasterize_b200 import encode
     from svgrasterize_b200.engine import Engine
 
-    n = len(progs)
-    bounds = [n * c // chunks for c in range(chunks + 1)]
-    parts, pins, offs = [], [], [0]
-    for c in range(chunks):
-        part = encode.Program.concat(progs[bounds[c]: bounds[c + 1]])
-        pins.append(pin_program(part))
-        parts.append(part)
-        offs.append(offs[-1] + part.canvas_bytes)
+    all_parts, pins = [], []
+    for progs in batches:
+        n = len(progs)
+        bounds = [n * c // chunks for c in range(chunks + 1)]
+        parts, offs = [], [0]
+        for c in range(chunks):
+            part = encode.Program.concat(progs[bounds[c]: bounds[c + 1]])
+            pins.append(pin_program(part))
+            parts.append(part)
+            offs.append(offs[-1] + part.canvas_bytes)
+        all_parts.append((parts, offs))
     engines = [Engine(device) for _ in range(workers)]
     errors = []
+    step_no = [0] * workers
 
     def work(w, reps):
         try:
             for _ in range(reps):
+                parts, offs = all_parts[step_no[w] % len(all_parts)]
+                step_no[w] += 1
                 for c in range(w, chunks, workers):
                     engines[w].render(parts[c], out=out_host_np[offs[c]: offs[c + 1]])
         except Exception as exc:  # noqa: BLE001
@@ -200,9 +206,99 @@ def run_e2e(progs, out_host_np, device, steps, warmup, workers, chunks):
         e.close()
     if errors:
         raise errors[0]
-    h2d = sum(p.h2d_bytes() for p in parts)
+    h2d = sum(p.h2d_bytes() for p in all_parts[0][0])
     del pins
     return dt / steps, h2d
+
+
+def time_other_configs(device, peak, with_cpu):
+    """BASELINE.json's single-render configurations at their stated sizes, timed like the icon batch (resident
+    program, CUDA events from svgr_render's stage timing, median of 5) with their own SURVEY 8(d) rooflines:
+      c2  demo/material-design.svg -w 4096 (scene + reference bytes from tests/golden_big): coverage 4 B per mask
+          pixel + 36 B per binned edge; compose 36 B per layer pixel + 20 B per canvas pixel
+      c4  feGaussianBlur 4 -> feMorphology dilate 3 -> feColorMatrix saturate on 8192 x 8192: 64 B/px per separable
+          stencil (two passes of 16 B in + 16 B out), 32 B/px colour matrix, 36 B/px fill, 20 B/px quantise
+    The CPU figure beside them is the oracle (1 core, the reference is single-threaded) on c2 at 4096 and on c4 at
+    2048 x 2048 scaled by 16 (the reference cannot hold 8192 x 8192 in float64)."""
+    import torch
+
+    from svgrasterize_b200 import encode, sceneio, synth
+    from svgrasterize_b200.engine import Engine
+
+    out = {}
+    eng = Engine(device)
+
+    def timed(prog, reps=5):
+        buf = torch.empty(max(prog.canvas_bytes, 4), dtype=torch.uint8, device="cuda")
+        eng.render(prog, out=buf)
+        eng.render_resident(buf)
+        rows = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            st = eng.render_resident(buf, timing=False, stream=torch.cuda.current_stream())
+            e1.record()
+            torch.cuda.synchronize()
+            rows.append((e0.elapsed_time(e1), st))
+        rows.sort(key=lambda r: r[0])
+        ms = rows[len(rows) // 2][0]
+        st = eng.render_resident(buf, timing=True, stream=torch.cuda.current_stream())
+        return ms, st, buf
+
+    def roof(st, ms_key, bytes_key):
+        ms = st[ms_key]
+        gbs = st[bytes_key] / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        return {"ms": ms, "algorithmic_bytes": int(st[bytes_key]), "achieved": gbs, "peak": peak, "unit": "GB/s",
+                "frac": gbs / peak}
+
+    # ---- c2
+    path = os.path.join(ROOT, "tests", "golden_big", "demo_material_w4096.npz")
+    if os.path.exists(path):
+        z = np.load(path, allow_pickle=False)
+        scene, size = sceneio.load_scene(z), tuple(float(v) for v in z["size"])
+        t0 = time.perf_counter()
+        prog = encode.encode_scene(scene, size, bool(z["linear_rgb"]), engine=eng)
+        t_enc = time.perf_counter() - t0
+        ms, st, buf = timed(prog)
+        got = buf.cpu().numpy()[: prog.canvas_bytes].reshape(z["canvas_u8"].shape)
+        out["c2"] = {"workload": "demo/material-design.svg -w 4096: 4096x4096 canvas, 1924 masks, one 935-layer group",
+                     "ms_per_render": ms, "mpx_s": size[0] * size[1] / ms / 1e3, "masks": int(len(prog.paths)),
+                     "edges": int(st["n_edges"]), "mask_px": int(st["mask_pixels"]), "host_encode_s": t_enc,
+                     "max_lsb_vs_reference_bytes": int(np.abs(got.astype(np.int16) - z["canvas_u8"].astype(np.int16)).max()),
+                     "stage_ms": {k[3:]: v for k, v in st.items() if k.startswith("ms_") and v > 0.0005},
+                     "roofline": {"coverage_kernel": roof(st, "ms_coverage", "coverage_bytes"),
+                                  "compose_kernel": roof(st, "ms_compose_busy", "compose_bytes_8d")}}
+        del buf
+    # ---- c4
+    n = 8192
+    t0 = time.perf_counter()
+    prog = encode.encode_scene(synth.filter_stack_scene(n), (n, n), False, engine=eng)
+    t_enc = time.perf_counter() - t0
+    ms, st, buf = timed(prog, reps=3)
+    out["c4"] = {"workload": f"filter stack blur(4) -> dilate(3) -> saturate(0.5) on a gradient-filled circle, {n}x{n} canvas",
+                 "ms_per_render": ms, "mpx_s": n * n / ms / 1e3, "host_encode_s": t_enc,
+                 "layer_GiB": st["layer_floats"] * 4 / 2**30,
+                 "stage_ms": {k[3:]: v for k, v in st.items() if k.startswith("ms_") and v > 0.0005},
+                 "roofline": {"stencil_and_compose_kernels": roof(st, "ms_compose_busy", "compose_bytes_8d")}}
+    del buf
+    eng.close()
+    if with_cpu:
+        from oracle import render as O
+
+        if "c2" in out:
+            t0 = time.perf_counter()
+            O.render_canvas(scene, size, bool(z["linear_rgb"]))
+            dt = time.perf_counter() - t0
+            out["c2"]["cpu_baseline"] = {"seconds": dt, "mpx_s": size[0] * size[1] / dt / 1e6, "cores": 1, "kind": "port",
+                                         "sample": "the same render, oracle/ on one core (the reference is single-threaded)"}
+        t0 = time.perf_counter()
+        O.render_canvas(synth.filter_stack_scene(2048), (2048, 2048))
+        dt = time.perf_counter() - t0
+        out["c4"]["cpu_baseline"] = {"seconds_scaled": dt * 16, "mpx_s": 2048 * 2048 / dt / 1e6, "cores": 1, "kind": "port",
+                                     "sample": f"2048x2048 in {dt:.1f} s on one core, x16 for 8192x8192 (float64 temporaries "
+                                               "of the full size do not fit)"}
+    return out
 
 
 def run_gpu(opts):
@@ -220,14 +316,25 @@ def run_gpu(opts):
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
-    eng = Engine(local)
     stream = torch.cuda.current_stream()
 
-    t0 = time.perf_counter()
-    prog, icon_progs = build_batch(opts.icons, opts.seed0 + rank * opts.icons, eng)
-    t_encode = time.perf_counter() - t0
-    pins = pin_program(prog)
+    # ---- distinct seeds per step: step k of every leg renders batch k mod n_batches, batch b of rank r holds the
+    # icons [(b * world + r) * icons, ... + icons).  One Engine (context) per batch keeps every program resident;
+    # the number of distinct batches is bounded by their arenas (~7 GiB per 2048 icons).
+    n_batches = max(1, min(opts.batches, opts.steps))
+    engines, progs, batches, pins = [], [], [], []
+    t_encode = 0.0
+    for b in range(n_batches):
+        e = Engine(local)
+        t0 = time.perf_counter()
+        prog_b, icon_progs_b = build_batch(opts.icons, opts.seed0 + (b * world + rank) * opts.icons, e)
+        t_encode += time.perf_counter() - t0
+        pins.append(pin_program(prog_b))
+        engines.append(e), progs.append(prog_b), batches.append(icon_progs_b)
+    t_encode /= n_batches
+    eng, prog = engines[0], progs[0]
     n_px = opts.icons * ICON_PX * ICON_PX
+    assert all(p.canvas_bytes == prog.canvas_bytes for p in progs)
     out_dev = torch.empty(prog.canvas_bytes, dtype=torch.uint8, device="cuda")
     out_host = torch.empty(prog.canvas_bytes, dtype=torch.uint8, pin_memory=True)
     out_host_np = out_host.numpy()
@@ -244,10 +351,11 @@ def run_gpu(opts):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- first render: uploads the program, sizes every buffer
-    eng.render(prog, out=out_dev, stream=stream)
-    for _ in range(opts.warmup):
-        eng.render_resident(out_dev, stream=stream)
+    # ---- first render of every batch: uploads its program, sizes every buffer; then W warm-up steps
+    for e, p in zip(engines, progs):
+        e.render(p, out=out_dev, stream=stream)
+    for k in range(max(opts.warmup, n_batches)):
+        engines[k % n_batches].render_resident(out_dev, stream=stream)
 
     # ---- value: resident program, device timing
     sampler = ClockSampler(local)
@@ -256,8 +364,8 @@ def run_gpu(opts):
     sampler.start()  # clocks are sampled during the timed region only
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    for _ in range(opts.steps):
-        eng.render_resident(out_dev, stream=stream)
+    for k in range(opts.steps):
+        engines[k % n_batches].render_resident(out_dev, stream=stream)
     e1.record(stream)
     torch.cuda.synchronize()
     sampler.stop_flag = True
@@ -276,19 +384,25 @@ def run_gpu(opts):
 
     # ---- the same steps once more with per-stage CUDA events (these add ~2 % of synchronisation, which is why
     # they are not part of the timed region above): stage times and the roofline of the dominant kernel
-    for _ in range(opts.steps):
-        st = eng.render_resident(out_dev, timing=True, stream=stream)
-        for k, v in st.items():
-            if k.startswith("ms_") or k.startswith("host_"):
-                acc[k] = acc.get(k, 0.0) + v
+    counts = {}
+    for k in range(opts.steps):
+        st = engines[k % n_batches].render_resident(out_dev, timing=True, stream=stream)
+        for key, v in st.items():
+            if key.startswith("ms_") or key.startswith("host_"):
+                acc[key] = acc.get(key, 0.0) + v
+            elif key.endswith("_bytes") or key.endswith("_bytes_8d") or key in ("mask_pixels", "n_edges", "n_kernels"):
+                counts[key] = counts.get(key, 0) + v
     torch.cuda.synchronize()
+    st = dict(st, **{key: v / opts.steps for key, v in counts.items()})  # per-step means over the distinct batches
 
     # ---- e2e: svgr_render with host buffers (H2D of the program, D2H of the RGBA8 result inside)
     barrier()
     # every host thread of the e2e leg needs a core to itself (it plans on the host between its launches)
     workers = max(1, min(opts.e2e_workers, (os.cpu_count() or 1) // max(world, 1) - 1))
     chunks = max(workers, opts.e2e_chunks if opts.e2e_chunks % workers == 0 else workers)
-    sec_e2e, h2d_bytes = run_e2e(icon_progs, out_host_np, local, opts.steps, opts.warmup, workers, chunks)
+    for e in engines[1:]:
+        e.close()  # their arenas are not needed any more
+    sec_e2e, h2d_bytes = run_e2e(batches, out_host_np, local, opts.steps, opts.warmup, workers, chunks)
     barrier()
     ms_e2e = max_over_ranks(sec_e2e * 1e3)
     e2e_value = world * n_px / (ms_e2e * 1e-3) / 1e6
@@ -355,8 +469,12 @@ def run_gpu(opts):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": workload_name(opts.icons), "icons_per_gpu_per_step": opts.icons,
+                   "distinct_batches": n_batches,
+                   "seeds": f"step k renders batch k mod {n_batches}; batch b of rank r = icons "
+                            f"[(b * {world} + r) * {opts.icons}, +{opts.icons}) -- {n_batches * world * opts.icons} distinct "
+                            "icons per run, in all three legs (value, stage timing, e2e)",
                    "canvas_px_per_step_per_gpu": n_px, "mask_px_per_step_per_gpu": st["mask_pixels"],
-                   "paths_per_step_per_gpu": int(len(prog.paths)), "edges_per_step_per_gpu": st["n_edges"],
+                   "paths_per_step_per_gpu": int(len(prog.paths)), "edges_per_step_per_gpu": int(st["n_edges"]),
                    "l2": "inputs larger than L2 (coverage + layer arenas of "
                          f"{(st['cov_floats'] + st['layer_floats']) * 4 / 2**30:.1f} GiB per step)",
                    "parallelism": f"whole SVGs sharded over {world} GPU(s), no collective",
@@ -375,6 +493,9 @@ def run_gpu(opts):
         "roofline_other": {k: v for k, v in kernels.items() if k != dominant},
         "host_encode_s_per_batch": t_encode,
     }
+    if world == 1 and not opts.no_configs:
+        eng.close()
+        line["configs"] = time_other_configs(local, peak, not opts.no_cpu)
     if world == 1 and not opts.no_cpu:
         cores = min(os.cpu_count() or 1, 32)
         n = max(cores * 48, 512)
@@ -395,6 +516,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--icons", type=int, default=2048, help="icons per GPU per step")
     ap.add_argument("--seed0", type=int, default=0, help="first icon seed (diagnostics: render another rank's batch)")
+    ap.add_argument("--batches", type=int, default=8, help="distinct icon batches kept resident (steps cycle through them)")
+    ap.add_argument("--no-configs", action="store_true", help="skip timing BASELINE.json's configs c2 / c4")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--e2e-workers", type=int, default=3, help="host threads (contexts) of the e2e leg")

@@ -155,7 +155,7 @@ def test_canvas_helpers(B, O):
     ref = O.merge_at(base.astype(np.float64).copy(), over.astype(np.float64), (15, -4))
     got = B.canvas_merge_at(base.copy(), over, (15, -4))
     assert np.abs(got - ref).max() <= 2e-5
-    pooled = B.pooling(base, (3, 2), method="max")
+    pooled = B.pooling(base, (3, 2), stride=(1, 1), method="max")
     want = O.morphology(O.OLayer(base.astype(np.float64), (0, 0), True, True), 3, 2, "max").image
     assert np.abs(pooled - want).max() <= 1e-6
     img, off = B.canvas_merge_union([(base, (0, 0)), (over, (5, 5))], full=False)
