@@ -126,7 +126,7 @@ struct Val {
 struct PlannedOp {
     OpRec op;
     int level;
-    int cls;  // 0 compose, 1 stencil, 2 conv2d, 3 canvas
+    int cls;  // 0 compose, 1 stencil, 2 conv2d, 3 canvas, 4 / 5 TMA-fed stencil along rows / down columns
 };
 
 struct Launch {
@@ -136,6 +136,8 @@ struct Launch {
     long long list_slots;  // compose launches: TileEntry slots (sum over ops of tiles x sources)
     long long head_off = 0, list_off = 0;  // where this launch's tile heads / entries start in the chunk's buffers
     bool simple = true;  // compose launches: only OVER folds without conversions, patterns or special outputs
+    int k_max = 0;       // TMA stencil launches: longest kernel of the launch
+    long long tmap_off = 0;  // TMA stencil launches: first tensor map of the launch in the chunk's map table
 };
 
 struct StatusBlock {  // device -> host after flatten
@@ -173,6 +175,9 @@ struct svgr_ctx {
     long long canvas_bytes = 0;
     double flatness = 0.0;
     DevBuf d_eager[3];  // scratch of the eager element-wise entry points
+    DevBuf d_tmaps;     // tensor maps of the TMA-fed stencil launches of the render in flight (128 B each)
+    PinBuf pin_tmaps;
+    int n_filter_nodes = 0;  // blur / morphology nodes of the loaded program (bounds the map table)
     DevBuf d_seg_tag, d_seg_data, d_seg_path, d_paths, d_strokes, d_ssub_off, d_ssub_job, d_stag, d_sdata, d_sseg_job;
     DevBuf d_sitems;            // stroke assembly work items: (sub-path, first segment, end segment), <= 256 segments each
     std::vector<int> h_sitems;
@@ -428,6 +433,25 @@ struct Planner {
 
     static int py_int(double v) { return (int)v; }  // Python int(): truncation toward zero
 
+    // A separable stencil pass whose source is a materialised RGBA layer runs on the TMA-fed kernels
+    // (k_stencil_tma.cu): the layer is a tensor, tile + halo a zero-filled box of it.  Anything else (coverage x
+    // paint, one-channel layers) is read element by element through fetch_src by the generic kernel.
+    bool tma_ok = getenv("SVGR_NO_TMA") == nullptr;
+    int stencil_cls(const Val &src, bool horiz) const { return (tma_ok && src.kind == SRC_L4) ? (horiz ? 4 : 5) : 1; }
+
+    // The generic stencil kernel stages a tile plus the whole kernel length in shared memory, which bounds the
+    // length; the TMA-fed kernels do not have that bound but need an RGBA layer.  A long kernel over anything else
+    // (coverage x paint, a one-channel layer) therefore gets its source written out as RGBA first.
+    Val stencil_source(const Val &v, int k_rows, int k_cols, int want_pre, int want_lin)
+    {
+        const bool fits = (size_t)SVGR_STH_TR * (SVGR_STH_TC + k_cols - 1) * 16 <= SVGR_MAX_DYN_SMEM &&
+                          (size_t)(SVGR_STV_TR + k_rows - 1) * SVGR_STV_TC * 16 <= SVGR_MAX_DYN_SMEM;
+        if (v.kind == SRC_L4 || v.kind == VAL_EMPTY || (fits && !getenv("SVGR_FORCE_RGBA_STENCIL")) || !tma_ok)
+            return v;
+        // written out in the flags the stencil wants (a one-channel value is only relabelled, like Layer.convert)
+        return unary(v, SRC_L4, want_pre, want_lin, want_pre, want_lin, POST_NONE, 1.0f);
+    }
+
     bool node(int i, Val &out)
     {
         const svgr_node &n = ctx->h_nodes[i];
@@ -614,24 +638,25 @@ struct Planner {
             break;
         }
         case SVGR_N_BLUR: {
-            const Val v = plain(child(0));
-            if (v.kind == VAL_EMPTY)
+            const Val v_in = plain(child(0));
+            if (v_in.kind == VAL_EMPTY)
                 break;
             if (n.a < 0 || n.a >= (int)ctx->h_kernels.size()) {
                 err = "blur: bad kernel index";
                 return false;
             }
             const svgr_kernel &kn = ctx->h_kernels[n.a];
+            const Val v = kn.separable ? stencil_source(v_in, kn.rows, kn.cols, 0, 1) : v_in;
             // Layer.convolve (svgrasterize.py:106-115): full convolution on straight-alpha linear RGBA
             int orows = v.rows + kn.rows - 1, ocols = v.cols + kn.cols - 1;
             int r0 = py_int((double)v.r0 - kn.rows / 2.0), c0 = py_int((double)v.c0 - kn.cols / 2.0);
             if (kn.separable) {
                 Val tmp = alloc(SRC_L4, v.r0, c0, v.rows, ocols, 0, 1, v.level + 1);
-                emit(1, OP_STENCIL_H, tmp, {src_of(v, 0, 1)}, 0, 0, 1.0f, tmp.level, nullptr, kn.weight_off + kn.rows,
-                     kn.cols, 0, STENCIL_CONV);
+                emit(stencil_cls(v, true), OP_STENCIL_H, tmp, {src_of(v, 0, 1)}, 0, 0, 1.0f, tmp.level, nullptr,
+                     kn.weight_off + kn.rows, kn.cols, 0, STENCIL_CONV);
                 out = alloc(SRC_L4, r0, c0, orows, ocols, 0, 1, tmp.level + 1);
-                emit(1, OP_STENCIL_V, out, {src_of(tmp, 0, 1)}, 0, 0, 1.0f, out.level, nullptr, kn.weight_off, kn.rows, 0,
-                     STENCIL_CONV);
+                emit(stencil_cls(tmp, false), OP_STENCIL_V, out, {src_of(tmp, 0, 1)}, 0, 0, 1.0f, out.level, nullptr,
+                     kn.weight_off, kn.rows, 0, STENCIL_CONV);
             } else {
                 out = alloc(SRC_L4, r0, c0, orows, ocols, 0, 1, v.level + 1);
                 emit(2, OP_CONV2D, out, {src_of(v, 0, 1)}, 0, 0, 1.0f, out.level, nullptr, kn.weight_off, kn.rows, kn.cols);
@@ -639,10 +664,11 @@ struct Planner {
             break;
         }
         case SVGR_N_MORPH: {
-            const Val v = plain(child(0));
-            if (v.kind == VAL_EMPTY)
+            const Val v_in = plain(child(0));
+            if (v_in.kind == VAL_EMPTY)
                 break;
             int k0 = n.a, k1 = n.b;
+            const Val v = stencil_source(v_in, std::max(k0, 1), std::max(k1, 1), 1, 1);
             int st = n.c ? STENCIL_MAX : STENCIL_MIN;
             int orows = v.rows - k0 + 1, ocols = v.cols - k1 + 1;
             if (k0 < 1 || k1 < 1) {
@@ -653,9 +679,10 @@ struct Planner {
                 break;
             // Layer.morphology (svgrasterize.py:120-127): premultiplied linear, top-left anchored, offset unchanged
             Val tmp = alloc(SRC_L4, v.r0, v.c0, v.rows, ocols, 1, 1, v.level + 1);
-            emit(1, OP_STENCIL_H, tmp, {src_of(v, 1, 1)}, 0, 0, 1.0f, tmp.level, nullptr, 0, k1, 0, st);
+            emit(stencil_cls(v, true), OP_STENCIL_H, tmp, {src_of(v, 1, 1)}, 0, 0, 1.0f, tmp.level, nullptr, 0, k1, 0, st);
             out = alloc(SRC_L4, v.r0, v.c0, orows, ocols, 1, 1, tmp.level + 1);
-            emit(1, OP_STENCIL_V, out, {src_of(tmp, 1, 1)}, 0, 0, 1.0f, out.level, nullptr, 0, k0, 0, st);
+            emit(stencil_cls(tmp, false), OP_STENCIL_V, out, {src_of(tmp, 1, 1)}, 0, 0, 1.0f, out.level, nullptr, 0, k0, 0,
+                 st);
             break;
         }
         case SVGR_N_CMATRIX: {
@@ -846,6 +873,7 @@ struct Planner {
         std::vector<int> &uses = c->node_uses;
         uses.assign(c->n_node, 0);
         std::vector<int> cuts;  // indices right after a canvas node: candidate scene boundaries
+        int n_filter = 0;
         for (int i = 0; i < c->n_node; i++) {
             const svgr_node &n = c->h_nodes[i];
             for (int k = 0; k < n.child_cnt; k++) {
@@ -859,7 +887,10 @@ struct Planner {
                 uses[i]++;  // read back by the caller
             if (n.tag == SVGR_N_CANVAS)
                 cuts.push_back(i + 1);
+            if (n.tag == SVGR_N_BLUR || n.tag == SVGR_N_MORPH)
+                n_filter++;
         }
+        c->n_filter_nodes = n_filter;
         // chunks of at least 4096 nodes, at most 8 of them, cut where no reference crosses
         std::vector<int> &bounds = c->chunk_bounds;
         bounds.assign(1, 0);
@@ -932,14 +963,14 @@ struct Planner {
             for (size_t q = op_begin; q < c->ops.size(); q++)
                 max_level = std::max(max_level, c->ops[q].level);
             if (max_level < (1 << 20)) {  // counting sort: a chunk has a handful of levels and many ops
-                std::vector<int> start((size_t)(max_level + 1) * 4 + 1, 0);
+                std::vector<int> start((size_t)(max_level + 1) * 8 + 1, 0);
                 for (size_t q = op_begin; q < c->ops.size(); q++)
-                    start[(size_t)c->ops[q].level * 4 + c->ops[q].cls + 1]++;
+                    start[(size_t)c->ops[q].level * 8 + c->ops[q].cls + 1]++;
                 for (size_t q = 1; q < start.size(); q++)
                     start[q] += start[q - 1];
                 sorted_ops.resize(n_new);
                 for (size_t q = op_begin; q < c->ops.size(); q++)
-                    sorted_ops[start[(size_t)c->ops[q].level * 4 + c->ops[q].cls]++] = c->ops[q];
+                    sorted_ops[start[(size_t)c->ops[q].level * 8 + c->ops[q].cls]++] = c->ops[q];
                 std::copy(sorted_ops.begin(), sorted_ops.end(), c->ops.begin() + op_begin);
             } else {
                 std::stable_sort(c->ops.begin() + op_begin, c->ops.end(), [](const PlannedOp &a, const PlannedOp &b) {
@@ -958,7 +989,13 @@ struct Planner {
                 OpRec &o = c->ops[j].op;
                 int tr = SVGR_CMP_TR, tc = SVGR_CMP_TC;
                 size_t smem = 0;
-                if (o.kind == OP_STENCIL_H) {
+                if (c->ops[j].cls == 4) {
+                    tr = SVGR_TMA_H_TR, tc = SVGR_TMA_H_TC;
+                    L.k_max = std::max(L.k_max, o.k0);
+                } else if (c->ops[j].cls == 5) {
+                    tr = SVGR_TMA_V_TR, tc = SVGR_TMA_V_TC;
+                    L.k_max = std::max(L.k_max, o.k0);
+                } else if (o.kind == OP_STENCIL_H) {
                     tr = SVGR_STH_TR, tc = SVGR_STH_TC;
                     smem = (size_t)SVGR_STH_TR * (SVGR_STH_TC + o.k0 - 1) * 16;
                 } else if (o.kind == OP_STENCIL_V) {
@@ -966,7 +1003,11 @@ struct Planner {
                     smem = (size_t)(SVGR_STV_TR + o.k0 - 1) * SVGR_STV_TC * 16;
                 } else if (o.kind == OP_CONV2D) {
                     tr = SVGR_C2D_TR, tc = SVGR_C2D_TC;
-                    smem = (size_t)(SVGR_C2D_TR + o.k0 - 1) * (SVGR_C2D_TC + o.k1 - 1) * 16;
+                    // the kernel walks the kernel rows in groups that fit the staging buffer (at least one row)
+                    const size_t row_bytes = (size_t)(SVGR_C2D_TC + o.k1 - 1) * 16;
+                    smem = (size_t)(SVGR_C2D_TR + o.k0 - 1) * row_bytes;
+                    if (smem > SVGR_MAX_DYN_SMEM)
+                        smem = std::max<size_t>(SVGR_C2D_TR, SVGR_MAX_DYN_SMEM / row_bytes) * row_bytes;
                 }
                 o.ntile_c = std::max(1, ceil_div(o.cols, tc));
                 o.tile_base = (int)tiles;
@@ -1029,7 +1070,10 @@ struct Planner {
             }
             L.list_slots = slots;
             if (L.smem > SVGR_MAX_DYN_SMEM) {
+                // only the generic kernels stage a whole kernel length at once (sources that are not plain RGBA
+                // layers); the TMA-fed kernels cut long kernels into tap groups
                 err = "stencil too long for shared-memory staging";
+                err_code = SVGR_E_UNSUPPORTED;
                 return false;
             }
             L.op_count = (int)(j - i), L.n_tiles = (int)tiles;
@@ -1465,6 +1509,13 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
         CK(ctx->d_focal_flags.ensure((size_t)std::max(ctx->n_focal, 1) * 4));
         if (ctx->n_focal > 0)
             CK(cudaMemsetAsync(ctx->d_focal_flags.p, 0, (size_t)ctx->n_focal * 4, s));
+        // tensor maps: two passes per filter node, a source and a destination map per pass
+        const size_t tmap_cap = (size_t)ctx->n_filter_nodes * 4 + 4;
+        if (ctx->n_filter_nodes > 0) {
+            CK(ctx->d_tmaps.ensure(tmap_cap * 128 + 128));
+            CK(ctx->pin_tmaps.ensure(tmap_cap * 128 + 128));
+        }
+        size_t tmap_top = 0;
         char *pin_ops = (char *)ctx->pin_plan.p;
         char *pin_srcs = pin_ops + ops_cap * sizeof(OpRec);
         char *pin_focal = pin_srcs + srcs_cap * sizeof(SrcRec);
@@ -1544,6 +1595,41 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
                 CK(cudaMemcpyAsync(ctx->d_focal_jobs.as<FocalJob>() + up_focal, pin_focal + up_focal * sizeof(FocalJob),
                                    n_focal * sizeof(FocalJob), cudaMemcpyHostToDevice, us));
             }
+            // tensor maps of this chunk's TMA-fed stencil launches: the layer arena cannot move any more before
+            // they run (it only grows above, with the stream drained), so device addresses are final here
+            {
+                const size_t first = tmap_top;
+                char *pin = (char *)(((uintptr_t)ctx->pin_tmaps.p + 63) & ~(uintptr_t)63);
+                char *dev = (char *)(((uintptr_t)ctx->d_tmaps.p + 63) & ~(uintptr_t)63);
+                for (size_t q = launch_begin; q < ctx->launches.size(); q++) {
+                    Launch &L = ctx->launches[q];
+                    if (L.cls != 4 && L.cls != 5)
+                        continue;
+                    L.tmap_off = (long long)tmap_top;
+                    int kc = 0;
+                    svgr_stencil_tma_smem(L.cls == 4, L.k_max, &kc);
+                    for (int j = 0; j < L.op_count; j++) {
+                        const OpRec &o = ctx->ops[L.op_begin + j].op;
+                        const SrcRec &sr = ctx->srcs[o.src_off];
+                        if (tmap_top + 2 > tmap_cap)
+                            FAIL(SVGR_E_NOMEM, "tensor map table larger than its bound");
+                        const float *src = ctx->d_layers.as<float>() + sr.off +
+                                           4 * ((long long)(sr.r0 - sr.br0) * sr.stride + (sr.c0 - sr.bc0));
+                        const int box_px = L.cls == 4 ? 128 : SVGR_TMA_V_TC;
+                        const int box_rows = L.cls == 4 ? SVGR_TMA_H_TR : std::min(o.k0, kc) + SVGR_TMA_V_TR - 1;
+                        if (svgr_encode_layer_map(pin + tmap_top * 128, src, sr.rows, sr.cols, sr.stride, box_px, box_rows))
+                            FAIL(SVGR_E_CUDA, "cuTensorMapEncodeTiled failed for a stencil source");
+                        if (L.cls == 4 &&
+                            svgr_encode_layer_map(pin + (tmap_top + 1) * 128, ctx->d_layers.as<float>() + o.out_off, o.rows,
+                                                  o.cols, o.stride, SVGR_TMA_H_TC / 2, SVGR_TMA_H_TR))
+                            FAIL(SVGR_E_CUDA, "cuTensorMapEncodeTiled failed for a stencil destination");
+                        tmap_top += 2;
+                    }
+                }
+                if (tmap_top > first)
+                    CK(cudaMemcpyAsync(dev + first * 128, pin + first * 128, (tmap_top - first) * 128, cudaMemcpyHostToDevice,
+                                       us));
+            }
             RenderTables T;
             T.srcs = ctx->d_srcs.as<SrcRec>(), T.paints = ctx->d_paints.as<PaintRec>(), T.stops = ctx->d_stops.as<StopRec>();
             T.focal_flags = ctx->d_focal_flags.as<int>(), T.cov = ctx->d_cov.as<float>(), T.layers = ctx->d_layers.as<float>();
@@ -1593,9 +1679,14 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
                 const int *tile_op = ctx->d_tile_map.as<int>();
                 const TileHead *heads = ctx->d_heads[par].as<TileHead>() + L.head_off;
                 const TileEntry *list = ctx->d_lists[par].as<TileEntry>() + L.list_off;
-                if (L.cls == 1 || L.cls == 2)
+                if (L.cls == 1 || L.cls == 2 || L.cls == 4 || L.cls == 5)
                     svgr_launch_expand_ops(ops, L.op_count, L.n_tiles, ctx->d_tile_map.as<int>(), s);
-                if (L.cls == 0)
+                if (L.cls == 4 || L.cls == 5) {
+                    const char *dev = (const char *)(((uintptr_t)ctx->d_tmaps.p + 63) & ~(uintptr_t)63);
+                    if (svgr_launch_stencil_tma(T, ops, tile_op, L.n_tiles, dev + L.tmap_off * 128, L.cls == 4, L.k_max, SM,
+                                                ctx->d_layers.as<float>(), s))
+                        FAIL(SVGR_E_UNSUPPORTED, "stencil needs more shared memory than available");
+                } else if (L.cls == 0)
                     svgr_launch_compose(T, ops, heads, list, L.n_tiles, L.simple, ctx->d_layers.as<float>(), nullptr, s);
                 else if (L.cls == 1) {
                     if (svgr_launch_stencil(T, ops, tile_op, L.n_tiles, L.smem, ctx->d_layers.as<float>(), s))
@@ -1789,11 +1880,12 @@ void svgr_destroy(svgr_ctx *ctx)
                       &ctx->d_focal_jobs, &ctx->d_focal_flags, &ctx->d_canvas, &ctx->d_q, &ctx->d_tile_map, &ctx->d_tile_rec, &ctx->d_bin_data, &ctx->d_heads[0], &ctx->d_heads[1], &ctx->d_lists[0],
                       &ctx->d_lists[1], &ctx->d_ovf_cubic[0], &ctx->d_ovf_cubic[1], &ctx->d_ovf_path[0], &ctx->d_ovf_path[1],
                       &ctx->d_ovf_depth[0], &ctx->d_ovf_depth[1], &ctx->d_ovf_counts, &ctx->d_eager[0], &ctx->d_eager[1],
-                      &ctx->d_eager[2]};
+                      &ctx->d_eager[2], &ctx->d_tmaps};
     for (DevBuf *b : bufs)
         b->release();
     ctx->pin_boxes.release(), ctx->pin_status.release(), ctx->pin_plan.release(), ctx->pin_out.release();
     ctx->pin_masks.release();
+    ctx->pin_tmaps.release();
     for (auto &e : ctx->ev)
         if (e)
             cudaEventDestroy(e);

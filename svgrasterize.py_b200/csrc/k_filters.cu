@@ -159,10 +159,12 @@ stencil_kernel(RenderTables T, const OpRec *__restrict__ ops, const int *__restr
     }
 }
 
-// Direct 2-D "full" convolution: out[i, j] = sum_{a, b} k[a, b] . in[i - a, j - b]; tile 8 x 32.
+// Direct 2-D "full" convolution: out[i, j] = sum_{a, b} k[a, b] . in[i - a, j - b]; tile 8 x 32.  The kernel rows
+// are walked in groups of `ga` rows whose input rows (8 + ga - 1 of them) fit the staging buffer, so the kernel
+// height is unbounded (ga = kr when everything fits at once, the common case).
 __global__ void __launch_bounds__(256)
 conv2d_kernel(RenderTables T, const OpRec *__restrict__ ops, const int *__restrict__ tile_op,
-              float *__restrict__ layers_out)
+              float *__restrict__ layers_out, int smem_bytes)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *sm = reinterpret_cast<float4 *>(smem_raw);
@@ -172,27 +174,35 @@ conv2d_kernel(RenderTables T, const OpRec *__restrict__ ops, const int *__restri
     const int tr = local / op.ntile_c, tc = local - tr * op.ntile_c;
     const int kr = op.k0, kc = op.k1;
     const int row0 = tr * SVGR_C2D_TR, col0 = tc * SVGR_C2D_TC;
-    const int srows = SVGR_C2D_TR + kr - 1, scols = SVGR_C2D_TC + kc - 1;
-    for (int i = threadIdx.x; i < srows * scols; i += 256) {
-        int rr = i / scols, cc = i - rr * scols;
-        sm[i] = load_local(T, s, row0 - kr + 1 + rr, col0 - kc + 1 + cc);
-    }
-    __syncthreads();
+    const int scols = SVGR_C2D_TC + kc - 1;
+    const int ga = min(kr, max(1, smem_bytes / (scols * 16) - SVGR_C2D_TR + 1));  // kernel rows per group
     const int ty = threadIdx.x >> 5, tx = threadIdx.x & 31;
     const int lr = row0 + ty, lc = col0 + tx;
-    if (lr >= op.rows || lc >= op.cols)
-        return;
     const float *w = T.weights + op.aux;
     float4 acc = zero4();
-    for (int a = 0; a < kr; a++)
-        for (int b = 0; b < kc; b++) {
-            float wt = w[a * kc + b];
-            float4 v = sm[(ty + kr - 1 - a) * scols + (tx + kc - 1 - b)];
-            acc = madd4(v, wt, acc);
+    for (int a0 = 0; a0 < kr; a0 += ga) {
+        const int na = min(ga, kr - a0);        // kernel rows a0 .. a0 + na - 1
+        const int srows = SVGR_C2D_TR + na - 1;  // input rows row0 - (a0 + na - 1) .. row0 + 7 - a0
+        if (a0 > 0)
+            __syncthreads();
+        for (int i = threadIdx.x; i < srows * scols; i += 256) {
+            int rr = i / scols, cc = i - rr * scols;
+            sm[i] = load_local(T, s, row0 - (a0 + na - 1) + rr, col0 - kc + 1 + cc);
         }
+        __syncthreads();
+        for (int a = 0; a < na; a++)
+            for (int b = 0; b < kc; b++) {
+                float wt = w[(a0 + a) * kc + b];
+                float4 v = sm[(ty + na - 1 - a) * scols + (tx + kc - 1 - b)];
+                acc = madd4(v, wt, acc);
+            }
+    }
+    if (lr >= op.rows || lc >= op.cols)
+        return;
     reinterpret_cast<float4 *>(layers_out + op.out_off)[(long long)lr * op.stride + lc] = acc;
 }
 
+// ---------------------------------------------------------------------------------------------
 // ---------------------------------------------------------------------------------------------
 // the opt-in is per device; setting it twice is harmless, so the flags only need to be atomic, not locked
 static std::atomic<bool> g_attr_set[64];
@@ -229,7 +239,7 @@ int svgr_launch_conv2d(const RenderTables &T, const OpRec *ops, const int *tile_
     if (smem_bytes > SVGR_MAX_DYN_SMEM)
         return -1;
     ensure_attrs();
-    conv2d_kernel<<<n_tiles, 256, smem_bytes, s>>>(T, ops, tile_op, layers_out);
+    conv2d_kernel<<<n_tiles, 256, smem_bytes, s>>>(T, ops, tile_op, layers_out, (int)smem_bytes);
     return 0;
 }
 

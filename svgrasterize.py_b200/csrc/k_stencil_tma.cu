@@ -165,7 +165,7 @@ stencil_tma_kernel(RenderTables T, const OpRec *__restrict__ ops, const int *__r
     __shared__ __align__(8) unsigned long long full[2];
     constexpr int R = HORIZ ? TH_R : TV_R;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    unsigned char *stage[2] = {smem, smem + stage_bytes};
+    auto stage_ptr = [&](int st) { return smem + (size_t)st * stage_bytes; };
     float4 *out_stage = reinterpret_cast<float4 *>(smem + 2 * (size_t)stage_bytes);
 
     if (tid == 0) {
@@ -184,12 +184,12 @@ stencil_tma_kernel(RenderTables T, const OpRec *__restrict__ ops, const int *__r
             const int n_box = (u.kc + TH_TC - 1 + TH_CHUNK - 1) / TH_CHUNK;
             mbar_expect_tx(&full[s], (unsigned)n_box * TH_TR * TH_CHUNK * 16);
             for (int c = 0; c < n_box; c++)
-                tma_load_2d(stage[s] + (size_t)c * TH_TR * TH_CHUNK * 16, map, 2 * (u.col0 + base + u.u0 + c * TH_CHUNK),
+                tma_load_2d(stage_ptr(s) + (size_t)c * TH_TR * TH_CHUNK * 16, map, 2 * (u.col0 + base + u.u0 + c * TH_CHUNK),
                             u.row0, &full[s]);
         } else {
             const int box_rows = min(u.k, kc_max) + TV_TR - 1;  // the map's box: fixed per op
             mbar_expect_tx(&full[s], (unsigned)box_rows * TV_TC * 16);
-            tma_load_2d(stage[s], map, 2 * u.col0, u.row0 + base + u.u0, &full[s]);
+            tma_load_2d(stage_ptr(s), map, 2 * u.col0, u.row0 + base + u.u0, &full[s]);
         }
     };
 
@@ -232,7 +232,7 @@ stencil_tma_kernel(RenderTables T, const OpRec *__restrict__ ops, const int *__r
             acc_init<R>(acc, cur.st);
         mbar_wait(&full[s], (n >> 1) & 1);
         const float *wp = T.weights + __ldg(&op->aux) + (cur.k - 1 - cur.u0);  // conv: tap u has weight w[k - 1 - u]
-        const unsigned char *sb = stage[s];
+        const unsigned char *sb = stage_ptr(s);
         auto fetch = [&](const float4 *p) {
             float4 v = *p;
             if (fix) {

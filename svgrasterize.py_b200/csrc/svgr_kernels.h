@@ -80,6 +80,13 @@ int svgr_launch_conv2d(const RenderTables &T, const OpRec *ops, const int *tile_
 void svgr_launch_pooling(const float *in, int rows, int cols, int ch, int ky, int kx, int sy, int sx, int method,
                          float *out, int orows, int ocols, cudaStream_t s);
 
+// k_stencil_tma.cu
+int svgr_encode_layer_map(void *out, const float *base, long long rows, long long cols, long long stride_px, int box_px,
+                          int box_rows);
+size_t svgr_stencil_tma_smem(bool horiz, int k_max, int *kc_out);
+int svgr_launch_stencil_tma(const RenderTables &T, const OpRec *ops, const int *tile_op, int n_tiles, const void *tmaps,
+                            bool horiz, int k_max, int sm_count, float *layers_out, cudaStream_t s);
+
 // k_stroke.cu
 size_t svgr_stroke_curve_bytes();
 void svgr_launch_stroke_count(const uint8_t *tag, const double *data, const int *seg_job, const StrokeRec *jobs,

@@ -219,3 +219,10 @@ struct FocalJob {
 #define SVGR_STH_TC 128
 #define SVGR_STV_TR 64
 #define SVGR_STV_TC 32
+// TMA-fed stencils (k_stencil_tma.cu): tile shapes and taps per shared-memory stage
+#define SVGR_TMA_H_TR 8
+#define SVGR_TMA_H_TC 224
+#define SVGR_TMA_H_KC 289
+#define SVGR_TMA_V_TR 64
+#define SVGR_TMA_V_TC 32
+#define SVGR_TMA_V_KC 65
