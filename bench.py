@@ -154,7 +154,7 @@ def build_batch(icons, seed0, engine):
     return encode.Program.concat(progs), progs
 
 
-def run_e2e(batches, out_host_np, device, steps, warmup, workers, chunks):
+def run_e2e(batches, out_host_np, device, steps, warmup, workers, chunks, png=False):
     """End to end through the public call (Engine.render -> svgr_render) with host buffers: step k renders batch
     k (mod the number of distinct batches), cut into `chunks` programs that `workers` host threads (one Engine =
     one context + stream each) render back to back, so that one chunk's device->host copy overlaps the next
@@ -178,6 +178,7 @@ def run_e2e(batches, out_host_np, device, steps, warmup, workers, chunks):
     engines = [Engine(device) for _ in range(workers)]
     errors = []
     step_no = [0] * workers
+    d2h = [0] * workers
 
     def work(w, reps):
         try:
@@ -185,7 +186,12 @@ def run_e2e(batches, out_host_np, device, steps, warmup, workers, chunks):
                 parts, offs = all_parts[step_no[w] % len(all_parts)]
                 step_no[w] += 1
                 for c in range(w, chunks, workers):
-                    engines[w].render(parts[c], out=out_host_np[offs[c]: offs[c + 1]])
+                    if png:  # PNG files made on the device: only they cross PCIe
+                        res = engines[w].render_png(parts[c], out=out_host_np[offs[c]: offs[c + 1]])
+                        d2h[w] += int(res["png_bytes"])
+                    else:
+                        engines[w].render(parts[c], out=out_host_np[offs[c]: offs[c + 1]])
+                        d2h[w] += parts[c].canvas_bytes
         except Exception as exc:  # noqa: BLE001
             errors.append(exc)
 
@@ -201,6 +207,8 @@ def run_e2e(batches, out_host_np, device, steps, warmup, workers, chunks):
         return time.perf_counter() - t0
 
     run(max(1, min(warmup, 2)))
+    for w in range(workers):
+        d2h[w] = 0
     dt = run(steps)
     for e in engines:
         e.close()
@@ -208,7 +216,7 @@ def run_e2e(batches, out_host_np, device, steps, warmup, workers, chunks):
         raise errors[0]
     h2d = sum(p.h2d_bytes() for p in all_parts[0][0])
     del pins
-    return dt / steps, h2d
+    return dt / steps, h2d, sum(d2h) // steps
 
 
 def time_other_configs(device, peak, with_cpu):
@@ -402,11 +410,17 @@ def run_gpu(opts):
     chunks = max(workers, opts.e2e_chunks if opts.e2e_chunks % workers == 0 else workers)
     for e in engines[1:]:
         e.close()  # their arenas are not needed any more
-    sec_e2e, h2d_bytes = run_e2e(batches, out_host_np, local, opts.steps, opts.warmup, workers, chunks)
+    sec_e2e, h2d_bytes, d2h_raw = run_e2e(batches, out_host_np, local, opts.steps, opts.warmup, workers, chunks)
     barrier()
-    ms_e2e = max_over_ranks(sec_e2e * 1e3)
-    e2e_value = world * n_px / (ms_e2e * 1e-3) / 1e6
+    ms_e2e_raw = max_over_ranks(sec_e2e * 1e3)
     check = int(out_host_np[:: max(1, len(out_host_np) // 4096)].astype(np.int64).sum())
+    # the same with the result delivered as PNG files encoded on the device (what the reference's main() writes)
+    sec_png, _h2d, d2h_png = run_e2e(batches, out_host_np, local, opts.steps, opts.warmup, workers, chunks, png=True)
+    barrier()
+    ms_e2e_png = max_over_ranks(sec_png * 1e3)
+    use_png = ms_e2e_png < ms_e2e_raw
+    ms_e2e = ms_e2e_png if use_png else ms_e2e_raw
+    e2e_value = world * n_px / (ms_e2e * 1e-3) / 1e6
 
     if rank != 0:
         if dist is not None:
@@ -481,10 +495,17 @@ def run_gpu(opts):
                    "arithmetic": "geometry f64, coverage/compose f32"},
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(h2d_bytes),
-                "d2h_bytes_per_step": int(prog.canvas_bytes), "checksum": check,
-                "how": f"Engine.render (svgr_render) on pinned host buffers; the batch goes through "
+                "d2h_bytes_per_step": int(d2h_png if use_png else d2h_raw), "checksum": check,
+                "result": ("PNG files encoded on the device (lossless: they decode to exactly the RGBA8 canvases, "
+                           "tests/test_gpu_png.py)" if use_png else "raw RGBA8 canvases"),
+                "how": ("Engine.render_png (svgr_render_png)" if use_png else "Engine.render (svgr_render)") +
+                       f" on pinned host buffers; the batch goes through "
                        f"{chunks} calls on {workers} host threads (one context + stream each) "
-                       "so that copies overlap compute; wall clock between device synchronisations"},
+                       "so that copies overlap compute; wall clock between device synchronisations",
+                "raw_rgba8": {"value": world * n_px / (ms_e2e_raw * 1e-3) / 1e6, "ms_per_step": ms_e2e_raw,
+                              "d2h_bytes_per_step": int(d2h_raw)},
+                "png": {"value": world * n_px / (ms_e2e_png * 1e-3) / 1e6, "ms_per_step": ms_e2e_png,
+                        "d2h_bytes_per_step": int(d2h_png)}},
         "gpu_launches": int(st["n_kernels"]) * opts.steps,
         "paths_per_s": world * len(prog.paths) / (ms_step * 1e-3),
         "stage_ms_per_step": {k: v / opts.steps for k, v in sorted(acc.items())},

@@ -183,6 +183,9 @@ typedef struct svgr_stats {
                                  (one HBM pass per layer: 4 B coverage + 16 B destination read + 16 B written) + 20 B
                                  per quantised canvas pixel; compose_bytes is less because the fold keeps the
                                  destination in registers */
+    int64_t png_bytes;        /* svgr_render_png: total bytes of the PNG files */
+    float ms_png;             /* device time of the PNG encoding kernels */
+    float pad3;
 } svgr_stats;
 
 typedef struct svgr_ctx svgr_ctx;
@@ -205,6 +208,23 @@ int svgr_render(svgr_ctx *ctx, const svgr_program *prog, void *stream, int stop_
 /* Re-run the device part of the last svgr_render with the program already resident in HBM
  * (no host->device copy of the program); used for kernel-only throughput measurements. */
 int svgr_render_resident(svgr_ctx *ctx, void *stream, uint8_t *out_device, int timing, svgr_stats *stats);
+
+/* Render `prog` and encode every canvas as a PNG file ON THE DEVICE (8-bit RGBA, Paeth filter, one zlib stream of
+ * dynamic-Huffman deflate blocks); only the files cross PCIe.  Replaces Layer.write_png / canvas_to_png
+ * (svgrasterize.py:209-213, :249-274) for batches: the files decode to exactly the canvas bytes svgr_render
+ * would have returned, but are not the reference's bytes (its filter-0 + zlib level 9 stream stays available
+ * through the host path).  `out` receives the files back to back (host pointer, or device when out_on_device);
+ * offsets (host, n_canvas + 1 entries, canvas node order) their byte ranges.  When out_cap is too small the call
+ * fails with SVGR_E_NOMEM and offsets[n_canvas] holds the size needed. */
+int svgr_render_png(svgr_ctx *ctx, const svgr_program *prog, void *stream, uint8_t *out, int64_t out_cap, int out_on_device,
+                    int64_t *offsets, int timing, svgr_stats *stats);
+/* The same on the program left resident by the last svgr_render / svgr_render_png. */
+int svgr_render_resident_png(svgr_ctx *ctx, void *stream, uint8_t *out, int64_t out_cap, int out_on_device,
+                             int64_t *offsets, int timing, svgr_stats *stats);
+/* PNG-encode RGBA8 images that are already in host memory (rows x cols x 4 each, back to back) on the device:
+ * the batch form of canvas_to_png's device path. */
+int svgr_png_encode(svgr_ctx *ctx, const uint8_t *images, int32_t n_images, const int32_t *rows, const int32_t *cols,
+                    uint8_t *out, int64_t out_cap, int64_t *offsets);
 
 /* Host-only: plan `prog` for the given path boxes (n_path x 4 int32) `reps` times without touching CUDA;
  * reports the best wall time of the two planning phases and info = {ops, sources, launches, levels,

@@ -7,6 +7,7 @@ from .scene import *  # noqa: F401,F403
 from . import api  # noqa: F401,E402  (attaches mask / fill / stroke / render to Path, Scene and Filter)
 from .api import (Layer, canvas_compose, canvas_create, canvas_merge_at, canvas_merge_intersect,  # noqa: F401,E402
                   canvas_merge_union, canvas_to_png, pooling, bezier3_flatten_batch, blur_kernel, render_canvas,
-                  line_signed_coverage, grad_pixels, grad_spread, grad_interpolate, install, uninstall)
+                  line_signed_coverage, grad_pixels, grad_spread, grad_interpolate, install, uninstall,
+                  render_png, render_png_batch)
 
 __version__ = "0.1.0"

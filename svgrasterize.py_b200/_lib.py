@@ -70,7 +70,7 @@ class Stats(C.Structure):
                                          "ms_coverage", "ms_compose", "ms_canvas", "ms_d2h")] + \
                [("retries", C.c_int32), ("pad", C.c_int32), ("host_plan_masks_ms", C.c_float),
                 ("host_plan_nodes_ms", C.c_float), ("ms_compose_busy", C.c_float), ("pad2", C.c_float),
-                ("compose_bytes_8d", C.c_int64)]
+                ("compose_bytes_8d", C.c_int64), ("png_bytes", C.c_int64), ("ms_png", C.c_float), ("pad3", C.c_float)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_ if not n.startswith("pad")}
@@ -86,6 +86,12 @@ SYMBOLS = {
     "svgr_render": (C.c_int, [C.c_void_p, C.POINTER(Program), C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
                               C.POINTER(Stats)]),
     "svgr_render_resident": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Stats)]),
+    "svgr_render_png": (C.c_int, [C.c_void_p, C.POINTER(Program), C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
+                                  C.c_int, C.POINTER(Stats)]),
+    "svgr_render_resident_png": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int,
+                                           C.POINTER(Stats)]),
+    "svgr_png_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                  C.c_void_p]),
     "svgr_debug_plan": (C.c_int, [C.POINTER(Program), C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                   C.c_void_p]),
     "svgr_read_edges": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),

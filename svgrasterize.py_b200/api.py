@@ -337,6 +337,28 @@ def render_canvas(scene, size, linear_rgb=False):
     return eng.canvas(prog, res["canvas"]).copy()
 
 
+def render_png(scene, size, linear_rgb=False) -> bytes:
+    """main() of the reference from the Scene to the PNG file (svgrasterize.py:3854-3881), with the file made on the
+    device (Paeth filter + dynamic-Huffman deflate, csrc/k_png.cu): decodes to the same pixels as render_canvas,
+    but is not the reference's byte stream (that is canvas_to_png's default path)."""
+    eng = default_engine()
+    enc = Encoder(eng)
+    enc.add_scene(scene, size, linear_rgb)
+    res = eng.render_png(enc.finish())
+    return res["png"].tobytes()
+
+
+def render_png_batch(jobs, processes: int = 0):
+    """[(scene, size, linear_rgb)] -> list of PNG files, all rendered and encoded as one batch."""
+    from .encode import encode_batch
+
+    eng = default_engine()
+    prog = encode_batch(jobs, processes)
+    res = eng.render_png(prog)
+    off = res["offsets"]
+    return [res["png"][off[i]: off[i + 1]].tobytes() for i in range(len(off) - 1)]
+
+
 # ---------------------------------------------------------------------------------------------
 # canvas helpers (svgrasterize.py:235-468)
 # ---------------------------------------------------------------------------------------------
@@ -491,7 +513,7 @@ def _deflate_parallel(raw: bytes, level: int, threads: int, block: int = 1 << 20
     return head + b"".join(parts) + struct.pack(">I", zlib.adler32(raw) & 0xFFFFFFFF)
 
 
-def canvas_to_png(canvas, output=None, threads=1, level=9):
+def canvas_to_png(canvas, output=None, threads=1, level=9, device=False):
     """canvas_to_png (svgrasterize.py:249-274): straight-alpha sRGB float image -> PNG bytes.  The
     float -> uint8 quantisation (:263) is the in-scope part; deflate stays on the host like the reference.
 
@@ -502,6 +524,12 @@ def canvas_to_png(canvas, output=None, threads=1, level=9):
     canvas = np.asarray(canvas)
     if canvas.dtype != np.uint8:
         canvas = default_engine().quantize_u8(canvas)  # np.round(canvas * 255).astype(uint8) on the device (:263)
+    if device:
+        # the whole file on the device (csrc/k_png.cu): same pixels, a different (Paeth + dynamic Huffman) stream
+        png = default_engine().png_encode([canvas])[0]
+        output = io.BytesIO() if output is None else output
+        output.write(png)
+        return output
     height, width = canvas.shape[:2]
     rows = np.zeros((height, 1 + width * 4), dtype=np.uint8)  # filter type 0 in front of every row
     rows[:, 1:] = canvas.reshape(height, width * 4)

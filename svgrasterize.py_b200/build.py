@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsvgr_b200.so")
 SOURCES = ["engine.cu", "k_flatten.cu", "k_stroke.cu", "k_coverage.cu", "k_compose.cu", "k_filters.cu",
-           "k_stencil_tma.cu"]
+           "k_stencil_tma.cu", "k_png.cu"]
 HEADERS = ["svgr_types.h", "svgr_kernels.h", "svgr_device.cuh", os.path.join("..", "..", "include", "svgr_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -26,7 +26,7 @@ NVCC_FLAGS = [
 # Geometry (flatten, stroke, coverage edge math, the planner) reproduces the reference's float64 roundings and
 # must not have multiplies and adds contracted behind its back; the pixel kernels are float32 work within a
 # 1e-5 tolerance and keep the default contraction (FFMA).
-FMAD = {"k_compose.cu": "true", "k_filters.cu": "true", "k_stencil_tma.cu": "true"}
+FMAD = {"k_compose.cu": "true", "k_filters.cu": "true", "k_stencil_tma.cu": "true", "k_png.cu": "true"}
 
 
 def _nvcc() -> str:

@@ -175,6 +175,11 @@ struct svgr_ctx {
     long long canvas_bytes = 0;
     double flatness = 0.0;
     DevBuf d_eager[3];  // scratch of the eager element-wise entry points
+    // PNG encoding (k_png.cu): segment / canvas tables, worst-case slots, sizes, packed files
+    DevBuf d_png_segs, d_png_canvases, d_png_scratch, d_png_seg_bytes, d_png_seg_adler, d_png_file_bytes, d_png_file_off,
+        d_png_out, d_png_in;
+    PinBuf pin_png;
+    cudaEvent_t ev_png[2] = {nullptr, nullptr};
     DevBuf d_tmaps;     // tensor maps of the TMA-fed stencil launches of the render in flight (128 B each)
     PinBuf pin_tmaps;
     int n_filter_nodes = 0;  // blur / morphology nodes of the loaded program (bounds the map table)
@@ -1859,6 +1864,7 @@ int svgr_create(int device, svgr_ctx **out)
     for (auto &e : ctx->ev_up)
         cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_up_begin, cudaEventDisableTiming);
+    cudaEventCreate(&ctx->ev_png[0]), cudaEventCreate(&ctx->ev_png[1]);
     for (auto &e : ctx->ev_done)
         cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     *out = ctx;
@@ -1880,12 +1886,18 @@ void svgr_destroy(svgr_ctx *ctx)
                       &ctx->d_focal_jobs, &ctx->d_focal_flags, &ctx->d_canvas, &ctx->d_q, &ctx->d_tile_map, &ctx->d_tile_rec, &ctx->d_bin_data, &ctx->d_heads[0], &ctx->d_heads[1], &ctx->d_lists[0],
                       &ctx->d_lists[1], &ctx->d_ovf_cubic[0], &ctx->d_ovf_cubic[1], &ctx->d_ovf_path[0], &ctx->d_ovf_path[1],
                       &ctx->d_ovf_depth[0], &ctx->d_ovf_depth[1], &ctx->d_ovf_counts, &ctx->d_eager[0], &ctx->d_eager[1],
-                      &ctx->d_eager[2], &ctx->d_tmaps};
+                      &ctx->d_eager[2], &ctx->d_tmaps, &ctx->d_png_segs, &ctx->d_png_canvases, &ctx->d_png_scratch,
+                      &ctx->d_png_seg_bytes, &ctx->d_png_seg_adler, &ctx->d_png_file_bytes, &ctx->d_png_file_off,
+                      &ctx->d_png_out, &ctx->d_png_in};
     for (DevBuf *b : bufs)
         b->release();
     ctx->pin_boxes.release(), ctx->pin_status.release(), ctx->pin_plan.release(), ctx->pin_out.release();
     ctx->pin_masks.release();
     ctx->pin_tmaps.release();
+    ctx->pin_png.release();
+    for (auto &e : ctx->ev_png)
+        if (e)
+            cudaEventDestroy(e);
     for (auto &e : ctx->ev)
         if (e)
             cudaEventDestroy(e);
@@ -1919,6 +1931,114 @@ const char *svgr_last_error(svgr_ctx *ctx) { return ctx ? ctx->err.c_str() : "nu
 
 // A call that failed half way may have left copies and kernels in flight on the side streams: nothing of it
 // may still be running when the caller reuses its buffers or renders again.
+// ---- PNG files from RGBA8 canvases that are in device memory (k_png.cu) -----------------------------------------
+namespace {
+struct PngSegH {
+    int32_t canvas, row0, rows, last;
+    int64_t slot;
+};
+struct PngCanvasH {
+    int64_t src;
+    int32_t rows, cols, seg0, nseg;
+};
+struct PngImage {
+    int64_t src;
+    int32_t rows, cols;
+};
+}  // namespace
+
+// images: canvases inside `canvas_buf` (device).  out / offsets as in svgr_render_png.
+static int encode_png(svgr_ctx *ctx, cudaStream_t s, const uint8_t *canvas_buf, const std::vector<PngImage> &images, uint8_t *out,
+                      int64_t out_cap, int out_on_device, int64_t *offsets, int timing, svgr_stats *stats)
+{
+    const int n = (int)images.size();
+    if (!offsets)
+        FAIL(SVGR_E_INVALID, "png: offsets must not be null");
+    offsets[0] = 0;
+    if (n == 0)
+        return SVGR_OK;
+    std::vector<PngSegH> segs;
+    std::vector<PngCanvasH> cvs((size_t)n);
+    int64_t slot_top = 0;
+    for (int i = 0; i < n; i++) {
+        const PngImage &im = images[(size_t)i];
+        if (im.rows <= 0 || im.cols <= 0)
+            FAIL(SVGR_E_INVALID, "png: empty canvas");
+        const int per = svgr_png_rows_per_segment(im.cols);
+        cvs[(size_t)i] = {im.src, im.rows, im.cols, (int32_t)segs.size(), (im.rows + per - 1) / per};
+        for (int r = 0; r < im.rows; r += per) {
+            const int rows = std::min(per, im.rows - r);
+            segs.push_back({i, r, rows, r + rows >= im.rows ? 1 : 0, slot_top});
+            slot_top += svgr_png_slot_bytes(rows, im.cols);
+        }
+    }
+    const size_t n_seg = segs.size();
+    CK(ctx->d_png_segs.ensure(n_seg * sizeof(PngSegH)));
+    CK(ctx->d_png_canvases.ensure((size_t)n * sizeof(PngCanvasH)));
+    CK(ctx->d_png_scratch.ensure((size_t)slot_top + 64));
+    CK(ctx->d_png_seg_bytes.ensure(n_seg * 4));
+    CK(ctx->d_png_seg_adler.ensure(n_seg * 8));
+    CK(ctx->d_png_file_bytes.ensure((size_t)n * 4));
+    CK(ctx->d_png_file_off.ensure((size_t)n * 8));
+    CK(ctx->pin_png.ensure((size_t)n * 4 + (size_t)n * 8 + 64));
+    if (timing)
+        cudaEventRecord(ctx->ev_png[0], s);
+    CK(cudaMemcpyAsync(ctx->d_png_segs.p, segs.data(), n_seg * sizeof(PngSegH), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->d_png_canvases.p, cvs.data(), (size_t)n * sizeof(PngCanvasH), cudaMemcpyHostToDevice, s));
+    svgr_launch_png_deflate(ctx->d_png_segs.p, (int)n_seg, ctx->d_png_canvases.p, canvas_buf, ctx->d_png_scratch.as<uint8_t>(),
+                            ctx->d_png_seg_bytes.as<int>(), ctx->d_png_seg_adler.as<unsigned>(), s);
+    svgr_launch_png_sizes(ctx->d_png_canvases.p, n, ctx->d_png_seg_bytes.as<int>(), ctx->d_png_file_bytes.as<int>(), s);
+    int *h_sizes = (int *)ctx->pin_png.p;
+    long long *h_off = (long long *)((char *)ctx->pin_png.p + (((size_t)n * 4 + 15) & ~(size_t)15));
+    CK(cudaMemcpyAsync(h_sizes, ctx->d_png_file_bytes.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));  // the file sizes decide where every file goes
+    int64_t total = 0;
+    for (int i = 0; i < n; i++) {
+        h_off[i] = total;
+        offsets[i] = total;
+        total += h_sizes[i];
+    }
+    offsets[n] = total;
+    if (out && total > out_cap)
+        FAIL(SVGR_E_NOMEM, "png: output buffer too small (offsets[n_canvas] holds the size needed)");
+    uint8_t *dst = (out && out_on_device) ? out : nullptr;
+    if (!dst) {
+        CK(ctx->d_png_out.ensure((size_t)total + 64));
+        dst = ctx->d_png_out.as<uint8_t>();
+    }
+    CK(cudaMemcpyAsync(ctx->d_png_file_off.p, h_off, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+    svgr_launch_png_pack(ctx->d_png_canvases.p, n, ctx->d_png_segs.p, ctx->d_png_seg_bytes.as<int>(),
+                         ctx->d_png_seg_adler.as<unsigned>(), ctx->d_png_scratch.as<uint8_t>(),
+                         ctx->d_png_file_off.as<long long>(), dst, s);
+    if (timing)
+        cudaEventRecord(ctx->ev_png[1], s);
+    if (out && !out_on_device)
+        CK(cudaMemcpyAsync(out, dst, (size_t)total, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    if (stats) {
+        stats->png_bytes = total;
+        stats->n_kernels += 3;
+        if (timing) {
+            stats->ms_png = ev_ms(ctx->ev_png[0], ctx->ev_png[1]);
+            stats->ms_total += stats->ms_png;
+        }
+    }
+    return SVGR_OK;
+}
+
+// the canvases of the resident program, in canvas node order
+static int program_canvases(svgr_ctx *ctx, std::vector<PngImage> &images)
+{
+    images.clear();
+    for (int i = 0; i < ctx->n_node; i++) {
+        const svgr_node &n = ctx->h_nodes[(size_t)i];
+        if (n.tag == SVGR_N_CANVAS)
+            images.push_back({(int64_t)n.f[0], n.a, n.b});
+    }
+    return SVGR_OK;
+}
+
 static void drain_after_failure(svgr_ctx *ctx, cudaStream_t s)
 {
     cudaStreamSynchronize(s);
@@ -1961,6 +2081,67 @@ int svgr_render(svgr_ctx *ctx, const svgr_program *prog, void *stream, int stop_
         }
         cudaEventDestroy(e0), cudaEventDestroy(e1);
     }
+    return rc;
+}
+
+int svgr_render_png(svgr_ctx *ctx, const svgr_program *prog, void *stream, uint8_t *out, int64_t out_cap, int out_on_device,
+                    int64_t *offsets, int timing, svgr_stats *stats)
+{
+    if (!ctx)
+        return SVGR_E_INVALID;
+    // the canvases stay in the context's device buffer; only the files are copied out
+    int rc = svgr_render(ctx, prog, stream, SVGR_STOP_NONE, nullptr, 1, timing, stats);
+    if (rc != SVGR_OK)
+        return rc;
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->own_stream;
+    std::vector<PngImage> images;
+    program_canvases(ctx, images);
+    rc = encode_png(ctx, s, ctx->d_canvas.as<uint8_t>(), images, out, out_cap, out_on_device, offsets, timing, stats);
+    if (rc != SVGR_OK)
+        drain_after_failure(ctx, s);
+    return rc;
+}
+
+int svgr_render_resident_png(svgr_ctx *ctx, void *stream, uint8_t *out, int64_t out_cap, int out_on_device,
+                             int64_t *offsets, int timing, svgr_stats *stats)
+{
+    if (!ctx)
+        return SVGR_E_INVALID;
+    int rc = svgr_render_resident(ctx, stream, nullptr, timing, stats);
+    if (rc != SVGR_OK)
+        return rc;
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->own_stream;
+    std::vector<PngImage> images;
+    program_canvases(ctx, images);
+    rc = encode_png(ctx, s, ctx->d_canvas.as<uint8_t>(), images, out, out_cap, out_on_device, offsets, timing, stats);
+    if (rc != SVGR_OK)
+        drain_after_failure(ctx, s);
+    return rc;
+}
+
+int svgr_png_encode(svgr_ctx *ctx, const uint8_t *images, int32_t n_images, const int32_t *rows, const int32_t *cols,
+                    uint8_t *out, int64_t out_cap, int64_t *offsets)
+{
+    if (!ctx)
+        return SVGR_E_INVALID;
+    if (n_images < 0 || (n_images > 0 && (!images || !rows || !cols)))
+        FAIL(SVGR_E_INVALID, "png_encode: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    std::vector<PngImage> list;
+    int64_t top = 0;
+    for (int i = 0; i < n_images; i++) {
+        if (rows[i] <= 0 || cols[i] <= 0)
+            FAIL(SVGR_E_INVALID, "png_encode: empty image");
+        list.push_back({top, rows[i], cols[i]});
+        top += 4ll * rows[i] * cols[i];
+    }
+    cudaStream_t s = ctx->own_stream;
+    CK(ctx->d_png_in.ensure((size_t)std::max<int64_t>(top, 4)));
+    if (top > 0)
+        CK(cudaMemcpyAsync(ctx->d_png_in.p, images, (size_t)top, cudaMemcpyHostToDevice, s));
+    const int rc = encode_png(ctx, s, ctx->d_png_in.as<uint8_t>(), list, out, out_cap, 0, offsets, 0, nullptr);
+    if (rc != SVGR_OK)
+        drain_after_failure(ctx, s);
     return rc;
 }
 

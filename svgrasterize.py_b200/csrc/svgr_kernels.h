@@ -87,6 +87,17 @@ size_t svgr_stencil_tma_smem(bool horiz, int k_max, int *kc_out);
 int svgr_launch_stencil_tma(const RenderTables &T, const OpRec *ops, const int *tile_op, int n_tiles, const void *tmaps,
                             bool horiz, int k_max, int sm_count, float *layers_out, cudaStream_t s);
 
+// k_png.cu
+struct PngSeg;
+struct PngCanvas;
+long long svgr_png_slot_bytes(int rows, int cols);
+int svgr_png_rows_per_segment(int cols);
+void svgr_launch_png_deflate(const void *segs, int n_seg, const void *canvases, const unsigned char *canvas_buf,
+                             unsigned char *scratch, int *seg_bytes, unsigned *seg_adler, cudaStream_t s);
+void svgr_launch_png_sizes(const void *canvases, int n_canvas, const int *seg_bytes, int *file_bytes, cudaStream_t s);
+void svgr_launch_png_pack(const void *canvases, int n_canvas, const void *segs, const int *seg_bytes, const unsigned *seg_adler,
+                          const unsigned char *scratch, const long long *file_off, unsigned char *out, cudaStream_t s);
+
 // k_stroke.cu
 size_t svgr_stroke_curve_bytes();
 void svgr_launch_stroke_count(const uint8_t *tag, const double *data, const int *seg_job, const StrokeRec *jobs,

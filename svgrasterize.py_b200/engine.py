@@ -113,6 +113,74 @@ class Engine:
         self._check(self.L.svgr_render_resident(self.ctx, self._stream(stream), ptr, int(bool(timing)), C.byref(stats)))
         return stats.as_dict()
 
+    # -- PNG files made on the device ------------------------------------------------------------------
+    def _png_call(self, fn, head, n_canvas, raw_bytes, out, timing):
+        """Shared tail of render_png / render_resident_png: out = None (a host buffer is allocated and trimmed),
+        a numpy uint8 array (host, e.g. pinned) or a torch CUDA uint8 tensor."""
+        stats = _lib.Stats()
+        offsets = np.zeros(n_canvas + 1, dtype=np.int64)
+        own = None
+        if out is None:
+            # PNG of flat vector art is a small fraction of the raw bytes; a pathological canvas can exceed them
+            own = out = np.empty(raw_bytes // 2 + 4096 * n_canvas + 65536, dtype=np.uint8)
+        for attempt in range(2):
+            if isinstance(out, np.ndarray):
+                if out.dtype != np.uint8 or not out.flags.c_contiguous:
+                    raise ValueError("out must be a C-contiguous uint8 array")
+                ptr, cap, on_dev = out.ctypes.data, out.nbytes, 0
+            else:
+                self._check_device_tensor(out, 0)
+                ptr, cap, on_dev = out.data_ptr(), out.numel() * out.element_size(), 1
+            rc = fn(*head, ptr, cap, on_dev, offsets.ctypes.data, int(bool(timing)), C.byref(stats))
+            if rc == _lib.E_NOMEM and own is not None and attempt == 0 and offsets[-1] > cap:
+                own = out = np.empty(int(offsets[-1]), dtype=np.uint8)  # rare: run again with the exact size
+                continue
+            self._check(rc)
+            break
+        res = stats.as_dict()
+        res["offsets"] = offsets
+        if own is not None:
+            res["png"] = own[: int(offsets[-1])]
+        self.last_stats = res
+        return res
+
+    def render_png(self, program: Program, out=None, timing: bool = False, stream=None):
+        """svgr_render_png: render and PNG-encode every canvas on the device.  -> stats with "offsets" (int64,
+        n_canvas + 1) and, when out is None, "png" (uint8 array holding the files back to back)."""
+        cprog, keep = program.to_c()
+        self.program, self._keep = program, keep
+        return self._png_call(self.L.svgr_render_png, (self.ctx, C.byref(cprog), self._stream(stream)),
+                              len(program.canvases), program.canvas_bytes, out, timing)
+
+    def render_resident_png(self, out=None, timing: bool = False, stream=None):
+        if self.program is None:
+            raise ValueError("no program resident: call render() / render_png() first")
+        return self._png_call(self.L.svgr_render_resident_png, (self.ctx, self._stream(stream)),
+                              len(self.program.canvases), self.program.canvas_bytes, out, timing)
+
+    def png_encode(self, images):
+        """PNG-encode host RGBA8 images (list of (rows, cols, 4) uint8 arrays) on the device -> list of bytes."""
+        images = [np.ascontiguousarray(im, dtype=np.uint8) for im in images]
+        for im in images:
+            if im.ndim != 3 or im.shape[2] != 4:
+                raise ValueError("png_encode expects (rows, cols, 4) uint8 images")
+        if not images:
+            return []
+        flat = np.concatenate([im.reshape(-1) for im in images])
+        rows = np.asarray([im.shape[0] for im in images], dtype=np.int32)
+        cols = np.asarray([im.shape[1] for im in images], dtype=np.int32)
+        offsets = np.zeros(len(images) + 1, dtype=np.int64)
+        out = np.empty(flat.nbytes // 2 + 4096 * len(images) + 65536, dtype=np.uint8)
+        for attempt in range(2):
+            rc = self.L.svgr_png_encode(self.ctx, flat.ctypes.data, len(images), rows.ctypes.data, cols.ctypes.data,
+                                        out.ctypes.data, out.nbytes, offsets.ctypes.data)
+            if rc == _lib.E_NOMEM and attempt == 0 and offsets[-1] > out.nbytes:
+                out = np.empty(int(offsets[-1]), dtype=np.uint8)
+                continue
+            self._check(rc)
+            break
+        return [out[offsets[i]: offsets[i + 1]].tobytes() for i in range(len(images))]
+
     def canvas(self, program: Program, raw: np.ndarray, index: int = 0) -> np.ndarray:
         _node, off, rows, cols = program.canvases[index]
         return raw[off: off + 4 * rows * cols].reshape(rows, cols, 4)
