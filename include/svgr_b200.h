@@ -262,6 +262,72 @@ int64_t svgr_arc_to_cubics(double cx, double cy, double rx, double ry, double ph
 int64_t svgr_expand_arcs(const uint8_t *tags, const double *data, int64_t n, uint8_t *out_tags, double *out_data,
                          int64_t cap, int64_t *new_index);
 
+/* ---- native scene encoder (csrc/encode_flat.cpp): the walk of Scene.render (svgrasterize.py:649-752) over flat
+ * scene arrays -> a scene program.  The arrays are what svgrasterize_b200/_flatten.c reads out of the reference's own
+ * Scene / Path / paint / Transform objects; many scenes share one set of tables (a batch). */
+typedef struct svgr_flat_paint {
+    int32_t kind;          /* 1 solid, 2 linear gradient, 3 radial gradient */
+    int32_t spread;        /* 0 pad, 1 repeat, 2 reflect */
+    int32_t bbox_units;    /* objectBoundingBox units: not covered, the scene takes the Python encoder */
+    int32_t lin;           /* paint.linear_rgb: -1 None, 0, 1 */
+    int32_t has_transform; /* 1: inv holds the inverse gradientTransform */
+    int32_t stop_off, stop_cnt;
+    int32_t focal;         /* radial: bit0 fcenter given, bit1 fradius given */
+    double p[8];           /* solid: r g b a | linear: p0x p0y p1x p1y | radial: cx cy r fx fy fr */
+    double inv[6];         /* inverse gradientTransform, 2 x 3 row-major (numpy's: Transform.invert) */
+} svgr_flat_paint;
+typedef struct svgr_flat_stop {
+    double offset;
+    double color[4]; /* premultiplied linear RGBA */
+} svgr_flat_stop;
+typedef struct svgr_flat_node {
+    int32_t tag; /* RENDER_* (svgrasterize.py:576-583): 0 fill (a path, b paint or -1, c rule 0 nonzero / 1 evenodd),
+                    1 stroke (a path, b paint, c cap 0 butt 1 round 2 square, d join 0 miter 1 round 2 bevel 3 other,
+                    f[0] width), 2 group, 3 opacity (f[0]), 4 clip / 5 mask (children target, other; a = bbox units),
+                    6 transform (a = index into tr), 7 filter (not covered) */
+    int32_t a, b, c, d;
+    int32_t child_off, child_cnt;
+    int32_t pad;
+    double f[2];
+} svgr_flat_node;
+typedef struct svgr_flat_scene {
+    int32_t root;          /* node index */
+    int32_t width, height; /* canvas size: main() renders with viewport [0, 0, height, width] (:3857-3861) */
+    int32_t linear_rgb;
+} svgr_flat_scene;
+typedef struct svgr_flat {
+    int64_t n_seg;
+    const uint8_t *seg_tag;  /* PATH_* tags; arcs are expanded by the encoder */
+    const double *seg_data;  /* n_seg x 8 */
+    int32_t n_sub;
+    const int32_t *sub_off;  /* n_sub + 1: sub-path -> segments (empty sub-paths already dropped) */
+    int32_t n_path;
+    const int32_t *path_off; /* n_path + 1: path -> sub-paths */
+    int32_t n_tr;
+    const double *tr;        /* n_tr x 6: 2 x 3 row-major matrices of the transform nodes */
+    int32_t n_paint;
+    const svgr_flat_paint *paints;
+    int32_t n_stop;
+    const svgr_flat_stop *stops;
+    int32_t n_node;
+    const svgr_flat_node *nodes;
+    int32_t n_child;
+    const int32_t *children;
+    int32_t n_scene;
+    const svgr_flat_scene *scenes;
+} svgr_flat;
+typedef struct svgr_encoded svgr_encoded;
+/* Encodes every scene of `in` (in order, one canvas each) into one program owned by the returned handle (also
+ * returned on failure, for svgr_encoded_error; free it with svgr_encoded_free).  SVGR_E_UNSUPPORTED: a scene uses
+ * a feature this encoder leaves to the Python one. */
+int svgr_encode_flat(const svgr_flat *in, svgr_encoded **out);
+const svgr_program *svgr_encoded_program(const svgr_encoded *e);
+const char *svgr_encoded_error(const svgr_encoded *e);
+/* canvases: 4 int64 per scene (canvas node, byte offset in the output, rows, cols); roots: the scenes' root nodes;
+ * returns the number of scenes */
+int64_t svgr_encoded_canvases(const svgr_encoded *e, const int64_t **canvases, const int32_t **roots);
+void svgr_encoded_free(svgr_encoded *e);
+
 /* ---- eager element-wise entry points of the reference's call surface.  Host pointers in and
  * out; every call copies up, launches one kernel on the context's stream and copies down (one synchronisation). */
 

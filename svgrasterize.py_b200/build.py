@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsvgr_b200.so")
 SOURCES = ["engine.cu", "k_flatten.cu", "k_stroke.cu", "k_coverage.cu", "k_compose.cu", "k_filters.cu",
-           "k_stencil_tma.cu", "k_png.cu"]
+           "k_stencil_tma.cu", "k_png.cu", "encode_flat.cpp"]
 HEADERS = ["svgr_types.h", "svgr_kernels.h", "svgr_device.cuh", os.path.join("..", "..", "include", "svgr_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -55,7 +55,7 @@ def build(force: bool = False, verbose: bool = False, lib: str = LIB) -> str:
     procs = []
     os.makedirs(os.path.join(CSRC, "build"), exist_ok=True)
     for src in SOURCES:
-        obj = os.path.join(CSRC, "build", src[:-3] + ".o")
+        obj = os.path.join(CSRC, "build", os.path.splitext(src)[0] + ".o")
         cmd = [nvcc, *NVCC_FLAGS, f"-fmad={FMAD.get(src, 'false')}", *EXTRA, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")

@@ -1,0 +1,570 @@
+// encode_flat.cpp -- the scene encoder in native code.
+//
+// The walk Scene.render makes over a scene tree (svgrasterize.py:649-752), which svgrasterize_b200/encode.py
+// restates in Python to *record* a scene program instead of rendering, done here on flat scene arrays
+// (include/svgr_b200.h: svgr_flat).  Python at ~1.3 ms per icon per core was 90 % of the wall time of a 100 000
+// icon job; this walk costs a few microseconds per icon.  The arrays come from svgrasterize_b200/_flatten.c, a
+// CPython extension that reads the reference's own Scene / Path / paint / Transform objects directly.
+//
+// Covered: fills and strokes with solid, linear and radial (incl. two-circle) paints in user space, groups,
+// opacity, transforms, clip paths and luminance masks.  Scenes that use objectBoundingBox units, pattern paints or
+// filters are encoded by encode.py (the flattener flags them), whose output this code reproduces record for
+// record on everything it does cover (tests/test_host_logic.py::test_native_encoder_*).
+//
+// Arithmetic: matrix products follow numpy's 3 x 3 matmul rounding (fma(a2, b2, fma(a1, b1, a0 b0)), measured),
+// small dots numpy's (fma(u1, v1, u0 v0)).  The inverse of a composed transform is an LU solve with partial
+// pivoting like numpy's (LAPACK gesv): identical for the scale / swap / translate transforms of real documents,
+// within an ulp of it for general matrices (the Python encoder remains the bit-exact path for those).
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/svgr_b200.h"
+#include "svgr_types.h"
+
+extern "C" int64_t svgr_arc_to_cubics(double cx, double cy, double rx, double ry, double phi, double eta, double eta_delta,
+                                      double *out, int64_t cap);
+
+namespace {
+
+enum { R_FILL = 0, R_STROKE = 1, R_GROUP = 2, R_OPACITY = 3, R_CLIP = 4, R_MASK = 5, R_TRANSFORM = 6, R_FILTER = 7 };
+
+struct M23 {
+    double m[6];  // row-major 2 x 3; the third row is (0, 0, 1)
+};
+
+// numpy: a @ b for 3 x 3 float64 (measured on this OpenBLAS: fma(a2, b2, fma(a1, b1, a0 * b0)) per element)
+M23 matmul(const M23 &a, const M23 &b)
+{
+    M23 c;
+    for (int i = 0; i < 2; i++) {
+        const double a0 = a.m[3 * i], a1 = a.m[3 * i + 1], a2 = a.m[3 * i + 2];
+        c.m[3 * i + 0] = fma(a2, 0.0, fma(a1, b.m[3], a0 * b.m[0]));
+        c.m[3 * i + 1] = fma(a2, 0.0, fma(a1, b.m[4], a0 * b.m[1]));
+        c.m[3 * i + 2] = fma(a2, 1.0, fma(a1, b.m[5], a0 * b.m[2]));
+    }
+    return c;
+}
+
+// np.linalg.inv of the 3 x 3 affine matrix: LU with partial pivoting, columns of the identity solved one by one
+// (right-looking elimination, multipliers scaled by the reciprocal pivot, fused substitution steps)
+bool invert(const M23 &t, M23 &out)
+{
+    double a[3][3] = {{t.m[0], t.m[1], t.m[2]}, {t.m[3], t.m[4], t.m[5]}, {0.0, 0.0, 1.0}};
+    int perm[3] = {0, 1, 2};
+    for (int k = 0; k < 3; k++) {
+        int p = k;
+        for (int i = k + 1; i < 3; i++)
+            if (fabs(a[i][k]) > fabs(a[p][k]))
+                p = i;
+        if (a[p][k] == 0.0)
+            return false;
+        if (p != k) {
+            for (int j = 0; j < 3; j++) {
+                const double tmp = a[k][j];
+                a[k][j] = a[p][j], a[p][j] = tmp;
+            }
+            const int tp = perm[k];
+            perm[k] = perm[p], perm[p] = tp;
+        }
+        const double rp = 1.0 / a[k][k];
+        for (int i = k + 1; i < 3; i++)
+            a[i][k] = a[i][k] * rp;
+        for (int i = k + 1; i < 3; i++)
+            for (int j = k + 1; j < 3; j++)
+                a[i][j] = a[i][j] - a[i][k] * a[k][j];
+    }
+    double x[3][3];
+    for (int c = 0; c < 3; c++) {
+        double y[3];
+        for (int i = 0; i < 3; i++)
+            y[i] = perm[i] == c ? 1.0 : 0.0;
+        for (int i = 0; i < 3; i++)
+            for (int q = 0; q < i; q++)
+                y[i] = fma(-a[i][q], y[q], y[i]);
+        for (int i = 2; i >= 0; i--) {
+            for (int q = i + 1; q < 3; q++)
+                y[i] = fma(-a[i][q], y[q], y[i]);
+            y[i] = y[i] * (1.0 / a[i][i]);
+        }
+        for (int i = 0; i < 3; i++)
+            x[i][c] = y[i];
+    }
+    for (int i = 0; i < 2; i++)
+        for (int j = 0; j < 3; j++)
+            out.m[3 * i + j] = x[i][j];
+    return true;
+}
+
+// color.py paint_to_srgb: premultiplied linear RGBA -> premultiplied sRGB RGBA
+void paint_to_srgb(const double *c, double *o)
+{
+    double r = c[0], g = c[1], b = c[2], a = c[3];
+    if (a > 0.0001)
+        r = r / a, g = g / a, b = b / a;
+    auto clip = [](double v) { return fmin(fmax(v, 0.0), 1.0); };
+    r = clip(r), g = clip(g), b = clip(b), a = clip(a);
+    auto enc = [](double v) { return v <= 0.0031308 ? v * 12.92 : 1.055 * pow(v, 1.0 / 2.4) - 0.055; };
+    o[0] = enc(r) * a, o[1] = enc(g) * a, o[2] = enc(b) * a, o[3] = a;
+}
+
+struct Canvas {
+    int32_t node;
+    int64_t off;
+    int32_t rows, cols;
+};
+
+}  // namespace
+
+struct svgr_encoded {
+    std::vector<uint8_t> seg_tag, stroke_tag;
+    std::vector<double> seg_data, stroke_data;
+    std::vector<uint32_t> seg_path;
+    std::vector<PathRec> paths;
+    std::vector<StrokeRec> strokes;
+    std::vector<int32_t> stroke_sub_off, stroke_sub_job, stroke_seg_job;
+    std::vector<PaintRec> paints;
+    std::vector<StopRec> stops;
+    std::vector<svgr_node> nodes;
+    std::vector<int32_t> children;
+    std::vector<int64_t> canvases;  // node, byte offset, rows, cols per canvas
+    std::vector<int32_t> roots;
+    int32_t n_focal = 0;
+    int64_t canvas_bytes = 0;
+    svgr_program prog;
+    std::string err;
+    int err_code = SVGR_OK;
+};
+
+namespace {
+
+struct Encoder {
+    const svgr_flat &in;
+    svgr_encoded &out;
+    // per path of the input: its segments with arcs expanded, built on first use
+    struct FlatPath {
+        bool ready = false;
+        std::vector<uint8_t> tag;
+        std::vector<double> data;
+        std::vector<int32_t> sub_off;  // relative to the path's first segment
+    };
+    std::vector<FlatPath> path_cache;
+    std::vector<int32_t> kid_stack;
+
+    Encoder(const svgr_flat &i, svgr_encoded &o) : in(i), out(o), path_cache((size_t)i.n_path) { out.stroke_sub_off.push_back(0); }
+
+    bool fail(int code, const char *msg)
+    {
+        if (out.err_code == SVGR_OK)
+            out.err_code = code, out.err = msg;
+        return false;
+    }
+
+    int node(int tag, int a = 0, int b = 0, int c = 0, int d = 0, const int32_t *kids = nullptr, int n_kids = 0, int flags = 0,
+             double f0 = 0.0, double f1 = 0.0, double f2 = 0.0, double f3 = 0.0)
+    {
+        svgr_node n;
+        n.tag = tag, n.a = a, n.b = b, n.c = c, n.d = d;
+        n.child_off = (int32_t)out.children.size(), n.child_cnt = n_kids, n.flags = flags;
+        n.f[0] = f0, n.f[1] = f1, n.f[2] = f2, n.f[3] = f3;
+        for (int k = 0; k < n_kids; k++)
+            out.children.push_back(kids[k]);
+        out.nodes.push_back(n);
+        return (int)out.nodes.size() - 1;
+    }
+    int empty() { return node(SVGR_N_EMPTY); }
+    bool is_empty(int n) const { return out.nodes[(size_t)n].tag == SVGR_N_EMPTY; }
+
+    // encode.py device_path: sub-path structure with arcs expanded to cubics (arc_to_bezier3, :2355)
+    const FlatPath *flat_path(int pid)
+    {
+        if (pid < 0 || pid >= in.n_path) {
+            fail(SVGR_E_INVALID, "flat scene: path index out of range");
+            return nullptr;
+        }
+        FlatPath &fp = path_cache[(size_t)pid];
+        if (fp.ready)
+            return &fp;
+        fp.sub_off.push_back(0);
+        for (int s = in.path_off[pid]; s < in.path_off[pid + 1]; s++) {
+            for (int i = in.sub_off[s]; i < in.sub_off[s + 1]; i++) {
+                const double *d = in.seg_data + 8 * (size_t)i;
+                if (in.seg_tag[i] == SEG_ARC) {
+                    double buf[64 * 8];
+                    const int64_t k = svgr_arc_to_cubics(d[0], d[1], d[2], d[3], d[4], d[5], d[6], buf, 64);
+                    if (k < 0) {
+                        fail(SVGR_E_INVALID, "arc sweeps more than 16 pi");
+                        return nullptr;
+                    }
+                    for (int64_t j = 0; j < k; j++) {
+                        fp.tag.push_back(SEG_CUBIC);
+                        fp.data.insert(fp.data.end(), buf + 8 * j, buf + 8 * j + 8);
+                    }
+                } else {
+                    fp.tag.push_back(in.seg_tag[i]);
+                    fp.data.insert(fp.data.end(), d, d + 8);
+                }
+            }
+            fp.sub_off.push_back((int32_t)fp.tag.size());
+        }
+        fp.ready = true;
+        return &fp;
+    }
+
+    int add_path_rec(const M23 &t, const int32_t *viewport, int rule)
+    {
+        PathRec p;
+        memset(&p, 0, sizeof p);
+        memcpy(p.m, t.m, sizeof p.m);
+        if (viewport) {
+            p.has_viewport = 1;
+            memcpy(p.viewport, viewport, sizeof p.viewport);
+        }
+        p.fill_rule = rule;
+        out.paths.push_back(p);
+        return (int)out.paths.size() - 1;
+    }
+
+    int add_fill_path(int path, const M23 &t, int rule, const int32_t *viewport)
+    {
+        const FlatPath *fp = flat_path(path);
+        if (!fp)
+            return -1;
+        const int pid = add_path_rec(t, viewport, rule);
+        out.seg_tag.insert(out.seg_tag.end(), fp->tag.begin(), fp->tag.end());
+        out.seg_data.insert(out.seg_data.end(), fp->data.begin(), fp->data.end());
+        out.seg_path.insert(out.seg_path.end(), fp->tag.size(), (uint32_t)pid);
+        return pid;
+    }
+
+    int add_stroke_path(int path, const M23 &t, double width, int cap, int join, const int32_t *viewport)
+    {
+        const FlatPath *fp = flat_path(path);
+        if (!fp)
+            return -1;
+        const int pid = add_path_rec(t, viewport, 0);
+        const int job = (int)out.strokes.size();
+        const int sub_begin = (int)out.stroke_sub_job.size();
+        const int n_sub = (int)fp->sub_off.size() - 1;
+        const int32_t base = (int32_t)out.stroke_tag.size();
+        for (int s = 1; s <= n_sub; s++)
+            out.stroke_sub_off.push_back(fp->sub_off[(size_t)s] + base);
+        out.stroke_sub_job.insert(out.stroke_sub_job.end(), (size_t)n_sub, job);
+        out.stroke_tag.insert(out.stroke_tag.end(), fp->tag.begin(), fp->tag.end());
+        out.stroke_data.insert(out.stroke_data.end(), fp->data.begin(), fp->data.end());
+        out.stroke_seg_job.insert(out.stroke_seg_job.end(), fp->tag.size(), job);
+        StrokeRec r;
+        memset(&r, 0, sizeof r);
+        r.half_width = width / 2, r.sub_begin = sub_begin, r.sub_end = sub_begin + n_sub, r.cap = cap, r.join = join, r.path = pid;
+        out.strokes.push_back(r);
+        return pid;
+    }
+
+    int paint_record(PaintRec &rec)
+    {
+        out.paints.push_back(rec);
+        return (int)out.paints.size() - 1;
+    }
+
+    // Path.fill / Path.mask on path `pid` (svgrasterize.py:995-1103; encode.py _leaf)
+    int leaf(int pid, int paint, const M23 &t, bool mask_only, bool linear_rgb)
+    {
+        if (mask_only)
+            return node(SVGR_N_LEAF, pid, -1, 1, -1);
+        if (paint < 0)
+            return empty();
+        if (paint >= in.n_paint) {
+            fail(SVGR_E_INVALID, "flat scene: paint index out of range");
+            return -1;
+        }
+        const svgr_flat_paint &p = in.paints[paint];
+        PaintRec rec;
+        memset(&rec, 0, sizeof rec);
+        rec.pat_node = -1;
+        if (p.kind == 1) {
+            double c[4];
+            if (linear_rgb)
+                memcpy(c, p.p, sizeof c);
+            else
+                paint_to_srgb(p.p, c);
+            rec.kind = PAINT_SOLID;
+            for (int k = 0; k < 4; k++)
+                rec.color[k] = (float)c[k];
+            return node(SVGR_N_LEAF, pid, paint_record(rec), linear_rgb ? 1 : 0, -1);
+        }
+        if (p.kind != 2 && p.kind != 3) {
+            fail(SVGR_E_UNSUPPORTED, "flat scene: paint kind needs the Python encoder");
+            return -1;
+        }
+        if (p.bbox_units) {
+            fail(SVGR_E_UNSUPPORTED, "flat scene: objectBoundingBox paint needs the Python encoder");
+            return -1;
+        }
+        if (p.spread < 0 || p.spread > 2) {
+            fail(SVGR_E_INVALID, "invalid spread method");
+            return -1;
+        }
+        const bool lin = p.lin < 0 ? linear_rgb : (p.lin != 0);
+        // stops in the target colour space (grad_stops_colorspace, :1686) + the reciprocal spans
+        if (p.stop_cnt < 1 || p.stop_off < 0 || p.stop_off + p.stop_cnt > in.n_stop) {
+            fail(SVGR_E_INVALID, "gradient without stops");
+            return -1;
+        }
+        rec.spread = p.spread, rec.stop_off = (int32_t)out.stops.size(), rec.stop_cnt = p.stop_cnt;
+        for (int k = 0; k < p.stop_cnt; k++) {
+            const svgr_flat_stop &s = in.stops[p.stop_off + k];
+            double c[4];
+            if (lin)
+                memcpy(c, s.color, sizeof c);
+            else
+                paint_to_srgb(s.color, c);
+            StopRec sr;
+            memset(&sr, 0, sizeof sr);
+            sr.offset = s.offset;
+            for (int q = 0; q < 4; q++)
+                sr.color[q] = (float)c[q];
+            sr.inv_span = k + 1 < p.stop_cnt ? 1.0 / (in.stops[p.stop_off + k + 1].offset - s.offset) : 0.0;
+            out.stops.push_back(sr);
+        }
+        // pixel centre -> gradient space: transform.invert, then the inverse gradientTransform (:1022-1031, :1558)
+        M23 to_user;
+        if (!invert(t, to_user)) {
+            fail(SVGR_E_INVALID, "Singular matrix");
+            return -1;
+        }
+        if (p.has_transform) {
+            M23 gi;
+            memcpy(gi.m, p.inv, sizeof gi.m);
+            to_user = matmul(gi, to_user);
+        }
+        const double A00 = to_user.m[0], A01 = to_user.m[1], T0 = to_user.m[2];
+        const double A10 = to_user.m[3], A11 = to_user.m[4], T1 = to_user.m[5];
+        if (p.kind == 2) {
+            const double v0 = p.p[2] - p.p[0], v1 = p.p[3] - p.p[1];
+            const double vv = fma(v1, v1, v0 * v0);
+            rec.kind = PAINT_LINEAR;
+            rec.g[0] = fma(v1, A10, v0 * A00) / vv;
+            rec.g[1] = fma(v1, A11, v0 * A01) / vv;
+            const double d0 = T0 - p.p[0], d1 = T1 - p.p[1];
+            rec.g[2] = fma(d1, v1, d0 * v0) / vv;
+        } else if (!(p.focal & 3)) {
+            const double r = p.p[2];
+            rec.kind = PAINT_RADIAL;
+            rec.m1[0] = A00 / r, rec.m1[1] = A01 / r, rec.m1[3] = A10 / r, rec.m1[4] = A11 / r;
+            rec.m1[2] = (T0 - p.p[0]) / r, rec.m1[5] = (T1 - p.p[1]) / r;
+        } else {
+            const double cx = p.p[0], cy = p.p[1], r = p.p[2];
+            const double fx = (p.focal & 1) ? p.p[3] : cx, fy = (p.focal & 1) ? p.p[4] : cy;
+            const double fr = (p.focal & 2) ? p.p[5] : 0.0;
+            const double cd0 = cx - fx, cd1 = cy - fy, rd = r - fr;
+            const double a = (cd0 * cd0 + cd1 * cd1) - rd * rd;
+            rec.kind = PAINT_RADIAL_FOCAL;
+            rec.m1[0] = A00, rec.m1[1] = A01, rec.m1[3] = A10, rec.m1[4] = A11;
+            rec.m1[2] = T0 - fx, rec.m1[5] = T1 - fy;
+            rec.g[0] = cd0, rec.g[1] = cd1, rec.g[2] = fr * rd, rec.g[3] = a, rec.g[4] = fr * fr;
+            rec.g[5] = fr / (fr - r), rec.g[6] = fr != r ? 1.0 : 0.0, rec.g[7] = 1.0 / a;
+            rec.flag = out.n_focal++;
+        }
+        return node(SVGR_N_LEAF, pid, paint_record(rec), lin ? 1 : 0, -1);
+    }
+
+    // Scene.render (svgrasterize.py:649-752; encode.py Encoder.encode)
+    int encode(int ni, const M23 &t, bool mask_only, const int32_t *viewport, bool linear_rgb, int depth = 0)
+    {
+        if (out.err_code != SVGR_OK)
+            return -1;
+        if (ni < 0 || ni >= in.n_node || depth > 4096) {
+            fail(SVGR_E_INVALID, "flat scene: node index out of range / tree too deep");
+            return -1;
+        }
+        const svgr_flat_node &n = in.nodes[ni];
+        if (n.child_off < 0 || n.child_cnt < 0 || (int64_t)n.child_off + n.child_cnt > in.n_child) {
+            fail(SVGR_E_INVALID, "flat scene: child range outside the children table");
+            return -1;
+        }
+        const int32_t *kids = in.children + n.child_off;
+        const int lin = linear_rgb ? 1 : 0;
+        switch (n.tag) {
+        case R_FILL: {
+            if (!mask_only && n.b < 0)
+                return empty();
+            if (n.c < 0 || n.c > 1) {
+                fail(SVGR_E_INVALID, "Invalid fill rule");
+                return -1;
+            }
+            const int pid = add_fill_path(n.a, t, n.c, viewport);
+            return pid < 0 ? -1 : leaf(pid, n.b, t, mask_only, linear_rgb);
+        }
+        case R_STROKE: {
+            if (n.c < 0) {
+                fail(SVGR_E_INVALID, "unkown line cap type");
+                return -1;
+            }
+            if (!mask_only && n.b < 0)
+                return empty();
+            const int pid = add_stroke_path(n.a, t, n.f[0], n.c, n.d, viewport);
+            return pid < 0 ? -1 : leaf(pid, n.b, t, mask_only, linear_rgb);
+        }
+        case R_GROUP: {
+            const size_t base = kid_stack.size();
+            for (int k = 0; k < n.child_cnt; k++) {
+                const int kid = encode(kids[k], t, mask_only, viewport, linear_rgb, depth + 1);
+                if (kid < 0)
+                    return -1;
+                if (!is_empty(kid))
+                    kid_stack.push_back(kid);
+            }
+            const int cnt = (int)(kid_stack.size() - base);
+            int res;
+            if (cnt == 0)
+                res = empty();
+            else if (cnt == 1)
+                res = kid_stack[base];
+            else
+                res = node(SVGR_N_GROUP, 0, 0, 0, 0, kid_stack.data() + base, cnt, lin);
+            kid_stack.resize(base);
+            return res;
+        }
+        case R_OPACITY: {
+            if (n.child_cnt != 1)
+                break;
+            const int tn = encode(kids[0], t, mask_only, viewport, linear_rgb, depth + 1);
+            if (tn < 0 || is_empty(tn))
+                return tn;
+            const int32_t c[1] = {tn};
+            return node(SVGR_N_OPACITY, 0, 0, 0, 0, c, 1, lin, n.f[0]);
+        }
+        case R_TRANSFORM: {
+            if (n.child_cnt != 1 || n.a < 0 || n.a >= in.n_tr)
+                break;
+            M23 tr;
+            memcpy(tr.m, in.tr + 6 * (size_t)n.a, sizeof tr.m);
+            return encode(kids[0], matmul(t, tr), mask_only, viewport, linear_rgb, depth + 1);
+        }
+        case R_CLIP:
+        case R_MASK: {
+            if (n.child_cnt != 2)
+                break;
+            const int tn = encode(kids[0], t, mask_only, viewport, linear_rgb, depth + 1);
+            if (tn < 0 || is_empty(tn))
+                return tn;
+            if (n.a) {
+                fail(SVGR_E_UNSUPPORTED, "flat scene: objectBoundingBox clip / mask needs the Python encoder");
+                return -1;
+            }
+            int stencil;
+            if (n.tag == R_CLIP) {
+                stencil = encode(kids[1], t, true, viewport, linear_rgb, depth + 1);
+                if (stencil < 0 || is_empty(stencil))
+                    return stencil;
+            } else {
+                const int sub = encode(kids[1], t, mask_only, viewport, linear_rgb, depth + 1);
+                if (sub < 0 || is_empty(sub))
+                    return sub;
+                const int32_t c[1] = {sub};
+                stencil = node(SVGR_N_LUMA, 0, 0, 0, 0, c, 1, lin);
+            }
+            const int32_t c[2] = {stencil, tn};
+            return node(SVGR_N_IN, 0, 0, 0, 0, c, 2, lin);
+        }
+        case R_FILTER:
+            fail(SVGR_E_UNSUPPORTED, "flat scene: filters need the Python encoder");
+            return -1;
+        default:
+            fail(SVGR_E_INVALID, "unhandled scene type");
+            return -1;
+        }
+        fail(SVGR_E_INVALID, "flat scene: malformed node");
+        return -1;
+    }
+
+    // main() of the reference (svgrasterize.py:3854-3881; encode.py add_scene)
+    bool add_scene(const svgr_flat_scene &sc)
+    {
+        const M23 swap = {{0.0, 1.0, 0.0, 1.0, 0.0, 0.0}};  // the x / y swap every render starts from (:246, :3823)
+        const int32_t viewport[4] = {0, 0, sc.height, sc.width};
+        const int root = encode(sc.root, swap, false, viewport, sc.linear_rgb != 0);
+        if (root < 0)
+            return false;
+        int nd;
+        if (is_empty(root)) {
+            nd = node(SVGR_N_CANVAS, sc.height, sc.width, 0, 0, nullptr, 0, sc.linear_rgb ? 1 : 0, (double)out.canvas_bytes);
+        } else {
+            const int32_t c[1] = {root};
+            nd = node(SVGR_N_CANVAS, sc.height, sc.width, 0, 0, c, 1, sc.linear_rgb ? 1 : 0, (double)out.canvas_bytes);
+        }
+        out.canvases.push_back(nd), out.canvases.push_back(out.canvas_bytes);
+        out.canvases.push_back(sc.height), out.canvases.push_back(sc.width);
+        out.canvas_bytes += 4ll * sc.height * sc.width;
+        out.roots.push_back(root);
+        return true;
+    }
+};
+
+}  // namespace
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+int svgr_encode_flat(const svgr_flat *in, svgr_encoded **out_handle)
+{
+    if (!in || !out_handle)
+        return SVGR_E_INVALID;
+    svgr_encoded *e = new svgr_encoded();
+    *out_handle = e;
+    if (in->n_path < 0 || in->n_sub < 0 || in->n_seg < 0 || in->n_node < 0 || in->n_scene < 0 || in->n_paint < 0 ||
+        in->n_stop < 0 || in->n_child < 0 || in->n_tr < 0) {
+        e->err_code = SVGR_E_INVALID, e->err = "flat scene: negative count";
+        return e->err_code;
+    }
+    for (int p = 0; p < in->n_path; p++)
+        if (in->path_off[p] < 0 || in->path_off[p] > in->path_off[p + 1] || in->path_off[p + 1] > in->n_sub) {
+            e->err_code = SVGR_E_INVALID, e->err = "flat scene: path offsets outside the sub-path table";
+            return e->err_code;
+        }
+    for (int s = 0; s < in->n_sub; s++)
+        if (in->sub_off[s] < 0 || in->sub_off[s] > in->sub_off[s + 1] || in->sub_off[s + 1] > in->n_seg) {
+            e->err_code = SVGR_E_INVALID, e->err = "flat scene: sub-path offsets outside the segments";
+            return e->err_code;
+        }
+    Encoder enc(*in, *e);
+    for (int s = 0; s < in->n_scene; s++)
+        if (!enc.add_scene(in->scenes[s]))
+            return e->err_code;
+    svgr_program &p = e->prog;
+    memset(&p, 0, sizeof p);
+    p.n_seg = (int64_t)e->seg_tag.size(), p.seg_tag = e->seg_tag.data(), p.seg_data = e->seg_data.data(), p.seg_path = e->seg_path.data();
+    p.n_path = (int32_t)e->paths.size(), p.paths = e->paths.data();
+    p.n_stroke = (int32_t)e->strokes.size(), p.strokes = e->strokes.data();
+    p.n_stroke_sub = (int32_t)e->stroke_sub_job.size(), p.stroke_sub_off = e->stroke_sub_off.data(), p.stroke_sub_job = e->stroke_sub_job.data();
+    p.n_stroke_seg = (int64_t)e->stroke_tag.size(), p.stroke_tag = e->stroke_tag.data(), p.stroke_data = e->stroke_data.data();
+    p.stroke_seg_job = e->stroke_seg_job.data();
+    p.n_paint = (int32_t)e->paints.size(), p.paints = e->paints.data();
+    p.n_stop = (int32_t)e->stops.size(), p.stops = e->stops.data();
+    p.n_focal = e->n_focal;
+    p.n_node = (int32_t)e->nodes.size(), p.nodes = e->nodes.data();
+    p.n_child = (int32_t)e->children.size(), p.children = e->children.data();
+    p.canvas_bytes = e->canvas_bytes;
+    return SVGR_OK;
+}
+
+const svgr_program *svgr_encoded_program(const svgr_encoded *e) { return e ? &e->prog : nullptr; }
+const char *svgr_encoded_error(const svgr_encoded *e) { return e ? e->err.c_str() : "null handle"; }
+/* canvases: 4 int64 per canvas (node, byte offset, rows, cols); roots: one node index per scene */
+int64_t svgr_encoded_canvases(const svgr_encoded *e, const int64_t **canvases, const int32_t **roots)
+{
+    if (!e)
+        return 0;
+    if (canvases)
+        *canvases = e->canvases.data();
+    if (roots)
+        *roots = e->roots.data();
+    return (int64_t)e->roots.size();
+}
+void svgr_encoded_free(svgr_encoded *e) { delete e; }
+
+#pragma GCC visibility pop
+}

@@ -6,34 +6,42 @@
 // (8-bit RGBA, one IDAT) and decode to exactly the canvas bytes; they are not the reference's bytes (different
 // filter and deflate strategy) -- the byte-identical path stays canvas_to_png's default.
 //
-//   filter     Paeth (type 4) on every row: flat areas and linear gradients become (near) zero residuals
+//   filter     Sub (type 1) on every row: one packed byte subtraction per pixel, no second row to read; flat
+//              areas become zeros, linear gradients near-constant small residuals.  (Paeth was measured first:
+//              files 3 % smaller, encoder 4 x slower -- 80 instructions per pixel wherever a gradient defeats
+//              its shortcuts.)
 //   LZ77       matches at distance 4 only (one pixel back in the residual stream), whole pixels, 1..64 pixels
 //              per match: a run of equal residual pixels -- what flat, anti-aliased vector art consists of
-//   Huffman    one dynamic block per segment (<= 256 work items of <= 256 pixels of a row): histogram ->
-//              length-limited code (15 bits) built by the segment's CTA -> canonical codes; the code lengths go
-//              out with a fixed 4-bit code-length code (no run-length symbols: 158 bytes of header per block)
+//   Huffman    one dynamic block per segment (<= 256 work items of <= 256 pixels of a row): histogram of every
+//              fourth item -> length-limited code (15 bits) built by the segment's CTA -> canonical codes; the
+//              code lengths go out with a fixed 4-bit code-length code (158 bytes of header per block)
 //   framing    segments end on a byte boundary (an empty stored block, zlib's sync-flush marker), so they
-//              concatenate by copying; zlib header, Adler-32 (combined from per-item sums), PNG chunks and their
-//              CRC-32 (per-thread table CRC + GF(2) shifts) are written by the packing kernels
+//              concatenate by copying; zlib header, Adler-32 (per-item sums by dp4a, combined), PNG chunks and
+//              their CRC-32 (per-thread table CRC + GF(2) shifts) are written by the packing kernel
 //
-// One CTA per segment does all of its passes back to back (walk 1: histogram + Adler, Huffman code, walk 2: bit
-// counts, scan, walk 3: emission); the filter is recomputed in every walk instead of being stored.
+// One CTA per segment; a warp takes an item at a time, 8 pixels per lane (two 16-byte loads): tokens are looked
+// up once and kept in registers as (bits, length) per pixel, a warp scan places the lanes' bits in a shared-memory
+// staging slot, the slot goes to the item's private area; when all items are done their offsets are known and
+// they are merged (shifted) behind the block header.
 #include <algorithm>
 
 #include "svgr_kernels.h"
 
 #define PNG_THREADS 256
+#define PNG_WARPS (PNG_THREADS / 32)
 #define PNG_ITEM_PX 256         // pixels of a row per work item
 #define PNG_NSYM 290            // 286 literal / length symbols + 4 distance symbols (codes 0..3)
 #define PNG_MAXBITS 15
 #define PNG_HEADER_BITS (3 + 5 + 5 + 4 + 19 * 3 + PNG_NSYM * 4)
+#define PNG_ITEM_WORDS 484      // words of an item's private slot: (4 * 256 + 1) bytes at <= 15 bits each (an item
+                                // the sample did not see may consist of the rarest symbols only)
 #define ADLER_MOD 65521u
 
 struct PngSeg {           // one deflate block
     int32_t canvas;       // index of the canvas
     int32_t row0, rows;   // rows of the canvas covered by the segment
     int32_t last;         // 1: last segment of its canvas (BFINAL)
-    int64_t slot;         // byte offset of the segment's worst-case slot in the scratch buffer
+    int64_t slot;         // byte offset of the segment's scratch (item slots, then the merged stream)
 };
 struct PngCanvas {
     int64_t src;          // byte offset of the RGBA8 canvas in the canvas buffer
@@ -49,122 +57,40 @@ __constant__ unsigned short c_len_extra[65]; // extra bits value
 __constant__ unsigned c_crc_table[256];
 __constant__ unsigned c_crc_pow[32];         // x^(8 * 2^k) mod P, reflected
 
-__device__ __forceinline__ int paeth(int a, int b, int c)
-{
-    const int p = a + b - c;
-    const int pa = abs(p - a), pb = abs(p - b), pc = abs(p - c);
-    return (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
-}
-
-// residual of pixel `cur` given its left, up and up-left neighbours (zero outside the image), bytes packed like
-// the pixel
-__device__ __forceinline__ unsigned residual(unsigned cur, unsigned left, unsigned up, unsigned ul)
-{
-    unsigned r = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int sh = 8 * k;
-        const int x = (cur >> sh) & 255, a = (left >> sh) & 255, b = (up >> sh) & 255, c = (ul >> sh) & 255;
-        r |= (unsigned)((x - paeth(a, b, c)) & 255) << sh;
-    }
-    return r;
-}
-
-// Walks one work item = pixels [c0, c1) of row `row` of a canvas and feeds its tokens to `sink`:
-//   sink.lit(byte), sink.match(n pixels).  ADLER: also accumulates the Adler-32 sums of the filtered bytes.
-template <bool ADLER, class Sink>
-__device__ __forceinline__ void walk_item(const unsigned *__restrict__ img, int cols, int row, int c0, int c1, Sink &sink,
-                                          unsigned &ad_a, unsigned &ad_b)
-{
-    const unsigned *cur_row = img + (size_t)row * cols;
-    const unsigned *up_row = row > 0 ? cur_row - cols : nullptr;
-    unsigned left = c0 > 0 ? cur_row[c0 - 1] : 0u;
-    unsigned ul = (up_row && c0 > 0) ? up_row[c0 - 1] : 0u;
-    if (c0 == 0) {
-        sink.lit(4);  // filter type byte: Paeth
-        if (ADLER)
-            ad_a += 4, ad_b += ad_a;
-    }
-    unsigned prev = 0;
-    int run = 0;  // pixels of the pending match
-    for (int c = c0; c < c1; c++) {
-        const unsigned cur = cur_row[c], up = up_row ? up_row[c] : 0u;
-        const unsigned r = residual(cur, left, up, ul);
-        left = cur, ul = up;
-        if (ADLER) {
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                ad_a += (r >> (8 * k)) & 255;
-                ad_b += ad_a;
-            }
-        }
-        if (c > c0 && r == prev) {
-            if (++run == 64) {
-                sink.match(64);
-                run = 0;
-            }
-            continue;
-        }
-        if (run) {
-            sink.match(run);
-            run = 0;
-        }
-        sink.lit(r & 255), sink.lit((r >> 8) & 255), sink.lit((r >> 16) & 255), sink.lit(r >> 24);
-        prev = r;
-    }
-    if (run)
-        sink.match(run);
-}
-
-struct HistSink {
-    unsigned *h;  // this warp's histogram
-    __device__ __forceinline__ void lit(unsigned b) { atomicAdd(h + b, 1u); }
-    __device__ __forceinline__ void match(int n)
-    {
-        atomicAdd(h + 257 + c_len_code[n], 1u);
-        atomicAdd(h + 286 + 3, 1u);
-    }
-};
-struct BitsSink {
-    const unsigned char *len;
-    unsigned bits;
-    __device__ __forceinline__ void lit(unsigned b) { bits += len[b]; }
-    __device__ __forceinline__ void match(int n) { bits += len[257 + c_len_code[n]] + c_len_ebits[n] + len[286 + 3]; }
-};
-struct EmitSink {
-    const unsigned char *len;
-    const unsigned short *code;
-    unsigned *out;             // the segment's slot as 32-bit words (zeroed)
-    unsigned long long acc;    // pending bits, LSB first
+// LSB-first bit writer into 32-bit words that start zeroed; the first and the last word of a writer may be shared
+// with its neighbours (atomicOr), the words in between are its own
+struct BitWriter {
+    unsigned *out;
+    unsigned long long acc;
     int nacc;
-    long long word;            // next word to write
+    long long word;
     bool first;
-    __device__ __forceinline__ void put(unsigned v, int n)
+    __device__ __forceinline__ void put(unsigned v, int n)  // n <= 32
     {
         acc |= (unsigned long long)v << nacc;
         nacc += n;
         if (nacc >= 32) {
             const unsigned w = (unsigned)acc;
             if (first)
-                atomicOr(out + word, w), first = false;  // shared with the item before
+                atomicOr(out + word, w), first = false;
             else
                 out[word] = w;
             word++, acc >>= 32, nacc -= 32;
         }
     }
-    __device__ __forceinline__ void lit(unsigned b) { put(code[b], len[b]); }
-    __device__ __forceinline__ void match(int n)
+    __device__ __forceinline__ void put64(unsigned long long v, int n)  // n <= 64
     {
-        const int s = 257 + c_len_code[n];
-        put(code[s], len[s]);
-        if (c_len_ebits[n])
-            put(c_len_extra[n], c_len_ebits[n]);
-        put(code[286 + 3], len[286 + 3]);
+        if (n > 32) {
+            put((unsigned)v, 32);
+            put((unsigned)(v >> 32), n - 32);
+        } else if (n > 0) {
+            put((unsigned)v, n);
+        }
     }
     __device__ __forceinline__ void finish()
     {
         if (nacc > 0)
-            atomicOr(out + word, (unsigned)acc);  // shared with the item after
+            atomicOr(out + word, (unsigned)acc);
     }
 };
 
@@ -179,137 +105,210 @@ __device__ __forceinline__ void adler_combine(unsigned &a, unsigned &b, unsigned
     b = (unsigned)nb;
 }
 
+// The 8 pixels of one lane of a work item (a warp covers the item's <= 256 pixels): Sub-filter residuals and the
+// token structure.
+struct LanePixels {
+    unsigned r[8];      // residuals, bytes packed like the pixel
+    unsigned lit;       // bit j: pixel j is a literal pixel (its residual differs from the pixel before)
+    unsigned valid;     // bit j: pixel j exists
+    int s_in;           // item-local index of the last literal pixel before this lane's pixels
+    unsigned next_lit;  // the pixel after this lane's last one is a literal (or the item ends there)
+};
+
+__device__ __forceinline__ void lane_pixels(const unsigned *__restrict__ img, int cols, int row, int c0, int c1, int lane,
+                                            LanePixels &px)
+{
+    const unsigned *cur_row = img + (size_t)row * cols;
+    const int p0 = c0 + 8 * lane;
+    const int nv = max(0, min(8, c1 - p0));
+    unsigned cur[8];
+    if (nv == 8 && ((reinterpret_cast<size_t>(cur_row + p0) & 15) == 0)) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(cur_row + p0)), b = __ldg(reinterpret_cast<const uint4 *>(cur_row + p0) + 1);
+        cur[0] = a.x, cur[1] = a.y, cur[2] = a.z, cur[3] = a.w, cur[4] = b.x, cur[5] = b.y, cur[6] = b.z, cur[7] = b.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            cur[j] = j < nv ? __ldg(cur_row + p0 + j) : 0u;
+    }
+    unsigned left = __shfl_up_sync(0xffffffffu, cur[7], 1);
+    if (lane == 0)
+        left = c0 > 0 ? __ldg(cur_row + c0 - 1) : 0u;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        px.r[j] = __vsub4(cur[j], left);  // per byte, modulo 256
+        left = cur[j];
+    }
+    unsigned prev = __shfl_up_sync(0xffffffffu, px.r[7], 1);
+    px.valid = nv >= 8 ? 0xffu : ((1u << nv) - 1u);
+    unsigned lit = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const bool first = lane == 0 && j == 0;  // nothing to repeat at the start of an item
+        if (first || px.r[j] != prev)
+            lit |= 1u << j;
+        prev = px.r[j];
+    }
+    px.lit = lit & px.valid;
+    // last literal pixel before this lane: inclusive max-scan of every lane's last literal index, shifted by one lane
+    int last = px.lit ? 8 * lane + (31 - __clz((int)px.lit)) : -1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, last, o);
+        if (lane >= o)
+            last = max(last, t);
+    }
+    px.s_in = __shfl_up_sync(0xffffffffu, last, 1);
+    if (lane == 0)
+        px.s_in = -1;
+    const unsigned mine = (px.valid & 1u) ? (px.lit & 1u) : 1u;
+    px.next_lit = __shfl_down_sync(0xffffffffu, mine, 1);
+    if (lane == 31)
+        px.next_lit = 1u;
+}
+
+// Token of pixel j of a lane: 0 nothing (inside a run), -1 a literal pixel, n > 0 a match of n pixels ending here
+// (a run of repeated residual pixels ends, or reaches 64 pixels).  `s` carries the last literal pixel's index.
+__device__ __forceinline__ int pixel_token(const LanePixels &px, int lane, int j, int &s)
+{
+    const int i = 8 * lane + j;
+    if (px.lit >> j & 1u) {
+        s = i;
+        return -1;
+    }
+    const int d = i - s;  // >= 1: pixels of the run so far
+    const bool last_of_lane = j == 7 || !(px.valid >> (j + 1) & 1u);
+    const bool run_ends = last_of_lane ? (j == 7 ? px.next_lit != 0u : true) : ((px.lit >> (j + 1)) & 1u) != 0u;
+    return ((d & 63) == 0 || run_ends) ? ((d - 1) & 63) + 1 : 0;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
-// one CTA per segment: histogram, code, bit counts, emission
+// one CTA per segment: sampled histogram -> code -> every item emitted into its own slot (warp per item, staged in
+// shared memory) -> items merged bit-exactly behind the block header into the segment's stream
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(PNG_THREADS)
 png_deflate_kernel(const PngSeg *__restrict__ segs, const PngCanvas *__restrict__ canvases,
                    const unsigned char *__restrict__ canvas_buf, unsigned char *__restrict__ scratch,
                    int *__restrict__ seg_bytes, unsigned *__restrict__ seg_adler /* a, b per segment */)
 {
-    __shared__ unsigned s_hist[PNG_THREADS / 32][PNG_NSYM + 6];
+    __shared__ unsigned s_hist[PNG_WARPS][PNG_NSYM + 6];
     __shared__ unsigned s_freq[PNG_NSYM];
     __shared__ unsigned char s_len[PNG_NSYM];
     __shared__ unsigned short s_code[PNG_NSYM];
-    __shared__ unsigned short s_order[PNG_NSYM];     // symbols with freq > 0 by ascending (freq, symbol)
+    __shared__ unsigned short s_order[PNG_NSYM];     // symbols by ascending (freq, symbol)
     __shared__ int s_parent[2 * PNG_NSYM];
     __shared__ unsigned s_weight[2 * PNG_NSYM];
     __shared__ unsigned s_item_bits[PNG_THREADS + 1];
     __shared__ unsigned s_item_a[PNG_THREADS], s_item_b[PNG_THREADS];
-    __shared__ int s_nused[2];
+    __shared__ unsigned s_stage[PNG_WARPS][PNG_ITEM_WORDS];
+    __shared__ unsigned s_match_bits[65];            // code + extra + distance of a match of n pixels ...
+    __shared__ unsigned char s_match_len[65];        // ... and its length in bits
 
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const PngSeg seg = segs[blockIdx.x];
     const PngCanvas cv = canvases[seg.canvas];
     const unsigned *img = reinterpret_cast<const unsigned *>(canvas_buf + cv.src);
     const int items_per_row = (cv.cols + PNG_ITEM_PX - 1) / PNG_ITEM_PX;
     const int n_items = seg.rows * items_per_row;  // <= PNG_THREADS by construction
-    const bool live = tid < n_items;
-    const int row = seg.row0 + (live ? tid / items_per_row : 0);
-    const int c0 = live ? (tid % items_per_row) * PNG_ITEM_PX : 0;
-    const int c1 = min(cv.cols, c0 + PNG_ITEM_PX);
+    unsigned *item_slots = reinterpret_cast<unsigned *>(scratch + seg.slot);
+    unsigned *out = item_slots + (size_t)n_items * PNG_ITEM_WORDS;
 
-    for (int i = tid; i < (PNG_THREADS / 32) * (PNG_NSYM + 6); i += PNG_THREADS)
+    for (int i = tid; i < PNG_WARPS * (PNG_NSYM + 6); i += PNG_THREADS)
         (&s_hist[0][0])[i] = 0;
     __syncthreads();
-    // ---- walk 1: histogram (per warp) and Adler-32 sums (per item)
-    unsigned ad_a = 1, ad_b = 0;
-    if (live) {
-        HistSink hs{s_hist[warp]};
-        walk_item<true>(img, cv.cols, row, c0, c1, hs, ad_a, ad_b);
+    // ---- histogram of a sample of the items (every fourth; all of a small segment): the code only has to be
+    // good, not optimal, and every symbol gets a code anyway (+1 below)
+    const int sample = n_items >= 32 ? 4 : 1;
+    for (int it = warp * sample; it < n_items; it += PNG_WARPS * sample) {
+        const int row = seg.row0 + it / items_per_row, c0 = (it % items_per_row) * PNG_ITEM_PX;
+        LanePixels px;
+        lane_pixels(img, cv.cols, row, c0, min(cv.cols, c0 + PNG_ITEM_PX), lane, px);
+        unsigned *h = s_hist[warp];
+        if (c0 == 0 && lane == 0)
+            atomicAdd(h + 1, 1u);  // filter type byte: Sub
+        int s = px.s_in;
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            if (px.valid >> j & 1u) {
+                const int t = pixel_token(px, lane, j, s);
+                if (t < 0) {
+                    const unsigned r = px.r[j];
+                    atomicAdd(h + (r & 255), 1u), atomicAdd(h + ((r >> 8) & 255), 1u);
+                    atomicAdd(h + ((r >> 16) & 255), 1u), atomicAdd(h + (r >> 24), 1u);
+                } else if (t > 0) {
+                    atomicAdd(h + 257 + c_len_code[t], 1u);
+                }
+            }
     }
-    s_item_a[tid] = ad_a % ADLER_MOD, s_item_b[tid] = ad_b % ADLER_MOD;
     __syncthreads();
     for (int s = tid; s < PNG_NSYM; s += PNG_THREADS) {
         unsigned f = 0;
 #pragma unroll
-        for (int w = 0; w < PNG_THREADS / 32; w++)
+        for (int w = 0; w < PNG_WARPS; w++)
             f += s_hist[w][s];
-        if (s == 256)
-            f = 1;  // end of block
-        if (s == 286 + 3 && f == 0)
-            f = 1;  // at least one distance code must be described
-        if (s >= 286 && s != 286 + 3)
-            f = 0;
-        s_freq[s] = f;
+        s_freq[s] = s < 286 ? f + 1 : 0;  // every literal / length symbol can occur in the unsampled items
         s_len[s] = 0;
     }
     __syncthreads();
     // ---- Huffman code lengths of the literal / length alphabet (0..285); the distance alphabet has one code
-    // order the used symbols by (freq, symbol): rank = number of used symbols that sort before this one
     for (int s = tid; s < 286; s += PNG_THREADS) {
         const unsigned f = s_freq[s];
-        if (f) {
-            int rank = 0;
-            for (int q = 0; q < 286; q++) {
-                const unsigned g = s_freq[q];
-                rank += (g && (g < f || (g == f && q < s))) ? 1 : 0;
-            }
-            s_order[rank] = (unsigned short)s;
+        int rank = 0;
+        for (int q = 0; q < 286; q++) {
+            const unsigned g = s_freq[q];
+            rank += (g < f || (g == f && q < s)) ? 1 : 0;
         }
-    }
-    if (tid == 0) {
-        int n = 0;
-        for (int q = 0; q < 286; q++)
-            n += s_freq[q] ? 1 : 0;
-        s_nused[0] = n;
+        s_order[rank] = (unsigned short)s;
     }
     __syncthreads();
     if (tid == 0) {
-        const int n = s_nused[0];
-        if (n == 1) {
-            s_len[s_order[0]] = 1;  // cannot happen (end of block + the filter byte are two symbols), kept for safety
-        } else {
-            // two-queue Huffman: leaves 0..n-1 in ascending weight, internal nodes n..2n-2 are created in
-            // ascending weight too
-            for (int i = 0; i < n; i++)
-                s_weight[i] = s_freq[s_order[i]];
-            int leaf = 0, node = n, next = n;
-            auto take = [&]() {
-                if (leaf < n && (node >= next || s_weight[leaf] <= s_weight[node]))
-                    return leaf++;
-                return node++;
-            };
-            for (; next < 2 * n - 1; next++) {
-                const int a = take(), b = take();
-                s_weight[next] = s_weight[a] + s_weight[b];
-                s_parent[a] = next, s_parent[b] = next;
-            }
-            // depths, root = 2n - 2; s_weight is reused for them
-            s_weight[2 * n - 2] = 0;
-            int count[PNG_MAXBITS + 2];
-            for (int i = 0; i <= PNG_MAXBITS + 1; i++)
-                count[i] = 0;
-            for (int i = 2 * n - 3; i >= 0; i--) {
-                const unsigned d = s_weight[s_parent[i]] + 1;
-                s_weight[i] = d;
-                if (i < n)
-                    count[d > PNG_MAXBITS ? PNG_MAXBITS : d]++;
-            }
-            // enforce the length limit on the counts per length, keeping the code complete
-            unsigned total = 0;
-            for (int i = PNG_MAXBITS; i > 0; i--)
-                total += (unsigned)count[i] << (PNG_MAXBITS - i);
-            while (total != (1u << PNG_MAXBITS)) {
-                count[PNG_MAXBITS]--;
-                for (int i = PNG_MAXBITS - 1; i > 0; i--)
-                    if (count[i]) {
-                        count[i]--;
-                        count[i + 1] += 2;
-                        break;
-                    }
-                total--;
-            }
-            // the least frequent symbols get the longest codes
-            int idx = 0;
-            for (int l = PNG_MAXBITS; l > 0; l--)
-                for (int q = count[l]; q > 0; q--)
-                    s_len[s_order[idx++]] = (unsigned char)l;
+        const int n = 286;
+        // two-queue Huffman: leaves 0..n-1 in ascending weight; internal nodes n..2n-2 come out ascending too
+        for (int i = 0; i < n; i++)
+            s_weight[i] = s_freq[s_order[i]];
+        int leaf = 0, node = n, next = n;
+        auto take = [&]() {
+            if (leaf < n && (node >= next || s_weight[leaf] <= s_weight[node]))
+                return leaf++;
+            return node++;
+        };
+        for (; next < 2 * n - 1; next++) {
+            const int a = take(), b = take();
+            s_weight[next] = s_weight[a] + s_weight[b];
+            s_parent[a] = next, s_parent[b] = next;
         }
+        // depths (root = 2n - 2); s_weight is reused for them
+        s_weight[2 * n - 2] = 0;
+        int count[PNG_MAXBITS + 2];
+        for (int i = 0; i <= PNG_MAXBITS + 1; i++)
+            count[i] = 0;
+        for (int i = 2 * n - 3; i >= 0; i--) {
+            const unsigned d = s_weight[s_parent[i]] + 1;
+            s_weight[i] = d;
+            if (i < n)
+                count[d > PNG_MAXBITS ? PNG_MAXBITS : d]++;
+        }
+        // enforce the length limit on the counts per length, keeping the code complete
+        unsigned total = 0;
+        for (int i = PNG_MAXBITS; i > 0; i--)
+            total += (unsigned)count[i] << (PNG_MAXBITS - i);
+        while (total != (1u << PNG_MAXBITS)) {
+            count[PNG_MAXBITS]--;
+            for (int i = PNG_MAXBITS - 1; i > 0; i--)
+                if (count[i]) {
+                    count[i]--;
+                    count[i + 1] += 2;
+                    break;
+                }
+            total--;
+        }
+        int idx = 0;  // the least frequent symbols get the longest codes
+        for (int l = PNG_MAXBITS; l > 0; l--)
+            for (int q = count[l]; q > 0; q--)
+                s_len[s_order[idx++]] = (unsigned char)l;
         s_len[286 + 3] = 1;  // distance 4: the only distance code, one bit
-        // canonical codes, stored bit-reversed (deflate packs Huffman codes starting from their most significant bit)
+        // canonical codes, stored bit-reversed (deflate packs Huffman codes from their most significant bit)
         int bl_count[PNG_MAXBITS + 1];
         for (int i = 0; i <= PNG_MAXBITS; i++)
             bl_count[i] = 0;
@@ -330,15 +329,88 @@ png_deflate_kernel(const PngSeg *__restrict__ segs, const PngCanvas *__restrict_
             s_code[q] = 0;  // distance code 3 = "0"
     }
     __syncthreads();
-    // ---- walk 2: bits per item, then their offsets behind the block header
-    unsigned bits = 0;
-    if (live) {
-        BitsSink bs{s_len, 0};
-        unsigned da = 0, db = 0;
-        walk_item<false>(img, cv.cols, row, c0, c1, bs, da, db);
-        bits = bs.bits;
+    if (tid >= 1 && tid <= 64) {
+        // a match of tid pixels: length code, its extra bits, the one-bit distance code "0"
+        const int sym = 257 + c_len_code[tid];
+        const int l = s_len[sym], eb = c_len_ebits[tid];
+        s_match_bits[tid] = (unsigned)s_code[sym] | ((unsigned)c_len_extra[tid] << l);
+        s_match_len[tid] = (unsigned char)(l + eb + 1);
     }
-    s_item_bits[tid] = bits;
+    __syncthreads();
+    // ---- every item: tokens -> (bits, length) per pixel in registers -> staged in shared memory -> its slot
+    for (int it = warp; it < n_items; it += PNG_WARPS) {
+        const int row = seg.row0 + it / items_per_row, c0 = (it % items_per_row) * PNG_ITEM_PX;
+        const int c1 = min(cv.cols, c0 + PNG_ITEM_PX);
+        LanePixels px;
+        lane_pixels(img, cv.cols, row, c0, c1, lane, px);
+        const int head = c0 == 0 ? 1 : 0;
+        const unsigned n_bytes = 4u * (unsigned)(c1 - c0) + head;
+        unsigned long long tb[8];
+        int tl[8];
+        unsigned lane_bits = 0, s1 = 0, s2 = 0;
+        if (head && lane == 0) {
+            lane_bits = s_len[1];
+            s1 = 1, s2 = n_bytes;  // the filter byte (value 1) at index 0
+        }
+        int s = px.s_in;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            tb[j] = 0ull, tl[j] = 0;
+            if (px.valid >> j & 1u) {
+                const unsigned r = px.r[j];
+                const int t = pixel_token(px, lane, j, s);
+                if (t < 0) {
+                    const unsigned b0 = r & 255, b1 = (r >> 8) & 255, b2 = (r >> 16) & 255, b3 = r >> 24;
+                    const int l0 = s_len[b0], l1 = s_len[b1], l2 = s_len[b2], l3 = s_len[b3];
+                    tb[j] = (unsigned long long)s_code[b0] | ((unsigned long long)s_code[b1] << l0) |
+                            ((unsigned long long)s_code[b2] << (l0 + l1)) | ((unsigned long long)s_code[b3] << (l0 + l1 + l2));
+                    tl[j] = l0 + l1 + l2 + l3;
+                } else if (t > 0) {
+                    tb[j] = s_match_bits[t], tl[j] = s_match_len[t];
+                }
+                lane_bits += tl[j];
+                // Adler-32 sums: A = 1 + sum x, B = N + sum (N - index) x
+                const unsigned sum = __dp4a(r, 0x01010101u, 0u), wsum = __dp4a(r, 0x03020100u, 0u);
+                s1 += sum;
+                s2 += (n_bytes - (head + 4u * (8 * lane + j))) * sum - wsum;
+            }
+        }
+        unsigned incl = lane_bits;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o)
+                incl += t;
+        }
+        const unsigned item_bits = __shfl_sync(0xffffffffu, incl, 31);
+        const unsigned off = incl - lane_bits;
+        const unsigned n_words = (item_bits + 31) >> 5;
+        unsigned *stage = s_stage[warp];
+        for (unsigned k = lane; k < n_words; k += 32)
+            stage[k] = 0;
+        __syncwarp();
+        BitWriter bw{stage, 0ull, (int)(off & 31), (long long)(off >> 5), true};
+        if (head && lane == 0)
+            bw.put(s_code[1], s_len[1]);
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            bw.put64(tb[j], tl[j]);
+        bw.finish();
+        __syncwarp();
+        unsigned *slot = item_slots + (size_t)it * PNG_ITEM_WORDS;
+        for (unsigned k = lane; k < n_words; k += 32)
+            slot[k] = stage[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        if (lane == 0) {
+            s_item_bits[it] = item_bits;
+            s_item_a[it] = (1u + s1) % ADLER_MOD, s_item_b[it] = (n_bytes + s2) % ADLER_MOD;
+        }
+        __syncwarp();
+    }
     __syncthreads();
     if (tid == 0) {
         // exclusive scan (<= 256 entries) + Adler-32 of the segment, items in stream order
@@ -352,11 +424,11 @@ png_deflate_kernel(const PngSeg *__restrict__ segs, const PngCanvas *__restrict_
             const unsigned long long nbytes = 4ull * (min(cv.cols, ic0 + PNG_ITEM_PX) - ic0) + (ic0 == 0 ? 1 : 0);
             adler_combine(a, b, s_item_a[i], s_item_b[i], nbytes);
         }
-        s_item_bits[PNG_THREADS] = off;  // end of the items: the end-of-block code follows
+        s_item_bits[n_items] = off;  // end of the items: the end-of-block code follows
         seg_adler[2 * blockIdx.x] = a, seg_adler[2 * blockIdx.x + 1] = b;
     }
     __syncthreads();
-    const unsigned end_bits = s_item_bits[PNG_THREADS];
+    const unsigned end_bits = s_item_bits[n_items];
     // block = header + items + end of block [+ 3 bits of an empty stored block, padding to a byte, 00 00 ff ff]
     const unsigned eob_len = s_len[256];
     unsigned total_bits = end_bits + eob_len;
@@ -367,23 +439,30 @@ png_deflate_kernel(const PngSeg *__restrict__ segs, const PngCanvas *__restrict_
         total_bits += 3;
         total_bytes = (total_bits + 7) / 8 + 4;
     }
-    unsigned *out = reinterpret_cast<unsigned *>(scratch + seg.slot);
-    const unsigned n_words = (total_bytes + 3) / 4 + 1;
-    for (unsigned i = tid; i < n_words; i += PNG_THREADS)
+    const unsigned n_out_words = (total_bytes + 3) / 4 + 1;
+    for (unsigned i = tid; i < n_out_words; i += PNG_THREADS)
         out[i] = 0;
     __syncthreads();
-    // ---- walk 3: emission
-    if (live) {
-        const unsigned off = s_item_bits[tid];
-        EmitSink es{s_len, s_code, out, 0ull, (int)(off & 31), (long long)(off >> 5), true};
-        unsigned da = 0, db = 0;
-        walk_item<false>(img, cv.cols, row, c0, c1, es, da, db);
-        es.finish();
+    // ---- merge: every item's bits move to their place in the stream (a shift by the offset's low 5 bits)
+    for (int it = warp; it < n_items; it += PNG_WARPS) {
+        const unsigned d0 = s_item_bits[it], nbits = s_item_bits[it + 1] - d0;
+        const unsigned sh = d0 & 31, w0 = d0 >> 5, n_src = (nbits + 31) >> 5;
+        const unsigned n_dst = (sh + nbits + 31) >> 5;  // destination words touched
+        const unsigned *slot = item_slots + (size_t)it * PNG_ITEM_WORDS;
+        for (unsigned k = lane; k < n_dst; k += 32) {
+            const unsigned lo = k < n_src ? slot[k] : 0u;
+            const unsigned hi = (k > 0 && sh) ? slot[k - 1] : 0u;
+            const unsigned v = (lo << sh) | (sh ? hi >> (32 - sh) : 0u);
+            if (k == 0 || k + 1 >= n_dst)
+                atomicOr(out + w0 + k, v);  // shared with the neighbouring items
+            else
+                out[w0 + k] = v;
+        }
     }
-    if (tid == PNG_THREADS - 1 || (tid == 0 && PNG_THREADS == 1)) {
+    if (tid == PNG_THREADS - 1) {
         // header: BFINAL, BTYPE = 2, HLIT = 29 (286 codes), HDIST = 3 (4 codes), HCLEN = 15 (19 lengths), the
         // code-length code (4 bits for 0..15, unused 16..18), then the 290 code lengths as 4-bit codes
-        EmitSink hs{s_len, s_code, out, 0ull, 0, 0ll, true};
+        BitWriter hs{out, 0ull, 0, 0ll, true};
         hs.put(seg.last ? 1u : 0u, 1), hs.put(2u, 2), hs.put(29u, 5), hs.put(3u, 5), hs.put(15u, 4);
         const int order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
         for (int i = 0; i < 19; i++)
@@ -392,16 +471,19 @@ png_deflate_kernel(const PngSeg *__restrict__ segs, const PngCanvas *__restrict_
             hs.put(bit_reverse(s_len[q], 4), 4);
         hs.finish();
         // end of block (+ sync marker)
-        EmitSink ts{s_len, s_code, out, 0ull, (int)(end_bits & 31), (long long)(end_bits >> 5), true};
+        BitWriter ts{out, 0ull, (int)(end_bits & 31), (long long)(end_bits >> 5), true};
         ts.put(s_code[256], (int)eob_len);
         if (!seg.last)
             ts.put(0u, 3);  // BFINAL = 0, BTYPE = 0: stored block of length 0
         ts.finish();
-        if (!seg.last) {
-            unsigned char *tail = scratch + seg.slot + total_bytes - 4;
+        seg_bytes[blockIdx.x] = (int)total_bytes;
+    }
+    if (!seg.last) {
+        __syncthreads();  // the marker bytes share a word with the last bits
+        if (tid == 0) {
+            unsigned char *tail = reinterpret_cast<unsigned char *>(out) + total_bytes - 4;
             tail[0] = 0, tail[1] = 0, tail[2] = 0xff, tail[3] = 0xff;
         }
-        seg_bytes[blockIdx.x] = (int)total_bytes;
     }
 }
 
@@ -451,14 +533,14 @@ __device__ __forceinline__ void put_be32(unsigned char *p, unsigned v)
 }
 
 // CRC-32 (zero init, no final xor) of bytes [0, n) by the whole CTA; result valid in thread 0
-__device__ unsigned block_crc0(const unsigned char *p, long long n, unsigned *s_part, long long *s_len)
+__device__ unsigned block_crc0(const unsigned char *p, long long n, unsigned *s_part, long long *s_len, const unsigned *s_table)
 {
     const int tid = threadIdx.x;
     const long long span = ((n + PNG_THREADS - 1) / PNG_THREADS + 3) & ~3ll;
     const long long a = min(n, (long long)tid * span), b = min(n, a + span);
     unsigned crc = 0;
     for (long long i = a; i < b; i++)
-        crc = c_crc_table[(crc ^ p[i]) & 255] ^ (crc >> 8);
+        crc = s_table[(crc ^ p[i]) & 255] ^ (crc >> 8);  // data-dependent index: shared memory, not the constant cache
     s_part[tid] = crc, s_len[tid] = b - a;
     __syncthreads();
     for (int step = 1; step < PNG_THREADS; step <<= 1) {
@@ -483,7 +565,9 @@ png_pack_kernel(const PngCanvas *__restrict__ canvases, const PngSeg *__restrict
 {
     __shared__ unsigned s_part[PNG_THREADS];
     __shared__ long long s_len[PNG_THREADS];
+    __shared__ unsigned s_table[256];
     const int tid = threadIdx.x;
+    s_table[tid & 255] = c_crc_table[tid & 255];
     const PngCanvas cv = canvases[blockIdx.x];
     unsigned char *f = out + file_off[blockIdx.x];
     long long idat = 2 + 4;
@@ -524,15 +608,32 @@ png_pack_kernel(const PngCanvas *__restrict__ canvases, const PngSeg *__restrict
     // segments -> body (byte copies; the segments are byte aligned)
     long long pos = 2;
     for (int s = 0; s < cv.nseg; s++) {
-        const unsigned char *src = scratch + segs[cv.seg0 + s].slot;
+        const PngSeg sg = segs[cv.seg0 + s];
+        const int seg_items = sg.rows * ((cv.cols + PNG_ITEM_PX - 1) / PNG_ITEM_PX);
+        const unsigned char *src = scratch + sg.slot + (size_t)seg_items * PNG_ITEM_WORDS * 4;
         const int n = seg_bytes[cv.seg0 + s];
-        for (int i = tid; i < n; i += PNG_THREADS)
-            body[pos + i] = src[i];
+        // the source is word aligned, the destination is not: every thread builds aligned destination words from two
+        // source words (funnel shift); the ragged ends go byte by byte
+        unsigned char *dst = body + pos;
+        const int lead = (int)((4 - (reinterpret_cast<size_t>(dst) & 3)) & 3);  // bytes up to the first aligned word
+        const int n_words = n > lead ? (n - lead) / 4 : 0;
+        for (int i = tid; i < min(lead, n); i += PNG_THREADS)
+            dst[i] = src[i];
+        const unsigned *sw = reinterpret_cast<const unsigned *>(src);
+        unsigned *dw = reinterpret_cast<unsigned *>(dst + lead);
+        const int sh = 8 * (lead & 3);
+        for (int i = tid; i < n_words; i += PNG_THREADS) {
+            const int sb = lead + 4 * i;  // source byte of this destination word
+            const unsigned lo = sw[sb >> 2], hi = sw[(sb >> 2) + 1];  // the slot has a spare word behind the stream
+            dw[i] = sh ? __funnelshift_r(lo, hi, sh) : lo;
+        }
+        for (int i = lead + 4 * n_words + tid; i < n; i += PNG_THREADS)
+            dst[i] = src[i];
         pos += n;
     }
     __syncthreads();
     // CRC of the IDAT chunk: type + data
-    const unsigned c0 = block_crc0(body - 4, idat + 4, s_part, s_len);
+    const unsigned c0 = block_crc0(body - 4, idat + 4, s_part, s_len, s_table);
     if (tid == 0) {
         // a CRC started from 0xffffffff = the zero-started one xor the shifted initial value
         const unsigned crc = c0 ^ crc_shift(0xffffffffu, (unsigned long long)(idat + 4));
@@ -597,13 +698,15 @@ static void png_init_tables()
     done[dev] = true;
 }
 
-// Upper bound of the bytes of a segment of `rows` x `cols`: a Huffman code is never longer in total than the
-// fixed 9-bit code of its 286 symbols and a match spends at most three symbols on at least four bytes, so
-// 10 bits per filtered byte cover the tokens; plus header, end of block and the sync marker.
+// Upper bound of the bytes of a segment of `rows` x `cols`: the code is built from a sample of the items, so the
+// only bound that always holds is the code length limit, 15 bits per filtered byte (a match spends at most 36 bits
+// on at least four bytes); plus header, end of block and the sync marker.  Scratch, not output: files are packed.
 long long svgr_png_slot_bytes(int rows, int cols)
 {
     const long long raw = (long long)rows * (4ll * cols + 1);
-    return ((raw * 10 + 7) / 8 + (PNG_HEADER_BITS + 7) / 8 + 32 + 15) & ~15ll;
+    const long long items = (long long)rows * ((cols + PNG_ITEM_PX - 1) / PNG_ITEM_PX);
+    // the items' private slots, then the merged stream
+    return (items * PNG_ITEM_WORDS * 4 + (raw * 15 + 7) / 8 + (PNG_HEADER_BITS + 7) / 8 + 32 + 15) & ~15ll;
 }
 
 int svgr_png_rows_per_segment(int cols)
