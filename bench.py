@@ -147,11 +147,18 @@ def pin_program(prog):
 
 
 def build_batch(icons, seed0, engine):
-    """-> (one program for the whole batch, the per-icon programs)"""
-    from svgrasterize_b200 import encode, synth
+    """-> (one program for the whole batch, its (scene, size, linear_rgb) jobs, seconds spent encoding).  The scenes
+    come from the synthetic generator (the stand-in for the reference's SVG parser, untimed); the encoding is the
+    native walk (svgrasterize_b200.native: csrc/_flatten.c + csrc/encode_flat.cpp)."""
+    from svgrasterize_b200 import native, synth
 
-    progs = [encode.encode_scene(synth.icon_scene(seed0 + i), synth.icon_size(), engine=engine) for i in range(icons)]
-    return encode.Program.concat(progs), progs
+    jobs = [(synth.icon_scene(seed0 + i), synth.icon_size(), False) for i in range(icons)]
+    t0 = time.perf_counter()
+    prog = native.encode_batch(jobs, engine=engine)
+    dt = time.perf_counter() - t0
+    if isinstance(prog, native.NativeProgram):
+        prog = prog.to_program()  # plain arrays: they are re-homed in pinned memory below
+    return prog, jobs, dt
 
 
 def run_e2e(batches, out_host_np, device, steps, warmup, workers, chunks, png=False):
@@ -164,13 +171,17 @@ def run_e2e(batches, out_host_np, device, steps, warmup, workers, chunks, png=Fa
     from svgrasterize_b200 import encode
     from svgrasterize_b200.engine import Engine
 
+    from svgrasterize_b200 import native
+
     all_parts, pins = [], []
-    for progs in batches:
-        n = len(progs)
+    for jobs in batches:
+        n = len(jobs)
         bounds = [n * c // chunks for c in range(chunks + 1)]
         parts, offs = [], [0]
         for c in range(chunks):
-            part = encode.Program.concat(progs[bounds[c]: bounds[c + 1]])
+            part = native.encode_batch(jobs[bounds[c]: bounds[c + 1]])
+            if isinstance(part, native.NativeProgram):
+                part = part.to_program()
             pins.append(pin_program(part))
             parts.append(part)
             offs.append(offs[-1] + part.canvas_bytes)
@@ -217,6 +228,54 @@ def run_e2e(batches, out_host_np, device, steps, warmup, workers, chunks, png=Fa
     h2d = sum(p.h2d_bytes() for p in all_parts[0][0])
     del pins
     return dt / steps, h2d, sum(d2h) // steps
+
+
+def run_from_scene(batches, out_host_np, device, steps, warmup):
+    """The same step starting from Scene objects in memory (what the reference's parser hands to Scene.render):
+    native encode (svgrasterize_b200.native: flatten under the GIL, then the C++ walk) -> svgr_render_png -> PNG
+    files in pinned host memory.  Two host threads: one encodes batch k + 1 while the other renders batch k.
+    Returns (wall seconds per step, encode seconds per step)."""
+    import queue
+
+    import torch
+
+    from svgrasterize_b200 import native
+    from svgrasterize_b200.engine import Engine
+
+    eng = Engine(device)
+    q = queue.Queue(maxsize=2)
+    t_enc = [0.0]
+
+    def producer(first, count):
+        for k in range(first, first + count):
+            t0 = time.perf_counter()
+            prog = native.encode_batch(batches[k % len(batches)])
+            t_enc[0] += time.perf_counter() - t0
+            q.put(prog)
+        q.put(None)
+
+    def run(first, count):
+        t_enc[0] = 0.0
+        th = threading.Thread(target=producer, args=(first, count))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        th.start()
+        while True:
+            prog = q.get()
+            if prog is None:
+                break
+            eng.render_png(prog, out=out_host_np)
+            if hasattr(prog, "close"):
+                prog.close()
+        th.join()
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0
+
+    run(0, max(1, min(warmup, 2)))
+    dt = run(0, steps)
+    enc = t_enc[0]
+    eng.close()
+    return dt / steps, enc / steps
 
 
 def time_other_configs(device, peak, with_cpu):
@@ -334,11 +393,10 @@ def run_gpu(opts):
     t_encode = 0.0
     for b in range(n_batches):
         e = Engine(local)
-        t0 = time.perf_counter()
-        prog_b, icon_progs_b = build_batch(opts.icons, opts.seed0 + (b * world + rank) * opts.icons, e)
-        t_encode += time.perf_counter() - t0
+        prog_b, jobs_b, dt = build_batch(opts.icons, opts.seed0 + (b * world + rank) * opts.icons, e)
+        t_encode += dt
         pins.append(pin_program(prog_b))
-        engines.append(e), progs.append(prog_b), batches.append(icon_progs_b)
+        engines.append(e), progs.append(prog_b), batches.append(jobs_b)
     t_encode /= n_batches
     eng, prog = engines[0], progs[0]
     n_px = opts.icons * ICON_PX * ICON_PX
@@ -418,6 +476,9 @@ def run_gpu(opts):
     sec_png, _h2d, d2h_png = run_e2e(batches, out_host_np, local, opts.steps, opts.warmup, workers, chunks, png=True)
     barrier()
     ms_e2e_png = max_over_ranks(sec_png * 1e3)
+    sec_scene, sec_scene_enc = run_from_scene(batches, out_host_np, local, opts.steps, opts.warmup)
+    barrier()
+    ms_from_scene = max_over_ranks(sec_scene * 1e3)
     use_png = ms_e2e_png < ms_e2e_raw
     ms_e2e = ms_e2e_png if use_png else ms_e2e_raw
     e2e_value = world * n_px / (ms_e2e * 1e-3) / 1e6
@@ -506,6 +567,11 @@ def run_gpu(opts):
                               "d2h_bytes_per_step": int(d2h_raw)},
                 "png": {"value": world * n_px / (ms_e2e_png * 1e-3) / 1e6, "ms_per_step": ms_e2e_png,
                         "d2h_bytes_per_step": int(d2h_png)}},
+        "e2e_from_scene": {"value": world * n_px / (ms_from_scene * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_from_scene,
+                           "encode_ms_per_step": sec_scene_enc * 1e3,
+                           "how": "Scene objects in memory -> native encoder (CPython flattener + C++ walk, one host "
+                                  "thread) -> svgr_render_png -> PNG files in pinned host memory, the encode of batch "
+                                  "k + 1 overlapping the render of batch k (one process, two threads)"},
         "gpu_launches": int(st["n_kernels"]) * opts.steps,
         "paths_per_s": world * len(prog.paths) / (ms_step * 1e-3),
         "stage_ms_per_step": {k: v / opts.steps for k, v in sorted(acc.items())},

@@ -105,6 +105,11 @@ SYMBOLS = {
     "svgr_cloud_bounds": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "svgr_arc_to_cubics": (C.c_int64, [C.c_double] * 7 + [C.c_void_p, C.c_int64]),
     "svgr_expand_arcs": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "svgr_encode_flat": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "svgr_encoded_program": (C.c_void_p, [C.c_void_p]),
+    "svgr_encoded_error": (C.c_char_p, [C.c_void_p]),
+    "svgr_encoded_canvases": (C.c_int64, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "svgr_encoded_free": (None, [C.c_void_p]),
     "svgr_line_signed_coverage": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int64]),
     "svgr_grad_pixels": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "svgr_grad_spread": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),

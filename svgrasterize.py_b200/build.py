@@ -47,7 +47,35 @@ def stale() -> bool:
 EXTRA = os.environ.get("SVGR_NVCC_EXTRA", "").split()
 
 
+FLATTEN_SRC = os.path.join(CSRC, "_flatten.c")
+
+
+def flatten_path() -> str:
+    import sysconfig
+
+    return os.path.join(HERE, "_svgr_flatten" + (sysconfig.get_config_var("EXT_SUFFIX") or ".so"))
+
+
+def build_flatten(force: bool = False) -> str:
+    """The CPython extension that reads Scene objects into flat arrays (csrc/_flatten.c), built in-tree with gcc."""
+    import sysconfig
+
+    out = flatten_path()
+    deps = [FLATTEN_SRC, os.path.join(HERE, "..", "include", "svgr_b200.h")]
+    if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
+        return out
+    cc = os.environ.get("CC") or shutil.which("gcc") or "cc"
+    import numpy
+
+    cmd = [cc, "-O2", "-shared", "-fPIC", "-Wall", "-I" + sysconfig.get_paths()["include"], "-I" + numpy.get_include(),
+           FLATTEN_SRC, "-o", out]
+    subprocess.run(cmd, check=True)
+    return out
+
+
 def build(force: bool = False, verbose: bool = False, lib: str = LIB) -> str:
+    if lib == LIB:
+        build_flatten(force)
     if not force and lib == LIB and not stale():
         return LIB
     nvcc = _nvcc()

@@ -360,7 +360,10 @@ struct Encoder {
             const double fx = (p.focal & 1) ? p.p[3] : cx, fy = (p.focal & 1) ? p.p[4] : cy;
             const double fr = (p.focal & 2) ? p.p[5] : 0.0;
             const double cd0 = cx - fx, cd1 = cy - fy, rd = r - fr;
-            const double a = (cd0 * cd0 + cd1 * cd1) - rd * rd;
+            // encode.py: (cd ** 2).sum() - rd ** 2 -- numpy squares by multiplying, Python's float ** 2 is libm's pow,
+            // which is not always the rounded product (the exponent is volatile so that the compiler keeps the call)
+            volatile double two = 2.0;
+            const double a = (cd0 * cd0 + cd1 * cd1) - pow(rd, two);
             rec.kind = PAINT_RADIAL_FOCAL;
             rec.m1[0] = A00, rec.m1[1] = A01, rec.m1[3] = A10, rec.m1[4] = A11;
             rec.m1[2] = T0 - fx, rec.m1[5] = T1 - fy;

@@ -227,8 +227,9 @@ class Program:
             parts["stroke_data"].append(p.stroke_data)
             parts["stroke_seg_job"].append(p.stroke_seg_job + np.int32(base["stroke"]))
             pa = p.paints.copy()
-            pa["stop_off"] += base["stop"]
-            pa["flag"] += base["focal"]
+            grad = (pa["kind"] != _lib.PAINT_SOLID) & (pa["kind"] != _lib.PAINT_PATTERN)
+            pa["stop_off"][grad] += base["stop"]
+            pa["flag"][pa["kind"] == _lib.PAINT_RADIAL_FOCAL] += base["focal"]
             pa["pat_node"] = np.where(pa["pat_node"] >= 0, pa["pat_node"] + base["node"], pa["pat_node"])
             parts["paints"].append(pa)
             parts["stops"].append(p.stops)
@@ -815,17 +816,24 @@ def _encode_job(job):
     return encode_scene(scene, size, linear_rgb)
 
 
-def encode_batch(jobs, processes: int = 0) -> Program:
-    """Encode many (scene, size, linear_rgb) jobs into one program.  Encoding is pure host work (a tree walk
-    per SVG, ~3 ms for a c5 icon), independent per scene and therefore the natural thing to spread over
-    worker processes when batches are large.  Scenes that use objectBoundingBox units need
-    the device at encode time and must be encoded in the rendering process (processes = 0)."""
+def encode_batch(jobs, processes: int = 0, engine=None, native: bool = True):
+    """Encode many (scene, size, linear_rgb) jobs into one program.
+
+    native (default): the scene walk runs in the library (native.encode_batch: csrc/_flatten.c reads the Scene
+    objects, csrc/encode_flat.cpp records the program, ~50 us per icon on one core against ~1.5 ms for this module);
+    scenes it does not cover (objectBoundingBox units, patterns, filters) are encoded by Encoder and spliced in.
+    native=False: every scene through Encoder, optionally spread over `processes` worker processes (scenes that use
+    objectBoundingBox units need the device at encode time and must be encoded in the rendering process)."""
     jobs = list(jobs)
+    if native:
+        from . import native as N
+
+        return N.encode_batch(jobs, engine=engine)
     if processes and processes > 1 and len(jobs) > 1:
         import multiprocessing as mp
 
         with mp.get_context("spawn").Pool(processes) as pool:
             progs = pool.map(_encode_job, jobs, chunksize=max(1, len(jobs) // (processes * 4)))
     else:
-        progs = [_encode_job(j) for j in jobs]
+        progs = [encode_scene(scene, size, lin, engine=engine) for scene, size, lin in jobs]
     return Program.concat(progs)

@@ -165,8 +165,8 @@ def test_encode_batch_in_worker_processes_matches_serial():
     from svgrasterize_b200 import encode, synth
 
     jobs = [(synth.icon_scene(s), synth.icon_size(), False) for s in range(6)]
-    a = encode.encode_batch(jobs)
-    b = encode.encode_batch(jobs, processes=2)
+    a = encode.encode_batch(jobs)  # native walk
+    b = encode.encode_batch(jobs, processes=2, native=False)  # Python encoder in worker processes
     for name in encode.Program.ARRAYS:
         x, y = getattr(a, name), getattr(b, name)
         assert x.dtype == y.dtype and x.shape == y.shape and x.tobytes() == y.tobytes(), name
@@ -289,3 +289,119 @@ def test_install_on_the_reference_module_itself():
         B.uninstall(token)
     assert all(getattr(ref, n) is originals[n] for n in api._MODULE_FUNCTIONS)
     assert ref.Scene.render is not api.scene_render and ref.Layer is not api.Layer
+
+
+def _programs_equal(a, b, paint_tol=0.0):
+    """Two scene programs record for record; paint_tol > 0 lets the gradient coefficients differ by that relative
+    amount (the native encoder's LU inverse vs numpy's for rotated transforms)."""
+    from svgrasterize_b200 import encode
+
+    for name in encode.Program.ARRAYS:
+        x, y = np.asarray(getattr(a, name)), np.asarray(getattr(b, name))
+        assert x.shape == y.shape, name
+        if name == "paints" and paint_tol > 0:
+            for f in x.dtype.names:
+                if f in ("m1", "g"):
+                    scale = np.maximum(np.abs(y[f]), 1e-300)
+                    assert (np.abs(x[f] - y[f]) / scale <= paint_tol).all() or np.allclose(x[f], y[f], rtol=paint_tol, atol=1e-300), f
+                else:
+                    assert x[f].tobytes() == y[f].tobytes(), f
+        else:
+            assert x.tobytes() == y.tobytes(), name
+    assert list(a.canvases) == list(b.canvases) and list(a.roots) == list(b.roots)
+    assert a.canvas_bytes == b.canvas_bytes and a.n_focal == b.n_focal
+
+
+def test_native_encoder_reproduces_the_python_encoder_on_icons():
+    """the C++ walk (csrc/encode_flat.cpp) over arrays read by the CPython flattener
+    (csrc/_flatten.c) gives the program encode.Encoder gives, bit for bit, for the c5 icons."""
+    from svgrasterize_b200 import encode, native, synth
+
+    scenes = [synth.icon_scene(4000 + i) for i in range(64)]
+    jobs = [(s, synth.icon_size(), bool(i % 5 == 0)) for i, s in enumerate(scenes)]
+    prog = native.encode_batch(jobs)
+    assert isinstance(prog, native.NativeProgram)
+    ref = encode.Program.concat([encode.encode_scene(s, size, lin) for s, size, lin in jobs])
+    _programs_equal(prog, ref)
+    assert prog.h2d_bytes() == ref.h2d_bytes()
+    _programs_equal(prog.to_program(), ref)
+    prog.close()
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_native_encoder_on_golden_scenes(name):
+    """Every golden scene: covered by the native walk -> the same program as the Python encoder (paint coefficients
+    to 1e-13 where a rotation makes the two inverses differ in the last bit); not covered (filters, patterns,
+    objectBoundingBox units) -> the flattener says so and leaves nothing of the scene behind."""
+    from svgrasterize_b200 import encode, native
+
+    scene, size, lin, _z = load_golden(name)
+    arr, skipped = native.flatten([(scene, size, lin)])
+    if skipped:
+        assert skipped == [0] and len(arr["nodes"]) == 0 and len(arr["seg_tag"]) == 0 and len(arr["scenes"]) == 0
+        return
+    prog = native.encode_flat(arr)
+    ref = encode.encode_scene(scene, size, lin)
+    _programs_equal(prog, ref, paint_tol=1e-13)
+    prog.close()
+
+
+def test_native_encoder_splices_python_encoded_scenes():
+    """A batch in which one scene needs the Python encoder (a filter): the result is the concatenation in order."""
+    from svgrasterize_b200 import encode, native, synth
+
+    jobs = [(synth.icon_scene(1), synth.icon_size(), False), (synth.filter_stack_scene(96), (96, 96), False),
+            (synth.icon_scene(2), synth.icon_size(), True), (synth.icon_scene(3), synth.icon_size(), False)]
+    prog = native.encode_batch(jobs)
+    assert isinstance(prog, encode.Program)
+    ref = encode.Program.concat([encode.encode_scene(s, size, lin) for s, size, lin in jobs])
+    _programs_equal(prog, ref)
+
+
+def test_native_encoder_error_behaviour():
+    """The reference's ValueErrors (:945, :989, :1492, :1668) surface from the native path too."""
+    from svgrasterize_b200 import native, scene as S, synth
+
+    path = synth.rect_path(1, 1, 10, 10)
+    red = synth.color(1, 0, 0)
+    with pytest.raises(ValueError, match="fill rule"):
+        native.encode_batch([(S.Scene.fill(path, red, "oddeven"), (16, 16), False)])
+    with pytest.raises(ValueError, match="line cap"):
+        native.encode_batch([(S.Scene.stroke(path, red, 2.0, "pointy", None), (16, 16), False)])
+    grad = S.GradLinear(np.zeros(2), np.ones(2), [(0.0, red), (1.0, red)], None, "mirror", False, None)
+    with pytest.raises(ValueError, match="spread"):
+        native.encode_batch([(S.Scene.fill(path, grad), (16, 16), False)])
+    nostops = S.GradLinear(np.zeros(2), np.ones(2), [], None, "pad", False, None)
+    with pytest.raises(ValueError, match="stops"):
+        native.encode_batch([(S.Scene.fill(path, nostops), (16, 16), False)])
+
+
+def test_native_encoder_reads_the_reference_modules_objects():
+    """The flattener is duck typed: scenes parsed by the unmodified reference (its own Scene / Path / Transform /
+    gradient classes) flatten and encode to what the Python encoder records for the same objects."""
+    import importlib.util
+    import os
+    import warnings
+
+    ref_py = "/root/reference/svgrasterize.py"
+    if not os.path.exists(ref_py):
+        pytest.skip("reference checkout not present (GPU box)")
+    from svgrasterize_b200 import encode, native
+
+    spec = importlib.util.spec_from_file_location("svgrasterize_ref_for_flatten_test", ref_py)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        fonts = ref.FontsDB()
+        fonts.register_file("/root/reference/fonts.svgz")
+        jobs = []
+        for file, width in (("material-design.svg", 512), ("prompt.svg", None)):
+            scene, _ids, size = ref.svg_scene_from_filepath(f"/root/reference/demo/{file}", width=width, fonts=fonts)
+            jobs.append((scene, size, False))
+    arr, skipped = native.flatten(jobs)
+    assert skipped == []
+    prog = native.encode_flat(arr)
+    want = encode.Program.concat([encode.encode_scene(s, size, lin) for s, size, lin in jobs])
+    _programs_equal(prog, want, paint_tol=1e-13)
+    prog.close()

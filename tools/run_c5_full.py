@@ -22,11 +22,18 @@ SUB = 128  # icons per encoding job
 
 
 def encode_range(span):
+    """Worker: generate the scenes (the stand-in for parsing) and encode them with the native walk."""
     import svgrasterize_b200  # noqa: F401
-    from svgrasterize_b200 import encode, synth
+    from svgrasterize_b200 import native, synth
 
     lo, hi = span
-    return encode.Program.concat([encode.encode_scene(synth.icon_scene(i), synth.icon_size()) for i in range(lo, hi)])
+    t0 = time.perf_counter()
+    jobs = [(synth.icon_scene(i), synth.icon_size(), False) for i in range(lo, hi)]
+    t1 = time.perf_counter()
+    prog = native.encode_batch(jobs)
+    out = prog.to_program() if isinstance(prog, native.NativeProgram) else prog
+    out.t_generate, out.t_encode = t1 - t0, time.perf_counter() - t1
+    return out
 
 
 def main():
@@ -47,11 +54,14 @@ def main():
     kept = {}
     spans = [(lo, min(lo + SUB, n)) for lo in range(0, n, SUB)]
     crc, t_render, done = 0, 0.0, 0
+    t_gen = t_enc = 0.0
     t0 = time.perf_counter()
     with mp.get_context("spawn").Pool(procs) as pool:
         pending = []
         for sub in pool.imap(encode_range, spans, chunksize=1):  # results arrive in order, encoded ahead
             pending.append(sub)
+            t_gen += sub.t_generate
+            t_enc += sub.t_encode
             if len(pending) * SUB < batch and done + sum(len(p.canvases) for p in pending) < n:
                 continue
             prog = encode.Program.concat(pending)
@@ -74,6 +84,7 @@ def main():
     print(json.dumps({
         "config": f"c5 full size: {done} synthetic icons at 256 x 256, batches of {batch}", "icons": done,
         "host_encode_processes": procs, "wall_s": round(wall, 3), "render_s": round(t_render, 3),
+        "worker_seconds_generating_scenes": round(t_gen, 2), "worker_seconds_encoding": round(t_enc, 2),
         "mpx_s_wall_incl_encode": round(done * px / wall / 1e6, 1),
         "mpx_s_render_calls": round(done * px / t_render / 1e6, 1), "crc32_of_all_bytes": crc,
         "sampled_icons_equal_to_single_renders": f"{same}/{len(kept)}"}))
