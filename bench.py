@@ -596,6 +596,87 @@ def run_gpu(opts):
         dist.destroy_process_group()
 
 
+def run_bands(opts):
+    """--config c2 | c4: ONE big render cut into row bands over the N ranks (SURVEY.md 8(e), strong scaling): every
+    rank keeps its band's program resident, a step = re-render the band + gather the RGBA8 bands on rank 0 (grouped
+    ncclSend / ncclRecv, the only collective).  value = canvas Mpx/s, device events, max over ranks."""
+    import torch
+
+    import svgrasterize_b200  # noqa: F401
+    from svgrasterize_b200 import parallel, sceneio, synth
+    from svgrasterize_b200.engine import Engine
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    stream = torch.cuda.current_stream()
+    eng = Engine(local)
+    if opts.config == "c2":
+        z = np.load(os.path.join(ROOT, "tests", "golden_big", "demo_material_w4096.npz"), allow_pickle=False)
+        scene, size, lin = sceneio.load_scene(z), tuple(int(v) for v in z["size"]), bool(z["linear_rgb"])
+        name = "c2: demo/material-design.svg -w 4096 (4096x4096, 1924 masks, one 935-layer group)"
+    else:
+        n = 8192
+        scene, size, lin = synth.filter_stack_scene(n), (n, n), False
+        name = f"c4: filter stack blur(4) -> dilate(3) -> saturate(0.5) on a gradient-filled circle, {n}x{n}"
+    w, h = size
+    prog, (a, b) = parallel.band_program(eng, scene, size, world, rank, lin)
+    band = torch.empty(max(prog.canvas_bytes, 4), dtype=torch.uint8, device="cuda")
+    eng.render(prog, out=band, stream=stream)
+    view = band[: prog.canvas_bytes].view(b - a, w, 4)
+
+    def step():
+        st = eng.render_resident(band, stream=stream)
+        return st, parallel.gather_bands(view, h, w, world, rank, dist)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(opts.warmup, 3)):
+        step()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(opts.steps):
+        st, canvas = step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    sampler.stop_flag = True
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    sampler.join()
+    if rank == 0:
+        ms_step = ms / opts.steps
+        check = None
+        if opts.config == "c2":
+            check = int(np.abs(canvas.cpu().numpy().astype(np.int16) - z["canvas_u8"].astype(np.int16)).max())
+        print(json.dumps({
+            "metric": "Mpixels/sec rendered (one canvas, row bands)", "value": w * h / (ms_step * 1e-3) / 1e6, "unit": UNIT,
+            "n_gpus": world, "steps": opts.steps, "warmup": max(opts.warmup, 3), "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": name, "bands": world, "rows_per_band": -(-h // world),
+                       "collective": "grouped ncclSend / ncclRecv of RGBA8 bands to rank 0" if world > 1 else "none",
+                       "l2": f"inputs larger than L2 (layer arena {st['layer_floats'] * 4 / 2**30:.2f} GiB on rank 0)"},
+            "clocks": sampler.summary(), "gpu_launches": int(st["n_kernels"]) * opts.steps,
+            "max_lsb_vs_reference_bytes": check}))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -605,6 +686,8 @@ def main():
     ap.add_argument("--seed0", type=int, default=0, help="first icon seed (diagnostics: render another rank's batch)")
     ap.add_argument("--batches", type=int, default=8, help="distinct icon batches kept resident (steps cycle through them)")
     ap.add_argument("--no-configs", action="store_true", help="skip timing BASELINE.json's configs c2 / c4")
+    ap.add_argument("--config", default="c5", choices=["c5", "c2", "c4"],
+                    help="c5 (default): the icon batch, whole SVGs per rank; c2 / c4: one big render in row bands")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--e2e-workers", type=int, default=3, help="host threads (contexts) of the e2e leg")
@@ -612,6 +695,8 @@ def main():
     opts = ap.parse_args()
     if opts.impl == "reference":
         run_reference(opts)
+    elif opts.config != "c5":
+        run_bands(opts)
     else:
         run_gpu(opts)
 

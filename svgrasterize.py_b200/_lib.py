@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("SVGR_LIB") or os.path.join(HERE, "libsvgr_b200.so")  
 
 # ---- record layouts (must match csrc/svgr_types.h and include/svgr_b200.h) ----------------
 PATH_DT = np.dtype([("m", "<f8", 6), ("viewport", "<i4", 4), ("has_viewport", "<i4"), ("fill_rule", "<i4"),
-                    ("pad", "<i4", 2)], align=True)
+                    ("has_full", "<i4"), ("pad", "<i4"), ("full_viewport", "<i4", 4)], align=True)
 STROKE_DT = np.dtype([("half_width", "<f8"), ("sub_begin", "<i4"), ("sub_end", "<i4"), ("cap", "<i4"), ("join", "<i4"),
                       ("path", "<i4"), ("pad", "<i4")], align=True)
 PAINT_DT = np.dtype([("kind", "<i4"), ("spread", "<i4"), ("stop_off", "<i4"), ("stop_cnt", "<i4"), ("has_m2", "<i4"),

@@ -208,6 +208,10 @@ struct svgr_ctx {
     long long edge_cap = 0;
     long long n_edges = 0;
     std::vector<PathBox> h_boxes;
+    std::vector<PathBox> h_full_boxes;  // band renders: the boxes the whole-canvas render would give (else empty)
+    bool band_mode = false;             // some path carries a full viewport
+    DevBuf d_full_boxes;
+    PinBuf pin_full_boxes;
     PinBuf pin_boxes, pin_status, pin_plan, pin_out, pin_masks;
 
     // ---- plan state
@@ -438,6 +442,135 @@ struct Planner {
 
     static int py_int(double v) { return (int)v; }  // Python int(): truncation toward zero
 
+    // ---- row-band renders.  Masks are clipped to the band, so a layer's origin differs from the one
+    // the whole-canvas render would compute -- and Layer.convolve (:114) / filter_offset (:1849) truncate *toward
+    // zero* from that origin: int(r0 - kw / 2) is a ceiling for a layer that starts within half a kernel of row 0
+    // and a floor below it.  A band must place its filter results where the full render does, or the bands do not
+    // join up.  The planner therefore also tracks, per node, the box of the full render (from the paths' boxes
+    // against the full viewport, same box algebra, no ops) and takes the truncations from it.
+    struct SBox {
+        bool live = false;
+        int r0 = 0, c0 = 0, rows = 0, cols = 0;
+    };
+    std::vector<SBox> shadow;  // empty unless the program is a band render
+
+    SBox shadow_union(const svgr_node &n, const int32_t *ch, bool intersect, bool need_all) const
+    {
+        SBox o;
+        int r0 = 0, c0 = 0, r1 = 0, c1 = 0;
+        for (int k = 0; k < n.child_cnt; k++) {
+            const SBox &b = shadow[ch[k]];
+            if (!b.live) {
+                if (need_all)
+                    return SBox();
+                continue;
+            }
+            if (!o.live) {
+                r0 = b.r0, c0 = b.c0, r1 = b.r0 + b.rows, c1 = b.c0 + b.cols;
+                o.live = true;
+            } else if (intersect) {
+                r0 = std::max(r0, b.r0), c0 = std::max(c0, b.c0);
+                r1 = std::min(r1, b.r0 + b.rows), c1 = std::min(c1, b.c0 + b.cols);
+            } else {
+                r0 = std::min(r0, b.r0), c0 = std::min(c0, b.c0);
+                r1 = std::max(r1, b.r0 + b.rows), c1 = std::max(c1, b.c0 + b.cols);
+            }
+        }
+        if (!o.live || r1 <= r0 || c1 <= c0)
+            return SBox();
+        o.r0 = r0, o.c0 = c0, o.rows = r1 - r0, o.cols = c1 - c0;
+        return o;
+    }
+
+    // the box node i has in the whole-canvas render (mirrors the box logic of node() below)
+    void shadow_node(int i)
+    {
+        const svgr_node &n = ctx->h_nodes[i];
+        const int32_t *ch = ctx->h_children.data() + n.child_off;
+        SBox o;
+        auto child = [&](int k) -> SBox { return (k < n.child_cnt && ch[k] >= 0 && ch[k] < i) ? shadow[ch[k]] : SBox(); };
+        switch (n.tag) {
+        case SVGR_N_LEAF:
+            if (n.a >= 0 && n.a < ctx->n_path) {
+                const PathBox &b = ctx->h_full_boxes[n.a];
+                if (b.rows > 0 && b.cols > 0) {
+                    o.live = true, o.r0 = b.r0, o.c0 = b.c0, o.rows = b.rows, o.cols = b.cols;
+                    if (n.b >= 0 && n.b < ctx->n_paint && ctx->h_paints[n.b].kind == PAINT_PATTERN &&
+                        !(n.d >= 0 && n.d < i && shadow[n.d].live))
+                        o = SBox();
+                }
+            }
+            break;
+        case SVGR_N_GROUP:
+            o = shadow_union(n, ch, false, false);
+            break;
+        case SVGR_N_IN:
+            o = shadow_union(n, ch, true, true);
+            break;
+        case SVGR_N_COMPOSE:
+            o = shadow_union(n, ch, n.a == MODE_IN || (n.flags & 4), true);
+            break;
+        case SVGR_N_OPACITY:
+        case SVGR_N_LUMA:
+        case SVGR_N_SRC_ALPHA:
+        case SVGR_N_CONVERT:
+        case SVGR_N_CMATRIX:
+        case SVGR_N_CANVAS:
+            o = child(0);
+            break;
+        case SVGR_N_BLUR: {
+            o = child(0);
+            if (o.live && n.a >= 0 && n.a < (int)ctx->h_kernels.size()) {
+                const svgr_kernel &kn = ctx->h_kernels[n.a];
+                const int r0 = py_int((double)o.r0 - kn.rows / 2.0), c0 = py_int((double)o.c0 - kn.cols / 2.0);
+                o.rows += kn.rows - 1, o.cols += kn.cols - 1, o.r0 = r0, o.c0 = c0;
+            }
+            break;
+        }
+        case SVGR_N_MORPH:
+            o = child(0);
+            if (o.live) {
+                o.rows -= n.a - 1, o.cols -= n.b - 1;
+                if (o.rows <= 0 || o.cols <= 0)
+                    o = SBox();
+            }
+            break;
+        case SVGR_N_OFFSET:
+            o = child(0);
+            if (o.live && n.a >= 0 && (size_t)(n.a + 1) * 12 <= ctx->h_offset_tr.size()) {
+                int dr, dc;
+                offset_shift(n, o.r0, o.c0, &dr, &dc);
+                o.r0 += dr, o.c0 += dc;
+            }
+            break;
+        case SVGR_N_MERGE_AT:
+            if (child(0).live && n.c > 0 && n.d > 0)
+                o.live = true, o.r0 = n.a, o.c0 = n.b, o.rows = n.c, o.cols = n.d;
+            break;
+        case SVGR_N_EXTERNAL:
+            if (n.a >= 0 && n.a < (int)ctx->h_ext.size() && ctx->h_ext[n.a].rows > 0 && ctx->h_ext[n.a].cols > 0) {
+                const svgr_external &e = ctx->h_ext[n.a];
+                o.live = true, o.r0 = e.r0, o.c0 = e.c0, o.rows = e.rows, o.cols = e.cols;
+            }
+            break;
+        default:
+            break;
+        }
+        shadow[i] = o;
+    }
+
+    // filter_offset (svgrasterize.py:1844-1850) for a layer whose origin is (r0, c0): the integer shift.  1-D points
+    // go through numpy's vector @ matrix path, whose rounding is fma(x, m0, y * m1) + m2.
+    void offset_shift(const svgr_node &n, int r0, int c0, int *dr, int *dc) const
+    {
+        const double *f = ctx->h_offset_tr.data() + 12 * n.a, *inv = f + 6;
+        double x = r0, y = c0;
+        double ux = fma(x, inv[0], y * inv[1]) + inv[2], uy = fma(x, inv[3], y * inv[4]) + inv[5];
+        ux = ux + n.f[0], uy = uy + n.f[1];
+        double tx = fma(ux, f[0], uy * f[1]) + f[2], ty = fma(ux, f[3], uy * f[4]) + f[5];
+        *dr = py_int(tx) - r0, *dc = py_int(ty) - c0;
+    }
+
     // A separable stencil pass whose source is a materialised RGBA layer runs on the TMA-fed kernels
     // (k_stencil_tma.cu): the layer is a tensor, tile + halo a zero-filled box of it.  Anything else (coverage x
     // paint, one-channel layers) is read element by element through fetch_src by the generic kernel.
@@ -516,8 +649,14 @@ struct Planner {
                 } else if (p.kind == PAINT_RADIAL_FOCAL) {
                     FocalJob j;
                     j.paint = n.b, j.r0 = m.r0, j.c0 = m.c0, j.rows = m.rows, j.cols = m.cols;
+                    if (!ctx->h_full_boxes.empty()) {
+                        // "any det < 0" (:1621) is a property of the whole mask box, not of the band's part of it
+                        const PathBox &fb = ctx->h_full_boxes[n.a];
+                        if (fb.rows > 0 && fb.cols > 0)
+                            j.r0 = fb.r0, j.c0 = fb.c0, j.rows = fb.rows, j.cols = fb.cols;
+                    }
                     j.block_base = n_focal_blocks;
-                    n_focal_blocks += (int)(((long long)m.rows * m.cols + 1023) / 1024);
+                    n_focal_blocks += (int)(((long long)j.rows * j.cols + 1023) / 1024);
                     focal_p->push_back(j);
                 }
             }
@@ -654,7 +793,10 @@ struct Planner {
             const Val v = kn.separable ? stencil_source(v_in, kn.rows, kn.cols, 0, 1) : v_in;
             // Layer.convolve (svgrasterize.py:106-115): full convolution on straight-alpha linear RGBA
             int orows = v.rows + kn.rows - 1, ocols = v.cols + kn.cols - 1;
-            int r0 = py_int((double)v.r0 - kn.rows / 2.0), c0 = py_int((double)v.c0 - kn.cols / 2.0);
+            // the truncation toward zero is taken where the whole-canvas render takes it (band renders: shadow box)
+            const int fr0 = (!shadow.empty() && shadow[ch[0]].live) ? shadow[ch[0]].r0 : v.r0;
+            const int fc0 = (!shadow.empty() && shadow[ch[0]].live) ? shadow[ch[0]].c0 : v.c0;
+            int r0 = v.r0 + (py_int((double)fr0 - kn.rows / 2.0) - fr0), c0 = v.c0 + (py_int((double)fc0 - kn.cols / 2.0) - fc0);
             if (kn.separable) {
                 Val tmp = alloc(SRC_L4, v.r0, c0, v.rows, ocols, 0, 1, v.level + 1);
                 emit(stencil_cls(v, true), OP_STENCIL_H, tmp, {src_of(v, 0, 1)}, 0, 0, 1.0f, tmp.level, nullptr,
@@ -709,17 +851,14 @@ struct Planner {
                 err = "offset: bad transform index";
                 return false;
             }
-            // filter_offset (svgrasterize.py:1844-1850): 1-D points go through numpy's vector @ matrix
-            // path, whose rounding is fma(x, m0, y*m1) + m2
-            const double *f = ctx->h_offset_tr.data() + 12 * n.a, *inv = f + 6;
-            double x = v.r0, y = v.c0;
-            double ux = fma(x, inv[0], y * inv[1]) + inv[2], uy = fma(x, inv[3], y * inv[4]) + inv[5];
-            ux = ux + n.f[0], uy = uy + n.f[1];
-            double tx = fma(ux, f[0], uy * f[1]) + f[2], ty = fma(ux, f[3], uy * f[4]) + f[5];
+            // filter_offset (svgrasterize.py:1844-1850); the shift is computed from the origin the layer has in the
+            // whole-canvas render (band renders: shadow box)
             // paint is evaluated at global pixel centres and stencils are anchored: move only real layers
             out = (v.kind == SRC_COVPAINT || v.kind == VAL_LUMA || v.st_kind) ? materialize(v) : v;
             {
-                int dr = py_int(tx) - v.r0, dc = py_int(ty) - v.c0;
+                const bool sh = !shadow.empty() && shadow[ch[0]].live;
+                int dr, dc;
+                offset_shift(n, sh ? shadow[ch[0]].r0 : v.r0, sh ? shadow[ch[0]].c0 : v.c0, &dr, &dc);
                 out.r0 += dr, out.c0 += dc, out.br0 += dr, out.bc0 += dc;
             }
             break;
@@ -869,6 +1008,9 @@ struct Planner {
         uses_p = &c->node_uses;
         chunk_bounds = c->chunk_bounds;
         c->vals.resize(c->n_node);  // every entry is assigned by plan_range before anyone reads it
+        shadow.clear();
+        if (!c->h_full_boxes.empty())
+            shadow.resize((size_t)c->n_node);
         return true;
     }
 
@@ -934,6 +1076,8 @@ struct Planner {
     {
         svgr_ctx *c = ctx;
         for (int i = a; i < b; i++) {
+            if (!shadow.empty())
+                shadow_node(i);
             // a value nobody reads is not computed (SourceAlpha of a filter that only uses SourceGraphic,
             // svgrasterize.py:1803-1809, is the common case)
             const svgr_node &n = c->h_nodes[i];
@@ -1223,6 +1367,9 @@ static int load_program(svgr_ctx *ctx, const svgr_program *p, cudaStream_t s, bo
     ctx->n_node = p->n_node, ctx->canvas_bytes = p->canvas_bytes;
     ctx->n_weight = p->n_weight, ctx->n_matrix = p->n_matrix;
     ctx->flatness = p->flatness;
+    ctx->band_mode = false;
+    for (int i = 0; i < p->n_path && !ctx->band_mode; i++)
+        ctx->band_mode = p->paths[i].has_full != 0;
     if (!host_only) {
         CK(upload(ctx->d_seg_tag, p->seg_tag, (size_t)p->n_seg, s));
         CK(upload(ctx->d_seg_data, p->seg_data, (size_t)p->n_seg * 8, s));
@@ -1377,8 +1524,16 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
                                              &d_st->n_edges, ctx->d_minmax.as<unsigned long long>(), SM, &ovf, s);
                 n_kernels += SVGR_FLAT_PASSES - 1;
             }
+            if (ctx->band_mode) {
+                CK(ctx->d_full_boxes.ensure((size_t)std::max(ctx->n_path, 1) * sizeof(PathBox)));
+                CK(ctx->pin_full_boxes.ensure((size_t)std::max(ctx->n_path, 1) * sizeof(PathBox)));
+            }
             svgr_launch_bounds(ctx->d_minmax.as<unsigned long long>(), ctx->d_paths.as<PathRec>(), ctx->n_path,
-                               ctx->d_boxes.as<PathBox>(), ctx->d_minmax_f64.as<double>(), s);
+                               ctx->d_boxes.as<PathBox>(), ctx->band_mode ? ctx->d_full_boxes.as<PathBox>() : nullptr,
+                               ctx->d_minmax_f64.as<double>(), s);
+            if (ctx->band_mode && ctx->n_path > 0)
+                CK(cudaMemcpyAsync(ctx->pin_full_boxes.p, ctx->d_full_boxes.p, (size_t)ctx->n_path * sizeof(PathBox),
+                                   cudaMemcpyDeviceToHost, s));
             n_kernels += (ctx->n_seg > 0) + (S > 0) + (ctx->n_path > 0);
             if (ctx->n_path > 0)
                 CK(cudaMemcpyAsync(ctx->pin_boxes.p, ctx->d_boxes.p, (size_t)ctx->n_path * sizeof(PathBox),
@@ -1423,6 +1578,10 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
     if (ctx->n_edges > 0x7fffffffll / 4)
         FAIL(SVGR_E_UNSUPPORTED, "more than 2^29 edges in one program: the band scans are 32-bit");
     ctx->h_boxes.assign((PathBox *)ctx->pin_boxes.p, (PathBox *)ctx->pin_boxes.p + ctx->n_path);
+    if (ctx->band_mode && stop_after != SVGR_STOP_STROKE)
+        ctx->h_full_boxes.assign((PathBox *)ctx->pin_full_boxes.p, (PathBox *)ctx->pin_full_boxes.p + ctx->n_path);
+    else
+        ctx->h_full_boxes.clear();
 
     if (stats) {
         memset(stats, 0, sizeof *stats);
@@ -1886,7 +2045,7 @@ void svgr_destroy(svgr_ctx *ctx)
                       &ctx->d_focal_jobs, &ctx->d_focal_flags, &ctx->d_canvas, &ctx->d_q, &ctx->d_tile_map, &ctx->d_tile_rec, &ctx->d_bin_data, &ctx->d_heads[0], &ctx->d_heads[1], &ctx->d_lists[0],
                       &ctx->d_lists[1], &ctx->d_ovf_cubic[0], &ctx->d_ovf_cubic[1], &ctx->d_ovf_path[0], &ctx->d_ovf_path[1],
                       &ctx->d_ovf_depth[0], &ctx->d_ovf_depth[1], &ctx->d_ovf_counts, &ctx->d_eager[0], &ctx->d_eager[1],
-                      &ctx->d_eager[2], &ctx->d_tmaps, &ctx->d_png_segs, &ctx->d_png_canvases, &ctx->d_png_scratch,
+                      &ctx->d_eager[2], &ctx->d_tmaps, &ctx->d_full_boxes, &ctx->d_png_segs, &ctx->d_png_canvases, &ctx->d_png_scratch,
                       &ctx->d_png_seg_bytes, &ctx->d_png_seg_adler, &ctx->d_png_file_bytes, &ctx->d_png_file_off,
                       &ctx->d_png_out, &ctx->d_png_in};
     for (DevBuf *b : bufs)
@@ -1894,6 +2053,7 @@ void svgr_destroy(svgr_ctx *ctx)
     ctx->pin_boxes.release(), ctx->pin_status.release(), ctx->pin_plan.release(), ctx->pin_out.release();
     ctx->pin_masks.release();
     ctx->pin_tmaps.release();
+    ctx->pin_full_boxes.release();
     ctx->pin_png.release();
     for (auto &e : ctx->ev_png)
         if (e)
@@ -2154,6 +2314,7 @@ int svgr_debug_plan(const svgr_program *prog, const int32_t *boxes, int reps, fl
     int rc = load_program(ctx, prog, nullptr, true);
     if (rc == SVGR_OK) {
         ctx->h_boxes.assign((const PathBox *)boxes, (const PathBox *)boxes + ctx->n_path);
+        ctx->h_full_boxes.clear();
         ctx->h_masks_store.resize((size_t)ctx->n_path + 1);
         ctx->h_masks = ctx->h_masks_store.data();
         float best_m = 1e30f, best_n = 1e30f;

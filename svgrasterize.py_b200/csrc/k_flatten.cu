@@ -339,12 +339,13 @@ __global__ void minmax_init_kernel(unsigned long long *minmax, int n_paths)
 
 // Mask sizing (svgrasterize.py:961-975): floor(min) - 1, ceil(max) + 1, clipped to the viewport.
 __global__ void bounds_kernel(const unsigned long long *__restrict__ minmax, const PathRec *__restrict__ paths,
-                              int n_paths, PathBox *__restrict__ boxes, double *__restrict__ minmax_f64)
+                              int n_paths, PathBox *__restrict__ boxes, PathBox *__restrict__ full_boxes,
+                              double *__restrict__ minmax_f64)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_paths)
         return;
-    PathBox b = {0, 0, 0, 0};
+    PathBox b = {0, 0, 0, 0}, fb = {0, 0, 0, 0};
     if (minmax[4 * i + 0] != ~0ull) {
         double mn_r = of_key(minmax[4 * i + 0]), mn_c = of_key(minmax[4 * i + 1]);
         double mx_r = of_key(minmax[4 * i + 2]), mx_c = of_key(minmax[4 * i + 3]);
@@ -358,23 +359,33 @@ __global__ void bounds_kernel(const unsigned long long *__restrict__ minmax, con
         long long min_r = (long long)floor(mn_r) - 1, min_c = (long long)floor(mn_c) - 1;
         long long max_r = (long long)ceil(mx_r) + 1, max_c = (long long)ceil(mx_c) + 1;
         const PathRec &p = paths[i];
-        if (p.has_viewport) {
-            long long vx = p.viewport[0], vy = p.viewport[1], vw = p.viewport[2], vh = p.viewport[3];
-            if (min_r < vx) min_r = vx;
-            if (min_c < vy) min_c = vy;
-            if (max_r > vx + vw) max_r = vx + vw;
-            if (max_c > vy + vh) max_c = vy + vh;
-        }
-        long long rows = max_r - min_r, cols = max_c - min_c;
-        if (rows > 0 && cols > 0) {
-            b.r0 = (int32_t)min_r, b.c0 = (int32_t)min_c;
-            b.rows = (int32_t)(rows < 0x7fffffff ? rows : 0x7fffffff);
-            b.cols = (int32_t)(cols < 0x7fffffff ? cols : 0x7fffffff);
-        }
+        auto clip_box = [&](bool has, const int32_t *vp, PathBox &o) {
+            long long a_r = min_r, a_c = min_c, z_r = max_r, z_c = max_c;
+            if (has) {
+                long long vx = vp[0], vy = vp[1], vw = vp[2], vh = vp[3];
+                if (a_r < vx) a_r = vx;
+                if (a_c < vy) a_c = vy;
+                if (z_r > vx + vw) z_r = vx + vw;
+                if (z_c > vy + vh) z_c = vy + vh;
+            }
+            long long rows = z_r - a_r, cols = z_c - a_c;
+            if (rows > 0 && cols > 0) {
+                o.r0 = (int32_t)a_r, o.c0 = (int32_t)a_c;
+                o.rows = (int32_t)(rows < 0x7fffffff ? rows : 0x7fffffff);
+                o.cols = (int32_t)(cols < 0x7fffffff ? cols : 0x7fffffff);
+            }
+        };
+        clip_box(p.has_viewport != 0, p.viewport, b);
+        if (p.has_full)
+            clip_box(true, p.full_viewport, fb);  // the box the whole-canvas render would give this mask
+        else
+            fb = b;
     } else if (minmax_f64) {
         minmax_f64[4 * i + 0] = minmax_f64[4 * i + 1] = minmax_f64[4 * i + 2] = minmax_f64[4 * i + 3] = 0.0;
     }
     boxes[i] = b;
+    if (full_boxes)
+        full_boxes[i] = fb;
 }
 
 // User-space bounding box of a set of paths' end points: ConvexHull.bbox
@@ -465,10 +476,11 @@ void svgr_launch_flatten_overflow(const PathRec *paths, double thr, double *edge
 }
 
 void svgr_launch_bounds(const unsigned long long *minmax, const PathRec *paths, int n_paths, PathBox *boxes,
+                        PathBox *full_boxes,
                         double *minmax_f64, cudaStream_t s)
 {
     if (n_paths > 0)
-        bounds_kernel<<<(n_paths + 255) / 256, 256, 0, s>>>(minmax, paths, n_paths, boxes, minmax_f64);
+        bounds_kernel<<<(n_paths + 255) / 256, 256, 0, s>>>(minmax, paths, n_paths, boxes, full_boxes, minmax_f64);
 }
 
 void svgr_launch_cloud_bounds(const double *edges, const uint32_t *edge_path, const unsigned long long *n_edges,

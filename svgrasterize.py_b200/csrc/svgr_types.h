@@ -25,7 +25,12 @@ struct PathRec {
     int32_t viewport[4];  // (r0, c0, rows, cols) clip, svgrasterize.py:968-971
     int32_t has_viewport;
     int32_t fill_rule;  // 0 nonzero (also None), 1 evenodd
-    int32_t pad[2];
+    // Row-band renders clip masks to the band (+ halo) but place filter results where the full-canvas render would
+    // (Layer.convolve / filter_offset truncate toward zero from the layer's origin, :114 / :1849): has_full = 1 adds
+    // the viewport of the whole canvas, against which a second box is computed.
+    int32_t has_full;
+    int32_t pad;
+    int32_t full_viewport[4];
 };
 
 // Per-path result of flatten + bounds (svgrasterize.py:961-975).

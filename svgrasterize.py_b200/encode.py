@@ -329,7 +329,7 @@ class Encoder:
         rule = fill_rule_code(fill_rule)
         tags, data, _sub = device_path(path)
         pid = len(self.paths)
-        self.paths.append((m6(transform), self._viewport(viewport), rule))
+        self.paths.append((m6(transform), self._viewport(viewport), rule, self._viewport(self.cloud_viewport)))
         if len(tags):
             self.seg_tag.append(tags)
             self.seg_data.append(data)
@@ -341,7 +341,7 @@ class Encoder:
             raise ValueError(f"unkown line cap type: `{linecap}`")  # svgrasterize.py:1492
         tags, data, sub_off = device_path(path)
         pid = len(self.paths)
-        self.paths.append((m6(transform), self._viewport(viewport), 0))
+        self.paths.append((m6(transform), self._viewport(viewport), 0, self._viewport(self.cloud_viewport)))
         job = len(self.strokes)
         sub_begin = len(self.s_sub_job)
         nsub = len(sub_off) - 1
@@ -748,10 +748,13 @@ class Encoder:
         n = len(self.paths)
         p.paths = np.zeros(n, _lib.PATH_DT)
         if n:
-            p.paths["m"] = np.asarray([m for m, _vp, _r in self.paths], dtype=np.float64).reshape(n, 6)
-            p.paths["has_viewport"] = [vp is not None for _m, vp, _r in self.paths]
-            p.paths["viewport"] = [vp if vp is not None else (0, 0, 0, 0) for _m, vp, _r in self.paths]
-            p.paths["fill_rule"] = [r for _m, _vp, r in self.paths]
+            p.paths["m"] = np.asarray([rec[0] for rec in self.paths], dtype=np.float64).reshape(n, 6)
+            p.paths["has_viewport"] = [rec[1] is not None for rec in self.paths]
+            p.paths["viewport"] = [rec[1] if rec[1] is not None else (0, 0, 0, 0) for rec in self.paths]
+            p.paths["fill_rule"] = [rec[2] for rec in self.paths]
+            # row-band renders: the whole canvas' viewport, against which filter origins are computed
+            p.paths["has_full"] = [rec[3] is not None for rec in self.paths]
+            p.paths["full_viewport"] = [rec[3] if rec[3] is not None else (0, 0, 0, 0) for rec in self.paths]
         n = len(self.strokes)
         p.strokes = np.zeros(n, _lib.STROKE_DT)
         if n:

@@ -31,51 +31,65 @@ def band_rows(height: int, world: int, rank: int):
 
 def gather_bands(band, height: int, width: int, world: int, rank: int, dist=None, dst: int = 0):
     """band: (rows, width, 4) uint8 tensor of this rank (CUDA with NCCL, CPU with gloo).  Returns the
-    (height, width, 4) canvas on `dst`, None elsewhere."""
+    (height, width, 4) canvas on `dst`, None elsewhere.  The only collective of a row-band render (SURVEY.md
+    8(e)): every other rank sends its band, `dst` receives each into its rows of the canvas -- one grouped
+    send / receive (ncclGroupStart ... ncclSend / ncclRecv ... ncclGroupEnd under torch's batch_isend_irecv),
+    nothing is broadcast and nobody but `dst` allocates the canvas."""
     import torch
 
-    step = -(-int(height) // int(world))
     if world == 1:
         return band[:height]
-    buf = torch.zeros((step, width, 4), dtype=torch.uint8, device=band.device)
-    buf[: band.shape[0]] = band
-    out = torch.empty((world * step, width, 4), dtype=torch.uint8, device=band.device) if rank == dst else None
-    if dist.get_backend() == "nccl":
-        # NCCL has no gather primitive for unequal roots in older torch; all ranks contribute, dst keeps
-        full = out if out is not None else torch.empty((world * step, width, 4), dtype=torch.uint8, device=band.device)
-        dist.all_gather_into_tensor(full.view(-1), buf.view(-1))
-        return full[:height] if rank == dst else None
-    parts = [torch.empty_like(buf) for _ in range(world)] if rank == dst else None
-    dist.gather(buf, parts, dst=dst)
-    if rank != dst:
-        return None
-    return torch.cat(parts, dim=0)[:height]
+    ops, out = [], None
+    if rank == dst:
+        out = torch.empty((height, width, 4), dtype=torch.uint8, device=band.device)
+        a, b = band_rows(height, world, rank)
+        out[a:b] = band
+        for r in range(world):
+            ra, rb = band_rows(height, world, r)
+            if r != dst and rb > ra:
+                ops.append(dist.P2POp(dist.irecv, out[ra:rb], r))
+    elif band.shape[0] > 0:
+        ops.append(dist.P2POp(dist.isend, band.contiguous(), dst))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return out
 
 
-def render_band(engine, scene, size, world: int, rank: int, linear_rgb: bool = False):
-    """Render this rank's row band of `scene` (canvas size = (width, height)); returns (rows, width, 4) uint8."""
+def band_program(engine, scene, size, world: int, rank: int, linear_rgb: bool = False):
+    """The scene program of this rank's row band (masks clipped to the band + the filters' reach, filter results
+    placed where the whole-canvas render places them) and the band's rows [a, b)."""
     from .encode import Encoder
 
-    w, h = int(size[0]), int(size[1])
+    h = int(size[1])
     a, b = band_rows(h, world, rank)
     probe = Encoder(engine)
     probe.add_scene(scene, size, linear_rgb)  # host-only pass to learn the filter reach
     halo = probe.filter_reach()
     enc = Encoder(engine)
     enc.add_scene_band(scene, size, (a, b), halo, linear_rgb)
-    prog = enc.finish()
+    return enc.finish(), (a, b)
+
+
+def render_band(engine, scene, size, world: int, rank: int, linear_rgb: bool = False, device_out: bool = False):
+    """Render this rank's row band of `scene` (canvas size = (width, height)) -> (rows, width, 4) uint8: a numpy
+    array, or with device_out a torch CUDA tensor that never left the GPU (what gather_bands sends)."""
+    w = int(size[0])
+    prog, (a, b) = band_program(engine, scene, size, world, rank, linear_rgb)
+    if device_out:
+        import torch
+
+        out = torch.empty(max(prog.canvas_bytes, 4), dtype=torch.uint8, device=f"cuda:{engine.device}")
+        engine.render(prog, out=out)
+        return out[: prog.canvas_bytes].view(b - a, w, 4)
     res = engine.render(prog)
     return np.asarray(res["canvas"]).reshape(b - a, w, 4) if b > a else np.zeros((0, w, 4), np.uint8)
 
 
 def render_distributed(engine, scene, size, linear_rgb: bool = False, dist=None):
-    """Row-band render of one scene over all ranks of the default process group; the canvas lands on rank 0."""
-    import torch
-
+    """Row-band render of one scene over all ranks of the default process group: every band is rendered into device
+    memory and goes to rank 0 over NCCL from there; rank 0 returns the canvas (a CUDA tensor), the others None."""
     world = dist.get_world_size() if dist is not None else 1
     rank = dist.get_rank() if dist is not None else 0
-    band = torch.from_numpy(render_band(engine, scene, size, world, rank, linear_rgb))
-    if dist is not None and dist.get_backend() == "nccl":
-        band = band.cuda()
-    out = gather_bands(band, int(size[1]), int(size[0]), world, rank, dist)
-    return None if out is None else out.cpu().numpy()
+    band = render_band(engine, scene, size, world, rank, linear_rgb, device_out=True)
+    return gather_bands(band, int(size[1]), int(size[0]), world, rank, dist)

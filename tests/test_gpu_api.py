@@ -171,9 +171,6 @@ def test_row_bands_reassemble_to_the_full_render(B, O):
     from svgrasterize_b200.engine import default_engine
 
     eng = default_engine()
-    # the blurred layer must start at least half a kernel below the canvas top: Layer.convolve places its
-    # result at int(r0 - kw / 2) (svgrasterize.py:114), which truncates toward zero, i.e. shifts by one pixel
-    # when that value is negative -- a band (whose clipped source starts lower) cannot reproduce that quirk.
     for scene, size in ((synth.filter_stack_scene(320), (320, 320)), (synth.icon_scene(1), synth.icon_size())):
         full = B.render_canvas(scene, size)
         for world in (2, 3):
@@ -181,6 +178,40 @@ def test_row_bands_reassemble_to_the_full_render(B, O):
             got = np.concatenate(bands, axis=0)
             assert got.shape == full.shape
             assert int(np.abs(got.astype(int) - full.astype(int)).max()) <= 1, (world, size)
+    dev = P.render_band(eng, synth.icon_scene(1), synth.icon_size(), 2, 1, device_out=True)
+    assert dev.is_cuda and tuple(dev.shape) == (128, 256, 4)
+
+
+def test_row_bands_place_filter_results_where_the_full_render_does(B, O):
+    """Layer.convolve puts its result at int(r0 - kw / 2) (svgrasterize.py:114) and feOffset shifts by int(...)
+    (:1849): truncation toward ZERO, i.e. a ceiling for a layer that starts within half a kernel of row 0 and a
+    floor for one that starts lower.  A band sees the layer clipped to its own rows, so it takes the truncation from
+    the box the whole-canvas render gives the layer (planner shadow boxes): the bands of a blurred / offset shape
+    that touches the canvas top must join up with no seam, and the two-circle gradient's any(det < 0) rule (:1621)
+    must be decided over the whole mask."""
+    from svgrasterize_b200 import parallel as P, scene as S, synth
+    from svgrasterize_b200.engine import default_engine
+
+    eng = default_engine()
+    w = h = 240
+    stops = [(0.0, synth.color(0.9, 0.2, 0.1)), (1.0, synth.color(0.1, 0.3, 0.9, 0.7))]
+    focal = S.GradRadial(np.array([120.0, 60.0]), 70.0, np.array([120.0 + 90.0, 60.0]), None, stops, None, "pad", False, None)
+    tall = synth.rect_path(30, 1, 180, 230, 12.0)  # starts at row 1: int(r0 - kw / 2) is negative in the full render
+    flt = S.Filter.empty().blur(3.0, 3.0).offset(2.6, -3.4)
+    scenes = [
+        S.Scene.fill(tall, focal).filter(flt),
+        S.Scene.group([S.Scene.fill(tall, synth.color(0.2, 0.6, 0.3)),
+                       S.Scene.fill(synth.ellipse_path(120, 200, 30), synth.color(0.9, 0.8, 0.1))]).filter(
+                           S.Filter.empty().blur(5.0, 2.0).morphology(2.0, 2.0, "max", None)),
+    ]
+    for scene in scenes:
+        full = B.render_canvas(scene, (w, h))
+        ref = O.render_canvas(scene, (w, h))
+        assert int(np.abs(full.astype(int) - ref.astype(int)).max()) <= 1
+        for world in (2, 3, 5):
+            got = np.concatenate([P.render_band(eng, scene, (w, h), world, r) for r in range(world)], axis=0)
+            assert got.shape == full.shape
+            assert int(np.abs(got.astype(int) - full.astype(int)).max()) <= 1, world
 
 
 def test_empty_and_degenerate_inputs(B, O):

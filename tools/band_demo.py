@@ -49,6 +49,7 @@ def main():
             prog = enc.finish()
             full = eng.canvas(prog, eng.render(prog)["canvas"])
             dt_full = time.perf_counter() - t1
+            out = out.cpu().numpy()
             diff = int(np.abs(out.astype(int) - full.astype(int)).max())
             print(f"{name} {sz[0]}x{sz[1]} on {world} GPUs: bands + NCCL gather {dt * 1e3:.1f} ms "
                   f"(one GPU, full canvas, incl. encode: {dt_full * 1e3:.1f} ms), max |bands - full| = {diff} LSB",
