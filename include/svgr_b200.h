@@ -174,7 +174,8 @@ typedef struct svgr_stats {
     int64_t n_kernels;      /* kernel launches issued by this call */
     float ms_total, ms_h2d, ms_stroke, ms_flatten, ms_plan, ms_bin, ms_coverage, ms_compose, ms_canvas, ms_d2h;
     int32_t retries;
-    int32_t pad;
+    int32_t plan_cached; /* 1: the render reused the plan (tables, tile lists, tensor maps) of the one before: same
+                            program, same path boxes */
     float host_plan_masks_ms, host_plan_nodes_ms; /* wall time of the two host planning phases */
     float ms_compose_busy; /* sum over plan chunks of first-launch -> last-launch device time: ms_compose minus
                               the waits for the host planner */

@@ -68,7 +68,7 @@ class Stats(C.Structure):
                                          "n_kernels")] + \
                [(n, C.c_float) for n in ("ms_total", "ms_h2d", "ms_stroke", "ms_flatten", "ms_plan", "ms_bin",
                                          "ms_coverage", "ms_compose", "ms_canvas", "ms_d2h")] + \
-               [("retries", C.c_int32), ("pad", C.c_int32), ("host_plan_masks_ms", C.c_float),
+               [("retries", C.c_int32), ("plan_cached", C.c_int32), ("host_plan_masks_ms", C.c_float),
                 ("host_plan_nodes_ms", C.c_float), ("ms_compose_busy", C.c_float), ("pad2", C.c_float),
                 ("compose_bytes_8d", C.c_int64), ("png_bytes", C.c_int64), ("ms_png", C.c_float), ("pad3", C.c_float)]
 

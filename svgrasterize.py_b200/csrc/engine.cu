@@ -227,11 +227,20 @@ struct svgr_ctx {
     long long mask_pixels = 0, layer_pixels = 0, compose_bytes = 0, compose_bytes_8d = 0, canvas_pixels = 0;
     int n_levels = 0;
     DevBuf d_masks, d_band_cnt, d_band_off, d_band_cur, d_bin_edges, d_cov, d_layers, d_ops, d_srcs, d_focal_jobs,
-        d_focal_flags, d_canvas, d_q, d_tile_map, d_tile_rec, d_bin_data, d_heads[2], d_lists[2], d_ovf_cubic[2],
+        d_focal_flags, d_canvas, d_q, d_tile_map, d_tile_rec, d_bin_data, d_heads, d_lists, d_ovf_cubic[2],
         d_ovf_path[2], d_ovf_depth[2], d_ovf_counts;
     long long bin_cap = 0;
     long long n_binned = 0;
     bool planned = false, covered = false, composed = false;
+    // Plan cache: the plan is a function of (program, path boxes, arena addresses).  A re-render of the resident
+    // program that finds the same boxes keeps every table the last render left on the device (masks, ops, sources,
+    // per-tile source lists, focal flags, tensor maps) and only repeats the launches: no host planning, no uploads,
+    // no culls.
+    bool plan_cached = false;
+    std::vector<PathBox> cache_boxes, cache_full_boxes;
+    const void *cache_layers = nullptr;
+    std::vector<int> chunk_launch_begin, chunk_op_begin;  // per planned chunk (+ the end), into launches / ops
+    int plan_cache_hits = 0;
 
     cudaEvent_t ev[16] = {nullptr};
     cudaEvent_t ev_chunk[16][2] = {{nullptr}};
@@ -1362,6 +1371,7 @@ static int load_program(svgr_ctx *ctx, const svgr_program *p, cudaStream_t s, bo
     }
     // ---- accepted: from here on the context describes the new program
     ctx->have_program = false;
+    ctx->plan_cached = false;
     ctx->n_seg = p->n_seg, ctx->n_path = p->n_path, ctx->n_stroke = p->n_stroke, ctx->n_stroke_sub = p->n_stroke_sub;
     ctx->n_stroke_seg = p->n_stroke_seg, ctx->n_paint = p->n_paint, ctx->n_stop = p->n_stop, ctx->n_focal = p->n_focal;
     ctx->n_node = p->n_node, ctx->canvas_bytes = p->canvas_bytes;
@@ -1588,6 +1598,7 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
         stats->n_edges = ctx->n_edges;
         stats->n_outline_segs = st.outline_count;
         stats->retries = retries;
+        stats->plan_cached = 0;
         stats->ms_stroke = ms_stroke, stats->ms_flatten = ms_flatten;
     }
     if (stop_after == SVGR_STOP_STROKE || stop_after == SVGR_STOP_FLATTEN)
@@ -1605,16 +1616,31 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
     // ---- plan, part 1: masks -> binning + coverage are launched before the node plan is made
     mark(3);
     Planner pl(ctx);
+    // the plan cache holds when this is the program the cached plan was made for, the device found the same boxes
+    // and nothing the tables point into has moved
+    const bool cached = ctx->plan_cached && stop_after == SVGR_STOP_NONE && ctx->h_ext.empty() &&
+                        ctx->cache_layers == ctx->d_layers.p && ctx->cache_boxes.size() == ctx->h_boxes.size() &&
+                        (ctx->h_boxes.empty() || memcmp(ctx->cache_boxes.data(), ctx->h_boxes.data(),
+                                                        ctx->h_boxes.size() * sizeof(PathBox)) == 0) &&
+                        ctx->cache_full_boxes.size() == ctx->h_full_boxes.size() &&
+                        (ctx->h_full_boxes.empty() || memcmp(ctx->cache_full_boxes.data(), ctx->h_full_boxes.data(),
+                                                             ctx->h_full_boxes.size() * sizeof(PathBox)) == 0) &&
+                        !getenv("SVGR_NO_PLAN_CACHE");
+    ctx->plan_cached = false;  // until this render has gone through
     const size_t b_masks = (size_t)ctx->n_path * sizeof(MaskRec);
-    CK(ctx->pin_masks.ensure(b_masks + 64));  // the GPU waits for this table: it is written where it is copied from
-    ctx->h_masks = (MaskRec *)ctx->pin_masks.p;
     auto t_h0 = std::chrono::steady_clock::now();
-    if (!pl.plan_masks())
-        FAIL(SVGR_E_INVALID, pl.err);
+    if (!cached) {
+        CK(ctx->pin_masks.ensure(b_masks + 64));  // the GPU waits for this table: it is written where it is copied from
+        ctx->h_masks = (MaskRec *)ctx->pin_masks.p;
+        if (!pl.plan_masks())
+            FAIL(SVGR_E_INVALID, pl.err);
+    }
     auto t_h1 = std::chrono::steady_clock::now();
-    CK(ctx->d_masks.ensure(std::max<size_t>(b_masks, 16)));
-    if (b_masks)
-        CK(cudaMemcpyAsync(ctx->d_masks.p, ctx->pin_masks.p, b_masks, cudaMemcpyHostToDevice, s));
+    if (!cached) {
+        CK(ctx->d_masks.ensure(std::max<size_t>(b_masks, 16)));
+        if (b_masks)
+            CK(cudaMemcpyAsync(ctx->d_masks.p, ctx->pin_masks.p, b_masks, cudaMemcpyHostToDevice, s));
+    }
     CK(ctx->d_cov.ensure((size_t)std::max<long long>(ctx->cov_floats, 4) * 4));
     mark(4);
 
@@ -1660,7 +1686,7 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
     int n_launches = 0, timed_chunks = 0;
     bool early_copy_ok = true;
     long long copied_bytes = 0, copied_hi = 0;
-    if (!pl.begin_nodes())
+    if (!cached && !pl.begin_nodes())
         FAIL(SVGR_E_INVALID, pl.err);
     {
         // capacities that hold for every chunk: device tables must not move while launches are in flight
@@ -1671,7 +1697,7 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
         CK(ctx->d_focal_jobs.ensure(focal_cap * sizeof(FocalJob)));
         CK(ctx->pin_plan.ensure(ops_cap * sizeof(OpRec) + srcs_cap * sizeof(SrcRec) + focal_cap * sizeof(FocalJob) + 64));
         CK(ctx->d_focal_flags.ensure((size_t)std::max(ctx->n_focal, 1) * 4));
-        if (ctx->n_focal > 0)
+        if (ctx->n_focal > 0 && !cached)
             CK(cudaMemsetAsync(ctx->d_focal_flags.p, 0, (size_t)ctx->n_focal * 4, s));
         // tensor maps: two passes per filter node, a source and a destination map per pass
         const size_t tmap_cap = (size_t)ctx->n_filter_nodes * 4 + 4;
@@ -1700,12 +1726,28 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
         // the zeroed flags), so that they overlap the compose launches of the chunk before
         CK(cudaEventRecord(ctx->ev_up_begin, s));
         CK(cudaStreamWaitEvent(ctx->up_stream, ctx->ev_up_begin, 0));
-        for (int k = 0; k < pl.n_chunks(); k++) {
+        if (!cached) {
+            ctx->chunk_launch_begin.clear(), ctx->chunk_op_begin.clear();
+        }
+        const int n_chunks = cached ? (int)ctx->chunk_launch_begin.size() - 1 : pl.n_chunks();
+        long long heads_top = 0, lists_top = 0;  // tile heads / source lists of the chunks so far
+        RenderTables T;
+        for (int k = 0; k < n_chunks; k++) {
             int op_begin = 0, launch_begin = 0;
+            size_t launch_end = 0, op_end = 0;
+            if (cached) {
+                op_begin = ctx->chunk_op_begin[k], launch_begin = ctx->chunk_launch_begin[k];
+                op_end = (size_t)ctx->chunk_op_begin[k + 1], launch_end = (size_t)ctx->chunk_launch_begin[k + 1];
+                T.srcs = ctx->d_srcs.as<SrcRec>(), T.paints = ctx->d_paints.as<PaintRec>(), T.stops = ctx->d_stops.as<StopRec>();
+                T.focal_flags = ctx->d_focal_flags.as<int>(), T.cov = ctx->d_cov.as<float>(), T.layers = ctx->d_layers.as<float>();
+                T.matrices = ctx->d_matrices.as<float>(), T.weights = ctx->d_weights.as<float>();
+            } else {
             auto t_c0 = std::chrono::steady_clock::now();
             if (!pl.plan_chunk(k, &op_begin, &launch_begin))
                 FAIL(pl.err_code, pl.err);
             host_nodes_ms += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_c0).count();
+            ctx->chunk_launch_begin.push_back(launch_begin), ctx->chunk_op_begin.push_back(op_begin);
+            launch_end = ctx->launches.size(), op_end = ctx->ops.size();
             if (stop_after == SVGR_STOP_COVERAGE)
                 continue;
             if (ctx->ops.size() > ops_cap || ctx->srcs.size() > srcs_cap || ctx->focal_jobs.size() > focal_cap)
@@ -1718,13 +1760,14 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
             // tile -> op map of the stencil launches; tile heads and source lists of the compose launches.  The
             // lists of a whole chunk are written on the side stream while the chunk before it composes, so they
             // live in two buffers used by alternate chunks.
-            const int par = k & 1;
-            long long max_tiles = 1, n_heads = 0, n_slots = 0;
+            // Every chunk gets its own stretch of the two buffers (they are kept for the plan cache, and a chunk's
+            // lists are written on the side stream while the chunk before it composes).
+            long long max_tiles = 1;
             for (size_t q = launch_begin; q < ctx->launches.size(); q++) {
                 Launch &L = ctx->launches[q];
                 if (L.cls == 0 || L.cls == 3) {
-                    L.head_off = n_heads, L.list_off = n_slots;
-                    n_heads += L.n_tiles, n_slots += L.list_slots;
+                    L.head_off = heads_top, L.list_off = lists_top;
+                    heads_top += L.n_tiles, lists_top += L.list_slots;
                 } else {
                     max_tiles = std::max<long long>(max_tiles, L.n_tiles);
                 }
@@ -1733,12 +1776,14 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
                 CK(cudaStreamSynchronize(s));
                 CK(ctx->d_tile_map.ensure((size_t)max_tiles * 4 * 2));
             }
-            if ((size_t)n_heads * sizeof(TileHead) > ctx->d_heads[par].cap ||
-                (size_t)n_slots * sizeof(TileEntry) > ctx->d_lists[par].cap) {
+            if ((size_t)heads_top * sizeof(TileHead) > ctx->d_heads.cap || (size_t)lists_top * sizeof(TileEntry) > ctx->d_lists.cap) {
+                // grow with the earlier chunks' lists preserved; nothing may be in flight while the buffers move
                 CK(cudaStreamSynchronize(s));
                 CK(cudaStreamSynchronize(ctx->up_stream));
-                CK(ctx->d_heads[par].ensure((size_t)std::max<long long>(n_heads, 1) * sizeof(TileHead) * 3 / 2));
-                CK(ctx->d_lists[par].ensure((size_t)std::max<long long>(n_slots, 1) * sizeof(TileEntry) * 3 / 2));
+                // room for the chunks still to come: they are about as large as the ones so far
+                const double grow = (double)n_chunks / (double)(k + 1);
+                CK(ctx->d_heads.ensure((size_t)((double)std::max<long long>(heads_top, 1) * sizeof(TileHead) * grow), true));
+                CK(ctx->d_lists.ensure((size_t)((double)std::max<long long>(lists_top, 1) * sizeof(TileEntry) * grow), true));
             }
             // stage + upload the new records
             const size_t n_ops = ctx->ops.size() - up_ops, n_srcs = ctx->srcs.size() - up_srcs;
@@ -1794,7 +1839,6 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
                     CK(cudaMemcpyAsync(dev + first * 128, pin + first * 128, (tmap_top - first) * 128, cudaMemcpyHostToDevice,
                                        us));
             }
-            RenderTables T;
             T.srcs = ctx->d_srcs.as<SrcRec>(), T.paints = ctx->d_paints.as<PaintRec>(), T.stops = ctx->d_stops.as<StopRec>();
             T.focal_flags = ctx->d_focal_flags.as<int>(), T.cov = ctx->d_cov.as<float>(), T.layers = ctx->d_layers.as<float>();
             T.matrices = ctx->d_matrices.as<float>(), T.weights = ctx->d_weights.as<float>();
@@ -1806,19 +1850,18 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
                 focal_blocks_done = ctx->n_focal_blocks;
             }
             // per-tile source lists of this chunk's compose launches: they depend on the tables only
-            if (us != s && k >= 2)
-                CK(cudaStreamWaitEvent(us, ctx->ev_done[k - 2], 0));  // the chunk that used these buffers last
             for (size_t q = launch_begin; q < ctx->launches.size(); q++) {
                 const Launch &L = ctx->launches[q];
                 if (L.cls == 0 || L.cls == 3)
                     svgr_launch_cull(T, ctx->d_ops.as<OpRec>() + L.op_begin, L.op_count, L.n_tiles,
-                                     ctx->d_heads[par].as<TileHead>() + L.head_off,
-                                     ctx->d_lists[par].as<TileEntry>() + L.list_off, us);
+                                     ctx->d_heads.as<TileHead>() + L.head_off, ctx->d_lists.as<TileEntry>() + L.list_off, us);
             }
             if (us != s) {
                 CK(cudaEventRecord(ctx->ev_up[k], us));
                 CK(cudaStreamWaitEvent(s, ctx->ev_up[k], 0));
             }
+            up_ops = ctx->ops.size(), up_srcs = ctx->srcs.size(), up_focal = ctx->focal_jobs.size();
+            }  // !cached
             if (!externals_up) {
                 externals_up = true;  // programs with external layers are planned as a single chunk
                 for (int i = 0; i < ctx->n_node; i++) {
@@ -1837,12 +1880,12 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
             }
             if (timing && k < 16)
                 cudaEventRecord(ctx->ev_chunk[k][0], s);
-            for (size_t q = launch_begin; q < ctx->launches.size(); q++) {
+            for (size_t q = launch_begin; q < launch_end; q++) {
                 const Launch &L = ctx->launches[q];
                 const OpRec *ops = ctx->d_ops.as<OpRec>() + L.op_begin;
                 const int *tile_op = ctx->d_tile_map.as<int>();
-                const TileHead *heads = ctx->d_heads[par].as<TileHead>() + L.head_off;
-                const TileEntry *list = ctx->d_lists[par].as<TileEntry>() + L.list_off;
+                const TileHead *heads = ctx->d_heads.as<TileHead>() + L.head_off;
+                const TileEntry *list = ctx->d_lists.as<TileEntry>() + L.list_off;
                 if (L.cls == 1 || L.cls == 2 || L.cls == 4 || L.cls == 5)
                     svgr_launch_expand_ops(ops, L.op_count, L.n_tiles, ctx->d_tile_map.as<int>(), s);
                 if (L.cls == 4 || L.cls == 5) {
@@ -1872,7 +1915,7 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
             // is planned and composed (chunks own increasing, disjoint byte ranges of the output)
             if (canvas && out && !out_on_device && early_copy_ok && k < 16) {
                 long long lo = -1, hi = -1;
-                for (size_t q = (size_t)op_begin; q < ctx->ops.size(); q++) {
+                for (size_t q = (size_t)op_begin; q < op_end; q++) {
                     const PlannedOp &po = ctx->ops[q];
                     if (po.cls != 3)
                         continue;
@@ -1893,8 +1936,9 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
                     }
                 }
             }
-            up_ops = ctx->ops.size(), up_srcs = ctx->srcs.size(), up_focal = ctx->focal_jobs.size();
         }
+        if (!cached)
+            ctx->chunk_launch_begin.push_back((int)ctx->launches.size()), ctx->chunk_op_begin.push_back((int)ctx->ops.size());
         ctx->planned = true;
         if (stop_after != SVGR_STOP_COVERAGE) {
             mark(7);
@@ -1935,6 +1979,13 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
             stats->retries += 1;
         return rc;
     }
+    if (stop_after == SVGR_STOP_NONE) {
+        // everything this render left on the device describes (program, boxes): the next render may reuse it
+        ctx->plan_cached = true;
+        ctx->cache_boxes = ctx->h_boxes, ctx->cache_full_boxes = ctx->h_full_boxes;
+        ctx->cache_layers = ctx->d_layers.p;
+        ctx->plan_cache_hits += cached ? 1 : 0;
+    }
     if (timing) {
         ms_plan = ev_ms(ctx->ev[3], ctx->ev[4]);
         ms_bin = ev_ms(ctx->ev[4], ctx->ev[5]);
@@ -1957,6 +2008,7 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
         stats->n_kernels = n_kernels;
         stats->host_plan_masks_ms = std::chrono::duration<float, std::milli>(t_h1 - t_h0).count();
         stats->host_plan_nodes_ms = host_nodes_ms;
+        stats->plan_cached = cached ? 1 : 0;
         stats->ms_compose_busy = 0.f;
         if (timing && stop_after != SVGR_STOP_COVERAGE)
             for (int k = 0; k < timed_chunks; k++)
@@ -2042,8 +2094,7 @@ void svgr_destroy(svgr_ctx *ctx)
                       &ctx->d_osub, &ctx->d_ocount, &ctx->d_edges, &ctx->d_edge_path, &ctx->d_minmax, &ctx->d_boxes,
                       &ctx->d_minmax_f64, &ctx->d_status, &ctx->d_masks, &ctx->d_band_cnt, &ctx->d_band_off,
                       &ctx->d_band_cur, &ctx->d_bin_edges, &ctx->d_cov, &ctx->d_layers, &ctx->d_ops, &ctx->d_srcs,
-                      &ctx->d_focal_jobs, &ctx->d_focal_flags, &ctx->d_canvas, &ctx->d_q, &ctx->d_tile_map, &ctx->d_tile_rec, &ctx->d_bin_data, &ctx->d_heads[0], &ctx->d_heads[1], &ctx->d_lists[0],
-                      &ctx->d_lists[1], &ctx->d_ovf_cubic[0], &ctx->d_ovf_cubic[1], &ctx->d_ovf_path[0], &ctx->d_ovf_path[1],
+                      &ctx->d_focal_jobs, &ctx->d_focal_flags, &ctx->d_canvas, &ctx->d_q, &ctx->d_tile_map, &ctx->d_tile_rec, &ctx->d_bin_data, &ctx->d_heads, &ctx->d_lists, &ctx->d_ovf_cubic[0], &ctx->d_ovf_cubic[1], &ctx->d_ovf_path[0], &ctx->d_ovf_path[1],
                       &ctx->d_ovf_depth[0], &ctx->d_ovf_depth[1], &ctx->d_ovf_counts, &ctx->d_eager[0], &ctx->d_eager[1],
                       &ctx->d_eager[2], &ctx->d_tmaps, &ctx->d_full_boxes, &ctx->d_png_segs, &ctx->d_png_canvases, &ctx->d_png_scratch,
                       &ctx->d_png_seg_bytes, &ctx->d_png_seg_adler, &ctx->d_png_file_bytes, &ctx->d_png_file_off,

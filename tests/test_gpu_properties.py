@@ -91,3 +91,39 @@ def test_filter_identities_8192(eng):
     sw = layer.color_matrix(m)
     assert np.array_equal(sw.image[..., 0], img[..., 2]) and np.array_equal(sw.image[..., 2], img[..., 0])
     assert np.array_equal(sw.image[..., 3], img[..., 3])
+
+
+def test_plan_cache_reuses_tables_only_for_the_same_program_and_boxes(eng):
+    """A resident re-render that finds the same path boxes repeats the launches on the tables of the render before
+    (no host planning, uploads or culls); a new program, or SVGR_NO_PLAN_CACHE, plans again.  Same pixels either way."""
+    import os
+
+    import torch
+
+    from svgrasterize_b200 import encode, synth
+
+    prog = encode.Program.concat([encode.encode_scene(synth.icon_scene(50 + i), synth.icon_size()) for i in range(40)])
+    other = encode.encode_scene(synth.filter_stack_scene(200), (200, 200))
+    out = torch.empty(prog.canvas_bytes, dtype=torch.uint8, device="cuda")
+    first = eng.render(prog, out=out)
+    assert first["plan_cached"] == 0
+    a = out.cpu().numpy().copy()
+    st = eng.render_resident(out)
+    assert st["plan_cached"] == 1 and st["host_plan_nodes_ms"] == 0.0 and st["n_launches"] == first["n_launches"]
+    b = out.cpu().numpy().copy()
+    assert int(np.abs(a.astype(np.int16) - b.astype(np.int16)).max()) <= 1
+    os.environ["SVGR_NO_PLAN_CACHE"] = "1"
+    try:
+        st = eng.render_resident(out)
+        assert st["plan_cached"] == 0 and st["host_plan_nodes_ms"] > 0.0
+    finally:
+        del os.environ["SVGR_NO_PLAN_CACHE"]
+    c = out.cpu().numpy()
+    assert int(np.abs(a.astype(np.int16) - c.astype(np.int16)).max()) <= 1
+    # filters (tensor maps) through the cache too
+    small = torch.empty(other.canvas_bytes, dtype=torch.uint8, device="cuda")
+    assert eng.render(other, out=small)["plan_cached"] == 0  # a new program invalidates
+    x = small.cpu().numpy().copy()
+    assert eng.render_resident(small)["plan_cached"] == 1
+    assert int(np.abs(x.astype(np.int16) - small.cpu().numpy().astype(np.int16)).max()) <= 1
+    assert eng.render(prog, out=out)["plan_cached"] == 0
