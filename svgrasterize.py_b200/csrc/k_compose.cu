@@ -163,6 +163,21 @@ compose_kernel(RenderTables T, const OpRec *__restrict__ ops, const TileHead *__
                 if (!live && skip_outside && !first)
                     continue;
                 const int base = s_toff[j] + ty * s.stride + tx, step = 8 * s.stride;  // a layer has < 2^31 px
+                // a stencil modifier (clip / mask fused into this source) is one more dependent load per pixel: its
+                // scalar kinds are requested here, together with the source's own data, instead of after the paint
+                const bool has_mod = j + 1 < n && s_src[j + 1].kind >= SRC_MOD_COV;
+                const int mod_kind = has_mod ? s_src[j + 1].kind : 0;
+                float mval[CMP_PX];
+                if (has_mod && mod_kind != SRC_MOD_LUMA) {
+                    const SrcRec &md = s_src[j + 1];
+                    const float *mp = (mod_kind == SRC_MOD_COV ? T.cov : T.layers) + md.off;
+                    const int esz = mod_kind == SRC_MOD_L4A ? 4 : 1, eoff = mod_kind == SRC_MOD_L4A ? 3 : 0;
+#pragma unroll
+                    for (int k = 0; k < CMP_PX; k++) {
+                        const long long idx = (long long)(r0 + 8 * k - md.br0) * md.stride + (c - md.bc0);
+                        mval[k] = (live >> (8 * k) & 1) ? __ldg(mp + esz * idx + eoff) : 0.f;
+                    }
+                }
                 float4 v[CMP_PX];
                 if (s.kind == SRC_L4) {
                     const float4 *p = reinterpret_cast<const float4 *>(T.layers + s.off);
@@ -230,15 +245,22 @@ compose_kernel(RenderTables T, const OpRec *__restrict__ ops, const TileHead *__
                         if (live >> (8 * k) & 1)
                             v[k] = convert_px(v[k], s.conv);
                 }
-                if (j + 1 < n && s_src[j + 1].kind >= SRC_MOD_COV) {
+                if (has_mod) {
                     // stencil of a clip / luminance mask that was never written out as a layer
                     const SrcRec &md = s_src[j + 1];
+                    if (mod_kind != SRC_MOD_LUMA) {
+                        const float mm = md.mul;
 #pragma unroll
-                    for (int k = 0; k < CMP_PX; k++)
-                        if (live >> (8 * k) & 1) {
-                            const float m = mod_value(T, md, r0 + 8 * k, c);
-                            v[k] = scale4(v[k], m);
-                        }
+                        for (int k = 0; k < CMP_PX; k++)
+                            v[k] = scale4(v[k], mval[k] * mm);  // dead pixels have v = 0
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < CMP_PX; k++)
+                            if (live >> (8 * k) & 1) {
+                                const float m = mod_value(T, md, r0 + 8 * k, c);
+                                v[k] = scale4(v[k], m);
+                            }
+                    }
                 }
                 if (first) {
 #pragma unroll

@@ -118,15 +118,23 @@ __device__ __forceinline__ double floored_mod(double a, double b)
     return r;
 }
 
+// np.remainder(u, 2.0) without the fmod call: u / 2 and 2 floor(u / 2) are exact, so u - 2 floor(u / 2) is the
+// exact floored remainder rounded once -- the same single rounding np.remainder makes (fmod is exact, its
+// "+ 2.0" for negative u is the one inexact step there).  NaN and infinities give NaN like fmod.
+__device__ __forceinline__ double floored_mod2(double u)
+{
+    const double r = u - 2.0 * floor(u * 0.5);
+    return (u - u == 0.0) ? r : __longlong_as_double(0x7ff8000000000000ll);
+}
+
 // grad_spread (svgrasterize.py:1661-1668)
 __device__ __forceinline__ double grad_spread(double t, int spread)
 {
-    if (spread == 1) {
-        double ip;
-        return modf(t, &ip);  // keeps the sign: repeat degenerates to pad for t < 0
-    }
+    if (spread == 1)
+        // np.modf's fractional part: exact, keeps the sign (repeat degenerates to pad for t < 0), 0 for +-inf
+        return fabs(t) == __longlong_as_double(0x7ff0000000000000ll) ? 0.0 : t - trunc(t);
     if (spread == 2)
-        return fabs(floored_mod(t + 1.0, 2.0) - 1.0);
+        return fabs(floored_mod2(t + 1.0) - 1.0);
     return t;
 }
 
