@@ -329,6 +329,14 @@ const char *svgr_encoded_error(const svgr_encoded *e);
 int64_t svgr_encoded_canvases(const svgr_encoded *e, const int64_t **canvases, const int32_t **roots);
 void svgr_encoded_free(svgr_encoded *e);
 
+/* ---- path-data reader (csrc/pathdata.cpp).  Path.from_svg (svgrasterize.py:1252-1430): tokenises a `d` attribute
+ * or glyph outline and builds the sub-paths, straight into flat segment arrays (PATH_* tag + 8 doubles per segment:
+ * the points of a line / quad / cubic, or cx cy rx ry phi eta eta_delta of an arc -- arc_svg_to_parametric, :2397).
+ * n_seg / n_sub receive the counts; SVGR_E_NOMEM when they exceed cap_seg / cap_sub (call again), SVGR_E_INVALID
+ * where the reference raises ValueError (message in err). */
+int svgr_path_from_svg(const char *d, int64_t len, uint8_t *tags, double *data, int64_t cap_seg, int32_t *sub_off,
+                       int64_t cap_sub, int64_t *n_seg, int64_t *n_sub, char *err, int32_t err_cap);
+
 /* ---- eager element-wise entry points of the reference's call surface.  Host pointers in and
  * out; every call copies up, launches one kernel on the context's stream and copies down (one synchronisation). */
 

@@ -105,6 +105,8 @@ SYMBOLS = {
     "svgr_cloud_bounds": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "svgr_arc_to_cubics": (C.c_int64, [C.c_double] * 7 + [C.c_void_p, C.c_int64]),
     "svgr_expand_arcs": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "svgr_path_from_svg": (C.c_int, [C.c_char_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                     C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_char_p, C.c_int32]),
     "svgr_encode_flat": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "svgr_encoded_program": (C.c_void_p, [C.c_void_p]),
     "svgr_encoded_error": (C.c_char_p, [C.c_void_p]),

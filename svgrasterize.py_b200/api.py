@@ -289,9 +289,29 @@ def grad_interpolate(offset, stops, linear_rgb):
     return default_engine().grad_interpolate(np.asarray(offset, dtype=np.float64), rec)
 
 
+def path_from_svg(input: str):
+    """Path.from_svg (svgrasterize.py:1252-1430) by the native path-data reader (csrc/pathdata.cpp): the path holds
+    flat segment arrays (what the encoder consumes) and unpacks them into ``subpaths`` only on demand."""
+    import ctypes as C
+
+    raw = input.encode("utf-8") if isinstance(input, str) else bytes(input)
+    cap = len(raw) // 2 + 8  # every segment and every sub-path costs at least two characters
+    tags = np.empty(cap, np.uint8)
+    data = np.empty((cap, 8), np.float64)
+    sub_off = np.empty(cap + 1, np.int32)
+    n_seg, n_sub = C.c_int64(), C.c_int64()
+    err = C.create_string_buffer(256)
+    rc = _lib.lib().svgr_path_from_svg(raw, len(raw), tags.ctypes.data, data.ctypes.data, cap, sub_off.ctypes.data, cap,
+                                      C.byref(n_seg), C.byref(n_sub), err, 256)
+    if rc != 0:
+        raise ValueError(err.value.decode() or "malformed path data")
+    return path_from_arrays(tags[: n_seg.value].copy(), data[: n_seg.value].copy(), sub_off[: n_sub.value + 1].copy())
+
+
 S.Path.mask = path_mask
 S.Path.fill = path_fill
 S.Path.stroke = path_stroke
+S.Path.from_svg = staticmethod(path_from_svg)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -578,6 +598,8 @@ def install(module):
     bind(module.Path, "mask", path_mask)
     bind(module.Path, "fill", path_fill)
     bind(module.Path, "stroke", path_stroke)
+    if isinstance(module.Path, type) and issubclass(module.Path, S.Path):
+        bind(module.Path, "from_svg", staticmethod(path_from_svg))  # array-backed paths need this package's Path
     bind(module.Scene, "render", scene_render)
     bind(module.Filter, "__call__", filter_call)
     bind(module, "Layer", Layer)

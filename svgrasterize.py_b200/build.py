@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsvgr_b200.so")
 SOURCES = ["engine.cu", "k_flatten.cu", "k_stroke.cu", "k_coverage.cu", "k_compose.cu", "k_filters.cu",
-           "k_stencil_tma.cu", "k_png.cu", "encode_flat.cpp"]
+           "k_stencil_tma.cu", "k_png.cu", "encode_flat.cpp", "pathdata.cpp"]
 HEADERS = ["svgr_types.h", "svgr_kernels.h", "svgr_device.cuh", os.path.join("..", "..", "include", "svgr_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

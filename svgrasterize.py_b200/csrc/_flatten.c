@@ -209,6 +209,42 @@ static long flatten_path(Ctx *c, PyObject *path)
     long idx = cached_index(c->path_ids, path);
     if (idx != -1)
         return idx; /* found, or -2 on error */
+    /* a path that already holds flat arrays (the native path-data reader, sceneio): copy them as they are */
+    {
+        PyObject *enc = PyObject_GetAttrString(path, "_enc");
+        if (!enc) {
+            PyErr_Clear();
+        } else if (PyTuple_Check(enc) && PyTuple_GET_SIZE(enc) == 3 && PyArray_Check(PyTuple_GET_ITEM(enc, 0)) &&
+                   PyArray_Check(PyTuple_GET_ITEM(enc, 1)) && PyArray_Check(PyTuple_GET_ITEM(enc, 2))) {
+            PyArrayObject *t = (PyArrayObject *)PyTuple_GET_ITEM(enc, 0), *d = (PyArrayObject *)PyTuple_GET_ITEM(enc, 1),
+                          *o = (PyArrayObject *)PyTuple_GET_ITEM(enc, 2);
+            const npy_intp n = PyArray_SIZE(t), ns = PyArray_SIZE(o) - 1;
+            if (PyArray_TYPE(t) == NPY_UINT8 && PyArray_TYPE(d) == NPY_DOUBLE && PyArray_TYPE(o) == NPY_INT32 &&
+                PyArray_IS_C_CONTIGUOUS(t) && PyArray_IS_C_CONTIGUOUS(d) && PyArray_IS_C_CONTIGUOUS(o) &&
+                PyArray_SIZE(d) == 8 * n && ns >= 0) {
+                const int32_t *off = (const int32_t *)PyArray_DATA(o);
+                int ok = buf_put(&c->seg_tag, PyArray_DATA(t), (size_t)n) == 0 &&
+                         buf_put(&c->seg_data, PyArray_DATA(d), (size_t)n * 64) == 0;
+                for (npy_intp k = 1; ok && k <= ns; k++) {
+                    const int32_t end = (int32_t)c->n_seg + off[k];
+                    ok = buf_put(&c->sub_off, &end, 4) == 0;
+                }
+                Py_DECREF(enc);
+                if (!ok)
+                    return -2;
+                c->n_seg += n;
+                c->n_sub += (int32_t)ns;
+                const int32_t end = c->n_sub;
+                if (buf_put(&c->path_off, &end, 4))
+                    return -2;
+                idx = c->n_path++;
+                return cache_index(c->path_ids, path, idx) ? -2 : idx;
+            }
+            Py_DECREF(enc);
+        } else {
+            Py_DECREF(enc);
+        }
+    }
     PyObject *subs = PyObject_GetAttrString(path, "subpaths");
     if (!subs)
         return -2;

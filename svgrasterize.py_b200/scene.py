@@ -135,23 +135,48 @@ class Transform:
 class Path:
     """List of sub-paths, each a list of ``(tag, points)`` segments
     (svgrasterize.py:896-913).  ``mask`` / ``fill`` / ``stroke`` are attached
-    by ``api.py`` and run on the device."""
+    by ``api.py`` and run on the device.
 
-    __slots__ = ("subpaths", "_enc", "_flat")
+    A path read by the native path-data reader (``Path.from_svg``) holds flat
+    arrays (``_enc``: tags, 8 doubles per segment, sub-path offsets) and only
+    builds the nested Python lists when somebody asks for ``subpaths``."""
+
+    __slots__ = ("_subpaths", "_enc", "_flat")
 
     def __init__(self, subpaths):
-        self.subpaths = subpaths
+        self._subpaths = subpaths
         self._enc = None
         self._flat = None
+
+    @classmethod
+    def from_arrays(cls, seg_tag, seg_data, sub_off) -> "Path":
+        """A path over flat segment arrays (the layout of sceneio.path_arrays); nothing is copied or unpacked."""
+        path = cls.__new__(cls)
+        path._subpaths = None
+        path._enc = (seg_tag, seg_data, sub_off)
+        path._flat = None
+        return path
+
+    @property
+    def subpaths(self):
+        if self._subpaths is None:
+            from .sceneio import subpaths_from_arrays
+
+            self._subpaths = subpaths_from_arrays(*self._enc)
+        return self._subpaths
+
+    @subpaths.setter
+    def subpaths(self, value):
+        self._subpaths, self._enc, self._flat = value, None, None
 
     def __iter__(self):
         return iter(self.subpaths)
 
     def __bool__(self) -> bool:
-        return bool(self.subpaths)
+        return bool(len(self._enc[2]) - 1) if self._subpaths is None else bool(self._subpaths)
 
     def is_empty(self) -> bool:
-        return not self.subpaths
+        return not bool(self)
 
 
 class GradLinear(NamedTuple):

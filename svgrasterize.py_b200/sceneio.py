@@ -61,7 +61,8 @@ def path_arrays(path):
     return enc
 
 
-def path_from_arrays(seg_tag, seg_data, sub_off) -> S.Path:
+def subpaths_from_arrays(seg_tag, seg_data, sub_off):
+    """The nested ``[[(tag, points), ...], ...]`` form of flat segment arrays."""
     npts = {S.PATH_LINE: 2, S.PATH_CLOSED: 2, S.PATH_UNCLOSED: 2, S.PATH_QUAD: 3, S.PATH_CUBIC: 4}
     subpaths = []
     for a, b in zip(sub_off[:-1], sub_off[1:]):
@@ -74,13 +75,15 @@ def path_from_arrays(seg_tag, seg_data, sub_off) -> S.Path:
             else:
                 sub.append((tag, row[: 2 * npts[tag]].reshape(-1, 2).copy()))
         subpaths.append(sub)
-    path = S.Path(subpaths)
-    path._enc = (
+    return subpaths
+
+
+def path_from_arrays(seg_tag, seg_data, sub_off) -> S.Path:
+    return S.Path.from_arrays(
         np.ascontiguousarray(seg_tag, dtype=np.uint8),
-        np.ascontiguousarray(seg_data, dtype=np.float64),
+        np.ascontiguousarray(seg_data, dtype=np.float64).reshape(-1, SEG_WIDTH),
         np.ascontiguousarray(sub_off, dtype=np.int32),
     )
-    return path
 
 
 def _f(v):

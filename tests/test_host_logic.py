@@ -405,3 +405,54 @@ def test_native_encoder_reads_the_reference_modules_objects():
     want = encode.Program.concat([encode.encode_scene(s, size, lin) for s, size, lin in jobs])
     _programs_equal(prog, want, paint_tol=1e-13)
     prog.close()
+
+
+def test_native_path_data_reader_is_bit_exact():
+    """Path.from_svg (svgrasterize.py:1252-1430) in native code (csrc/pathdata.cpp) against the
+    reference's own segments for every `d` attribute of the demo files, a sample of the Iosevka glyph outlines,
+    grammar corner cases and 300 random arc commands (tests/golden_eager/pathdata.npz, tools/make_golden_eager.py)."""
+    import svgrasterize_b200 as B
+    from svgrasterize_b200 import sceneio
+
+    z = np.load(os.path.join(ROOT, "tests", "golden_eager", "pathdata.npz"), allow_pickle=False)
+    strings = z["strings"].tobytes().decode().split("\n")
+    seg_end, sub_end = z["seg_end"], z["sub_end"]
+    assert len(strings) == len(seg_end) > 2000
+    s0 = b0 = 0
+    arcs = 0
+    for k, text in enumerate(strings):
+        path = B.Path.from_svg(text)
+        t, d, o = sceneio.path_arrays(path)
+        s1, b1 = int(seg_end[k]), int(sub_end[k])
+        assert np.array_equal(t, z["tags"][s0:s1]), text[:60]
+        assert d.tobytes() == z["data"][s0:s1].tobytes(), text[:60]
+        assert np.array_equal(o[1:], z["sub_off"][b0:b1]), text[:60]
+        assert bool(path) == (b1 > b0)
+        arcs += int((t == 3).sum())
+        s0, b0 = s1, b1
+    assert arcs > 500
+    for text in z["invalid"].tobytes().decode().split("\n"):
+        with pytest.raises(ValueError):
+            B.Path.from_svg(text)
+    # the nested form is built on demand and round-trips
+    path = B.Path.from_svg("M1 2L3 4Q5 6 7 8zm1 1a2 3 10 0 1 4 4")
+    assert [len(sub) for sub in path.subpaths] == [3, 2] and path.subpaths[0][0][0] == B.PATH_LINE
+    again = sceneio.path_arrays(B.Path(path.subpaths))
+    assert all(np.array_equal(x, y) for x, y in zip(again, sceneio.path_arrays(path)))
+
+
+def test_array_backed_paths_go_through_both_encoders():
+    """Paths read by the native reader hold flat arrays; the flattener copies them wholesale, the Python encoder
+    reads them through sceneio.path_arrays: same program."""
+    import svgrasterize_b200 as B
+    from svgrasterize_b200 import encode, native, synth
+
+    d1 = "M4 4h40a8 8 0 0 1 8 8v30q0 10-10 10H4z M20 20l10 0 0 10z"
+    d2 = "M10 50C20 10 40 10 50 50S80 90 90 50"
+    scene = B.Scene.group([B.Scene.fill(B.Path.from_svg(d1), synth.color(0.8, 0.2, 0.1), "evenodd"),
+                           B.Scene.stroke(B.Path.from_svg(d2), synth.color(0.1, 0.2, 0.9), 3.0, "round", "bevel")])
+    jobs = [(scene, (100, 100), False)]
+    nat = native.encode_batch(jobs)
+    ref = encode.encode_scene(scene, (100, 100), False)
+    _programs_equal(nat, ref)
+    nat.close()

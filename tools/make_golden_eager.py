@@ -118,6 +118,57 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     np.savez_compressed(os.path.join(OUT, "eager.npz"), **z)
     print("wrote", os.path.join(OUT, "eager.npz"), len(z), "arrays")
+    pathdata()
+
+
+def pathdata():
+    """Path.from_svg (:1252-1430) on real path data: every `d` attribute of the three demo files, every 16th glyph
+    outline of fonts.svgz, hand-written strings for the corners of the grammar, and random arc commands (the
+    conversion to the parametric form, :2397-2450).  Stored: the strings and the reference's segments, flattened."""
+    import gzip
+    import re
+
+    sys.path.insert(0, ROOT)
+    from svgrasterize_b200 import sceneio  # the flat segment layout (tags, 8 doubles, sub-path offsets)
+
+    strings = []
+    for f in ("icons.svg", "material-design.svg", "prompt.svg"):
+        strings += re.findall(r'\sd="([^"]+)"', open(f"/root/reference/demo/{f}").read())
+    strings += re.findall(r'\sd="([^"]+)"', gzip.open("/root/reference/fonts.svgz").read().decode())[::16]
+    strings = sorted(set(s.replace("&#10;", " ") for s in strings))
+    strings += [
+        "", "M1 2", "1 2 3 M4 5 6 7z", "m1,2 3,4-5-6", "M0 0h10v10H0V0z", "M.5.5l1.5e1-2E-1,3.,-4", "M0 0 1 1 2 0zm5 5 1 1z",
+        "M0 0C1 1 2 2 3 0S5 -1 6 0s1 1 2 0", "M0 0S1 1 2 0", "M0 0Q1 2 3 0T6 0t3 0", "M0 0T3 3", "M0 0L1 1zL2 2", "M0 0zz",
+        "M10 10A5 5 0 0 1 20 10a5,3 30 1,0 10,0", "M0 0A0 5 0 0 1 9 9", "M0 0A5 5 0 1 1 0 0", "M0 0A1 1 45 0 0 100 100",
+        "M 0,0 a 25,25 -30 0,1 50,-25 l 50,-25", "M0 0L+1-1L-.5+.5", "M0 0 L 1e2 1E+2 1.e-1 .1E1",
+    ]
+    rng = np.random.default_rng(77)
+    for _ in range(300):
+        rx, ry, rot = rng.uniform(0.1, 80), rng.uniform(0.1, 80), rng.uniform(-400, 400)
+        strings.append("M%r %r%s%r %r %r %d %d %r %r" % (float(rng.uniform(-50, 50)), float(rng.uniform(-50, 50)),
+                                                         "Aa"[int(rng.integers(0, 2))], float(rx), float(ry), float(rot),
+                                                         int(rng.integers(0, 2)), int(rng.integers(0, 2)),
+                                                         float(rng.uniform(-90, 90)), float(rng.uniform(-90, 90))))
+    tags, data, sub_off, seg_end, sub_end = [], [], [], [], []
+    n_seg = n_sub = 0
+    for s in strings:
+        t, d, o = sceneio.path_arrays(R.Path.from_svg(s))
+        tags.append(t), data.append(d), sub_off.append(o[1:] if len(o) > 1 else np.zeros(0, np.int32))
+        n_seg += len(t)
+        n_sub += len(o) - 1
+        seg_end.append(n_seg), sub_end.append(n_sub)
+    blob = "\n".join(strings).encode()
+    bad = []
+    for s in ("M0 0L1", "M0 0Z1", "M0 0X", "M0 0h", "M", "M0 0C1 2 3 4 5", "M0 0 L 1 . 2"):
+        try:
+            R.Path.from_svg(s)
+        except ValueError:
+            bad.append(s)
+    np.savez_compressed(os.path.join(OUT, "pathdata.npz"), strings=np.frombuffer(blob, np.uint8),
+                        tags=np.concatenate(tags), data=np.concatenate(data).reshape(-1, 8),
+                        sub_off=np.concatenate(sub_off).astype(np.int32), seg_end=np.asarray(seg_end, np.int64),
+                        sub_end=np.asarray(sub_end, np.int64), invalid=np.frombuffer("\n".join(bad).encode(), np.uint8))
+    print("wrote pathdata.npz:", len(strings), "strings,", n_seg, "segments,", len(bad), "invalid strings")
 
 
 if __name__ == "__main__":
