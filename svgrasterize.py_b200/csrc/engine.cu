@@ -193,6 +193,7 @@ struct svgr_ctx {
     std::vector<svgr_node> h_nodes;
     std::vector<int32_t> h_children;
     std::vector<svgr_kernel> h_kernels;
+    std::vector<float> h_matrices;
     std::vector<double> h_offset_tr;
     std::vector<svgr_external> h_ext;
     std::vector<std::vector<float>> h_ext_data;
@@ -384,6 +385,7 @@ struct Planner {
         std::vector<SrcRec> &ss = sl.v;
         int level = push_src(ss, v, want_pre, want_lin) + 1;
         Val out = alloc(out_kind, v.r0, v.c0, v.rows, v.cols, out_pre, out_lin, level);
+        out.op_index = (int)ops_p->size();
         emit(0, OP_COMPOSE, out, ss, MODE_OVER, post, mul, out.level, nullptr, aux);
         return out;
     }
@@ -905,14 +907,23 @@ struct Planner {
             }
             // When the root is an over-group that nobody else reads, its fold writes the canvas directly
             // (clip, straight-alpha sRGB, RGBA8) instead of a float layer that is read back once.
-            if (v.kind == SRC_L4 && !v.is_virtual() && v.op_index >= 0 && v.owner == ch[0] && (*uses_p)[ch[0]] == 1 &&
-                v.pre == 1 && v.lin == lin) {
+            // The same for a feColorMatrix at the root (a filter that ends in a colour matrix): its pass applies the
+            // matrix and then goes on to the canvas steps -- as long as the matrix has no bias column, because the
+            // canvas is larger than the layer and M . 0 + bias would paint the outside.
+            if (v.kind == SRC_L4 && !v.is_virtual() && v.op_index >= 0 && v.owner == ch[0] && (*uses_p)[ch[0]] == 1) {
                 PlannedOp &po = (*ops_p)[v.op_index];
-                if (po.cls == 0 && po.op.kind == OP_COMPOSE && po.op.mode == MODE_OVER && po.op.post == POST_NONE &&
+                const bool plain_over = v.pre == 1 && v.lin == lin && po.op.post == POST_NONE;
+                bool matrix_root = false;
+                if (po.op.post == POST_MATRIX && v.pre == 0 && v.lin == 1 && po.op.aux >= 0 &&
+                    (size_t)(po.op.aux + 1) * 20 <= ctx->h_matrices.size()) {
+                    const float *M = ctx->h_matrices.data() + 20 * (size_t)po.op.aux;
+                    matrix_root = M[4] == 0.f && M[9] == 0.f && M[14] == 0.f && M[19] == 0.f;
+                }
+                if (po.cls == 0 && po.op.kind == OP_COMPOSE && po.op.mode == MODE_OVER && (plain_over || matrix_root) &&
                     po.op.mul == 1.0f) {
                     po.cls = 3;
                     OpRec &o = po.op;
-                    o.kind = OP_CANVAS, o.aux = lin;
+                    o.kind = OP_CANVAS, o.k1 = lin;
                     o.r0 = n.c, o.c0 = n.d, o.rows = n.a, o.cols = n.b, o.stride = n.b, o.out_ch = 4;
                     o.out_off = out_off;
                     layer_pixels -= (long long)v.rows * v.cols;
@@ -924,7 +935,7 @@ struct Planner {
             memset(&p, 0, sizeof p);
             p.cls = 3;
             OpRec &o = p.op;
-            o.kind = OP_CANVAS, o.mode = MODE_OVER, o.aux = lin;
+            o.kind = OP_CANVAS, o.mode = MODE_OVER, o.k1 = lin;
             o.r0 = n.c, o.c0 = n.d, o.rows = n.a, o.cols = n.b, o.stride = n.b, o.out_ch = 4;
             o.out_off = out_off;
             o.mul = 1.0f;
@@ -1183,7 +1194,7 @@ struct Planner {
                 const bool fold = po.cls == 0 || po.cls == 3;
                 if (fold) {
                     if (o.mode != MODE_OVER || (o.post & (POST_ALPHA | POST_MATRIX | POST_LUMA)) ||
-                        (po.cls == 3 ? o.aux != 0 : o.out_ch != 4))
+                        (po.cls == 3 ? o.k1 != 0 : o.out_ch != 4))
                         L.simple = false;
                     for (int q = 0; q < o.src_cnt && L.simple; q++) {
                         const SrcRec &sr = c->srcs[o.src_off + q];
@@ -1293,6 +1304,7 @@ static int finish_load(svgr_ctx *ctx)
     ctx->h_nodes.assign(p->nodes, p->nodes + p->n_node);
     ctx->h_children.assign(p->children, p->children + p->n_child);
     ctx->h_kernels.assign(p->kernels, p->kernels + p->n_kernel);
+    ctx->h_matrices.assign(p->matrices, p->matrices + (size_t)p->n_matrix * 20);
     ctx->h_offset_tr.assign(p->offset_tr, p->offset_tr + (size_t)p->n_offset_tr * 12);
     ctx->h_ext.assign(p->externals, p->externals + p->n_external);
     ctx->h_ext_data.clear();

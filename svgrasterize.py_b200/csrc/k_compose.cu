@@ -319,9 +319,13 @@ compose_kernel(RenderTables T, const OpRec *__restrict__ ops, const TileHead *__
         if (op.kind == OP_CANVAS) {
             // main() :3870-3881: the premultiplied result over a zero canvas, clipped to [0, 1]
             // (canvas_merge_at :326), converted to straight-alpha sRGB (Layer.write_png :212) and quantised
-            // with round-half-even (np.round, :263).  op.aux carries the render's linear_rgb flag.
+            // with round-half-even (np.round, :263).  op.k1 carries the render's linear_rgb flag.
+            if (!SIMPLE && (op.post & POST_MATRIX))
+                // a colour matrix folded into the canvas pass: its result is straight-alpha linear; main() first
+                // converts the layer to premultiplied render space (:3871)
+                a = convert_px(a, SVGR_CONV(0, 1, 1, op.k1 != 0));
             a = f4(clip01(a.x), clip01(a.y), clip01(a.z), clip01(a.w));
-            if (!SIMPLE && op.aux != 0)
+            if (!SIMPLE && op.k1 != 0)
                 a = convert_px(a, SVGR_CONV(1, 1, 0, 0));
             else
                 a = unpremultiply(a);  // sRGB render mode: Layer.convert is the alpha division only

@@ -21,8 +21,9 @@
 
 __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 
-__device__ __forceinline__ float nanmax1(float a, float v) { return (v != v) ? a : ((a != a || v > a) ? v : a); }
-__device__ __forceinline__ float nanmin1(float a, float v) { return (v != v) ? a : ((a != a || v < a) ? v : a); }
+// np.nanmax / np.nanmin of two values: IEEE maxNum / minNum (one FMNMX): the operand that is not NaN wins
+__device__ __forceinline__ float nanmax1(float a, float v) { return fmaxf(a, v); }
+__device__ __forceinline__ float nanmin1(float a, float v) { return fminf(a, v); }
 
 template <int ST>
 __device__ __forceinline__ float4 stencil_init()

@@ -79,8 +79,9 @@ __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.b
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__device__ __forceinline__ float nanmax_t(float a, float v) { return (v != v) ? a : ((a != a || v > a) ? v : a); }
-__device__ __forceinline__ float nanmin_t(float a, float v) { return (v != v) ? a : ((a != a || v < a) ? v : a); }
+// np.nanmax / np.nanmin of two values: IEEE maxNum / minNum (one FMNMX): the operand that is not NaN wins
+__device__ __forceinline__ float nanmax_t(float a, float v) { return fmaxf(a, v); }
+__device__ __forceinline__ float nanmin_t(float a, float v) { return fminf(a, v); }
 
 template <int ST>
 __device__ __forceinline__ void tap(float4 &a, float w, const float4 &v)
