@@ -2412,6 +2412,29 @@ int svgr_debug_plan(const svgr_program *prog, const int32_t *boxes, int reps, fl
             info[2] = (int64_t)ctx->launches.size(), info[3] = ctx->n_levels, info[4] = ctx->layer_floats;
             info[5] = ctx->compose_bytes;
         }
+        if (getenv("SVGR_PLAN_DEBUG")) {
+            // tiles per compose op / sources per op, weighted by tiles
+            int64_t by_tiles[8] = {0}, by_srcs[8] = {0}, total = 0;
+            for (const PlannedOp &po : ctx->ops) {
+                const OpRec &o = po.op;
+                if (o.kind != OP_COMPOSE && o.kind != OP_CANVAS)
+                    continue;
+                const int64_t nt = (int64_t)((o.rows + SVGR_CMP_TR - 1) / SVGR_CMP_TR) * o.ntile_c;
+                int b = 0, c = 0;
+                while ((1 << b) < nt && b < 7)
+                    b++;
+                while ((1 << c) < o.src_cnt && c < 7)
+                    c++;
+                by_tiles[b] += nt, by_srcs[c] += nt, total += nt;
+            }
+            fprintf(stderr, "[plan] compose tiles %lld; share by tiles/op (<=1,2,4,..,128+):", (long long)total);
+            for (int i = 0; i < 8; i++)
+                fprintf(stderr, " %.3f", (double)by_tiles[i] / (double)std::max<int64_t>(total, 1));
+            fprintf(stderr, "\n[plan] share by sources/op (<=1,2,4,..,128+):");
+            for (int i = 0; i < 8; i++)
+                fprintf(stderr, " %.3f", (double)by_srcs[i] / (double)std::max<int64_t>(total, 1));
+            fprintf(stderr, "\n");
+        }
     }
     delete ctx;
     return rc;
