@@ -202,6 +202,9 @@ png_deflate_kernel(const PngSeg *__restrict__ segs, const PngCanvas *__restrict_
     __shared__ unsigned s_item_bits[PNG_THREADS + 1];
     __shared__ unsigned s_item_a[PNG_THREADS], s_item_b[PNG_THREADS];
     __shared__ unsigned s_stage[PNG_WARPS][PNG_ITEM_WORDS];
+    __shared__ int s_count[PNG_MAXBITS + 2];         // symbols per code length
+    __shared__ unsigned s_next_code[PNG_MAXBITS + 1];
+    __shared__ unsigned s_warp_tot[3][PNG_WARPS];
     __shared__ unsigned s_match_bits[65];            // code + extra + distance of a match of n pixels ...
     __shared__ unsigned char s_match_len[65];        // ... and its length in bits
 
@@ -264,69 +267,92 @@ png_deflate_kernel(const PngSeg *__restrict__ segs, const PngCanvas *__restrict_
     __syncthreads();
     if (tid == 0) {
         const int n = 286;
-        // two-queue Huffman: leaves 0..n-1 in ascending weight; internal nodes n..2n-2 come out ascending too
+        // two-queue Huffman: leaves 0..n-1 in ascending weight; internal nodes n..2n-2 come out ascending too.
+        // This merge is the one sequential piece of the construction; everything after it runs on all threads.
         for (int i = 0; i < n; i++)
             s_weight[i] = s_freq[s_order[i]];
         int leaf = 0, node = n, next = n;
-        auto take = [&]() {
-            if (leaf < n && (node >= next || s_weight[leaf] <= s_weight[node]))
-                return leaf++;
-            return node++;
+        unsigned w_leaf = s_weight[0], w_node = 0xffffffffu;  // heads of the two queues, kept in registers
+        auto take = [&](unsigned &w) {
+            if (leaf < n && (node >= next || w_leaf <= w_node)) {
+                w = w_leaf;
+                const int r = leaf++;
+                w_leaf = leaf < n ? s_weight[leaf] : 0xffffffffu;
+                return r;
+            }
+            w = w_node;
+            const int r = node++;
+            w_node = node < next ? s_weight[node] : 0xffffffffu;
+            return r;
         };
         for (; next < 2 * n - 1; next++) {
-            const int a = take(), b = take();
-            s_weight[next] = s_weight[a] + s_weight[b];
+            unsigned wa, wb;
+            const int a = take(wa);
+            const int b = take(wb);
+            const unsigned w = wa + wb;
+            s_weight[next] = w;
+            if (node == next)
+                w_node = w;  // the node queue was empty: the new node is its head
             s_parent[a] = next, s_parent[b] = next;
         }
-        // depths (root = 2n - 2); s_weight is reused for them
-        s_weight[2 * n - 2] = 0;
-        int count[PNG_MAXBITS + 2];
-        for (int i = 0; i <= PNG_MAXBITS + 1; i++)
-            count[i] = 0;
-        for (int i = 2 * n - 3; i >= 0; i--) {
-            const unsigned d = s_weight[s_parent[i]] + 1;
-            s_weight[i] = d;
-            if (i < n)
-                count[d > PNG_MAXBITS ? PNG_MAXBITS : d]++;
-        }
+    }
+    for (int i = tid; i <= PNG_MAXBITS + 1; i += PNG_THREADS)
+        s_count[i] = 0;
+    __syncthreads();
+    // depth of every leaf (its code length before the limit): walk to the root, 286 walks side by side
+    for (int i = tid; i < 286; i += PNG_THREADS) {
+        int d = 0;
+        for (int q = i; q != 2 * 286 - 2; q = s_parent[q])
+            d++;
+        atomicAdd(&s_count[d > PNG_MAXBITS ? PNG_MAXBITS : d], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
         // enforce the length limit on the counts per length, keeping the code complete
         unsigned total = 0;
         for (int i = PNG_MAXBITS; i > 0; i--)
-            total += (unsigned)count[i] << (PNG_MAXBITS - i);
+            total += (unsigned)s_count[i] << (PNG_MAXBITS - i);
         while (total != (1u << PNG_MAXBITS)) {
-            count[PNG_MAXBITS]--;
+            s_count[PNG_MAXBITS]--;
             for (int i = PNG_MAXBITS - 1; i > 0; i--)
-                if (count[i]) {
-                    count[i]--;
-                    count[i + 1] += 2;
+                if (s_count[i]) {
+                    s_count[i]--;
+                    s_count[i + 1] += 2;
                     break;
                 }
             total--;
         }
-        int idx = 0;  // the least frequent symbols get the longest codes
-        for (int l = PNG_MAXBITS; l > 0; l--)
-            for (int q = count[l]; q > 0; q--)
-                s_len[s_order[idx++]] = (unsigned char)l;
-        s_len[286 + 3] = 1;  // distance 4: the only distance code, one bit
-        // canonical codes, stored bit-reversed (deflate packs Huffman codes from their most significant bit)
-        int bl_count[PNG_MAXBITS + 1];
-        for (int i = 0; i <= PNG_MAXBITS; i++)
-            bl_count[i] = 0;
-        for (int q = 0; q < 286; q++)
-            bl_count[s_len[q]]++;
-        bl_count[0] = 0;
-        unsigned next_code[PNG_MAXBITS + 1];
+        // first canonical code of every length
         unsigned code = 0;
+        s_count[0] = 0;
         for (int b = 1; b <= PNG_MAXBITS; b++) {
-            code = (code + bl_count[b - 1]) << 1;
-            next_code[b] = code;
+            code = (code + (unsigned)s_count[b - 1]) << 1;
+            s_next_code[b] = code;
         }
-        for (int q = 0; q < 286; q++) {
+        s_len[286 + 3] = 1;  // distance 4: the only distance code, one bit
+    }
+    __syncthreads();
+    // the least frequent symbols get the longest codes: position p of the ascending order has length l where the
+    // counts of the lengths above l cover fewer than p + 1 symbols
+    for (int p = tid; p < 286; p += PNG_THREADS) {
+        int l = PNG_MAXBITS, covered = s_count[PNG_MAXBITS];
+        while (covered <= p)
+            covered += s_count[--l];
+        s_len[s_order[p]] = (unsigned char)l;
+    }
+    __syncthreads();
+    // canonical codes, stored bit-reversed (deflate packs Huffman codes from their most significant bit): the
+    // code of a symbol = first code of its length + the number of smaller symbols of that length
+    for (int q = tid; q < PNG_NSYM; q += PNG_THREADS) {
+        unsigned short c = 0;
+        if (q < 286) {
             const int l = s_len[q];
-            s_code[q] = l ? (unsigned short)bit_reverse(next_code[l]++, l) : 0;
+            int before = 0;
+            for (int r = 0; r < q; r++)
+                before += s_len[r] == l ? 1 : 0;
+            c = (unsigned short)bit_reverse(s_next_code[l] + (unsigned)before, l);
         }
-        for (int q = 286; q < PNG_NSYM; q++)
-            s_code[q] = 0;  // distance code 3 = "0"
+        s_code[q] = c;  // distance code 3 = "0"
     }
     __syncthreads();
     if (tid >= 1 && tid <= 64) {
@@ -412,20 +438,49 @@ png_deflate_kernel(const PngSeg *__restrict__ segs, const PngCanvas *__restrict_
         __syncwarp();
     }
     __syncthreads();
-    if (tid == 0) {
-        // exclusive scan (<= 256 entries) + Adler-32 of the segment, items in stream order
-        unsigned off = PNG_HEADER_BITS;
-        unsigned a = 1, b = 0;
-        for (int i = 0; i < n_items; i++) {
-            const unsigned t = s_item_bits[i];
-            s_item_bits[i] = off;
-            off += t;
-            const int ic0 = (i % items_per_row) * PNG_ITEM_PX;
-            const unsigned long long nbytes = 4ull * (min(cv.cols, ic0 + PNG_ITEM_PX) - ic0) + (ic0 == 0 ? 1 : 0);
-            adler_combine(a, b, s_item_a[i], s_item_b[i], nbytes);
+    {
+        // exclusive scan of the item sizes (<= 256 = one per thread) + Adler-32 of the segment, items in stream order:
+        // A = 1 + sum (a_i - 1), B = sum b_i + sum n_i * (A before item i - 1)   (zlib's adler32_combine, unrolled)
+        const bool on = tid < n_items;
+        const unsigned bits = on ? s_item_bits[tid] : 0u;
+        const unsigned a1 = on ? (s_item_a[tid] + ADLER_MOD - 1) % ADLER_MOD : 0u;
+        unsigned inc_bits = bits, inc_a = a1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t0 = __shfl_up_sync(0xffffffffu, inc_bits, o), t1 = __shfl_up_sync(0xffffffffu, inc_a, o);
+            if (lane >= o)
+                inc_bits += t0, inc_a += t1;
         }
-        s_item_bits[n_items] = off;  // end of the items: the end-of-block code follows
-        seg_adler[2 * blockIdx.x] = a, seg_adler[2 * blockIdx.x + 1] = b;
+        if (lane == 31)
+            s_warp_tot[0][warp] = inc_bits, s_warp_tot[1][warp] = inc_a;
+        __syncthreads();
+        unsigned base_bits = PNG_HEADER_BITS, base_a = 0;
+        for (int w = 0; w < warp; w++)
+            base_bits += s_warp_tot[0][w], base_a += s_warp_tot[1][w];
+        const unsigned ex_bits = base_bits + inc_bits - bits;
+        const unsigned ex_a = base_a + inc_a - a1;  // < 256 * 65521: no reduction needed before the product
+        unsigned term = 0;
+        if (on) {
+            const int ic0 = (tid % items_per_row) * PNG_ITEM_PX;
+            const unsigned long long nbytes = 4ull * (min(cv.cols, ic0 + PNG_ITEM_PX) - ic0) + (ic0 == 0 ? 1 : 0);
+            term = (unsigned)((s_item_b[tid] + nbytes * (ex_a % ADLER_MOD)) % ADLER_MOD);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+            term += __shfl_xor_sync(0xffffffffu, term, o);  // <= 32 * 65520
+        if (lane == 0)
+            s_warp_tot[2][warp] = term;
+        __syncthreads();  // every thread has read its s_item_bits entry
+        if (on)
+            s_item_bits[tid] = ex_bits;
+        if (tid == PNG_THREADS - 1) {
+            s_item_bits[n_items] = base_bits + inc_bits;  // end of the items: the end-of-block code follows
+            unsigned bsum = 0;
+            for (int w = 0; w < PNG_WARPS; w++)
+                bsum += s_warp_tot[2][w];
+            seg_adler[2 * blockIdx.x] = (1u + (base_a + inc_a) % ADLER_MOD) % ADLER_MOD;
+            seg_adler[2 * blockIdx.x + 1] = bsum % ADLER_MOD;
+        }
     }
     __syncthreads();
     const unsigned end_bits = s_item_bits[n_items];
@@ -467,9 +522,7 @@ png_deflate_kernel(const PngSeg *__restrict__ segs, const PngCanvas *__restrict_
         const int order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
         for (int i = 0; i < 19; i++)
             hs.put(order[i] < 16 ? 4u : 0u, 3);
-        for (int q = 0; q < PNG_NSYM; q++)
-            hs.put(bit_reverse(s_len[q], 4), 4);
-        hs.finish();
+        hs.finish();  // the 290 code lengths follow, written by all threads below
         // end of block (+ sync marker)
         BitWriter ts{out, 0ull, (int)(end_bits & 31), (long long)(end_bits >> 5), true};
         ts.put(s_code[256], (int)eob_len);
@@ -477,6 +530,14 @@ png_deflate_kernel(const PngSeg *__restrict__ segs, const PngCanvas *__restrict_
             ts.put(0u, 3);  // BFINAL = 0, BTYPE = 0: stored block of length 0
         ts.finish();
         seg_bytes[blockIdx.x] = (int)total_bytes;
+    }
+    for (int q = tid; q < PNG_NSYM; q += PNG_THREADS) {
+        // code length q as a 4-bit code of the fixed code-length code, at its place in the header
+        const unsigned pos = PNG_HEADER_BITS - PNG_NSYM * 4 + 4u * q;
+        const unsigned long long v = (unsigned long long)bit_reverse(s_len[q], 4) << (pos & 31);
+        atomicOr(out + (pos >> 5), (unsigned)v);
+        if ((unsigned)(v >> 32))
+            atomicOr(out + (pos >> 5) + 1, (unsigned)(v >> 32));
     }
     if (!seg.last) {
         __syncthreads();  // the marker bytes share a word with the last bits
