@@ -55,6 +55,7 @@ __constant__ unsigned char c_len_code[65];   // match of n pixels (4 n bytes): l
 __constant__ unsigned char c_len_ebits[65];  // number of extra bits
 __constant__ unsigned short c_len_extra[65]; // extra bits value
 __constant__ unsigned c_crc_table[256];
+__constant__ unsigned c_crc_slice[4][256];  // slicing-by-4: [k][i] = CRC of byte i followed by k zero bytes
 __constant__ unsigned c_crc_pow[32];         // x^(8 * 2^k) mod P, reflected
 
 // LSB-first bit writer into 32-bit words that start zeroed; the first and the last word of a writer may be shared
@@ -593,28 +594,41 @@ __device__ __forceinline__ void put_be32(unsigned char *p, unsigned v)
     p[0] = (unsigned char)(v >> 24), p[1] = (unsigned char)(v >> 16), p[2] = (unsigned char)(v >> 8), p[3] = (unsigned char)v;
 }
 
-// CRC-32 (zero init, no final xor) of bytes [0, n) by the whole CTA; result valid in thread 0
-__device__ unsigned block_crc0(const unsigned char *p, long long n, unsigned *s_part, long long *s_len, const unsigned *s_table)
+// CRC-32 (zero init, no final xor) of bytes [0, n) by the whole CTA; result valid in thread 0.  Every thread takes
+// a contiguous span (a multiple of 4 bytes), reads it as aligned words (the message may start at any byte: two
+// words and a funnel shift; up to 3 bytes behind the message are read, the caller guarantees they exist), four
+// bytes per step through four tables, then moves its CRC to the end of the message (crc * x^(8 * bytes after the
+// span), a few GF(2) multiplications, all threads at once) -- the message CRC is the xor of those.
+__device__ unsigned block_crc0(const unsigned char *p, long long n, unsigned *s_part, const unsigned (*s_slice)[256])
 {
     const int tid = threadIdx.x;
     const long long span = ((n + PNG_THREADS - 1) / PNG_THREADS + 3) & ~3ll;
     const long long a = min(n, (long long)tid * span), b = min(n, a + span);
     unsigned crc = 0;
-    for (long long i = a; i < b; i++)
-        crc = s_table[(crc ^ p[i]) & 255] ^ (crc >> 8);  // data-dependent index: shared memory, not the constant cache
-    s_part[tid] = crc, s_len[tid] = b - a;
-    __syncthreads();
-    for (int step = 1; step < PNG_THREADS; step <<= 1) {
-        if ((tid & (2 * step - 1)) == 0) {
-            const long long lb = s_len[tid + step];
-            if (lb > 0) {
-                s_part[tid] = crc_shift(s_part[tid], (unsigned long long)lb) ^ s_part[tid + step];
-                s_len[tid] += lb;
-            }
-        }
-        __syncthreads();
+    const int mis = (int)(reinterpret_cast<size_t>(p + a) & 3);
+    const unsigned *w = reinterpret_cast<const unsigned *>(p + a - mis);
+    const long long full = (b - a) >> 2;
+    unsigned lo = full > 0 || b > a ? w[0] : 0u;
+    for (long long i = 0; i < full; i++) {
+        const unsigned hi = mis ? w[i + 1] : 0u;
+        const unsigned v = mis ? __funnelshift_r(lo, hi, 8 * mis) : lo;
+        lo = mis ? hi : (i + 1 < full || (b - a) & 3 ? w[i + 1] : 0u);
+        crc ^= v;
+        crc = s_slice[3][crc & 255] ^ s_slice[2][(crc >> 8) & 255] ^ s_slice[1][(crc >> 16) & 255] ^ s_slice[0][crc >> 24];
     }
-    return s_part[0];
+    for (long long i = a + 4 * full; i < b; i++)
+        crc = s_slice[0][(crc ^ p[i]) & 255] ^ (crc >> 8);
+    crc = crc_shift(crc, (unsigned long long)(n - b));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        crc ^= __shfl_xor_sync(0xffffffffu, crc, o);
+    if ((tid & 31) == 0)
+        s_part[tid >> 5] = crc;
+    __syncthreads();
+    unsigned r = 0;
+    for (int k = 0; k < PNG_WARPS; k++)
+        r ^= s_part[k];
+    return r;
 }
 
 }  // namespace
@@ -624,11 +638,11 @@ png_pack_kernel(const PngCanvas *__restrict__ canvases, const PngSeg *__restrict
                 const unsigned *__restrict__ seg_adler, const unsigned char *__restrict__ scratch,
                 const long long *__restrict__ file_off, unsigned char *__restrict__ out)
 {
-    __shared__ unsigned s_part[PNG_THREADS];
-    __shared__ long long s_len[PNG_THREADS];
-    __shared__ unsigned s_table[256];
+    __shared__ unsigned s_part[PNG_WARPS];
+    __shared__ unsigned s_slice[4][256];  // data-dependent indices: shared memory, not the constant cache
     const int tid = threadIdx.x;
-    s_table[tid & 255] = c_crc_table[tid & 255];
+    for (int i = tid; i < 4 * 256; i += PNG_THREADS)
+        (&s_slice[0][0])[i] = (&c_crc_slice[0][0])[i];
     const PngCanvas cv = canvases[blockIdx.x];
     unsigned char *f = out + file_off[blockIdx.x];
     long long idat = 2 + 4;
@@ -694,7 +708,7 @@ png_pack_kernel(const PngCanvas *__restrict__ canvases, const PngSeg *__restrict
     }
     __syncthreads();
     // CRC of the IDAT chunk: type + data
-    const unsigned c0 = block_crc0(body - 4, idat + 4, s_part, s_len, s_table);
+    const unsigned c0 = block_crc0(body - 4, idat + 4, s_part, s_slice);  // the 4 CRC bytes + IEND follow: readable
     if (tid == 0) {
         // a CRC started from 0xffffffff = the zero-started one xor the shifted initial value
         const unsigned crc = c0 ^ crc_shift(0xffffffffu, (unsigned long long)(idat + 4));
@@ -737,6 +751,13 @@ static void png_init_tables()
         table[i] = c;
     }
     cudaMemcpyToSymbol(c_crc_table, table, sizeof table);
+    unsigned slice[4][256];
+    for (unsigned i = 0; i < 256; i++) {
+        slice[0][i] = table[i];
+        for (int k = 1; k < 4; k++)
+            slice[k][i] = (slice[k - 1][i] >> 8) ^ table[slice[k - 1][i] & 255];
+    }
+    cudaMemcpyToSymbol(c_crc_slice, slice, sizeof slice);
     // x^(8 * 2^k) mod P in reflected order: x^8 is the CRC of the byte 0x80 followed by ... computed by squaring
     auto mul = [](unsigned a, unsigned b) {
         unsigned p = 0;
