@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define SVGR_VERSION 200
+#define SVGR_VERSION 210
 
 enum {
     SVGR_OK = 0,
@@ -107,6 +107,21 @@ typedef struct svgr_external {
     int32_t pad;
 } svgr_external;
 
+/* A gradient paint in objectBoundingBox units (paint.bbox_units, svgrasterize.py:1023-1026): its pixel -> gradient
+ * map depends on ConvexHull.bbox_transform (:2002-2023) of the leaf's own end points, which only exist once the path
+ * is flattened.  The encoder leaves the map out of the PaintRec and records this job; the render completes the record
+ * on the device (bounds of transform.invert(points) -> transform.translate(x, y).scale(w, h) -> inverse ->
+ * coefficients) between flattening and compositing, without a host round trip. */
+typedef struct svgr_bbox_job {
+    int32_t paint;       /* PaintRec to complete (kind, stops, spread, the two-circle constants are already there) */
+    int32_t path;        /* the leaf's path */
+    int32_t has_grad_tr; /* 1: grad_inv holds the inverse gradientTransform */
+    int32_t pad;
+    double inv[6];       /* transform.invert of the leaf's transform, 2 x 3 row-major (numpy's) */
+    double grad_inv[6];  /* inverse gradientTransform, 2 x 3 row-major */
+    double geom[6];      /* linear: p0x p0y vx vy vv | radial: cx cy r | two-circle: fx fy */
+} svgr_bbox_job;
+
 /* The records below are declared in svgr_types.h (same layout on host and device). */
 struct PathRec;
 struct StrokeRec;
@@ -158,6 +173,10 @@ typedef struct svgr_program {
     /* output */
     int64_t canvas_bytes; /* total RGBA8 bytes written by the canvas nodes */
     double flatness;      /* bezier3_flatten_batch(batch, flatness) (:2091); 0 = Path.mask's literal 0.1 (:955) */
+    /* objectBoundingBox gradients completed on the device */
+    int32_t n_bbox_job;
+    int32_t pad_bbox;
+    const svgr_bbox_job *bbox_jobs;
 } svgr_program;
 
 typedef struct svgr_stats {
@@ -193,7 +212,7 @@ typedef struct svgr_ctx svgr_ctx;
 
 int svgr_version(void);
 /* sizeof of the ABI records, for binding self-checks: 0 PathRec, 1 StrokeRec, 2 PaintRec, 3 StopRec,
- * 4 svgr_node, 5 svgr_kernel, 6 svgr_external, 7 svgr_program, 8 svgr_stats */
+ * 4 svgr_node, 5 svgr_kernel, 6 svgr_external, 7 svgr_program, 8 svgr_stats, 9 MaskRec, 10 svgr_bbox_job */
 int svgr_sizeof(int what);
 int svgr_create(int device, svgr_ctx **out);
 void svgr_destroy(svgr_ctx *ctx);
@@ -269,7 +288,7 @@ int64_t svgr_expand_arcs(const uint8_t *tags, const double *data, int64_t n, uin
 typedef struct svgr_flat_paint {
     int32_t kind;          /* 1 solid, 2 linear gradient, 3 radial gradient */
     int32_t spread;        /* 0 pad, 1 repeat, 2 reflect */
-    int32_t bbox_units;    /* objectBoundingBox units: not covered, the scene takes the Python encoder */
+    int32_t bbox_units;    /* objectBoundingBox units: the encoder records a svgr_bbox_job, the render completes it */
     int32_t lin;           /* paint.linear_rgb: -1 None, 0, 1 */
     int32_t has_transform; /* 1: inv holds the inverse gradientTransform */
     int32_t stop_off, stop_cnt;

@@ -27,6 +27,9 @@ STOP_DT = np.dtype([("offset", "<f8"), ("color", "<f4", 4), ("inv_span", "<f8")]
 NODE_DT = np.dtype([("tag", "<i4"), ("a", "<i4"), ("b", "<i4"), ("c", "<i4"), ("d", "<i4"), ("child_off", "<i4"),
                     ("child_cnt", "<i4"), ("flags", "<i4"), ("f", "<f8", 4)], align=True)
 KERNEL_DT = np.dtype([("rows", "<i4"), ("cols", "<i4"), ("separable", "<i4"), ("weight_off", "<i4")], align=True)
+# svgr_bbox_job: an objectBoundingBox gradient the render completes on the device
+BBOX_JOB_DT = np.dtype([("paint", "<i4"), ("path", "<i4"), ("has_grad_tr", "<i4"), ("pad", "<i4"), ("inv", "<f8", 6),
+                        ("grad_inv", "<f8", 6), ("geom", "<f8", 6)], align=True)
 
 PAINT_SOLID, PAINT_LINEAR, PAINT_RADIAL, PAINT_RADIAL_FOCAL, PAINT_PATTERN = range(5)
 (N_EMPTY, N_LEAF, N_GROUP, N_OPACITY, N_IN, N_LUMA, N_COMPOSE, N_SRC_ALPHA, N_CONVERT, N_BLUR, N_MORPH, N_CMATRIX,
@@ -58,6 +61,7 @@ class Program(C.Structure):
         ("n_external", C.c_int32), ("externals", C.c_void_p),
         ("canvas_bytes", C.c_int64),
         ("flatness", C.c_double),
+        ("n_bbox_job", C.c_int32), ("pad_bbox", C.c_int32), ("bbox_jobs", C.c_void_p),
     ]
 
 
@@ -137,7 +141,7 @@ def lib():
             fn.restype, fn.argtypes = res, args
         sizes = [PATH_DT.itemsize, STROKE_DT.itemsize, PAINT_DT.itemsize, STOP_DT.itemsize, NODE_DT.itemsize,
                  KERNEL_DT.itemsize, C.sizeof(External), C.sizeof(Program), C.sizeof(Stats)]
-        for what, size in enumerate(sizes):
+        for what, size in list(enumerate(sizes)) + [(10, BBOX_JOB_DT.itemsize)]:
             if L.svgr_sizeof(what) != size:
                 raise ImportError(f"ABI mismatch for record {what}: library {L.svgr_sizeof(what)} vs binding {size}")
         _lib = L

@@ -389,8 +389,7 @@ static long flatten_paint(Ctx *c, PyObject *paint)
         int bbox = 0;
         if (truthy_attr(paint, "bbox_units", &bbox))
             return -2;
-        if (bbox)
-            return -3;
+        rec.bbox_units = bbox; /* completed on the device (svgr_bbox_job) */
         PyObject *spread = PyObject_GetAttrString(paint, "spread");
         if (!spread)
             return -2;

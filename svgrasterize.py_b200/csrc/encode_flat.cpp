@@ -25,6 +25,8 @@
 #include "../../include/svgr_b200.h"
 #include "svgr_types.h"
 
+#include "svgr_affine.h"
+
 extern "C" int64_t svgr_arc_to_cubics(double cx, double cy, double rx, double ry, double phi, double eta, double eta_delta,
                                       double *out, int64_t cap);
 
@@ -32,72 +34,8 @@ namespace {
 
 enum { R_FILL = 0, R_STROKE = 1, R_GROUP = 2, R_OPACITY = 3, R_CLIP = 4, R_MASK = 5, R_TRANSFORM = 6, R_FILTER = 7 };
 
-struct M23 {
-    double m[6];  // row-major 2 x 3; the third row is (0, 0, 1)
-};
-
-// numpy: a @ b for 3 x 3 float64 (measured on this OpenBLAS: fma(a2, b2, fma(a1, b1, a0 * b0)) per element)
-M23 matmul(const M23 &a, const M23 &b)
-{
-    M23 c;
-    for (int i = 0; i < 2; i++) {
-        const double a0 = a.m[3 * i], a1 = a.m[3 * i + 1], a2 = a.m[3 * i + 2];
-        c.m[3 * i + 0] = fma(a2, 0.0, fma(a1, b.m[3], a0 * b.m[0]));
-        c.m[3 * i + 1] = fma(a2, 0.0, fma(a1, b.m[4], a0 * b.m[1]));
-        c.m[3 * i + 2] = fma(a2, 1.0, fma(a1, b.m[5], a0 * b.m[2]));
-    }
-    return c;
-}
-
-// np.linalg.inv of the 3 x 3 affine matrix: LU with partial pivoting, columns of the identity solved one by one
-// (right-looking elimination, multipliers scaled by the reciprocal pivot, fused substitution steps)
-bool invert(const M23 &t, M23 &out)
-{
-    double a[3][3] = {{t.m[0], t.m[1], t.m[2]}, {t.m[3], t.m[4], t.m[5]}, {0.0, 0.0, 1.0}};
-    int perm[3] = {0, 1, 2};
-    for (int k = 0; k < 3; k++) {
-        int p = k;
-        for (int i = k + 1; i < 3; i++)
-            if (fabs(a[i][k]) > fabs(a[p][k]))
-                p = i;
-        if (a[p][k] == 0.0)
-            return false;
-        if (p != k) {
-            for (int j = 0; j < 3; j++) {
-                const double tmp = a[k][j];
-                a[k][j] = a[p][j], a[p][j] = tmp;
-            }
-            const int tp = perm[k];
-            perm[k] = perm[p], perm[p] = tp;
-        }
-        const double rp = 1.0 / a[k][k];
-        for (int i = k + 1; i < 3; i++)
-            a[i][k] = a[i][k] * rp;
-        for (int i = k + 1; i < 3; i++)
-            for (int j = k + 1; j < 3; j++)
-                a[i][j] = a[i][j] - a[i][k] * a[k][j];
-    }
-    double x[3][3];
-    for (int c = 0; c < 3; c++) {
-        double y[3];
-        for (int i = 0; i < 3; i++)
-            y[i] = perm[i] == c ? 1.0 : 0.0;
-        for (int i = 0; i < 3; i++)
-            for (int q = 0; q < i; q++)
-                y[i] = fma(-a[i][q], y[q], y[i]);
-        for (int i = 2; i >= 0; i--) {
-            for (int q = i + 1; q < 3; q++)
-                y[i] = fma(-a[i][q], y[q], y[i]);
-            y[i] = y[i] * (1.0 / a[i][i]);
-        }
-        for (int i = 0; i < 3; i++)
-            x[i][c] = y[i];
-    }
-    for (int i = 0; i < 2; i++)
-        for (int j = 0; j < 3; j++)
-            out.m[3 * i + j] = x[i][j];
-    return true;
-}
+inline M23 matmul(const M23 &a, const M23 &b) { return affine_matmul(a, b); }
+inline bool invert(const M23 &t, M23 &out) { return affine_invert(t, out); }
 
 // color.py paint_to_srgb: premultiplied linear RGBA -> premultiplied sRGB RGBA
 void paint_to_srgb(const double *c, double *o)
@@ -130,6 +68,7 @@ struct svgr_encoded {
     std::vector<StopRec> stops;
     std::vector<svgr_node> nodes;
     std::vector<int32_t> children;
+    std::vector<svgr_bbox_job> bbox_jobs;
     std::vector<int64_t> canvases;  // node, byte offset, rows, cols per canvas
     std::vector<int32_t> roots;
     int32_t n_focal = 0;
@@ -299,10 +238,6 @@ struct Encoder {
             fail(SVGR_E_UNSUPPORTED, "flat scene: paint kind needs the Python encoder");
             return -1;
         }
-        if (p.bbox_units) {
-            fail(SVGR_E_UNSUPPORTED, "flat scene: objectBoundingBox paint needs the Python encoder");
-            return -1;
-        }
         if (p.spread < 0 || p.spread > 2) {
             fail(SVGR_E_INVALID, "invalid spread method");
             return -1;
@@ -329,32 +264,15 @@ struct Encoder {
             sr.inv_span = k + 1 < p.stop_cnt ? 1.0 / (in.stops[p.stop_off + k + 1].offset - s.offset) : 0.0;
             out.stops.push_back(sr);
         }
-        // pixel centre -> gradient space: transform.invert, then the inverse gradientTransform (:1022-1031, :1558)
-        M23 to_user;
-        if (!invert(t, to_user)) {
-            fail(SVGR_E_INVALID, "Singular matrix");
-            return -1;
-        }
-        if (p.has_transform) {
-            M23 gi;
-            memcpy(gi.m, p.inv, sizeof gi.m);
-            to_user = matmul(gi, to_user);
-        }
-        const double A00 = to_user.m[0], A01 = to_user.m[1], T0 = to_user.m[2];
-        const double A10 = to_user.m[3], A11 = to_user.m[4], T1 = to_user.m[5];
+        // the gradient's own geometry: what does not depend on the transform
+        double geom[6] = {0, 0, 0, 0, 0, 0};
         if (p.kind == 2) {
             const double v0 = p.p[2] - p.p[0], v1 = p.p[3] - p.p[1];
-            const double vv = fma(v1, v1, v0 * v0);
             rec.kind = PAINT_LINEAR;
-            rec.g[0] = fma(v1, A10, v0 * A00) / vv;
-            rec.g[1] = fma(v1, A11, v0 * A01) / vv;
-            const double d0 = T0 - p.p[0], d1 = T1 - p.p[1];
-            rec.g[2] = fma(d1, v1, d0 * v0) / vv;
+            geom[0] = p.p[0], geom[1] = p.p[1], geom[2] = v0, geom[3] = v1, geom[4] = fma(v1, v1, v0 * v0);
         } else if (!(p.focal & 3)) {
-            const double r = p.p[2];
             rec.kind = PAINT_RADIAL;
-            rec.m1[0] = A00 / r, rec.m1[1] = A01 / r, rec.m1[3] = A10 / r, rec.m1[4] = A11 / r;
-            rec.m1[2] = (T0 - p.p[0]) / r, rec.m1[5] = (T1 - p.p[1]) / r;
+            geom[0] = p.p[0], geom[1] = p.p[1], geom[2] = p.p[2];
         } else {
             const double cx = p.p[0], cy = p.p[1], r = p.p[2];
             const double fx = (p.focal & 1) ? p.p[3] : cx, fy = (p.focal & 1) ? p.p[4] : cy;
@@ -365,12 +283,36 @@ struct Encoder {
             volatile double two = 2.0;
             const double a = (cd0 * cd0 + cd1 * cd1) - pow(rd, two);
             rec.kind = PAINT_RADIAL_FOCAL;
-            rec.m1[0] = A00, rec.m1[1] = A01, rec.m1[3] = A10, rec.m1[4] = A11;
-            rec.m1[2] = T0 - fx, rec.m1[5] = T1 - fy;
+            geom[0] = fx, geom[1] = fy;
             rec.g[0] = cd0, rec.g[1] = cd1, rec.g[2] = fr * rd, rec.g[3] = a, rec.g[4] = fr * fr;
             rec.g[5] = fr / (fr - r), rec.g[6] = fr != r ? 1.0 : 0.0, rec.g[7] = 1.0 / a;
             rec.flag = out.n_focal++;
         }
+        // pixel centre -> gradient space: transform.invert, then the inverse gradientTransform (:1022-1031, :1558)
+        M23 to_user;
+        if (!invert(t, to_user)) {
+            fail(SVGR_E_INVALID, "Singular matrix");
+            return -1;
+        }
+        if (p.bbox_units) {
+            // the map needs ConvexHull.bbox_transform of the flattened leaf (:1023-1026): the render completes it
+            svgr_bbox_job job;
+            memset(&job, 0, sizeof job);
+            job.path = pid, job.has_grad_tr = p.has_transform ? 1 : 0;
+            memcpy(job.inv, to_user.m, sizeof job.inv);
+            if (p.has_transform)
+                memcpy(job.grad_inv, p.inv, sizeof job.grad_inv);
+            memcpy(job.geom, geom, sizeof job.geom);
+            job.paint = paint_record(rec);
+            out.bbox_jobs.push_back(job);
+            return node(SVGR_N_LEAF, pid, job.paint, lin ? 1 : 0, -1);
+        }
+        if (p.has_transform) {
+            M23 gi;
+            memcpy(gi.m, p.inv, sizeof gi.m);
+            to_user = matmul(gi, to_user);
+        }
+        gradient_coefficients(rec.kind, geom, to_user, rec.g, rec.m1);
         return node(SVGR_N_LEAF, pid, paint_record(rec), lin ? 1 : 0, -1);
     }
 
@@ -551,6 +493,7 @@ int svgr_encode_flat(const svgr_flat *in, svgr_encoded **out_handle)
     p.n_node = (int32_t)e->nodes.size(), p.nodes = e->nodes.data();
     p.n_child = (int32_t)e->children.size(), p.children = e->children.data();
     p.canvas_bytes = e->canvas_bytes;
+    p.n_bbox_job = (int32_t)e->bbox_jobs.size(), p.bbox_jobs = e->bbox_jobs.data();
     return SVGR_OK;
 }
 

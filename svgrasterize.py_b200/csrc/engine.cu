@@ -147,7 +147,7 @@ struct StatusBlock {  // device -> host after flatten
     int outline_total;   // outline segments incl. padding
     int outline_count;   // segments visible to flatten
     int binned_total;
-    int pad;
+    int paint_err;       // resolve_paints_kernel: bit 0 = singular objectBoundingBox matrix
 };
 
 }  // namespace
@@ -188,6 +188,10 @@ struct svgr_ctx {
     std::vector<int> h_sitems;
     int n_sitems = 0;
     DevBuf d_paints, d_stops, d_matrices, d_weights;
+    DevBuf d_bbox_jobs, d_bbox_csr, d_bbox_inv, d_bbox_keys;  // objectBoundingBox gradients completed after flattening
+    int n_bbox_job = 0;
+    std::vector<int> h_bbox_csr;
+    std::vector<double> h_bbox_inv;
     std::vector<PathRec> h_paths;
     std::vector<PaintRec> h_paints;
     std::vector<svgr_node> h_nodes;
@@ -1381,6 +1385,16 @@ static int load_program(svgr_ctx *ctx, const svgr_program *p, cudaStream_t s, bo
         if (e.channels != 1 && e.channels != 4)
             FAIL(SVGR_E_INVALID, "external layer must have 1 or 4 channels");
     }
+    if (p->n_bbox_job < 0 || (p->n_bbox_job > 0 && !p->bbox_jobs))
+        FAIL(SVGR_E_INVALID, "bad objectBoundingBox job table");
+    for (int i = 0; i < p->n_bbox_job; i++) {
+        const svgr_bbox_job &j = p->bbox_jobs[i];
+        if (j.path < 0 || j.path >= p->n_path || j.paint < 0 || j.paint >= p->n_paint)
+            FAIL(SVGR_E_INVALID, "objectBoundingBox job refers outside the path / paint tables");
+        const int kind = p->paints[j.paint].kind;
+        if (kind != PAINT_LINEAR && kind != PAINT_RADIAL && kind != PAINT_RADIAL_FOCAL)
+            FAIL(SVGR_E_INVALID, "objectBoundingBox job on a paint that is not a gradient");
+    }
     // ---- accepted: from here on the context describes the new program
     ctx->have_program = false;
     ctx->plan_cached = false;
@@ -1418,6 +1432,29 @@ static int load_program(svgr_ctx *ctx, const svgr_program *p, cudaStream_t s, bo
         CK(upload(ctx->d_sseg_job, p->stroke_seg_job, (size_t)p->n_stroke_seg, s));
         CK(upload(ctx->d_paints, p->paints, (size_t)p->n_paint, s));
         CK(upload(ctx->d_stops, p->stops, (size_t)p->n_stop, s));
+        ctx->n_bbox_job = p->n_bbox_job;
+        if (p->n_bbox_job > 0) {
+            // CSR path -> jobs for cloud_bounds_kernel (one query per job, its path list = the leaf's own path)
+            std::vector<int> &csr = ctx->h_bbox_csr;
+            csr.assign((size_t)p->n_path + 1 + p->n_bbox_job, 0);
+            for (int i = 0; i < p->n_bbox_job; i++)
+                csr[p->bbox_jobs[i].path + 1]++;
+            for (int i = 0; i < p->n_path; i++)
+                csr[i + 1] += csr[i];
+            std::vector<int> cur(csr.begin(), csr.begin() + p->n_path);
+            for (int i = 0; i < p->n_bbox_job; i++)
+                csr[(size_t)p->n_path + 1 + cur[p->bbox_jobs[i].path]++] = i;
+            std::vector<double> &inv = ctx->h_bbox_inv;
+            inv.resize((size_t)p->n_bbox_job * 6);
+            for (int i = 0; i < p->n_bbox_job; i++)
+                memcpy(&inv[6 * (size_t)i], p->bbox_jobs[i].inv, 48);
+            CK(ctx->d_bbox_csr.ensure(csr.size() * sizeof(int)));
+            CK(ctx->d_bbox_inv.ensure(inv.size() * sizeof(double)));
+            CK(ctx->d_bbox_keys.ensure((size_t)p->n_bbox_job * 32));
+            CK(cudaMemcpyAsync(ctx->d_bbox_csr.p, csr.data(), csr.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+            CK(cudaMemcpyAsync(ctx->d_bbox_inv.p, inv.data(), inv.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+            CK(upload(ctx->d_bbox_jobs, p->bbox_jobs, (size_t)p->n_bbox_job, s));
+        }
         CK(upload(ctx->d_matrices, p->matrices, (size_t)p->n_matrix * 20, s));
         CK(upload(ctx->d_weights, p->weights, (size_t)p->n_weight, s));
     }
@@ -1556,6 +1593,17 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
             if (ctx->band_mode && ctx->n_path > 0)
                 CK(cudaMemcpyAsync(ctx->pin_full_boxes.p, ctx->d_full_boxes.p, (size_t)ctx->n_path * sizeof(PathBox),
                                    cudaMemcpyDeviceToHost, s));
+            if (ctx->n_bbox_job > 0) {
+                // objectBoundingBox gradients: the boxes of the flattened leaves exist now
+                svgr_launch_resolve_paints(ctx->d_edges.as<double>(), ctx->d_edge_path.as<uint32_t>(), &d_st->n_edges,
+                                           (unsigned long long)ctx->edge_cap, ctx->d_bbox_csr.as<int>(),
+                                           ctx->d_bbox_csr.as<int>() + ctx->n_path + 1, ctx->d_bbox_inv.as<double>(),
+                                           ctx->d_bbox_keys.as<unsigned long long>(),
+                                           ctx->d_bbox_jobs.as<svgr_bbox_job>(), ctx->n_bbox_job,
+                                           ctx->d_paths.as<PathRec>(), ctx->d_paints.as<PaintRec>(), &d_st->paint_err,
+                                           SM, s);
+                n_kernels += 3;
+            }
             n_kernels += (ctx->n_seg > 0) + (S > 0) + (ctx->n_path > 0);
             if (ctx->n_path > 0)
                 CK(cudaMemcpyAsync(ctx->pin_boxes.p, ctx->d_boxes.p, (size_t)ctx->n_path * sizeof(PathBox),
@@ -1596,6 +1644,8 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
         FAIL(SVGR_E_STROKE, "cannot unpack non-iterable NoneType object");
     if (st.stroke_err & 2)
         FAIL(SVGR_E_INVALID, "stroke assembly overflow or unknown line cap");
+    if (st.paint_err & 1)
+        FAIL(SVGR_E_INVALID, "Singular matrix");  // numpy.linalg.LinAlgError in ConvexHull.bbox_transform(...).invert
     ctx->n_edges = (long long)st.n_edges;
     if (ctx->n_edges > 0x7fffffffll / 4)
         FAIL(SVGR_E_UNSUPPORTED, "more than 2^29 edges in one program: the band scans are 32-bit");
@@ -2053,6 +2103,7 @@ int svgr_sizeof(int what)
     case 7: return (int)sizeof(svgr_program);
     case 8: return (int)sizeof(svgr_stats);
     case 9: return (int)sizeof(MaskRec);
+    case 10: return (int)sizeof(svgr_bbox_job);
     default: return -1;
     }
 }

@@ -22,6 +22,8 @@
 // at t = 1/2 and pushes both halves.  Lanes therefore stay busy regardless of
 // how unevenly the subdivision depth is distributed over the input curves.
 #include "svgr_kernels.h"
+#include "svgr_affine.h"
+#include "../../include/svgr_b200.h"
 #include <algorithm>
 
 #define FLAT_WARPS 4
@@ -416,6 +418,47 @@ __global__ void cloud_bounds_kernel(const double *__restrict__ edges, const uint
     }
 }
 
+// Completes the PaintRec of every objectBoundingBox gradient (svgr_bbox_job): ConvexHull.bbox of the leaf's end
+// points in user space (the min / max keys cloud_bounds_kernel has just accumulated for the job) ->
+// ConvexHull.bbox_transform = transform.translate(x, y).scale(w, h), or the transform itself for an empty box
+// (svgrasterize.py:2002-2023) -> inverse -> inverse gradientTransform -> the coefficients paint_eval reads.  The same
+// float64 recipes as the host encoder (svgr_affine.h); a singular matrix (a box of zero width xor height) is the
+// reference's LinAlgError and raises *err.
+__global__ void resolve_paints_kernel(const svgr_bbox_job *__restrict__ jobs, int n_jobs, const PathRec *__restrict__ paths,
+                                      const unsigned long long *__restrict__ keys, PaintRec *paints, int *err)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_jobs)
+        return;
+    const svgr_bbox_job j = jobs[i];
+    if (keys[4 * i] == ~0ull)
+        return;  // no end points: the leaf renders nothing and the paint is never evaluated
+    const double x = of_key(keys[4 * i + 0]), y = of_key(keys[4 * i + 1]);
+    const double w = of_key(keys[4 * i + 2]) - x, h = of_key(keys[4 * i + 3]) - y;
+    M23 t, to_user;
+    for (int k = 0; k < 6; k++)
+        t.m[k] = paths[j.path].m[k];
+    if (w <= 0 && h <= 0) {
+        for (int k = 0; k < 6; k++)
+            to_user.m[k] = j.inv[k];  // transform.invert as numpy computed it
+    } else {
+        const M23 tr = {{1.0, 0.0, x, 0.0, 1.0, y}}, sc = {{w, 0.0, 0.0, 0.0, h, 0.0}};
+        t = affine_matmul(affine_matmul(t, tr), sc);
+        if (!affine_invert(t, to_user)) {
+            atomicOr(err, 1);
+            return;
+        }
+    }
+    if (j.has_grad_tr) {
+        M23 gi;
+        for (int k = 0; k < 6; k++)
+            gi.m[k] = j.grad_inv[k];
+        to_user = affine_matmul(gi, to_user);
+    }
+    PaintRec &p = paints[j.paint];
+    gradient_coefficients(p.kind, j.geom, to_user, p.g, p.m1);
+}
+
 __global__ void keys_to_f64_kernel(const unsigned long long *__restrict__ keys, double *__restrict__ out, int n4)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -481,6 +524,18 @@ void svgr_launch_bounds(const unsigned long long *minmax, const PathRec *paths, 
 {
     if (n_paths > 0)
         bounds_kernel<<<(n_paths + 255) / 256, 256, 0, s>>>(minmax, paths, n_paths, boxes, full_boxes, minmax_f64);
+}
+
+void svgr_launch_resolve_paints(const double *edges, const uint32_t *edge_path, const unsigned long long *n_edges,
+                                unsigned long long cap, const int *pq_off, const int *pq_idx, const double *q_inv,
+                                unsigned long long *keys, const svgr_bbox_job *jobs, int n_jobs, const PathRec *paths,
+                                PaintRec *paints, int *err, int sm_count, cudaStream_t s)
+{
+    if (n_jobs <= 0)
+        return;
+    minmax_init_kernel<<<(n_jobs + 255) / 256, 256, 0, s>>>(keys, n_jobs);
+    cloud_bounds_kernel<<<sm_count * 4, 256, 0, s>>>(edges, edge_path, n_edges, cap, pq_off, pq_idx, q_inv, keys);
+    resolve_paints_kernel<<<(n_jobs + 255) / 256, 256, 0, s>>>(jobs, n_jobs, paths, keys, paints, err);
 }
 
 void svgr_launch_cloud_bounds(const double *edges, const uint32_t *edge_path, const unsigned long long *n_edges,

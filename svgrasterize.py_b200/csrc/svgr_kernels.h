@@ -40,6 +40,11 @@ void svgr_launch_flatten_overflow(const PathRec *paths, double thr, double *edge
                                   int sm_count, const svgr_flat_overflow *ovf, cudaStream_t s);
 void svgr_launch_bounds(const unsigned long long *minmax, const PathRec *paths, int n_paths, PathBox *boxes,
                         PathBox *full_boxes, double *minmax_f64, cudaStream_t s);
+struct svgr_bbox_job;
+void svgr_launch_resolve_paints(const double *edges, const uint32_t *edge_path, const unsigned long long *n_edges,
+                                unsigned long long cap, const int *pq_off, const int *pq_idx, const double *q_inv,
+                                unsigned long long *keys, const svgr_bbox_job *jobs, int n_jobs, const PathRec *paths,
+                                PaintRec *paints, int *err, int sm_count, cudaStream_t s);
 void svgr_launch_cloud_bounds(const double *edges, const uint32_t *edge_path, const unsigned long long *n_edges,
                               unsigned long long cap, const int *pq_off, const int *pq_idx, const double *q_inv,
                               unsigned long long *q_minmax, double *q_out, int n_q, int sm_count, cudaStream_t s);

@@ -124,7 +124,7 @@ class Program:
 
     ARRAYS = ("seg_tag", "seg_data", "seg_path", "paths", "strokes", "stroke_sub_off", "stroke_sub_job", "stroke_tag",
               "stroke_data", "stroke_seg_job", "paints", "stops", "nodes", "children", "kernels", "weights", "matrices",
-              "offset_tr")
+              "offset_tr", "bbox_jobs")
 
     def __init__(self):
         self.seg_tag = np.zeros(0, np.uint8)
@@ -146,6 +146,7 @@ class Program:
         self.weights = np.zeros(0, np.float32)
         self.matrices = np.zeros((0, 20), np.float32)
         self.offset_tr = np.zeros((0, 12), np.float64)
+        self.bbox_jobs = np.zeros(0, _lib.BBOX_JOB_DT)  # objectBoundingBox gradients completed on the device
         self.externals = []  # (image float32, r0, c0, pre_alpha, linear_rgb)
         self.canvas_bytes = 0
         self.canvases = []  # (node, byte offset, rows, cols)
@@ -184,6 +185,7 @@ class Program:
         put("weights", self.weights, "n_weight")
         put("matrices", self.matrices, "n_matrix")
         put("offset_tr", self.offset_tr, "n_offset_tr")
+        put("bbox_jobs", self.bbox_jobs, "n_bbox_job")
         ext = (_lib.External * max(len(self.externals), 1))()
         for i, (img, r0, c0, pre, lin) in enumerate(self.externals):
             img = np.ascontiguousarray(img, dtype=np.float32)
@@ -253,6 +255,10 @@ class Program:
             parts["weights"].append(p.weights)
             parts["matrices"].append(p.matrices)
             parts["offset_tr"].append(p.offset_tr)
+            bj = p.bbox_jobs.copy()
+            bj["paint"] += base["paint"]
+            bj["path"] += base["path"]
+            parts["bbox_jobs"].append(bj)
             out.externals.extend(p.externals)
             out.canvases.extend((n + base["node"], off + base["canvas"], r, c) for n, off, r, c in p.canvases)
             out.roots.extend(n + base["node"] for n in p.roots)
@@ -295,6 +301,7 @@ class Encoder:
         self.s_tag, self.s_data, self.s_seg_job = [], [], []
         self.n_sseg = 0
         self.paints, self.stops, self.n_focal = [], [], 0
+        self.bbox_jobs = []  # (paint, path, has_grad_tr, inv6, grad_inv6, geom6)
         self.nodes, self.children = [], []
         self.kernels, self.weights, self.n_weight = [], [], 0
         self.matrices, self.offset_tr = [], []
@@ -428,49 +435,61 @@ class Encoder:
         elif kind in ("linear", "radial"):
             if paint.spread not in SPREAD:
                 raise ValueError(f"invalid spread method: {paint.spread}")  # svgrasterize.py:1668
-            tr = transform
-            if paint.bbox_units:
-                bbox = self_cloud()
-                if bbox is None:
-                    return self._empty()
-                tr = self._bbox_transform(bbox, transform)
             lin = linear_rgb if paint.linear_rgb is None else bool(paint.linear_rgb)
             stop_off, stop_cnt = self._stops(paint, lin)
             rec = dict(spread=SPREAD[paint.spread], stop_off=stop_off, stop_cnt=stop_cnt)
-            # pixel centre -> gradient space: transform.invert, then the inverse gradientTransform
-            # (svgrasterize.py:1022-1031, :1558, :1602); composed here so that the device evaluates one
-            # affine expression per pixel
-            to_user = tr.invert.m
-            if paint.transform is not None:
-                to_user = paint.transform.invert.m @ to_user
-            A, T = to_user[:2, :2], to_user[:2, 2]
-            g, m1 = np.zeros(8), np.zeros(6)
+            # the gradient's own geometry (what does not depend on the transform)
+            g, m1, geom = np.zeros(8), np.zeros(6), np.zeros(6)
             if kind == "linear":
                 p0, vec = np.asarray(paint.p0, dtype=np.float64), np.asarray(paint.p1, dtype=np.float64) - paint.p0
-                vv = float(np.dot(vec, vec))
-                with np.errstate(divide="ignore", invalid="ignore"):
-                    g[0:2] = (vec @ A) / vv
-                    g[2] = np.dot(T - p0, vec) / vv
-                rec.update(kind=_lib.PAINT_LINEAR, g=g)
+                geom[0:2], geom[2:4], geom[4] = p0, vec, float(np.dot(vec, vec))
+                rec.update(kind=_lib.PAINT_LINEAR)
             elif paint.fcenter is None and paint.fradius is None:
-                c, r = np.asarray(paint.center, dtype=np.float64), float(paint.radius)
-                with np.errstate(divide="ignore", invalid="ignore"):
-                    m1[0:2], m1[3:5] = A[0] / r, A[1] / r
-                    m1[2], m1[5] = (T - c) / r
-                rec.update(kind=_lib.PAINT_RADIAL, m1=m1)
+                geom[0:2], geom[2] = np.asarray(paint.center, dtype=np.float64), float(paint.radius)
+                rec.update(kind=_lib.PAINT_RADIAL)
             else:
                 c, r = np.asarray(paint.center, dtype=np.float64), float(paint.radius)
                 f = c if paint.fcenter is None else np.asarray(paint.fcenter, dtype=np.float64)
                 fr = float(paint.fradius or 0)
                 cd, rd = c - f, r - fr
                 a = float((cd ** 2).sum() - rd ** 2)
-                m1[0:2], m1[3:5] = A[0], A[1]
-                m1[2], m1[5] = T - f
+                geom[0:2] = f
                 with np.errstate(divide="ignore", invalid="ignore"):
                     g[:] = (cd[0], cd[1], fr * rd, a, fr * fr, np.float64(fr) / np.float64(fr - r), float(fr != r),
                             np.float64(1.0) / np.float64(a))
-                rec.update(kind=_lib.PAINT_RADIAL_FOCAL, m1=m1, g=g, flag=self.n_focal)
+                rec.update(kind=_lib.PAINT_RADIAL_FOCAL, flag=self.n_focal)
                 self.n_focal += 1
+            # pixel centre -> gradient space: transform.invert, then the inverse gradientTransform
+            # (svgrasterize.py:1022-1031, :1558, :1602); composed here so that the device evaluates one
+            # affine expression per pixel
+            to_user = transform.invert.m
+            if paint.bbox_units:
+                # hull.bbox_transform(transform) (:1023-1026) needs the flattened leaf: the map is completed on the
+                # device between flattening and compositing (svgr_bbox_job), no round trip here
+                rec.update(g=g, m1=m1)
+                pidx = self._paint_record(**rec)
+                grad_inv = np.zeros(6) if paint.transform is None else m6(paint.transform.invert)
+                self.bbox_jobs.append((pidx, pid, int(paint.transform is not None), to_user[:2, :].reshape(6).copy(),
+                                       grad_inv, geom))
+                node = self._node(_lib.N_LEAF, pid, pidx, int(lin), -1)
+                self.cloud[node] = [(node, pid)]
+                return node
+            if paint.transform is not None:
+                to_user = paint.transform.invert.m @ to_user
+            A, T = to_user[:2, :2], to_user[:2, 2]
+            with np.errstate(divide="ignore", invalid="ignore"):
+                if kind == "linear":
+                    vec, vv = geom[2:4], geom[4]
+                    g[0:2] = (vec @ A) / vv
+                    g[2] = np.dot(T - geom[0:2], vec) / vv
+                elif rec["kind"] == _lib.PAINT_RADIAL:
+                    r = geom[2]
+                    m1[0:2], m1[3:5] = A[0] / r, A[1] / r
+                    m1[2], m1[5] = (T - geom[0:2]) / r
+                else:
+                    m1[0:2], m1[3:5] = A[0], A[1]
+                    m1[2], m1[5] = T - geom[0:2]
+            rec.update(g=g, m1=m1)
             pidx = self._paint_record(**rec)
             node = self._node(_lib.N_LEAF, pid, pidx, int(lin), -1)
         elif kind == "pattern":
@@ -796,6 +815,9 @@ class Encoder:
             p.matrices = np.stack(self.matrices).astype(np.float32)
         if self.offset_tr:
             p.offset_tr = np.stack(self.offset_tr).astype(np.float64)
+        p.bbox_jobs = np.zeros(len(self.bbox_jobs), _lib.BBOX_JOB_DT)
+        for i, (paint, path, has_tr, inv, grad_inv, geom) in enumerate(self.bbox_jobs):
+            p.bbox_jobs[i] = (paint, path, has_tr, 0, inv, grad_inv, geom)
         p.externals = list(self.externals)
         p.canvas_bytes = self.canvas_bytes
         p.canvases = list(self.canvases)

@@ -140,6 +140,7 @@ class NativeProgram:
             "stroke_seg_job": (p.stroke_seg_job, p.n_stroke_seg, np.int32, None),
             "paints": (p.paints, p.n_paint, _lib.PAINT_DT, None), "stops": (p.stops, p.n_stop, _lib.STOP_DT, None),
             "nodes": (p.nodes, p.n_node, _lib.NODE_DT, None), "children": (p.children, p.n_child, np.int32, None),
+            "bbox_jobs": (p.bbox_jobs, p.n_bbox_job, _lib.BBOX_JOB_DT, None),
         }
         if name in views:
             return self._view(*views[name])

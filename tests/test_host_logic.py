@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), name
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
-    assert L.svgr_version() == 200
+    assert L.svgr_version() == 210
 
 
 def test_arc_expansion_is_bit_exact():
