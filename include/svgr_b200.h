@@ -304,12 +304,22 @@ typedef struct svgr_flat_node {
     int32_t tag; /* RENDER_* (svgrasterize.py:576-583): 0 fill (a path, b paint or -1, c rule 0 nonzero / 1 evenodd),
                     1 stroke (a path, b paint, c cap 0 butt 1 round 2 square, d join 0 miter 1 round 2 bevel 3 other,
                     f[0] width), 2 group, 3 opacity (f[0]), 4 clip / 5 mask (children target, other; a = bbox units),
-                    6 transform (a = index into tr), 7 filter (not covered) */
+                    6 transform (a = index into tr), 7 filter (child = the target, a = first primitive in fes,
+                    b = number of primitives) */
     int32_t a, b, c, d;
     int32_t child_off, child_cnt;
     int32_t pad;
     double f[2];
 } svgr_flat_node;
+/* one filter primitive (svgrasterize.py:1733-1799, Filter.__call__ :1801-1831) */
+typedef struct svgr_flat_fe {
+    int32_t tag;    /* FE_*: 0 blend, 1 colour matrix, 3 composite, 8 gaussian blur, 9 merge, 10 morphology, 11 offset */
+    int32_t n_in;   /* inputs: slots of the filter's stack (0 SourceAlpha, 1 SourceGraphic, i + 2 primitive i) */
+    int32_t in_off; /* into fe_inputs */
+    int32_t flag;   /* composite: 1 arithmetic (a = k1..k4), 0 a[0] = mode, -1 invalid mode | colour matrix: 1 a = the
+                       4 x 5 matrix, 0 not a 4 x 5 array (the primitive is skipped) | morphology: 1 max, 0 min, -1 other */
+    double a[20];   /* offset: dx dy | blur: std_x std_y (std_y = std_x when None) | morphology: rx ry */
+} svgr_flat_fe;
 typedef struct svgr_flat_scene {
     int32_t root;          /* node index */
     int32_t width, height; /* canvas size: main() renders with viewport [0, 0, height, width] (:3857-3861) */
@@ -335,6 +345,10 @@ typedef struct svgr_flat {
     const int32_t *children;
     int32_t n_scene;
     const svgr_flat_scene *scenes;
+    int32_t n_fe;
+    const svgr_flat_fe *fes;
+    int32_t n_fe_input;
+    const int32_t *fe_inputs;
 } svgr_flat;
 typedef struct svgr_encoded svgr_encoded;
 /* Encodes every scene of `in` (in order, one canvas each) into one program owned by the returned handle (also

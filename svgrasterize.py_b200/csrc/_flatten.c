@@ -9,7 +9,7 @@
  *   flatten(jobs) -> (dict of bytes, list of job indices left to the Python encoder)
  *     jobs: sequence of (scene, (width, height), linear_rgb)
  *
- * A scene that uses something encode_flat.cpp does not cover (objectBoundingBox units, pattern paints, filters,
+ * A scene that uses something encode_flat.cpp does not cover (objectBoundingBox clip / mask units, pattern paints,
  * unknown paints) is skipped and its index returned; everything it had appended is rolled back.
  */
 #define PY_SSIZE_T_CLEAN
@@ -48,9 +48,9 @@ static int buf_put(Buf *b, const void *src, size_t n)
 }
 
 typedef struct {
-    Buf seg_tag, seg_data, sub_off, path_off, tr, paints, stops, nodes, children, scenes;
+    Buf seg_tag, seg_data, sub_off, path_off, tr, paints, stops, nodes, children, scenes, fes, fe_inputs;
     int64_t n_seg;
-    int32_t n_sub, n_path, n_tr, n_paint, n_stop, n_node, n_child, n_scene;
+    int32_t n_sub, n_path, n_tr, n_paint, n_stop, n_node, n_child, n_scene, n_fe, n_fe_input;
     PyObject *path_ids, *paint_ids; /* id(object) -> index, per scene */
     PyObject *asarray;              /* numpy.ascontiguousarray, for inputs that are not float64 buffers */
     PyObject *float64;
@@ -475,6 +475,136 @@ static long put_node(Ctx *c, const svgr_flat_node *n, const int32_t *kids)
 }
 
 /* -> node index, -2 on error (Python exception set), -3 the scene is left to the Python encoder */
+/* Filter.filters = [(tag, attrs, input slots), ...] (svgrasterize.py:1750-1799) -> svgr_flat_fe records.
+ * Returns 0, -2 on a Python error. */
+static long flatten_filter(Ctx *c, PyObject *flt)
+{
+    PyObject *list = PyObject_GetAttrString(flt, "filters");
+    if (!list)
+        return -2;
+    PyObject *seq = PySequence_Fast(list, "Filter.filters must be a sequence");
+    Py_DECREF(list);
+    if (!seq)
+        return -2;
+    long rc = 0;
+    for (Py_ssize_t i = 0; i < PySequence_Fast_GET_SIZE(seq) && rc == 0; i++) {
+        PyObject *prim = PySequence_Fast(PySequence_Fast_GET_ITEM(seq, i), "a filter primitive must be (tag, attrs, inputs)");
+        if (!prim) {
+            rc = -2;
+            break;
+        }
+        PyObject *attrs = NULL, *inputs = NULL;
+        svgr_flat_fe fe;
+        memset(&fe, 0, sizeof fe);
+        if (PySequence_Fast_GET_SIZE(prim) != 3) {
+            PyErr_SetString(PyExc_ValueError, "a filter primitive must be (tag, attrs, inputs)");
+            rc = -2;
+        }
+        if (rc == 0) {
+            const long tag = PyLong_AsLong(PySequence_Fast_GET_ITEM(prim, 0));
+            if (tag == -1 && PyErr_Occurred())
+                rc = -2;
+            fe.tag = (int32_t)tag;
+        }
+        if (rc == 0) {
+            attrs = PySequence_Fast(PySequence_Fast_GET_ITEM(prim, 1), "filter attributes must be a sequence");
+            inputs = PySequence_Fast(PySequence_Fast_GET_ITEM(prim, 2), "filter inputs must be a sequence");
+            if (!attrs || !inputs)
+                rc = -2;
+        }
+        if (rc == 0) {
+            fe.in_off = c->n_fe_input, fe.n_in = (int32_t)PySequence_Fast_GET_SIZE(inputs);
+            for (Py_ssize_t k = 0; k < PySequence_Fast_GET_SIZE(inputs) && rc == 0; k++) {
+                const long slot = PyLong_AsLong(PySequence_Fast_GET_ITEM(inputs, k));
+                const int32_t s32 = (int32_t)slot;
+                if ((slot == -1 && PyErr_Occurred()) || buf_put(&c->fe_inputs, &s32, 4))
+                    rc = -2;
+                else
+                    c->n_fe_input++;
+            }
+        }
+        if (rc == 0) {
+            const Py_ssize_t nat = PySequence_Fast_GET_SIZE(attrs);
+            PyObject **at = PySequence_Fast_ITEMS(attrs);
+            switch (fe.tag) {
+            case 11: /* offset: (dx, dy) */
+            case 10: /* morphology: (rx, ry, method) */
+                if (nat < 2) {
+                    PyErr_SetString(PyExc_ValueError, "filter primitive: missing attributes");
+                    rc = -2;
+                    break;
+                }
+                fe.a[0] = PyFloat_AsDouble(at[0]), fe.a[1] = PyFloat_AsDouble(at[1]);
+                if (PyErr_Occurred())
+                    rc = -2;
+                if (fe.tag == 10)
+                    fe.flag = nat > 2 && str_is(at[2], "max") ? 1 : nat > 2 && str_is(at[2], "min") ? 0 : -1;
+                break;
+            case 8: /* gaussian blur: (std_x, std_y or None) */
+                if (nat < 2) {
+                    PyErr_SetString(PyExc_ValueError, "filter primitive: missing attributes");
+                    rc = -2;
+                    break;
+                }
+                fe.a[0] = PyFloat_AsDouble(at[0]);
+                fe.a[1] = at[1] == Py_None ? fe.a[0] : PyFloat_AsDouble(at[1]);
+                if (PyErr_Occurred())
+                    rc = -2;
+                break;
+            case 0: /* blend: rendered as a plain over-merge, with the reference's warning (:1877) */
+                if (PyErr_WarnEx(PyExc_UserWarning, "feBlend is not properly supported", 1))
+                    rc = -2;
+                break;
+            case 3: { /* composite: (mode,) -- a COMPOSE_* code or the four arithmetic coefficients */
+                PyObject *mode = nat > 0 ? at[0] : Py_None;
+                fe.flag = -1;
+                if (PyTuple_Check(mode) && PyTuple_GET_SIZE(mode) == 4) {
+                    fe.flag = 1;
+                    for (int k = 0; k < 4; k++)
+                        fe.a[k] = PyFloat_AsDouble(PyTuple_GET_ITEM(mode, k));
+                    if (PyErr_Occurred())
+                        rc = -2;
+                } else if (!PyBool_Check(mode) && (PyIndex_Check(mode) || PyFloat_Check(mode))) {
+                    /* `mode in (0, 1, 2, 3, 4)`: ints of any kind, and floats that equal one of them */
+                    const double m = PyFloat_Check(mode) ? PyFloat_AS_DOUBLE(mode) : (double)PyNumber_AsSsize_t(mode, NULL);
+                    if (PyErr_Occurred())
+                        PyErr_Clear();
+                    else if (m == 0.0 || m == 1.0 || m == 2.0 || m == 3.0 || m == 4.0)
+                        fe.flag = 0, fe.a[0] = m;
+                }
+                break;
+            }
+            case 1: { /* colour matrix: (matrix,) */
+                PyObject *m = nat > 0 ? at[0] : Py_None;
+                if (PyArray_Check(m) && PyArray_NDIM((PyArrayObject *)m) == 2 && PyArray_DIM((PyArrayObject *)m, 0) == 4 &&
+                    PyArray_DIM((PyArrayObject *)m, 1) == 5) {
+                    /* np.asarray(matrix, dtype=np.float32): through float64 is the same value for every real dtype */
+                    if (read_doubles(c, m, fe.a, 20))
+                        rc = -2;
+                    fe.flag = 1;
+                } else if (PyErr_WarnFormat(PyExc_UserWarning, 1, "invalid color matrix: %S", m)) {
+                    rc = -2;
+                }
+                break;
+            }
+            default: /* merge (9) has no attributes; unknown tags are the walk's ValueError */
+                break;
+            }
+        }
+        if (rc == 0) {
+            if (buf_put(&c->fes, &fe, sizeof fe))
+                rc = -2;
+            else
+                c->n_fe++;
+        }
+        Py_XDECREF(attrs);
+        Py_XDECREF(inputs);
+        Py_DECREF(prim);
+    }
+    Py_DECREF(seq);
+    return rc;
+}
+
 static long flatten_node(Ctx *c, PyObject *scene, int depth)
 {
     if (depth > 2000) {
@@ -586,8 +716,18 @@ static long flatten_node(Ctx *c, PyObject *scene, int depth)
                 rc = put_node(c, &n, kids);
             }
         }
-    } else if (tag == 7) { /* filter */
-        rc = -3;
+    } else if (tag == 7 && na == 2) { /* filter: (scene, Filter) */
+        rc = flatten_node(c, a[0], depth + 1);
+        if (rc >= 0) {
+            kids[0] = (int32_t)rc;
+            const int32_t first = c->n_fe;
+            rc = flatten_filter(c, a[1]);
+            if (rc >= 0) {
+                n.a = first, n.b = c->n_fe - first;
+                n.child_cnt = 1;
+                rc = put_node(c, &n, kids);
+            }
+        }
     } else {
         PyErr_Format(PyExc_ValueError, "unhandled scene type: %ld", tag);
         rc = -2;
@@ -664,9 +804,10 @@ static PyObject *py_flatten(PyObject *self, PyObject *args)
         if (root == -3) {
             c.seg_tag.n = mark.seg_tag.n, c.seg_data.n = mark.seg_data.n, c.sub_off.n = mark.sub_off.n;
             c.path_off.n = mark.path_off.n, c.tr.n = mark.tr.n, c.paints.n = mark.paints.n, c.stops.n = mark.stops.n;
-            c.nodes.n = mark.nodes.n, c.children.n = mark.children.n;
+            c.nodes.n = mark.nodes.n, c.children.n = mark.children.n, c.fes.n = mark.fes.n, c.fe_inputs.n = mark.fe_inputs.n;
             c.n_seg = mark.n_seg, c.n_sub = mark.n_sub, c.n_path = mark.n_path, c.n_tr = mark.n_tr;
             c.n_paint = mark.n_paint, c.n_stop = mark.n_stop, c.n_node = mark.n_node, c.n_child = mark.n_child;
+            c.n_fe = mark.n_fe, c.n_fe_input = mark.n_fe_input;
             PyObject *idx = PyLong_FromSsize_t(j);
             const int rc = idx ? PyList_Append(skipped, idx) : -1;
             Py_XDECREF(idx);
@@ -688,7 +829,7 @@ static PyObject *py_flatten(PyObject *self, PyObject *args)
             Buf *b;
         } items[] = {{"seg_tag", &c.seg_tag}, {"seg_data", &c.seg_data}, {"sub_off", &c.sub_off}, {"path_off", &c.path_off},
                      {"tr", &c.tr}, {"paints", &c.paints}, {"stops", &c.stops}, {"nodes", &c.nodes},
-                     {"children", &c.children}, {"scenes", &c.scenes}};
+                     {"children", &c.children}, {"scenes", &c.scenes}, {"fes", &c.fes}, {"fe_inputs", &c.fe_inputs}};
         int ok = 1;
         for (size_t i = 0; i < sizeof items / sizeof items[0] && ok; i++) {
             PyObject *b = take_bytes(items[i].b);
@@ -705,6 +846,7 @@ static PyObject *py_flatten(PyObject *self, PyObject *args)
 done:
     free(c.seg_tag.p), free(c.seg_data.p), free(c.sub_off.p), free(c.path_off.p), free(c.tr.p);
     free(c.paints.p), free(c.stops.p), free(c.nodes.p), free(c.children.p), free(c.scenes.p);
+    free(c.fes.p), free(c.fe_inputs.p);
     Py_XDECREF(c.path_ids);
     Py_XDECREF(c.paint_ids);
     Py_XDECREF(c.asarray);

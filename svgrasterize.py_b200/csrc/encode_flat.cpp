@@ -69,6 +69,9 @@ struct svgr_encoded {
     std::vector<svgr_node> nodes;
     std::vector<int32_t> children;
     std::vector<svgr_bbox_job> bbox_jobs;
+    std::vector<svgr_kernel> kernels;
+    std::vector<float> weights, matrices;  // matrices: 20 per colour matrix
+    std::vector<double> offset_tr;         // 12 per feOffset: forward 2 x 3, inverse 2 x 3
     std::vector<int64_t> canvases;  // node, byte offset, rows, cols per canvas
     std::vector<int32_t> roots;
     int32_t n_focal = 0;
@@ -316,6 +319,261 @@ struct Encoder {
         return node(SVGR_N_LEAF, pid, paint_record(rec), lin ? 1 : 0, -1);
     }
 
+    // Transform.__call__ on rows of points (svgrasterize.py:531-534): points @ m[:2, :2].T + m[:2, 2]
+    static void apply(const M23 &m, double x, double y, double &ox, double &oy)
+    {
+        ox = fma(y, m.m[1], x * m.m[0]) + m.m[2];
+        oy = fma(y, m.m[4], x * m.m[3]) + m.m[5];
+    }
+
+    // numpy's pairwise summation of a contiguous run (np.add.reduce): blocks of 8 accumulators below 128 elements
+    static double pairwise_sum(const double *a, size_t n, size_t stride)
+    {
+        if (n < 8) {
+            double r = 0.0;  // numpy starts from the first element; adding it to -0.0 / 0.0 is the same value here
+            for (size_t i = 0; i < n; i++)
+                r = i == 0 ? a[0] : r + a[i * stride];
+            return r;
+        }
+        if (n <= 128) {
+            double r[8];
+            for (int k = 0; k < 8; k++)
+                r[k] = a[k * stride];
+            size_t i = 8;
+            for (; i + 8 <= n; i += 8)
+                for (int k = 0; k < 8; k++)
+                    r[k] += a[(i + k) * stride];
+            double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+            for (; i < n; i++)
+                res += a[i * stride];
+            return res;
+        }
+        size_t n2 = n / 2;
+        n2 -= n2 % 8;
+        return pairwise_sum(a, n2, stride) + pairwise_sum(a + n2 * stride, n - n2, stride);
+    }
+
+    // blur_kernel (svgrasterize.py:1903-1944; encode.py blur_kernel): the Gaussian of feGaussianBlur under `t`.
+    // false: the blur is a no-op (< half a pixel both ways).  rows x cols weights, row-major.
+    bool blur_kernel(const M23 &t, double sx, double sy, int &rows, int &cols, std::vector<double> &w)
+    {
+        double ox, oy;
+        apply(t, 0.0, 0.0, ox, oy);
+        // basis = transform(np.eye(2)) - origin; scale = np.linalg.norm(basis, axis=1)
+        double b00, b01, b10, b11;
+        apply(t, 1.0, 0.0, b00, b01);
+        apply(t, 0.0, 1.0, b10, b11);
+        b00 -= ox, b01 -= oy, b10 -= ox, b11 -= oy;
+        const double scale_x = sqrt(b00 * b00 + b01 * b01), scale_y = sqrt(b10 * b10 + b11 * b11);
+        if (scale_x * sx < 0.5 && scale_y * sy < 0.5)
+            return false;
+        if (scale_x * sx < 0.5)
+            sx = 0.5 / scale_x;
+        else if (scale_y * sy < 0.5)
+            sy = 0.5 / scale_y;
+        const double reach = 2.5;
+        const double bx[4] = {-reach * sx, -reach * sx, reach * sx, reach * sx};
+        const double by[4] = {-reach * sy, reach * sy, reach * sy, -reach * sy};
+        double lo0 = 0, lo1 = 0, hi0 = 0, hi1 = 0;
+        for (int k = 0; k < 4; k++) {
+            double px, py;
+            apply(t, bx[k], by[k], px, py);
+            px -= ox, py -= oy;
+            if (k == 0 || px < lo0) lo0 = px;
+            if (k == 0 || px > hi0) hi0 = px;
+            if (k == 0 || py < lo1) lo1 = py;
+            if (k == 0 || py > hi1) hi1 = py;
+        }
+        // .astype(int): truncation toward zero
+        const long long l0 = (long long)lo0, l1 = (long long)lo1, h0 = (long long)hi0, h1 = (long long)hi1;
+        long long kw = h0 - l0, kh = h1 - l1;
+        kw += 1 - (kw & 1), kh += 1 - (kh & 1);
+        if (kw <= 0 || kh <= 0 || kw > 1 << 15 || kh > 1 << 15 || kw * kh > (1ll << 26)) {
+            fail(SVGR_E_UNSUPPORTED, "blur kernel too large");
+            return false;
+        }
+        M23 inv;
+        if (!invert(t, inv)) {
+            fail(SVGR_E_INVALID, "Singular matrix");
+            return false;
+        }
+        double zx, zy;
+        apply(inv, 0.0, 0.0, zx, zy);
+        const double cx = -(double)kw / 2 + 0.5, cy = -(double)kh / 2 + 0.5;
+        const double dx = 2 * (sx * sx), dy = 2 * (sy * sy);
+        rows = (int)kw, cols = (int)kh;
+        w.resize((size_t)rows * cols);
+        for (int r = 0; r < rows; r++)
+            for (int c = 0; c < cols; c++) {
+                double px, py;
+                apply(inv, (double)r + cx, (double)c + cy, px, py);
+                px -= zx, py -= zy;
+                w[(size_t)r * cols + c] = exp(-(px * px) / dx) * exp(-(py * py) / dy);
+            }
+        const double total = pairwise_sum(w.data(), w.size(), 1);
+        for (double &v : w)
+            v = v / total;
+        return true;
+    }
+
+    // encode.py _compose: Layer.compose as a node (mode code, or 5 + the arithmetic coefficients)
+    int compose(const int32_t *kids, int n_kids, int mode, const double *k4)
+    {
+        if (k4)
+            return node(SVGR_N_COMPOSE, 5, 0, 0, 0, kids, n_kids, 1, k4[0], k4[1], k4[2], k4[3]);
+        return node(SVGR_N_COMPOSE, mode, 0, 0, 0, kids, n_kids, 1);
+    }
+
+    // Filter.__call__ (svgrasterize.py:1801-1831; encode.py _filter) lowered to nodes
+    int filter(int first, int count, const M23 &t, int source)
+    {
+        std::vector<int> stack;
+        {
+            const int32_t c[1] = {source};
+            stack.push_back(node(SVGR_N_SRC_ALPHA, 0, 0, 0, 0, c, 1));
+            stack.push_back(node(SVGR_N_CONVERT, 0, 1, 0, 0, c, 1));
+        }
+        for (int i = first; i < first + count; i++) {
+            const svgr_flat_fe &fe = in.fes[i];
+            if (fe.n_in < 0 || fe.in_off < 0 || (int64_t)fe.in_off + fe.n_in > in.n_fe_input) {
+                fail(SVGR_E_INVALID, "flat scene: filter inputs outside the table");
+                return -1;
+            }
+            std::vector<int32_t> args;
+            for (int k = 0; k < fe.n_in; k++) {
+                const int slot = in.fe_inputs[fe.in_off + k];
+                if (slot < 0 || slot >= (int)stack.size()) {
+                    fail(SVGR_E_INVALID, "list index out of range");  // the reference's IndexError on stack[i]
+                    return -1;
+                }
+                args.push_back(stack[(size_t)slot]);
+            }
+            auto need = [&](int n) {
+                if ((int)args.size() < n) {
+                    fail(SVGR_E_INVALID, "filter primitive: missing input");
+                    return false;
+                }
+                return true;
+            };
+            int outn = -1;
+            switch (fe.tag) {
+            case 11: {  // feOffset
+                if (!need(1))
+                    return -1;
+                M23 inv;
+                if (!invert(t, inv)) {
+                    fail(SVGR_E_INVALID, "Singular matrix");
+                    return -1;
+                }
+                out.offset_tr.insert(out.offset_tr.end(), t.m, t.m + 6);
+                out.offset_tr.insert(out.offset_tr.end(), inv.m, inv.m + 6);
+                outn = node(SVGR_N_OFFSET, (int)(out.offset_tr.size() / 12) - 1, 0, 0, 0, args.data(), 1, 0, fe.a[0], fe.a[1]);
+                break;
+            }
+            case 9:  // feMerge
+                outn = compose(args.data(), (int)args.size(), 0, nullptr);
+                break;
+            case 0: {  // feBlend: a plain over-merge (:1877)
+                if (!need(2))
+                    return -1;
+                const int32_t c[2] = {args[1], args[0]};
+                outn = compose(c, 2, 0, nullptr);
+                break;
+            }
+            case 3: {  // feComposite
+                if (!need(2))
+                    return -1;
+                if (fe.flag < 0) {
+                    fail(SVGR_E_INVALID, "invalid compose mode");
+                    return -1;
+                }
+                const int32_t c[2] = {args[1], args[0]};
+                outn = fe.flag == 1 ? compose(c, 2, 5, fe.a) : compose(c, 2, (int)fe.a[0], nullptr);
+                break;
+            }
+            case 8: {  // feGaussianBlur
+                if (!need(1))
+                    return -1;
+                int rows = 0, cols = 0;
+                std::vector<double> w;
+                if (!blur_kernel(t, fe.a[0], fe.a[1], rows, cols, w)) {
+                    if (out.err_code != SVGR_OK)
+                        return -1;
+                    outn = args[0];
+                    break;
+                }
+                // encode.py _blur: separable when the outer product of the marginals reproduces the kernel
+                std::vector<double> a((size_t)rows), b((size_t)cols);
+                for (int r = 0; r < rows; r++)
+                    a[(size_t)r] = pairwise_sum(w.data() + (size_t)r * cols, (size_t)cols, 1);
+                for (int c = 0; c < cols; c++) {
+                    // numpy reduces axis 0 of a C-contiguous array row by row: a plain running sum per column
+                    double acc = w[(size_t)c];
+                    for (int r = 1; r < rows; r++)
+                        acc += w[(size_t)r * cols + c];
+                    b[(size_t)c] = acc;
+                }
+                double worst = 0.0;
+                for (int r = 0; r < rows; r++)
+                    for (int c = 0; c < cols; c++)
+                        worst = fmax(worst, fabs(a[(size_t)r] * b[(size_t)c] - w[(size_t)r * cols + c]));
+                svgr_kernel k;
+                k.rows = rows, k.cols = cols, k.separable = worst < 1e-12 ? 1 : 0, k.weight_off = (int32_t)out.weights.size();
+                if (k.separable) {
+                    for (double v : a)
+                        out.weights.push_back((float)v);
+                    for (double v : b)
+                        out.weights.push_back((float)v);
+                } else {
+                    for (double v : w)
+                        out.weights.push_back((float)v);
+                }
+                out.kernels.push_back(k);
+                outn = node(SVGR_N_BLUR, (int)out.kernels.size() - 1, 0, 0, 0, args.data(), 1);
+                break;
+            }
+            case 1: {  // feColorMatrix
+                if (!need(1))
+                    return -1;
+                if (fe.flag != 1) {
+                    outn = args[0];  // "invalid color matrix" (:1857): the primitive is skipped
+                    break;
+                }
+                for (int k = 0; k < 20; k++)
+                    out.matrices.push_back((float)fe.a[k]);
+                outn = node(SVGR_N_CMATRIX, (int)(out.matrices.size() / 20) - 1, 0, 0, 0, args.data(), 1);
+                break;
+            }
+            case 10: {  // feMorphology
+                if (!need(1))
+                    return -1;
+                // u = transform([[rx, 0], [0, ry]]) - transform(zeros): the window is twice the length of its rows
+                double zx, zy, u00, u01, u10, u11;
+                apply(t, 0.0, 0.0, zx, zy);
+                apply(t, fe.a[0], 0.0, u00, u01);
+                apply(t, 0.0, fe.a[1], u10, u11);
+                u00 -= zx, u01 -= zy, u10 -= zx, u11 -= zy;
+                const int k0 = (int)(sqrt(fma(u01, u01, u00 * u00)) * 2), k1 = (int)(sqrt(fma(u11, u11, u10 * u10)) * 2);
+                if (k0 < 1 || k1 < 1) {
+                    outn = args[0];
+                } else {
+                    if (fe.flag < 0) {
+                        fail(SVGR_E_INVALID, "invalid poll method");
+                        return -1;
+                    }
+                    outn = node(SVGR_N_MORPH, k0, k1, fe.flag, 0, args.data(), 1);
+                }
+                break;
+            }
+            default:
+                fail(SVGR_E_INVALID, "unsupported filter type");
+                return -1;
+            }
+            stack.push_back(outn);
+        }
+        return stack.back();
+    }
+
     // Scene.render (svgrasterize.py:649-752; encode.py Encoder.encode)
     int encode(int ni, const M23 &t, bool mask_only, const int32_t *viewport, bool linear_rgb, int depth = 0)
     {
@@ -415,9 +673,14 @@ struct Encoder {
             const int32_t c[2] = {stencil, tn};
             return node(SVGR_N_IN, 0, 0, 0, 0, c, 2, lin);
         }
-        case R_FILTER:
-            fail(SVGR_E_UNSUPPORTED, "flat scene: filters need the Python encoder");
-            return -1;
+        case R_FILTER: {
+            if (n.child_cnt != 1 || n.a < 0 || n.b < 0 || (int64_t)n.a + n.b > in.n_fe)
+                break;
+            const int tn = encode(kids[0], t, mask_only, viewport, linear_rgb, depth + 1);
+            if (tn < 0 || is_empty(tn))
+                return tn;
+            return filter(n.a, n.b, t, tn);
+        }
         default:
             fail(SVGR_E_INVALID, "unhandled scene type");
             return -1;
@@ -494,6 +757,10 @@ int svgr_encode_flat(const svgr_flat *in, svgr_encoded **out_handle)
     p.n_child = (int32_t)e->children.size(), p.children = e->children.data();
     p.canvas_bytes = e->canvas_bytes;
     p.n_bbox_job = (int32_t)e->bbox_jobs.size(), p.bbox_jobs = e->bbox_jobs.data();
+    p.n_kernel = (int32_t)e->kernels.size(), p.kernels = e->kernels.data();
+    p.n_weight = (int32_t)e->weights.size(), p.weights = e->weights.data();
+    p.n_matrix = (int32_t)(e->matrices.size() / 20), p.matrices = e->matrices.data();
+    p.n_offset_tr = (int32_t)(e->offset_tr.size() / 12), p.offset_tr = e->offset_tr.data();
     return SVGR_OK;
 }
 

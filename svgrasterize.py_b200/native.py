@@ -24,6 +24,7 @@ FLAT_PAINT_DT = np.dtype([("kind", "<i4"), ("spread", "<i4"), ("bbox_units", "<i
 FLAT_STOP_DT = np.dtype([("offset", "<f8"), ("color", "<f8", 4)], align=True)
 FLAT_NODE_DT = np.dtype([("tag", "<i4"), ("a", "<i4"), ("b", "<i4"), ("c", "<i4"), ("d", "<i4"), ("child_off", "<i4"),
                          ("child_cnt", "<i4"), ("pad", "<i4"), ("f", "<f8", 2)], align=True)
+FLAT_FE_DT = np.dtype([("tag", "<i4"), ("n_in", "<i4"), ("in_off", "<i4"), ("flag", "<i4"), ("a", "<f8", 20)], align=True)
 FLAT_SCENE_DT = np.dtype([("root", "<i4"), ("width", "<i4"), ("height", "<i4"), ("linear_rgb", "<i4")], align=True)
 
 
@@ -32,7 +33,8 @@ class Flat(C.Structure):
                 ("n_sub", C.c_int32), ("sub_off", C.c_void_p), ("n_path", C.c_int32), ("path_off", C.c_void_p),
                 ("n_tr", C.c_int32), ("tr", C.c_void_p), ("n_paint", C.c_int32), ("paints", C.c_void_p),
                 ("n_stop", C.c_int32), ("stops", C.c_void_p), ("n_node", C.c_int32), ("nodes", C.c_void_p),
-                ("n_child", C.c_int32), ("children", C.c_void_p), ("n_scene", C.c_int32), ("scenes", C.c_void_p)]
+                ("n_child", C.c_int32), ("children", C.c_void_p), ("n_scene", C.c_int32), ("scenes", C.c_void_p),
+                ("n_fe", C.c_int32), ("fes", C.c_void_p), ("n_fe_input", C.c_int32), ("fe_inputs", C.c_void_p)]
 
 
 _flatten_mod = None
@@ -61,6 +63,7 @@ def flatten(jobs):
         "tr": np.frombuffer(raw["tr"], np.float64).reshape(-1, 6), "paints": np.frombuffer(raw["paints"], FLAT_PAINT_DT),
         "stops": np.frombuffer(raw["stops"], FLAT_STOP_DT), "nodes": np.frombuffer(raw["nodes"], FLAT_NODE_DT),
         "children": np.frombuffer(raw["children"], np.int32), "scenes": np.frombuffer(raw["scenes"], FLAT_SCENE_DT),
+        "fes": np.frombuffer(raw["fes"], FLAT_FE_DT), "fe_inputs": np.frombuffer(raw["fe_inputs"], np.int32),
     }
     return arr, list(skipped)
 
@@ -76,6 +79,8 @@ def _flat_struct(arr):
     f.n_node, f.nodes = len(arr["nodes"]), _lib.ptr(arr["nodes"])
     f.n_child, f.children = len(arr["children"]), _lib.ptr(arr["children"])
     f.n_scene, f.scenes = len(arr["scenes"]), _lib.ptr(arr["scenes"])
+    f.n_fe, f.fes = len(arr["fes"]), _lib.ptr(arr["fes"])
+    f.n_fe_input, f.fe_inputs = len(arr["fe_inputs"]), _lib.ptr(arr["fe_inputs"])
     return f
 
 
@@ -141,17 +146,12 @@ class NativeProgram:
             "paints": (p.paints, p.n_paint, _lib.PAINT_DT, None), "stops": (p.stops, p.n_stop, _lib.STOP_DT, None),
             "nodes": (p.nodes, p.n_node, _lib.NODE_DT, None), "children": (p.children, p.n_child, np.int32, None),
             "bbox_jobs": (p.bbox_jobs, p.n_bbox_job, _lib.BBOX_JOB_DT, None),
+            "kernels": (p.kernels, p.n_kernel, _lib.KERNEL_DT, None), "weights": (p.weights, p.n_weight, np.float32, None),
+            "matrices": (p.matrices, p.n_matrix, np.float32, (20,)),
+            "offset_tr": (p.offset_tr, p.n_offset_tr, np.float64, (12,)),
         }
         if name in views:
             return self._view(*views[name])
-        if name == "kernels":
-            return np.zeros(0, _lib.KERNEL_DT)
-        if name == "weights":
-            return np.zeros(0, np.float32)
-        if name == "matrices":
-            return np.zeros((0, 20), np.float32)
-        if name == "offset_tr":
-            return np.zeros((0, 12), np.float64)
         raise AttributeError(name)
 
     def h2d_bytes(self) -> int:

@@ -34,7 +34,12 @@ def test_native_batch_renders_like_the_python_encoded_batch(eng):
 
 
 @pytest.mark.parametrize("name", ["demo_material_w1024", "demo_prompt", "icon_tiger", "icon_rust", "synth_icon_4",
-                                  "feat_radial_focal_outside", "feat_stroke_caps_joins"])
+                                  "feat_radial_focal_outside", "feat_stroke_caps_joins",
+                                  # filters (blur incl. rotated, offset, merge, composite, colour matrix, morphology)
+                                  # and objectBoundingBox gradients through the native walk
+                                  "demo_icons_w512", "icon_inkscape", "icon_office", "feat_filter_blur_rotated",
+                                  "feat_filter_drop_shadow", "feat_filter_arithmetic", "feat_filter_erode_matrix",
+                                  "synth_filter_stack_192", "feat_linear_bbox_reflect", "feat_radial_focal_bbox"])
 def test_native_encoder_against_the_reference_bytes(eng, name):
     from svgrasterize_b200 import native
 

@@ -5,6 +5,8 @@ import os
 import re
 import socket
 
+import warnings
+
 import numpy as np
 import pytest
 
@@ -299,7 +301,15 @@ def _programs_equal(a, b, paint_tol=0.0):
     for name in encode.Program.ARRAYS:
         x, y = np.asarray(getattr(a, name)), np.asarray(getattr(b, name))
         assert x.shape == y.shape, name
-        if name == "paints" and paint_tol > 0:
+        if name in ("weights", "offset_tr") and paint_tol > 0:
+            assert np.allclose(x, y, rtol=2e-7 if name == "weights" else paint_tol, atol=1e-300), name
+        elif name == "bbox_jobs" and paint_tol > 0:
+            for f in x.dtype.names:
+                if f == "inv":
+                    assert np.allclose(x[f], y[f], rtol=paint_tol, atol=1e-300), f
+                else:
+                    assert x[f].tobytes() == y[f].tobytes(), f
+        elif name == "paints" and paint_tol > 0:
             for f in x.dtype.names:
                 if f in ("m1", "g"):
                     scale = np.maximum(np.abs(y[f]), 1e-300)
@@ -330,9 +340,10 @@ def test_native_encoder_reproduces_the_python_encoder_on_icons():
 
 @pytest.mark.parametrize("name", golden_names())
 def test_native_encoder_on_golden_scenes(name):
-    """Every golden scene: covered by the native walk -> the same program as the Python encoder (paint coefficients
-    to 1e-13 where a rotation makes the two inverses differ in the last bit); not covered (filters, patterns,
-    objectBoundingBox units) -> the flattener says so and leaves nothing of the scene behind."""
+    """Every golden scene: covered by the native walk (filters and objectBoundingBox gradients included) -> the same
+    program as the Python encoder (paint coefficients and the inverse matrices of feOffset / bbox jobs to 1e-13 where
+    a rotation makes the two inverses differ in the last bit, blur weights to one float32 ulp); not covered (patterns,
+    objectBoundingBox clip / mask units) -> the flattener says so and leaves nothing of the scene behind."""
     from svgrasterize_b200 import encode, native
 
     scene, size, lin, _z = load_golden(name)
@@ -341,16 +352,20 @@ def test_native_encoder_on_golden_scenes(name):
         assert skipped == [0] and len(arr["nodes"]) == 0 and len(arr["seg_tag"]) == 0 and len(arr["scenes"]) == 0
         return
     prog = native.encode_flat(arr)
-    ref = encode.encode_scene(scene, size, lin)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")  # feBlend's "not properly supported"
+        ref = encode.encode_scene(scene, size, lin)
     _programs_equal(prog, ref, paint_tol=1e-13)
     prog.close()
 
 
 def test_native_encoder_splices_python_encoded_scenes():
-    """A batch in which one scene needs the Python encoder (a filter): the result is the concatenation in order."""
+    """A batch in which one scene needs the Python encoder (a pattern paint): the result is the concatenation in
+    order."""
     from svgrasterize_b200 import encode, native, synth
 
-    jobs = [(synth.icon_scene(1), synth.icon_size(), False), (synth.filter_stack_scene(96), (96, 96), False),
+    pat, pat_size = synth.feature_scenes()["pattern_user_space"]
+    jobs = [(synth.icon_scene(1), synth.icon_size(), False), (pat, pat_size, False),
             (synth.icon_scene(2), synth.icon_size(), True), (synth.icon_scene(3), synth.icon_size(), False)]
     prog = native.encode_batch(jobs)
     assert isinstance(prog, encode.Program)
