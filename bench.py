@@ -293,7 +293,8 @@ def run_from_scene(batches, out_host_np, device, steps, warmup, enc_threads=3, p
 
 
 def time_other_configs(device, peak, with_cpu):
-    """BASELINE.json's single-render configurations at their stated sizes, timed like the icon batch (resident
+    """BASELINE.json's single-render configurations at their stated sizes (c1 and c3 at the sizes the reference's own
+    goldens were recorded at), timed like the icon batch (resident
     program, CUDA events from svgr_render's stage timing, median of 5) with their own SURVEY 8(d) rooflines:
       c2  demo/material-design.svg -w 4096 (scene + reference bytes from tests/golden_big): coverage 4 B per mask
           pixel + 36 B per binned edge; compose 36 B per layer pixel + 20 B per canvas pixel
@@ -351,6 +352,29 @@ def time_other_configs(device, peak, with_cpu):
                      "roofline": {"coverage_kernel": roof(st, "ms_coverage", "coverage_bytes"),
                                   "compose_kernel": roof(st, "ms_compose_busy", "compose_bytes_8d")}}
         del buf
+    # ---- c1 / c3: the reference's own CPU-runnable cases (scene + reference bytes from tests/golden)
+    from svgrasterize_b200 import native
+
+    for key, fixture, what in (("c1", "demo_icons_w512", "demo/icons.svg -w 512: 991 masks, filters, strokes"),
+                               ("c3", "demo_prompt", "demo/prompt.svg: 10 masks")):
+        path = os.path.join(ROOT, "tests", "golden", fixture + ".npz")
+        if not os.path.exists(path):
+            continue
+        z = np.load(path, allow_pickle=False)
+        sc, sz = sceneio.load_scene(z), tuple(float(v) for v in z["size"])
+        t0 = time.perf_counter()
+        prog = native.encode_batch([(sc, sz, bool(z["linear_rgb"]))], engine=eng)
+        t_enc = time.perf_counter() - t0
+        ms, st, buf = timed(prog)
+        got = eng.canvas(prog, buf.cpu().numpy())
+        out[key] = {"workload": what, "canvas": f"{int(sz[0])}x{int(sz[1])}", "ms_per_render": ms,
+                    "mpx_s": sz[0] * sz[1] / ms / 1e3, "masks": int(len(prog.paths)), "edges": int(st["n_edges"]),
+                    "host_encode_s": t_enc, "native_encoder": isinstance(prog, native.NativeProgram),
+                    "max_lsb_vs_reference_bytes": int(np.abs(got.astype(np.int16) - z["canvas_u8"].astype(np.int16)).max()),
+                    "stage_ms": {k[3:]: v for k, v in st.items() if k.startswith("ms_") and v > 0.0005}}
+        del buf
+        if hasattr(prog, "close"):
+            prog.close()
     # ---- c4
     n = 8192
     t0 = time.perf_counter()
