@@ -24,6 +24,7 @@
 // staging slot, the slot goes to the item's private area; when all items are done their offsets are known and
 // they are merged (shifted) behind the block header.
 #include <algorithm>
+#include <atomic>
 
 #include "svgr_kernels.h"
 
@@ -721,11 +722,12 @@ png_pack_kernel(const PngCanvas *__restrict__ canvases, const PngSeg *__restrict
 // ---------------------------------------------------------------------------------------------
 static void png_init_tables()
 {
-    static bool done[64] = {false};
+    // per device; two threads racing here both upload the same constants, which is harmless
+    static std::atomic<bool> done[64];
     int dev = 0;
     cudaGetDevice(&dev);
     dev &= 63;
-    if (done[dev])
+    if (done[dev].load(std::memory_order_acquire))
         return;
     // deflate length codes (RFC 1951, 3.2.5)
     const int base[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
@@ -777,7 +779,7 @@ static void png_init_tables()
     for (int k = 1; k < 32; k++)
         pow[k] = mul(pow[k - 1], pow[k - 1]);
     cudaMemcpyToSymbol(c_crc_pow, pow, sizeof pow);
-    done[dev] = true;
+    done[dev].store(true, std::memory_order_release);
 }
 
 // Upper bound of the bytes of a segment of `rows` x `cols`: the code is built from a sample of the items, so the
