@@ -24,7 +24,9 @@
 
 #include "svgr_kernels.h"
 
+#ifndef COV_THREADS
 #define COV_THREADS 128
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // generic exclusive scan of int32 (count -> offset), three phases

@@ -471,3 +471,51 @@ def test_array_backed_paths_go_through_both_encoders():
     ref = encode.encode_scene(scene, (100, 100), False)
     _programs_equal(nat, ref)
     nat.close()
+
+
+def test_native_encoder_rejects_corrupted_flat_arrays_without_crashing():
+    """svgr_encode_flat is a public C entry point: a flat batch with one corrupted index / count / tag either encodes or
+    comes back as an error -- never a crash (filters, gradients, strokes and clips in the batch)."""
+    import warnings as W
+
+    from svgrasterize_b200 import native, synth
+
+    jobs = [(synth.icon_scene(3), synth.icon_size(), False), (synth.filter_stack_scene(64), (64, 64), False)]
+    sc, size = synth.feature_scenes()["filter_drop_shadow"]
+    jobs.append((sc, size, False))
+    with W.catch_warnings():
+        W.simplefilter("ignore")
+        arr, skipped = native.flatten(jobs)
+    assert not skipped and len(arr["fes"]) >= 4
+    rng = np.random.default_rng(7)
+    names = ["nodes", "fes", "fe_inputs", "children", "paints", "sub_off", "path_off", "scenes"]
+    outcomes = {"ok": 0, "rejected": 0}
+    for it in range(400):
+        a = {k: v.copy() for k, v in arr.items()}
+        v = a[names[it % len(names)]].view(np.int32).reshape(-1)
+        v[rng.integers(0, v.size)] = int(rng.choice([-1, -5, 0, 1, 2, 7, 1000, 2 ** 30, -2 ** 31]))
+        try:
+            native.encode_flat(a).close()
+            outcomes["ok"] += 1
+        except (ValueError, NotImplementedError, MemoryError):
+            outcomes["rejected"] += 1
+    assert outcomes["rejected"] > 50 and outcomes["ok"] > 50
+
+
+def test_path_reader_survives_garbage():
+    """svgr_path_from_svg on random strings over the path-data alphabet: a Path or a ValueError, like Path.from_svg."""
+    import random
+
+    from svgrasterize_b200 import api
+
+    rnd = random.Random(5)
+    alphabet = "MmLlHhVvCcSsQqTtAaZz0123456789.-+eE, \t\n" + "xyz%#"
+    seen = {"ok": 0, "error": 0}
+    for _ in range(3000):
+        s = "".join(rnd.choice(alphabet) for _ in range(rnd.randint(0, 60)))
+        try:
+            api.path_from_svg(s)
+            seen["ok"] += 1
+        except ValueError:
+            seen["error"] += 1
+    assert seen["ok"] > 0 and seen["error"] > 0
