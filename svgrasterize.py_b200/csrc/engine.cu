@@ -161,6 +161,7 @@ struct svgr_ctx {
     cudaStream_t up_stream = nullptr;  // plan tables of the next chunk go up (and its focal flags are computed)
     cudaEvent_t ev_up[16] = {nullptr}; // while the current chunk composes
     cudaEvent_t ev_up_begin = nullptr;
+    cudaEvent_t ev_geo[2] = {nullptr, nullptr};  // fill-segment flatten on up_stream beside the stroke kernels
     cudaEvent_t ev_done[16] = {nullptr};  // a chunk's launches have finished (its list buffers may be rewritten)
     std::string err;
 
@@ -1511,6 +1512,38 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
         svgr_launch_minmax_init(ctx->d_minmax.as<unsigned long long>(), ctx->n_path, s);
         n_kernels += 1;
         mark(0);
+        // Path.mask's literal flatness 0.1 (svgrasterize.py:955/:957) unless the program carries another one
+        // (bezier3_flatten_batch(batch, flatness), :2091-2093: threshold = flatness^2 * 16)
+        const double tol = ctx->flatness > 0.0 ? ctx->flatness : 0.1;
+        const double thr = (tol * tol) * 16;
+        // overflow lists of the multi-pass flatten (deep subdivision trees are re-spread over all warps)
+        svgr_flat_overflow ovf;
+        ovf.cap = 1 << 18;
+        const bool flatten_wanted = stop_after != SVGR_STOP_STROKE;
+        // the fill segments do not depend on the stroke outlines: their flatten runs on the side stream while the
+        // stroke kernels (short, latency-bound) run here; both append to the same edge list with atomics
+        const bool fill_on_side = flatten_wanted && S > 0 && ctx->n_seg > 0;
+        if (flatten_wanted) {
+            for (int q = 0; q < 2; q++) {
+                CK(ctx->d_ovf_cubic[q].ensure((size_t)ovf.cap * 64));
+                CK(ctx->d_ovf_path[q].ensure((size_t)ovf.cap * 4));
+                CK(ctx->d_ovf_depth[q].ensure((size_t)ovf.cap));
+                ovf.cubic[q] = ctx->d_ovf_cubic[q].as<double>(), ovf.path[q] = ctx->d_ovf_path[q].as<uint32_t>();
+                ovf.depth[q] = ctx->d_ovf_depth[q].as<uint8_t>();
+            }
+            CK(ctx->d_ovf_counts.ensure(SVGR_FLAT_PASSES * sizeof(int)));
+            ovf.counts = ctx->d_ovf_counts.as<int>();
+            CK(cudaMemsetAsync(ovf.counts, 0, SVGR_FLAT_PASSES * sizeof(int), s));
+        }
+        if (fill_on_side) {
+            CK(cudaEventRecord(ctx->ev_geo[0], s));
+            CK(cudaStreamWaitEvent(ctx->up_stream, ctx->ev_geo[0], 0));
+            svgr_launch_flatten(ctx->d_seg_tag.as<uint8_t>(), ctx->d_seg_data.as<double>(), ctx->d_seg_path.as<uint32_t>(),
+                                ctx->n_seg, nullptr, ctx->d_paths.as<PathRec>(), thr, ctx->d_edges.as<double>(),
+                                ctx->d_edge_path.as<uint32_t>(), (unsigned long long)ctx->edge_cap, &d_st->n_edges,
+                                ctx->d_minmax.as<unsigned long long>(), SM, &ovf, ctx->up_stream);
+            CK(cudaEventRecord(ctx->ev_geo[1], ctx->up_stream));
+        }
         // ---- stroke outlines
         if (S > 0) {
             if (S > 0x3fffffff)
@@ -1549,28 +1582,14 @@ static int run_pipeline(svgr_ctx *ctx, cudaStream_t s, int stop_after, uint8_t *
         }
         mark(1);
         // ---- flatten + bounds
-        if (stop_after != SVGR_STOP_STROKE) {
-            // Path.mask's literal flatness 0.1 (svgrasterize.py:955/:957) unless the program carries another one
-            // (bezier3_flatten_batch(batch, flatness), :2091-2093: threshold = flatness^2 * 16)
-            const double tol = ctx->flatness > 0.0 ? ctx->flatness : 0.1;
-            const double thr = (tol * tol) * 16;
-            // overflow lists of the multi-pass flatten (deep subdivision trees are re-spread over all warps)
-            svgr_flat_overflow ovf;
-            ovf.cap = 1 << 18;
-            for (int q = 0; q < 2; q++) {
-                CK(ctx->d_ovf_cubic[q].ensure((size_t)ovf.cap * 64));
-                CK(ctx->d_ovf_path[q].ensure((size_t)ovf.cap * 4));
-                CK(ctx->d_ovf_depth[q].ensure((size_t)ovf.cap));
-                ovf.cubic[q] = ctx->d_ovf_cubic[q].as<double>(), ovf.path[q] = ctx->d_ovf_path[q].as<uint32_t>();
-                ovf.depth[q] = ctx->d_ovf_depth[q].as<uint8_t>();
-            }
-            CK(ctx->d_ovf_counts.ensure(SVGR_FLAT_PASSES * sizeof(int)));
-            ovf.counts = ctx->d_ovf_counts.as<int>();
-            CK(cudaMemsetAsync(ovf.counts, 0, SVGR_FLAT_PASSES * sizeof(int), s));
-            svgr_launch_flatten(ctx->d_seg_tag.as<uint8_t>(), ctx->d_seg_data.as<double>(), ctx->d_seg_path.as<uint32_t>(),
-                                ctx->n_seg, nullptr, ctx->d_paths.as<PathRec>(), thr, ctx->d_edges.as<double>(),
-                                ctx->d_edge_path.as<uint32_t>(), (unsigned long long)ctx->edge_cap, &d_st->n_edges,
-                                ctx->d_minmax.as<unsigned long long>(), SM, &ovf, s);
+        if (flatten_wanted) {
+            if (fill_on_side)
+                CK(cudaStreamWaitEvent(s, ctx->ev_geo[1], 0));  // the fill segments' edges are in the list
+            else
+                svgr_launch_flatten(ctx->d_seg_tag.as<uint8_t>(), ctx->d_seg_data.as<double>(), ctx->d_seg_path.as<uint32_t>(),
+                                    ctx->n_seg, nullptr, ctx->d_paths.as<PathRec>(), thr, ctx->d_edges.as<double>(),
+                                    ctx->d_edge_path.as<uint32_t>(), (unsigned long long)ctx->edge_cap, &d_st->n_edges,
+                                    ctx->d_minmax.as<unsigned long long>(), SM, &ovf, s);
             if (S > 0)
                 svgr_launch_flatten(ctx->d_otag.as<uint8_t>(), ctx->d_odata.as<double>(), ctx->d_opath.as<uint32_t>(),
                                     ctx->outline_cap, &d_st->outline_count, ctx->d_paths.as<PathRec>(), thr,
@@ -2138,6 +2157,8 @@ int svgr_create(int device, svgr_ctx **out)
     for (auto &e : ctx->ev_up)
         cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_up_begin, cudaEventDisableTiming);
+    for (auto &e : ctx->ev_geo)
+        cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     cudaEventCreate(&ctx->ev_png[0]), cudaEventCreate(&ctx->ev_png[1]);
     for (auto &e : ctx->ev_done)
         cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
@@ -2191,6 +2212,9 @@ void svgr_destroy(svgr_ctx *ctx)
             cudaEventDestroy(e);
     if (ctx->ev_up_begin)
         cudaEventDestroy(ctx->ev_up_begin);
+    for (auto &e : ctx->ev_geo)
+        if (e)
+            cudaEventDestroy(e);
     for (auto &e : ctx->ev_done)
         if (e)
             cudaEventDestroy(e);
