@@ -395,6 +395,22 @@ struct Planner {
         return out;
     }
 
+    // the region of a node its consumers can observe (demand_range below)
+    struct DBox {
+        bool any = false, inf = false;
+        int r0 = 0, c0 = 0, r1 = 0, c1 = 0;
+        void add_all() { any = inf = true; }
+        void add(int a0, int b0, int a1, int b1)
+        {
+            if (a1 <= a0 || b1 <= b0 || inf)
+                return;
+            if (!any)
+                r0 = a0, c0 = b0, r1 = a1, c1 = b1, any = true;
+            else
+                r0 = std::min(r0, a0), c0 = std::min(c0, b0), r1 = std::max(r1, a1), c1 = std::max(c1, b1);
+        }
+    };
+
     Val materialize(const Val &v)
     {
         if (v.kind == VAL_EMPTY || !v.is_virtual())
@@ -421,7 +437,7 @@ struct Planner {
     // intersect: blend on the intersection of the boxes whatever the mode (canvas_merge_intersect, :382-416);
     // raw: the layers are plain arrays, blended as they are (canvas_compose, :277-298, has no Layer.convert)
     Val compose(const std::vector<Val> &layers, int mode, const float *k, int lin, bool intersect = false,
-                bool raw = false)
+                bool raw = false, const DBox *clip = nullptr)
     {
         if (layers.empty())
             return Val();
@@ -443,6 +459,13 @@ struct Planner {
                 r0 = std::min(r0, l.r0), c0 = std::min(c0, l.c0);
                 r1 = std::max(r1, l.r0 + l.rows), c1 = std::max(c1, l.c0 + l.cols);
             }
+        }
+        if (clip && clip->any && !clip->inf) {
+            // only this much of the result is ever looked at (demand_range)
+            r0 = std::max(r0, clip->r0), c0 = std::max(c0, clip->c0);
+            r1 = std::min(r1, clip->r1), c1 = std::min(c1, clip->c1);
+            if (r1 - r0 <= 0 || c1 - c0 <= 0)
+                return Val();
         }
         SrcList sl(*this);
         std::vector<SrcRec> &ss = sl.v;
@@ -470,7 +493,8 @@ struct Planner {
     };
     std::vector<SBox> shadow;  // empty unless the program is a band render
 
-    SBox shadow_union(const svgr_node &n, const int32_t *ch, bool intersect, bool need_all) const
+    static SBox shadow_union(const std::vector<SBox> &shadow, const svgr_node &n, const int32_t *ch, bool intersect,
+                             bool need_all)
     {
         SBox o;
         int r0 = 0, c0 = 0, r1 = 0, c1 = 0;
@@ -499,7 +523,10 @@ struct Planner {
     }
 
     // the box node i has in the whole-canvas render (mirrors the box logic of node() below)
-    void shadow_node(int i)
+    void shadow_node(int i) { box_node(i, ctx->h_full_boxes, shadow); }
+
+    // the box of node i from the path boxes `pb`, children's boxes taken from `shadow` (= the vector being filled)
+    void box_node(int i, const std::vector<PathBox> &pb, std::vector<SBox> &shadow)
     {
         const svgr_node &n = ctx->h_nodes[i];
         const int32_t *ch = ctx->h_children.data() + n.child_off;
@@ -508,7 +535,7 @@ struct Planner {
         switch (n.tag) {
         case SVGR_N_LEAF:
             if (n.a >= 0 && n.a < ctx->n_path) {
-                const PathBox &b = ctx->h_full_boxes[n.a];
+                const PathBox &b = pb[n.a];
                 if (b.rows > 0 && b.cols > 0) {
                     o.live = true, o.r0 = b.r0, o.c0 = b.c0, o.rows = b.rows, o.cols = b.cols;
                     if (n.b >= 0 && n.b < ctx->n_paint && ctx->h_paints[n.b].kind == PAINT_PATTERN &&
@@ -518,13 +545,13 @@ struct Planner {
             }
             break;
         case SVGR_N_GROUP:
-            o = shadow_union(n, ch, false, false);
+            o = shadow_union(shadow, n, ch, false, false);
             break;
         case SVGR_N_IN:
-            o = shadow_union(n, ch, true, true);
+            o = shadow_union(shadow, n, ch, true, true);
             break;
         case SVGR_N_COMPOSE:
-            o = shadow_union(n, ch, n.a == MODE_IN || (n.flags & 4), true);
+            o = shadow_union(shadow, n, ch, n.a == MODE_IN || (n.flags & 4), true);
             break;
         case SVGR_N_OPACITY:
         case SVGR_N_LUMA:
@@ -573,6 +600,56 @@ struct Planner {
             break;
         }
         shadow[i] = o;
+    }
+
+    // ---- demand boxes.  compose([stencil, image], IN) lives on the intersection of its two boxes (:382-416), so
+    // whatever a group under a clip or a mask renders outside the other operand's box is never seen -- in the c5 icon
+    // the four blobs are composited over their whole union box and then clipped to the circle, the mask group is
+    // rendered over 192 x 192 px for a stroke that covers a part of it.  Per plan range (scenes do not refer across
+    // ranges): the natural box of every node (box_node, the algebra band renders already use), then top-down the
+    // region of every node its consumers can observe.  Every operator between a group and its consumer here is
+    // pointwise (pixel p of the input only reaches pixel p of the output), so the observable region of a child is
+    // that of its parent cut to the parent's own box; filters with reach (blur, morphology, offset), merge_at,
+    // pattern tiles and anything read back by the caller observe everything.  A group's fold is then emitted on its
+    // box cut to its demand: same sources, same order, same arithmetic per pixel, fewer tiles.
+    std::vector<SBox> natural;
+    std::vector<DBox> demand;
+    bool use_demand = true;
+
+    void demand_range(int a, int b)
+    {
+        svgr_ctx *c = ctx;
+        natural.resize((size_t)c->n_node);
+        demand.resize((size_t)c->n_node);
+        for (int i = a; i < b; i++) {
+            box_node(i, c->h_boxes, natural);
+            demand[i] = DBox();
+        }
+        for (int i = b - 1; i >= a; i--) {
+            const svgr_node &n = c->h_nodes[i];
+            DBox &d = demand[i];
+            if (!d.any || (n.flags & 2) || n.tag == SVGR_N_CANVAS || i == c->n_node - 1)
+                d.add_all();  // nobody above restricts it (or the caller reads it)
+            const int32_t *ch = c->h_children.data() + n.child_off;
+            const bool pointwise = n.tag == SVGR_N_GROUP || n.tag == SVGR_N_IN || n.tag == SVGR_N_COMPOSE ||
+                                   n.tag == SVGR_N_OPACITY || n.tag == SVGR_N_LUMA || n.tag == SVGR_N_SRC_ALPHA ||
+                                   n.tag == SVGR_N_CONVERT || n.tag == SVGR_N_CMATRIX || n.tag == SVGR_N_CANVAS;
+            const SBox &nb = natural[i];
+            for (int k = 0; k < n.child_cnt; k++) {
+                const int kid = ch[k];
+                if (kid < a || kid >= i)
+                    continue;
+                if (!pointwise || !nb.live)
+                    demand[kid].add_all();
+                else if (d.inf)
+                    demand[kid].add(nb.r0, nb.c0, nb.r0 + nb.rows, nb.c0 + nb.cols);
+                else
+                    demand[kid].add(std::max(d.r0, nb.r0), std::max(d.c0, nb.c0), std::min(d.r1, nb.r0 + nb.rows),
+                                    std::min(d.c1, nb.c0 + nb.cols));
+            }
+            if (n.tag == SVGR_N_LEAF && n.d >= a && n.d < i)
+                demand[n.d].add_all();  // pattern tile: gathered from anywhere
+        }
     }
 
     // filter_offset (svgrasterize.py:1844-1850) for a layer whose origin is (r0, c0): the integer shift.  1-D points
@@ -684,7 +761,7 @@ struct Planner {
             for (int k = 0; k < n.child_cnt; k++)
                 if (child(k).kind != VAL_EMPTY)
                     ls.push_back(child(k));
-            out = compose(ls, MODE_OVER, nullptr, lin);
+            out = compose(ls, MODE_OVER, nullptr, lin, false, false, use_demand ? &demand[i] : nullptr);
             break;
         }
         case SVGR_N_OPACITY: {
@@ -1100,6 +1177,9 @@ struct Planner {
     bool plan_range(int a, int b)
     {
         svgr_ctx *c = ctx;
+        use_demand = !getenv("SVGR_NO_DEMAND");
+        if (use_demand)
+            demand_range(a, b);
         for (int i = a; i < b; i++) {
             if (!shadow.empty())
                 shadow_node(i);
