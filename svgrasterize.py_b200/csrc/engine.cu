@@ -650,6 +650,26 @@ struct Planner {
             if (n.tag == SVGR_N_LEAF && n.d >= a && n.d < i)
                 demand[n.d].add_all();  // pattern tile: gathered from anywhere
         }
+        if (getenv("SVGR_PLAN_DEBUG")) {
+            long long nat_px = 0, seen_px = 0;
+            for (int i = a; i < b; i++) {
+                const svgr_node &n = c->h_nodes[i];
+                if (n.tag != SVGR_N_LEAF || !natural[i].live)
+                    continue;
+                const SBox &nb = natural[i];
+                const DBox &d = demand[i];
+                nat_px += (long long)nb.rows * nb.cols;
+                if (d.inf)
+                    seen_px += (long long)nb.rows * nb.cols;
+                else if (d.any) {
+                    const long long rr = std::min(d.r1, nb.r0 + nb.rows) - std::max(d.r0, nb.r0);
+                    const long long cc = std::min(d.c1, nb.c0 + nb.cols) - std::max(d.c0, nb.c0);
+                    seen_px += std::max(0ll, rr) * std::max(0ll, cc);
+                }
+            }
+            fprintf(stderr, "[plan] leaf mask pixels %lld, observable %lld (%.1f%%)\n", nat_px, seen_px,
+                    100.0 * (double)seen_px / (double)std::max(1ll, nat_px));
+        }
     }
 
     // filter_offset (svgrasterize.py:1844-1850) for a layer whose origin is (r0, c0): the integer shift.  1-D points
