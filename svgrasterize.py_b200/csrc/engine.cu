@@ -178,7 +178,7 @@ struct svgr_ctx {
     DevBuf d_eager[3];  // scratch of the eager element-wise entry points
     // PNG encoding (k_png.cu): segment / canvas tables, worst-case slots, sizes, packed files
     DevBuf d_png_segs, d_png_canvases, d_png_scratch, d_png_seg_bytes, d_png_seg_adler, d_png_file_bytes, d_png_file_off,
-        d_png_out, d_png_in;
+        d_png_out, d_png_in, d_png_code;
     PinBuf pin_png;
     cudaEvent_t ev_png[2] = {nullptr, nullptr};
     DevBuf d_tmaps;     // tensor maps of the TMA-fed stencil launches of the render in flight (128 B each)
@@ -2282,7 +2282,8 @@ void svgr_destroy(svgr_ctx *ctx)
                       &ctx->d_ovf_depth[0], &ctx->d_ovf_depth[1], &ctx->d_ovf_counts, &ctx->d_eager[0], &ctx->d_eager[1],
                       &ctx->d_eager[2], &ctx->d_tmaps, &ctx->d_full_boxes, &ctx->d_png_segs, &ctx->d_png_canvases, &ctx->d_png_scratch,
                       &ctx->d_png_seg_bytes, &ctx->d_png_seg_adler, &ctx->d_png_file_bytes, &ctx->d_png_file_off,
-                      &ctx->d_png_out, &ctx->d_png_in};
+                      &ctx->d_png_out, &ctx->d_png_in, &ctx->d_png_code, &ctx->d_bbox_jobs, &ctx->d_bbox_csr, &ctx->d_bbox_inv,
+                      &ctx->d_bbox_keys};
     for (DevBuf *b : bufs)
         b->release();
     ctx->pin_boxes.release(), ctx->pin_status.release(), ctx->pin_plan.release(), ctx->pin_out.release();
@@ -2383,8 +2384,11 @@ static int encode_png(svgr_ctx *ctx, cudaStream_t s, const uint8_t *canvas_buf, 
         cudaEventRecord(ctx->ev_png[0], s);
     CK(cudaMemcpyAsync(ctx->d_png_segs.p, segs.data(), n_seg * sizeof(PngSegH), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->d_png_canvases.p, cvs.data(), (size_t)n * sizeof(PngCanvasH), cudaMemcpyHostToDevice, s));
-    svgr_launch_png_deflate(ctx->d_png_segs.p, (int)n_seg, ctx->d_png_canvases.p, canvas_buf, ctx->d_png_scratch.as<uint8_t>(),
-                            ctx->d_png_seg_bytes.as<int>(), ctx->d_png_seg_adler.as<unsigned>(), s);
+    CK(ctx->d_png_code.ensure(svgr_png_code_scratch_bytes()));
+    const int n_deflate_kernels =
+        svgr_launch_png_deflate(ctx->d_png_segs.p, (int)n_seg, ctx->d_png_canvases.p, canvas_buf,
+                                ctx->d_png_scratch.as<uint8_t>(), ctx->d_png_seg_bytes.as<int>(),
+                                ctx->d_png_seg_adler.as<unsigned>(), ctx->d_png_code.p, s);
     svgr_launch_png_sizes(ctx->d_png_canvases.p, n, ctx->d_png_seg_bytes.as<int>(), ctx->d_png_file_bytes.as<int>(), s);
     int *h_sizes = (int *)ctx->pin_png.p;
     long long *h_off = (long long *)((char *)ctx->pin_png.p + (((size_t)n * 4 + 15) & ~(size_t)15));
@@ -2416,7 +2420,7 @@ static int encode_png(svgr_ctx *ctx, cudaStream_t s, const uint8_t *canvas_buf, 
     CK(cudaGetLastError());
     if (stats) {
         stats->png_bytes = total;
-        stats->n_kernels += 3;
+        stats->n_kernels += 2 + n_deflate_kernels;
         if (timing) {
             stats->ms_png = ev_ms(ctx->ev_png[0], ctx->ev_png[1]);
             stats->ms_total += stats->ms_png;

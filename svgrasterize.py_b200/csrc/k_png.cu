@@ -14,7 +14,10 @@
 //              per match: a run of equal residual pixels -- what flat, anti-aliased vector art consists of
 //   Huffman    one dynamic block per segment (<= 256 work items of <= 256 pixels of a row): histogram of every
 //              fourth item -> length-limited code (15 bits) built by the segment's CTA -> canonical codes; the
-//              code lengths go out with a fixed 4-bit code-length code (158 bytes of header per block)
+//              code lengths go out with a fixed 4-bit code-length code (158 bytes of header per block).  A call
+//              with many segments (a batch of icons) shares ONE code: png_hist_kernel samples every 16th item of
+//              every segment, png_code_kernel builds the code once, the segments only emit (files 2 % larger,
+//              encoder 12 % faster)
 //   framing    segments end on a byte boundary (an empty stored block, zlib's sync-flush marker), so they
 //              concatenate by copying; zlib header, Adler-32 (per-item sums by dp4a, combined), PNG chunks and
 //              their CRC-32 (per-thread table CRC + GF(2) shifts) are written by the packing kernel
@@ -23,6 +26,8 @@
 // up once and kept in registers as (bits, length) per pixel, a warp scan places the lanes' bits in a shared-memory
 // staging slot, the slot goes to the item's private area; when all items are done their offsets are known and
 // they are merged (shifted) behind the block header.
+#include <stdlib.h>
+
 #include <algorithm>
 #include <atomic>
 
@@ -37,6 +42,8 @@
 #define PNG_ITEM_WORDS 484      // words of an item's private slot: (4 * 256 + 1) bytes at <= 15 bits each (an item
                                 // the sample did not see may consist of the rarest symbols only)
 #define ADLER_MOD 65521u
+#define PNG_SHARED_SAMPLE 16     // shared code: every how many items of a segment enter the call's histogram
+#define PNG_SHARED_MIN_SEGS 64   // a call with at least this many segments shares one code
 
 struct PngSeg {           // one deflate block
     int32_t canvas;       // index of the canvas
@@ -189,42 +196,34 @@ __device__ __forceinline__ int pixel_token(const LanePixels &px, int lane, int j
 // one CTA per segment: sampled histogram -> code -> every item emitted into its own slot (warp per item, staged in
 // shared memory) -> items merged bit-exactly behind the block header into the segment's stream
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(PNG_THREADS)
-png_deflate_kernel(const PngSeg *__restrict__ segs, const PngCanvas *__restrict__ canvases,
-                   const unsigned char *__restrict__ canvas_buf, unsigned char *__restrict__ scratch,
-                   int *__restrict__ seg_bytes, unsigned *__restrict__ seg_adler /* a, b per segment */)
+// Everything the Huffman code of a block consists of, in shared memory: frequencies in, lengths / codes / match
+// tokens out (build_code).
+struct CodeTables {
+    unsigned freq[PNG_NSYM];
+    unsigned char len[PNG_NSYM];
+    unsigned short code[PNG_NSYM];
+    unsigned short order[PNG_NSYM];     // symbols by ascending (freq, symbol)
+    int parent[2 * PNG_NSYM];
+    unsigned weight[2 * PNG_NSYM];
+    int count[PNG_MAXBITS + 2];         // symbols per code length
+    unsigned next_code[PNG_MAXBITS + 1];
+    unsigned match_bits[65];            // code + extra + distance of a match of n pixels ...
+    unsigned char match_len[65];        // ... and its length in bits
+};
+
+// What a whole call shares when its segments are many and alike (png_code_kernel -> png_deflate_kernel<true>)
+struct PngCode {
+    unsigned char len[PNG_NSYM];
+    unsigned short code[PNG_NSYM];
+    unsigned match_bits[65];
+    unsigned char match_len[65];
+};
+
+// Sampled histogram of one segment's tokens into s_hist (one row per warp), `sample` = every how many items
+__device__ __forceinline__ void segment_histogram(unsigned (*s_hist)[PNG_NSYM + 6], const unsigned *img, const PngCanvas &cv,
+                                                  const PngSeg &seg, int items_per_row, int n_items, int sample)
 {
-    __shared__ unsigned s_hist[PNG_WARPS][PNG_NSYM + 6];
-    __shared__ unsigned s_freq[PNG_NSYM];
-    __shared__ unsigned char s_len[PNG_NSYM];
-    __shared__ unsigned short s_code[PNG_NSYM];
-    __shared__ unsigned short s_order[PNG_NSYM];     // symbols by ascending (freq, symbol)
-    __shared__ int s_parent[2 * PNG_NSYM];
-    __shared__ unsigned s_weight[2 * PNG_NSYM];
-    __shared__ unsigned s_item_bits[PNG_THREADS + 1];
-    __shared__ unsigned s_item_a[PNG_THREADS], s_item_b[PNG_THREADS];
-    __shared__ unsigned s_stage[PNG_WARPS][PNG_ITEM_WORDS];
-    __shared__ int s_count[PNG_MAXBITS + 2];         // symbols per code length
-    __shared__ unsigned s_next_code[PNG_MAXBITS + 1];
-    __shared__ unsigned s_warp_tot[3][PNG_WARPS];
-    __shared__ unsigned s_match_bits[65];            // code + extra + distance of a match of n pixels ...
-    __shared__ unsigned char s_match_len[65];        // ... and its length in bits
-
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const PngSeg seg = segs[blockIdx.x];
-    const PngCanvas cv = canvases[seg.canvas];
-    const unsigned *img = reinterpret_cast<const unsigned *>(canvas_buf + cv.src);
-    const int items_per_row = (cv.cols + PNG_ITEM_PX - 1) / PNG_ITEM_PX;
-    const int n_items = seg.rows * items_per_row;  // <= PNG_THREADS by construction
-    unsigned *item_slots = reinterpret_cast<unsigned *>(scratch + seg.slot);
-    unsigned *out = item_slots + (size_t)n_items * PNG_ITEM_WORDS;
-
-    for (int i = tid; i < PNG_WARPS * (PNG_NSYM + 6); i += PNG_THREADS)
-        (&s_hist[0][0])[i] = 0;
-    __syncthreads();
-    // ---- histogram of a sample of the items (every fourth; all of a small segment): the code only has to be
-    // good, not optimal, and every symbol gets a code anyway (+1 below)
-    const int sample = n_items >= 32 ? 4 : 1;
     for (int it = warp * sample; it < n_items; it += PNG_WARPS * sample) {
         const int row = seg.row0 + it / items_per_row, c0 = (it % items_per_row) * PNG_ITEM_PX;
         LanePixels px;
@@ -246,16 +245,19 @@ png_deflate_kernel(const PngSeg *__restrict__ segs, const PngCanvas *__restrict_
                 }
             }
     }
-    __syncthreads();
-    for (int s = tid; s < PNG_NSYM; s += PNG_THREADS) {
-        unsigned f = 0;
-#pragma unroll
-        for (int w = 0; w < PNG_WARPS; w++)
-            f += s_hist[w][s];
-        s_freq[s] = s < 286 ? f + 1 : 0;  // every literal / length symbol can occur in the unsampled items
-        s_len[s] = 0;
-    }
-    __syncthreads();
+}
+
+// Length-limited canonical Huffman code from T.freq (every thread of the CTA calls this after a barrier that made
+// the frequencies visible; returns with the tables complete and a barrier behind them).
+__device__ void build_code(CodeTables &T)
+{
+    const int tid = threadIdx.x;
+    unsigned *s_freq = T.freq;
+    unsigned char *s_len = T.len;
+    unsigned short *s_code = T.code, *s_order = T.order;
+    int *s_parent = T.parent, *s_count = T.count;
+    unsigned *s_weight = T.weight, *s_next_code = T.next_code, *s_match_bits = T.match_bits;
+    unsigned char *s_match_len = T.match_len;
     // ---- Huffman code lengths of the literal / length alphabet (0..285); the distance alphabet has one code
     for (int s = tid; s < 286; s += PNG_THREADS) {
         const unsigned f = s_freq[s];
@@ -365,6 +367,106 @@ png_deflate_kernel(const PngSeg *__restrict__ segs, const PngCanvas *__restrict_
         s_match_len[tid] = (unsigned char)(l + eb + 1);
     }
     __syncthreads();
+}
+
+// Per call, when its segments are many and alike (a batch of icons): one sampled histogram over all segments ...
+__global__ void __launch_bounds__(PNG_THREADS)
+png_hist_kernel(const PngSeg *__restrict__ segs, const PngCanvas *__restrict__ canvases,
+                const unsigned char *__restrict__ canvas_buf, unsigned *__restrict__ hist /* PNG_NSYM, zeroed */)
+{
+    __shared__ unsigned s_hist[PNG_WARPS][PNG_NSYM + 6];
+    const int tid = threadIdx.x;
+    const PngSeg seg = segs[blockIdx.x];
+    const PngCanvas cv = canvases[seg.canvas];
+    const unsigned *img = reinterpret_cast<const unsigned *>(canvas_buf + cv.src);
+    const int items_per_row = (cv.cols + PNG_ITEM_PX - 1) / PNG_ITEM_PX;
+    for (int i = tid; i < PNG_WARPS * (PNG_NSYM + 6); i += PNG_THREADS)
+        (&s_hist[0][0])[i] = 0;
+    __syncthreads();
+    segment_histogram(s_hist, img, cv, seg, items_per_row, seg.rows * items_per_row, PNG_SHARED_SAMPLE);
+    __syncthreads();
+    for (int s = tid; s < PNG_NSYM; s += PNG_THREADS) {
+        unsigned f = 0;
+#pragma unroll
+        for (int w = 0; w < PNG_WARPS; w++)
+            f += s_hist[w][s];
+        if (f)
+            atomicAdd(hist + s, f);
+    }
+}
+
+// ... and one code for all of them (a single CTA)
+__global__ void __launch_bounds__(PNG_THREADS)
+png_code_kernel(const unsigned *__restrict__ hist, PngCode *__restrict__ out)
+{
+    __shared__ CodeTables T;
+    const int tid = threadIdx.x;
+    for (int s = tid; s < PNG_NSYM; s += PNG_THREADS) {
+        T.freq[s] = s < 286 ? hist[s] + 1 : 0;  // every literal / length symbol can occur in the unsampled items
+        T.len[s] = 0;
+    }
+    __syncthreads();
+    build_code(T);
+    for (int s = tid; s < PNG_NSYM; s += PNG_THREADS)
+        out->len[s] = T.len[s], out->code[s] = T.code[s];
+    if (tid <= 64)
+        out->match_bits[tid] = tid ? T.match_bits[tid] : 0u, out->match_len[tid] = tid ? T.match_len[tid] : 0;
+}
+
+// SHARED_CODE: the Huffman code comes from png_code_kernel (the call's segments share it) instead of being built
+// from this segment's own sampled histogram.
+template <bool SHARED_CODE>
+__global__ void __launch_bounds__(PNG_THREADS)
+png_deflate_kernel(const PngSeg *__restrict__ segs, const PngCanvas *__restrict__ canvases,
+                   const unsigned char *__restrict__ canvas_buf, unsigned char *__restrict__ scratch,
+                   int *__restrict__ seg_bytes, unsigned *__restrict__ seg_adler /* a, b per segment */,
+                   const PngCode *__restrict__ shared_code)
+{
+    __shared__ unsigned s_hist[SHARED_CODE ? 1 : PNG_WARPS][PNG_NSYM + 6];
+    __shared__ CodeTables T;
+    __shared__ unsigned s_item_bits[PNG_THREADS + 1];
+    __shared__ unsigned s_item_a[PNG_THREADS], s_item_b[PNG_THREADS];
+    __shared__ unsigned s_stage[PNG_WARPS][PNG_ITEM_WORDS];
+    __shared__ unsigned s_warp_tot[3][PNG_WARPS];
+    unsigned char *s_len = T.len;
+    unsigned short *s_code = T.code;
+    unsigned *s_match_bits = T.match_bits;
+    unsigned char *s_match_len = T.match_len;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const PngSeg seg = segs[blockIdx.x];
+    const PngCanvas cv = canvases[seg.canvas];
+    const unsigned *img = reinterpret_cast<const unsigned *>(canvas_buf + cv.src);
+    const int items_per_row = (cv.cols + PNG_ITEM_PX - 1) / PNG_ITEM_PX;
+    const int n_items = seg.rows * items_per_row;  // <= PNG_THREADS by construction
+    unsigned *item_slots = reinterpret_cast<unsigned *>(scratch + seg.slot);
+    unsigned *out = item_slots + (size_t)n_items * PNG_ITEM_WORDS;
+
+    if (SHARED_CODE) {
+        for (int s = tid; s < PNG_NSYM; s += PNG_THREADS)
+            T.len[s] = shared_code->len[s], T.code[s] = shared_code->code[s];
+        if (tid <= 64)
+            T.match_bits[tid] = shared_code->match_bits[tid], T.match_len[tid] = shared_code->match_len[tid];
+        __syncthreads();
+    } else {
+        for (int i = tid; i < PNG_WARPS * (PNG_NSYM + 6); i += PNG_THREADS)
+            (&s_hist[0][0])[i] = 0;
+        __syncthreads();
+        // ---- histogram of a sample of the items (every fourth; all of a small segment): the code only has to be
+        // good, not optimal, and every symbol gets a code anyway (+1 below)
+        segment_histogram(s_hist, img, cv, seg, items_per_row, n_items, n_items >= 32 ? 4 : 1);
+        __syncthreads();
+        for (int s = tid; s < PNG_NSYM; s += PNG_THREADS) {
+            unsigned f = 0;
+#pragma unroll
+            for (int w = 0; w < (SHARED_CODE ? 1 : PNG_WARPS); w++)
+                f += s_hist[w][s];
+            T.freq[s] = s < 286 ? f + 1 : 0;  // every literal / length symbol can occur in the unsampled items
+            T.len[s] = 0;
+        }
+        __syncthreads();
+        build_code(T);
+    }
     // ---- every item: tokens -> (bits, length) per pixel in registers -> staged in shared memory -> its slot
     for (int it = warp; it < n_items; it += PNG_WARPS) {
         const int row = seg.row0 + it / items_per_row, c0 = (it % items_per_row) * PNG_ITEM_PX;
@@ -799,13 +901,32 @@ int svgr_png_rows_per_segment(int cols)
     return std::max(1, PNG_THREADS / items_per_row);
 }
 
-void svgr_launch_png_deflate(const void *segs, int n_seg, const void *canvases, const unsigned char *canvas_buf,
-                             unsigned char *scratch, int *seg_bytes, unsigned *seg_adler, cudaStream_t s)
+size_t svgr_png_code_scratch_bytes() { return ((PNG_NSYM * sizeof(unsigned) + 15) & ~(size_t)15) + sizeof(PngCode); }
+
+// code_scratch: svgr_png_code_scratch_bytes() of device memory (the call's histogram and its code).  Returns the
+// number of kernels launched.
+int svgr_launch_png_deflate(const void *segs, int n_seg, const void *canvases, const unsigned char *canvas_buf,
+                            unsigned char *scratch, int *seg_bytes, unsigned *seg_adler, void *code_scratch, cudaStream_t s)
 {
     png_init_tables();
-    if (n_seg > 0)
-        png_deflate_kernel<<<n_seg, PNG_THREADS, 0, s>>>((const PngSeg *)segs, (const PngCanvas *)canvases, canvas_buf, scratch,
-                                                         seg_bytes, seg_adler);
+    if (n_seg <= 0)
+        return 0;
+    const PngSeg *sg = (const PngSeg *)segs;
+    const PngCanvas *cv = (const PngCanvas *)canvases;
+    static const bool no_shared = getenv("SVGR_PNG_PER_SEGMENT_CODE") != nullptr;
+    if (n_seg >= PNG_SHARED_MIN_SEGS && code_scratch && !no_shared) {
+        // many segments (a batch of icons): one sampled histogram and one Huffman code for the whole call instead of
+        // a histogram pass and a code construction per segment
+        unsigned *hist = (unsigned *)code_scratch;
+        PngCode *code = (PngCode *)((char *)code_scratch + ((PNG_NSYM * sizeof(unsigned) + 15) & ~(size_t)15));
+        cudaMemsetAsync(hist, 0, PNG_NSYM * sizeof(unsigned), s);
+        png_hist_kernel<<<n_seg, PNG_THREADS, 0, s>>>(sg, cv, canvas_buf, hist);
+        png_code_kernel<<<1, PNG_THREADS, 0, s>>>(hist, code);
+        png_deflate_kernel<true><<<n_seg, PNG_THREADS, 0, s>>>(sg, cv, canvas_buf, scratch, seg_bytes, seg_adler, code);
+        return 3;
+    }
+    png_deflate_kernel<false><<<n_seg, PNG_THREADS, 0, s>>>(sg, cv, canvas_buf, scratch, seg_bytes, seg_adler, nullptr);
+    return 1;
 }
 
 void svgr_launch_png_sizes(const void *canvases, int n_canvas, const int *seg_bytes, int *file_bytes, cudaStream_t s)

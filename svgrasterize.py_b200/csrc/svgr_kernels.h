@@ -97,8 +97,9 @@ struct PngSeg;
 struct PngCanvas;
 long long svgr_png_slot_bytes(int rows, int cols);
 int svgr_png_rows_per_segment(int cols);
-void svgr_launch_png_deflate(const void *segs, int n_seg, const void *canvases, const unsigned char *canvas_buf,
-                             unsigned char *scratch, int *seg_bytes, unsigned *seg_adler, cudaStream_t s);
+size_t svgr_png_code_scratch_bytes();
+int svgr_launch_png_deflate(const void *segs, int n_seg, const void *canvases, const unsigned char *canvas_buf,
+                            unsigned char *scratch, int *seg_bytes, unsigned *seg_adler, void *code_scratch, cudaStream_t s);
 void svgr_launch_png_sizes(const void *canvases, int n_canvas, const int *seg_bytes, int *file_bytes, cudaStream_t s);
 void svgr_launch_png_pack(const void *canvases, int n_canvas, const void *segs, const int *seg_bytes, const unsigned *seg_adler,
                           const unsigned char *scratch, const long long *file_off, unsigned char *out, cudaStream_t s);
