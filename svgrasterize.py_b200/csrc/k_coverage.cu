@@ -10,7 +10,7 @@
 // whose rows they cross (count -> scan -> fill), and one CTA renders one tile =
 // (band, chunk of SVGR_TILE_COLS columns):
 //   1. signed-area deltas of the band's edges are accumulated into a shared-memory
-//      trace tile (float32 shared atomics; the edge arithmetic itself is float64),
+//      trace tile (32-bit fixed-point shared atomics: deterministic; the edge arithmetic itself is float64),
 //   2. each warp prefix-sums rows with register scans + warp shuffles,
 //   3. the fill rule and the 1e-6 snap are applied and the row leaves as 128-bit stores.
 // The trace never touches HBM: traffic is 36 B per binned edge in, 4 B per pixel out.
@@ -222,23 +222,55 @@ __global__ void bin_fill_kernel(const double *__restrict__ edges, const uint32_t
 // ---------------------------------------------------------------------------------------------
 // coverage
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void put(float *row, int w, long long ix, double val)
+// Where the signed-area deltas go.  The tile kernel accumulates in shared memory in 32-bit fixed point: integer adds
+// commute exactly, so a mask no longer depends on the order in which the threads arrive (float atomics made masks
+// differ in their last bit from run to run), and an integer shared-memory atomic is one instruction (ATOMS.ADD)
+// where the float one is a compare-and-swap loop (ATOMS.CAST.SPIN).  Scale 2^22: a delta is rounded to 1.2e-7 (a
+// float32 near 1.0: 6e-8), the row's prefix sum is then exact; sums wrap modulo 2^32 and are right as long as the
+// final winding-weighted coverage stays below 512 in magnitude.  line_coverage_kernel (the eager entry point
+// onto a caller's float trace) keeps float atomics.
+#define COV_FIX_SCALE 4194304.0
+#define COV_FIX_INV (1.0f / 4194304.0f)
+struct FixedTrace {
+    typedef int cell;
+    static __device__ __forceinline__ void add(int *p, double v) { atomicAdd(p, __double2int_rn(v * COV_FIX_SCALE)); }
+    static __device__ __forceinline__ void add_run(int *p, long long lo, long long hi, double v)
+    {
+        const int q = __double2int_rn(v * COV_FIX_SCALE);
+        for (long long xi = lo; xi < hi; xi++)
+            atomicAdd(p + xi, q);
+    }
+};
+struct FloatTrace {
+    typedef float cell;
+    static __device__ __forceinline__ void add(float *p, double v) { atomicAdd(p, (float)v); }
+    static __device__ __forceinline__ void add_run(float *p, long long lo, long long hi, double v)
+    {
+        const float q = (float)v;
+        for (long long xi = lo; xi < hi; xi++)
+            atomicAdd(p + xi, q);
+    }
+};
+
+template <class A>
+__device__ __forceinline__ void put(typename A::cell *row, int w, long long ix, double val)
 {
     // index >= w dropped, index < 0 accumulated into column 0 (svgrasterize.py:2262 etc.)
     if (ix >= w)
         return;
-    atomicAdd(row + (ix > 0 ? (int)ix : 0), (float)val);
+    A::add(row + (ix > 0 ? (int)ix : 0), val);
 }
 
 // One row crossing of one edge (svgrasterize.py:2244-2303), columns local to the tile.
-__device__ __forceinline__ void edge_row(float *row, int w, double x, double x_next, double d)
+template <class A>
+__device__ __forceinline__ void edge_row(typename A::cell *row, int w, double x, double x_next, double d)
 {
     double x0 = x, x1 = x_next;
     if (!(x < x_next))
         x0 = x_next, x1 = x;
     double x0_floor = floor(x0), x1_ceil = ceil(x1);
     if (x1_ceil <= 0.0) {  // whole span left of the tile: the deltas sum to d, all into column 0
-        atomicAdd(row, (float)d);
+        A::add(row, d);
         return;
     }
     if (x0_floor >= (double)w)
@@ -246,8 +278,8 @@ __device__ __forceinline__ void edge_row(float *row, int w, double x, double x_n
     long long x0i = (long long)x0_floor, x1i = (long long)x1_ceil;
     if (x1i <= x0i + 1) {
         double xmf = 0.5 * (x + x_next) - x0_floor;
-        put(row, w, x0i, d * (1.0 - xmf));
-        put(row, w, x0i + 1, d * xmf);
+        put<A>(row, w, x0i, d * (1.0 - xmf));
+        put<A>(row, w, x0i + 1, d * xmf);
         return;
     }
     double s = 1.0 / (x1 - x0);
@@ -255,29 +287,27 @@ __device__ __forceinline__ void edge_row(float *row, int w, double x, double x_n
     double x1f = x1 - x1_ceil + 1.0;
     double a0 = 0.5 * s * ((1.0 - x0f) * (1.0 - x0f));
     double am = 0.5 * s * (x1f * x1f);
-    put(row, w, x0i, d * a0);
+    put<A>(row, w, x0i, d * a0);
     if (x1i == x0i + 2) {
-        put(row, w, x0i + 1, d * (1.0 - a0 - am));
+        put<A>(row, w, x0i + 1, d * (1.0 - a0 - am));
     } else {
         double a1 = s * (1.5 - x0f);
-        put(row, w, x0i + 1, d * (a1 - a0));
+        put<A>(row, w, x0i + 1, d * (a1 - a0));
         double ds = d * s;
         long long lo = x0i + 2, hi = x1i - 1;  // interior columns [lo, hi)
         if (lo < 0) {
             long long neg_end = hi < 0 ? hi : 0;
             if (neg_end > lo)
-                atomicAdd(row, (float)((double)(neg_end - lo) * ds));
+                A::add(row, (double)(neg_end - lo) * ds);
             lo = neg_end > lo ? neg_end : lo;
         }
         if (hi > w)
             hi = w;
-        float fds = (float)ds;
-        for (long long xi = lo; xi < hi; xi++)
-            atomicAdd(row + xi, fds);
+        A::add_run(row, lo, hi, ds);
         double a2 = a1 + (double)(x1i - x0i - 3) * s;
-        put(row, w, x1i - 1, d * (1.0 - a2 - am));
+        put<A>(row, w, x1i - 1, d * (1.0 - a2 - am));
     }
-    put(row, w, x1i, d * am);
+    put<A>(row, w, x1i, d * am);
 }
 
 __device__ __forceinline__ float fill_rule_apply(float m, int rule)
@@ -309,7 +339,7 @@ __global__ void __launch_bounds__(COV_THREADS)
 coverage_kernel(const TileRec *__restrict__ tiles, int n_tiles, const double2 *__restrict__ bin_data,
                 float *__restrict__ cov)
 {
-    __shared__ __align__(16) float trace[SVGR_BAND_ROWS][SVGR_TILE_COLS];
+    __shared__ __align__(16) int trace[SVGR_BAND_ROWS][SVGR_TILE_COLS];  // fixed point, see FixedTrace
     __shared__ double s_r0[COV_THREADS], s_r1[COV_THREADS], s_c0[COV_THREADS], s_dxdy[COV_THREADS];
     __shared__ float s_dir[COV_THREADS];
     __shared__ uint16_t s_pairs[COV_THREADS * SVGR_BAND_ROWS];  // (edge << 4) | row of the band, compacted
@@ -319,7 +349,7 @@ coverage_kernel(const TileRec *__restrict__ tiles, int n_tiles, const double2 *_
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // the trace tile starts zeroed and every tile leaves it zeroed again (the scan clears what it reads)
     for (int i = tid; i < SVGR_BAND_ROWS * SVGR_TILE_COLS / 4; i += COV_THREADS)
-        reinterpret_cast<float4 *>(&trace[0][0])[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        reinterpret_cast<int4 *>(&trace[0][0])[i] = make_int4(0, 0, 0, 0);
     int tile = blockIdx.x, cur = 0, chunk_no = 0;
     if (tid < 2)
         s_npairs[tid] = 0;
@@ -407,7 +437,7 @@ coverage_kernel(const TileRec *__restrict__ tiles, int n_tiles, const double2 *_
                 double dy = ytop - ybot;
                 double x = s_c0[ei] + dxdy * (ybot - r0);
                 double x_next = x + dxdy * dy;
-                edge_row(trace[yl], w, x, x_next, (double)s_dir[ei] * dy);
+                edge_row<FixedTrace>(trace[yl], w, x, x_next, (double)s_dir[ei] * dy);
             }
         }
         cp_async_wait_all();
@@ -421,33 +451,33 @@ coverage_kernel(const TileRec *__restrict__ tiles, int n_tiles, const double2 *_
 
         // ---- 2. prefix sum along columns, fill rule, 128-bit stores; the trace is cleared as it is read
         for (int y = warp; y < nrows; y += COV_THREADS / 32) {
-            float carry = 0.f;
+            int carry = 0;
             float *dst = cov + m.off + (long long)(yb + y) * m.stride + col0;
             for (int cb = 0; cb < wpad; cb += 128) {
                 int c = cb + 4 * lane;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                int4 v = make_int4(0, 0, 0, 0);
                 if (c < wpad) {
-                    v = *reinterpret_cast<const float4 *>(&trace[y][c]);
-                    *reinterpret_cast<float4 *>(&trace[y][c]) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    v = *reinterpret_cast<const int4 *>(&trace[y][c]);
+                    *reinterpret_cast<int4 *>(&trace[y][c]) = make_int4(0, 0, 0, 0);
                 }
                 v.y += v.x;
                 v.z += v.y;
                 v.w += v.z;
-                float incl = v.w;
+                int incl = v.w;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
-                    float t = __shfl_up_sync(0xffffffffu, incl, o);
+                    int t = __shfl_up_sync(0xffffffffu, incl, o);
                     if (lane >= o)
                         incl += t;
                 }
-                float ex = incl - v.w + carry;
+                int ex = incl - v.w + carry;
                 carry += __shfl_sync(0xffffffffu, incl, 31);
                 if (c < wpad) {
-                    float4 o4;
-                    o4.x = fill_rule_apply(v.x + ex, m.fill_rule);
-                    o4.y = fill_rule_apply(v.y + ex, m.fill_rule);
-                    o4.z = fill_rule_apply(v.z + ex, m.fill_rule);
-                    o4.w = fill_rule_apply(v.w + ex, m.fill_rule);
+                    float4 o4;  // exact integer prefix sums -> coverage
+                    o4.x = fill_rule_apply((float)(v.x + ex) * COV_FIX_INV, m.fill_rule);
+                    o4.y = fill_rule_apply((float)(v.y + ex) * COV_FIX_INV, m.fill_rule);
+                    o4.z = fill_rule_apply((float)(v.z + ex) * COV_FIX_INV, m.fill_rule);
+                    o4.w = fill_rule_apply((float)(v.w + ex) * COV_FIX_INV, m.fill_rule);
                     *reinterpret_cast<float4 *>(dst + c) = o4;
                 }
             }
@@ -485,7 +515,7 @@ __global__ void line_coverage_kernel(const double *__restrict__ lines, long long
             const double dy = ytop - ybot;
             const double x = c0 + dxdy * (ybot - r0);
             const double x_next = x + dxdy * dy;
-            edge_row(trace + (long long)y * cols, cols, x, x_next, dir * dy);
+            edge_row<FloatTrace>(trace + (long long)y * cols, cols, x, x_next, dir * dy);
         }
     }
 }
