@@ -78,7 +78,8 @@ def test_leaf_stages(name, eng):
         mask = eng.mask(i, boxes[i])
         ref_m = z["masks"][moff[i]: moff[i + 1]].reshape(mask.shape)
         worst = max(worst, float(np.abs(mask - ref_m).max()))
-    assert worst <= 1e-5, worst
+    # the bar is 1e-5; the fixed-point accumulator (22 fractional bits) measures 2.4e-6 at worst over all fixtures
+    assert worst <= 4e-6, worst
 
 
 @pytest.mark.parametrize("name", STAGED)
