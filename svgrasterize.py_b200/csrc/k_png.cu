@@ -206,6 +206,7 @@ struct CodeTables {
     int parent[2 * PNG_NSYM];
     unsigned weight[2 * PNG_NSYM];
     int count[PNG_MAXBITS + 2];         // symbols per code length
+    int n_unseen, pseudo_pos;           // symbols outside the sample; where their pseudo-leaf sorts among the others
     unsigned next_code[PNG_MAXBITS + 1];
     unsigned match_bits[65];            // code + extra + distance of a match of n pixels ...
     unsigned char match_len[65];        // ... and its length in bits
@@ -258,7 +259,14 @@ __device__ void build_code(CodeTables &T)
     int *s_parent = T.parent, *s_count = T.count;
     unsigned *s_weight = T.weight, *s_next_code = T.next_code, *s_match_bits = T.match_bits;
     unsigned char *s_match_len = T.match_len;
-    // ---- Huffman code lengths of the literal / length alphabet (0..285); the distance alphabet has one code
+    // ---- Huffman code lengths of the literal / length alphabet (0..285); the distance alphabet has one code.
+    // Symbols the sample never saw (frequency 1 after the smoothing -- two thirds of the alphabet for an icon) do not
+    // enter the merge one by one: they hang as a complete binary subtree below ONE pseudo-leaf of their total weight,
+    // which is where Huffman's algorithm would put most of them anyway; the sequential merge shrinks from 285 steps
+    // to the number of symbols that occur.
+    if (tid == 0)
+        T.n_unseen = 0, T.pseudo_pos = 0;
+    __syncthreads();
     for (int s = tid; s < 286; s += PNG_THREADS) {
         const unsigned f = s_freq[s];
         int rank = 0;
@@ -267,14 +275,27 @@ __device__ void build_code(CodeTables &T)
             rank += (g < f || (g == f && q < s)) ? 1 : 0;
         }
         s_order[rank] = (unsigned short)s;
+        if (f == 1)
+            atomicAdd(&T.n_unseen, 1);
     }
     __syncthreads();
-    if (tid == 0) {
-        const int n = 286;
+    const int k = T.n_unseen;                    // the first k symbols of the ascending order
+    const int n_seen = 286 - k;
+    const int m = n_seen + (k > 0 ? 1 : 0);      // leaves of the merge
+    for (int s = tid; s < 286; s += PNG_THREADS) // the pseudo-leaf (weight k) sorts behind the seen symbols lighter than it
+        if (s_freq[s] > 1 && s_freq[s] < (unsigned)k)
+            atomicAdd(&T.pseudo_pos, 1);
+    __syncthreads();
+    const int ppos = k > 0 ? T.pseudo_pos : -1;
+    for (int r = tid; r < n_seen; r += PNG_THREADS)
+        s_weight[r + ((k > 0 && r >= ppos) ? 1 : 0)] = s_freq[s_order[k + r]];
+    if (tid == 0 && k > 0)
+        s_weight[ppos] = (unsigned)k;
+    __syncthreads();
+    if (tid == 0 && m >= 2) {
+        const int n = m;
         // two-queue Huffman: leaves 0..n-1 in ascending weight; internal nodes n..2n-2 come out ascending too.
         // This merge is the one sequential piece of the construction; everything after it runs on all threads.
-        for (int i = 0; i < n; i++)
-            s_weight[i] = s_freq[s_order[i]];
         int leaf = 0, node = n, next = n;
         unsigned w_leaf = s_weight[0], w_node = 0xffffffffu;  // heads of the two queues, kept in registers
         auto take = [&](unsigned &w) {
@@ -303,12 +324,22 @@ __device__ void build_code(CodeTables &T)
     for (int i = tid; i <= PNG_MAXBITS + 1; i += PNG_THREADS)
         s_count[i] = 0;
     __syncthreads();
-    // depth of every leaf (its code length before the limit): walk to the root, 286 walks side by side
-    for (int i = tid; i < 286; i += PNG_THREADS) {
+    // depth of every leaf (its code length before the limit): walk to the root, all walks side by side; the
+    // pseudo-leaf contributes the depths of its complete subtree of k leaves
+    for (int i = tid; i < m; i += PNG_THREADS) {
         int d = 0;
-        for (int q = i; q != 2 * 286 - 2; q = s_parent[q])
-            d++;
-        atomicAdd(&s_count[d > PNG_MAXBITS ? PNG_MAXBITS : d], 1);
+        if (m >= 2)
+            for (int q = i; q != 2 * m - 2; q = s_parent[q])
+                d++;
+        if (i == ppos && k > 1) {
+            const int e = 31 - __clz(k);  // floor(log2 k)
+            const int shallow = (2 << e) - k, deep = 2 * (k - (1 << e));
+            atomicAdd(&s_count[min(d + e, PNG_MAXBITS)], shallow);
+            if (deep)
+                atomicAdd(&s_count[min(d + e + 1, PNG_MAXBITS)], deep);
+        } else {
+            atomicAdd(&s_count[min(d, PNG_MAXBITS)], 1);
+        }
     }
     __syncthreads();
     if (tid == 0) {
