@@ -27,7 +27,7 @@ def test_native_batch_renders_like_the_python_encoded_batch(eng):
     ref = encode.Program.concat([encode.encode_scene(s, size, lin) for s, size, lin in jobs])
     b = eng.render(ref)["canvas"]
     assert a.shape == b.shape
-    assert int(np.abs(a.astype(np.int16) - b.astype(np.int16)).max()) <= 1  # coverage float atomics, run to run
+    assert np.array_equal(a, b)  # the two encoders record the same program; rendering is deterministic
     res = eng.render_png(nat)
     assert len(res["offsets"]) == 65 and res["png_bytes"] > 0
     nat.close()

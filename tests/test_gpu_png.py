@@ -107,8 +107,8 @@ def test_demo_files(eng, name):
     got = decode_fast(png)
     assert got.shape == z["canvas_u8"].shape
     assert int(np.abs(got.astype(np.int16) - z["canvas_u8"].astype(np.int16)).max()) <= 1
-    again = B.render_canvas(scene, size, lin)  # a second render: float atomics may move a mask by an ulp
-    assert int(np.abs(got.astype(np.int16) - again.astype(np.int16)).max()) <= 1
+    again = B.render_canvas(scene, size, lin)  # a second render: coverage is deterministic, the pixels are the same
+    assert np.array_equal(got, again)
 
 
 def test_encode_host_images_of_odd_shapes(eng):
