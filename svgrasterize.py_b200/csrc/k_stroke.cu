@@ -10,9 +10,10 @@
 // stroke).  Here the work is cut along its real dependencies:
 //   phase A  one thread per input segment: offset curves at +w/2 and -w/2
 //            (count pass, exclusive scan, emit pass -- no per-thread buffers);
-//   phase B  one thread per sub-path: walk the forward offsets, the cap, the
-//            reversed backward offsets, inserting joins, and write the outline
-//            segments (padded with SEG_NOP to a scanned upper bound).
+//   phase B  one warp per range of <= 256 segments of a sub-path (stroke_assemble_kernel): every curve owns
+//            three fixed outline slots (at most two join curves + itself, unused = SEG_NOP), so what a curve
+//            writes depends on its neighbour only -- forward offsets, the cap, the reversed backward offsets,
+//            joins in between; slot offsets come from a scanned upper bound per sub-path.
 // All arithmetic is float64 with the reference's rounding recipes (SURVEY.md
 // appendix B; file compiled with -fmad=false, fma() spelled out), so outlines are
 // bit-identical to the reference's and flatten like any other path afterwards.
