@@ -519,3 +519,39 @@ def test_path_reader_survives_garbage():
         except ValueError:
             seen["error"] += 1
     assert seen["ok"] > 0 and seen["error"] > 0
+
+
+def test_planner_demand_boxes_cut_groups_under_clips_and_masks(monkeypatch):
+    """engine.cu demand_range on fabricated boxes (no GPU): a group of two large fills clipped by a small circle is
+    folded on the circle's box only; a group under a blur keeps its whole box (the blur reaches across); switching
+    the demand boxes off restores the union box.  The layer arena (info[4], floats) shows the difference."""
+    import ctypes as C
+
+    from svgrasterize_b200 import _lib, encode, scene as S, synth
+
+    def plan(scene, boxes):
+        prog = encode.encode_scene(scene, (256, 256))
+        assert len(prog.paths) == len(boxes)
+        cprog, keep = prog.to_c()
+        a, b = C.c_float(), C.c_float()
+        info = (C.c_int64 * 8)()
+        arr = np.asarray(boxes, dtype=np.int32)
+        assert _lib.lib().svgr_debug_plan(C.byref(cprog), arr.ctypes.data, 1, C.byref(a), C.byref(b), info) == 0
+        return [int(v) for v in info]
+
+    red, blue = synth.color(1, 0, 0), synth.color(0, 0, 1, 0.5)
+    big = S.Scene.group([S.Scene.fill(synth.rect_path(0, 0, 50, 50), red), S.Scene.fill(synth.rect_path(10, 10, 50, 50), blue)])
+    clip = S.Scene.fill(synth.ellipse_path(30, 30, 5), np.ones(4))
+    boxes = [[0, 0, 200, 200], [40, 40, 200, 200], [100, 100, 40, 40]]  # the two fills, the clip circle
+    clipped = big.opacity(0.9).clip(clip)
+    monkeypatch.delenv("SVGR_NO_DEMAND", raising=False)
+    with_demand = plan(clipped, boxes)
+    monkeypatch.setenv("SVGR_NO_DEMAND", "1")
+    without = plan(clipped, boxes)
+    assert with_demand[0] == without[0] and with_demand[3] == without[3]   # same ops, same levels
+    assert without[4] >= 240 * 240 * 4                                       # the union box of the two fills
+    assert with_demand[4] <= 40 * 40 * 4 + 64                                # only what the circle can show
+    # a blur between the group and the clip: the group is observed through the kernel's reach -> not cut
+    monkeypatch.delenv("SVGR_NO_DEMAND", raising=False)
+    blurred = big.filter(S.Filter.empty().blur(2.0, 2.0)).clip(clip)
+    assert plan(blurred, boxes)[4] >= 240 * 240 * 4
