@@ -357,51 +357,52 @@ __device__ bool offset_segment(int tag, const double *d, double dist, Sink &out)
 }
 
 // seg_job[i] = stroke job of input segment i
+// Two threads per input segment, one per side of the stroke: the kernels are one wave of long, branchy float64
+// threads, so their time is the latency of the slowest thread -- which is half as long when it offsets one side.
 __global__ void stroke_count_kernel(const uint8_t *__restrict__ tag, const double *__restrict__ data,
                                     const int *__restrict__ seg_job, const StrokeRec *__restrict__ jobs, int n_seg,
                                     int *__restrict__ counts, int *__restrict__ err)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = t >> 1, side = t & 1;
     if (i >= n_seg)
         return;
     double dist = jobs[seg_job[i]].half_width;
     double d[8];
     for (int k = 0; k < 8; k++)
         d[k] = data[8 * (size_t)i + k];
-    Sink f = {nullptr, 0, 0, {}}, b = {nullptr, 0, 0, {}};
-    bool ok = offset_segment(tag[i], d, dist, f);
-    // a degenerate line contributes to neither side (svgrasterize.py:1121-1125)
-    if (tag[i] == SEG_LINE || tag[i] == SEG_CLOSED) {
-        b.n = f.n;
-    } else {
-        ok = offset_segment(tag[i], d, -dist, b) && ok;
-    }
-    if (!ok)
+    Sink q = {nullptr, 0, 0, {}};
+    // a degenerate line contributes to neither side (svgrasterize.py:1121-1125): the backward side of a line
+    // counts what the forward side counts
+    const bool line = tag[i] == SEG_LINE || tag[i] == SEG_CLOSED;
+    const bool ok = offset_segment(tag[i], d, (side == 0 || line) ? dist : -dist, q);
+    if (!ok && (side == 0 || !line))
         atomicOr(err, 1);
-    counts[i] = f.n;
-    counts[n_seg + i] = b.n;
+    counts[side * n_seg + i] = q.n;
 }
 
 __global__ void stroke_emit_kernel(const uint8_t *__restrict__ tag, const double *__restrict__ data,
                                    const int *__restrict__ seg_job, const StrokeRec *__restrict__ jobs, int n_seg,
                                    const int *__restrict__ offs, DCurve *__restrict__ pool, int pool_cap)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = t >> 1, side = t & 1;
     if (i >= n_seg)
         return;
     double dist = jobs[seg_job[i]].half_width;
     double d[8];
     for (int k = 0; k < 8; k++)
         d[k] = data[8 * (size_t)i + k];
-    int of = offs[i], ob = offs[n_seg + i];
-    Sink f = {pool + of, 0, max(0, pool_cap - of), {}}, b = {pool + ob, 0, max(0, pool_cap - ob), {}};
-    offset_segment(tag[i], d, dist, f);
-    if (tag[i] == SEG_LINE || tag[i] == SEG_CLOSED) {
+    const int o = offs[side * n_seg + i];
+    Sink q = {pool + o, 0, max(0, pool_cap - o), {}};
+    if (side == 0) {
+        offset_segment(tag[i], d, dist, q);
+    } else if (tag[i] == SEG_LINE || tag[i] == SEG_CLOSED) {
         double off[4];
         if (line_offset(d, -dist, off))
-            b.push(mk_line(off, off + 2));
+            q.push(mk_line(off, off + 2));
     } else {
-        offset_segment(tag[i], d, -dist, b);
+        offset_segment(tag[i], d, -dist, q);
     }
 }
 
@@ -640,14 +641,14 @@ void svgr_launch_stroke_count(const uint8_t *tag, const double *data, const int 
                               int n_seg, int *counts, int *err, cudaStream_t s)
 {
     if (n_seg > 0)
-        stroke_count_kernel<<<(n_seg + 63) / 64, 64, 0, s>>>(tag, data, seg_job, jobs, n_seg, counts, err);
+        stroke_count_kernel<<<(2 * n_seg + 63) / 64, 64, 0, s>>>(tag, data, seg_job, jobs, n_seg, counts, err);
 }
 
 void svgr_launch_stroke_emit(const uint8_t *tag, const double *data, const int *seg_job, const StrokeRec *jobs,
                              int n_seg, const int *offs, void *pool, int pool_cap, cudaStream_t s)
 {
     if (n_seg > 0)
-        stroke_emit_kernel<<<(n_seg + 63) / 64, 64, 0, s>>>(tag, data, seg_job, jobs, n_seg, offs, (DCurve *)pool,
+        stroke_emit_kernel<<<(2 * n_seg + 63) / 64, 64, 0, s>>>(tag, data, seg_job, jobs, n_seg, offs, (DCurve *)pool,
                                                             pool_cap);
 }
 
