@@ -585,7 +585,8 @@ def install(module):
         Layer (:61-232) and the module functions canvas_* / pooling (:235-468), bezier3_flatten_batch (:2091),
         line_signed_coverage (:2213), grad_pixels / grad_spread / grad_interpolate (:1653-1683), blur_kernel (:1903).
 
-    Everything else (Transform, paints, the SVG parser, fonts) stays the module's own.  Returns a token for
+    Path.from_svg (:1252) is rebound to the native path-data reader, which the module's parser and fonts then use for
+    every `d` attribute and glyph.  Everything else (Transform, paints, the SVG parser, fonts) stays the module's own.  Returns a token for
     uninstall()."""
     import functools
 
@@ -600,6 +601,13 @@ def install(module):
     bind(module.Path, "stroke", path_stroke)
     if isinstance(module.Path, type) and issubclass(module.Path, S.Path):
         bind(module.Path, "from_svg", staticmethod(path_from_svg))  # array-backed paths need this package's Path
+    elif callable(getattr(module.Path, "from_svg", None)):
+        # the module's own Path class: the native reader tokenises (svgrasterize.py:1252-1430, bit-identical
+        # segments), the sub-path lists the class expects are built from its arrays
+        def from_svg(input, _Path=module.Path):
+            return _Path(path_from_svg(input).subpaths)
+
+        bind(module.Path, "from_svg", staticmethod(from_svg))
     bind(module.Scene, "render", scene_render)
     bind(module.Filter, "__call__", filter_call)
     bind(module, "Layer", Layer)

@@ -282,6 +282,27 @@ def test_install_on_the_reference_module_itself():
     token = B.install(ref)
     try:
         assert ref.Scene.render is api.scene_render and ref.Layer is api.Layer
+        # Path.from_svg now runs the native path-data reader and hands back the module's own Path class with the
+        # same sub-path lists, bit for bit, on every `d` attribute of the demo files
+        import re
+
+        original_from_svg = token[(ref.Path, "from_svg")].__func__
+        n_checked = 0
+        for name in ("icons.svg", "prompt.svg"):
+            for d in re.findall(r'\sd="([^"]+)"', open("/root/reference/demo/" + name).read())[:400]:
+                a, b = original_from_svg(d), ref.Path.from_svg(d)
+                assert type(b) is ref.Path and len(a.subpaths) == len(b.subpaths)
+                for sa, sb in zip(a.subpaths, b.subpaths):
+                    assert [t for t, _ in sa] == [t for t, _ in sb]
+                    for (tag, pa), (_t, pb) in zip(sa, sb):
+                        if tag == ref.PATH_ARC:
+                            fa = np.concatenate([np.asarray(pa[0], float).ravel(), np.asarray(pa[1:], float)])
+                            fb = np.concatenate([np.asarray(pb[0], float).ravel(), np.asarray(pb[1:], float)])
+                        else:
+                            fa, fb = np.asarray(pa, float).ravel(), np.asarray(pb, float).ravel()
+                        assert fa.tobytes() == fb.tobytes()
+                n_checked += 1
+        assert n_checked > 300
         scene, _ids, size = ref.svg_scene_from_filepath("/root/reference/demo/material-design.svg", width=256)
         enc = encode.Encoder(None)
         enc.add_scene(scene, size, False)
